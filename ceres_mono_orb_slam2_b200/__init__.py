@@ -1,0 +1,10 @@
+"""B200-native ORB front-end and bundle-adjustment engine behind the class signatures of
+b51/ceres_mono_orb_slam2 (ORBextractor, ORBmatcher, CeresOptimizer).  See DESIGN.md.
+
+All compute lives in libcmos_b200.so (hand-written sm_100a CUDA behind the C ABI in include/cmos_b200.h).
+Nothing in this package falls back to the CPU.
+"""
+from ._lib import KP_DTYPE, CmosError, LIB_PATH  # noqa: F401
+from .orb_extractor import ORBextractor  # noqa: F401
+
+__all__ = ["ORBextractor", "KP_DTYPE", "CmosError", "LIB_PATH"]

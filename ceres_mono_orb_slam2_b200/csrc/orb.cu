@@ -1,0 +1,1146 @@
+// ORB front-end for sm_100a: pyramid -> per-cell FAST-9 + NMS -> quadtree distribution ->
+// intensity-centroid angle -> 7x7 Gaussian -> steered BRIEF-256, batched over frames.
+//
+// Behaviour follows the reference's ORBextractor (src/ORBextractor.cc:410-470,765-853,1043-1132) and the
+// OpenCV 4.13 fixed-point primitives it calls; the architecture does not: every
+// stage is one batched launch over (work item, frame), the FAST threshold fallback and the quadtree run
+// on the device, and nothing returns to the host between stages.
+//
+// Compiled with --fmad=false: the descriptor rotation and fastAtan2 must round exactly like the unfused
+// float32 CPU arithmetic (SURVEY.md §7 hard part 2).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/cmos_orb_pattern.h"
+#include "cmos_common.h"
+#include "orb_device.cuh"
+
+namespace cmos {
+
+// =================================================================================================
+// Kernels
+// =================================================================================================
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  // valid for -n < i < 2n-1 (border 19 <= level size is enforced on the host)
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// Level 0: input image -> bordered plane (cv::copyMakeBorder REFLECT_101, ORBextractor.cc:1127).
+// One thread writes one aligned 4-byte word of the plane.
+__global__ void __launch_bounds__(256) k_level0(OrbGeom g, const uint8_t* __restrict__ images,
+                                                long long frame_stride, int in_pitch,
+                                                uint8_t* __restrict__ pyr) {
+  const LevelGeom& L = g.lv[0];
+  int c4 = blockIdx.x * blockDim.x + threadIdx.x;
+  int row = blockIdx.y * blockDim.y + threadIdx.y;
+  int f = blockIdx.z;
+  if (c4 * 4 >= L.pitch || row >= L.rows) return;
+  const uint8_t* src = images + (long long)f * frame_stride;
+  int sy = reflect101(row - kBorder, L.h);
+  uint32_t word = 0;
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    int bx = c4 * 4 + b - kXOff;
+    if (bx >= -kBorder && bx < L.w + kBorder) {
+      int sx = reflect101(bx, L.w);
+      word |= (uint32_t)__ldg(src + (long long)sy * in_pitch + sx) << (8 * b);
+    }
+  }
+  *(uint32_t*)(pyr + (long long)f * g.frame_bytes + L.plane_off + (long long)row * L.pitch + c4 * 4) = word;
+}
+
+// Level l from level l-1: cv::resize INTER_LINEAR fixed-point (Appendix A.1) fused with the
+// reflect-101 border (ORBextractor.cc:1120-1123).  tab entries: {src offset, coeff0, coeff1, 0}.
+__global__ void __launch_bounds__(256) k_resize(OrbGeom g, int level, const short4* __restrict__ xtab,
+                                                const short4* __restrict__ ytab, uint8_t* __restrict__ pyr) {
+  const LevelGeom& L = g.lv[level];
+  const LevelGeom& S = g.lv[level - 1];
+  int c4 = blockIdx.x * blockDim.x + threadIdx.x;
+  int row = blockIdx.y * blockDim.y + threadIdx.y;
+  int f = blockIdx.z;
+  if (c4 * 4 >= L.pitch || row >= L.rows) return;
+  uint8_t* frame = pyr + (long long)f * g.frame_bytes;
+  const uint8_t* src = frame + S.plane_off + (long long)kBorder * S.pitch + kXOff;
+  int dy = reflect101(row - kBorder, L.h);
+  short4 ty = __ldg(ytab + dy);
+  int sy0 = min(max((int)ty.x, 0), S.h - 1), sy1 = min(max((int)ty.x + 1, 0), S.h - 1);
+  const uint8_t* r0 = src + (long long)sy0 * S.pitch;
+  const uint8_t* r1 = src + (long long)sy1 * S.pitch;
+  int b0 = ty.y, b1 = ty.z;
+  uint32_t word = 0;
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    int bx = c4 * 4 + b - kXOff;
+    if (bx >= -kBorder && bx < L.w + kBorder) {
+      int dx = reflect101(bx, L.w);
+      short4 tx = __ldg(xtab + dx);
+      int sx0 = tx.x, sx1 = min(sx0 + 1, S.w - 1);
+      int t0 = r0[sx0] * (int)tx.y + r0[sx1] * (int)tx.z;
+      int t1 = r1[sx0] * (int)tx.y + r1[sx1] * (int)tx.z;
+      int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+      v = min(max(v, 0), 255);
+      word |= (uint32_t)v << (8 * b);
+    }
+  }
+  *(uint32_t*)(frame + L.plane_off + (long long)row * L.pitch + c4 * 4) = word;
+}
+
+// -------------------------------------------------------------------------------------------------
+// FAST-9/16 arc score: max over the 16 arcs of 9 contiguous ring pixels of min(ring - c) and of
+// min(c - ring) (cv::FAST's cornerScore, Appendix A.3).  Returns 0 when the pixel cannot be a corner
+// above `tmin` (cheap compass rejection), else the exact value.
+__device__ __forceinline__ int fast_arc_max(const uint8_t* __restrict__ p, int tw, int tmin) {
+  const int c = p[0];
+  int d[16];
+  d[0] = (int)p[3 * tw] - c;
+  d[4] = (int)p[3] - c;
+  d[8] = (int)p[-3 * tw] - c;
+  d[12] = (int)p[-3] - c;
+  // a 9-arc contains at least one pixel of every opposing pair
+  const bool bright = (d[0] > tmin || d[8] > tmin) && (d[4] > tmin || d[12] > tmin);
+  const bool dark = (d[0] < -tmin || d[8] < -tmin) && (d[4] < -tmin || d[12] < -tmin);
+  if (!bright && !dark) return 0;
+  d[1] = (int)p[3 * tw + 1] - c;
+  d[2] = (int)p[2 * tw + 2] - c;
+  d[3] = (int)p[tw + 3] - c;
+  d[5] = (int)p[-tw + 3] - c;
+  d[6] = (int)p[-2 * tw + 2] - c;
+  d[7] = (int)p[-3 * tw + 1] - c;
+  d[9] = (int)p[-3 * tw - 1] - c;
+  d[10] = (int)p[-2 * tw - 2] - c;
+  d[11] = (int)p[-tw - 3] - c;
+  d[13] = (int)p[tw - 3] - c;
+  d[14] = (int)p[2 * tw - 2] - c;
+  d[15] = (int)p[3 * tw - 1] - c;
+  int lo2[16], hi2[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    lo2[k] = min(d[k], d[(k + 1) & 15]);
+    hi2[k] = max(d[k], d[(k + 1) & 15]);
+  }
+  int lo4[16], hi4[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    lo4[k] = min(lo2[k], lo2[(k + 2) & 15]);
+    hi4[k] = max(hi2[k], hi2[(k + 2) & 15]);
+  }
+  int best = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
+    int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
+    best = max(best, max(lo9, -hi9));
+  }
+  return best;
+}
+
+// One CTA per (cell, frame): stage the (w_cell+6) x (h_cell+6) tile in shared memory, score the
+// detection area, 3x3 strict NMS with zero outside the cell, threshold fallback ini -> min decided per
+// cell after NMS (ORBextractor.cc:789-829), append survivors to the (frame, level) candidate list.
+__global__ void __launch_bounds__(kFastThreads) k_fast(OrbGeom g, const int4* __restrict__ cells,
+                                                      const uint8_t* __restrict__ pyr,
+                                                      uint32_t* __restrict__ cand,
+                                                      int* __restrict__ cand_count, int* __restrict__ overflow) {
+  __shared__ __align__(16) uint8_t tile[kTileH * kTileW];
+  __shared__ __align__(16) uint8_t score[kTileH * kTileW];
+  __shared__ uint32_t s_list[kCellListCap];
+  __shared__ int s_n, s_base;
+
+  const int4 ce = __ldg(cells + blockIdx.x);
+  const int level = ce.x & 0xff, ci = (ce.x >> 8) & 0xfff, cj = (ce.x >> 20) & 0xfff;
+  const int x0 = ce.y & 0xffff, y0 = ce.y >> 16, cw = ce.z & 0xffff, ch = ce.z >> 16;
+  const LevelGeom& L = g.lv[level];
+  const int f = blockIdx.y, tid = threadIdx.x;
+  const uint8_t* plane = pyr + (long long)f * g.frame_bytes + L.plane_off;
+  const long long org = (long long)(y0 + kBorder) * L.pitch + kXOff + x0;
+  const int shift = (int)(org & 3);
+  const int words = (shift + cw + 3) >> 2;
+
+  for (int i = tid; i < ch * words; i += kFastThreads) {
+    int r = i / words, w = i - r * words;
+    uint32_t v = __ldg((const uint32_t*)(plane + org - shift + (long long)r * L.pitch) + w);
+    *(uint32_t*)(tile + r * kTileW + 4 * w) = v;
+  }
+  for (int i = tid; i < (kTileH * kTileW) / 4; i += kFastThreads) ((uint32_t*)score)[i] = 0;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+
+  const int dw = cw - 6, dh = ch - 6;   // detection area
+  const int npx = dw > 0 && dh > 0 ? dw * dh : 0;
+  for (int i = tid; i < npx; i += kFastThreads) {
+    int y = i / dw, x = i - y * dw;
+    int m = fast_arc_max(tile + (y + 3) * kTileW + shift + x + 3, kTileW, g.min_th);
+    score[(y + 3) * kTileW + x + 3] = (uint8_t)(m > g.min_th ? m : 0);
+  }
+  __syncthreads();
+
+  int th = g.ini_th;
+  for (int pass = 0; pass < 2; pass++) {
+    int kept = 0;
+    for (int i = tid; i < npx; i += kFastThreads) {
+      int y = i / dw, x = i - y * dw;
+      const uint8_t* s = score + (y + 3) * kTileW + x + 3;
+      int m = s[0];
+      if (m <= th) continue;
+      bool keep = true;
+#pragma unroll
+      for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+          if (dx == 0 && dy == 0) continue;
+          int n = s[dy * kTileW + dx];
+          keep = keep && (n <= th || n < m);
+        }
+      if (keep) {
+        int slot = atomicAdd(&s_n, 1);
+        // reference coordinates: cell-local + (j*wCell, i*hCell), relative to minBorder (:820-825)
+        if (slot < kCellListCap)
+          s_list[slot] = (uint32_t)(x + 3 + cj * L.w_cell) | ((uint32_t)(y + 3 + ci * L.h_cell) << 12) |
+                         ((uint32_t)(m - 1) << 24);
+        kept++;
+      }
+    }
+    if (__syncthreads_count(kept) > 0 || th == g.min_th) break;
+    th = g.min_th;
+  }
+  const int n = s_n;
+  if (n == 0) return;
+  if (tid == 0) s_base = atomicAdd(cand_count + f * kMaxLevels + level, n);
+  __syncthreads();
+  const int base = s_base;
+  uint32_t* out = cand + (long long)f * g.cand_frame + L.cand_off;
+  if (n > kCellListCap || base + n > L.cand_cap) {
+    if (tid == 0) atomicExch(overflow, 1);
+    return;
+  }
+  for (int i = tid; i < n; i += kFastThreads) out[base + i] = s_list[i];
+}
+
+// -------------------------------------------------------------------------------------------------
+// Quadtree distribution (DistributeOctTree / DivideNode, ORBextractor.cc:481-763), one CTA per
+// (level, frame).  The std::list is emulated by position: every round rebuilds the node array in list
+// order (new children reversed at the front, survivors behind), and every candidate carries the list
+// position of its node.  Rounds: split all multi-point nodes in list order ("full"), or, once
+// size + 3*expandable > N, in (size desc, newest first) order stopping at N ("careful", :673-738).
+struct OctNode { short x0, x1, y0, y1; };
+
+__device__ __forceinline__ int oct_quadrant(const OctNode& nd, int x, int y) {
+  int mx = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1);   // ceil(float(w)/2), :483-484
+  int my = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
+  return (x < mx ? 0 : 1) + (y < my ? 0 : 2);
+}
+
+// exclusive scan of v[0..n) in shared memory, in place; returns the total. All threads must call.
+__device__ int block_exscan(int* v, int n, int* warp_tmp) {
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int per = (n + T - 1) / T;
+  const int lo = min(tid * per, n), hi = min(lo + per, n);
+  int sum = 0;
+  for (int i = lo; i < hi; i++) sum += v[i];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += t;
+  }
+  if ((tid & 31) == 31) warp_tmp[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int nw = T >> 5;
+    int w = tid < nw ? warp_tmp[tid] : 0;
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (tid >= o) wi += t;
+    }
+    warp_tmp[tid] = wi - w;            // exclusive warp offsets
+    if (tid == 31) warp_tmp[32] = wi;  // total (nw <= 32)
+  }
+  __syncthreads();
+  int run = warp_tmp[tid >> 5] + incl - sum;
+  const int total = warp_tmp[32];
+  for (int i = lo; i < hi; i++) {
+    int t = v[i];
+    v[i] = run;
+    run += t;
+  }
+  __syncthreads();
+  return total;
+}
+
+__global__ void __launch_bounds__(kOctThreads) k_octree(OrbGeom g, const uint32_t* __restrict__ cand,
+                                                       uint16_t* __restrict__ pnode,
+                                                       const int* __restrict__ cand_count,
+                                                       uint32_t* __restrict__ stage,
+                                                       int* __restrict__ level_counts, int maxn) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // carve
+  OctNode* nodeA = (OctNode*)smem_raw;
+  OctNode* nodeB = nodeA + maxn;
+  int* cntA = (int*)(nodeB + maxn);
+  int* cntB = cntA + maxn;
+  int* child = cntB + maxn;          // [maxn][4]
+  int* rank = child + 4 * maxn;      // processing rank of a todo node, -1 otherwise
+  int* proc = rank + maxn;           // node position at processing rank r
+  int* scanA = proc + maxn;          // scratch scans
+  int* scanB = scanA + maxn;
+  unsigned long long* best = (unsigned long long*)(scanB + maxn);   // [maxn]
+  __shared__ int warp_tmp[33];
+  __shared__ int s_k, s_kp, s_nexp;
+
+  const int level = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, T = kOctThreads;
+  const LevelGeom& L = g.lv[level];
+  const int N = L.quota;
+  const int np = min(cand_count[f * kMaxLevels + level], L.cand_cap);
+  const uint32_t* pts = cand + (long long)f * g.cand_frame + L.cand_off;
+  uint16_t* pn = pnode + (long long)f * g.cand_frame + L.cand_off;
+  int* out_count = level_counts + f * kMaxLevels + level;
+  if (np == 0 || L.n_ini < 1) {
+    if (tid == 0) *out_count = 0;
+    return;
+  }
+
+  // ---- roots (:543-570): nIni nodes of width hX; point -> root by float division ----
+  const int n_ini = L.n_ini;
+  for (int i = tid; i < n_ini; i += T) {
+    OctNode nd;
+    nd.x0 = (short)(int)(L.hx * (float)i);
+    nd.x1 = (short)(int)(L.hx * (float)(i + 1));
+    nd.y0 = 0;
+    nd.y1 = (short)L.oh;
+    nodeA[i] = nd;
+    cntA[i] = 0;
+  }
+  __syncthreads();
+  for (int p = tid; p < np; p += T) {
+    int x = pts[p] & 0xfff;
+    int r = (int)((float)x / L.hx);
+    r = min(r, n_ini - 1);
+    pn[p] = (uint16_t)r;
+    atomicAdd(&cntA[r], 1);
+  }
+  __syncthreads();
+  // drop empty roots (:574-585), keep order
+  for (int i = tid; i < n_ini; i += T) scanA[i] = cntA[i] > 0;
+  __syncthreads();
+  int n = block_exscan(scanA, n_ini, warp_tmp);
+  if (n != n_ini) {
+    for (int i = tid; i < n_ini; i += T)
+      if (cntA[i] > 0) { nodeB[scanA[i]] = nodeA[i]; cntB[scanA[i]] = cntA[i]; }
+    for (int p = tid; p < np; p += T) pn[p] = (uint16_t)scanA[pn[p]];
+    __syncthreads();
+    OctNode* tn = nodeA; nodeA = nodeB; nodeB = tn;
+    int* tc = cntA; cntA = cntB; cntB = tc;
+  }
+  __syncthreads();
+
+  bool careful = false;
+  for (;;) {
+    // ---- todo set = nodes with more than one point ----
+    for (int i = tid; i < n; i += T) { scanA[i] = cntA[i] > 1; rank[i] = -1; }
+    __syncthreads();
+    if (!careful) {
+      // processing order = list order
+      for (int i = tid; i < n; i += T) scanB[i] = scanA[i];
+      __syncthreads();
+      int k = block_exscan(scanB, n, warp_tmp);
+      for (int i = tid; i < n; i += T)
+        if (scanA[i]) { rank[i] = scanB[i]; proc[scanB[i]] = i; }
+      if (tid == 0) s_k = k;
+    } else {
+      // processing order = (size desc, newest first == position asc): rank by counting
+      for (int i = tid; i < n; i += T) scanB[i] = scanA[i];
+      __syncthreads();
+      int k = block_exscan(scanB, n, warp_tmp);   // compact todo list into proc[] first
+      for (int i = tid; i < n; i += T)
+        if (scanA[i]) proc[scanB[i]] = i;
+      __syncthreads();
+      for (int i = tid; i < k; i += T) scanB[i] = proc[i];   // unsorted todo positions
+      __syncthreads();
+      for (int i = tid; i < k; i += T) {
+        int a = scanB[i], ca = cntA[a], r = 0;
+        for (int j = 0; j < k; j++) {
+          int b = scanB[j], cb = cntA[b];
+          r += (cb > ca) || (cb == ca && b < a);
+        }
+        rank[a] = r;
+      }
+      __syncthreads();
+      for (int i = tid; i < k; i += T) proc[rank[scanB[i]]] = scanB[i];
+      if (tid == 0) s_k = k;
+    }
+    __syncthreads();
+    const int k = s_k;
+    if (k == 0) break;   // nothing left to split: list size cannot change (:669)
+
+    // ---- child sizes of every todo node ----
+    for (int i = tid; i < 4 * n; i += T) child[i] = 0;
+    __syncthreads();
+    for (int p = tid; p < np; p += T) {
+      int a = pn[p];
+      if (rank[a] >= 0) {
+        uint32_t v = pts[p];
+        atomicAdd(&child[4 * a + oct_quadrant(nodeA[a], v & 0xfff, (v >> 12) & 0xfff)], 1);
+      }
+    }
+    __syncthreads();
+    // gain per processing rank, inclusive running size
+    for (int r = tid; r < k; r += T) {
+      int a = proc[r];
+      int nch = (child[4 * a] > 0) + (child[4 * a + 1] > 0) + (child[4 * a + 2] > 0) + (child[4 * a + 3] > 0);
+      scanA[r] = nch;          // children created by rank r
+      scanB[r] = nch - 1;      // list growth
+    }
+    __syncthreads();
+    block_exscan(scanB, k, warp_tmp);   // scanB[r] = growth before rank r
+    if (tid == 0) s_kp = k;
+    __syncthreads();
+    if (careful) {
+      // first rank after which size >= N (:731-732): size_after(r) = n + scanB[r] + (nch_r - 1)
+      for (int r = tid; r < k; r += T)
+        if (n + scanB[r] + scanA[r] - 1 >= N) atomicMin(&s_kp, r + 1);
+      __syncthreads();
+    }
+    const int kp = s_kp;   // ranks [0,kp) are split this round
+    for (int r = tid; r < k; r += T)
+      if (r >= kp) { rank[proc[r]] = -1; scanA[r] = 0; }
+    __syncthreads();
+    const int C = block_exscan(scanA, k, warp_tmp);   // scanA[r] = creation index of rank r's first child
+    // survivors keep their relative order behind the C new children
+    int* keep = scanB;
+    for (int i = tid; i < n; i += T) keep[i] = rank[i] < 0;
+    __syncthreads();
+    block_exscan(keep, n, warp_tmp);
+    const int n_new = C + n - kp;
+    if (tid == 0) s_nexp = 0;
+    __syncthreads();
+    // ---- build the new list ----
+    for (int i = tid; i < n; i += T) {
+      const OctNode nd = nodeA[i];
+      if (rank[i] < 0) {
+        nodeB[C + keep[i]] = nd;
+        cntB[C + keep[i]] = cntA[i];
+      } else {
+        int mx = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), my = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
+        int cidx = scanA[rank[i]], nexp = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          int c = child[4 * i + q];
+          if (c == 0) continue;
+          OctNode ch;
+          ch.x0 = (q & 1) ? (short)mx : nd.x0;
+          ch.x1 = (q & 1) ? nd.x1 : (short)mx;
+          ch.y0 = (q & 2) ? (short)my : nd.y0;
+          ch.y1 = (q & 2) ? nd.y1 : (short)my;
+          int pos = C - 1 - cidx;   // push_front: later children sit nearer the front
+          nodeB[pos] = ch;
+          cntB[pos] = c;
+          child[4 * i + q] = -(pos + 1);   // remember where the child went (negative marks "position")
+          nexp += c > 1;
+          cidx++;
+        }
+        if (nexp) atomicAdd(&s_nexp, nexp);
+      }
+    }
+    __syncthreads();
+    for (int p = tid; p < np; p += T) {
+      int a = pn[p];
+      if (rank[a] < 0) {
+        pn[p] = (uint16_t)(C + keep[a]);
+      } else {
+        uint32_t v = pts[p];
+        int q = oct_quadrant(nodeA[a], v & 0xfff, (v >> 12) & 0xfff);
+        pn[p] = (uint16_t)(-child[4 * a + q] - 1);
+      }
+    }
+    __syncthreads();
+    { OctNode* tn = nodeA; nodeA = nodeB; nodeB = tn; int* tc = cntA; cntA = cntB; cntB = tc; }
+    const int n_prev = n;
+    n = n_new;
+    const int nexp = s_nexp;
+    __syncthreads();
+    if (n >= N || n == n_prev) break;                       // :669-672, :734-735
+    if (!careful && n + 3 * nexp > N) careful = true;       // :673
+  }
+
+  // ---- best response per node, first candidate in reference order wins ties (:744-760) ----
+  for (int i = tid; i < n; i += T) best[i] = 0ull;
+  __syncthreads();
+  for (int p = tid; p < np; p += T) {
+    uint32_t v = pts[p];
+    int x = v & 0xfff, y = (v >> 12) & 0xfff;
+    // vToDistributeKeys order: cell row-major, then row-major inside the cell's detection area
+    int cj = (x - 3) / L.w_cell, ci = (y - 3) / L.h_cell;
+    uint32_t order = (uint32_t)(((ci * L.n_cols + cj) * 128 + (y - ci * L.h_cell)) * 128 + (x - cj * L.w_cell));
+    unsigned long long key = ((unsigned long long)(v >> 24) << 32) | (0xffffffffu - order);
+    atomicMax(&best[pn[p]], key);
+  }
+  __syncthreads();
+  uint32_t* out = stage + (long long)f * g.kp_cap + L.kp_off;
+  for (int i = tid; i < n; i += T) {
+    unsigned long long key = best[i];
+    uint32_t order = 0xffffffffu - (uint32_t)key;
+    int xl = order & 127, yl = (order >> 7) & 127, cell = order >> 14;
+    int ci = cell / L.n_cols, cj = cell - ci * L.n_cols;
+    uint32_t x = xl + cj * L.w_cell, y = yl + ci * L.h_cell;
+    out[i] = x | (y << 12) | ((uint32_t)(key >> 32) << 24);
+  }
+  if (tid == 0) *out_count = n;
+}
+
+// -------------------------------------------------------------------------------------------------
+// cv::GaussianBlur 7x7 sigma 2 (Appendix A.2) of every level's interior; reads the reflect-101 border
+// that the pyramid planes already carry (equivalent to blurring the un-bordered clone, :1085-1086).
+__global__ void __launch_bounds__(256) k_blur(OrbGeom g, const int2* __restrict__ tiles,
+                                              const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
+  __shared__ __align__(16) uint8_t in[(kBlurTH + 6) * kBlurInPitch];
+  __shared__ __align__(16) uint16_t hs[(kBlurTH + 6) * kBlurTW];
+  const int2 te = __ldg(tiles + blockIdx.x);
+  const int level = te.x & 0xff, x0 = (te.x >> 8) * kBlurTW, y0 = te.y * kBlurTH;
+  const LevelGeom& L = g.lv[level];
+  const int f = blockIdx.y, tid = threadIdx.x;
+  const uint8_t* plane = pyr + (long long)f * g.frame_bytes + L.plane_off;
+  // input rows y0-3 .. y0+TH+2, columns x0-4 .. x0+TW+3 (word aligned: kXOff + x0 - 4 is a multiple of 4)
+  const int in_words = kBlurInPitch / 4;
+  for (int i = tid; i < (kBlurTH + 6) * in_words; i += 256) {
+    int r = i / in_words, w = i - r * in_words;
+    int row = y0 - 3 + r + kBorder, col = kXOff + x0 - 4 + 4 * w;
+    uint32_t v = 0;
+    if (row < L.rows && col + 3 < L.pitch) v = __ldg((const uint32_t*)(plane + (long long)row * L.pitch + col));
+    *(uint32_t*)(in + r * kBlurInPitch + 4 * w) = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < (kBlurTH + 6) * kBlurTW; i += 256) {
+    int r = i / kBlurTW, x = i - r * kBlurTW;
+    const uint8_t* s = in + r * kBlurInPitch + x + 1;   // s[0] is pixel x-3
+    hs[i] = (uint16_t)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
+  }
+  __syncthreads();
+  uint8_t* dst = blur + (long long)f * g.frame_bytes + L.plane_off;
+  for (int i = tid; i < kBlurTH * (kBlurTW / 4); i += 256) {
+    int r = i / (kBlurTW / 4), x4 = (i - r * (kBlurTW / 4)) * 4;
+    int y = y0 + r, x = x0 + x4;
+    if (y >= L.h || x >= L.w) continue;
+    uint32_t word = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const uint16_t* h = hs + r * kBlurTW + x4 + b;
+      uint32_t acc = 18u * (h[0] + h[6 * kBlurTW]) + 34u * (h[kBlurTW] + h[5 * kBlurTW]) +
+                     48u * (h[2 * kBlurTW] + h[4 * kBlurTW]) + 56u * h[3 * kBlurTW];
+      word |= ((acc + 32768u) >> 16) << (8 * b);
+    }
+    // bytes past the interior width land in the border columns of the blurred plane, which nothing reads
+    *(uint32_t*)(dst + (long long)(y + kBorder) * L.pitch + kXOff + x) = word;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// IC_Angle (:77-104) + computeOrbDescriptor (:108-147), one warp per output keypoint; also writes the
+// cv::KeyPoint record with pt scaled to level-0 coordinates (:1095-1101).
+__global__ void __launch_bounds__(kDescThreads) k_describe(OrbGeom g, const uint32_t* __restrict__ stage,
+                                                          const int* __restrict__ level_counts,
+                                                          const uint8_t* __restrict__ pyr,
+                                                          const uint8_t* __restrict__ blur,
+                                                          const int8_t* __restrict__ pattern,
+                                                          cmos_keypoint* __restrict__ kps,
+                                                          uint8_t* __restrict__ desc, int* __restrict__ counts) {
+  const int f = blockIdx.y, lane = threadIdx.x & 31;
+  const int slot = blockIdx.x * (kDescThreads / 32) + (threadIdx.x >> 5);
+  int level = -1, idx = 0, total = 0;
+  for (int l = 0; l < g.nlevels; l++) {
+    int c = level_counts[f * kMaxLevels + l];
+    if (level < 0 && slot < total + c) { level = l; idx = slot - total; }
+    total += c;
+  }
+  if (slot == 0 && lane == 0) counts[f] = total;
+  if (level < 0) return;
+  const LevelGeom& L = g.lv[level];
+  const uint32_t v = stage[(long long)f * g.kp_cap + L.kp_off + idx];
+  const int x = (int)(v & 0xfff) + kMinBorder, y = (int)((v >> 12) & 0xfff) + kMinBorder;   // level coords
+  const long long plane = (long long)f * g.frame_bytes + L.plane_off;
+  const uint8_t* c = pyr + plane + (long long)(y + kBorder) * L.pitch + kXOff + x;
+
+  // intensity centroid over the 31-px disc: lane = column u+15
+  int m10 = 0, m01 = 0;
+  const int u = lane - 15;
+  if (lane < 31) {
+    const int au = u < 0 ? -u : u;
+#pragma unroll
+    for (int vv = -15; vv <= 15; vv++) {
+      const int av = vv < 0 ? -vv : vv;
+      if (au <= g.umax[av]) {
+        int I = c[vv * L.pitch + u];
+        m10 += u * I;
+        m01 += vv * I;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+  }
+  const float angle = dev_fast_atan2((float)m01, (float)m10);
+
+  // steered BRIEF: lane = descriptor byte
+  const float rad = angle * kFactorPi;
+  const float a = glibc_cosf(rad), b = glibc_sinf(rad);
+  const uint8_t* bc = blur + plane + (long long)(y + kBorder) * L.pitch + kXOff + x;
+  const int8_t* pat = pattern + lane * 32;
+  int byte = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1], x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
+    int t0 = bc[__float2int_rn(x0 * b + y0 * a) * L.pitch + __float2int_rn(x0 * a - y0 * b)];
+    int t1 = bc[__float2int_rn(x1 * b + y1 * a) * L.pitch + __float2int_rn(x1 * a - y1 * b)];
+    byte |= (t0 < t1) << k;
+  }
+  desc[((long long)f * g.kp_cap + slot) * 32 + lane] = (uint8_t)byte;
+  if (lane == 0) {
+    cmos_keypoint kp;
+    float fx = (float)x, fy = (float)y;
+    if (level != 0) { fx *= L.scale; fy *= L.scale; }
+    kp.x = fx; kp.y = fy; kp.size = (float)L.patch; kp.angle = angle; kp.response = (float)(v >> 24);
+    kp.octave = level; kp.class_id = -1;
+    kps[(long long)f * g.kp_cap + slot] = kp;
+  }
+}
+
+// Verification taps for the bit-exact float helpers (tests only).
+__global__ void k_debug_sincos(const float* __restrict__ deg, float* __restrict__ c, float* __restrict__ s, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float rad = deg[i] * kFactorPi;
+  c[i] = glibc_cosf(rad);
+  s[i] = glibc_sinf(rad);
+}
+__global__ void k_debug_atan2(const float* __restrict__ y, const float* __restrict__ x, float* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = dev_fast_atan2(y[i], x[i]);
+}
+
+// =================================================================================================
+// Host side
+// =================================================================================================
+
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+static inline int cv_round_d(double v) { return (int)lrint(v); }
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace cmos
+
+using namespace cmos;
+
+struct cmos_orb {
+  cmos_orb_params p{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<float> sf, inv_sf, sigma2, inv_sigma2;
+  std::vector<int> quota;
+  int umax[16];
+  int kp_cap = 0;
+  // geometry of the current (width, height); cap_* describe the allocation made for (max_w, max_h)
+  int cur_w = -1, cur_h = -1;
+  OrbGeom geom{};
+  int n_cells = 0, n_tiles = 0, oct_maxn = 0;
+  size_t cap_frame_bytes = 0, cap_cand_frame = 0, cap_cells = 0, cap_tiles = 0, cap_tab = 0;
+  // device buffers
+  uint8_t *d_images = nullptr, *d_pyr = nullptr, *d_blur = nullptr, *d_desc = nullptr;
+  uint32_t *d_cand = nullptr, *d_stage = nullptr;
+  uint16_t* d_pnode = nullptr;
+  int *d_cand_count = nullptr, *d_level_counts = nullptr, *d_counts = nullptr, *d_overflow = nullptr;
+  cmos_keypoint* d_kps = nullptr;
+  int4* d_cells = nullptr;
+  int2* d_tiles = nullptr;
+  short4* d_tab = nullptr;      // x tables then y tables of every level
+  int8_t* d_pattern = nullptr;
+  std::vector<int> xtab_off, ytab_off;
+  size_t images_cap = 0;
+  int last_frames = 0, launches = 0;
+  bool has_result = false;
+};
+
+namespace {
+
+// Geometry for one image size.  Mirrors ComputePyramid (:1107-1132) sizes and the cell grid of
+// ComputeKeyPointsOctTree (:765-806).  Also produces the host tables to upload.
+struct GeomBuild {
+  OrbGeom g{};
+  std::vector<int4> cells;
+  std::vector<int2> tiles;
+  std::vector<short4> tab;
+  std::vector<int> xoff, yoff;
+  int oct_maxn = 0;
+};
+
+bool build_geometry(const cmos_orb* h, int w, int ht, GeomBuild* out) {
+  const int nl = h->p.nlevels;
+  OrbGeom& g = out->g;
+  std::memset(&g, 0, sizeof(g));
+  g.nlevels = nl;
+  g.ini_th = h->p.ini_th_fast;
+  g.min_th = h->p.min_th_fast;
+  for (int i = 0; i < 16; i++) g.umax[i] = h->umax[i];
+  long long plane = 0, cand = 0;
+  int kp = 0, maxn = 8;
+  out->xoff.assign(nl, 0);
+  out->yoff.assign(nl, 0);
+  for (int l = 0; l < nl; l++) {
+    LevelGeom& L = g.lv[l];
+    float s = h->inv_sf[l];
+    L.w = cv_round_f((float)w * s);
+    L.h = cv_round_f((float)ht * s);
+    if (L.w <= kBorder || L.h <= kBorder || L.w > 4000 || L.h > 4000) {
+      set_error("level %d size %dx%d unsupported (need > %d and <= 4000 per side)", l, L.w, L.h, kBorder);
+      return false;
+    }
+    L.pitch = round_up(kXOff + L.w + kBorder, 128);
+    L.rows = L.h + 2 * kBorder;
+    L.plane_off = (int)plane;
+    plane += (long long)round_up(L.pitch * L.rows, 256);
+    L.scale = h->sf[l];
+    L.patch = (int)(31 * h->sf[l]);
+    L.quota = h->quota[l];
+    L.kp_off = kp;
+    kp += L.quota + 3;
+    const int min_b = kMinBorder, max_bx = L.w - kMinBorder, max_by = L.h - kMinBorder;
+    const float width = (float)(max_bx - min_b), height = (float)(max_by - min_b);
+    L.n_cols = (int)(width / 30.f);
+    L.n_rows = (int)(height / 30.f);
+    L.cand_off = (int)cand;
+    L.cand_cap = 0;
+    L.n_ini = 0;
+    if (L.n_cols >= 1 && L.n_rows >= 1) {
+      L.w_cell = (int)std::ceil(width / L.n_cols);
+      L.h_cell = (int)std::ceil(height / L.n_rows);
+      for (int i = 0; i < L.n_rows; i++) {
+        const float ini_y = (float)(min_b + i * L.h_cell);
+        float max_y = ini_y + L.h_cell + 6;
+        if (ini_y >= max_by - 3) continue;
+        if (max_y > max_by) max_y = (float)max_by;
+        for (int j = 0; j < L.n_cols; j++) {
+          const float ini_x = (float)(min_b + j * L.w_cell);
+          float max_x = ini_x + L.w_cell + 6;
+          if (ini_x >= max_bx - 6) continue;
+          if (max_x > max_bx) max_x = (float)max_bx;
+          int cw = (int)max_x - (int)ini_x, ch = (int)max_y - (int)ini_y;
+          if (cw > kTileW - 4 || ch > kTileH || i > 0xfff || j > 0xfff) {
+            set_error("FAST cell %dx%d exceeds the shared-memory tile", cw, ch);
+            return false;
+          }
+          out->cells.push_back(make_int4(l | (i << 8) | (j << 20), (int)ini_x | ((int)ini_y << 16), cw | (ch << 16), 0));
+        }
+      }
+      // strict 3x3 NMS keeps at most one pixel per 2x2 block of the detection area
+      L.cand_cap = ((max_bx - min_b) / 2 + 1) * ((max_by - min_b) / 2 + 1);
+      L.ow = max_bx - min_b;
+      L.oh = max_by - min_b;
+      L.n_ini = (int)std::round(static_cast<float>(L.ow) / L.oh);
+      if (L.n_ini >= 1) L.hx = static_cast<float>(L.ow) / L.n_ini;
+      maxn = std::max(maxn, std::max(L.quota + 3, 4 * std::max(L.n_ini, 1)));
+    }
+    cand += round_up(L.cand_cap, 64);
+    for (int ty = 0; ty * kBlurTH < L.h; ty++)
+      for (int tx = 0; tx * kBlurTW < L.w; tx++) out->tiles.push_back(make_int2(l | (tx << 8), ty));
+    // resize tables for level l (from l-1): Appendix A.1
+    if (l > 0) {
+      const LevelGeom& S = g.lv[l - 1];
+      out->xoff[l] = (int)out->tab.size();
+      const double scale_x = (double)S.w / L.w, scale_y = (double)S.h / L.h;
+      for (int dx = 0; dx < L.w; dx++) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = (int)std::floor(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
+        out->tab.push_back(make_short4((short)sx, (short)cv_round_f((1.f - fx) * 2048.f), (short)cv_round_f(fx * 2048.f), 0));
+      }
+      out->yoff[l] = (int)out->tab.size();
+      for (int dy = 0; dy < L.h; dy++) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = (int)std::floor(fy);
+        fy -= sy;
+        out->tab.push_back(make_short4((short)sy, (short)cv_round_f((1.f - fy) * 2048.f), (short)cv_round_f(fy * 2048.f), 0));
+      }
+    }
+  }
+  g.frame_bytes = plane;
+  g.cand_frame = cand;
+  g.kp_cap = kp;
+  out->oct_maxn = round_up(maxn, 32);
+  return true;
+}
+
+size_t oct_smem_bytes(int maxn) {
+  // nodeA,nodeB (8 B) + cntA,cntB + child[4] + rank + proc + scanA + scanB (4 B each) + best (8 B)
+  return (size_t)maxn * (2 * 8 + (2 + 4 + 4) * 4 + 8);
+}
+
+int ensure_geometry(cmos_orb* h, int w, int ht) {
+  if (h->cur_w == w && h->cur_h == ht) return CMOS_OK;
+  GeomBuild gb;
+  if (!build_geometry(h, w, ht, &gb)) return CMOS_ERR_ARG;
+  if ((size_t)gb.g.frame_bytes > h->cap_frame_bytes || (size_t)gb.g.cand_frame > h->cap_cand_frame ||
+      gb.cells.size() > h->cap_cells || gb.tiles.size() > h->cap_tiles || gb.tab.size() > h->cap_tab ||
+      oct_smem_bytes(gb.oct_maxn) > 200 * 1024) {
+    set_error("image %dx%d does not fit the buffers sized for max %dx%d", w, ht, h->p.max_width, h->p.max_height);
+    return CMOS_ERR_ARG;
+  }
+  CMOS_CUDA_OK(cudaMemcpyAsync(h->d_cells, gb.cells.data(), gb.cells.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+  CMOS_CUDA_OK(cudaMemcpyAsync(h->d_tiles, gb.tiles.data(), gb.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+  CMOS_CUDA_OK(cudaMemcpyAsync(h->d_tab, gb.tab.data(), gb.tab.size() * sizeof(short4), cudaMemcpyHostToDevice, h->stream));
+  CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));   // host vectors die with gb
+  h->geom = gb.g;
+  h->n_cells = (int)gb.cells.size();
+  h->n_tiles = (int)gb.tiles.size();
+  h->xtab_off = gb.xoff;
+  h->ytab_off = gb.yoff;
+  h->oct_maxn = gb.oct_maxn;
+  h->cur_w = w;
+  h->cur_h = ht;
+  return CMOS_OK;
+}
+
+int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride, int pitch, int n_frames,
+                    cudaStream_t st) {
+  const OrbGeom& g = h->geom;
+  int launches = 0;
+  CMOS_CUDA_OK(cudaMemsetAsync(h->d_cand_count, 0, (size_t)h->p.max_batch * kMaxLevels * sizeof(int), st));
+  CMOS_CUDA_OK(cudaMemsetAsync(h->d_overflow, 0, sizeof(int), st));
+  dim3 blk(64, 4);
+  {
+    const LevelGeom& L = g.lv[0];
+    dim3 grid((L.pitch / 4 + 63) / 64, (L.rows + 3) / 4, n_frames);
+    k_level0<<<grid, blk, 0, st>>>(g, d_images, frame_stride, pitch, h->d_pyr);
+    launches++;
+  }
+  for (int l = 1; l < g.nlevels; l++) {
+    const LevelGeom& L = g.lv[l];
+    dim3 grid((L.pitch / 4 + 63) / 64, (L.rows + 3) / 4, n_frames);
+    k_resize<<<grid, blk, 0, st>>>(g, l, h->d_tab + h->xtab_off[l], h->d_tab + h->ytab_off[l], h->d_pyr);
+    launches++;
+  }
+  if (h->n_cells > 0) {
+    k_fast<<<dim3(h->n_cells, n_frames), kFastThreads, 0, st>>>(g, h->d_cells, h->d_pyr, h->d_cand, h->d_cand_count,
+                                                              h->d_overflow);
+    launches++;
+  }
+  k_octree<<<dim3(g.nlevels, n_frames), kOctThreads, oct_smem_bytes(h->oct_maxn), st>>>(
+      g, h->d_cand, h->d_pnode, h->d_cand_count, h->d_stage, h->d_level_counts, h->oct_maxn);
+  launches++;
+  k_blur<<<dim3(h->n_tiles, n_frames), 256, 0, st>>>(g, h->d_tiles, h->d_pyr, h->d_blur);
+  launches++;
+  k_describe<<<dim3((g.kp_cap + kDescThreads / 32 - 1) / (kDescThreads / 32), n_frames), kDescThreads, 0, st>>>(
+      g, h->d_stage, h->d_level_counts, h->d_pyr, h->d_blur, h->d_pattern, h->d_kps, h->d_desc, h->d_counts);
+  launches++;
+  CMOS_CUDA_OK(cudaGetLastError());
+  h->launches = launches;
+  h->last_frames = n_frames;
+  h->has_result = true;
+  return CMOS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cmos_orb_create(const cmos_orb_params* params, cmos_orb_t* out) {
+  CMOS_REQUIRE(params && out, "null argument");
+  CMOS_REQUIRE(params->nlevels >= 1 && params->nlevels <= kMaxLevels, "nlevels must be in 1..%d", kMaxLevels);
+  CMOS_REQUIRE(params->nfeatures > 0 && params->scale_factor > 1.0f, "bad nfeatures/scale_factor");
+  CMOS_REQUIRE(params->max_width > 0 && params->max_height > 0 && params->max_batch > 0, "bad max sizes");
+  CMOS_REQUIRE(params->min_th_fast >= 1 && params->ini_th_fast >= params->min_th_fast && params->ini_th_fast < 255,
+               "FAST thresholds must satisfy 1 <= min <= ini < 255");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: this library has no CPU fallback");
+    return CMOS_ERR_CUDA;
+  }
+  CMOS_REQUIRE(params->device >= 0 && params->device < ndev, "device %d out of range", params->device);
+  CMOS_CUDA_OK(cudaSetDevice(params->device));
+  cmos_orb* h = new cmos_orb();
+  h->p = *params;
+  h->device = params->device;
+  // tables of the constructor, ORBextractor.cc:410-470 (scaleFactor member is double, ORBextractor.h:95)
+  const int nl = params->nlevels;
+  const double scale_d = (double)params->scale_factor;
+  h->sf.resize(nl); h->inv_sf.resize(nl); h->sigma2.resize(nl); h->inv_sigma2.resize(nl); h->quota.resize(nl);
+  h->sf[0] = 1.f; h->sigma2[0] = 1.f;
+  for (int i = 1; i < nl; i++) {
+    h->sf[i] = (float)(h->sf[i - 1] * scale_d);
+    h->sigma2[i] = h->sf[i] * h->sf[i];
+  }
+  for (int i = 0; i < nl; i++) { h->inv_sf[i] = 1.0f / h->sf[i]; h->inv_sigma2[i] = 1.0f / h->sigma2[i]; }
+  float factor = (float)(1.0f / scale_d);
+  float per = params->nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nl));
+  int sum = 0;
+  for (int l = 0; l < nl - 1; l++) {
+    h->quota[l] = cv_round_f(per);
+    sum += h->quota[l];
+    per *= factor;
+  }
+  h->quota[nl - 1] = std::max(params->nfeatures - sum, 0);
+  {
+    int vmax = (int)std::floor(15 * std::sqrt(2.f) / 2 + 1), vmin = (int)std::ceil(15 * std::sqrt(2.f) / 2);
+    for (int v = 0; v < 16; v++) h->umax[v] = 0;
+    for (int v = 0; v <= vmax; ++v) h->umax[v] = cv_round_d(std::sqrt(225.0 - v * v));
+    for (int v = 15, v0 = 0; v >= vmin; --v) {
+      while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
+      h->umax[v] = v0;
+      ++v0;
+    }
+  }
+  GeomBuild gb;
+  if (!build_geometry(h, params->max_width, params->max_height, &gb)) { delete h; return CMOS_ERR_ARG; }
+  if (oct_smem_bytes(gb.oct_maxn) > 200 * 1024) {
+    set_error("nfeatures too large for the quadtree kernel's shared memory");
+    delete h;
+    return CMOS_ERR_ARG;
+  }
+  h->kp_cap = gb.g.kp_cap;
+  const size_t B = params->max_batch;
+  // a little slack so that smaller images with unluckier rounding still fit
+  h->cap_frame_bytes = gb.g.frame_bytes + 64 * 1024;
+  h->cap_cand_frame = gb.g.cand_frame + 4096;
+  h->cap_cells = gb.cells.size() + 256;
+  h->cap_tiles = gb.tiles.size() + 256;
+  h->cap_tab = gb.tab.size() + 1024;
+  h->images_cap = (size_t)params->max_width * params->max_height * B;
+  cudaError_t err = cudaSuccess;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) err = cudaErrorUnknown;
+  h->d_images = dev_alloc<uint8_t>(h->images_cap, &err);
+  h->d_pyr = dev_alloc<uint8_t>(h->cap_frame_bytes * B, &err);
+  h->d_blur = dev_alloc<uint8_t>(h->cap_frame_bytes * B, &err);
+  h->d_cand = dev_alloc<uint32_t>(h->cap_cand_frame * B, &err);
+  h->d_pnode = dev_alloc<uint16_t>(h->cap_cand_frame * B, &err);
+  h->d_stage = dev_alloc<uint32_t>((size_t)h->kp_cap * B, &err);
+  h->d_kps = dev_alloc<cmos_keypoint>((size_t)h->kp_cap * B, &err);
+  h->d_desc = dev_alloc<uint8_t>((size_t)h->kp_cap * B * 32, &err);
+  h->d_cand_count = dev_alloc<int>(B * kMaxLevels, &err);
+  h->d_level_counts = dev_alloc<int>(B * kMaxLevels, &err);
+  h->d_counts = dev_alloc<int>(B, &err);
+  h->d_overflow = dev_alloc<int>(1, &err);
+  h->d_cells = dev_alloc<int4>(h->cap_cells, &err);
+  h->d_tiles = dev_alloc<int2>(h->cap_tiles, &err);
+  h->d_tab = dev_alloc<short4>(h->cap_tab, &err);
+  h->d_pattern = dev_alloc<int8_t>(1024, &err);
+  if (err != cudaSuccess) {
+    set_error("device allocation failed: %s", cudaGetErrorString(err));
+    cmos_orb_destroy(h);
+    return CMOS_ERR_CUDA;
+  }
+  cudaMemcpy(h->d_pattern, cmos_orb_pattern_xy, 1024, cudaMemcpyHostToDevice);
+  cudaMemset(h->d_blur, 0, h->cap_frame_bytes * B);
+  cudaMemset(h->d_level_counts, 0, B * kMaxLevels * sizeof(int));
+  cudaMemset(h->d_counts, 0, B * sizeof(int));
+  cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  CMOS_CUDA_OK(cudaGetLastError());
+  *out = h;
+  return CMOS_OK;
+}
+
+int cmos_orb_destroy(cmos_orb_t h) {
+  if (!h) return CMOS_OK;
+  cudaSetDevice(h->device);
+  void* bufs[] = {h->d_images, h->d_pyr, h->d_blur, h->d_cand, h->d_pnode, h->d_stage, h->d_kps, h->d_desc,
+                  h->d_cand_count, h->d_level_counts, h->d_counts, h->d_overflow, h->d_cells, h->d_tiles,
+                  h->d_tab, h->d_pattern};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return CMOS_OK;
+}
+
+int cmos_orb_get_levels(cmos_orb_t h, int32_t* nlevels) {
+  CMOS_REQUIRE(h && nlevels, "null argument");
+  *nlevels = h->p.nlevels;
+  return CMOS_OK;
+}
+
+int cmos_orb_get_scale_factors(cmos_orb_t h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2) {
+  CMOS_REQUIRE(h, "null handle");
+  for (int i = 0; i < h->p.nlevels; i++) {
+    if (scale) scale[i] = h->sf[i];
+    if (inv_scale) inv_scale[i] = h->inv_sf[i];
+    if (sigma2) sigma2[i] = h->sigma2[i];
+    if (inv_sigma2) inv_sigma2[i] = h->inv_sigma2[i];
+  }
+  return CMOS_OK;
+}
+
+int cmos_orb_get_features_per_level(cmos_orb_t h, int32_t* quota) {
+  CMOS_REQUIRE(h && quota, "null argument");
+  for (int i = 0; i < h->p.nlevels; i++) quota[i] = h->quota[i];
+  return CMOS_OK;
+}
+
+int cmos_orb_keypoint_capacity(cmos_orb_t h, int32_t* cap) {
+  CMOS_REQUIRE(h && cap, "null argument");
+  *cap = h->kp_cap;
+  return CMOS_OK;
+}
+
+int cmos_orb_extract_device(cmos_orb_t h, const uint8_t* d_images, int64_t frame_stride, int32_t pitch,
+                            int32_t width, int32_t height, int32_t n_frames, void* stream) {
+  CMOS_REQUIRE(h && d_images, "null argument");
+  CMOS_REQUIRE(n_frames >= 1 && n_frames <= h->p.max_batch, "n_frames %d outside 1..%d", n_frames, h->p.max_batch);
+  CMOS_REQUIRE(width > 0 && height > 0 && width <= h->p.max_width && height <= h->p.max_height && pitch >= width,
+               "bad image size %dx%d pitch %d", width, height, pitch);
+  CMOS_CUDA_OK(cudaSetDevice(h->device));
+  int rc = ensure_geometry(h, width, height);
+  if (rc) return rc;
+  return enqueue_extract(h, d_images, frame_stride, pitch, n_frames, stream ? (cudaStream_t)stream : h->stream);
+}
+
+int cmos_orb_download(cmos_orb_t h, int32_t n_frames, cmos_keypoint* keypoints, uint8_t* descriptors,
+                      int32_t* counts, int32_t capacity, void* stream) {
+  CMOS_REQUIRE(h && counts, "null argument");
+  if (!h->has_result) { set_error("download before extract"); return CMOS_ERR_STATE; }
+  CMOS_REQUIRE(n_frames >= 1 && n_frames <= h->last_frames, "n_frames %d outside 1..%d", n_frames, h->last_frames);
+  CMOS_REQUIRE(capacity >= h->kp_cap, "capacity %d < cmos_orb_keypoint_capacity %d", capacity, h->kp_cap);
+  CMOS_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  int overflow = 0;
+  CMOS_CUDA_OK(cudaMemcpyAsync(counts, h->d_counts, n_frames * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CMOS_CUDA_OK(cudaMemcpyAsync(&overflow, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (keypoints)
+    CMOS_CUDA_OK(cudaMemcpy2DAsync(keypoints, (size_t)capacity * sizeof(cmos_keypoint), h->d_kps,
+                                   (size_t)h->kp_cap * sizeof(cmos_keypoint), (size_t)h->kp_cap * sizeof(cmos_keypoint),
+                                   n_frames, cudaMemcpyDeviceToHost, st));
+  if (descriptors)
+    CMOS_CUDA_OK(cudaMemcpy2DAsync(descriptors, (size_t)capacity * 32, h->d_desc, (size_t)h->kp_cap * 32,
+                                   (size_t)h->kp_cap * 32, n_frames, cudaMemcpyDeviceToHost, st));
+  CMOS_CUDA_OK(cudaStreamSynchronize(st));
+  if (overflow) {
+    set_error("FAST candidate buffer overflow");
+    return CMOS_ERR_CAPACITY;
+  }
+  return CMOS_OK;
+}
+
+int cmos_orb_extract(cmos_orb_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
+                     int32_t height, int32_t n_frames, cmos_keypoint* keypoints, uint8_t* descriptors,
+                     int32_t* counts, int32_t capacity) {
+  CMOS_REQUIRE(h && counts, "null argument");
+  CMOS_REQUIRE(n_frames >= 1 && n_frames <= h->p.max_batch, "n_frames %d outside 1..%d", n_frames, h->p.max_batch);
+  if (width == 0 || height == 0 || !images) {   // empty image: silent no-op (ORBextractor.cc:1046-1047)
+    for (int f = 0; f < n_frames; f++) counts[f] = 0;
+    return CMOS_OK;
+  }
+  CMOS_REQUIRE(width > 0 && height > 0 && width <= h->p.max_width && height <= h->p.max_height && pitch >= width,
+               "bad image size %dx%d pitch %d", width, height, pitch);
+  CMOS_REQUIRE(capacity >= h->kp_cap, "capacity %d < cmos_orb_keypoint_capacity %d", capacity, h->kp_cap);
+  CMOS_CUDA_OK(cudaSetDevice(h->device));
+  CMOS_CUDA_OK(cudaMemcpy2DAsync(h->d_images, width, images, pitch, width, (size_t)height, cudaMemcpyHostToDevice,
+                                 h->stream));
+  for (int f = 1; f < n_frames; f++)
+    CMOS_CUDA_OK(cudaMemcpy2DAsync(h->d_images + (size_t)f * width * height, width, images + f * frame_stride, pitch,
+                                   width, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+  int rc = cmos_orb_extract_device(h, h->d_images, (int64_t)width * height, width, width, height, n_frames, h->stream);
+  if (rc) return rc;
+  return cmos_orb_download(h, n_frames, keypoints, descriptors, counts, capacity, h->stream);
+}
+
+int cmos_orb_device_results(cmos_orb_t h, cmos_keypoint** d_keypoints, uint8_t** d_descriptors, int32_t** d_counts,
+                            int32_t** d_level_counts, int32_t* capacity) {
+  CMOS_REQUIRE(h, "null handle");
+  if (d_keypoints) *d_keypoints = h->d_kps;
+  if (d_descriptors) *d_descriptors = h->d_desc;
+  if (d_counts) *d_counts = h->d_counts;
+  if (d_level_counts) *d_level_counts = h->d_level_counts;
+  if (capacity) *capacity = h->kp_cap;
+  return CMOS_OK;
+}
+
+int cmos_orb_level_size(cmos_orb_t h, int32_t level, int32_t* w, int32_t* ht) {
+  CMOS_REQUIRE(h && w && ht && level >= 0 && level < h->p.nlevels, "bad argument");
+  if (h->cur_w < 0) { set_error("no extraction yet"); return CMOS_ERR_STATE; }
+  *w = h->geom.lv[level].w;
+  *ht = h->geom.lv[level].h;
+  return CMOS_OK;
+}
+
+static int debug_plane(cmos_orb_t h, const uint8_t* base, int frame, int level, uint8_t* out, bool bordered) {
+  CMOS_REQUIRE(h && out && level >= 0 && level < h->p.nlevels && frame >= 0 && frame < h->p.max_batch, "bad argument");
+  if (!h->has_result) { set_error("no extraction yet"); return CMOS_ERR_STATE; }
+  CMOS_CUDA_OK(cudaSetDevice(h->device));
+  const LevelGeom& L = h->geom.lv[level];
+  CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));
+  const uint8_t* src = base + (size_t)frame * h->geom.frame_bytes + L.plane_off;
+  if (bordered)
+    CMOS_CUDA_OK(cudaMemcpy2D(out, L.w + 2 * kBorder, src + kXOff - kBorder, L.pitch, L.w + 2 * kBorder, L.rows,
+                              cudaMemcpyDeviceToHost));
+  else
+    CMOS_CUDA_OK(cudaMemcpy2D(out, L.w, src + (size_t)kBorder * L.pitch + kXOff, L.pitch, L.w, L.h,
+                              cudaMemcpyDeviceToHost));
+  return CMOS_OK;
+}
+
+int cmos_orb_debug_level_image(cmos_orb_t h, int32_t frame, int32_t level, uint8_t* out) {
+  return debug_plane(h, h ? h->d_pyr : nullptr, frame, level, out, true);
+}
+int cmos_orb_debug_level_blurred(cmos_orb_t h, int32_t frame, int32_t level, uint8_t* out) {
+  return debug_plane(h, h ? h->d_blur : nullptr, frame, level, out, false);
+}
+
+int cmos_orb_debug_level_candidates(cmos_orb_t h, int32_t frame, int32_t level, uint32_t* out, int32_t capacity,
+                                    int32_t* n) {
+  CMOS_REQUIRE(h && n && level >= 0 && level < h->p.nlevels && frame >= 0 && frame < h->p.max_batch, "bad argument");
+  if (!h->has_result) { set_error("no extraction yet"); return CMOS_ERR_STATE; }
+  CMOS_CUDA_OK(cudaSetDevice(h->device));
+  CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));
+  int cnt = 0;
+  CMOS_CUDA_OK(cudaMemcpy(&cnt, h->d_cand_count + frame * kMaxLevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+  const LevelGeom& L = h->geom.lv[level];
+  cnt = std::min(cnt, L.cand_cap);
+  *n = cnt;
+  if (out) {
+    CMOS_REQUIRE(capacity >= cnt, "capacity %d < %d candidates", capacity, cnt);
+    CMOS_CUDA_OK(cudaMemcpy(out, h->d_cand + (size_t)frame * h->geom.cand_frame + L.cand_off, (size_t)cnt * 4,
+                            cudaMemcpyDeviceToHost));
+  }
+  return CMOS_OK;
+}
+
+int cmos_orb_last_launch_count(cmos_orb_t h, int32_t* n) {
+  CMOS_REQUIRE(h && n, "null argument");
+  *n = h->launches;
+  return CMOS_OK;
+}
+
+int cmos_debug_sincos_deg(const float* deg, float* cos_out, float* sin_out, int32_t n) {
+  CMOS_REQUIRE(deg && cos_out && sin_out && n > 0, "bad argument");
+  float *d = nullptr, *c = nullptr, *s = nullptr;
+  CMOS_CUDA_OK(cudaMalloc(&d, n * 4)); CMOS_CUDA_OK(cudaMalloc(&c, n * 4)); CMOS_CUDA_OK(cudaMalloc(&s, n * 4));
+  CMOS_CUDA_OK(cudaMemcpy(d, deg, n * 4, cudaMemcpyHostToDevice));
+  k_debug_sincos<<<(n + 255) / 256, 256>>>(d, c, s, n);
+  CMOS_CUDA_OK(cudaMemcpy(cos_out, c, n * 4, cudaMemcpyDeviceToHost));
+  CMOS_CUDA_OK(cudaMemcpy(sin_out, s, n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d); cudaFree(c); cudaFree(s);
+  return CMOS_OK;
+}
+
+int cmos_debug_fast_atan2(const float* y, const float* x, float* out, int32_t n) {
+  CMOS_REQUIRE(y && x && out && n > 0, "bad argument");
+  float *dy = nullptr, *dx = nullptr, *d = nullptr;
+  CMOS_CUDA_OK(cudaMalloc(&dy, n * 4)); CMOS_CUDA_OK(cudaMalloc(&dx, n * 4)); CMOS_CUDA_OK(cudaMalloc(&d, n * 4));
+  CMOS_CUDA_OK(cudaMemcpy(dy, y, n * 4, cudaMemcpyHostToDevice));
+  CMOS_CUDA_OK(cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice));
+  k_debug_atan2<<<(n + 255) / 256, 256>>>(dy, dx, d, n);
+  CMOS_CUDA_OK(cudaMemcpy(out, d, n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dy); cudaFree(dx); cudaFree(d);
+  return CMOS_OK;
+}
+
+}  // extern "C"

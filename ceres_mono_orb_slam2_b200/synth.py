@@ -1,0 +1,227 @@
+"""Seeded synthetic inputs for the two hot paths.  numpy only.
+
+Images: mid-grey canvas + random rectangles + small blobs + mild noise, with a flat band kept so that
+empty FAST cells and the iniThFAST -> minThFAST fallback (ORBextractor.cc:808-816) are exercised.
+Frame pairs: frame t+1 is frame t shifted by a few pixels, so SearchByProjection has true matches.
+BA graphs: cameras on an arc / loop looking at a point cloud, float32 observations with octave-dependent
+noise and gross outliers, float32 intrinsics widened to double as the reference does
+(CeresOptimizer.cc:150-154).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+KITTI_K = (718.856, 718.856, 607.1928, 185.2157)   # configs/KITTI00-02.yaml:8-11
+TUM2_K = (520.908620, 521.007327, 325.141442, 249.701764)   # configs/TUM2.yaml:8-11
+
+
+def make_image(width: int, height: int, seed: int, n_rect: int = 400, n_blob: int = 200,
+               noise: int = 6) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    img = np.full((height, width), 128, np.int32)
+    flat_y0 = int(height * 0.86)          # bottom band stays flat (+ noise only)
+    for _ in range(n_rect):
+        w = int(rng.integers(8, 121)); h = int(rng.integers(8, 121))
+        x = int(rng.integers(-w // 2, width)); y = int(rng.integers(-h // 2, flat_y0))
+        v = int(rng.integers(0, 256))
+        img[max(y, 0):min(y + h, flat_y0), max(x, 0):x + w] = v
+    for _ in range(n_blob):
+        r = int(rng.integers(3, 10))
+        x = int(rng.integers(0, width)); y = int(rng.integers(0, flat_y0))
+        v = int(rng.integers(0, 256))
+        yy, xx = np.ogrid[-r:r + 1, -r:r + 1]
+        m = (xx * xx + yy * yy) <= r * r
+        y0, y1 = max(y - r, 0), min(y + r + 1, flat_y0)
+        x0, x1 = max(x - r, 0), min(x + r + 1, width)
+        if y1 <= y0 or x1 <= x0:
+            continue
+        sub = img[y0:y1, x0:x1]
+        mm = m[y0 - (y - r):y1 - (y - r), x0 - (x - r):x1 - (x - r)]
+        sub[mm] = v
+    if noise > 0:
+        img += rng.integers(-noise, noise + 1, size=img.shape)
+    # a noise-free flat strip inside the band: cells here are empty even at minThFAST
+    img[int(height * 0.93):, : width // 2] = 128
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def make_sequence(width: int, height: int, n_frames: int, seed: int, max_shift: int = 6) -> np.ndarray:
+    """n_frames images; frame t+1 is a shifted crop of the same scene as frame t plus fresh noise."""
+    rng = np.random.default_rng(seed)
+    pad = max_shift * n_frames + 8
+    scene = make_image(width + 2 * pad, height + 2 * pad, seed, n_rect=int(400 * (1 + 2 * pad / width) ** 2),
+                       n_blob=int(200 * (1 + 2 * pad / width) ** 2), noise=0).astype(np.int32)
+    out = np.empty((n_frames, height, width), np.uint8)
+    ox, oy = pad, pad
+    for t in range(n_frames):
+        crop = scene[oy:oy + height, ox:ox + width] + rng.integers(-4, 5, size=(height, width))
+        out[t] = np.clip(crop, 0, 255).astype(np.uint8)
+        ox += int(rng.integers(-max_shift, max_shift + 1))
+        oy += int(rng.integers(-max_shift // 2, max_shift // 2 + 1))
+        ox = min(max(ox, 0), 2 * pad); oy = min(max(oy, 0), 2 * pad)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# SE3 helpers (camera-from-world, q stored x,y,z,w as MatEigenConverter.cc:68-77 does)
+
+def quat_from_rotvec(rv: np.ndarray) -> np.ndarray:
+    th = np.linalg.norm(rv)
+    if th < 1e-12:
+        return np.array([0.0, 0.0, 0.0, 1.0])
+    ax = rv / th
+    return np.concatenate([ax * np.sin(th / 2), [np.cos(th / 2)]])
+
+
+def quat_mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    ax, ay, az, aw = a; bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by,
+                     aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw,
+                     aw * bw - ax * bx - ay * by - az * bz])
+
+
+def quat_to_R(q: np.ndarray) -> np.ndarray:
+    x, y, z, w = q / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def project(pose7: np.ndarray, X: np.ndarray, K) -> tuple[np.ndarray, np.ndarray]:
+    R = quat_to_R(pose7[3:7]); pc = X @ R.T + pose7[:3]
+    fx, fy, cx, cy = K
+    uv = np.stack([fx * pc[:, 0] / pc[:, 2] + cx, fy * pc[:, 1] / pc[:, 2] + cy], 1)
+    return uv, pc[:, 2]
+
+
+def _octaves(rng, n, n_levels=8):
+    p = 0.8 ** np.arange(n_levels); p /= p.sum()
+    return rng.choice(n_levels, size=n, p=p).astype(np.int32)
+
+
+def inv_sigma2_table(n_levels=8, scale=1.2) -> np.ndarray:
+    """float32 table computed as ORBextractor.cc:419-431 does (float products)."""
+    sf = np.empty(n_levels, np.float32); sf[0] = 1.0
+    s = np.float64(np.float32(scale))
+    for i in range(1, n_levels):
+        sf[i] = np.float32(np.float64(sf[i - 1]) * s)
+    sig = (sf * sf).astype(np.float32)
+    return (np.float32(1.0) / sig).astype(np.float32)
+
+
+def make_pose_problem(n_points: int = 1500, seed: int = 3, K=KITTI_K, outlier_frac: float = 0.1):
+    """C3: one frame x n 3D-2D correspondences.  Returns dict of arrays (see keys)."""
+    rng = np.random.default_rng(seed)
+    Kf = np.array(K, np.float32).astype(np.float64)
+    fx, fy, cx, cy = Kf
+    true_pose = np.concatenate([rng.normal(0, 0.3, 3), quat_from_rotvec(rng.normal(0, 0.05, 3))])
+    # points in the frustum of the true pose
+    z = rng.uniform(2, 40, n_points)
+    u = rng.uniform(20, 1221, n_points); v = rng.uniform(20, 356, n_points)
+    pc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    R = quat_to_R(true_pose[3:]); Xw = (pc - true_pose[:3]) @ R      # R^T (pc - t)
+    octv = _octaves(rng, n_points)
+    inv_s2 = inv_sigma2_table()[octv]
+    sigma = 1.0 / np.sqrt(inv_s2.astype(np.float64))
+    uv, _ = project(true_pose, Xw, Kf)
+    uv = uv + rng.normal(0, 1.0, uv.shape) * sigma[:, None]
+    n_out = int(outlier_frac * n_points)
+    idx = rng.choice(n_points, n_out, replace=False)
+    uv[idx] += rng.uniform(-50, 50, (n_out, 2))
+    init = true_pose.copy()
+    init[:3] += rng.normal(0, 0.2 / np.sqrt(3), 3)
+    init[3:] = quat_mul(quat_from_rotvec(rng.normal(0, 0.05 / np.sqrt(3), 3)), true_pose[3:])
+    return dict(pose=init, true_pose=true_pose, Xw=Xw, uv=uv.astype(np.float32), inv_sigma2=inv_s2,
+                K=Kf, octave=octv)
+
+
+def make_ba_problem(n_cams: int, n_points: int, obs_per_point: int, seed: int, n_fixed_extra: int = 0,
+                    window: int | None = None, K=KITTI_K, outlier_frac: float = 0.05,
+                    pose_noise=(0.01, 0.05), point_noise: float = 0.05):
+    """C4/C5: cameras on an arc (or loop) looking outward at a shell of points.
+    Every point is seen by exactly `obs_per_point` cameras, chosen inside a +-window camera window when
+    `window` is given (C5), else uniformly (C4).  Camera 0 is always fixed (KF id 0 constant,
+    CeresOptimizer.cc:115-120); `n_fixed_extra` additional fixed cameras follow the variable ones."""
+    rng = np.random.default_rng(seed)
+    Kf = np.array(K, np.float32).astype(np.float64)
+    fx, fy, cx, cy = Kf
+    n_total = n_cams + n_fixed_extra
+    # camera centres along an arc, each looking along +z of a slowly turning heading
+    poses = np.zeros((n_total, 7))
+    step = 0.5
+    heading = np.linspace(0, (2 * np.pi if window is not None else 0.6), n_total, endpoint=False)
+    centre = np.zeros((n_total, 3))
+    for i in range(1, n_total):
+        centre[i] = centre[i - 1] + step * np.array([np.cos(heading[i]), 0.0, np.sin(heading[i])])
+    for i in range(n_total):
+        # camera z axis = heading direction rotated by -90deg about y so that cameras look sideways/outward
+        yaw = heading[i] - np.pi / 2
+        q_wc = quat_from_rotvec(np.array([0.0, -yaw, 0.0]))     # world-from-camera
+        R_wc = quat_to_R(q_wc)
+        R_cw = R_wc.T
+        q_cw = np.array([-q_wc[0], -q_wc[1], -q_wc[2], q_wc[3]])
+        poses[i, :3] = -R_cw @ centre[i]
+        poses[i, 3:] = q_cw
+    # points: for each point choose an anchor camera, place the point in its frustum
+    cam_idx = np.empty((n_points, obs_per_point), np.int32)
+    Xw = np.empty((n_points, 3))
+    for j in range(n_points):
+        for _try in range(100):
+            a = int(rng.integers(0, n_total))
+            z = rng.uniform(5, 40)
+            u = rng.uniform(200, 1041); v = rng.uniform(60, 316)
+            pc = np.array([(u - cx) / fx * z, (v - cy) / fy * z, z])
+            R = quat_to_R(poses[a, 3:])
+            X = R.T @ (pc - poses[a, :3])
+            if window is None:
+                pool = np.arange(n_total)
+            else:
+                pool = (a + np.arange(-window, window + 1)) % n_total
+            uvp, zp = project_many(poses[pool], X, Kf)
+            ok = (zp > 1.0) & (uvp[:, 0] > 0) & (uvp[:, 0] < 1241) & (uvp[:, 1] > 0) & (uvp[:, 1] < 376)
+            vis = pool[ok]
+            if len(vis) >= obs_per_point:
+                cam_idx[j] = np.sort(rng.choice(vis, obs_per_point, replace=False))
+                Xw[j] = X
+                break
+        else:
+            raise RuntimeError("could not place point")
+    obs_cam = cam_idx.reshape(-1)
+    obs_pt = np.repeat(np.arange(n_points, dtype=np.int32), obs_per_point)
+    n_obs = obs_cam.size
+    octv = _octaves(rng, n_obs)
+    inv_s2 = inv_sigma2_table()[octv]
+    sigma = 1.0 / np.sqrt(inv_s2.astype(np.float64))
+    uv = np.empty((n_obs, 2))
+    for c in np.unique(obs_cam):
+        m = obs_cam == c
+        uv[m], _ = project(poses[c], Xw[obs_pt[m]], Kf)
+    uv += rng.normal(0, 1.0, uv.shape) * sigma[:, None]
+    n_out = int(outlier_frac * n_obs)
+    idx = rng.choice(n_obs, n_out, replace=False)
+    uv[idx] += rng.uniform(-50, 50, (n_out, 2))
+    fixed = np.zeros(n_total, np.uint8)
+    fixed[0] = 1
+    fixed[n_cams:] = 1
+    init_poses = poses.copy()
+    for i in range(n_total):
+        if fixed[i]:
+            continue
+        init_poses[i, :3] += rng.normal(0, pose_noise[1] / np.sqrt(3), 3)
+        init_poses[i, 3:] = quat_mul(quat_from_rotvec(rng.normal(0, pose_noise[0] / np.sqrt(3), 3)), poses[i, 3:])
+    init_pts = Xw + rng.normal(0, point_noise / np.sqrt(3), Xw.shape)
+    return dict(poses=init_poses, true_poses=poses, fixed=fixed, points=init_pts, true_points=Xw,
+                obs_cam=obs_cam.astype(np.int32), obs_pt=obs_pt, uv=uv.astype(np.float32),
+                inv_sigma2=inv_s2, K=Kf)
+
+
+def project_many(poses: np.ndarray, X: np.ndarray, K):
+    fx, fy, cx, cy = K
+    uv = np.empty((len(poses), 2)); z = np.empty(len(poses))
+    for i, p in enumerate(poses):
+        pc = quat_to_R(p[3:]) @ X + p[:3]
+        z[i] = pc[2]
+        zz = pc[2] if abs(pc[2]) > 1e-9 else 1e-9
+        uv[i] = (fx * pc[0] / zz + cx, fy * pc[1] / zz + cy)
+    return uv, z

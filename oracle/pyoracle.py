@@ -1,0 +1,197 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY (see oracle/orb_oracle.cpp header).
+
+ctypes front for oracle/liboracle.so plus a second, independent ORB oracle that calls cv2 (OpenCV 4.13,
+Python wheel) at exactly the entry points where the reference calls the C++ API
+(cv::resize / copyMakeBorder / FAST / GaussianBlur / fastAtan2, ORBextractor.cc:809,814,1086,1120-1127,103).
+The cv2 oracle pins the C++ restatement; neither is ever imported by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(".cpp")]
+    newest = max(os.path.getmtime(s) for s in srcs)
+    if force or not os.path.exists(so) or os.path.getmtime(so) < newest:
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True, capture_output=True)
+    return so
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orb_oracle_create.restype = C.c_void_p
+        _LIB.orb_oracle_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        _LIB.orb_oracle_destroy.argtypes = [C.c_void_p]
+        for name in ("orb_oracle_tables", "orb_oracle_extract", "orb_oracle_result", "orb_oracle_level_size",
+                     "orb_oracle_level_image", "orb_oracle_level_blurred", "orb_oracle_level_candidates",
+                     "orb_oracle_level_keypoints"):
+            getattr(_LIB, name).argtypes = None
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OrbOracle:
+    """C++ restatement of ORBextractor (oracle/orb_oracle.cpp)."""
+
+    def __init__(self, nfeatures=2000, scale=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.L = lib()
+        self.nlevels = nlevels
+        self.h = C.c_void_p(self.L.orb_oracle_create(nfeatures, C.c_float(scale), nlevels, ini_th, min_th))
+        sf, isf, s2, is2 = (np.zeros(nlevels, np.float32) for _ in range(4))
+        quota = np.zeros(nlevels, np.int32); umax = np.zeros(16, np.int32)
+        self.L.orb_oracle_tables(self.h, _p(sf), _p(isf), _p(s2), _p(is2), _p(quota), _p(umax))
+        self.scale_factors, self.inv_scale_factors, self.sigma2, self.inv_sigma2 = sf, isf, s2, is2
+        self.quota, self.umax = quota, umax
+
+    def __del__(self):
+        try:
+            self.L.orb_oracle_destroy(self.h)
+        except Exception:
+            pass
+
+    def extract(self, img: np.ndarray):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        n = self.L.orb_oracle_extract(self.h, _p(img), w, h, w)
+        kps = np.zeros(n, KP_DTYPE); desc = np.zeros((n, 32), np.uint8)
+        self.L.orb_oracle_result(self.h, _p(kps), _p(desc))
+        return kps, desc
+
+    def level_size(self, l):
+        w, h = C.c_int(), C.c_int()
+        self.L.orb_oracle_level_size(self.h, l, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def level_image(self, l):
+        w, h = self.level_size(l)
+        out = np.zeros((h + 38, w + 38), np.uint8)
+        self.L.orb_oracle_level_image(self.h, l, _p(out))
+        return out
+
+    def level_blurred(self, l):
+        w, h = self.level_size(l)
+        out = np.zeros((h, w), np.uint8)
+        self.L.orb_oracle_level_blurred(self.h, l, _p(out))
+        return out
+
+    def level_candidates(self, l):
+        n = self.L.orb_oracle_level_candidates(self.h, l, None)
+        out = np.zeros(n, KP_DTYPE)
+        self.L.orb_oracle_level_candidates(self.h, l, _p(out))
+        return out
+
+    def level_keypoints(self, l):
+        n = self.L.orb_oracle_level_keypoints(self.h, l, None)
+        out = np.zeros(n, KP_DTYPE)
+        self.L.orb_oracle_level_keypoints(self.h, l, _p(out))
+        return out
+
+
+def resize(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().orb_oracle_resize(_p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), dw, dh, dw)
+    return dst
+
+
+def blur7(src: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros_like(src)
+    lib().orb_oracle_blur7(_p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), src.shape[1])
+    return dst
+
+
+def fast(img: np.ndarray, threshold: int) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = img.size // 4 + 16
+    out = np.zeros((cap, 3), np.int32)
+    n = lib().orb_oracle_fast(_p(img), img.shape[1], img.shape[0], img.shape[1], threshold, _p(out), cap)
+    return out[:n]
+
+
+def fast_atan2(y: np.ndarray, x: np.ndarray) -> np.ndarray:
+    y = np.ascontiguousarray(y, np.float32); x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros_like(y)
+    lib().orb_oracle_fast_atan2(_p(y), _p(x), _p(out), y.size)
+    return out
+
+
+def sincos_deg(deg: np.ndarray):
+    deg = np.ascontiguousarray(deg, np.float32)
+    c = np.zeros_like(deg); s = np.zeros_like(deg)
+    lib().orb_oracle_sincos(_p(deg), _p(c), _p(s), deg.size)
+    return c, s
+
+
+def descriptor_distance(a: np.ndarray, b: np.ndarray) -> int:
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return int(lib().orb_oracle_descriptor_distance(_p(a), _p(b)))
+
+
+# ---------------------------------------------------------------------------------------------------
+# cv2-based pipeline front half: pyramid + per-cell FAST candidates + blurred levels, built from the
+# same cv2 calls the reference makes.  Used to pin the C++ restatement stage by stage.
+
+def cv2_pyramid(img: np.ndarray, inv_scale_factors: np.ndarray):
+    import cv2
+    levels = []
+    h, w = img.shape
+    for l, s in enumerate(inv_scale_factors):
+        sw = int(np.rint(np.float32(w) * np.float32(s))); sh = int(np.rint(np.float32(h) * np.float32(s)))
+        if l == 0:
+            cur = img
+        else:
+            prev = levels[-1][19:-19, 19:-19]
+            cur = cv2.resize(prev, (sw, sh), interpolation=cv2.INTER_LINEAR)
+        levels.append(cv2.copyMakeBorder(cur, 19, 19, 19, 19, cv2.BORDER_REFLECT_101))
+    return levels
+
+
+def cv2_level_candidates(bordered: np.ndarray, ini_th=20, min_th=7):
+    """ORBextractor.cc:765-829 with cv2.FastFeatureDetector per cell; returns (x, y, response) rows in
+    vToDistributeKeys order, coordinates relative to minBorder."""
+    import cv2
+    im = bordered[19:-19, 19:-19]
+    h, w = im.shape
+    min_b = 16; max_bx = w - 16; max_by = h - 16
+    width = np.float32(max_bx - min_b); height = np.float32(max_by - min_b)
+    n_cols = int(width / np.float32(30)); n_rows = int(height / np.float32(30))
+    w_cell = int(np.ceil(width / n_cols)); h_cell = int(np.ceil(height / n_rows))
+    det_ini = cv2.FastFeatureDetector_create(ini_th, True)
+    det_min = cv2.FastFeatureDetector_create(min_th, True)
+    out = []
+    for i in range(n_rows):
+        ini_y = min_b + i * h_cell; max_y = ini_y + h_cell + 6
+        if ini_y >= max_by - 3:
+            continue
+        max_y = min(max_y, max_by)
+        for j in range(n_cols):
+            ini_x = min_b + j * w_cell; max_x = ini_x + w_cell + 6
+            if ini_x >= max_bx - 6:
+                continue
+            max_x = min(max_x, max_bx)
+            cell = np.ascontiguousarray(im[ini_y:max_y, ini_x:max_x])
+            kps = det_ini.detect(cell)
+            if not kps:
+                kps = det_min.detect(cell)
+            for kp in kps:
+                out.append((kp.pt[0] + j * w_cell, kp.pt[1] + i * h_cell, kp.response))
+    return np.array(out, np.float32).reshape(-1, 3)
