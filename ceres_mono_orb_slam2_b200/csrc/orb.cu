@@ -133,14 +133,16 @@ __device__ __forceinline__ int fast_arc_max(const uint8_t* __restrict__ p, int t
     lo4[k] = min(lo2[k], lo2[(k + 2) & 15]);
     hi4[k] = max(hi2[k], hi2[(k + 2) & 15]);
   }
-  int best = 0;
+  // brightest arc = max over arcs of the arc minimum; darkest arc = min over arcs of the arc maximum
+  int bright_best = -255, dark_best = 255;
 #pragma unroll
   for (int k = 0; k < 16; k++) {
     int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
     int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
-    best = max(best, max(lo9, -hi9));
+    bright_best = max(bright_best, lo9);
+    dark_best = min(dark_best, hi9);
   }
-  return best;
+  return max(0, max(bright_best, -dark_best));
 }
 
 // One CTA per (cell, frame): stage the (w_cell+6) x (h_cell+6) tile in shared memory, score the
@@ -149,7 +151,8 @@ __device__ __forceinline__ int fast_arc_max(const uint8_t* __restrict__ p, int t
 __global__ void __launch_bounds__(kFastThreads) k_fast(OrbGeom g, const int4* __restrict__ cells,
                                                       const uint8_t* __restrict__ pyr,
                                                       uint32_t* __restrict__ cand,
-                                                      int* __restrict__ cand_count, int* __restrict__ overflow) {
+                                                      int* __restrict__ cand_count, int* __restrict__ overflow,
+                                                      uint8_t* __restrict__ dbg, int dbg_cell) {
   __shared__ __align__(16) uint8_t tile[kTileH * kTileW];
   __shared__ __align__(16) uint8_t score[kTileH * kTileW];
   __shared__ uint32_t s_list[kCellListCap];
@@ -183,6 +186,10 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(OrbGeom g, const int4* __
   }
   __syncthreads();
 
+  if (dbg && (int)blockIdx.x == dbg_cell && f == 0) {   // verification tap
+    for (int i = tid; i < kTileH * kTileW; i += kFastThreads) { dbg[i] = tile[i]; dbg[kTileH * kTileW + i] = score[i]; }
+    if (tid == 0) { int* q = (int*)(dbg + 2 * kTileH * kTileW); q[0] = x0; q[1] = y0; q[2] = cw; q[3] = ch; q[4] = shift; q[5] = level; q[6] = g.ini_th; q[7] = g.min_th; }
+  }
   int th = g.ini_th;
   for (int pass = 0; pass < 2; pass++) {
     int kept = 0;
@@ -664,6 +671,8 @@ struct cmos_orb {
   int2* d_tiles = nullptr;
   short4* d_tab = nullptr;      // x tables then y tables of every level
   int8_t* d_pattern = nullptr;
+  uint8_t* d_dbg = nullptr;
+  int dbg_cell = -1;
   std::vector<int> xtab_off, ytab_off;
   size_t images_cap = 0;
   int last_frames = 0, launches = 0;
@@ -832,7 +841,7 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
   }
   if (h->n_cells > 0) {
     k_fast<<<dim3(h->n_cells, n_frames), kFastThreads, 0, st>>>(g, h->d_cells, h->d_pyr, h->d_cand, h->d_cand_count,
-                                                              h->d_overflow);
+                                                              h->d_overflow, h->d_dbg, h->dbg_cell);
     launches++;
   }
   k_octree<<<dim3(g.nlevels, n_frames), kOctThreads, oct_smem_bytes(h->oct_maxn), st>>>(
@@ -1110,6 +1119,19 @@ int cmos_orb_debug_level_candidates(cmos_orb_t h, int32_t frame, int32_t level, 
     CMOS_CUDA_OK(cudaMemcpy(out, h->d_cand + (size_t)frame * h->geom.cand_frame + L.cand_off, (size_t)cnt * 4,
                             cudaMemcpyDeviceToHost));
   }
+  return CMOS_OK;
+}
+
+int cmos_orb_debug_fast_cell(cmos_orb_t h, int32_t cell, uint8_t* out) {
+  CMOS_REQUIRE(h, "null handle");
+  CMOS_CUDA_OK(cudaSetDevice(h->device));
+  const size_t bytes = 2 * kTileH * kTileW + 64;
+  if (!h->d_dbg) CMOS_CUDA_OK(cudaMalloc(&h->d_dbg, bytes));
+  if (out) {
+    CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    CMOS_CUDA_OK(cudaMemcpy(out, h->d_dbg, bytes, cudaMemcpyDeviceToHost));
+  }
+  h->dbg_cell = cell;
   return CMOS_OK;
 }
 

@@ -113,6 +113,9 @@ int cmos_orb_debug_level_blurred(cmos_orb_t h, int32_t frame, int32_t level, uin
  * relative to minBorder (ORBextractor.cc:820-825), unordered.  Returns the count through *n. */
 int cmos_orb_debug_level_candidates(cmos_orb_t h, int32_t frame, int32_t level, uint32_t* out,
                                     int32_t capacity, int32_t* n);
+/* Selects the FAST cell (index into the handle's cell table, frame 0) whose shared-memory tile and score map the
+ * next extraction records; if `out` is non-NULL first copies the previous record: 2*72*80 bytes + 16 ints. */
+int cmos_orb_debug_fast_cell(cmos_orb_t h, int32_t cell, uint8_t* out);
 /* Number of kernels launched by the last cmos_orb_extract* call. */
 int cmos_orb_last_launch_count(cmos_orb_t h, int32_t* n);
 /* Device evaluation of the two float helpers that must round like the CPU (cosf/sinf of angle*pi/180 as

@@ -19,7 +19,6 @@ def _dump(name, **arrays):
 
 
 def _compare_frame(ext, oracle, img, frame, tag):
-    ok = True
     okps, odesc = oracle.extract(img)
     for l in range(oracle.nlevels):
         a = ext.debug_level_image(frame, l); b = oracle.level_image(l)
@@ -33,8 +32,9 @@ def _compare_frame(ext, oracle, img, frame, tag):
         if not np.array_equal(gc, ocs):
             _dump(f"cand_{tag}_{l}", gpu=gc, oracle=ocs)
             raise AssertionError(f"{tag}: FAST candidates level {l}: gpu {len(gc)} vs oracle {len(ocs)}")
+        if len(oracle.level_keypoints(l)) == 0:
+            continue   # the reference (and the oracle) only blur levels that hold keypoints (:1079-1086)
         gb = ext.debug_level_blurred(frame, l); ob = oracle.level_blurred(l)
-        # the reference only reads blurred pixels >= 1 px inside the level (|pattern| <= 18 < 19)
         nbad = int((gb != ob).sum())
         assert nbad == 0, f"{tag}: blurred level {l}: {nbad} bytes differ"
     return okps, odesc
