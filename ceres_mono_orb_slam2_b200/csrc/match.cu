@@ -1,0 +1,879 @@
+// ORB matcher for sm_100a: Frame grid (CSR), SearchByProjection(frame, last frame) and
+// SearchByProjection(frame, map points), isInFrustum — batched over frames, one CTA per frame.
+//
+// Behaviour follows src/ORBmatcher.cc:42-126,1161-1271,1386-1437 and src/Frame.cc:158-173,191-320.
+// The reference's searches are greedy and order dependent (a keypoint claimed by an earlier map point is
+// skipped by later ones).  Here the Hamming work is done in parallel — every warp of the CTA takes
+// queries, walks the grid window in the reference's iteration order and leaves a short, ordered
+// candidate list per query in shared memory — and then ONE warp replays the queries in order against the
+// `claimed` bytes, which reproduces the sequential result exactly.  Queries whose list overflowed are
+// re-enumerated by that warp, so the result never depends on the list capacity.
+//
+// Compiled with --fmad=false (projection and window arithmetic must round like the unfused CPU floats).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "cmos_common.h"
+
+namespace cmos {
+
+constexpr int kCols = CMOS_GRID_COLS, kRows = CMOS_GRID_ROWS, kCells = kCols * kRows;
+constexpr int kSearchThreads = 1024;
+constexpr int kListCap = 8;        // candidates kept per query for the sequential replay (overflow -> re-enumerate)
+constexpr int kListCapPts = 16;
+
+struct FrameDev {                 // one current frame on the device
+  const cmos_keypoint* kps;
+  const uint8_t* desc;
+  const int* grid_start;
+  const int* grid_idx;
+  int n;
+};
+
+__device__ __forceinline__ int hamming256(const uint32_t a[8], const uint8_t* __restrict__ b) {
+  const uint32_t* w = (const uint32_t*)b;
+  int d = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) d += __popc(a[i] ^ __ldg(w + i));
+  return d;
+}
+
+struct Window { int min_cx, max_cx, min_cy, max_cy; bool ok; };
+
+// cell range of Frame::GetFeaturesInArea (Frame.cc:250-275)
+__device__ __forceinline__ Window make_window(const cmos_camera& cam, float x, float y, float r) {
+  Window w;
+  w.ok = false;
+  w.min_cx = max(0, (int)floorf((x - cam.min_x - r) * cam.grid_element_width_inv));
+  if (w.min_cx >= kCols) return w;
+  w.max_cx = min(kCols - 1, (int)ceilf((x - cam.min_x + r) * cam.grid_element_width_inv));
+  if (w.max_cx < 0) return w;
+  w.min_cy = max(0, (int)floorf((y - cam.min_y - r) * cam.grid_element_height_inv));
+  if (w.min_cy >= kRows) return w;
+  w.max_cy = min(kRows - 1, (int)ceilf((y - cam.min_y + r) * cam.grid_element_height_inv));
+  if (w.max_cy < 0) return w;
+  w.ok = true;
+  return w;
+}
+
+// Warp-synchronous walk over the candidates of GetFeaturesInArea in the reference's order (ix outer, iy
+// inner, insertion order inside a cell — with cell = ix*48+iy one ix column is one contiguous CSR run).
+// Calls visit(idx, pass) with 32 consecutive candidates at a time; pass == false for padding lanes and
+// for keypoints rejected by the level / window tests (Frame.cc:283-301).
+template <typename Visit>
+__device__ __forceinline__ void walk_window(const FrameDev& F, const Window& w, float x, float y, float r,
+                                            int min_level, int max_level, int lane, Visit visit) {
+  const bool check_levels = (min_level > 0) || (max_level >= 0);
+  for (int ix = w.min_cx; ix <= w.max_cx; ix++) {
+    const int k0 = F.grid_start[ix * kRows + w.min_cy], k1 = F.grid_start[ix * kRows + w.max_cy + 1];
+    for (int k = k0; k < k1; k += 32) {
+      const int kk = k + lane;
+      bool pass = kk < k1;
+      int idx = 0;
+      if (pass) {
+        idx = F.grid_idx[kk];
+        const cmos_keypoint* kp = F.kps + idx;
+        const int oct = kp->octave;
+        if (check_levels) {
+          if (oct < min_level) pass = false;
+          if (max_level >= 0 && oct > max_level) pass = false;
+        }
+        const float dx = kp->x - x, dy = kp->y - y;
+        pass = pass && fabsf(dx) < r && fabsf(dy) < r;
+      }
+      visit(idx, pass);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Frame::AssignFeaturesToGrid (Frame.cc:158-173) + PosInGrid (:309-320) as CSR, one CTA per frame.
+__global__ void __launch_bounds__(256) k_build_grid(cmos_camera cam, const cmos_keypoint* __restrict__ kps,
+                                                    const int* __restrict__ counts, int stride, int max_kp,
+                                                    int* __restrict__ grid_start, int* __restrict__ grid_idx) {
+  extern __shared__ int sm[];
+  int* cnt = sm;                              // [kCells + 1]
+  short* cell_of = (short*)(cnt + kCells + 1);   // [n]
+  __shared__ int warp_tmp[8];
+  const int f = blockIdx.x, tid = threadIdx.x;
+  const int n = min(counts[f], stride);
+  const cmos_keypoint* kp = kps + (long long)f * stride;
+  for (int i = tid; i <= kCells; i += 256) cnt[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += 256) {
+    const int px = (int)roundf((kp[i].x - cam.min_x) * cam.grid_element_width_inv);
+    const int py = (int)roundf((kp[i].y - cam.min_y) * cam.grid_element_height_inv);
+    int c = -1;
+    if (px >= 0 && px < kCols && py >= 0 && py < kRows) { c = px * kRows + py; atomicAdd(&cnt[c], 1); }
+    cell_of[i] = (short)c;
+  }
+  __syncthreads();
+  // exclusive scan of 3072 counts: 12 per thread
+  constexpr int per = kCells / 256;
+  int local[per], sum = 0;
+#pragma unroll
+  for (int j = 0; j < per; j++) { local[j] = cnt[tid * per + j]; sum += local[j]; }
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += t;
+  }
+  if ((tid & 31) == 31) warp_tmp[tid >> 5] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < (tid >> 5); w++) base += warp_tmp[w];
+  int run = base + incl - sum;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < per; j++) { cnt[tid * per + j] = run; run += local[j]; }
+  if (tid == 255) cnt[kCells] = run;
+  __syncthreads();
+  int* gs = grid_start + (long long)f * (kCells + 1);
+  for (int i = tid; i <= kCells; i += 256) gs[i] = cnt[i];
+  // position inside the cell = number of earlier keypoints in the same cell (insertion order)
+  int* gi = grid_idx + (long long)f * max_kp;
+  for (int i = tid; i < n; i += 256) {
+    const short c = cell_of[i];
+    if (c < 0) continue;
+    int r = 0;
+    for (int j = 0; j < i; j++) r += cell_of[j] == c;
+    gi[cnt[c] + r] = i;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th), one CTA per frame pair.
+struct SearchFrameArgs {
+  const double* Tcw;                 // [B][16]
+  const cmos_keypoint* last_kps;     // [B][last_stride]
+  const int* last_counts;
+  const uint8_t* last_flags;
+  const double* last_xw;
+  const uint8_t* last_desc;
+  int last_stride;
+  float th;
+  int check_ori;
+  uint8_t* claimed;                  // [B][stride] or null
+  int* match;                        // [B][stride]
+  int* nmatches;                     // [B]
+};
+
+struct QueryFrame { float u, v, radius; int oct; bool ok; };
+
+__device__ __forceinline__ QueryFrame project_last(const cmos_camera& cam, const double* __restrict__ T,
+                                                   const double* __restrict__ X, int oct) {
+  QueryFrame q;
+  q.ok = false;
+  q.oct = oct;
+  const double pcx = (T[0] * X[0] + T[1] * X[1]) + T[2] * X[2] + T[3];
+  const double pcy = (T[4] * X[0] + T[5] * X[1]) + T[6] * X[2] + T[7];
+  const double pcz = (T[8] * X[0] + T[9] * X[1]) + T[10] * X[2] + T[11];
+  const float xc = (float)pcx, yc = (float)pcy;
+  const float invzc = (float)(1.0 / pcz);
+  if (invzc < 0) return q;
+  q.u = cam.fx * xc * invzc + cam.cx;
+  q.v = cam.fy * yc * invzc + cam.cy;
+  if (q.u < cam.min_x || q.u > cam.max_x) return q;
+  if (q.v < cam.min_y || q.v > cam.max_y) return q;
+  q.radius = 0.f;
+  q.ok = true;
+  return q;
+}
+
+__global__ void __launch_bounds__(kSearchThreads) k_search_frame(cmos_camera cam, const cmos_keypoint* __restrict__ kps,
+                                                                const uint8_t* __restrict__ desc,
+                                                                const int* __restrict__ counts, int stride,
+                                                                const int* __restrict__ grid_start,
+                                                                const int* __restrict__ grid_idx, int max_kp,
+                                                                SearchFrameArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(counts[f], stride);
+  const int nq = min(a.last_counts[f], a.last_stride);
+  // carve: lists[nq][kListCap] u32 | match[n] i32 | ev_idx[nq] u16 | cnt[nq] u16 | claimed[n] u8 | ev_bin[nq] u8
+  uint32_t* lists = (uint32_t*)smem_raw;
+  int* s_match = (int*)(lists + (size_t)a.last_stride * kListCap);
+  uint16_t* ev_idx = (uint16_t*)(s_match + stride);
+  uint16_t* cnt = ev_idx + a.last_stride;
+  uint8_t* s_claimed = (uint8_t*)(cnt + a.last_stride);
+  uint8_t* ev_bin = s_claimed + stride;
+  __shared__ int s_nmatch, s_nev, s_hist[CMOS_HISTO_LENGTH], s_keep[3];
+
+  FrameDev F{kps + (long long)f * stride, desc + (long long)f * stride * 32,
+             grid_start + (long long)f * (kCells + 1), grid_idx + (long long)f * max_kp, n};
+  const cmos_keypoint* last = a.last_kps + (long long)f * a.last_stride;
+  const uint8_t* lflags = a.last_flags + (long long)f * a.last_stride;
+  const double* lxw = a.last_xw + (long long)f * a.last_stride * 3;
+  const uint8_t* ldesc = a.last_desc + (long long)f * a.last_stride * 32;
+  const double* T = a.Tcw + (long long)f * 16;
+
+  for (int i = tid; i < n; i += kSearchThreads) {
+    s_match[i] = -1;
+    s_claimed[i] = a.claimed ? a.claimed[(long long)f * stride + i] : 0;
+  }
+  if (tid < CMOS_HISTO_LENGTH) s_hist[tid] = 0;
+  if (tid == 0) { s_nmatch = 0; s_nev = 0; }
+
+  // ---- parallel part: ordered candidate lists (distance <= TH_HIGH) ----
+  for (int q = warp; q < nq; q += kSearchThreads / 32) {
+    int total = 0;
+    if (lflags[q] & 1) {
+      const int oct = last[q].octave;
+      QueryFrame Q = project_last(cam, T, lxw + 3 * q, oct);
+      if (Q.ok) {
+        const float radius = a.th * cam.scale_factors[oct];
+        const Window w = make_window(cam, Q.u, Q.v, radius);
+        if (w.ok) {
+          uint32_t dq[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) dq[i] = __ldg((const uint32_t*)(ldesc + 32 * (size_t)q) + i);
+          walk_window(F, w, Q.u, Q.v, radius, oct - 1, oct + 1, lane, [&](int idx, bool pass) {
+            int d = 256;
+            if (pass) d = hamming256(dq, F.desc + 32 * (size_t)idx);
+            const bool keep = pass && d <= CMOS_TH_HIGH;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            const int pos = total + __popc(m & ((1u << lane) - 1));
+            if (keep && pos < kListCap) lists[(size_t)q * kListCap + pos] = ((uint32_t)d << 16) | (uint32_t)idx;
+            total += __popc(m);
+          });
+        }
+      }
+    }
+    if (lane == 0) cnt[q] = (uint16_t)min(total, 65535);
+  }
+  __syncthreads();
+
+  // ---- sequential replay by one warp (ORBmatcher.cc:1176-1250) ----
+  if (warp == 0) {
+    const float factor = 1.0f / CMOS_HISTO_LENGTH;
+    for (int q = 0; q < nq; q++) {
+      const int c = cnt[q];
+      if (c == 0) continue;
+      unsigned best = 0xffffffffu;   // (dist << 16 | order) then idx separately
+      int best_idx = -1;
+      if (c <= kListCap) {
+        unsigned key = 0xffffffffu;
+        int idx = -1;
+        if (lane < c) {
+          const uint32_t e = lists[(size_t)q * kListCap + lane];
+          idx = e & 0xffff;
+          if (!s_claimed[idx]) key = ((e >> 16) << 16) | (unsigned)lane;
+        }
+        unsigned mk = key;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mk = min(mk, __shfl_xor_sync(0xffffffffu, mk, o));
+        best = mk;
+        const unsigned who = __ballot_sync(0xffffffffu, key == mk && key != 0xffffffffu);
+        if (who) best_idx = __shfl_sync(0xffffffffu, idx, __ffs(who) - 1);
+      } else {
+        // list overflowed: walk the window again, now against the claimed bytes
+        const int oct = last[q].octave;
+        QueryFrame Q = project_last(cam, T, lxw + 3 * q, oct);
+        const float radius = a.th * cam.scale_factors[oct];
+        const Window w = make_window(cam, Q.u, Q.v, radius);
+        uint32_t dq[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) dq[i] = __ldg((const uint32_t*)(ldesc + 32 * (size_t)q) + i);
+        int bd = 256, bi = -1;
+        walk_window(F, w, Q.u, Q.v, radius, oct - 1, oct + 1, lane, [&](int idx, bool pass) {
+          int d = 256;
+          if (pass && !s_claimed[idx]) d = hamming256(dq, F.desc + 32 * (size_t)idx);
+          // first strict minimum in candidate order: lanes are in order inside a chunk, chunks in order
+          unsigned key = ((unsigned)d << 8) | (unsigned)lane;
+          unsigned mk = key;
+#pragma unroll
+          for (int o = 16; o; o >>= 1) mk = min(mk, __shfl_xor_sync(0xffffffffu, mk, o));
+          const int cd = (int)(mk >> 8);
+          if (cd < bd) { bd = cd; bi = __shfl_sync(0xffffffffu, idx, mk & 31); }
+        });
+        if (bd <= CMOS_TH_HIGH) { best = (unsigned)bd << 16; best_idx = bi; }
+      }
+      if (best_idx >= 0 && (best >> 16) <= CMOS_TH_HIGH) {
+        if (lane == 0) {
+          s_match[best_idx] = q;
+          s_claimed[best_idx] = (lflags[q] >> 1) & 1;
+          s_nmatch++;
+          if (a.check_ori) {
+            float rot = last[q].angle - F.kps[best_idx].angle;
+            if (rot < 0.0f) rot += 360.0f;
+            int bin = (int)roundf(rot * factor);
+            if (bin == CMOS_HISTO_LENGTH) bin = 0;
+            const int e = s_nev++;
+            ev_idx[e] = (uint16_t)best_idx;
+            ev_bin[e] = (uint8_t)bin;
+            s_hist[bin]++;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // ComputeThreeMaxima (ORBmatcher.cc:1386-1418)
+    if (lane == 0 && a.check_ori) {
+      int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+      for (int i = 0; i < CMOS_HISTO_LENGTH; i++) {
+        const int s = s_hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
+        else if (s > max3) { max3 = s; i3 = i; }
+      }
+      if (max2 < 0.1f * (float)max1) { i2 = -1; i3 = -1; }
+      else if (max3 < 0.1f * (float)max1) { i3 = -1; }
+      s_keep[0] = i1; s_keep[1] = i2; s_keep[2] = i3;
+    }
+  }
+  __syncthreads();
+  if (a.check_ori) {
+    const int nev = s_nev;
+    int removed = 0;
+    for (int e = tid; e < nev; e += kSearchThreads) {
+      const int b = ev_bin[e];
+      if (b != s_keep[0] && b != s_keep[1] && b != s_keep[2]) { s_match[ev_idx[e]] = -1; removed++; }
+    }
+    if (removed) atomicSub(&s_nmatch, removed);
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += kSearchThreads) {
+    a.match[(long long)f * stride + i] = s_match[i];
+    if (a.claimed) a.claimed[(long long)f * stride + i] = s_claimed[i];
+  }
+  for (int i = n + tid; i < stride; i += kSearchThreads) a.match[(long long)f * stride + i] = -1;
+  if (tid == 0) a.nmatches[f] = s_nmatch;
+}
+
+// -------------------------------------------------------------------------------------------------
+// ORBmatcher::SearchByProjection(F, vpMapPoints, th), one CTA per frame.
+struct SearchPointsArgs {
+  const int* n_points;
+  const uint8_t* in_view;
+  const int* level;
+  const float* view_cos;
+  const float* proj_xy;
+  const uint8_t* desc;
+  const uint8_t* has_obs;
+  int point_stride;
+  float th, nn_ratio;
+  int list_thresh;     // candidates above this distance can never change a decision (see host code)
+  uint8_t* claimed;
+  int* assign;
+  int* nmatches;
+};
+
+__global__ void __launch_bounds__(kSearchThreads) k_search_points(cmos_camera cam, const cmos_keypoint* __restrict__ kps,
+                                                                 const uint8_t* __restrict__ desc,
+                                                                 const int* __restrict__ counts, int stride,
+                                                                 const int* __restrict__ grid_start,
+                                                                 const int* __restrict__ grid_idx, int max_kp,
+                                                                 SearchPointsArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(counts[f], stride);
+  const int np = min(a.n_points[f], a.point_stride);
+  // carve: lists[np][kListCapPts] u32 | assign[n] i32 | cnt[np] u16 | claimed[n] u8
+  uint32_t* lists = (uint32_t*)smem_raw;
+  int* s_assign = (int*)(lists + (size_t)a.point_stride * kListCapPts);
+  uint16_t* cnt = (uint16_t*)(s_assign + stride);
+  uint8_t* s_claimed = (uint8_t*)(cnt + a.point_stride);
+  __shared__ int s_nmatch;
+
+  FrameDev F{kps + (long long)f * stride, desc + (long long)f * stride * 32,
+             grid_start + (long long)f * (kCells + 1), grid_idx + (long long)f * max_kp, n};
+  const long long pb = (long long)f * a.point_stride;
+  const bool b_factor = a.th != 1.0f;
+
+  for (int i = tid; i < n; i += kSearchThreads) {
+    s_assign[i] = -1;
+    s_claimed[i] = a.claimed ? a.claimed[(long long)f * stride + i] : 0;
+  }
+  if (tid == 0) s_nmatch = 0;
+
+  auto query = [&](int p, float& x, float& y, float& r, int& lvl) {
+    lvl = a.level[pb + p];
+    r = ((double)a.view_cos[pb + p] > 0.998) ? 2.5f : 4.0f;   // RadiusByViewingCos, :121-126
+    if (b_factor) r *= a.th;
+    r = r * cam.scale_factors[lvl];
+    x = a.proj_xy[2 * (pb + p)];
+    y = a.proj_xy[2 * (pb + p) + 1];
+  };
+
+  for (int p = warp; p < np; p += kSearchThreads / 32) {
+    int total = 0;
+    if (a.in_view[pb + p]) {
+      float x, y, r; int lvl;
+      query(p, x, y, r, lvl);
+      const Window w = make_window(cam, x, y, r);
+      if (w.ok) {
+        uint32_t dq[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) dq[i] = __ldg((const uint32_t*)(a.desc + 32 * (size_t)(pb + p)) + i);
+        walk_window(F, w, x, y, r, lvl - 1, lvl, lane, [&](int idx, bool pass) {
+          int d = 256;
+          if (pass) d = hamming256(dq, F.desc + 32 * (size_t)idx);
+          const bool keep = pass && d <= a.list_thresh;
+          const unsigned m = __ballot_sync(0xffffffffu, keep);
+          const int pos = total + __popc(m & ((1u << lane) - 1));
+          if (keep && pos < kListCapPts)
+            lists[(size_t)p * kListCapPts + pos] = ((uint32_t)d << 20) | ((uint32_t)F.kps[idx].octave << 16) | (uint32_t)idx;
+          total += __popc(m);
+        });
+      }
+    }
+    if (lane == 0) cnt[p] = (uint16_t)min(total, 65535);
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    for (int p = 0; p < np; p++) {
+      const int c = cnt[p];
+      if (c == 0) continue;
+      int b1 = 256, l1 = -1, b2 = 256, l2 = -1, bi = -1;
+      if (c <= kListCapPts) {
+        unsigned key = 0xffffffffu;
+        uint32_t e = 0;
+        if (lane < c) {
+          e = lists[(size_t)p * kListCapPts + lane];
+          if (!s_claimed[e & 0xffff]) key = ((e >> 20) << 8) | (unsigned)lane;
+        }
+        unsigned m1 = key;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m1 = min(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+        if (m1 != 0xffffffffu) {
+          const int src = m1 & 31;
+          const uint32_t e1 = __shfl_sync(0xffffffffu, e, src);
+          b1 = e1 >> 20; l1 = (e1 >> 16) & 15; bi = e1 & 0xffff;
+          unsigned k2 = (lane == src) ? 0xffffffffu : key;
+#pragma unroll
+          for (int o = 16; o; o >>= 1) k2 = min(k2, __shfl_xor_sync(0xffffffffu, k2, o));
+          if (k2 != 0xffffffffu) {
+            const uint32_t e2 = __shfl_sync(0xffffffffu, e, k2 & 31);
+            b2 = e2 >> 20; l2 = (e2 >> 16) & 15;
+          }
+        }
+      } else {
+        float x, y, r; int lvl;
+        query(p, x, y, r, lvl);
+        const Window w = make_window(cam, x, y, r);
+        uint32_t dq[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) dq[i] = __ldg((const uint32_t*)(a.desc + 32 * (size_t)(pb + p)) + i);
+        // stable top-2 by (distance, candidate order): merge each 32-chunk's two minima into the running pair
+        walk_window(F, w, x, y, r, lvl - 1, lvl, lane, [&](int idx, bool pass) {
+          int d = 256;
+          if (pass && !s_claimed[idx]) d = hamming256(dq, F.desc + 32 * (size_t)idx);
+          const int oct = pass ? F.kps[idx].octave : -1;
+          unsigned key = ((unsigned)d << 8) | (unsigned)lane;
+          for (int round = 0; round < 2; round++) {
+            unsigned mk = key;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) mk = min(mk, __shfl_xor_sync(0xffffffffu, mk, o));
+            const int cd = (int)(mk >> 8), src = mk & 31;
+            if (cd >= 256) break;
+            const int ci = __shfl_sync(0xffffffffu, idx, src), co = __shfl_sync(0xffffffffu, oct, src);
+            if (cd < b1) { b2 = b1; l2 = l1; b1 = cd; l1 = co; bi = ci; }
+            else if (cd < b2) { b2 = cd; l2 = co; }
+            if (lane == src) key = 0xffffffffu;
+          }
+        });
+      }
+      if (b1 <= CMOS_TH_HIGH) {
+        if (l1 == l2 && (float)b1 > a.nn_ratio * (float)b2) continue;
+        if (lane == 0) {
+          s_assign[bi] = p;
+          s_claimed[bi] = a.has_obs[pb + p];
+          s_nmatch++;
+        }
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kSearchThreads) {
+    a.assign[(long long)f * stride + i] = s_assign[i];
+    if (a.claimed) a.claimed[(long long)f * stride + i] = s_claimed[i];
+  }
+  for (int i = n + tid; i < stride; i += kSearchThreads) a.assign[(long long)f * stride + i] = -1;
+  if (tid == 0) a.nmatches[f] = s_nmatch;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Frame::isInFrustum (Frame.cc:191-241) + MapPoint::PredictScale (MapPoint.cc:405-420), thread per point.
+__global__ void __launch_bounds__(256) k_in_frustum(cmos_camera cam, const double* __restrict__ pose15, float cos_limit,
+                                                    const int* __restrict__ n_points, const double* __restrict__ xw,
+                                                    const double* __restrict__ normal, const float* __restrict__ min_d,
+                                                    const float* __restrict__ max_d, int point_stride,
+                                                    uint8_t* __restrict__ in_view, float* __restrict__ proj_xy,
+                                                    int* __restrict__ level, float* __restrict__ view_cos) {
+  const int f = blockIdx.y, p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= point_stride) return;
+  const long long i = (long long)f * point_stride + p;
+  in_view[i] = 0;
+  if (p >= n_points[f]) return;
+  const double* R = pose15 + 15 * f; const double* t = R + 9; const double* Ow = R + 12;
+  const double* P = xw + 3 * i;
+  const double pcx = (R[0] * P[0] + R[1] * P[1]) + R[2] * P[2] + t[0];
+  const double pcy = (R[3] * P[0] + R[4] * P[1]) + R[5] * P[2] + t[1];
+  const double pcz = (R[6] * P[0] + R[7] * P[1]) + R[8] * P[2] + t[2];
+  const float PcX = (float)pcx, PcY = (float)pcy, PcZ = (float)pcz;
+  if (PcZ < 0.0f) return;
+  const float invz = 1.0f / PcZ;
+  const float u = cam.fx * PcX * invz + cam.cx, v = cam.fy * PcY * invz + cam.cy;
+  if (u < cam.min_x || u > cam.max_x) return;
+  if (v < cam.min_y || v > cam.max_y) return;
+  const float maxd = 1.2f * max_d[i], mind = 0.8f * min_d[i];
+  const double po0 = P[0] - Ow[0], po1 = P[1] - Ow[1], po2 = P[2] - Ow[2];
+  const float dist = (float)sqrt((po0 * po0 + po1 * po1) + po2 * po2);
+  if (dist < mind || dist > maxd) return;
+  const double* Pn = normal + 3 * i;
+  const float vc = (float)(((po0 * Pn[0] + po1 * Pn[1]) + po2 * Pn[2]) / (double)dist);
+  if (vc < cos_limit) return;
+  const float ratio = max_d[i] / dist;
+  int ns = (int)ceilf((float)log((double)ratio) / cam.log_scale_factor);
+  if (ns < 0) ns = 0;
+  else if (ns >= cam.nlevels) ns = cam.nlevels - 1;
+  in_view[i] = 1;
+  proj_xy[2 * i] = u;
+  proj_xy[2 * i + 1] = v;
+  level[i] = ns;
+  view_cos[i] = vc;
+}
+
+}  // namespace cmos
+
+using namespace cmos;
+
+// =================================================================================================
+// Host side
+// =================================================================================================
+struct cmos_match {
+  cmos_match_params p{};
+  cudaStream_t stream = nullptr;
+  cmos_camera cam{};
+  // bound current frames
+  const cmos_keypoint* kps = nullptr;
+  const uint8_t* desc = nullptr;
+  const int* counts = nullptr;
+  int n_frames = 0, stride = 0;
+  bool bound = false;
+  int launches = 0;
+  // own device buffers
+  int *d_grid_start = nullptr, *d_grid_idx = nullptr;
+  // staging for host callers
+  cmos_keypoint *s_kps = nullptr, *s_last_kps = nullptr;
+  uint8_t *s_desc = nullptr, *s_last_desc = nullptr, *s_last_flags = nullptr, *s_claimed = nullptr;
+  int *s_counts = nullptr, *s_last_counts = nullptr, *s_match = nullptr, *s_nmatches = nullptr;
+  double *s_last_xw = nullptr, *s_T = nullptr;
+  // points staging
+  int *s_np = nullptr, *s_level = nullptr;
+  uint8_t *s_in_view = nullptr, *s_pdesc = nullptr, *s_has_obs = nullptr;
+  float *s_view_cos = nullptr, *s_proj = nullptr, *s_mind = nullptr, *s_maxd = nullptr;
+  double *s_pxw = nullptr, *s_pnormal = nullptr, *s_pose = nullptr;
+};
+
+namespace {
+template <typename T>
+int h2d(T* dst, const T* src, size_t n, cudaStream_t st) {
+  CMOS_CUDA_OK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+  return CMOS_OK;
+}
+template <typename T>
+int d2h(T* dst, const T* src, size_t n, cudaStream_t st) {
+  CMOS_CUDA_OK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+  return CMOS_OK;
+}
+size_t search_frame_smem(int last_stride, int stride) {
+  return (size_t)last_stride * kListCap * 4 + (size_t)stride * 4 + (size_t)last_stride * 2 * 2 + stride + last_stride + 16;
+}
+size_t search_points_smem(int point_stride, int stride) {
+  return (size_t)point_stride * kListCapPts * 4 + (size_t)stride * 4 + (size_t)point_stride * 2 + stride + 16;
+}
+}  // namespace
+
+extern "C" {
+
+int cmos_camera_init(cmos_camera* cam, int32_t width, int32_t height, float fx, float fy, float cx, float cy,
+                     const float* scale_factors, int32_t nlevels, float scale_factor) {
+  CMOS_REQUIRE(cam && scale_factors && nlevels >= 1 && nlevels <= CMOS_MAX_LEVELS && width > 0 && height > 0,
+               "bad argument");
+  std::memset(cam, 0, sizeof(*cam));
+  cam->min_x = 0.0f; cam->max_x = (float)width; cam->min_y = 0.0f; cam->max_y = (float)height;
+  cam->grid_element_width_inv = static_cast<float>(CMOS_GRID_COLS) / static_cast<float>(cam->max_x - cam->min_x);
+  cam->grid_element_height_inv = static_cast<float>(CMOS_GRID_ROWS) / static_cast<float>(cam->max_y - cam->min_y);
+  cam->fx = fx; cam->fy = fy; cam->cx = cx; cam->cy = cy;
+  cam->nlevels = nlevels;
+  for (int i = 0; i < nlevels; i++) cam->scale_factors[i] = scale_factors[i];
+  cam->log_scale_factor = (float)std::log((double)scale_factor);   // Frame.cc:110: log(float) assigned to float
+  return CMOS_OK;
+}
+
+int cmos_match_create(const cmos_match_params* params, cmos_match_t* out) {
+  CMOS_REQUIRE(params && out, "null argument");
+  CMOS_REQUIRE(params->max_batch > 0 && params->max_keypoints > 0 && params->max_keypoints <= 65535 &&
+               params->max_points >= 0 && params->max_points <= 65535, "bad sizes");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: this library has no CPU fallback");
+    return CMOS_ERR_CUDA;
+  }
+  CMOS_REQUIRE(params->device >= 0 && params->device < ndev, "device %d out of range", params->device);
+  CMOS_CUDA_OK(cudaSetDevice(params->device));
+  if (search_frame_smem(params->max_keypoints, params->max_keypoints) > 220 * 1024 ||
+      search_points_smem(std::max(params->max_points, 1), params->max_keypoints) > 220 * 1024) {
+    set_error("max_keypoints/max_points too large for the search kernels' shared memory");
+    return CMOS_ERR_ARG;
+  }
+  cmos_match* h = new cmos_match();
+  h->p = *params;
+  const size_t B = params->max_batch, K = params->max_keypoints, P = std::max(params->max_points, 1);
+  cudaError_t err = cudaSuccess;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) err = cudaErrorUnknown;
+  h->d_grid_start = dev_alloc<int>(B * (kCells + 1), &err);
+  h->d_grid_idx = dev_alloc<int>(B * K, &err);
+  h->s_kps = dev_alloc<cmos_keypoint>(B * K, &err);
+  h->s_last_kps = dev_alloc<cmos_keypoint>(B * K, &err);
+  h->s_desc = dev_alloc<uint8_t>(B * K * 32, &err);
+  h->s_last_desc = dev_alloc<uint8_t>(B * K * 32, &err);
+  h->s_last_flags = dev_alloc<uint8_t>(B * K, &err);
+  h->s_claimed = dev_alloc<uint8_t>(B * K, &err);
+  h->s_counts = dev_alloc<int>(B, &err);
+  h->s_last_counts = dev_alloc<int>(B, &err);
+  h->s_match = dev_alloc<int>(B * K, &err);
+  h->s_nmatches = dev_alloc<int>(B, &err);
+  h->s_last_xw = dev_alloc<double>(B * K * 3, &err);
+  h->s_T = dev_alloc<double>(B * 16, &err);
+  h->s_np = dev_alloc<int>(B, &err);
+  h->s_level = dev_alloc<int>(B * P, &err);
+  h->s_in_view = dev_alloc<uint8_t>(B * P, &err);
+  h->s_pdesc = dev_alloc<uint8_t>(B * P * 32, &err);
+  h->s_has_obs = dev_alloc<uint8_t>(B * P, &err);
+  h->s_view_cos = dev_alloc<float>(B * P, &err);
+  h->s_proj = dev_alloc<float>(B * P * 2, &err);
+  h->s_mind = dev_alloc<float>(B * P, &err);
+  h->s_maxd = dev_alloc<float>(B * P, &err);
+  h->s_pxw = dev_alloc<double>(B * P * 3, &err);
+  h->s_pnormal = dev_alloc<double>(B * P * 3, &err);
+  h->s_pose = dev_alloc<double>(B * 15, &err);
+  if (err != cudaSuccess) {
+    set_error("device allocation failed: %s", cudaGetErrorString(err));
+    cmos_match_destroy(h);
+    return CMOS_ERR_CUDA;
+  }
+  cudaFuncSetAttribute(k_search_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  cudaFuncSetAttribute(k_search_points, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  cudaFuncSetAttribute(k_build_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  CMOS_CUDA_OK(cudaGetLastError());
+  *out = h;
+  return CMOS_OK;
+}
+
+int cmos_match_destroy(cmos_match_t h) {
+  if (!h) return CMOS_OK;
+  cudaSetDevice(h->p.device);
+  void* bufs[] = {h->d_grid_start, h->d_grid_idx, h->s_kps, h->s_last_kps, h->s_desc, h->s_last_desc, h->s_last_flags,
+                  h->s_claimed, h->s_counts, h->s_last_counts, h->s_match, h->s_nmatches, h->s_last_xw, h->s_T,
+                  h->s_np, h->s_level, h->s_in_view, h->s_pdesc, h->s_has_obs, h->s_view_cos, h->s_proj, h->s_mind,
+                  h->s_maxd, h->s_pxw, h->s_pnormal, h->s_pose};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return CMOS_OK;
+}
+
+int cmos_match_set_frames(cmos_match_t h, const cmos_camera* cam, const cmos_keypoint* keypoints,
+                          const uint8_t* descriptors, const int32_t* counts, int32_t n_frames, int32_t stride,
+                          int32_t on_device, void* stream) {
+  CMOS_REQUIRE(h && cam && keypoints && descriptors && counts, "null argument");
+  CMOS_REQUIRE(n_frames >= 1 && n_frames <= h->p.max_batch, "n_frames %d outside 1..%d", n_frames, h->p.max_batch);
+  CMOS_REQUIRE(stride >= 1 && stride <= h->p.max_keypoints, "stride %d outside 1..%d", stride, h->p.max_keypoints);
+  CMOS_REQUIRE(cam->nlevels >= 1 && cam->nlevels <= CMOS_MAX_LEVELS, "bad camera");
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  h->cam = *cam;
+  if (on_device) {
+    h->kps = keypoints; h->desc = descriptors; h->counts = counts;
+  } else {
+    const size_t n = (size_t)n_frames * stride;
+    int rc;
+    if ((rc = h2d(h->s_kps, keypoints, n, st))) return rc;
+    if ((rc = h2d(h->s_desc, descriptors, n * 32, st))) return rc;
+    if ((rc = h2d(h->s_counts, counts, n_frames, st))) return rc;
+    h->kps = h->s_kps; h->desc = h->s_desc; h->counts = h->s_counts;
+  }
+  h->n_frames = n_frames;
+  h->stride = stride;
+  const size_t smem = (kCells + 1) * sizeof(int) + (size_t)stride * sizeof(short) + 16;
+  k_build_grid<<<n_frames, 256, smem, st>>>(h->cam, h->kps, h->counts, stride, h->p.max_keypoints, h->d_grid_start,
+                                            h->d_grid_idx);
+  CMOS_CUDA_OK(cudaGetLastError());
+  h->launches = 1;
+  h->bound = true;
+  if (!on_device) CMOS_CUDA_OK(cudaStreamSynchronize(st));
+  return CMOS_OK;
+}
+
+int cmos_match_debug_grid(cmos_match_t h, int32_t frame, int32_t* grid_start, int32_t* grid_idx) {
+  CMOS_REQUIRE(h && grid_start && grid_idx && frame >= 0 && frame < h->p.max_batch, "bad argument");
+  if (!h->bound) { set_error("no frames bound"); return CMOS_ERR_STATE; }
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  CMOS_CUDA_OK(cudaDeviceSynchronize());
+  CMOS_CUDA_OK(cudaMemcpy(grid_start, h->d_grid_start + (size_t)frame * (kCells + 1), (kCells + 1) * sizeof(int),
+                          cudaMemcpyDeviceToHost));
+  CMOS_CUDA_OK(cudaMemcpy(grid_idx, h->d_grid_idx + (size_t)frame * h->p.max_keypoints, (size_t)h->stride * sizeof(int),
+                          cudaMemcpyDeviceToHost));
+  return CMOS_OK;
+}
+
+int cmos_match_search_by_projection_frame(cmos_match_t h, const double* Tcw, const cmos_keypoint* last_keypoints,
+                                          const int32_t* last_counts, const uint8_t* last_flags,
+                                          const double* last_xw, const uint8_t* last_descriptors,
+                                          int32_t last_stride, float th, int32_t check_orientation,
+                                          uint8_t* claimed, int32_t* match, int32_t* nmatches, int32_t on_device,
+                                          void* stream) {
+  CMOS_REQUIRE(h && Tcw && last_keypoints && last_counts && last_flags && last_xw && last_descriptors && match &&
+               nmatches, "null argument");
+  if (!h->bound) { set_error("cmos_match_set_frames must be called first"); return CMOS_ERR_STATE; }
+  CMOS_REQUIRE(last_stride >= 1 && last_stride <= h->p.max_keypoints, "last_stride %d outside 1..%d", last_stride,
+               h->p.max_keypoints);
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const int B = h->n_frames;
+  const size_t nl = (size_t)B * last_stride, nc = (size_t)B * h->stride;
+  SearchFrameArgs a{};
+  a.last_stride = last_stride; a.th = th; a.check_ori = check_orientation;
+  if (on_device) {
+    a.Tcw = Tcw; a.last_kps = last_keypoints; a.last_counts = last_counts; a.last_flags = last_flags;
+    a.last_xw = last_xw; a.last_desc = last_descriptors; a.claimed = claimed; a.match = match; a.nmatches = nmatches;
+  } else {
+    int rc;
+    if ((rc = h2d(h->s_T, Tcw, (size_t)B * 16, st))) return rc;
+    if ((rc = h2d(h->s_last_kps, last_keypoints, nl, st))) return rc;
+    if ((rc = h2d(h->s_last_counts, last_counts, B, st))) return rc;
+    if ((rc = h2d(h->s_last_flags, last_flags, nl, st))) return rc;
+    if ((rc = h2d(h->s_last_xw, last_xw, nl * 3, st))) return rc;
+    if ((rc = h2d(h->s_last_desc, last_descriptors, nl * 32, st))) return rc;
+    if (claimed && (rc = h2d(h->s_claimed, claimed, nc, st))) return rc;
+    a.Tcw = h->s_T; a.last_kps = h->s_last_kps; a.last_counts = h->s_last_counts; a.last_flags = h->s_last_flags;
+    a.last_xw = h->s_last_xw; a.last_desc = h->s_last_desc; a.claimed = claimed ? h->s_claimed : nullptr;
+    a.match = h->s_match; a.nmatches = h->s_nmatches;
+  }
+  k_search_frame<<<B, kSearchThreads, search_frame_smem(last_stride, h->stride), st>>>(
+      h->cam, h->kps, h->desc, h->counts, h->stride, h->d_grid_start, h->d_grid_idx, h->p.max_keypoints, a);
+  CMOS_CUDA_OK(cudaGetLastError());
+  h->launches = 1;
+  if (!on_device) {
+    int rc;
+    if ((rc = d2h(match, h->s_match, nc, st))) return rc;
+    if ((rc = d2h(nmatches, h->s_nmatches, B, st))) return rc;
+    if (claimed && (rc = d2h(claimed, h->s_claimed, nc, st))) return rc;
+    CMOS_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return CMOS_OK;
+}
+
+int cmos_match_search_by_projection_points(cmos_match_t h, const int32_t* n_points, const uint8_t* in_view,
+                                           const int32_t* level, const float* view_cos, const float* proj_xy,
+                                           const uint8_t* descriptors, const uint8_t* has_obs,
+                                           int32_t point_stride, float th, float nn_ratio, uint8_t* claimed,
+                                           int32_t* assign, int32_t* nmatches, int32_t on_device, void* stream) {
+  CMOS_REQUIRE(h && n_points && in_view && level && view_cos && proj_xy && descriptors && has_obs && assign && nmatches,
+               "null argument");
+  if (!h->bound) { set_error("cmos_match_set_frames must be called first"); return CMOS_ERR_STATE; }
+  CMOS_REQUIRE(point_stride >= 1 && point_stride <= h->p.max_points, "point_stride %d outside 1..%d", point_stride,
+               h->p.max_points);
+  CMOS_REQUIRE(nn_ratio > 0.f, "nn_ratio must be positive");
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const int B = h->n_frames;
+  const size_t np = (size_t)B * point_stride, nc = (size_t)B * h->stride;
+  SearchPointsArgs a{};
+  a.point_stride = point_stride; a.th = th; a.nn_ratio = nn_ratio;
+  // A second-best candidate with nn_ratio * dist > TH_HIGH can never reject a best <= TH_HIGH
+  // (ORBmatcher.cc:109-110), so such candidates need not be listed; +2 is slack for float rounding.
+  a.list_thresh = std::min(255, (int)std::ceil(CMOS_TH_HIGH / nn_ratio) + 2);
+  if (on_device) {
+    a.n_points = n_points; a.in_view = in_view; a.level = level; a.view_cos = view_cos; a.proj_xy = proj_xy;
+    a.desc = descriptors; a.has_obs = has_obs; a.claimed = claimed; a.assign = assign; a.nmatches = nmatches;
+  } else {
+    int rc;
+    if ((rc = h2d(h->s_np, n_points, B, st))) return rc;
+    if ((rc = h2d(h->s_in_view, in_view, np, st))) return rc;
+    if ((rc = h2d(h->s_level, level, np, st))) return rc;
+    if ((rc = h2d(h->s_view_cos, view_cos, np, st))) return rc;
+    if ((rc = h2d(h->s_proj, proj_xy, np * 2, st))) return rc;
+    if ((rc = h2d(h->s_pdesc, descriptors, np * 32, st))) return rc;
+    if ((rc = h2d(h->s_has_obs, has_obs, np, st))) return rc;
+    if (claimed && (rc = h2d(h->s_claimed, claimed, nc, st))) return rc;
+    a.n_points = h->s_np; a.in_view = h->s_in_view; a.level = h->s_level; a.view_cos = h->s_view_cos;
+    a.proj_xy = h->s_proj; a.desc = h->s_pdesc; a.has_obs = h->s_has_obs;
+    a.claimed = claimed ? h->s_claimed : nullptr; a.assign = h->s_match; a.nmatches = h->s_nmatches;
+  }
+  k_search_points<<<B, kSearchThreads, search_points_smem(point_stride, h->stride), st>>>(
+      h->cam, h->kps, h->desc, h->counts, h->stride, h->d_grid_start, h->d_grid_idx, h->p.max_keypoints, a);
+  CMOS_CUDA_OK(cudaGetLastError());
+  h->launches = 1;
+  if (!on_device) {
+    int rc;
+    if ((rc = d2h(assign, h->s_match, nc, st))) return rc;
+    if ((rc = d2h(nmatches, h->s_nmatches, B, st))) return rc;
+    if (claimed && (rc = d2h(claimed, h->s_claimed, nc, st))) return rc;
+    CMOS_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return CMOS_OK;
+}
+
+int cmos_match_is_in_frustum(cmos_match_t h, const cmos_camera* cam, const double* pose15, float view_cos_limit,
+                             const int32_t* n_points, const double* xw, const double* normal,
+                             const float* min_distance, const float* max_distance, int32_t point_stride,
+                             int32_t n_frames, uint8_t* in_view, float* proj_xy, int32_t* level, float* view_cos,
+                             int32_t on_device, void* stream) {
+  CMOS_REQUIRE(h && cam && pose15 && n_points && xw && normal && min_distance && max_distance && in_view && proj_xy &&
+               level && view_cos, "null argument");
+  CMOS_REQUIRE(n_frames >= 1 && n_frames <= h->p.max_batch, "n_frames %d outside 1..%d", n_frames, h->p.max_batch);
+  CMOS_REQUIRE(point_stride >= 1 && point_stride <= h->p.max_points, "point_stride %d outside 1..%d", point_stride,
+               h->p.max_points);
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const size_t np = (size_t)n_frames * point_stride;
+  const double *d_pose = pose15, *d_xw = xw, *d_n = normal;
+  const int* d_np = n_points;
+  const float *d_min = min_distance, *d_max = max_distance;
+  uint8_t* o_view = in_view; float* o_proj = proj_xy; int* o_level = level; float* o_cos = view_cos;
+  if (!on_device) {
+    int rc;
+    if ((rc = h2d(h->s_pose, pose15, (size_t)n_frames * 15, st))) return rc;
+    if ((rc = h2d(h->s_np, n_points, n_frames, st))) return rc;
+    if ((rc = h2d(h->s_pxw, xw, np * 3, st))) return rc;
+    if ((rc = h2d(h->s_pnormal, normal, np * 3, st))) return rc;
+    if ((rc = h2d(h->s_mind, min_distance, np, st))) return rc;
+    if ((rc = h2d(h->s_maxd, max_distance, np, st))) return rc;
+    d_pose = h->s_pose; d_np = h->s_np; d_xw = h->s_pxw; d_n = h->s_pnormal; d_min = h->s_mind; d_max = h->s_maxd;
+    o_view = h->s_in_view; o_proj = h->s_proj; o_level = h->s_level; o_cos = h->s_view_cos;
+  }
+  k_in_frustum<<<dim3((point_stride + 255) / 256, n_frames), 256, 0, st>>>(*cam, d_pose, view_cos_limit, d_np, d_xw, d_n,
+                                                                        d_min, d_max, point_stride, o_view, o_proj,
+                                                                        o_level, o_cos);
+  CMOS_CUDA_OK(cudaGetLastError());
+  h->launches = 1;
+  if (!on_device) {
+    int rc;
+    if ((rc = d2h(in_view, h->s_in_view, np, st))) return rc;
+    if ((rc = d2h(proj_xy, h->s_proj, np * 2, st))) return rc;
+    if ((rc = d2h(level, h->s_level, np, st))) return rc;
+    if ((rc = d2h(view_cos, h->s_view_cos, np, st))) return rc;
+    CMOS_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return CMOS_OK;
+}
+
+int cmos_match_last_launch_count(cmos_match_t h, int32_t* n) {
+  CMOS_REQUIRE(h && n, "null argument");
+  *n = h->launches;
+  return CMOS_OK;
+}
+
+}  // extern "C"

@@ -45,21 +45,47 @@ def make_image(width: int, height: int, seed: int, n_rect: int = 400, n_blob: in
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
-def make_sequence(width: int, height: int, n_frames: int, seed: int, max_shift: int = 6) -> np.ndarray:
-    """n_frames images; frame t+1 is a shifted crop of the same scene as frame t plus fresh noise."""
+def make_sequence(width: int, height: int, n_frames: int, seed: int, max_shift: int = 6,
+                  return_offsets: bool = False):
+    """n_frames images; frame t+1 is a shifted crop of the same scene as frame t plus fresh noise.
+    With return_offsets also returns the crop origin (ox, oy) of every frame."""
     rng = np.random.default_rng(seed)
-    pad = max_shift * n_frames + 8
+    pad = max_shift * min(n_frames, 12) + 8
     scene = make_image(width + 2 * pad, height + 2 * pad, seed, n_rect=int(400 * (1 + 2 * pad / width) ** 2),
                        n_blob=int(200 * (1 + 2 * pad / width) ** 2), noise=0).astype(np.int32)
     out = np.empty((n_frames, height, width), np.uint8)
+    offs = np.zeros((n_frames, 2), np.int32)
     ox, oy = pad, pad
     for t in range(n_frames):
         crop = scene[oy:oy + height, ox:ox + width] + rng.integers(-4, 5, size=(height, width))
         out[t] = np.clip(crop, 0, 255).astype(np.uint8)
+        offs[t] = (ox, oy)
         ox += int(rng.integers(-max_shift, max_shift + 1))
         oy += int(rng.integers(-max_shift // 2, max_shift // 2 + 1))
         ox = min(max(ox, 0), 2 * pad); oy = min(max(oy, 0), 2 * pad)
-    return out
+    return (out, offs) if return_offsets else out
+
+
+def make_last_frame_view(last_kps: np.ndarray, last_desc: np.ndarray, shift_xy, seed: int, K=KITTI_K,
+                         valid_frac: float = 0.85, obs_frac: float = 0.95, flip_bits: int = 6):
+    """Map points for SearchByProjection(cur, last): every last-frame keypoint gets a 3D point at a random
+    depth that, under the identity current pose, projects to the keypoint moved by `shift_xy` (+ sub-pixel
+    noise); the map-point descriptor is the keypoint's with a few bits flipped.
+    Returns flags (bit0 valid, bit1 has observations), Xw [n,3] float64, descriptors [n,32]."""
+    rng = np.random.default_rng(seed)
+    n = len(last_kps)
+    fx, fy, cx, cy = np.array(K, np.float32).astype(np.float64)
+    z = rng.uniform(5, 50, n)
+    u = last_kps["x"].astype(np.float64) + shift_xy[0] + rng.normal(0, 0.7, n)
+    v = last_kps["y"].astype(np.float64) + shift_xy[1] + rng.normal(0, 0.7, n)
+    xw = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    flags = (rng.random(n) < valid_frac).astype(np.uint8)
+    flags |= ((rng.random(n) < obs_frac).astype(np.uint8) << 1)
+    desc = last_desc.copy()
+    for _ in range(flip_bits):
+        byte = rng.integers(0, 32, n); bit = rng.integers(0, 8, n)
+        desc[np.arange(n), byte] ^= (1 << bit).astype(np.uint8)
+    return flags, xw, desc
 
 
 # ------------------------------------------------------------------------------------------------

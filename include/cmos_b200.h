@@ -123,6 +123,96 @@ int cmos_orb_last_launch_count(cmos_orb_t h, int32_t* n);
 int cmos_debug_sincos_deg(const float* deg, float* cos_out, float* sin_out, int32_t n);
 int cmos_debug_fast_atan2(const float* y, const float* x, float* out, int32_t n);
 
+/* ------------------------------------------------------------------------------------------------
+ * Path 1b: ORBmatcher  (replaces ORBmatcher::SearchByProjection x2 and the Frame grid they read;
+ * reference include/ORBmatcher.h:43-53, src/ORBmatcher.cc:42-126,1161-1271,1386-1437,
+ * src/Frame.cc:158-173,191-320).  Pointer graphs are flattened: a MapPoint* is an index,
+ * "F.map_points_[i] && F.map_points_[i]->Observations() > 0" is the per-keypoint `claimed` byte.
+ * Every array argument is batched: [n_frames][stride]...; with on_device != 0 all array pointers are device
+ * pointers, the call enqueues on `stream` and does not synchronise; with on_device == 0 they are host
+ * pointers and the call is synchronous.
+ * ---------------------------------------------------------------------------------------------- */
+
+#define CMOS_GRID_COLS 64   /* FRAME_GRID_COLS, Frame.h:46 */
+#define CMOS_GRID_ROWS 48   /* FRAME_GRID_ROWS, Frame.h:45 */
+#define CMOS_TH_HIGH 100    /* ORBmatcher::TH_HIGH, ORBmatcher.cc:35 */
+#define CMOS_TH_LOW 50      /* ORBmatcher::TH_LOW,  ORBmatcher.cc:36 */
+#define CMOS_HISTO_LENGTH 30
+
+/* The Frame statics a search reads (Frame.h:158-189): image bounds, grid pitch, intrinsics, scale table. */
+typedef struct {
+  float min_x, max_x, min_y, max_y;                         /* Frame::ComputeImageBounds, Frame.cc:357-385 */
+  float grid_element_width_inv, grid_element_height_inv;   /* Frame.cc:133-136 */
+  float fx, fy, cx, cy;                                     /* float32 like Frame.cc:138-141 */
+  int32_t nlevels;
+  float scale_factors[CMOS_MAX_LEVELS];
+  float log_scale_factor;                                   /* log(scaleFactor) as float, Frame.cc:110 */
+} cmos_camera;
+
+/* Fills `cam` for an undistorted width x height image (the k1 == 0 branch of ComputeImageBounds). */
+int cmos_camera_init(cmos_camera* cam, int32_t width, int32_t height, float fx, float fy, float cx, float cy,
+                     const float* scale_factors, int32_t nlevels, float scale_factor);
+
+typedef struct {
+  int32_t max_batch;       /* frames per call */
+  int32_t max_keypoints;   /* keypoints per frame (stride upper bound), <= 65535 */
+  int32_t max_points;      /* map points per frame for search_by_projection_points, <= 65535 */
+  int32_t device;
+} cmos_match_params;
+
+typedef struct cmos_match* cmos_match_t;
+
+int cmos_match_create(const cmos_match_params* params, cmos_match_t* out);
+int cmos_match_destroy(cmos_match_t h);
+
+/* Binds the current frames of the batch and runs Frame::AssignFeaturesToGrid (Frame.cc:158-173) for each:
+ *   keypoints [n_frames][stride] (undistort_keypoints_), descriptors [n_frames][stride][32], counts [n_frames].
+ * With on_device the handle keeps the pointers (they must stay valid until the searches have run). */
+int cmos_match_set_frames(cmos_match_t h, const cmos_camera* cam, const cmos_keypoint* keypoints,
+                          const uint8_t* descriptors, const int32_t* counts, int32_t n_frames, int32_t stride,
+                          int32_t on_device, void* stream);
+
+/* Verification tap: CSR grid of one frame, cell = ix*48+iy: grid_start[64*48+1], grid_idx[stride]. Host out. */
+int cmos_match_debug_grid(cmos_match_t h, int32_t frame, int32_t* grid_start, int32_t* grid_idx);
+
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th)  (ORBmatcher.cc:1161-1271)
+ *   Tcw          [n_frames][16]  row-major CurrentFrame.Tcw_ (double)
+ *   last_*       [n_frames][last_stride]...: keypoints (octave, angle read), counts, flags (bit0: map point
+ *                present and not outlier; bit1: that point has Observations() > 0), world position
+ *                [..][3] double, MapPoint::GetDescriptor() [..][32]
+ *   claimed      [n_frames][stride] in/out, may be NULL (= all zero, not returned)
+ *   match        [n_frames][stride] out: last-frame index assigned to each current keypoint, or -1
+ *   nmatches     [n_frames] out: the function's return value */
+int cmos_match_search_by_projection_frame(cmos_match_t h, const double* Tcw, const cmos_keypoint* last_keypoints,
+                                          const int32_t* last_counts, const uint8_t* last_flags,
+                                          const double* last_xw, const uint8_t* last_descriptors,
+                                          int32_t last_stride, float th, int32_t check_orientation,
+                                          uint8_t* claimed, int32_t* match, int32_t* nmatches, int32_t on_device,
+                                          void* stream);
+
+/* ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th)  (ORBmatcher.cc:42-119)
+ *   per point [n_frames][point_stride]: in_view (is_track_in_view_ && !isBad()), level (track_scale_level_),
+ *   view_cos, proj_xy [..][2], descriptors [..][32], has_obs (Observations() > 0); n_points [n_frames]
+ *   assign [n_frames][stride] out: point index newly written to F.map_points_[i], or -1 */
+int cmos_match_search_by_projection_points(cmos_match_t h, const int32_t* n_points, const uint8_t* in_view,
+                                           const int32_t* level, const float* view_cos, const float* proj_xy,
+                                           const uint8_t* descriptors, const uint8_t* has_obs,
+                                           int32_t point_stride, float th, float nn_ratio, uint8_t* claimed,
+                                           int32_t* assign, int32_t* nmatches, int32_t on_device, void* stream);
+
+/* Frame::isInFrustum + MapPoint::PredictScale for a batch of points (Frame.cc:191-241, MapPoint.cc:405-420).
+ *   pose15 [n_frames][15]: Rcw row-major (9), tcw (3), Ow (3), double;  per point: world position, normal
+ *   (double[3]), min/max distance (float, un-scaled: the 0.8 / 1.2 factors are applied inside).
+ *   Outputs feed cmos_match_search_by_projection_points. */
+int cmos_match_is_in_frustum(cmos_match_t h, const cmos_camera* cam, const double* pose15, float view_cos_limit,
+                             const int32_t* n_points, const double* xw, const double* normal,
+                             const float* min_distance, const float* max_distance, int32_t point_stride,
+                             int32_t n_frames, uint8_t* in_view, float* proj_xy, int32_t* level, float* view_cos,
+                             int32_t on_device, void* stream);
+
+/* Number of kernels launched by the last cmos_match_* call. */
+int cmos_match_last_launch_count(cmos_match_t h, int32_t* n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -195,3 +195,72 @@ def cv2_level_candidates(bordered: np.ndarray, ini_th=20, min_th=7):
             for kp in kps:
                 out.append((kp.pt[0] + j * w_cell, kp.pt[1] + i * h_cell, kp.response))
     return np.array(out, np.float32).reshape(-1, 3)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Matcher oracle (oracle/matcher_oracle.cpp)
+
+def build_grid(kps: np.ndarray, bounds6: np.ndarray):
+    kps = np.ascontiguousarray(kps)
+    gs = np.zeros(64 * 48 + 1, np.int32); gi = np.zeros(max(len(kps), 1), np.int32)
+    n = lib().match_oracle_build_grid(_p(kps), len(kps), C.c_float(bounds6[0]), C.c_float(bounds6[2]),
+                                      C.c_float(bounds6[4]), C.c_float(bounds6[5]), _p(gs), _p(gi))
+    return gs, gi[:n]
+
+
+def features_in_area(kps, gs, gi, bounds6, x, y, r, min_level, max_level):
+    kps = np.ascontiguousarray(kps); out = np.zeros(max(len(kps), 1), np.int32)
+    gi2 = np.ascontiguousarray(np.concatenate([gi, np.zeros(1, np.int32)]))
+    b = np.ascontiguousarray(bounds6, np.float32)
+    n = lib().match_oracle_features_in_area(_p(kps), len(kps), _p(gs), _p(gi2), _p(b), C.c_float(x), C.c_float(y),
+                                            C.c_float(r), int(min_level), int(max_level), _p(out))
+    return out[:n]
+
+
+def search_by_projection_frame(cur_kps, cur_desc, gs, gi, bounds6, K4, scale_factors, Tcw, last_kps, last_flags,
+                               last_xw, last_desc, th, check_ori, claimed=None):
+    cur_kps = np.ascontiguousarray(cur_kps); cur_desc = np.ascontiguousarray(cur_desc)
+    last_kps = np.ascontiguousarray(last_kps)
+    n = len(cur_kps)
+    gi2 = np.ascontiguousarray(np.concatenate([gi, np.zeros(1, np.int32)]))
+    claimed = np.zeros(max(n, 1), np.uint8) if claimed is None else claimed
+    match = np.full(max(n, 1), -1, np.int32)
+    b = np.ascontiguousarray(bounds6, np.float32); k = np.ascontiguousarray(K4, np.float32)
+    sf = np.ascontiguousarray(scale_factors, np.float32); T = np.ascontiguousarray(Tcw, np.float64)
+    lf = np.ascontiguousarray(last_flags, np.uint8); lx = np.ascontiguousarray(last_xw, np.float64)
+    ld = np.ascontiguousarray(last_desc, np.uint8)
+    fn = lib().match_oracle_search_by_projection_frame
+    nm = fn(_p(cur_kps), _p(cur_desc), n, _p(gs), _p(gi2), _p(b), _p(k), _p(sf), _p(T), _p(last_kps), len(last_kps),
+            _p(lf), _p(lx), _p(ld), C.c_float(th), int(check_ori), _p(claimed), _p(match))
+    return match[:n], nm, claimed[:n]
+
+
+def search_by_projection_points(kps, desc, gs, gi, bounds6, scale_factors, in_view, level, view_cos, proj_xy,
+                                mp_desc, has_obs, th, nn_ratio, claimed=None):
+    kps = np.ascontiguousarray(kps); desc = np.ascontiguousarray(desc)
+    n = len(kps)
+    gi2 = np.ascontiguousarray(np.concatenate([gi, np.zeros(1, np.int32)]))
+    claimed = np.zeros(max(n, 1), np.uint8) if claimed is None else claimed
+    assign = np.full(max(n, 1), -1, np.int32)
+    b = np.ascontiguousarray(bounds6, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    iv = np.ascontiguousarray(in_view, np.uint8); lv = np.ascontiguousarray(level, np.int32)
+    vc = np.ascontiguousarray(view_cos, np.float32); pj = np.ascontiguousarray(proj_xy, np.float32)
+    md = np.ascontiguousarray(mp_desc, np.uint8); ho = np.ascontiguousarray(has_obs, np.uint8)
+    fn = lib().match_oracle_search_by_projection_points
+    nm = fn(_p(kps), _p(desc), n, _p(gs), _p(gi2), _p(b), _p(sf), len(iv), _p(iv), _p(lv), _p(vc), _p(pj), _p(md),
+            _p(ho), C.c_float(th), C.c_float(nn_ratio), _p(claimed), _p(assign))
+    return assign[:n], nm, claimed[:n]
+
+
+def is_in_frustum(pose15, K4, bounds4, log_scale_factor, n_levels, cos_limit, xw, normal, min_dist, max_dist):
+    n = len(xw)
+    pose15 = np.ascontiguousarray(pose15, np.float64); k = np.ascontiguousarray(K4, np.float32)
+    b = np.ascontiguousarray(bounds4, np.float32)
+    xw = np.ascontiguousarray(xw, np.float64); normal = np.ascontiguousarray(normal, np.float64)
+    mn = np.ascontiguousarray(min_dist, np.float32); mx = np.ascontiguousarray(max_dist, np.float32)
+    in_view = np.zeros(n, np.uint8); proj = np.zeros((n, 2), np.float32)
+    level = np.zeros(n, np.int32); vcos = np.zeros(n, np.float32)
+    lib().match_oracle_is_in_frustum(_p(pose15), _p(k), _p(b), C.c_float(log_scale_factor), int(n_levels),
+                                     C.c_float(cos_limit), n, _p(xw), _p(normal), _p(mn), _p(mx), _p(in_view),
+                                     _p(proj), _p(level), _p(vcos))
+    return in_view, proj, level, vcos

@@ -1,0 +1,209 @@
+"""GPU parity tests of the matcher: Frame grid, both SearchByProjection variants and isInFrustum through the
+C ABI against the CPU oracle, index-exact.  Covers batches, pre-claimed keypoints, points without
+observations (re-claimable), the list-overflow path (many equally good candidates) and empty inputs."""
+import numpy as np
+import pytest
+
+from ceres_mono_orb_slam2_b200 import KP_DTYPE, Camera, ORBmatcher, synth
+from oracle import pyoracle as po
+from tests.matcher_scenarios import camera_arrays, extract_sequence, identity_T, points_view
+
+pytestmark = pytest.mark.gpu
+
+W, H, K = 1241, 376, synth.KITTI_K
+
+
+@pytest.fixture(scope="module")
+def seq():
+    frames, offs, ext, o = extract_sequence(W, H, 5, 2000, seed=77)
+    return offs, ext, o
+
+
+def _pack(ext, stride):
+    B = len(ext)
+    kps = np.zeros((B, stride), KP_DTYPE); desc = np.zeros((B, stride, 32), np.uint8); counts = np.zeros(B, np.int32)
+    for f, (k, d) in enumerate(ext):
+        kps[f, :len(k)] = k; desc[f, :len(k)] = d; counts[f] = len(k)
+    return kps, desc, counts
+
+
+def test_grid_matches_oracle(seq):
+    _, ext, o = seq
+    cam = Camera.create(W, H, K, o.scale_factors)
+    stride = 2024
+    kps, desc, counts = _pack(ext, stride)
+    m = ORBmatcher(0.9, True, max_batch=len(ext), max_keypoints=stride)
+    m.set_frames(cam, kps, desc, counts, len(ext), stride)
+    assert np.array_equal(cam.bounds6(), camera_arrays(W, H, K, o.scale_factors)[0])
+    for f in range(len(ext)):
+        gs, gi = m.debug_grid(f)
+        ogs, ogi = po.build_grid(ext[f][0], cam.bounds6())
+        assert np.array_equal(gs, ogs) and np.array_equal(gi, ogi), f"frame {f}"
+
+
+@pytest.mark.parametrize("check_ori,th", [(True, 15.0), (False, 15.0), (True, 30.0)])
+def test_search_by_projection_frame_batch(seq, check_ori, th):
+    offs, ext, o = seq
+    cam = Camera.create(W, H, K, o.scale_factors)
+    b, K4, sf = cam.bounds6(), cam.K4(), o.scale_factors
+    stride = 2024
+    B = len(ext) - 1
+    cur = ext[1:]; last = ext[:-1]
+    kps, desc, counts = _pack(cur, stride)
+    lkps, ldesc_kp, lcounts = _pack(last, stride)
+    flags = np.zeros((B, stride), np.uint8); xw = np.zeros((B, stride, 3)); mdesc = np.zeros((B, stride, 32), np.uint8)
+    T = np.tile(identity_T(), (B, 1))
+    claimed0 = np.zeros((B, stride), np.uint8)
+    rng = np.random.default_rng(4)
+    for f in range(B):
+        shift = (offs[f] - offs[f + 1]).astype(np.float64)
+        fl, x, md = synth.make_last_frame_view(last[f][0], last[f][1], shift, seed=100 + f, K=K)
+        n = len(fl)
+        flags[f, :n] = fl; xw[f, :n] = x; mdesc[f, :n] = md
+        claimed0[f, :counts[f]] = rng.random(counts[f]) < 0.05      # some keypoints already hold a point
+        # a small camera motion so the fp64 projection is not the identity
+        T[f] = np.array([[1, 0.001 * f, 0, 0.01], [-0.001 * f, 1, 0, -0.02], [0, 0, 1, 0.03], [0, 0, 0, 1]]).reshape(-1)
+    m = ORBmatcher(0.9, check_ori, max_batch=B, max_keypoints=stride)
+    m.set_frames(cam, kps, desc, counts, B, stride)
+    claimed = claimed0.copy()
+    match, nm = m.SearchByProjectionFrame(T, lkps, lcounts, flags, xw, mdesc, stride, th, claimed=claimed)
+    total = 0
+    for f in range(B):
+        ck, cd = cur[f]
+        gs, gi = po.build_grid(ck, b)
+        om, onm, ocl = po.search_by_projection_frame(ck, cd, gs, gi, b, K4, sf, T[f], last[f][0], flags[f, :lcounts[f]],
+                                                     xw[f, :lcounts[f]], mdesc[f, :lcounts[f]], th, check_ori,
+                                                     claimed=claimed0[f, :counts[f]].copy())
+        assert nm[f] == onm, f"frame {f}: nmatches {nm[f]} vs {onm}"
+        bad = np.nonzero(match[f, :counts[f]] != om)[0]
+        assert bad.size == 0, f"frame {f}: {bad.size} keypoints differ, first {bad[:5]}"
+        assert (match[f, counts[f]:] == -1).all()
+        assert np.array_equal(claimed[f, :counts[f]], ocl)
+        total += onm
+    assert total > 300 * B
+
+
+def test_search_frame_overflow_and_reclaim():
+    """All descriptors identical: every window candidate ties at distance 0, lists overflow, first candidate in
+    grid order must win; points without observations do not block later queries."""
+    rng = np.random.default_rng(8)
+    n = 1500
+    kps = np.zeros(n, KP_DTYPE)
+    kps["x"] = rng.uniform(20, W - 20, n).astype(np.float32); kps["y"] = rng.uniform(20, H - 20, n).astype(np.float32)
+    kps["octave"] = rng.integers(0, 3, n); kps["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    desc = np.zeros((n, 32), np.uint8)
+    o = po.OrbOracle(2000, 1.2, 8, 20, 7)
+    cam = Camera.create(W, H, K, o.scale_factors)
+    flags = np.where(rng.random(n) < 0.5, 3, 1).astype(np.uint8)       # half the points have no observations
+    xw = np.zeros((n, 3)); z = rng.uniform(5, 30, n)
+    fx, fy, cx, cy = [float(np.float32(v)) for v in K]
+    xw[:, 0] = (kps["x"] - cx) / fx * z; xw[:, 1] = (kps["y"] - cy) / fy * z; xw[:, 2] = z
+    T = identity_T()[None]
+    m = ORBmatcher(0.9, True, max_batch=1, max_keypoints=n)
+    m.set_frames(cam, kps[None], desc[None], np.array([n], np.int32), 1, n)
+    match, nm = m.SearchByProjectionFrame(T, kps[None], np.array([n], np.int32), flags[None], xw[None], desc[None], n, 30.0)
+    gs, gi = po.build_grid(kps, cam.bounds6())
+    om, onm, _ = po.search_by_projection_frame(kps, desc, gs, gi, cam.bounds6(), cam.K4(), o.scale_factors, T[0], kps,
+                                               flags, xw, desc, 30.0, True)
+    assert nm[0] == onm and np.array_equal(match[0], om)
+
+
+@pytest.mark.parametrize("th,ratio", [(1.0, 0.8), (5.0, 0.8), (3.0, 0.6)])
+def test_search_by_projection_points_batch(seq, th, ratio):
+    offs, ext, o = seq
+    cam = Camera.create(W, H, K, o.scale_factors)
+    b, sf = cam.bounds6(), o.scale_factors
+    stride, pstride = 2024, 2100
+    B = len(ext) - 1
+    cur = ext[1:]; last = ext[:-1]
+    kps, desc, counts = _pack(cur, stride)
+    npts = np.zeros(B, np.int32)
+    in_view = np.zeros((B, pstride), np.uint8); level = np.zeros((B, pstride), np.int32)
+    vcos = np.zeros((B, pstride), np.float32); proj = np.zeros((B, pstride, 2), np.float32)
+    mdesc = np.zeros((B, pstride, 32), np.uint8); has_obs = np.zeros((B, pstride), np.uint8)
+    views = []
+    for f in range(B):
+        shift = (offs[f] - offs[f + 1]).astype(np.float64)
+        v = points_view(last[f][0], last[f][1], shift, seed=50 + f, th_noise=1.0 if th == 1.0 else 3.0)
+        n = len(v[0]); npts[f] = n
+        in_view[f, :n], level[f, :n], vcos[f, :n], proj[f, :n], mdesc[f, :n], has_obs[f, :n] = v
+        views.append(v)
+    m = ORBmatcher(ratio, True, max_batch=B, max_keypoints=stride, max_points=pstride)
+    m.set_frames(cam, kps, desc, counts, B, stride)
+    claimed = np.zeros((B, stride), np.uint8)
+    assign, nm = m.SearchByProjectionPoints(npts, in_view, level, vcos, proj, mdesc, has_obs, pstride, th, claimed=claimed)
+    total = 0
+    for f in range(B):
+        ck, cd = cur[f]
+        gs, gi = po.build_grid(ck, b)
+        oa, onm, ocl = po.search_by_projection_points(ck, cd, gs, gi, b, sf, *views[f], th, ratio)
+        assert nm[f] == onm, f"frame {f}: {nm[f]} vs {onm}"
+        bad = np.nonzero(assign[f, :counts[f]] != oa)[0]
+        assert bad.size == 0, f"frame {f}: {bad.size} differ, first {bad[:5]}"
+        assert np.array_equal(claimed[f, :counts[f]], ocl)
+        total += onm
+    assert total > 100 * B
+
+
+def test_search_points_overflow_ties():
+    rng = np.random.default_rng(12)
+    n = 1200
+    kps = np.zeros(n, KP_DTYPE)
+    kps["x"] = rng.uniform(20, W - 20, n).astype(np.float32); kps["y"] = rng.uniform(20, H - 20, n).astype(np.float32)
+    kps["octave"] = rng.integers(0, 2, n)
+    desc = rng.integers(0, 2, (n, 32)).astype(np.uint8)          # distances are small and tie often
+    o = po.OrbOracle(2000, 1.2, 8, 20, 7)
+    cam = Camera.create(W, H, K, o.scale_factors)
+    npnt = 900
+    in_view = np.ones(npnt, np.uint8); level = rng.integers(0, 2, npnt).astype(np.int32)
+    vcos = rng.uniform(0.99, 1, npnt).astype(np.float32)
+    proj = np.stack([rng.uniform(0, W, npnt), rng.uniform(0, H, npnt)], 1).astype(np.float32)
+    mdesc = rng.integers(0, 2, (npnt, 32)).astype(np.uint8); has_obs = (rng.random(npnt) < 0.7).astype(np.uint8)
+    m = ORBmatcher(0.8, True, max_batch=1, max_keypoints=n, max_points=npnt)
+    m.set_frames(cam, kps[None], desc[None], np.array([n], np.int32), 1, n)
+    assign, nm = m.SearchByProjectionPoints(np.array([npnt], np.int32), in_view[None], level[None], vcos[None], proj[None],
+                                            mdesc[None], has_obs[None], npnt, 25.0)
+    gs, gi = po.build_grid(kps, cam.bounds6())
+    oa, onm, _ = po.search_by_projection_points(kps, desc, gs, gi, cam.bounds6(), o.scale_factors, in_view, level, vcos,
+                                                proj, mdesc, has_obs, 25.0, 0.8)
+    assert nm[0] == onm and np.array_equal(assign[0], oa)
+
+
+def test_empty_inputs():
+    o = po.OrbOracle(2000, 1.2, 8, 20, 7)
+    cam = Camera.create(W, H, K, o.scale_factors)
+    n = 64
+    kps = np.zeros((1, n), KP_DTYPE); desc = np.zeros((1, n, 32), np.uint8)
+    m = ORBmatcher(0.9, True, max_batch=1, max_keypoints=n, max_points=n)
+    m.set_frames(cam, kps, desc, np.zeros(1, np.int32), 1, n)             # frame without keypoints
+    match, nm = m.SearchByProjectionFrame(identity_T()[None], kps, np.zeros(1, np.int32), np.zeros((1, n), np.uint8),
+                                          np.zeros((1, n, 3)), desc, n, 15.0)
+    assert nm[0] == 0 and (match == -1).all()
+    assign, nm = m.SearchByProjectionPoints(np.zeros(1, np.int32), np.zeros((1, n), np.uint8), np.zeros((1, n), np.int32),
+                                            np.zeros((1, n), np.float32), np.zeros((1, n, 2), np.float32), desc,
+                                            np.zeros((1, n), np.uint8), n, 3.0)
+    assert nm[0] == 0 and (assign == -1).all()
+
+
+def test_is_in_frustum(seq):
+    _, ext, o = seq
+    cam = Camera.create(W, H, K, o.scale_factors)
+    rng = np.random.default_rng(3)
+    n = 3000
+    pose7 = np.concatenate([rng.normal(0, 0.2, 3), synth.quat_from_rotvec(rng.normal(0, 0.05, 3))])
+    R = synth.quat_to_R(pose7[3:]); t = pose7[:3]; Ow = -R.T @ t
+    pose15 = np.concatenate([R.reshape(-1), t, Ow])
+    xw = rng.uniform([-30, -10, -5], [30, 10, 60], (n, 3))
+    normal = -xw / np.linalg.norm(xw, axis=1, keepdims=True) + rng.normal(0, 0.3, (n, 3))
+    normal /= np.linalg.norm(normal, axis=1, keepdims=True)
+    d = np.linalg.norm(xw - Ow, axis=1)
+    min_d = (d * rng.uniform(0.3, 1.3, n)).astype(np.float32); max_d = (min_d * rng.uniform(1.5, 4.0, n)).astype(np.float32)
+    m = ORBmatcher(0.8, True, max_batch=1, max_keypoints=64, max_points=n)
+    iv, pj, lv, vc = m.IsInFrustum(cam, pose15[None], 0.5, np.array([n], np.int32), xw[None], normal[None], min_d[None],
+                                   max_d[None], n, 1)
+    oiv, opj, olv, ovc = po.is_in_frustum(pose15, cam.K4(), cam.bounds6()[:4], cam.log_scale_factor, 8, 0.5, xw, normal,
+                                          min_d, max_d)
+    assert 100 < oiv.sum() < n
+    assert np.array_equal(iv[0], oiv)
+    sel = oiv.astype(bool)
+    assert np.array_equal(pj[0][sel], opj[sel]) and np.array_equal(lv[0][sel], olv[sel]) and np.array_equal(vc[0][sel], ovc[sel])
