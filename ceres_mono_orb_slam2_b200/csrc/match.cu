@@ -25,7 +25,7 @@ namespace cmos {
 constexpr int kCols = CMOS_GRID_COLS, kRows = CMOS_GRID_ROWS, kCells = kCols * kRows;
 constexpr int kSearchThreads = 1024;
 constexpr int kListCap = 8;        // candidates kept per query for the sequential replay (overflow -> re-enumerate)
-constexpr int kListCapPts = 16;
+constexpr int kListCapPts = 8;
 
 struct FrameDev {                 // one current frame on the device
   const cmos_keypoint* kps;
@@ -621,9 +621,8 @@ int cmos_match_create(const cmos_match_params* params, cmos_match_t* out) {
   }
   CMOS_REQUIRE(params->device >= 0 && params->device < ndev, "device %d out of range", params->device);
   CMOS_CUDA_OK(cudaSetDevice(params->device));
-  if (search_frame_smem(params->max_keypoints, params->max_keypoints) > 220 * 1024 ||
-      search_points_smem(std::max(params->max_points, 1), params->max_keypoints) > 220 * 1024) {
-    set_error("max_keypoints/max_points too large for the search kernels' shared memory");
+  if (search_frame_smem(params->max_keypoints, params->max_keypoints) > 220 * 1024) {
+    set_error("max_keypoints too large for the search kernels' shared memory");
     return CMOS_ERR_ARG;
   }
   cmos_match* h = new cmos_match();
@@ -786,6 +785,8 @@ int cmos_match_search_by_projection_points(cmos_match_t h, const int32_t* n_poin
   CMOS_REQUIRE(point_stride >= 1 && point_stride <= h->p.max_points, "point_stride %d outside 1..%d", point_stride,
                h->p.max_points);
   CMOS_REQUIRE(nn_ratio > 0.f, "nn_ratio must be positive");
+  CMOS_REQUIRE(search_points_smem(point_stride, h->stride) <= 220 * 1024,
+               "point_stride %d x stride %d exceeds the search kernel's shared memory", point_stride, h->stride);
   CMOS_CUDA_OK(cudaSetDevice(h->p.device));
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   const int B = h->n_frames;

@@ -194,7 +194,7 @@ def test_is_in_frustum(seq):
     R = synth.quat_to_R(pose7[3:]); t = pose7[:3]; Ow = -R.T @ t
     pose15 = np.concatenate([R.reshape(-1), t, Ow])
     xw = rng.uniform([-30, -10, -5], [30, 10, 60], (n, 3))
-    normal = -xw / np.linalg.norm(xw, axis=1, keepdims=True) + rng.normal(0, 0.3, (n, 3))
+    normal = (xw - Ow) / np.linalg.norm(xw - Ow, axis=1, keepdims=True) + rng.normal(0, 0.5, (n, 3))
     normal /= np.linalg.norm(normal, axis=1, keepdims=True)
     d = np.linalg.norm(xw - Ow, axis=1)
     min_d = (d * rng.uniform(0.3, 1.3, n)).astype(np.float32); max_d = (min_d * rng.uniform(1.5, 4.0, n)).astype(np.float32)
