@@ -1,0 +1,467 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native ORB front-end (+ bundle adjustment) engine.
+
+Metric (BASELINE.json): ORB Mfeat/s at 1241x376 — keypoints returned by ORBextractor::operator() and then
+matched with ORBmatcher::SearchByProjection(cur, last, th=15) per second, on the KITTI00-02 configuration
+(2000 features, 8 levels, scale 1.2), a batch of 64 synthetic frames per GPU.  A "step" is one pass of
+extract + grid + match over one 64-frame batch.  LocalBA / PoseOptimization / GlobalBA numbers are added
+under the "ba" key (M residual-Jacobian evaluations per second).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the CPU restatement of the reference path on the host cores
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 1241, 376, 2000, 8, 1.2, 20, 7
+TH_PROJ = 15.0
+METRIC = "orb_extract_match_mfeat_per_s_1241x376"
+UNIT = "Mfeat/s"
+
+
+# ----------------------------------------------------------------------------------------------------
+# Workload (shared by both arms)
+
+def level_sizes():
+    sf = np.empty(NLEVELS, np.float32); sf[0] = 1.0
+    for i in range(1, NLEVELS):
+        sf[i] = np.float32(np.float64(sf[i - 1]) * np.float64(SCALE))
+    inv = (np.float32(1.0) / sf).astype(np.float32)
+    return [(int(np.rint(np.float32(W) * s)), int(np.rint(np.float32(H) * s))) for s in inv]
+
+
+def algorithmic_bytes_per_frame(n_feat: float):
+    """Per-frame algorithmic bytes of every kernel stage."""
+    px = [w * h for w, h in level_sizes()]
+    p_all, p0 = sum(px), px[0]
+    return {
+        "pyramid": p0 + p_all + sum(px[:-1]),          # read input, write every level, read every source level
+        "fast": p_all,                                 # every level read once (candidates are intermediates)
+        "quadtree": 0,                                 # works on intermediates only
+        "blur": 2 * p_all,                             # read level, write blurred level
+        "describe": n_feat * (2 * 31 * 31 + 60),       # 31x31 patch of level + blurred level, 32 B desc + 28 B keypoint
+        "grid": n_feat * (8 + 4),                      # x,y read, index written
+        "search_frame": n_feat * 104,                  # SURVEY.md §8d B_match
+        "frame_total": p0 + 2 * (p_all - p0) + n_feat * 60 + n_feat * 104,   # SURVEY.md §8d B_frame
+    }
+
+
+def make_batch(batch: int, seed: int):
+    from ceres_mono_orb_slam2_b200 import synth
+    return synth.make_sequence(W, H, batch, seed, return_offsets=True)
+
+
+def make_last_views(kps, desc, counts, offs, cap, seed):
+    """Ring pairing: current frame f is matched against last = (f-1) mod B."""
+    from ceres_mono_orb_slam2_b200 import KP_DTYPE, synth
+    B = len(counts)
+    lk = np.zeros((B, cap), KP_DTYPE); lcounts = np.zeros(B, np.int32)
+    flags = np.zeros((B, cap), np.uint8); xw = np.zeros((B, cap, 3)); mdesc = np.zeros((B, cap, 32), np.uint8)
+    T = np.tile(np.eye(4).reshape(-1), (B, 1))
+    for f in range(B):
+        l = (f - 1) % B
+        n = int(counts[l])
+        shift = (offs[l] - offs[f]).astype(np.float64)
+        fl, x, md = synth.make_last_frame_view(kps[l, :n], desc[l, :n], shift, seed=seed + f)
+        lk[f, :n] = kps[l, :n]; lcounts[f] = n
+        flags[f, :n] = fl; xw[f, :n] = x; mdesc[f, :n] = md
+        T[f] = np.array([[1, 1e-4 * (f % 7), 0, 0.002], [-1e-4 * (f % 7), 1, 0, -0.001], [0, 0, 1, 0.004],
+                         [0, 0, 0, 1]]).reshape(-1)
+    return lk, lcounts, flags, xw, mdesc, T
+
+
+# ----------------------------------------------------------------------------------------------------
+# Clock sampling during the timed region
+
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []      # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        self._nv = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._dev = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._dev, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+
+    def _run(self):
+        nv = self._nv
+        if nv is None:
+            self._run_smi()
+            return
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self._dev, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self._dev)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._dev)
+                self.samples.append((mhz, int(rs)))
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def _run_smi(self):
+        import subprocess
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.max_mhz = int(f[1])
+                mask = 0
+                for bit, v in zip((0x8, 0x40, 0x20, 0x4), f[2:6]):
+                    if v.lower().startswith("active"):
+                        mask |= bit
+                self.samples.append((int(f[0]), mask))
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=6)
+        names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+        reasons = set()
+        for _, m in self.samples:
+            for bit, nm in names.items():
+                if m & bit:
+                    reasons.add(nm)
+        mhz = [s for s, _ in self.samples]
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(mhz),
+                "source": "nvml" if self._nv is not None else "nvidia-smi"}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the restated reference path (oracle/) on the host cores
+
+def cpu_orb_throughput(n_frames: int, threads: int, seed: int, repeats: int = 1):
+    """Extract + SearchByProjection(cur,last) of `n_frames` frames with the CPU oracle, `threads` frames in
+    flight.  Returns (Mfeat/s, seconds per pass, features per pass)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as po
+    from ceres_mono_orb_slam2_b200 import synth
+    frames, offs = make_batch(n_frames, seed)
+    oracles = [po.OrbOracle(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH) for _ in range(threads)]
+    sfs = oracles[0].scale_factors
+    bounds6 = np.array([0.0, W, 0.0, H, np.float32(64) / np.float32(W), np.float32(48) / np.float32(H)], np.float32)
+    K4 = np.array(synth.KITTI_K, np.float32)
+    # map-point views are inputs, prepared outside the timed region from a first extraction
+    with ThreadPoolExecutor(threads) as ex0:
+        ext0 = [r for part in ex0.map(lambda t: [(f, oracles[t].extract(frames[f])) for f in range(t, n_frames, threads)],
+                                      range(threads)) for r in part]
+    ext0 = [r for _, r in sorted(ext0, key=lambda a: a[0])]
+    views = []
+    for f in range(n_frames):
+        l = (f - 1) % n_frames
+        shift = (offs[l] - offs[f]).astype(np.float64)
+        views.append(synth.make_last_frame_view(ext0[l][0], ext0[l][1], shift, seed=seed + f))
+    T = np.eye(4).reshape(-1)
+
+    def work(tid):
+        o = oracles[tid]
+        feats = 0
+        for f in range(tid, n_frames, threads):
+            k, d = o.extract(frames[f])
+            gs, gi = po.build_grid(k, bounds6)
+            l = (f - 1) % n_frames
+            fl, xw, md = views[f]
+            po.search_by_projection_frame(k, d, gs, gi, bounds6, K4, sfs, T, ext0[l][0], fl, xw, md, TH_PROJ, True)
+            feats += len(k)
+        return feats
+
+    best = None
+    feats = 0
+    with ThreadPoolExecutor(threads) as ex:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            feats = sum(ex.map(work, range(threads)))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return feats / best / 1e6, best, feats
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__ as ge
+    ge.build_oracle()
+    cores = os.cpu_count() or 1
+    sample = max(cores, 8)
+    for _ in range(max(args.warmup, 0)):
+        cpu_orb_throughput(min(sample, cores), cores, seed=1000)
+        break     # one warm-up pass is enough for a CPU loop (page-in, thread pool)
+    t_total, feats_total = 0.0, 0
+    for _ in range(args.steps):
+        _, dt, feats = cpu_orb_throughput(sample, cores, seed=1000)
+        t_total += dt; feats_total += feats
+    value = feats_total / t_total / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "configs[1]: ORB extract + SearchByProjection(cur,last,th=15), KITTI00-02 "
+                               "(1241x376, 2000 feat, 8 levels)",
+                   "step": f"bounded sample: {sample} frames of the 64-frame batch per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} frames x {args.steps} steps, {cores} threads (one frame per thread)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference's own C++ (OpenCV + Ceres) cannot be built in this image; this arm times the CPU "
+                "restatement in oracle/ (bit-identical to OpenCV 4.13 semantics)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from ceres_mono_orb_slam2_b200 import KP_DTYPE, Camera, ORBextractor, ORBmatcher, synth
+
+    B = args.batch
+    frames, offs = make_batch(B, seed=1000 + 64 * rank)
+    ext = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, max_batch=B,
+                       device=local_rank)
+    cap = ext.capacity
+    matcher = ORBmatcher(0.9, True, max_batch=B, max_keypoints=cap, max_points=1, device=local_rank)
+    cam = Camera.create(W, H, synth.KITTI_K, ext.GetScaleFactors(), SCALE)
+
+    # ---- untimed pre-pass: one extraction gives the last-frame views (map points) the matcher consumes ----
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+    h_images = pin((B, H, W), torch.uint8); h_images.numpy()[:] = frames
+    h_kps_u8 = pin((B, cap * 28), torch.uint8); h_desc = pin((B, cap, 32), torch.uint8)
+    h_counts = pin((B,), torch.int32)
+    h_kps = h_kps_u8.numpy().view(KP_DTYPE).reshape(B, cap)
+    out_bufs = (h_kps, h_desc.numpy(), h_counts.numpy())
+    kps, desc, counts = ext.extract_batch(h_images.numpy(), out=out_bufs)
+    feats_per_step = int(counts.sum())
+    lk, lcounts, flags, xw, mdesc, T = make_last_views(kps, desc, counts, offs, cap, seed=5000 + 64 * rank)
+    h_flags = pin((B, cap), torch.uint8); h_flags.numpy()[:] = flags
+    h_xw = pin((B, cap, 3), torch.float64); h_xw.numpy()[:] = xw
+    h_mdesc = pin((B, cap, 32), torch.uint8); h_mdesc.numpy()[:] = mdesc
+    h_T = pin((B, 16), torch.float64); h_T.numpy()[:] = T
+    h_match = pin((B, cap), torch.int32); h_nm = pin((B,), torch.int32)
+
+    d_images = h_images.to(dev)
+    d_lk = torch.from_numpy(lk.view(np.uint8).reshape(B, cap * 28)).to(dev)
+    d_lcounts = torch.from_numpy(lcounts).to(dev)
+    d_flags = h_flags.to(dev); d_xw = h_xw.to(dev); d_mdesc = h_mdesc.to(dev); d_T = h_T.to(dev)
+    d_match = torch.empty((B, cap), dtype=torch.int32, device=dev)
+    d_nm = torch.empty((B,), dtype=torch.int32, device=dev)
+
+    stream = torch.cuda.Stream(device=dev)
+    sp = stream.cuda_stream
+    kp_ptr, desc_ptr, cnt_ptr, _, _ = ext.device_results()
+
+    def step_device():
+        ext.extract_device(d_images, H * W, W, W, H, B, stream=sp)
+        matcher.set_frames(cam, kp_ptr, desc_ptr, cnt_ptr, B, cap, on_device=True, stream=sp)
+        matcher.SearchByProjectionFrame(d_T, d_lk, d_lcounts, d_flags, d_xw, d_mdesc, cap, TH_PROJ, claimed=None,
+                                        out=(d_match, d_nm), on_device=True, stream=sp)
+
+    def step_e2e():
+        # host images in, host keypoints/descriptors/matches out; the map-point views come from host memory too
+        ext.extract_batch(h_images.numpy(), out=out_bufs)                       # H2D images, D2H kps/desc/counts
+        with torch.cuda.stream(stream):
+            d_flags.copy_(h_flags, non_blocking=True); d_xw.copy_(h_xw, non_blocking=True)
+            d_mdesc.copy_(h_mdesc, non_blocking=True); d_T.copy_(h_T, non_blocking=True)
+        matcher.set_frames(cam, kp_ptr, desc_ptr, cnt_ptr, B, cap, on_device=True, stream=sp)
+        matcher.SearchByProjectionFrame(d_T, d_lk, d_lcounts, d_flags, d_xw, d_mdesc, cap, TH_PROJ, claimed=None,
+                                        out=(d_match, d_nm), on_device=True, stream=sp)
+        with torch.cuda.stream(stream):
+            h_match.copy_(d_match, non_blocking=True); h_nm.copy_(d_nm, non_blocking=True)
+        stream.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")
+    nvml_index = int(vis[local_rank]) if local_rank < len(vis) and vis[local_rank].strip().isdigit() else local_rank
+    sampler = ClockSampler(nvml_index)
+    sampler.start()
+
+    # ---- device-resident timing ----
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    ext.set_profiling(True); matcher.set_profiling(True)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    orb_ms, orb_calls = ext.stage_times()
+    match_ms = matcher.stage_times()
+    ext.set_profiling(False); matcher.set_profiling(False)
+    nm_device = int(d_nm.sum().item())
+    counts_dev = np.zeros(B, np.int32)
+    ext.download(B, out=(None, None, counts_dev))
+    assert int(counts_dev.sum()) == feats_per_step, "extraction is not deterministic across steps"
+
+    # ---- end to end through the host-buffer C ABI ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    assert int(h_nm.sum().item()) == nm_device, "host-buffer path and device path disagree on the matches"
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    tot = torch.tensor([feats_per_step], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    feats_all = float(tot[0])
+    value = feats_all * args.steps / (ms_max * 1e-3) / 1e6
+    e2e_value = feats_all * args.steps / (e2e_ms_max * 1e-3) / 1e6
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        alg = algorithmic_bytes_per_frame(feats_per_step / B)
+        stage_avg = {k: v / max(orb_calls, 1) for k, v in orb_ms.items()}
+        for k, (v, c) in match_ms.items():
+            if c:
+                stage_avg[k] = v / c
+        dom = max(stage_avg, key=stage_avg.get)
+        dom_ms = stage_avg[dom]
+        achieved = alg[dom] * B / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        except Exception:
+            pass
+        step_ms = ms_max / args.steps
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: ORB extract + SearchByProjection(cur,last,th=15), KITTI00-02 "
+                                   "(1241x376, 2000 feat, 8 levels, scale 1.2), 64 synthetic frames per GPU",
+                       "batch_per_gpu": B, "features_per_step_per_gpu": feats_per_step,
+                       "matches_per_step_rank0": nm_device,
+                       "l2": "no explicit flush: one step touches ~%d MB (images + pyramid + blurred pyramid) > 126 MB L2"
+                             % ((B * (H * W) + 2 * B * 1738559) // 1000000),
+                       "parallelism": f"frames sharded, {world} rank(s), no collective on the data path"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg[dom] * B, "kernel_ms": dom_ms,
+                         "stage_ms": stage_avg, "stage_share": {k: v / step_ms for k, v in stage_avg.items()},
+                         "whole_step": {"algorithmic_bytes": alg["frame_total"] * B,
+                                        "achieved": alg["frame_total"] * B / (step_ms * 1e-3) / 1e9,
+                                        "frac": alg["frame_total"] * B / (step_ms * 1e-3) / 1e9 / peak}},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(h_images.numel() + h_flags.numel() + h_xw.numel() * 8 +
+                                              h_mdesc.numel() + h_T.numel() * 8),
+                    "d2h_bytes_per_step": int(h_kps_u8.numel() + h_desc.numel() + h_counts.numel() * 4 +
+                                              h_match.numel() * 4 + h_nm.numel() * 4),
+                    "ms_per_step": e2e_ms_max / args.steps},
+            "gpu_launches": (ext.launch_count() + 2) * args.steps,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            import __graft_entry__ as ge
+            ge.build_oracle()
+            cores = os.cpu_count() or 1
+            n_s = max(cores, 8)
+            v, dt, _ = cpu_orb_throughput(n_s, cores, seed=1000, repeats=2)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n_s} frames of the same workload, {cores} threads, best of 2 "
+                                              f"({dt:.2f} s per pass)"}
+        if not args.no_ba:
+            try:
+                from ceres_mono_orb_slam2_b200 import ba_bench
+                line["ba"] = ba_bench.run(local_rank, world, args)
+            except ImportError:
+                pass
+        print(json.dumps(line), flush=True)
+    elif not args.no_ba:
+        try:
+            from ceres_mono_orb_slam2_b200 import ba_bench
+            ba_bench.run(local_rank, world, args)
+        except ImportError:
+            pass
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ba", action="store_true", help="skip the bundle-adjustment section")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

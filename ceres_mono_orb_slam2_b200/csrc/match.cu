@@ -572,6 +572,7 @@ struct cmos_match {
   uint8_t *s_in_view = nullptr, *s_pdesc = nullptr, *s_has_obs = nullptr;
   float *s_view_cos = nullptr, *s_proj = nullptr, *s_mind = nullptr, *s_maxd = nullptr;
   double *s_pxw = nullptr, *s_pnormal = nullptr, *s_pose = nullptr;
+  StageTimer timer[4];   // 0 grid, 1 search(frame,last), 2 search(frame,points), 3 isInFrustum
 };
 
 namespace {
@@ -679,6 +680,7 @@ int cmos_match_destroy(cmos_match_t h) {
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (h->stream) cudaStreamDestroy(h->stream);
+  for (StageTimer& t : h->timer) t.destroy();
   delete h;
   return CMOS_OK;
 }
@@ -706,8 +708,10 @@ int cmos_match_set_frames(cmos_match_t h, const cmos_camera* cam, const cmos_key
   h->n_frames = n_frames;
   h->stride = stride;
   const size_t smem = (kCells + 1) * sizeof(int) + (size_t)stride * sizeof(short) + 16;
+  h->timer[0].begin(st);
   k_build_grid<<<n_frames, 256, smem, st>>>(h->cam, h->kps, h->counts, stride, h->p.max_keypoints, h->d_grid_start,
                                             h->d_grid_idx);
+  h->timer[0].mark(st);
   CMOS_CUDA_OK(cudaGetLastError());
   h->launches = 1;
   h->bound = true;
@@ -760,8 +764,10 @@ int cmos_match_search_by_projection_frame(cmos_match_t h, const double* Tcw, con
     a.last_xw = h->s_last_xw; a.last_desc = h->s_last_desc; a.claimed = claimed ? h->s_claimed : nullptr;
     a.match = h->s_match; a.nmatches = h->s_nmatches;
   }
+  h->timer[1].begin(st);
   k_search_frame<<<B, kSearchThreads, search_frame_smem(last_stride, h->stride), st>>>(
       h->cam, h->kps, h->desc, h->counts, h->stride, h->d_grid_start, h->d_grid_idx, h->p.max_keypoints, a);
+  h->timer[1].mark(st);
   CMOS_CUDA_OK(cudaGetLastError());
   h->launches = 1;
   if (!on_device) {
@@ -813,8 +819,10 @@ int cmos_match_search_by_projection_points(cmos_match_t h, const int32_t* n_poin
     a.proj_xy = h->s_proj; a.desc = h->s_pdesc; a.has_obs = h->s_has_obs;
     a.claimed = claimed ? h->s_claimed : nullptr; a.assign = h->s_match; a.nmatches = h->s_nmatches;
   }
+  h->timer[2].begin(st);
   k_search_points<<<B, kSearchThreads, search_points_smem(point_stride, h->stride), st>>>(
       h->cam, h->kps, h->desc, h->counts, h->stride, h->d_grid_start, h->d_grid_idx, h->p.max_keypoints, a);
+  h->timer[2].mark(st);
   CMOS_CUDA_OK(cudaGetLastError());
   h->launches = 1;
   if (!on_device) {
@@ -855,9 +863,11 @@ int cmos_match_is_in_frustum(cmos_match_t h, const cmos_camera* cam, const doubl
     d_pose = h->s_pose; d_np = h->s_np; d_xw = h->s_pxw; d_n = h->s_pnormal; d_min = h->s_mind; d_max = h->s_maxd;
     o_view = h->s_in_view; o_proj = h->s_proj; o_level = h->s_level; o_cos = h->s_view_cos;
   }
+  h->timer[3].begin(st);
   k_in_frustum<<<dim3((point_stride + 255) / 256, n_frames), 256, 0, st>>>(*cam, d_pose, view_cos_limit, d_np, d_xw, d_n,
                                                                         d_min, d_max, point_stride, o_view, o_proj,
                                                                         o_level, o_cos);
+  h->timer[3].mark(st);
   CMOS_CUDA_OK(cudaGetLastError());
   h->launches = 1;
   if (!on_device) {
@@ -867,6 +877,24 @@ int cmos_match_is_in_frustum(cmos_match_t h, const cmos_camera* cam, const doubl
     if ((rc = d2h(level, h->s_level, np, st))) return rc;
     if ((rc = d2h(view_cos, h->s_view_cos, np, st))) return rc;
     CMOS_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return CMOS_OK;
+}
+
+int cmos_match_set_profiling(cmos_match_t h, int32_t enable) {
+  CMOS_REQUIRE(h, "null handle");
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  for (StageTimer& t : h->timer) { t.reset(); t.enabled = enable != 0; }
+  return CMOS_OK;
+}
+
+int cmos_match_stage_times(cmos_match_t h, double* ms, int64_t* calls) {
+  CMOS_REQUIRE(h && ms && calls, "null argument");
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  for (int i = 0; i < 4; i++) {
+    h->timer[i].fold();
+    ms[i] = h->timer[i].total_ms[0];
+    calls[i] = h->timer[i].calls;
   }
   return CMOS_OK;
 }

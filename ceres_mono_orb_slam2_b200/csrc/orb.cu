@@ -677,6 +677,7 @@ struct cmos_orb {
   size_t images_cap = 0;
   int last_frames = 0, launches = 0;
   bool has_result = false;
+  StageTimer timer;
 };
 
 namespace {
@@ -827,6 +828,7 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
   CMOS_CUDA_OK(cudaMemsetAsync(h->d_cand_count, 0, (size_t)h->p.max_batch * kMaxLevels * sizeof(int), st));
   CMOS_CUDA_OK(cudaMemsetAsync(h->d_overflow, 0, sizeof(int), st));
   dim3 blk(64, 4);
+  h->timer.begin(st);
   {
     const LevelGeom& L = g.lv[0];
     dim3 grid((L.pitch / 4 + 63) / 64, (L.rows + 3) / 4, n_frames);
@@ -839,19 +841,24 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
     k_resize<<<grid, blk, 0, st>>>(g, l, h->d_tab + h->xtab_off[l], h->d_tab + h->ytab_off[l], h->d_pyr);
     launches++;
   }
+  h->timer.mark(st);   // stage 0: pyramid
   if (h->n_cells > 0) {
     k_fast<<<dim3(h->n_cells, n_frames), kFastThreads, 0, st>>>(g, h->d_cells, h->d_pyr, h->d_cand, h->d_cand_count,
                                                               h->d_overflow, h->d_dbg, h->dbg_cell);
     launches++;
   }
+  h->timer.mark(st);   // stage 1: FAST
   k_octree<<<dim3(g.nlevels, n_frames), kOctThreads, oct_smem_bytes(h->oct_maxn), st>>>(
       g, h->d_cand, h->d_pnode, h->d_cand_count, h->d_stage, h->d_level_counts, h->oct_maxn);
   launches++;
+  h->timer.mark(st);   // stage 2: quadtree
   k_blur<<<dim3(h->n_tiles, n_frames), 256, 0, st>>>(g, h->d_tiles, h->d_pyr, h->d_blur);
   launches++;
+  h->timer.mark(st);   // stage 3: blur
   k_describe<<<dim3((g.kp_cap + kDescThreads / 32 - 1) / (kDescThreads / 32), n_frames), kDescThreads, 0, st>>>(
       g, h->d_stage, h->d_level_counts, h->d_pyr, h->d_blur, h->d_pattern, h->d_kps, h->d_desc, h->d_counts);
   launches++;
+  h->timer.mark(st);   // stage 4: orientation + descriptors
   CMOS_CUDA_OK(cudaGetLastError());
   h->launches = launches;
   h->last_frames = n_frames;
@@ -967,7 +974,26 @@ int cmos_orb_destroy(cmos_orb_t h) {
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (h->stream) cudaStreamDestroy(h->stream);
+  h->timer.destroy();
   delete h;
+  return CMOS_OK;
+}
+
+int cmos_orb_set_profiling(cmos_orb_t h, int32_t enable) {
+  CMOS_REQUIRE(h, "null handle");
+  CMOS_CUDA_OK(cudaSetDevice(h->device));
+  h->timer.reset();
+  h->timer.enabled = enable != 0;
+  return CMOS_OK;
+}
+
+int cmos_orb_stage_times(cmos_orb_t h, double* ms, int32_t capacity, int32_t* n_stages, int64_t* calls) {
+  CMOS_REQUIRE(h && ms && n_stages && calls, "null argument");
+  CMOS_CUDA_OK(cudaSetDevice(h->device));
+  h->timer.fold();
+  *n_stages = h->timer.n_stages;
+  *calls = h->timer.calls;
+  for (int i = 0; i < capacity && i < h->timer.n_stages; i++) ms[i] = h->timer.total_ms[i];
   return CMOS_OK;
 }
 

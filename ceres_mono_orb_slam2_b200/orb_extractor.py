@@ -111,6 +111,17 @@ class ORBextractor:
         check(self._L.cmos_orb_last_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def set_profiling(self, enable: bool = True):
+        check(self._L.cmos_orb_set_profiling(self._h, int(enable)))
+
+    def stage_times(self):
+        """-> (dict stage name -> accumulated ms, number of extractions covered)."""
+        ms = (C.c_double * 8)()
+        n, calls = C.c_int32(), C.c_int64()
+        check(self._L.cmos_orb_stage_times(self._h, ms, 8, C.byref(n), C.byref(calls)))
+        names = ["pyramid", "fast", "quadtree", "blur", "describe"]
+        return {names[i]: ms[i] for i in range(n.value)}, calls.value
+
     # ---- verification taps ----
     def level_size(self, level: int):
         w, h = C.c_int32(), C.c_int32()

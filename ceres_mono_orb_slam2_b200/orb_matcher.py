@@ -127,6 +127,17 @@ class ORBmatcher:
                                                ptr(level), ptr(vcos), 0, C.c_void_p(0)))
         return in_view, proj, level, vcos
 
+    def set_profiling(self, enable: bool = True):
+        check(self._L.cmos_match_set_profiling(self._h, int(enable)))
+
+    def stage_times(self):
+        """-> dict kernel name -> (accumulated ms, calls)."""
+        ms = (C.c_double * 4)()
+        calls = (C.c_int64 * 4)()
+        check(self._L.cmos_match_stage_times(self._h, ms, calls))
+        names = ["grid", "search_frame", "search_points", "in_frustum"]
+        return {names[i]: (ms[i], calls[i]) for i in range(4)}
+
     def launch_count(self) -> int:
         n = C.c_int32()
         check(self._L.cmos_match_last_launch_count(self._h, C.byref(n)))

@@ -116,6 +116,13 @@ int cmos_orb_debug_level_candidates(cmos_orb_t h, int32_t frame, int32_t level, 
 /* Selects the FAST cell (index into the handle's cell table, frame 0) whose shared-memory tile and score map the
  * next extraction records; if `out` is non-NULL first copies the previous record: 2*72*80 bytes + 16 ints. */
 int cmos_orb_debug_fast_cell(cmos_orb_t h, int32_t cell, uint8_t* out);
+/* Per-stage device timing (CUDA events recorded on the launching stream around each stage of every
+ * cmos_orb_extract* call while enabled).  Stages: 0 pyramid, 1 FAST+NMS, 2 quadtree, 3 blur, 4 orientation +
+ * descriptors.  cmos_orb_stage_times returns the milliseconds accumulated since profiling was enabled, summed
+ * over `calls` extractions (it waits for the recorded events). */
+#define CMOS_ORB_STAGES 5
+int cmos_orb_set_profiling(cmos_orb_t h, int32_t enable);
+int cmos_orb_stage_times(cmos_orb_t h, double* ms, int32_t capacity, int32_t* n_stages, int64_t* calls);
 /* Number of kernels launched by the last cmos_orb_extract* call. */
 int cmos_orb_last_launch_count(cmos_orb_t h, int32_t* n);
 /* Device evaluation of the two float helpers that must round like the CPU (cosf/sinf of angle*pi/180 as
@@ -210,6 +217,10 @@ int cmos_match_is_in_frustum(cmos_match_t h, const cmos_camera* cam, const doubl
                              int32_t n_frames, uint8_t* in_view, float* proj_xy, int32_t* level, float* view_cos,
                              int32_t on_device, void* stream);
 
+/* Per-kernel device timing, as cmos_orb_set_profiling.  ms[4] / calls[4]: 0 grid, 1 search(frame,last),
+ * 2 search(frame,points), 3 isInFrustum. */
+int cmos_match_set_profiling(cmos_match_t h, int32_t enable);
+int cmos_match_stage_times(cmos_match_t h, double* ms, int64_t* calls);
 /* Number of kernels launched by the last cmos_match_* call. */
 int cmos_match_last_launch_count(cmos_match_t h, int32_t* n);
 
