@@ -1,0 +1,666 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Never linked, imported or executed by the product path
+// (ceres_mono_orb_slam2_b200/); only tests/, __graft_entry__.smoke() and bench.py's CPU legs use it.
+//
+// CPU fp64 restatement of the optimisation behind CeresOptimizer::{PoseOptimization, LocalBundleAdjustment,
+// BundleAdjustment} of the reference (src/CeresOptimizer.cc:59-225,275-342,344-599, cost functors
+// include/CeresOptimizer.h:56-166).
+//
+// PARITY UNPINNED: the arithmetic lives in Ceres Solver (un-vendored, unpinned, needs <= 2.1 because of
+// ceres::LocalParameterization) and the reference ships no tests or golden vectors for this path.  Ceres is not
+// in this image, so this file restates its documented algorithm:
+//   * cost functors evaluated with forward-mode dual numbers exactly as AutoDiffCostFunction does, including
+//     Eigen's Quaternion::_transformVector formula and the K * p_c product order;
+//   * HuberLoss(sqrt(5.991)) through the Triggs corrector (rho'' <= 0 -> alpha = 0: rows scaled by sqrt(rho'));
+//   * EigenQuaternionParameterization (q stored x,y,z,w; Plus = delta_q * q; its 4x3 Jacobian);
+//   * TrustRegionMinimizer + LevenbergMarquardtStrategy with Solver::Options defaults: Jacobi scaling
+//     1/(1+||col||) fixed at iteration 0, D^2 = clamp(diag(J'J),1e-6,1e32)/radius reused after a rejected step,
+//     step quality rho, radius schedule, function / parameter / gradient tolerances 1e-6 / 1e-8 / 1e-10,
+//     max 5 consecutive invalid steps;
+//   * SPARSE_NORMAL_CHOLESKY = exact solve of (J'J + D'D) y = J'r; done here by eliminating the 3x3 point blocks
+//     first (algebraically the same linear solve as CHOLMOD's).
+// and the reference's quirks Q1 (residual = e * invSigma2), Q2 (LocalBA pass 1 keeps the pass-0 Huber blocks and
+// adds a loss-free copy of the inliers) and Q5 (PoseOptimization = one robust solve + one classification).
+// It is sanity-checked in tests/test_oracle_ba.py against finite differences and scipy.optimize.least_squares.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// forward-mode dual number (ceres::Jet<double, N>)
+template <int N>
+struct Jet {
+  double a;
+  double v[N];
+  Jet() : a(0) { for (int i = 0; i < N; i++) v[i] = 0; }
+  Jet(double s) : a(s) { for (int i = 0; i < N; i++) v[i] = 0; }   // NOLINT
+  Jet(double s, int k) : a(s) { for (int i = 0; i < N; i++) v[i] = 0; v[k] = 1; }
+};
+template <int N> Jet<N> operator+(const Jet<N>& f, const Jet<N>& g) { Jet<N> h; h.a = f.a + g.a; for (int i = 0; i < N; i++) h.v[i] = f.v[i] + g.v[i]; return h; }
+template <int N> Jet<N> operator-(const Jet<N>& f, const Jet<N>& g) { Jet<N> h; h.a = f.a - g.a; for (int i = 0; i < N; i++) h.v[i] = f.v[i] - g.v[i]; return h; }
+template <int N> Jet<N> operator*(const Jet<N>& f, const Jet<N>& g) { Jet<N> h; h.a = f.a * g.a; for (int i = 0; i < N; i++) h.v[i] = f.a * g.v[i] + f.v[i] * g.a; return h; }
+template <int N> Jet<N> operator/(const Jet<N>& f, const Jet<N>& g) {
+  Jet<N> h; const double gi = 1.0 / g.a; const double fg = f.a * gi; h.a = fg;
+  for (int i = 0; i < N; i++) h.v[i] = (f.v[i] - fg * g.v[i]) * gi;
+  return h;
+}
+template <int N> Jet<N> operator*(double s, const Jet<N>& f) { Jet<N> h; h.a = s * f.a; for (int i = 0; i < N; i++) h.v[i] = s * f.v[i]; return h; }
+template <int N> Jet<N> operator-(double s, const Jet<N>& f) { Jet<N> h; h.a = s - f.a; for (int i = 0; i < N; i++) h.v[i] = -f.v[i]; return h; }
+inline double operator_val(double x) { return x; }
+
+// PoseGraph3dErrorTerm::operator() / PoseErrorTerm::operator()  (CeresOptimizer.h:63-88,122-143)
+template <typename T>
+void reprojection_residual(const T* t, const T* q, const T* X, const double K4[4], double u, double v, double w,
+                           T* r) {
+  // Eigen::Quaternion * vector (QuaternionBase::_transformVector): uv = 2 * vec x v; v + w*uv + vec x uv
+  T uv0 = q[1] * X[2] - q[2] * X[1];
+  T uv1 = q[2] * X[0] - q[0] * X[2];
+  T uv2 = q[0] * X[1] - q[1] * X[0];
+  uv0 = uv0 + uv0; uv1 = uv1 + uv1; uv2 = uv2 + uv2;
+  T p0 = X[0] + q[3] * uv0 + (q[1] * uv2 - q[2] * uv1) + t[0];
+  T p1 = X[1] + q[3] * uv1 + (q[2] * uv0 - q[0] * uv2) + t[1];
+  T p2 = X[2] + q[3] * uv2 + (q[0] * uv1 - q[1] * uv0) + t[2];
+  // projected = K * p_cp
+  T px = K4[0] * p0 + K4[2] * p2;
+  T py = K4[1] * p1 + K4[3] * p2;
+  T pz = p2;
+  T r0 = u - px / pz;
+  T r1 = v - py / pz;
+  r[0] = w * r0;   // applyOnTheLeft(diag(invSigma2, invSigma2))  — quirk Q1
+  r[1] = w * r1;
+}
+
+// EigenQuaternionParameterization::Plus, q = (x, y, z, w)
+void quat_plus(const double* q, const double* d, double* out) {
+  const double n = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  if (n > 0.0) {
+    const double s = std::sin(n) / n;
+    const double ax = s * d[0], ay = s * d[1], az = s * d[2], aw = std::cos(n);
+    const double bx = q[0], by = q[1], bz = q[2], bw = q[3];
+    out[3] = aw * bw - ax * bx - ay * by - az * bz;
+    out[0] = aw * bx + ax * bw + ay * bz - az * by;
+    out[1] = aw * by + ay * bw + az * bx - ax * bz;
+    out[2] = aw * bz + az * bw + ax * by - ay * bx;
+  } else {
+    for (int i = 0; i < 4; i++) out[i] = q[i];
+  }
+}
+
+// EigenQuaternionParameterization::ComputeJacobian, 4x3 row-major
+void quat_plus_jacobian(const double* x, double* J) {
+  J[0] = x[3];  J[1] = x[2];   J[2] = -x[1];
+  J[3] = -x[2]; J[4] = x[3];   J[5] = x[0];
+  J[6] = x[1];  J[7] = -x[0];  J[8] = x[3];
+  J[9] = -x[0]; J[10] = -x[1]; J[11] = -x[2];
+}
+
+constexpr double kHuberA = 2.447651936039926;   // sqrt(5.991)
+
+struct Block {   // one ceres residual block
+  int cam, pt;
+  double u, v, w;
+  int huber;     // loss_function != nullptr
+};
+
+struct Lin {     // one linearised residual block (already corrected by the loss)
+  double r[2];
+  double Jc[12];   // 2x6 tangent: t(3), delta(3)
+  double Jp[6];    // 2x3
+};
+
+struct Solver {
+  int K = 0, M = 0;
+  std::vector<double> cams, pts;   // current x
+  std::vector<uint8_t> cam_const;
+  bool pts_const = false;
+  double K4[4];
+  std::vector<Block> blocks;
+  std::vector<int> cam_var;        // cam -> variable index or -1
+  int Kv = 0;
+
+  // ---- evaluation -------------------------------------------------------------------------------
+  double cost_only(const std::vector<double>& c, const std::vector<double>& p) const {
+    double cost = 0.0;
+    for (const Block& b : blocks) {
+      double r[2];
+      reprojection_residual<double>(&c[7 * b.cam], &c[7 * b.cam + 3], &p[3 * b.pt], K4, b.u, b.v, b.w, r);
+      const double s = r[0] * r[0] + r[1] * r[1];
+      double rho0 = s;
+      if (b.huber && s > kHuberA * kHuberA) rho0 = 2.0 * kHuberA * std::sqrt(s) - kHuberA * kHuberA;
+      cost += 0.5 * rho0;
+    }
+    return cost;
+  }
+
+  double linearize(std::vector<Lin>& lin) const {
+    lin.resize(blocks.size());
+    double cost = 0.0;
+    for (size_t i = 0; i < blocks.size(); i++) {
+      const Block& b = blocks[i];
+      typedef Jet<10> J10;
+      J10 t[3], q[4], X[3], r[2];
+      for (int k = 0; k < 3; k++) t[k] = J10(cams[7 * b.cam + k], k);
+      for (int k = 0; k < 4; k++) q[k] = J10(cams[7 * b.cam + 3 + k], 3 + k);
+      for (int k = 0; k < 3; k++) X[k] = J10(pts[3 * b.pt + k], 7 + k);
+      reprojection_residual<J10>(t, q, X, K4, b.u, b.v, b.w, r);
+      double PJ[12];
+      quat_plus_jacobian(&cams[7 * b.cam + 3], PJ);
+      Lin& L = lin[i];
+      const double s = r[0].a * r[0].a + r[1].a * r[1].a;
+      double rho0 = s, rho1 = 1.0;
+      if (b.huber && s > kHuberA * kHuberA) {
+        const double rr = std::sqrt(s);
+        rho0 = 2.0 * kHuberA * rr - kHuberA * kHuberA;
+        rho1 = std::max(std::numeric_limits<double>::min(), kHuberA / rr);
+      }
+      cost += 0.5 * rho0;
+      const double sc = b.huber ? std::sqrt(rho1) : 1.0;   // corrector with alpha = 0
+      for (int row = 0; row < 2; row++) {
+        L.r[row] = sc * r[row].a;
+        for (int k = 0; k < 3; k++) L.Jc[row * 6 + k] = sc * r[row].v[k];
+        for (int k = 0; k < 3; k++) {
+          double acc = 0.0;
+          for (int g = 0; g < 4; g++) acc += r[row].v[3 + g] * PJ[g * 3 + k];
+          L.Jc[row * 6 + 3 + k] = sc * acc;
+        }
+        for (int k = 0; k < 3; k++) L.Jp[row * 3 + k] = sc * r[row].v[7 + k];
+      }
+    }
+    return cost;
+  }
+
+  int n_cols() const { return 6 * Kv + (pts_const ? 0 : 3 * M); }
+  int cam_col(int cam) const { return 6 * cam_var[cam]; }
+  int pt_col(int pt) const { return 6 * Kv + 3 * pt; }
+
+  void plus(const std::vector<double>& c, const std::vector<double>& p, const double* delta, std::vector<double>& co,
+            std::vector<double>& po) const {
+    co = c; po = p;
+    for (int k = 0; k < K; k++) {
+      if (cam_var[k] < 0) continue;
+      const double* d = delta + 6 * cam_var[k];
+      for (int i = 0; i < 3; i++) co[7 * k + i] = c[7 * k + i] + d[i];
+      quat_plus(&c[7 * k + 3], d + 3, &co[7 * k + 3]);
+    }
+    if (!pts_const)
+      for (int j = 0; j < M; j++)
+        for (int i = 0; i < 3; i++) po[3 * j + i] = p[3 * j + i] + delta[6 * Kv + 3 * j + i];
+  }
+
+  double ambient_norm(const std::vector<double>& c, const std::vector<double>& p) const {
+    double s = 0.0;
+    for (int k = 0; k < K; k++)
+      if (cam_var[k] >= 0)
+        for (int i = 0; i < 7; i++) s += c[7 * k + i] * c[7 * k + i];
+    if (!pts_const)
+      for (double x : p) s += x * x;
+    return std::sqrt(s);
+  }
+  double ambient_diff(const std::vector<double>& c0, const std::vector<double>& p0, const std::vector<double>& c1,
+                      const std::vector<double>& p1, bool inf_norm) const {
+    double s = 0.0;
+    auto acc = [&](double d) { if (inf_norm) s = std::max(s, std::fabs(d)); else s += d * d; };
+    for (int k = 0; k < K; k++)
+      if (cam_var[k] >= 0)
+        for (int i = 0; i < 7; i++) acc(c0[7 * k + i] - c1[7 * k + i]);
+    if (!pts_const)
+      for (size_t i = 0; i < p0.size(); i++) acc(p0[i] - p1[i]);
+    return inf_norm ? s : std::sqrt(s);
+  }
+};
+
+// dense symmetric positive definite solve, in place (lower Cholesky); returns false if not PD
+bool cholesky_solve(std::vector<double>& A, int n, std::vector<double>& b) {
+  for (int j = 0; j < n; j++) {
+    double d = A[(size_t)j * n + j];
+    for (int k = 0; k < j; k++) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+    if (!(d > 0.0) || !std::isfinite(d)) return false;
+    d = std::sqrt(d);
+    A[(size_t)j * n + j] = d;
+    for (int i = j + 1; i < n; i++) {
+      double s = A[(size_t)i * n + j];
+      const double* ai = &A[(size_t)i * n];
+      const double* aj = &A[(size_t)j * n];
+      for (int k = 0; k < j; k++) s -= ai[k] * aj[k];
+      A[(size_t)i * n + j] = s / d;
+    }
+  }
+  for (int i = 0; i < n; i++) {
+    double s = b[i];
+    for (int k = 0; k < i; k++) s -= A[(size_t)i * n + k] * b[k];
+    b[i] = s / A[(size_t)i * n + i];
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    double s = b[i];
+    for (int k = i + 1; k < n; k++) s -= A[(size_t)k * n + i] * b[k];
+    b[i] = s / A[(size_t)i * n + i];
+  }
+  return true;
+}
+
+bool invert3_sym(const double* H /*6: 00 01 02 11 12 22*/, double* inv) {
+  const double a = H[0], b = H[1], c = H[2], d = H[3], e = H[4], f = H[5];
+  // Cholesky of the 3x3 (same PD test a sparse Cholesky would make)
+  if (!(a > 0)) return false;
+  const double l00 = std::sqrt(a), l10 = b / l00, l20 = c / l00;
+  const double t11 = d - l10 * l10;
+  if (!(t11 > 0)) return false;
+  const double l11 = std::sqrt(t11), l21 = (e - l20 * l10) / l11;
+  const double t22 = f - l20 * l20 - l21 * l21;
+  if (!(t22 > 0)) return false;
+  const double l22 = std::sqrt(t22);
+  // inverse of L
+  const double i00 = 1 / l00, i11 = 1 / l11, i22 = 1 / l22;
+  const double i10 = -l10 * i00 * i11;
+  const double i21 = -l21 * i11 * i22;
+  const double i20 = -(l20 * i00 + l21 * i10) * i22;
+  inv[0] = i00 * i00 + i10 * i10 + i20 * i20;
+  inv[1] = i10 * i11 + i20 * i21;
+  inv[2] = i20 * i22;
+  inv[3] = i11 * i11 + i21 * i21;
+  inv[4] = i21 * i22;
+  inv[5] = i22 * i22;
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+struct ba_oracle_summary {
+  int32_t iterations;            // LM iterations performed (successful + unsuccessful + invalid)
+  int32_t successful_steps;
+  int32_t termination;           // 0 max iterations, 1 function tol, 2 parameter tol, 3 gradient tol, 4 user stop,
+                                 // 5 failure, 6 min trust-region radius
+  int32_t jacobian_evaluations;
+  double initial_cost, final_cost;
+};
+
+// trace: [iterations+1][8] = cost, cost_change, gradient_max_norm, step_norm, relative_decrease, radius, accepted, valid
+int ba_oracle_solve(int K, double* cams, const uint8_t* cam_const, int M, double* pts, int pts_const, int N,
+                    const int32_t* obs_cam, const int32_t* obs_pt, const float* uv, const float* inv_sigma2,
+                    const uint8_t* mode, const double* K4, int max_iterations, ba_oracle_summary* out, double* trace,
+                    int trace_cap) {
+  Solver S;
+  S.K = K; S.M = M;
+  S.cams.assign(cams, cams + 7 * (size_t)K);
+  S.pts.assign(pts, pts + 3 * (size_t)M);
+  S.cam_const.assign(cam_const, cam_const + K);
+  S.pts_const = pts_const != 0;
+  for (int i = 0; i < 4; i++) S.K4[i] = K4[i];
+  S.cam_var.assign(K, -1);
+  for (int k = 0; k < K; k++)
+    if (!cam_const[k]) S.cam_var[k] = S.Kv++;
+  for (int i = 0; i < N; i++) {
+    const int m = mode ? mode[i] : 1;
+    Block b{obs_cam[i], obs_pt[i], (double)uv[2 * i], (double)uv[2 * i + 1], (double)inv_sigma2[i], 1};
+    if (m & 1) { b.huber = 1; S.blocks.push_back(b); }
+    if (m & 2) { b.huber = 0; S.blocks.push_back(b); }
+  }
+  const int n = S.n_cols(), nc = 6 * S.Kv;
+  const bool have_pts = !S.pts_const;
+  ba_oracle_summary sum{};
+  std::vector<Lin> lin;
+  std::vector<double> scale(n, 1.0), grad(n), diag(n), lm(n), step(n), delta(n);
+  std::vector<double> cand_c, cand_p;
+  double x_cost = 0, radius = 1e4, decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+  int consecutive_invalid = 0;
+  int tr = 0;
+  auto put_trace = [&](double cost, double dc, double gmax, double sn, double rd, double rad, double acc, double valid) {
+    if (trace && tr < trace_cap) {
+      double* t = trace + 8 * tr;
+      t[0] = cost; t[1] = dc; t[2] = gmax; t[3] = sn; t[4] = rd; t[5] = rad; t[6] = acc; t[7] = valid;
+    }
+    tr++;
+  };
+
+  // EvaluateGradientAndJacobian
+  double gmax = 0.0;
+  auto evaluate = [&](bool first) {
+    x_cost = S.linearize(lin);
+    sum.jacobian_evaluations++;
+    std::fill(grad.begin(), grad.end(), 0.0);
+    std::vector<double> col2(first ? n : 0, 0.0);
+    for (size_t i = 0; i < lin.size(); i++) {
+      const Block& b = S.blocks[i];
+      const Lin& L = lin[i];
+      const int cv = S.cam_var[b.cam];
+      if (cv >= 0)
+        for (int k = 0; k < 6; k++) {
+          grad[6 * cv + k] += L.Jc[k] * L.r[0] + L.Jc[6 + k] * L.r[1];
+          if (first) col2[6 * cv + k] += L.Jc[k] * L.Jc[k] + L.Jc[6 + k] * L.Jc[6 + k];
+        }
+      if (have_pts)
+        for (int k = 0; k < 3; k++) {
+          grad[nc + 3 * b.pt + k] += L.Jp[k] * L.r[0] + L.Jp[3 + k] * L.r[1];
+          if (first) col2[nc + 3 * b.pt + k] += L.Jp[k] * L.Jp[k] + L.Jp[3 + k] * L.Jp[3 + k];
+        }
+    }
+    if (first)
+      for (int i = 0; i < n; i++) scale[i] = 1.0 / (1.0 + std::sqrt(col2[i]));
+    // gradient_max_norm = || x - Plus(x, -g) ||_inf
+    std::vector<double> ng(n);
+    for (int i = 0; i < n; i++) ng[i] = -grad[i];
+    std::vector<double> pc, pp;
+    S.plus(S.cams, S.pts, ng.data(), pc, pp);
+    gmax = S.ambient_diff(S.cams, S.pts, pc, pp, true);
+  };
+
+  double x_norm = S.ambient_norm(S.cams, S.pts);
+  evaluate(true);
+  sum.initial_cost = x_cost;
+  put_trace(x_cost, 0, gmax, 0, 0, radius, 0, 0);
+  int iteration = 0;
+  sum.termination = 0;
+  bool done = false;
+  if (gmax <= 1e-10) { sum.termination = 3; done = true; }
+  if (!done && max_iterations <= 0) done = true;
+
+  std::vector<double> Hpp, Hinv, gp, Sm, rhs;
+  while (!done) {
+    iteration++;
+    // ---- ComputeTrustRegionStep: LevenbergMarquardtStrategy::ComputeStep on the scaled Jacobian ----
+    if (!reuse_diagonal) {
+      std::fill(diag.begin(), diag.end(), 0.0);
+      for (size_t i = 0; i < lin.size(); i++) {
+        const Block& b = S.blocks[i];
+        const Lin& L = lin[i];
+        const int cv = S.cam_var[b.cam];
+        if (cv >= 0)
+          for (int k = 0; k < 6; k++) {
+            const double s = scale[6 * cv + k];
+            diag[6 * cv + k] += (L.Jc[k] * s) * (L.Jc[k] * s) + (L.Jc[6 + k] * s) * (L.Jc[6 + k] * s);
+          }
+        if (have_pts)
+          for (int k = 0; k < 3; k++) {
+            const double s = scale[nc + 3 * b.pt + k];
+            diag[nc + 3 * b.pt + k] += (L.Jp[k] * s) * (L.Jp[k] * s) + (L.Jp[3 + k] * s) * (L.Jp[3 + k] * s);
+          }
+      }
+      for (int i = 0; i < n; i++) diag[i] = std::min(std::max(diag[i], 1e-6), 1e32);
+    }
+    for (int i = 0; i < n; i++) lm[i] = std::sqrt(diag[i] / radius);
+    // normal equations (scaled): (J'J + D'D) y = J'r, points eliminated first
+    Sm.assign((size_t)nc * nc, 0.0);
+    rhs.assign(nc, 0.0);
+    bool ok = true;
+    if (have_pts) { Hpp.assign(6 * (size_t)S.M, 0.0); gp.assign(3 * (size_t)S.M, 0.0); Hinv.assign(6 * (size_t)S.M, 0.0); }
+    for (size_t i = 0; i < lin.size(); i++) {
+      const Block& b = S.blocks[i];
+      const Lin& L = lin[i];
+      const int cv = S.cam_var[b.cam];
+      if (cv >= 0) {
+        double Js[12];
+        for (int k = 0; k < 6; k++) { Js[k] = L.Jc[k] * scale[6 * cv + k]; Js[6 + k] = L.Jc[6 + k] * scale[6 * cv + k]; }
+        for (int a = 0; a < 6; a++) {
+          rhs[6 * cv + a] += Js[a] * L.r[0] + Js[6 + a] * L.r[1];
+          for (int c = 0; c < 6; c++) Sm[(size_t)(6 * cv + a) * nc + 6 * cv + c] += Js[a] * Js[c] + Js[6 + a] * Js[6 + c];
+        }
+      }
+      if (have_pts) {
+        double Js[6];
+        for (int k = 0; k < 3; k++) { Js[k] = L.Jp[k] * scale[nc + 3 * b.pt + k]; Js[3 + k] = L.Jp[3 + k] * scale[nc + 3 * b.pt + k]; }
+        double* H = &Hpp[6 * (size_t)b.pt];
+        H[0] += Js[0] * Js[0] + Js[3] * Js[3]; H[1] += Js[0] * Js[1] + Js[3] * Js[4]; H[2] += Js[0] * Js[2] + Js[3] * Js[5];
+        H[3] += Js[1] * Js[1] + Js[4] * Js[4]; H[4] += Js[1] * Js[2] + Js[4] * Js[5]; H[5] += Js[2] * Js[2] + Js[5] * Js[5];
+        for (int k = 0; k < 3; k++) gp[3 * (size_t)b.pt + k] += Js[k] * L.r[0] + Js[3 + k] * L.r[1];
+      }
+    }
+    for (int i = 0; i < nc; i++) Sm[(size_t)i * nc + i] += lm[i] * lm[i];
+    if (have_pts) {
+      for (int j = 0; j < S.M && ok; j++) {
+        double H[6];
+        for (int k = 0; k < 6; k++) H[k] = Hpp[6 * (size_t)j + k];
+        H[0] += lm[nc + 3 * j] * lm[nc + 3 * j]; H[3] += lm[nc + 3 * j + 1] * lm[nc + 3 * j + 1]; H[5] += lm[nc + 3 * j + 2] * lm[nc + 3 * j + 2];
+        ok = invert3_sym(H, &Hinv[6 * (size_t)j]);
+      }
+      if (ok) {
+        // group residual blocks by point
+        std::vector<std::vector<int>> by_pt(S.M);
+        for (size_t i = 0; i < lin.size(); i++)
+          if (S.cam_var[S.blocks[i].cam] >= 0) by_pt[S.blocks[i].pt].push_back((int)i);
+        std::vector<double> Wb;   // per block of the point: W = Jc_s' Jp_s (6x3)
+        for (int j = 0; j < S.M; j++) {
+          const std::vector<int>& ids = by_pt[j];
+          if (ids.empty()) continue;
+          const double* Hi = &Hinv[6 * (size_t)j];
+          const double Hf[9] = {Hi[0], Hi[1], Hi[2], Hi[1], Hi[3], Hi[4], Hi[2], Hi[4], Hi[5]};
+          Wb.assign(ids.size() * 18, 0.0);
+          std::vector<double> WH(ids.size() * 18, 0.0);
+          for (size_t a = 0; a < ids.size(); a++) {
+            const Lin& L = lin[ids[a]];
+            const int cv = S.cam_var[S.blocks[ids[a]].cam];
+            for (int r6 = 0; r6 < 6; r6++)
+              for (int c3 = 0; c3 < 3; c3++)
+                Wb[a * 18 + r6 * 3 + c3] = (L.Jc[r6] * L.Jp[c3] + L.Jc[6 + r6] * L.Jp[3 + c3]) * scale[6 * cv + r6] * scale[nc + 3 * j + c3];
+            for (int r6 = 0; r6 < 6; r6++)
+              for (int c3 = 0; c3 < 3; c3++) {
+                double acc = 0;
+                for (int k = 0; k < 3; k++) acc += Wb[a * 18 + r6 * 3 + k] * Hf[k * 3 + c3];
+                WH[a * 18 + r6 * 3 + c3] = acc;
+              }
+          }
+          for (size_t a = 0; a < ids.size(); a++) {
+            const int ca = S.cam_var[S.blocks[ids[a]].cam];
+            for (int r6 = 0; r6 < 6; r6++) {
+              double acc = 0;
+              for (int k = 0; k < 3; k++) acc += WH[a * 18 + r6 * 3 + k] * gp[3 * (size_t)j + k];
+              rhs[6 * ca + r6] -= acc;
+            }
+            for (size_t bq = 0; bq < ids.size(); bq++) {
+              const int cb = S.cam_var[S.blocks[ids[bq]].cam];
+              for (int r6 = 0; r6 < 6; r6++)
+                for (int c6 = 0; c6 < 6; c6++) {
+                  double acc = 0;
+                  for (int k = 0; k < 3; k++) acc += WH[a * 18 + r6 * 3 + k] * Wb[bq * 18 + c6 * 3 + k];
+                  Sm[(size_t)(6 * ca + r6) * nc + 6 * cb + c6] -= acc;
+                }
+            }
+          }
+        }
+      }
+    }
+    std::vector<double> yc = rhs;
+    if (ok && nc > 0) ok = cholesky_solve(Sm, nc, yc);
+    bool step_valid = ok;
+    double model_cost_change = 0.0;
+    if (ok) {
+      for (int i = 0; i < nc; i++) step[i] = -yc[i];
+      if (have_pts) {
+        // y_p = Hinv (g_p - W' y_c)
+        std::vector<double> acc(3 * (size_t)S.M, 0.0);
+        for (size_t i = 0; i < lin.size(); i++) {
+          const Block& b = S.blocks[i];
+          const int cv = S.cam_var[b.cam];
+          if (cv < 0) continue;
+          const Lin& L = lin[i];
+          for (int c3 = 0; c3 < 3; c3++) {
+            double a = 0;
+            for (int r6 = 0; r6 < 6; r6++)
+              a += (L.Jc[r6] * L.Jp[c3] + L.Jc[6 + r6] * L.Jp[3 + c3]) * scale[6 * cv + r6] * scale[nc + 3 * b.pt + c3] * yc[6 * cv + r6];
+            acc[3 * (size_t)b.pt + c3] += a;
+          }
+        }
+        for (int j = 0; j < S.M; j++) {
+          const double* Hi = &Hinv[6 * (size_t)j];
+          const double b0 = gp[3 * (size_t)j] - acc[3 * (size_t)j], b1 = gp[3 * (size_t)j + 1] - acc[3 * (size_t)j + 1],
+                       b2 = gp[3 * (size_t)j + 2] - acc[3 * (size_t)j + 2];
+          step[nc + 3 * j] = -(Hi[0] * b0 + Hi[1] * b1 + Hi[2] * b2);
+          step[nc + 3 * j + 1] = -(Hi[1] * b0 + Hi[3] * b1 + Hi[4] * b2);
+          step[nc + 3 * j + 2] = -(Hi[2] * b0 + Hi[4] * b1 + Hi[5] * b2);
+        }
+      }
+      for (int i = 0; i < n; i++)
+        if (!std::isfinite(step[i])) step_valid = false;
+    }
+    reuse_diagonal = true;
+    if (step_valid) {
+      // model_cost_change = -(J s)'(r + J s / 2) with the scaled Jacobian
+      for (size_t i = 0; i < lin.size(); i++) {
+        const Block& b = S.blocks[i];
+        const Lin& L = lin[i];
+        const int cv = S.cam_var[b.cam];
+        for (int row = 0; row < 2; row++) {
+          double m = 0.0;
+          if (cv >= 0)
+            for (int k = 0; k < 6; k++) m += L.Jc[row * 6 + k] * scale[6 * cv + k] * step[6 * cv + k];
+          if (have_pts)
+            for (int k = 0; k < 3; k++) m += L.Jp[row * 3 + k] * scale[nc + 3 * b.pt + k] * step[nc + 3 * b.pt + k];
+          model_cost_change -= m * (L.r[row] + m / 2.0);
+        }
+      }
+      if (!(model_cost_change > 0.0)) step_valid = false;
+    }
+    if (!step_valid) {
+      // HandleInvalidStep
+      consecutive_invalid++;
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      put_trace(x_cost, 0, gmax, 0, 0, radius, 0, 0);
+      if (consecutive_invalid >= 5) { sum.termination = 5; break; }
+      if (iteration >= max_iterations) { sum.termination = 0; break; }
+      if (radius < 1e-32) { sum.termination = 6; break; }
+      continue;
+    }
+    consecutive_invalid = 0;
+    for (int i = 0; i < n; i++) delta[i] = step[i] * scale[i];
+    S.plus(S.cams, S.pts, delta.data(), cand_c, cand_p);
+    const double cand_cost = S.cost_only(cand_c, cand_p);
+    const double step_norm = S.ambient_diff(S.cams, S.pts, cand_c, cand_p, false);
+    if (step_norm <= 1e-8 * (x_norm + 1e-8)) {   // ParameterToleranceReached
+      sum.termination = 2;
+      put_trace(x_cost, 0, gmax, step_norm, 0, radius, 0, 1);
+      break;
+    }
+    const double cost_change = x_cost - cand_cost;
+    if (std::fabs(cost_change) <= 1e-6 * x_cost) {   // FunctionToleranceReached
+      sum.termination = 1;
+      put_trace(x_cost, cost_change, gmax, step_norm, 0, radius, 0, 1);
+      break;
+    }
+    const double relative_decrease = cost_change / model_cost_change;
+    bool accepted = relative_decrease > 1e-3;
+    if (accepted) {
+      S.cams = cand_c; S.pts = cand_p;
+      x_norm = S.ambient_norm(S.cams, S.pts);
+      evaluate(false);
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * relative_decrease - 1.0, 3));
+      radius = std::min(1e16, radius);
+      decrease_factor = 2.0;
+      reuse_diagonal = false;
+      sum.successful_steps++;
+    } else {
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+    }
+    put_trace(x_cost, cost_change, gmax, step_norm, relative_decrease, radius, accepted ? 1 : 0, 1);
+    // FinalizeIterationAndCheckIfMinimizerCanContinue
+    if (iteration >= max_iterations) { sum.termination = 0; break; }
+    if (gmax <= 1e-10) { sum.termination = 3; break; }
+    if (radius < 1e-32) { sum.termination = 6; break; }
+  }
+  sum.iterations = iteration;
+  sum.final_cost = x_cost;
+  std::memcpy(cams, S.cams.data(), sizeof(double) * 7 * (size_t)K);
+  if (!S.pts_const) std::memcpy(pts, S.pts.data(), sizeof(double) * 3 * (size_t)M);
+  if (out) *out = sum;
+  return tr;
+}
+
+// residuals + tangent Jacobians of one observation (tests: finite differences, scipy cross-check)
+void ba_oracle_residual(const double* cam7, const double* X, const double* K4, float u, float v, float inv_sigma2,
+                        double* r, double* Jc /*2x6*/, double* Jp /*2x3*/) {
+  Solver S;
+  S.K = 1; S.M = 1; S.cams.assign(cam7, cam7 + 7); S.pts.assign(X, X + 3);
+  for (int i = 0; i < 4; i++) S.K4[i] = K4[i];
+  S.cam_var.assign(1, 0); S.Kv = 1;
+  S.blocks.push_back(Block{0, 0, (double)u, (double)v, (double)inv_sigma2, 0});
+  std::vector<Lin> lin;
+  S.linearize(lin);
+  for (int i = 0; i < 2; i++) r[i] = lin[0].r[i];
+  for (int i = 0; i < 12; i++) Jc[i] = lin[0].Jc[i];
+  for (int i = 0; i < 6; i++) Jp[i] = lin[0].Jp[i];
+}
+
+void ba_oracle_quat_plus(const double* q, const double* d, double* out) { quat_plus(q, d, out); }
+
+// CeresOptimizer::CheckOutlier (CeresOptimizer.cc:227-241) + the z <= 0 test of LocalBundleAdjustment (:558-564)
+static void check_obs(const double* cam7, const double* X, const double* K4, float u, float v, float inv_sigma,
+                      double* chi2, double* z) {
+  double r[2];
+  // pixel = K * (q * X + t); error = obs - pixel.xy / pixel.z; error^2 * inv_sigma
+  reprojection_residual<double>(cam7, cam7 + 3, X, K4, (double)u, (double)v, 1.0, r);
+  *chi2 = (r[0] * r[0] + r[1] * r[1]) * (double)inv_sigma;
+  double one[4] = {0, 0, 0, 0};
+  (void)one;
+  // z of q * X + t
+  const double* q = cam7 + 3;
+  double uv0 = q[1] * X[2] - q[2] * X[1], uv1 = q[2] * X[0] - q[0] * X[2], uv2 = q[0] * X[1] - q[1] * X[0];
+  uv0 += uv0; uv1 += uv1; uv2 += uv2;
+  *z = X[2] + q[3] * uv2 + (q[0] * uv1 - q[1] * uv0) + cam7[2];
+}
+
+// CeresOptimizer::PoseOptimization (CeresOptimizer.cc:275-342) for one frame.
+// Returns n_initial_correspondences - n_bad; pose7 in/out (q normalised on output, :335); is_outlier out.
+int ba_oracle_pose_optimization(double* pose7, int n, const double* xw, const float* uv, const float* inv_sigma2,
+                                const double* K4, int max_iterations, uint8_t* is_outlier, ba_oracle_summary* out,
+                                double* trace, int trace_cap) {
+  if (n < 3) { if (out) std::memset(out, 0, sizeof(*out)); return 0; }
+  std::vector<int32_t> oc(n, 0), op(n);
+  for (int i = 0; i < n; i++) op[i] = i;
+  std::vector<double> pts(xw, xw + 3 * (size_t)n);
+  const uint8_t cc = 0;
+  ba_oracle_solve(1, pose7, &cc, n, pts.data(), 1, n, oc.data(), op.data(), uv, inv_sigma2, nullptr, K4,
+                  max_iterations, out, trace, trace_cap);
+  int n_bad = 0;
+  for (int i = 0; i < n; i++) {
+    double chi2, z;
+    check_obs(pose7, xw + 3 * (size_t)i, K4, uv[2 * i], uv[2 * i + 1], inv_sigma2[i], &chi2, &z);
+    is_outlier[i] = chi2 > 5.991;
+    n_bad += is_outlier[i];
+  }
+  const double nq = std::sqrt(pose7[3] * pose7[3] + pose7[4] * pose7[4] + pose7[5] * pose7[5] + pose7[6] * pose7[6]);
+  for (int i = 3; i < 7; i++) pose7[i] /= nq;
+  return n - n_bad;
+}
+
+// CeresOptimizer::LocalBundleAdjustment (CeresOptimizer.cc:344-599) on a flattened graph.
+// cam_flags: bit0 = constant (fixed keyframe, or keyframe id 0), bit1 = not a local keyframe (no outlier scan).
+// erase[n_obs] out: observations the reference would erase from the map (:573-581).  summaries[2].
+void ba_oracle_local(int K, double* cams, const uint8_t* cam_flags, int M, double* pts, int N, const int32_t* obs_cam,
+                     const int32_t* obs_pt, const float* uv, const float* inv_sigma2, const double* K4,
+                     int iters_pass0, int iters_pass1, uint8_t* erase, ba_oracle_summary* summaries) {
+  std::vector<uint8_t> cc(K), mode(N, 1);
+  for (int k = 0; k < K; k++) cc[k] = cam_flags[k] & 1;
+  auto scan = [&]() {
+    for (int i = 0; i < N; i++) {
+      erase[i] = 0;
+      if (cam_flags[obs_cam[i]] & 2) continue;
+      double chi2, z;
+      check_obs(cams + 7 * (size_t)obs_cam[i], pts + 3 * (size_t)obs_pt[i], K4, uv[2 * i], uv[2 * i + 1], inv_sigma2[i],
+                &chi2, &z);
+      erase[i] = (chi2 > 5.991) || (z <= 0);
+    }
+  };
+  ba_oracle_solve(K, cams, cc.data(), M, pts, 0, N, obs_cam, obs_pt, uv, inv_sigma2, mode.data(), K4, iters_pass0,
+                  summaries, nullptr, 0);
+  scan();
+  for (int i = 0; i < N; i++) mode[i] = erase[i] ? 1 : 3;   // quirk Q2: Huber blocks stay, inliers added again without loss
+  ba_oracle_solve(K, cams, cc.data(), M, pts, 0, N, obs_cam, obs_pt, uv, inv_sigma2, mode.data(), K4, iters_pass1,
+                  summaries + 1, nullptr, 0);
+  scan();
+}
+
+// CeresOptimizer::BundleAdjustment (CeresOptimizer.cc:59-225)
+void ba_oracle_global(int K, double* cams, const uint8_t* cam_const, int M, double* pts, int N, const int32_t* obs_cam,
+                      const int32_t* obs_pt, const float* uv, const float* inv_sigma2, const double* K4, int n_iterations,
+                      int robust, ba_oracle_summary* summary, double* trace, int trace_cap) {
+  std::vector<uint8_t> mode(N, robust ? 1 : 2);
+  ba_oracle_solve(K, cams, cam_const, M, pts, 0, N, obs_cam, obs_pt, uv, inv_sigma2, mode.data(), K4, n_iterations,
+                  summary, trace, trace_cap);
+}
+
+}  // extern "C"

@@ -37,6 +37,8 @@ def lib() -> C.CDLL:
         _LIB.orb_oracle_create.restype = C.c_void_p
         _LIB.orb_oracle_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
         _LIB.orb_oracle_destroy.argtypes = [C.c_void_p]
+        _LIB.ba_oracle_solve.restype = C.c_int
+        _LIB.ba_oracle_pose_optimization.restype = C.c_int
         for name in ("orb_oracle_tables", "orb_oracle_extract", "orb_oracle_result", "orb_oracle_level_size",
                      "orb_oracle_level_image", "orb_oracle_level_blurred", "orb_oracle_level_candidates",
                      "orb_oracle_level_keypoints"):
@@ -264,3 +266,84 @@ def is_in_frustum(pose15, K4, bounds4, log_scale_factor, n_levels, cos_limit, xw
                                      C.c_float(cos_limit), n, _p(xw), _p(normal), _p(mn), _p(mx), _p(in_view),
                                      _p(proj), _p(level), _p(vcos))
     return in_view, proj, level, vcos
+
+
+# ---------------------------------------------------------------------------------------------------
+# Bundle-adjustment oracle (oracle/ba_oracle.cpp)
+
+class BaSummary(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("successful_steps", C.c_int32), ("termination", C.c_int32),
+                ("jacobian_evaluations", C.c_int32), ("initial_cost", C.c_double), ("final_cost", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+TRACE_COLS = ("cost", "cost_change", "gradient_max_norm", "step_norm", "relative_decrease", "radius", "accepted",
+              "valid")
+
+
+def ba_residual(cam7, X, K4, u, v, inv_sigma2):
+    cam7 = np.ascontiguousarray(cam7, np.float64); X = np.ascontiguousarray(X, np.float64)
+    K4 = np.ascontiguousarray(K4, np.float64)
+    r = np.zeros(2); Jc = np.zeros((2, 6)); Jp = np.zeros((2, 3))
+    lib().ba_oracle_residual(_p(cam7), _p(X), _p(K4), C.c_float(u), C.c_float(v), C.c_float(inv_sigma2), _p(r), _p(Jc),
+                             _p(Jp))
+    return r, Jc, Jp
+
+
+def quat_plus(q, d):
+    q = np.ascontiguousarray(q, np.float64); d = np.ascontiguousarray(d, np.float64); out = np.zeros(4)
+    lib().ba_oracle_quat_plus(_p(q), _p(d), _p(out))
+    return out
+
+
+def ba_solve(cams, cam_const, pts, pts_const, obs_cam, obs_pt, uv, inv_sigma2, mode, K4, max_iterations):
+    """Restated ceres::Solve on a flattened graph.  Returns cams, pts, summary dict, trace [it+1, 8]."""
+    cams = np.array(cams, np.float64, copy=True, order="C"); pts = np.array(pts, np.float64, copy=True, order="C")
+    cc = np.ascontiguousarray(cam_const, np.uint8)
+    oc = np.ascontiguousarray(obs_cam, np.int32); op = np.ascontiguousarray(obs_pt, np.int32)
+    uv = np.ascontiguousarray(uv, np.float32); w = np.ascontiguousarray(inv_sigma2, np.float32)
+    md = None if mode is None else np.ascontiguousarray(mode, np.uint8)
+    K4 = np.ascontiguousarray(K4, np.float64)
+    s = BaSummary(); cap = max_iterations + 2
+    trace = np.zeros((cap, 8))
+    n = lib().ba_oracle_solve(len(cams), _p(cams), _p(cc), len(pts), _p(pts), int(pts_const), len(oc), _p(oc), _p(op),
+                              _p(uv), _p(w), None if md is None else _p(md), _p(K4), int(max_iterations), C.byref(s),
+                              _p(trace), cap)
+    return cams, pts, s.as_dict(), trace[:n]
+
+
+def ba_pose_optimization(pose7, xw, uv, inv_sigma2, K4, max_iterations=100):
+    pose = np.array(pose7, np.float64, copy=True); xw = np.ascontiguousarray(xw, np.float64)
+    uv = np.ascontiguousarray(uv, np.float32); w = np.ascontiguousarray(inv_sigma2, np.float32)
+    K4 = np.ascontiguousarray(K4, np.float64)
+    out = np.zeros(len(xw), np.uint8); s = BaSummary(); cap = max_iterations + 2
+    trace = np.zeros((cap, 8))
+    n_in = lib().ba_oracle_pose_optimization(_p(pose), len(xw), _p(xw), _p(uv), _p(w), _p(K4), int(max_iterations),
+                                             _p(out), C.byref(s), _p(trace), cap)
+    return pose, out, n_in, s.as_dict(), trace[:s.iterations + 1]
+
+
+def ba_local(cams, cam_flags, pts, obs_cam, obs_pt, uv, inv_sigma2, K4, iters=(5, 10)):
+    cams = np.array(cams, np.float64, copy=True, order="C"); pts = np.array(pts, np.float64, copy=True, order="C")
+    cf = np.ascontiguousarray(cam_flags, np.uint8)
+    oc = np.ascontiguousarray(obs_cam, np.int32); op = np.ascontiguousarray(obs_pt, np.int32)
+    uv = np.ascontiguousarray(uv, np.float32); w = np.ascontiguousarray(inv_sigma2, np.float32)
+    K4 = np.ascontiguousarray(K4, np.float64)
+    erase = np.zeros(len(oc), np.uint8); s = (BaSummary * 2)()
+    lib().ba_oracle_local(len(cams), _p(cams), _p(cf), len(pts), _p(pts), len(oc), _p(oc), _p(op), _p(uv), _p(w),
+                          _p(K4), int(iters[0]), int(iters[1]), _p(erase), s)
+    return cams, pts, erase, [s[0].as_dict(), s[1].as_dict()]
+
+
+def ba_global(cams, cam_const, pts, obs_cam, obs_pt, uv, inv_sigma2, K4, n_iterations, robust=True):
+    cams = np.array(cams, np.float64, copy=True, order="C"); pts = np.array(pts, np.float64, copy=True, order="C")
+    cc = np.ascontiguousarray(cam_const, np.uint8)
+    oc = np.ascontiguousarray(obs_cam, np.int32); op = np.ascontiguousarray(obs_pt, np.int32)
+    uv = np.ascontiguousarray(uv, np.float32); w = np.ascontiguousarray(inv_sigma2, np.float32)
+    K4 = np.ascontiguousarray(K4, np.float64)
+    s = BaSummary(); cap = n_iterations + 2; trace = np.zeros((cap, 8))
+    lib().ba_oracle_global(len(cams), _p(cams), _p(cc), len(pts), _p(pts), len(oc), _p(oc), _p(op), _p(uv), _p(w),
+                           _p(K4), int(n_iterations), int(robust), C.byref(s), _p(trace), cap)
+    return cams, pts, s.as_dict(), trace[:s.iterations + 1]
