@@ -7,5 +7,6 @@ Nothing in this package falls back to the CPU.
 from ._lib import KP_DTYPE, CmosError, LIB_PATH  # noqa: F401
 from .orb_extractor import ORBextractor  # noqa: F401
 from .orb_matcher import ORBmatcher, Camera  # noqa: F401
+from .ceres_optimizer import CeresOptimizer  # noqa: F401
 
-__all__ = ["ORBextractor", "ORBmatcher", "Camera", "KP_DTYPE", "CmosError", "LIB_PATH"]
+__all__ = ["ORBextractor", "ORBmatcher", "Camera", "CeresOptimizer", "KP_DTYPE", "CmosError", "LIB_PATH"]

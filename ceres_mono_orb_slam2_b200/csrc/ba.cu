@@ -1,0 +1,1447 @@
+// Bundle-adjustment engine for sm_100a behind CeresOptimizer::{PoseOptimization, LocalBundleAdjustment,
+// BundleAdjustment / GlobalBundleAdjustemnt} (reference src/CeresOptimizer.cc:59-225,275-342,344-599).
+//
+// What the reference does per ceres::Solve — autodiff residual blocks, Huber corrector, quaternion manifold,
+// SPARSE_NORMAL_CHOLESKY inside a Levenberg-Marquardt trust region — is restated here as a fixed sequence of
+// fp64 kernels whose control flow lives on the device (LmState): the host enqueues max_iterations rounds and
+// never synchronises inside a solve.
+//
+//   k_linearize      thread per map point: residual + analytic 2x(6+3) Jacobians of its observations, loss
+//                    weights, the 3x3 point block H_pp, g_p (no atomics: observations are stored point-major)
+//   k_cam_blocks     CTA per variable keyframe: 6x6 block H_cc, g_c over the keyframe's observation list
+//   k_point_prep     (H_pp + D_p^2)^-1 and (H_pp + D_p^2)^-1 g_p per point
+//   k_schur          warp per non-zero 6x6 block (a,b) of the reduced camera system: S_ab = [a==b](H_cc + D_c^2)
+//                    - sum over co-observing points of Jc_a' (Jp_a Hpp^-1 Jp_b') Jc_b; no atomics, fixed order
+//   k_solve_small /  Cholesky of the 6Kv x 6Kv reduced system (one CTA in shared memory up to Kv = 40, a blocked
+//   blocked path     right-looking factorisation in HBM above that), candidate keyframe poses
+//   k_backsub        thread per point: back-substitution, candidate point, candidate cost of its observations
+//   k_decide         step quality, radius schedule, termination tests (device-side LM state machine)
+// PoseOptimization (6 unknowns, constant points) is one persistent CTA per frame that runs the whole solve.
+//
+// Everything is deterministic (no floating-point atomics), so 1-GPU and N-GPU runs and repeated runs agree.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "ba_device.cuh"
+#include "cmos_common.h"
+
+namespace cmos {
+
+#define SYM6(a, b) ((a) * 6 - (a) * ((a) - 1) / 2 + ((b) - (a)))   // a <= b, packed upper triangle of a 6x6
+
+constexpr int kPoseThreads = 256;
+constexpr int kLinThreads = 128;
+constexpr int kCamThreads = 128;
+constexpr int kSolveThreads = 1024;
+constexpr int kSmallMaxN = 234;      // packed lower triangle (+ rhs row) of 234x234 doubles = 221 840 B of shared memory
+constexpr int kNB = 64;              // panel width of the blocked factorisation
+constexpr int kTraceCols = 8;
+constexpr size_t kPanelSmem = 2 * kNB * (kNB + 1) * sizeof(double);   // two 64 x 65 fp64 tiles
+
+// =================================================================================================
+// PoseOptimization: one CTA per frame, whole LM solve in one launch
+// =================================================================================================
+struct PoseArgs {
+  double* pose7;              // [B][7] in/out
+  const int* n_corr;          // [B]
+  const double* xw;           // [B][stride][3]
+  const float* uv;            // [B][stride][2]
+  const float* inv_sigma2;    // [B][stride]
+  int stride;
+  double fx, fy, cx, cy;
+  int max_iterations;
+  uint8_t* is_outlier;        // [B][stride]
+  int* n_inliers;             // [B]
+  cmos_ba_summary* summaries; // [B] or null
+  double* trace;              // [B][trace_rows][8] or null
+  int trace_rows;
+};
+
+__device__ bool chol6_solve(double A[6][6], double* b) {
+  for (int j = 0; j < 6; j++) {
+    double d = A[j][j];
+    for (int k = 0; k < j; k++) d -= A[j][k] * A[j][k];
+    if (!(d > 0.0) || !isfinite(d)) return false;
+    d = sqrt(d);
+    A[j][j] = d;
+    for (int i = j + 1; i < 6; i++) {
+      double s = A[i][j];
+      for (int k = 0; k < j; k++) s -= A[i][k] * A[j][k];
+      A[i][j] = s / d;
+    }
+  }
+  for (int i = 0; i < 6; i++) {
+    double s = b[i];
+    for (int k = 0; k < i; k++) s -= A[i][k] * b[k];
+    b[i] = s / A[i][i];
+  }
+  for (int i = 5; i >= 0; i--) {
+    double s = b[i];
+    for (int k = i + 1; k < 6; k++) s -= A[k][i] * b[k];
+    b[i] = s / A[i][i];
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(kPoseThreads) k_pose_opt(PoseArgs a) {
+  __shared__ double s_pose[2][7];
+  __shared__ double s_red[kPoseThreads / 32][28];
+  __shared__ double s_acc[28];        // 21 H (packed upper) | 6 g | cost
+  __shared__ double s_scale[6];
+  __shared__ double s_scratch[33];
+  __shared__ LmState st;
+  __shared__ double s_mcc, s_step_norm;
+  __shared__ int s_ok;
+
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(a.n_corr[f], a.stride);
+  const double* X = a.xw + (size_t)f * a.stride * 3;
+  const float* uv = a.uv + (size_t)f * a.stride * 2;
+  const float* ws = a.inv_sigma2 + (size_t)f * a.stride;
+  double* trace = a.trace ? a.trace + (size_t)f * a.trace_rows * kTraceCols : nullptr;
+  if (n < 3) {   // CeresOptimizer.cc:330: fewer than 3 correspondences -> return 0, pose untouched
+    if (tid == 0) {
+      a.n_inliers[f] = 0;
+      if (a.summaries) { cmos_ba_summary z; memset(&z, 0, sizeof(z)); a.summaries[f] = z; }
+    }
+    return;
+  }
+  if (tid < 7) s_pose[0][tid] = a.pose7[(size_t)f * 7 + tid];
+  if (tid == 0) lm_init(st, a.max_iterations, 0);
+  __syncthreads();
+
+  for (;;) {
+    if (st.need_lin) {
+      // ---- EvaluateGradientAndJacobian at x ----
+      const double* pose = s_pose[st.cur];
+      double acc[28];
+#pragma unroll
+      for (int k = 0; k < 28; k++) acc[k] = 0.0;
+      for (int i = tid; i < n; i += kPoseThreads) {
+        const Proj P = project_obs(pose, X + 3 * i, a.fx, a.fy, a.cx, a.cy, (double)uv[2 * i], (double)uv[2 * i + 1], (double)ws[i]);
+        double Jc[12], w;
+        jac_cam(P, a.fx, a.fy, (double)ws[i], Jc);
+        acc[27] += loss_eval(P.r0 * P.r0 + P.r1 * P.r1, 1, &w);
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          const double j0 = w * Jc[r], j1 = w * Jc[6 + r];
+#pragma unroll
+          for (int c = r; c < 6; c++) acc[SYM6(r, c)] += j0 * Jc[c] + j1 * Jc[6 + c];
+          acc[21 + r] += j0 * P.r0 + j1 * P.r1;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 28; k++) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) s_red[warp][k] = v;
+      }
+      __syncthreads();
+      if (tid < 28) {
+        double t = 0.0;
+        for (int w2 = 0; w2 < kPoseThreads / 32; w2++) t += s_red[w2][tid];
+        s_acc[tid] = t;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        if (st.first)
+          for (int k = 0; k < 6; k++) s_scale[k] = 1.0 / (1.0 + sqrt(s_acc[SYM6(k, k)]));
+        double xn = 0.0;
+        for (int k = 0; k < 7; k++) xn += pose[k] * pose[k];
+        lm_after_linearize(st, s_acc[27], pose_gradient_max(pose, s_acc + 21), sqrt(xn), trace);
+      }
+      __syncthreads();
+    }
+    if (st.done) break;
+    // ---- LevenbergMarquardtStrategy::ComputeStep on the Jacobi-scaled system (thread 0: 6x6) ----
+    if (tid == 0) {
+      const double* pose = s_pose[st.cur];
+      double* cand = s_pose[st.cur ^ 1];
+      double A[6][6], b[6], D2[6], gs[6];
+      for (int r = 0; r < 6; r++) {
+        D2[r] = fmin(fmax(s_scale[r] * s_scale[r] * s_acc[SYM6(r, r)], kMinLmDiag), kMaxLmDiag) / st.radius;
+        gs[r] = s_scale[r] * s_acc[21 + r];
+        b[r] = gs[r];
+        for (int c = 0; c < 6; c++) {
+          const int lo = r < c ? r : c, hi = r < c ? c : r;
+          A[r][c] = s_scale[r] * s_scale[c] * s_acc[SYM6(lo, hi)] + (r == c ? D2[r] : 0.0);
+        }
+      }
+      bool ok = chol6_solve(A, b);
+      double mcc = 0.0, delta[6];
+      for (int r = 0; r < 6; r++) {
+        const double step = -b[r];
+        if (!isfinite(step)) ok = false;
+        mcc += step * (D2[r] * step - gs[r]);
+        delta[r] = step * s_scale[r];
+      }
+      mcc *= 0.5;
+      double sn = 0.0;
+      if (ok) {
+        for (int k = 0; k < 3; k++) cand[k] = pose[k] + delta[k];
+        quat_plus(pose + 3, delta + 3, cand + 3);
+        for (int k = 0; k < 7; k++) sn += (pose[k] - cand[k]) * (pose[k] - cand[k]);
+      }
+      s_ok = ok; s_mcc = mcc; s_step_norm = sqrt(sn);
+    }
+    __syncthreads();
+    double cand_cost = 0.0;
+    if (s_ok && s_mcc > 0.0) {
+      const double* cand = s_pose[st.cur ^ 1];
+      double c = 0.0, w;
+      for (int i = tid; i < n; i += kPoseThreads) {
+        const Proj P = project_obs(cand, X + 3 * i, a.fx, a.fy, a.cx, a.cy, (double)uv[2 * i], (double)uv[2 * i + 1], (double)ws[i]);
+        c += loss_eval(P.r0 * P.r0 + P.r1 * P.r1, 1, &w);
+      }
+      cand_cost = block_sum(c, s_scratch);
+    }
+    if (tid == 0) lm_decide(st, s_ok != 0, s_mcc, cand_cost, s_step_norm, trace);
+    __syncthreads();
+    if (st.done) break;
+  }
+  // ---- CheckOutliers (:243-269) on the optimised pose, then q.normalized() (:335) ----
+  const double* pose = s_pose[st.cur];
+  int bad = 0;
+  for (int i = tid; i < n; i += kPoseThreads) {
+    const Proj P = project_obs(pose, X + 3 * i, a.fx, a.fy, a.cx, a.cy, (double)uv[2 * i], (double)uv[2 * i + 1], 1.0);
+    const double chi2 = (P.r0 * P.r0 + P.r1 * P.r1) * (double)ws[i];
+    const bool out = chi2 > kChi2;
+    a.is_outlier[(size_t)f * a.stride + i] = out;
+    bad += out;
+  }
+  const double nbad = block_sum((double)bad, s_scratch);
+  if (tid == 0) {
+    a.n_inliers[f] = n - (int)nbad;
+    const double nq = sqrt(pose[3] * pose[3] + pose[4] * pose[4] + pose[5] * pose[5] + pose[6] * pose[6]);
+    for (int k = 0; k < 3; k++) a.pose7[(size_t)f * 7 + k] = pose[k];
+    for (int k = 3; k < 7; k++) a.pose7[(size_t)f * 7 + k] = pose[k] / nq;
+    if (a.summaries) {
+      cmos_ba_summary s;
+      s.iterations = st.iteration; s.successful_steps = st.successful; s.termination = st.termination;
+      s.jacobian_evaluations = st.jac_evals; s.initial_cost = st.initial_cost; s.final_cost = st.x_cost;
+      a.summaries[f] = s;
+    }
+  }
+}
+
+// =================================================================================================
+// General engine (LocalBundleAdjustment / BundleAdjustment)
+// =================================================================================================
+struct BaDev {
+  int K, Kv, M, N, n_blocks, nc;            // nc = 6 * Kv
+  double fx, fy, cx, cy;
+  double* cams[2];                          // [K][7]
+  double* pts[2];                           // [M][3]
+  const int* cam_var;                       // [K]
+  const int *o_cam, *o_cv, *o_pt;           // [N] point-major
+  const float2* o_uv;
+  const float* o_w;
+  uint8_t* o_mode;
+  const int* pt_start;                      // [M+1]
+  const int *cam_start, *cam_obs;           // [Kv+1], [#obs of variable keyframes]
+  const int *blk_a, *blk_b, *blk_start;     // [n_blocks], [n_blocks], [n_blocks+1]
+  const int *pair_a, *pair_b;               // observation pairs of every block
+  double *Jc, *Jp, *res;                    // [N][12], [N][6], [N][2]  (rows already weighted by sqrt(rho'))
+  double *Hpp, *gp, *Hinv, *tp, *scale_p;   // [M][6], [M][3], [M][6], [M][3], [M][3]
+  double *Hcc, *gc, *scale_c;               // [Kv][21], [Kv][6], [Kv][6]
+  double *S, *rhs, *yc;                     // [nc][nc] lower, [nc], [nc]
+  double *part;                             // partial sums, see offsets
+  int n_lin_blocks;
+  // offsets into part
+  int o_lin_cost, o_lin_gmax, o_lin_xn2, o_cam_gmax, o_cam_xn2, o_bs_cost, o_bs_mcc, o_bs_sn2, o_cam_mcc, o_cam_sn2;
+  LmState* st;
+  double* trace;                            // [rows][8] of the running pass, or null
+  const volatile uint8_t* stop_flag;        // mapped host byte or null
+};
+
+// `pad` of LmState doubles as the "aborted" flag: LocalBundleAdjustment returns without writing anything back
+// when the stop flag is up at the start of a pass (CeresOptimizer.cc:509-512).
+__global__ void k_lm_init(BaDev d, int max_iterations) {
+  const int cur = d.st->cur, aborted = d.st->pad;
+  lm_init(*d.st, max_iterations, cur & 1);
+  d.st->pad = aborted;
+  if (aborted || (d.stop_flag && *d.stop_flag)) { d.st->pad = 1; d.st->done = 1; d.st->termination = TERM_USER; }
+}
+
+__global__ void __launch_bounds__(kLinThreads) k_linearize(BaDev d) {
+  __shared__ double scratch[33];
+  const LmState& st = *d.st;
+  if (st.done || !st.need_lin) return;
+  const int j = blockIdx.x * kLinThreads + threadIdx.x;
+  const double* cams = d.cams[st.cur];
+  const double* pts = d.pts[st.cur];
+  double cost = 0.0, gmax = 0.0, xn2 = 0.0;
+  if (j < d.M) {
+    const double X[3] = {pts[3 * j], pts[3 * j + 1], pts[3 * j + 2]};
+    double H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+    for (int p = d.pt_start[j]; p < d.pt_start[j + 1]; p++) {
+      const int cam = d.o_cam[p];
+      const float2 uv = d.o_uv[p];
+      const double w = (double)d.o_w[p];
+      const double* c = cams + 7 * (size_t)cam;
+      const Proj P = project_obs(c, X, d.fx, d.fy, d.cx, d.cy, (double)uv.x, (double)uv.y, w);
+      double wsum;
+      cost += loss_eval(P.r0 * P.r0 + P.r1 * P.r1, d.o_mode[p], &wsum);
+      const double sw = sqrt(wsum);
+      double Jp[6];
+      jac_point(P, c, d.fx, d.fy, w, Jp);
+#pragma unroll
+      for (int k = 0; k < 6; k++) Jp[k] *= sw;
+      const double r0 = sw * P.r0, r1 = sw * P.r1;
+      H[0] += Jp[0] * Jp[0] + Jp[3] * Jp[3]; H[1] += Jp[0] * Jp[1] + Jp[3] * Jp[4]; H[2] += Jp[0] * Jp[2] + Jp[3] * Jp[5];
+      H[3] += Jp[1] * Jp[1] + Jp[4] * Jp[4]; H[4] += Jp[1] * Jp[2] + Jp[4] * Jp[5]; H[5] += Jp[2] * Jp[2] + Jp[5] * Jp[5];
+      g[0] += Jp[0] * r0 + Jp[3] * r1; g[1] += Jp[1] * r0 + Jp[4] * r1; g[2] += Jp[2] * r0 + Jp[5] * r1;
+      double2* jp = (double2*)(d.Jp + 6 * (size_t)p);
+      jp[0] = make_double2(Jp[0], Jp[1]); jp[1] = make_double2(Jp[2], Jp[3]); jp[2] = make_double2(Jp[4], Jp[5]);
+      *(double2*)(d.res + 2 * (size_t)p) = make_double2(r0, r1);
+      if (d.o_cv[p] >= 0) {
+        double Jc[12];
+        jac_cam(P, d.fx, d.fy, w, Jc);
+        double2* jc = (double2*)(d.Jc + 12 * (size_t)p);
+#pragma unroll
+        for (int k = 0; k < 6; k++) jc[k] = make_double2(sw * Jc[2 * k], sw * Jc[2 * k + 1]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) d.Hpp[6 * (size_t)j + k] = H[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) d.gp[3 * (size_t)j + k] = g[k];
+    if (st.first) {
+      d.scale_p[3 * (size_t)j] = 1.0 / (1.0 + sqrt(H[0]));
+      d.scale_p[3 * (size_t)j + 1] = 1.0 / (1.0 + sqrt(H[3]));
+      d.scale_p[3 * (size_t)j + 2] = 1.0 / (1.0 + sqrt(H[5]));
+    }
+    gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
+    xn2 = X[0] * X[0] + X[1] * X[1] + X[2] * X[2];
+  }
+  cost = block_sum(cost, scratch);
+  gmax = block_max(gmax, scratch);
+  xn2 = block_sum(xn2, scratch);
+  if (threadIdx.x == 0) {
+    d.part[d.o_lin_cost + blockIdx.x] = cost;
+    d.part[d.o_lin_gmax + blockIdx.x] = gmax;
+    d.part[d.o_lin_xn2 + blockIdx.x] = xn2;
+  }
+}
+
+__global__ void __launch_bounds__(kCamThreads) k_cam_blocks(BaDev d) {
+  __shared__ double s_red[kCamThreads / 32][27];
+  const LmState& st = *d.st;
+  if (st.done || !st.need_lin) return;
+  const int a = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double acc[27];
+#pragma unroll
+  for (int k = 0; k < 27; k++) acc[k] = 0.0;
+  for (int e = d.cam_start[a] + tid; e < d.cam_start[a + 1]; e += kCamThreads) {
+    const int p = d.cam_obs[e];
+    double Jc[12];
+    const double2* jc = (const double2*)(d.Jc + 12 * (size_t)p);
+#pragma unroll
+    for (int k = 0; k < 6; k++) { const double2 v = jc[k]; Jc[2 * k] = v.x; Jc[2 * k + 1] = v.y; }
+    const double2 r = *(const double2*)(d.res + 2 * (size_t)p);
+#pragma unroll
+    for (int rr = 0; rr < 6; rr++) {
+#pragma unroll
+      for (int c = rr; c < 6; c++) acc[SYM6(rr, c)] += Jc[rr] * Jc[c] + Jc[6 + rr] * Jc[6 + c];
+      acc[21 + rr] += Jc[rr] * r.x + Jc[6 + rr] * r.y;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 27; k++) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) s_red[warp][k] = v;
+  }
+  __syncthreads();
+  __shared__ double s_out[27];
+  if (tid < 27) {
+    double t = 0.0;
+    for (int w = 0; w < kCamThreads / 32; w++) t += s_red[w][tid];
+    s_out[tid] = t;
+    if (tid < 21) d.Hcc[21 * (size_t)a + tid] = t; else d.gc[6 * (size_t)a + tid - 21] = t;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (st.first)
+      for (int k = 0; k < 6; k++) d.scale_c[6 * (size_t)a + k] = 1.0 / (1.0 + sqrt(s_out[SYM6(k, k)]));
+    // the variable keyframe's pose: find it through the first observation (every variable keyframe has one)
+    int cam = -1;
+    if (d.cam_start[a + 1] > d.cam_start[a]) cam = d.o_cam[d.cam_obs[d.cam_start[a]]];
+    double gm = 0.0, xn2 = 0.0;
+    if (cam >= 0) {
+      const double* c = d.cams[st.cur] + 7 * (size_t)cam;
+      gm = pose_gradient_max(c, s_out + 21);
+      for (int k = 0; k < 7; k++) xn2 += c[k] * c[k];
+    }
+    d.part[d.o_cam_gmax + a] = gm;
+    d.part[d.o_cam_xn2 + a] = xn2;
+  }
+}
+
+// strided, fixed-order sum / max of a partial array by one CTA
+__device__ double part_sum(const double* p, int n, double* scratch) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += p[i];
+  return block_sum(v, scratch);
+}
+__device__ double part_max(const double* p, int n, double* scratch) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v = fmax(v, p[i]);
+  return block_max(v, scratch);
+}
+
+__global__ void __launch_bounds__(256) k_post_lin(BaDev d) {
+  __shared__ double scratch[33];
+  LmState& st = *d.st;
+  if (st.done || !st.need_lin) return;
+  const double cost = part_sum(d.part + d.o_lin_cost, d.n_lin_blocks, scratch);
+  const double g1 = part_max(d.part + d.o_lin_gmax, d.n_lin_blocks, scratch);
+  const double g2 = part_max(d.part + d.o_cam_gmax, d.Kv, scratch);
+  const double x1 = part_sum(d.part + d.o_lin_xn2, d.n_lin_blocks, scratch);
+  const double x2 = part_sum(d.part + d.o_cam_xn2, d.Kv, scratch);
+  if (threadIdx.x == 0) {
+    lm_after_linearize(st, cost, fmax(g1, g2), sqrt(x1 + x2), d.trace);
+    if (!st.done && d.stop_flag && *d.stop_flag) { st.done = 1; st.termination = TERM_USER; }   // StopFlagCallback
+  }
+}
+
+__global__ void __launch_bounds__(kLinThreads) k_point_prep(BaDev d) {
+  LmState& st = *d.st;
+  if (st.done) return;
+  const int j = blockIdx.x * kLinThreads + threadIdx.x;
+  if (j >= d.M) return;
+  const double* H = d.Hpp + 6 * (size_t)j;
+  const double s0 = d.scale_p[3 * (size_t)j], s1 = d.scale_p[3 * (size_t)j + 1], s2 = d.scale_p[3 * (size_t)j + 2];
+  const double ir = 1.0 / st.radius;
+  (void)ir;
+  double A[6];
+  A[0] = s0 * s0 * H[0]; A[1] = s0 * s1 * H[1]; A[2] = s0 * s2 * H[2];
+  A[3] = s1 * s1 * H[3]; A[4] = s1 * s2 * H[4]; A[5] = s2 * s2 * H[5];
+  A[0] += fmin(fmax(A[0], kMinLmDiag), kMaxLmDiag) / st.radius;
+  A[3] += fmin(fmax(A[3], kMinLmDiag), kMaxLmDiag) / st.radius;
+  A[5] += fmin(fmax(A[5], kMinLmDiag), kMaxLmDiag) / st.radius;
+  double inv[6];
+  if (!invert3_sym(A, inv)) {
+    st.solve_failed = 1;   // benign race: every writer stores 1
+#pragma unroll
+    for (int k = 0; k < 6; k++) inv[k] = 0.0;
+  }
+  const double g0 = s0 * d.gp[3 * (size_t)j], g1 = s1 * d.gp[3 * (size_t)j + 1], g2 = s2 * d.gp[3 * (size_t)j + 2];
+#pragma unroll
+  for (int k = 0; k < 6; k++) d.Hinv[6 * (size_t)j + k] = inv[k];
+  d.tp[3 * (size_t)j] = inv[0] * g0 + inv[1] * g1 + inv[2] * g2;
+  d.tp[3 * (size_t)j + 1] = inv[1] * g0 + inv[3] * g1 + inv[4] * g2;
+  d.tp[3 * (size_t)j + 2] = inv[2] * g0 + inv[4] * g1 + inv[5] * g2;
+}
+
+__device__ __forceinline__ void load_jc_scaled(const BaDev& d, int p, const double* sc, double* Jc) {
+  const double2* jc = (const double2*)(d.Jc + 12 * (size_t)p);
+#pragma unroll
+  for (int k = 0; k < 6; k++) { const double2 v = jc[k]; Jc[2 * k] = v.x; Jc[2 * k + 1] = v.y; }
+#pragma unroll
+  for (int k = 0; k < 6; k++) { Jc[k] *= sc[k]; Jc[6 + k] *= sc[k]; }
+}
+__device__ __forceinline__ void load_jp_scaled(const BaDev& d, int p, int j, double* Jp) {
+  const double2* jp = (const double2*)(d.Jp + 6 * (size_t)p);
+  const double2 v0 = jp[0], v1 = jp[1], v2 = jp[2];
+  const double s0 = d.scale_p[3 * (size_t)j], s1 = d.scale_p[3 * (size_t)j + 1], s2 = d.scale_p[3 * (size_t)j + 2];
+  Jp[0] = v0.x * s0; Jp[1] = v0.y * s1; Jp[2] = v1.x * s2; Jp[3] = v1.y * s0; Jp[4] = v2.x * s1; Jp[5] = v2.y * s2;
+}
+
+// warp per non-zero block (a,b), a <= b (variable-keyframe indices); writes the lower-triangle copy S[b][a]
+__global__ void __launch_bounds__(128) k_schur(BaDev d) {
+  const LmState& st = *d.st;
+  if (st.done) return;
+  const int blk = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (blk >= d.n_blocks) return;
+  const int a = d.blk_a[blk], b = d.blk_b[blk];
+  double sca[6], scb[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) { sca[k] = d.scale_c[6 * (size_t)a + k]; scb[k] = d.scale_c[6 * (size_t)b + k]; }
+  double acc[36], racc[6];
+#pragma unroll
+  for (int k = 0; k < 36; k++) acc[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; k++) racc[k] = 0.0;
+  for (int e = d.blk_start[blk] + lane; e < d.blk_start[blk + 1]; e += 32) {
+    const int pa = d.pair_a[e], pb = d.pair_b[e];
+    const int j = d.o_pt[pa];
+    double Jca[12], Jpa[6], Jpb[6], U[12];
+    load_jc_scaled(d, pa, sca, Jca);
+    load_jp_scaled(d, pa, j, Jpa);
+    const double* Hi = d.Hinv + 6 * (size_t)j;
+    const double h0 = Hi[0], h1 = Hi[1], h2 = Hi[2], h3 = Hi[3], h4 = Hi[4], h5 = Hi[5];
+    // V = Jp_a * Hinv (2x3)
+    const double V00 = Jpa[0] * h0 + Jpa[1] * h1 + Jpa[2] * h2, V01 = Jpa[0] * h1 + Jpa[1] * h3 + Jpa[2] * h4,
+                 V02 = Jpa[0] * h2 + Jpa[1] * h4 + Jpa[2] * h5;
+    const double V10 = Jpa[3] * h0 + Jpa[4] * h1 + Jpa[5] * h2, V11 = Jpa[3] * h1 + Jpa[4] * h3 + Jpa[5] * h4,
+                 V12 = Jpa[3] * h2 + Jpa[4] * h4 + Jpa[5] * h5;
+    if (pa == pb) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) Jpb[k] = Jpa[k];
+#pragma unroll
+      for (int k = 0; k < 12; k++) U[k] = Jca[k];
+      // rhs: Jc_a' (Jp_a (Hpp^-1 g_p))
+      const double* t = d.tp + 3 * (size_t)j;
+      const double q0 = Jpa[0] * t[0] + Jpa[1] * t[1] + Jpa[2] * t[2], q1 = Jpa[3] * t[0] + Jpa[4] * t[1] + Jpa[5] * t[2];
+#pragma unroll
+      for (int k = 0; k < 6; k++) racc[k] += Jca[k] * q0 + Jca[6 + k] * q1;
+    } else {
+      load_jp_scaled(d, pb, j, Jpb);
+      load_jc_scaled(d, pb, scb, U);
+    }
+    // Q = V * Jp_b' (2x2)
+    const double Q00 = V00 * Jpb[0] + V01 * Jpb[1] + V02 * Jpb[2], Q01 = V00 * Jpb[3] + V01 * Jpb[4] + V02 * Jpb[5];
+    const double Q10 = V10 * Jpb[0] + V11 * Jpb[1] + V12 * Jpb[2], Q11 = V10 * Jpb[3] + V11 * Jpb[4] + V12 * Jpb[5];
+    // U = Q * Jc_b (2x6), acc += Jc_a' U
+    double U0[6], U1[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { U0[k] = Q00 * U[k] + Q01 * U[6 + k]; U1[k] = Q10 * U[k] + Q11 * U[6 + k]; }
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) acc[r * 6 + c] += Jca[r] * U0[c] + Jca[6 + r] * U1[c];
+  }
+#pragma unroll
+  for (int k = 0; k < 36; k++) acc[k] = warp_sum(acc[k]);
+  if (a == b) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) racc[k] = warp_sum(racc[k]);
+  }
+  // lane l writes entries l and l+32 (36 values); diagonal blocks add H_cc + D^2 and emit the rhs
+  const double* Hc = d.Hcc + 21 * (size_t)a;
+  for (int idx = lane; idx < 36; idx += 32) {
+    const int r = idx / 6, c = idx - 6 * r;
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 36; k++) if (k == idx) v = acc[k];
+    v = -v;
+    if (a == b) {
+      const int lo = r < c ? r : c, hi = r < c ? c : r;
+      const double h = sca[r] * sca[c] * Hc[SYM6(lo, hi)];
+      v += h;
+      if (r == c) v += fmin(fmax(h, kMinLmDiag), kMaxLmDiag) / st.radius;
+    }
+    // value is S[a-block row r][b-block col c]; store transposed into the lower triangle
+    d.S[(size_t)(6 * b + c) * d.nc + 6 * a + r] = v;
+  }
+  if (a == b && lane < 6) {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) if (k == lane) v = racc[k];
+    d.rhs[6 * a + lane] = sca[lane] * d.gc[6 * (size_t)a + lane] - v;
+  }
+}
+
+// candidate keyframe poses from the solved reduced system + the keyframes' share of the step statistics
+__device__ void cam_candidate(const BaDev& d, const LmState& st, int cam) {
+  const int a = d.cam_var[cam];
+  const double* c = d.cams[st.cur] + 7 * (size_t)cam;
+  double* cc = d.cams[st.cur ^ 1] + 7 * (size_t)cam;
+  if (a < 0) {   // constant keyframes are identical in both buffers (set at upload)
+    return;
+  }
+  const double* Hc = d.Hcc + 21 * (size_t)a;
+  double delta[6], mcc = 0.0;
+  for (int k = 0; k < 6; k++) {
+    const double s = d.scale_c[6 * (size_t)a + k];
+    const double step = -d.yc[6 * a + k];
+    const double D2 = fmin(fmax(s * s * Hc[SYM6(k, k)], kMinLmDiag), kMaxLmDiag) / st.radius;
+    mcc += step * (D2 * step - s * d.gc[6 * (size_t)a + k]);
+    delta[k] = step * s;
+  }
+  for (int k = 0; k < 3; k++) cc[k] = c[k] + delta[k];
+  quat_plus(c + 3, delta + 3, cc + 3);
+  double sn2 = 0.0;
+  for (int k = 0; k < 7; k++) sn2 += (c[k] - cc[k]) * (c[k] - cc[k]);
+  d.part[d.o_cam_mcc + a] = 0.5 * mcc;
+  d.part[d.o_cam_sn2 + a] = sn2;
+}
+
+// Cholesky of the reduced camera system in shared memory (packed lower triangle, rhs as an extra row so the
+// forward substitution rides on the factorisation), back substitution by one warp, then candidate poses.
+__global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
+  extern __shared__ double L[];   // rows 0..n (row n = rhs), row i at i*(i+1)/2
+  LmState& st = *d.st;
+  if (st.done) return;
+  const int n = d.nc, tid = threadIdx.x;
+  __shared__ int s_fail;
+  if (tid == 0) s_fail = st.solve_failed;
+  for (int idx = tid; idx < n * n; idx += kSolveThreads) {
+    const int i = idx / n, k = idx - i * n;
+    if (k <= i) L[i * (i + 1) / 2 + k] = d.S[(size_t)i * n + k];
+  }
+  for (int k = tid; k < n; k += kSolveThreads) L[n * (n + 1) / 2 + k] = d.rhs[k];
+  __syncthreads();
+  for (int j = 0; j < n; j++) {
+    const double djj = L[j * (j + 1) / 2 + j];
+    if (!(djj > 0.0) || !isfinite(djj)) { if (tid == 0) s_fail = 1; break; }   // uniform: all threads read the same value
+    const double ljj = sqrt(djj);
+    __syncthreads();
+    for (int i = j + tid; i <= n; i += kSolveThreads) {
+      if (i == j) L[j * (j + 1) / 2 + j] = ljj; else L[i * (i + 1) / 2 + j] /= ljj;
+    }
+    __syncthreads();
+    const int m = n - j;   // rows j+1 .. n
+    for (int idx = tid; idx < m * m; idx += kSolveThreads) {
+      const int ii = idx / m, kk = idx - ii * m;
+      const int i = j + 1 + ii, k = j + 1 + kk;
+      if (k <= i && k < n) L[i * (i + 1) / 2 + k] -= L[i * (i + 1) / 2 + j] * L[k * (k + 1) / 2 + j];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid < 32) {
+    // back substitution L' x = y, y = row n
+    double* y = L + n * (n + 1) / 2;
+    if (!s_fail) {
+      for (int j = n - 1; j >= 0; j--) {
+        const double xj = y[j] / L[j * (j + 1) / 2 + j];
+        __syncwarp();
+        if (tid == 0) y[j] = xj;
+        for (int k = tid; k < j; k += 32) y[k] -= L[j * (j + 1) / 2 + k] * xj;
+        __syncwarp();
+      }
+    }
+    for (int k = tid; k < n; k += 32) {
+      const double v = s_fail ? 0.0 : y[k];
+      d.yc[k] = v;
+      if (!isfinite(v)) s_fail = 1;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) st.solve_failed = s_fail;
+  if (!s_fail)
+    for (int cam = tid; cam < d.K; cam += kSolveThreads) cam_candidate(d, st, cam);
+}
+
+__global__ void __launch_bounds__(kLinThreads) k_backsub(BaDev d) {
+  __shared__ double scratch[33];
+  const LmState& st = *d.st;
+  if (st.done) return;
+  const int j = blockIdx.x * kLinThreads + threadIdx.x;
+  double cost = 0.0, mcc = 0.0, sn2 = 0.0;
+  if (j < d.M && !st.solve_failed) {
+    const double* cams_c = d.cams[st.cur ^ 1];
+    const double* X = d.pts[st.cur] + 3 * (size_t)j;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    for (int p = d.pt_start[j]; p < d.pt_start[j + 1]; p++) {
+      const int a = d.o_cv[p];
+      if (a < 0) continue;
+      double Jc[12], Jp[6];
+      load_jc_scaled(d, p, d.scale_c + 6 * (size_t)a, Jc);
+      load_jp_scaled(d, p, j, Jp);
+      const double* y = d.yc + 6 * a;
+      double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) { v0 += Jc[k] * y[k]; v1 += Jc[6 + k] * y[k]; }
+      acc0 += Jp[0] * v0 + Jp[3] * v1; acc1 += Jp[1] * v0 + Jp[4] * v1; acc2 += Jp[2] * v0 + Jp[5] * v1;
+    }
+    const double* Hi = d.Hinv + 6 * (size_t)j;
+    const double* t = d.tp + 3 * (size_t)j;
+    // y_p = Hpp^-1 (g_p - W' y_c) ; step = -y_p
+    const double step[3] = {-(t[0] - (Hi[0] * acc0 + Hi[1] * acc1 + Hi[2] * acc2)),
+                            -(t[1] - (Hi[1] * acc0 + Hi[3] * acc1 + Hi[4] * acc2)),
+                            -(t[2] - (Hi[2] * acc0 + Hi[4] * acc1 + Hi[5] * acc2))};
+    const double* H = d.Hpp + 6 * (size_t)j;
+    const double hd[3] = {H[0], H[3], H[5]};
+    double Xc[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double s = d.scale_p[3 * (size_t)j + k];
+      const double D2 = fmin(fmax(s * s * hd[k], kMinLmDiag), kMaxLmDiag) / st.radius;
+      mcc += step[k] * (D2 * step[k] - s * d.gp[3 * (size_t)j + k]);
+      const double delta = step[k] * s;
+      Xc[k] = X[k] + delta;
+      sn2 += (X[k] - Xc[k]) * (X[k] - Xc[k]);
+    }
+    mcc *= 0.5;
+    double* Xo = d.pts[st.cur ^ 1] + 3 * (size_t)j;
+    Xo[0] = Xc[0]; Xo[1] = Xc[1]; Xo[2] = Xc[2];
+    for (int p = d.pt_start[j]; p < d.pt_start[j + 1]; p++) {
+      const float2 uv = d.o_uv[p];
+      const Proj P = project_obs(cams_c + 7 * (size_t)d.o_cam[p], Xc, d.fx, d.fy, d.cx, d.cy, (double)uv.x, (double)uv.y,
+                                 (double)d.o_w[p]);
+      double w;
+      cost += loss_eval(P.r0 * P.r0 + P.r1 * P.r1, d.o_mode[p], &w);
+    }
+  }
+  cost = block_sum(cost, scratch);
+  mcc = block_sum(mcc, scratch);
+  sn2 = block_sum(sn2, scratch);
+  if (threadIdx.x == 0) {
+    d.part[d.o_bs_cost + blockIdx.x] = cost;
+    d.part[d.o_bs_mcc + blockIdx.x] = mcc;
+    d.part[d.o_bs_sn2 + blockIdx.x] = sn2;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_decide(BaDev d) {
+  __shared__ double scratch[33];
+  LmState& st = *d.st;
+  if (st.done) return;
+  const bool ok = !st.solve_failed;
+  double cost = 0, mcc = 0, sn2 = 0;
+  if (ok) {
+    cost = part_sum(d.part + d.o_bs_cost, d.n_lin_blocks, scratch);
+    mcc = part_sum(d.part + d.o_bs_mcc, d.n_lin_blocks, scratch) + part_sum(d.part + d.o_cam_mcc, d.Kv, scratch);
+    sn2 = part_sum(d.part + d.o_bs_sn2, d.n_lin_blocks, scratch) + part_sum(d.part + d.o_cam_sn2, d.Kv, scratch);
+  }
+  if (threadIdx.x == 0) {
+    lm_decide(st, ok, mcc, cost, sqrt(sn2), d.trace);
+    st.solve_failed = 0;
+    if (!st.done && d.stop_flag && *d.stop_flag) { st.done = 1; st.termination = TERM_USER; }
+  }
+}
+
+// CheckOutlier (:227-241) + the z <= 0 test (:558-564) over the observations of local keyframes; also sets the
+// per-observation loss mode of the next pass (quirk Q2) and copies the pass summary out.
+__global__ void __launch_bounds__(256) k_outlier_scan(BaDev d, const uint8_t* __restrict__ cam_flags,
+                                                      const int* __restrict__ perm, uint8_t* __restrict__ erase,
+                                                      int set_mode) {
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= d.N) return;
+  const int cur = d.st->cur;
+  const int cam = d.o_cam[p];
+  uint8_t e = 0;
+  if (!(cam_flags[cam] & 2) && !d.st->pad) {
+    const float2 uv = d.o_uv[p];
+    const Proj P = project_obs(d.cams[cur] + 7 * (size_t)cam, d.pts[cur] + 3 * (size_t)d.o_pt[p], d.fx, d.fy, d.cx, d.cy,
+                               (double)uv.x, (double)uv.y, 1.0);
+    const double chi2 = (P.r0 * P.r0 + P.r1 * P.r1) * (double)d.o_w[p];
+    e = (chi2 > kChi2) || (P.p2 <= 0.0);
+  }
+  erase[perm[p]] = e;
+  if (set_mode) d.o_mode[p] = e ? 1 : 3;
+}
+
+__global__ void k_set_mode(BaDev d, int mode) {
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p < d.N) d.o_mode[p] = (uint8_t)mode;
+}
+
+__global__ void k_summary(BaDev d, cmos_ba_summary* out) {
+  const LmState& st = *d.st;
+  cmos_ba_summary s;
+  s.iterations = st.iteration; s.successful_steps = st.successful; s.termination = st.termination;
+  s.jacobian_evaluations = st.jac_evals; s.initial_cost = st.initial_cost; s.final_cost = st.x_cost;
+  *out = s;
+}
+
+// final parameters always end up in buffer 0 of the handle's "result" view
+__global__ void k_gather_result(BaDev d, const double* cams0, const double* pts0, double* cams_out, double* pts_out) {
+  const int cur = d.st->cur, aborted = d.st->pad;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < 7 * d.K) cams_out[i] = aborted ? cams0[i] : d.cams[cur][i];
+  if (i < 3 * d.M) pts_out[i] = aborted ? pts0[i] : d.pts[cur][i];
+}
+
+// -------------------------------------------------------------------------------------------------
+// Blocked right-looking Cholesky in HBM for reduced systems that do not fit one CTA's shared memory
+// (GlobalBundleAdjustemnt: 6000 x 6000 at 1000 keyframes).  Row-major lower triangle, panel width kNB.
+// The rhs is carried as row n (so the forward substitution is part of the factorisation); the inverses of
+// the diagonal panels are kept so that the panel solve and the back substitution are plain products.
+// -------------------------------------------------------------------------------------------------
+// factor the kb x kb diagonal block at (k0,k0) in place and store inv(L11) (lower) into Linv[panel]
+__global__ void __launch_bounds__(256) k_potrf_diag(BaDev d, int k0, int kb, double* Linv) {
+  extern __shared__ double dyn_smem[];
+  double (*A)[kNB + 1] = (double (*)[kNB + 1])dyn_smem;
+  double (*Li)[kNB + 1] = (double (*)[kNB + 1])(dyn_smem + kNB * (kNB + 1));
+  __shared__ int s_fail;
+  LmState& st = *d.st;
+  if (st.done || st.solve_failed) return;
+  const int n = d.nc, tid = threadIdx.x;
+  if (tid == 0) s_fail = 0;
+  for (int idx = tid; idx < kb * kb; idx += 256) {
+    const int i = idx / kb, k = idx - i * kb;
+    A[i][k] = k <= i ? d.S[(size_t)(k0 + i) * n + k0 + k] : 0.0;
+    Li[i][k] = 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < kb; j++) {
+    const double djj = A[j][j];
+    if (!(djj > 0.0) || !isfinite(djj)) { if (tid == 0) s_fail = 1; break; }
+    const double ljj = sqrt(djj);
+    __syncthreads();
+    for (int i = j + tid; i < kb; i += 256) { if (i == j) A[j][j] = ljj; else A[i][j] /= ljj; }
+    __syncthreads();
+    const int m = kb - j - 1;
+    for (int idx = tid; idx < m * m; idx += 256) {
+      const int ii = idx / m, kk = idx - ii * m;
+      const int i = j + 1 + ii, k = j + 1 + kk;
+      if (k <= i) A[i][k] -= A[i][j] * A[k][j];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (s_fail) { if (tid == 0) st.solve_failed = 1; return; }
+  // inverse of the lower-triangular factor: column c by forward substitution, one thread per column
+  if (tid < kb) {
+    const int c = tid;
+    for (int i = c; i < kb; i++) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; k++) s -= A[i][k] * Li[k][c];
+      Li[i][c] = s / A[i][i];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < kb * kb; idx += 256) {
+    const int i = idx / kb, k = idx - i * kb;
+    if (k <= i) d.S[(size_t)(k0 + i) * n + k0 + k] = A[i][k];
+    Linv[(size_t)(k0 / kNB) * kNB * kNB + i * kNB + k] = Li[i][k];
+  }
+}
+
+// panel solve: rows i > k0+kb (and the rhs row): L21[i][:] = A21[i][:] * inv(L11)'  -> L21[i][c] = sum_k A21[i][k] Linv[c][k]
+__global__ void __launch_bounds__(256) k_trsm_panel(BaDev d, int k0, int kb, const double* __restrict__ Linv) {
+  extern __shared__ double dyn_smem[];
+  double (*Li)[kNB + 1] = (double (*)[kNB + 1])dyn_smem;
+  double (*Arow)[kNB + 1] = (double (*)[kNB + 1])(dyn_smem + kNB * (kNB + 1));
+  const LmState& st = *d.st;
+  if (st.done || st.solve_failed) return;
+  const int n = d.nc, tid = threadIdx.x;
+  const double* Lp = Linv + (size_t)(k0 / kNB) * kNB * kNB;
+  for (int idx = tid; idx < kNB * kNB; idx += 256) Li[idx / kNB][idx % kNB] = Lp[idx];
+  const int row0 = k0 + kb + blockIdx.x * 32;   // rows row0..row0+31; logical row n = rhs
+  for (int idx = tid; idx < 32 * kb; idx += 256) {
+    const int r = idx / kb, k = idx - r * kb;
+    const int i = row0 + r;
+    double v = 0.0;
+    if (i < n) v = d.S[(size_t)i * n + k0 + k];
+    else if (i == n) v = d.rhs[k0 + k];
+    Arow[r][k] = v;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 32 * kb; idx += 256) {
+    const int r = idx / kb, c = idx - r * kb;
+    const int i = row0 + r;
+    if (i > n) continue;
+    double s = 0.0;
+    for (int k = 0; k <= c; k++) s += Arow[r][k] * Li[c][k];
+    if (i < n) d.S[(size_t)i * n + k0 + c] = s; else d.rhs[k0 + c] = s;
+  }
+}
+
+// trailing update: A22 -= L21 L21' on 64x64 tiles of the lower triangle (and the rhs row), 256 threads, 4x4 per thread
+__global__ void __launch_bounds__(256) k_syrk_tile(BaDev d, int k0, int kb) {
+  extern __shared__ double dyn_smem[];
+  double (*As)[64 + 1] = (double (*)[64 + 1])dyn_smem;                      // [k][i]
+  double (*Bs)[64 + 1] = (double (*)[64 + 1])(dyn_smem + kNB * (64 + 1));   // [k][j]
+  const LmState& st = *d.st;
+  if (st.done || st.solve_failed) return;
+  const int n = d.nc, tid = threadIdx.x;
+  const int t0 = k0 + kb;
+  // tile coordinates in the trailing matrix from the linear block index (lower triangle incl. diagonal)
+  int bi = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((bi + 1) * (bi + 2) / 2 <= (int)blockIdx.x) bi++;
+  while (bi * (bi + 1) / 2 > (int)blockIdx.x) bi--;
+  const int bj = blockIdx.x - bi * (bi + 1) / 2;
+  const int i0 = t0 + bi * 64, j0 = t0 + bj * 64;
+  for (int idx = tid; idx < 64 * kb; idx += 256) {
+    const int r = idx / kb, k = idx - r * kb;
+    const int i = i0 + r, j = j0 + r;
+    double va = 0.0, vb = 0.0;
+    if (i < n) va = d.S[(size_t)i * n + k0 + k]; else if (i == n) va = d.rhs[k0 + k];
+    if (j < n) vb = d.S[(size_t)j * n + k0 + k];
+    As[k][r] = va; Bs[k][r] = vb;
+  }
+  __syncthreads();
+  const int ti = (tid >> 4) * 4, tj = (tid & 15) * 4;
+  double acc[4][4] = {};
+  for (int k = 0; k < kb; k++) {
+    double av[4], bv[4];
+#pragma unroll
+    for (int x = 0; x < 4; x++) { av[x] = As[k][ti + x]; bv[x] = Bs[k][tj + x]; }
+#pragma unroll
+    for (int x = 0; x < 4; x++)
+#pragma unroll
+      for (int y = 0; y < 4; y++) acc[x][y] += av[x] * bv[y];
+  }
+#pragma unroll
+  for (int x = 0; x < 4; x++) {
+    const int i = i0 + ti + x;
+    if (i > n) continue;
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+      const int j = j0 + tj + y;
+      if (j >= n || (i < n && j > i)) continue;
+      if (i < n) d.S[(size_t)i * n + j] -= acc[x][y]; else d.rhs[j] -= acc[x][y];
+    }
+  }
+}
+
+// back substitution, panel by panel from the last: x_k = inv(L_kk)' y_k, then y_i -= L_ki' x_k for i < k0
+__global__ void __launch_bounds__(256) k_backsolve_panel(BaDev d, int k0, int kb, const double* __restrict__ Linv) {
+  __shared__ double xk[kNB];
+  LmState& st = *d.st;
+  if (st.done || st.solve_failed) return;
+  const int n = d.nc, tid = threadIdx.x;
+  const double* Lp = Linv + (size_t)(k0 / kNB) * kNB * kNB;
+  if (tid < kb) {
+    double s = 0.0;
+    for (int r = tid; r < kb; r++) s += Lp[r * kNB + tid] * d.rhs[k0 + r];   // (inv L)' y
+    xk[tid] = s;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid < kb) d.yc[k0 + tid] = xk[tid];
+  const int c = blockIdx.x * 256 + tid;   // columns c < k0
+  if (c < k0) {
+    double s = 0.0;
+    for (int r = 0; r < kb; r++) s += d.S[(size_t)(k0 + r) * n + c] * xk[r];
+    d.rhs[c] -= s;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cam_candidates(BaDev d) {
+  LmState& st = *d.st;
+  if (st.done) return;
+  const int cam = blockIdx.x * 256 + threadIdx.x;
+  if (cam == 0) {
+    // validate the solution (finite), single thread: cheap relative to the factorisation
+  }
+  if (cam < d.K && !st.solve_failed) {
+    const int a = d.cam_var[cam];
+    if (a >= 0) {
+      bool fin = true;
+      for (int k = 0; k < 6; k++) fin = fin && isfinite(d.yc[6 * a + k]);
+      if (!fin) { st.solve_failed = 1; return; }
+    }
+    cam_candidate(d, st, cam);
+  }
+}
+
+}  // namespace cmos
+
+using namespace cmos;
+
+// =================================================================================================
+// Host side
+// =================================================================================================
+struct cmos_ba {
+  cmos_ba_params p{};
+  cudaStream_t stream = nullptr;
+  // capacities
+  size_t cap_pairs = 0, cap_blocks = 0, cap_S = 0;
+  // device storage
+  BaDev d{};
+  double *d_cams0 = nullptr, *d_pts0 = nullptr;      // initial values (restore)
+  double *d_cams_out = nullptr, *d_pts_out = nullptr;
+  int *d_cam_var = nullptr, *d_o_cam = nullptr, *d_o_cv = nullptr, *d_o_pt = nullptr, *d_pt_start = nullptr;
+  int *d_cam_start = nullptr, *d_cam_obs = nullptr, *d_blk_a = nullptr, *d_blk_b = nullptr, *d_blk_start = nullptr;
+  int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_perm = nullptr;
+  float2* d_o_uv = nullptr;
+  float* d_o_w = nullptr;
+  uint8_t *d_o_mode = nullptr, *d_cam_flags = nullptr, *d_erase = nullptr;
+  double* d_Linv = nullptr;
+  double* d_trace = nullptr;       // [2][trace_rows][8]
+  int trace_rows = 0;
+  cmos_ba_summary* d_summaries = nullptr;   // [2]
+  bool has_problem = false, ran = false;
+  int launches = 0;
+  // pose optimisation staging
+  double *dp_pose = nullptr, *dp_xw = nullptr, *dp_trace = nullptr;
+  float *dp_uv = nullptr, *dp_w = nullptr;
+  int *dp_n = nullptr, *dp_inl = nullptr;
+  uint8_t* dp_out = nullptr;
+  cmos_ba_summary* dp_sum = nullptr;
+  // stop flag mapping
+  const void* stop_host_page = nullptr;
+  uint8_t* stop_dev_page = nullptr;
+  bool stop_registered_by_us = false;
+  StageTimer timer;
+};
+
+namespace {
+
+template <typename T>
+bool alloc(T** p, size_t n) {
+  return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)) == cudaSuccess;
+}
+
+int map_stop_flag(cmos_ba* h, const uint8_t* flag, const volatile uint8_t** dev) {
+  *dev = nullptr;
+  if (!flag) return CMOS_OK;
+  const uintptr_t page = (uintptr_t)flag & ~(uintptr_t)4095;
+  if (h->stop_host_page != (const void*)page) {
+    if (h->stop_registered_by_us && h->stop_host_page) cudaHostUnregister((void*)h->stop_host_page);
+    h->stop_registered_by_us = false;
+    h->stop_host_page = nullptr;
+    cudaError_t e = cudaHostRegister((void*)page, 4096, cudaHostRegisterMapped);
+    if (e == cudaSuccess) h->stop_registered_by_us = true;
+    else if (e != cudaErrorHostMemoryAlreadyRegistered) {
+      cudaGetLastError();
+      set_error("cannot map the stop flag into the device address space: %s", cudaGetErrorString(e));
+      return CMOS_ERR_CUDA;
+    }
+    cudaGetLastError();
+    void* dp = nullptr;
+    CMOS_CUDA_OK(cudaHostGetDevicePointer(&dp, (void*)page, 0));
+    h->stop_host_page = (const void*)page;
+    h->stop_dev_page = (uint8_t*)dp;
+  }
+  *dev = h->stop_dev_page + ((uintptr_t)flag - page);
+  return CMOS_OK;
+}
+
+// Enqueue one ceres::Solve: max_iterations LM rounds driven by the device-side state machine.
+int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
+  BaDev d = h->d;
+  d.trace = h->d_trace + (size_t)pass * h->trace_rows * kTraceCols;
+  const int nlb = d.n_lin_blocks;
+  const bool small = d.nc <= kSmallMaxN;
+  const size_t small_smem = (size_t)(d.nc + 1) * (d.nc + 2) / 2 * sizeof(double);
+  k_lm_init<<<1, 1, 0, st>>>(d, max_iterations);
+  h->launches++;
+  for (int it = 0; it < max_iterations; it++) {
+    k_linearize<<<nlb, kLinThreads, 0, st>>>(d);
+    if (d.Kv > 0) k_cam_blocks<<<d.Kv, kCamThreads, 0, st>>>(d);
+    k_post_lin<<<1, 256, 0, st>>>(d);
+    k_point_prep<<<nlb, kLinThreads, 0, st>>>(d);
+    h->launches += 4;
+    if (d.Kv > 0) {
+      if (!small) { CMOS_CUDA_OK(cudaMemsetAsync(d.S, 0, (size_t)d.nc * d.nc * sizeof(double), st)); }
+      k_schur<<<(d.n_blocks + 3) / 4, 128, 0, st>>>(d);
+      h->launches++;
+      if (small) {
+        k_solve_small<<<1, kSolveThreads, small_smem, st>>>(d);
+        h->launches++;
+      } else {
+        const int n = d.nc;
+        for (int k0 = 0; k0 < n; k0 += kNB) {
+          const int kb = std::min(kNB, n - k0);
+          k_potrf_diag<<<1, 256, kPanelSmem, st>>>(d, k0, kb, h->d_Linv);
+          const int rows_below = n + 1 - (k0 + kb);   // incl. the rhs row
+          if (rows_below > 0) {
+            k_trsm_panel<<<(rows_below + 31) / 32, 256, kPanelSmem, st>>>(d, k0, kb, h->d_Linv);
+            const int nt = (rows_below + 63) / 64;
+            k_syrk_tile<<<nt * (nt + 1) / 2, 256, kPanelSmem, st>>>(d, k0, kb);
+            h->launches += 2;
+          }
+          h->launches++;
+        }
+        for (int k0 = ((n - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {
+          const int kb = std::min(kNB, n - k0);
+          k_backsolve_panel<<<std::max(1, (k0 + 255) / 256), 256, 0, st>>>(d, k0, kb, h->d_Linv);
+          h->launches++;
+        }
+        k_cam_candidates<<<(d.K + 255) / 256, 256, 0, st>>>(d);
+        h->launches++;
+      }
+    }
+    k_backsub<<<nlb, kLinThreads, 0, st>>>(d);
+    k_decide<<<1, 256, 0, st>>>(d);
+    h->launches += 2;
+  }
+  if (max_iterations == 0) {   // Ceres still evaluates iteration 0
+    k_linearize<<<nlb, kLinThreads, 0, st>>>(d);
+    if (d.Kv > 0) k_cam_blocks<<<d.Kv, kCamThreads, 0, st>>>(d);
+    k_post_lin<<<1, 256, 0, st>>>(d);
+    h->launches += 3;
+  }
+  k_summary<<<1, 1, 0, st>>>(d, h->d_summaries + pass);
+  h->launches++;
+  CMOS_CUDA_OK(cudaGetLastError());
+  return CMOS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
+  CMOS_REQUIRE(params && out, "null argument");
+  CMOS_REQUIRE(params->max_cams >= 1 && params->max_points >= 1 && params->max_obs >= 1, "bad sizes");
+  CMOS_REQUIRE(params->max_pose_batch >= 0 && params->max_pose_corr >= 0, "bad pose sizes");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: this library has no CPU fallback");
+    return CMOS_ERR_CUDA;
+  }
+  CMOS_REQUIRE(params->device >= 0 && params->device < ndev, "device %d out of range", params->device);
+  CMOS_CUDA_OK(cudaSetDevice(params->device));
+  cmos_ba* h = new cmos_ba();
+  h->p = *params;
+  const size_t K = params->max_cams, M = params->max_points, N = params->max_obs;
+  const size_t pairs_per_obs = params->max_pairs_per_obs > 0 ? params->max_pairs_per_obs : 8;
+  h->cap_pairs = N * pairs_per_obs;
+  h->cap_blocks = std::min<size_t>(K * (K + 1) / 2, h->cap_pairs) + 1;
+  h->cap_S = (6 * K) * (6 * K);
+  h->trace_rows = 256;
+  bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+  BaDev& d = h->d;
+  const size_t nlb = (M + kLinThreads - 1) / kLinThreads;
+  ok = ok && alloc(&d.cams[0], 7 * K) && alloc(&d.cams[1], 7 * K) && alloc(&d.pts[0], 3 * M) && alloc(&d.pts[1], 3 * M);
+  ok = ok && alloc(&h->d_cams0, 7 * K) && alloc(&h->d_pts0, 3 * M) && alloc(&h->d_cams_out, 7 * K) && alloc(&h->d_pts_out, 3 * M);
+  ok = ok && alloc(&h->d_cam_var, K) && alloc(&h->d_o_cam, N) && alloc(&h->d_o_cv, N) && alloc(&h->d_o_pt, N) &&
+       alloc(&h->d_pt_start, M + 1) && alloc(&h->d_cam_start, K + 1) && alloc(&h->d_cam_obs, N) &&
+       alloc(&h->d_blk_a, h->cap_blocks) && alloc(&h->d_blk_b, h->cap_blocks) && alloc(&h->d_blk_start, h->cap_blocks + 1) &&
+       alloc(&h->d_pair_a, h->cap_pairs) && alloc(&h->d_pair_b, h->cap_pairs) && alloc(&h->d_perm, N) &&
+       alloc(&h->d_o_uv, N) && alloc(&h->d_o_w, N) && alloc(&h->d_o_mode, N) && alloc(&h->d_cam_flags, K) &&
+       alloc(&h->d_erase, N);
+  ok = ok && alloc(&d.Jc, 12 * N) && alloc(&d.Jp, 6 * N) && alloc(&d.res, 2 * N) && alloc(&d.Hpp, 6 * M) && alloc(&d.gp, 3 * M) &&
+       alloc(&d.Hinv, 6 * M) && alloc(&d.tp, 3 * M) && alloc(&d.scale_p, 3 * M) && alloc(&d.Hcc, 21 * K) &&
+       alloc(&d.gc, 6 * K) && alloc(&d.scale_c, 6 * K) && alloc(&d.S, h->cap_S) && alloc(&d.rhs, 6 * K + 8) &&
+       alloc(&d.yc, 6 * K + 8) && alloc(&d.part, 6 * nlb + 4 * K + 16) && alloc(&d.st, 1) &&
+       alloc(&h->d_Linv, ((6 * K + kNB - 1) / kNB) * kNB * kNB) && alloc(&h->d_trace, 2 * (size_t)h->trace_rows * kTraceCols) &&
+       alloc(&h->d_summaries, 2);
+  const size_t PB = std::max(params->max_pose_batch, 1), PC = std::max(params->max_pose_corr, 1);
+  ok = ok && alloc(&h->dp_pose, 7 * PB) && alloc(&h->dp_xw, 3 * PB * PC) && alloc(&h->dp_uv, 2 * PB * PC) &&
+       alloc(&h->dp_w, PB * PC) && alloc(&h->dp_n, PB) && alloc(&h->dp_inl, PB) && alloc(&h->dp_out, PB * PC) &&
+       alloc(&h->dp_sum, PB) && alloc(&h->dp_trace, PB * (size_t)h->trace_rows * kTraceCols);
+  if (!ok) {
+    set_error("device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cmos_ba_destroy(h);
+    return CMOS_ERR_CUDA;
+  }
+  cudaMemset(d.st, 0, sizeof(LmState));
+  cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+  cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
+  cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
+  cudaFuncSetAttribute(k_syrk_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
+  CMOS_CUDA_OK(cudaGetLastError());
+  *out = h;
+  return CMOS_OK;
+}
+
+int cmos_ba_destroy(cmos_ba_t h) {
+  if (!h) return CMOS_OK;
+  cudaSetDevice(h->p.device);
+  BaDev& d = h->d;
+  void* bufs[] = {d.cams[0], d.cams[1], d.pts[0], d.pts[1], h->d_cams0, h->d_pts0, h->d_cams_out, h->d_pts_out, h->d_cam_var,
+                  h->d_o_cam, h->d_o_cv, h->d_o_pt, h->d_pt_start, h->d_cam_start, h->d_cam_obs, h->d_blk_a, h->d_blk_b,
+                  h->d_blk_start, h->d_pair_a, h->d_pair_b, h->d_perm, h->d_o_uv, h->d_o_w, h->d_o_mode, h->d_cam_flags,
+                  h->d_erase, d.Jc, d.Jp, d.res, d.Hpp, d.gp, d.Hinv, d.tp, d.scale_p, d.Hcc, d.gc, d.scale_c, d.S, d.rhs,
+                  d.yc, d.part, d.st, h->d_Linv, h->d_trace, h->d_summaries, h->dp_pose, h->dp_xw, h->dp_uv, h->dp_w,
+                  h->dp_n, h->dp_inl, h->dp_out, h->dp_sum, h->dp_trace};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  if (h->stop_registered_by_us && h->stop_host_page) cudaHostUnregister((void*)h->stop_host_page);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  h->timer.destroy();
+  delete h;
+  return CMOS_OK;
+}
+
+int cmos_ba_pose_optimization(cmos_ba_t h, int32_t n_frames, double* pose7, const int32_t* n_corr, const double* xw,
+                              const float* uv, const float* inv_sigma2, int32_t stride, const float* K4,
+                              int32_t max_iterations, uint8_t* is_outlier, int32_t* n_inliers,
+                              cmos_ba_summary* summaries, int32_t on_device, void* stream) {
+  CMOS_REQUIRE(h && pose7 && n_corr && xw && uv && inv_sigma2 && K4 && is_outlier && n_inliers, "null argument");
+  CMOS_REQUIRE(n_frames >= 1 && stride >= 1 && max_iterations >= 0, "bad sizes");
+  CMOS_REQUIRE(max_iterations + 1 < h->trace_rows, "max_iterations %d too large", max_iterations);
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  PoseArgs a{};
+  a.stride = stride;
+  a.fx = (double)K4[0]; a.fy = (double)K4[1]; a.cx = (double)K4[2]; a.cy = (double)K4[3];
+  a.max_iterations = max_iterations;
+  a.trace_rows = h->trace_rows;
+  const size_t B = n_frames, BC = B * stride;
+  if (on_device) {
+    a.pose7 = pose7; a.n_corr = n_corr; a.xw = xw; a.uv = uv; a.inv_sigma2 = inv_sigma2;
+    a.is_outlier = is_outlier; a.n_inliers = n_inliers; a.summaries = summaries; a.trace = nullptr;
+  } else {
+    CMOS_REQUIRE(n_frames <= h->p.max_pose_batch && stride <= h->p.max_pose_corr,
+                 "batch %d x %d exceeds the handle's pose capacity %d x %d", n_frames, stride, h->p.max_pose_batch,
+                 h->p.max_pose_corr);
+    CMOS_CUDA_OK(cudaMemcpyAsync(h->dp_pose, pose7, 7 * B * sizeof(double), cudaMemcpyHostToDevice, st));
+    CMOS_CUDA_OK(cudaMemcpyAsync(h->dp_n, n_corr, B * sizeof(int), cudaMemcpyHostToDevice, st));
+    CMOS_CUDA_OK(cudaMemcpyAsync(h->dp_xw, xw, 3 * BC * sizeof(double), cudaMemcpyHostToDevice, st));
+    CMOS_CUDA_OK(cudaMemcpyAsync(h->dp_uv, uv, 2 * BC * sizeof(float), cudaMemcpyHostToDevice, st));
+    CMOS_CUDA_OK(cudaMemcpyAsync(h->dp_w, inv_sigma2, BC * sizeof(float), cudaMemcpyHostToDevice, st));
+    a.pose7 = h->dp_pose; a.n_corr = h->dp_n; a.xw = h->dp_xw; a.uv = h->dp_uv; a.inv_sigma2 = h->dp_w;
+    a.is_outlier = h->dp_out; a.n_inliers = h->dp_inl; a.summaries = h->dp_sum; a.trace = h->dp_trace;
+  }
+  h->timer.begin(st);
+  k_pose_opt<<<n_frames, kPoseThreads, 0, st>>>(a);
+  h->timer.mark(st);
+  CMOS_CUDA_OK(cudaGetLastError());
+  h->launches = 1;
+  if (!on_device) {
+    CMOS_CUDA_OK(cudaMemcpyAsync(pose7, h->dp_pose, 7 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CMOS_CUDA_OK(cudaMemcpyAsync(is_outlier, h->dp_out, BC, cudaMemcpyDeviceToHost, st));
+    CMOS_CUDA_OK(cudaMemcpyAsync(n_inliers, h->dp_inl, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (summaries)
+      CMOS_CUDA_OK(cudaMemcpyAsync(summaries, h->dp_sum, B * sizeof(cmos_ba_summary), cudaMemcpyDeviceToHost, st));
+    CMOS_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return CMOS_OK;
+}
+
+int cmos_ba_debug_pose_trace(cmos_ba_t h, int32_t frame, double* trace, int32_t rows) {
+  CMOS_REQUIRE(h && trace && frame >= 0 && frame < h->p.max_pose_batch && rows >= 1 && rows <= h->trace_rows, "bad argument");
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  CMOS_CUDA_OK(cudaDeviceSynchronize());
+  CMOS_CUDA_OK(cudaMemcpy(trace, h->dp_trace + (size_t)frame * h->trace_rows * kTraceCols, (size_t)rows * kTraceCols * sizeof(double),
+                          cudaMemcpyDeviceToHost));
+  return CMOS_OK;
+}
+
+int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const uint8_t* cam_flags, int32_t n_points,
+                        const double* points, int32_t n_obs, const int32_t* obs_cam, const int32_t* obs_pt,
+                        const float* uv, const float* inv_sigma2, const float* K4) {
+  CMOS_REQUIRE(h && cams && cam_flags && points && obs_cam && obs_pt && uv && inv_sigma2 && K4, "null argument");
+  CMOS_REQUIRE(n_cams >= 1 && n_cams <= h->p.max_cams && n_points >= 1 && n_points <= h->p.max_points && n_obs >= 1 &&
+               n_obs <= h->p.max_obs, "problem %d keyframes / %d points / %d observations exceeds the handle (%d / %d / %d)",
+               n_cams, n_points, n_obs, h->p.max_cams, h->p.max_points, h->p.max_obs);
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  const int K = n_cams, M = n_points, N = n_obs;
+  // ---- structure (host, counting sorts only) ----
+  std::vector<int> cam_var(K, -1);
+  int Kv = 0;
+  for (int k = 0; k < K; k++)
+    if (!(cam_flags[k] & 1)) cam_var[k] = Kv++;
+  std::vector<int> pt_start(M + 1, 0);
+  for (int i = 0; i < N; i++) {
+    CMOS_REQUIRE(obs_cam[i] >= 0 && obs_cam[i] < K && obs_pt[i] >= 0 && obs_pt[i] < M, "observation %d out of range", i);
+    pt_start[obs_pt[i] + 1]++;
+  }
+  for (int j = 0; j < M; j++) pt_start[j + 1] += pt_start[j];
+  std::vector<int> perm(N), fill(pt_start.begin(), pt_start.end() - 1);
+  for (int i = 0; i < N; i++) perm[fill[obs_pt[i]]++] = i;
+  std::vector<int> o_cam(N), o_cv(N), o_pt(N);
+  std::vector<float2> o_uv(N);
+  std::vector<float> o_w(N);
+  std::vector<int> cam_start(Kv + 1, 0);
+  for (int p = 0; p < N; p++) {
+    const int i = perm[p];
+    o_cam[p] = obs_cam[i]; o_cv[p] = cam_var[obs_cam[i]]; o_pt[p] = obs_pt[i];
+    o_uv[p] = make_float2(uv[2 * i], uv[2 * i + 1]); o_w[p] = inv_sigma2[i];
+    if (o_cv[p] >= 0) cam_start[o_cv[p] + 1]++;
+  }
+  for (int a = 0; a < Kv; a++) {
+    CMOS_REQUIRE(cam_start[a + 1] > 0, "a variable keyframe has no observation");
+    cam_start[a + 1] += cam_start[a];
+  }
+  std::vector<int> cam_obs(std::max(cam_start[Kv], 1));
+  {
+    std::vector<int> f2(cam_start.begin(), cam_start.end() - 1);
+    for (int p = 0; p < N; p++)
+      if (o_cv[p] >= 0) cam_obs[f2[o_cv[p]]++] = p;
+  }
+  // pair lists per non-zero block (a <= b)
+  CMOS_REQUIRE((size_t)Kv * Kv <= (size_t)64 << 20, "too many variable keyframes (%d) for the dense block table", Kv);
+  std::vector<int> table((size_t)Kv * Kv, 0);
+  size_t n_pairs = 0;
+  for (int j = 0; j < M; j++)
+    for (int pa = pt_start[j]; pa < pt_start[j + 1]; pa++) {
+      if (o_cv[pa] < 0) continue;
+      for (int pb = pt_start[j]; pb < pt_start[j + 1]; pb++) {
+        if (o_cv[pb] < 0) continue;
+        if (o_cv[pa] < o_cv[pb] || (o_cv[pa] == o_cv[pb])) { table[(size_t)o_cv[pa] * Kv + o_cv[pb]]++; n_pairs++; }
+      }
+    }
+  CMOS_REQUIRE(n_pairs <= h->cap_pairs, "%zu co-observation pairs exceed the handle's capacity %zu (raise max_pairs_per_obs)",
+               n_pairs, h->cap_pairs);
+  std::vector<int> blk_a, blk_b, blk_start;
+  blk_start.push_back(0);
+  for (int a = 0; a < Kv; a++)
+    for (int b = a; b < Kv; b++) {
+      int& t = table[(size_t)a * Kv + b];
+      if (t > 0) {
+        blk_a.push_back(a); blk_b.push_back(b);
+        blk_start.push_back(blk_start.back() + t);
+        t = (int)blk_a.size();      // 1-based block id
+      } else if (a == b) {          // every variable keyframe gets its diagonal block
+        blk_a.push_back(a); blk_b.push_back(b);
+        blk_start.push_back(blk_start.back());
+        t = (int)blk_a.size();
+      }
+    }
+  const int nb = (int)blk_a.size();
+  CMOS_REQUIRE((size_t)nb <= h->cap_blocks, "%d reduced-system blocks exceed the handle's capacity %zu", nb, h->cap_blocks);
+  std::vector<int> pair_a(std::max<size_t>(n_pairs, 1)), pair_b(std::max<size_t>(n_pairs, 1));
+  {
+    std::vector<int> f3(blk_start.begin(), blk_start.end() - 1);
+    for (int j = 0; j < M; j++)
+      for (int pa = pt_start[j]; pa < pt_start[j + 1]; pa++) {
+        if (o_cv[pa] < 0) continue;
+        for (int pb = pt_start[j]; pb < pt_start[j + 1]; pb++) {
+          if (o_cv[pb] < 0 || o_cv[pa] > o_cv[pb]) continue;
+          const int id = table[(size_t)o_cv[pa] * Kv + o_cv[pb]] - 1;
+          pair_a[f3[id]] = pa; pair_b[f3[id]] = pb; f3[id]++;
+        }
+      }
+  }
+  // ---- upload ----
+  cudaStream_t st = h->stream;
+  auto up = [&](void* dst, const void* src, size_t bytes) {
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  };
+  BaDev& d = h->d;
+  CMOS_CUDA_OK(up(h->d_cams0, cams, 7 * (size_t)K * sizeof(double)));
+  CMOS_CUDA_OK(up(h->d_pts0, points, 3 * (size_t)M * sizeof(double)));
+  CMOS_CUDA_OK(up(h->d_cam_var, cam_var.data(), K * sizeof(int)));
+  CMOS_CUDA_OK(up(h->d_cam_flags, cam_flags, K));
+  CMOS_CUDA_OK(up(h->d_o_cam, o_cam.data(), N * sizeof(int)));
+  CMOS_CUDA_OK(up(h->d_o_cv, o_cv.data(), N * sizeof(int)));
+  CMOS_CUDA_OK(up(h->d_o_pt, o_pt.data(), N * sizeof(int)));
+  CMOS_CUDA_OK(up(h->d_o_uv, o_uv.data(), N * sizeof(float2)));
+  CMOS_CUDA_OK(up(h->d_o_w, o_w.data(), N * sizeof(float)));
+  CMOS_CUDA_OK(up(h->d_perm, perm.data(), N * sizeof(int)));
+  CMOS_CUDA_OK(up(h->d_pt_start, pt_start.data(), (M + 1) * sizeof(int)));
+  CMOS_CUDA_OK(up(h->d_cam_start, cam_start.data(), (Kv + 1) * sizeof(int)));
+  CMOS_CUDA_OK(up(h->d_cam_obs, cam_obs.data(), cam_obs.size() * sizeof(int)));
+  CMOS_CUDA_OK(up(h->d_blk_a, blk_a.data(), nb * sizeof(int)));
+  CMOS_CUDA_OK(up(h->d_blk_b, blk_b.data(), nb * sizeof(int)));
+  CMOS_CUDA_OK(up(h->d_blk_start, blk_start.data(), (nb + 1) * sizeof(int)));
+  CMOS_CUDA_OK(up(h->d_pair_a, pair_a.data(), pair_a.size() * sizeof(int)));
+  CMOS_CUDA_OK(up(h->d_pair_b, pair_b.data(), pair_b.size() * sizeof(int)));
+  d.K = K; d.Kv = Kv; d.M = M; d.N = N; d.n_blocks = nb; d.nc = 6 * Kv;
+  d.fx = (double)K4[0]; d.fy = (double)K4[1]; d.cx = (double)K4[2]; d.cy = (double)K4[3];
+  d.cam_var = h->d_cam_var; d.o_cam = h->d_o_cam; d.o_cv = h->d_o_cv; d.o_pt = h->d_o_pt; d.o_uv = h->d_o_uv;
+  d.o_w = h->d_o_w; d.o_mode = h->d_o_mode; d.pt_start = h->d_pt_start; d.cam_start = h->d_cam_start;
+  d.cam_obs = h->d_cam_obs; d.blk_a = h->d_blk_a; d.blk_b = h->d_blk_b; d.blk_start = h->d_blk_start;
+  d.pair_a = h->d_pair_a; d.pair_b = h->d_pair_b;
+  const int nlb = (M + kLinThreads - 1) / kLinThreads;
+  d.n_lin_blocks = nlb;
+  int o = 0;
+  d.o_lin_cost = o; o += nlb; d.o_lin_gmax = o; o += nlb; d.o_lin_xn2 = o; o += nlb;
+  d.o_bs_cost = o; o += nlb; d.o_bs_mcc = o; o += nlb; d.o_bs_sn2 = o; o += nlb;
+  d.o_cam_gmax = o; o += Kv; d.o_cam_xn2 = o; o += Kv; d.o_cam_mcc = o; o += Kv; d.o_cam_sn2 = o; o += Kv;
+  d.trace = nullptr; d.stop_flag = nullptr;
+  CMOS_CUDA_OK(cudaMemsetAsync(d.part, 0, (size_t)o * sizeof(double), st));
+  if (d.nc <= kSmallMaxN && d.nc > 0) CMOS_CUDA_OK(cudaMemsetAsync(d.S, 0, (size_t)d.nc * d.nc * sizeof(double), st));
+  CMOS_CUDA_OK(cudaStreamSynchronize(st));   // the host vectors die here
+  h->has_problem = true;
+  h->ran = false;
+  return CMOS_OK;
+}
+
+static int restore_and_prepare(cmos_ba* h, cudaStream_t st) {
+  BaDev& d = h->d;
+  for (int b = 0; b < 2; b++) {
+    CMOS_CUDA_OK(cudaMemcpyAsync(d.cams[b], h->d_cams0, 7 * (size_t)d.K * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CMOS_CUDA_OK(cudaMemcpyAsync(d.pts[b], h->d_pts0, 3 * (size_t)d.M * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  CMOS_CUDA_OK(cudaMemsetAsync(d.st, 0, sizeof(LmState), st));
+  CMOS_CUDA_OK(cudaMemsetAsync(h->d_trace, 0, 2 * (size_t)h->trace_rows * kTraceCols * sizeof(double), st));
+  CMOS_CUDA_OK(cudaMemsetAsync(h->d_erase, 0, d.N, st));
+  CMOS_CUDA_OK(cudaMemsetAsync(h->d_summaries, 0, 2 * sizeof(cmos_ba_summary), st));
+  h->launches = 0;
+  return CMOS_OK;
+}
+
+int cmos_ba_run_local(cmos_ba_t h, int32_t iterations_pass0, int32_t iterations_pass1, const uint8_t* stop_flag,
+                      void* stream) {
+  CMOS_REQUIRE(h, "null handle");
+  if (!h->has_problem) { set_error("cmos_ba_set_problem must be called first"); return CMOS_ERR_STATE; }
+  CMOS_REQUIRE(iterations_pass0 >= 0 && iterations_pass1 >= 0 && iterations_pass0 + 1 < h->trace_rows &&
+               iterations_pass1 + 1 < h->trace_rows, "bad iteration counts");
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  int rc = map_stop_flag(h, stop_flag, &h->d.stop_flag);
+  if (rc) return rc;
+  if ((rc = restore_and_prepare(h, st))) return rc;
+  h->ran = true;
+  BaDev& d = h->d;
+  const int gN = (d.N + 255) / 256;
+  h->timer.begin(st);
+  k_set_mode<<<gN, 256, 0, st>>>(d, 1);
+  if ((rc = enqueue_solve(h, iterations_pass0, 0, st))) return rc;
+  k_outlier_scan<<<gN, 256, 0, st>>>(d, h->d_cam_flags, h->d_perm, h->d_erase, 1);
+  if ((rc = enqueue_solve(h, iterations_pass1, 1, st))) return rc;
+  k_outlier_scan<<<gN, 256, 0, st>>>(d, h->d_cam_flags, h->d_perm, h->d_erase, 0);
+  k_gather_result<<<(std::max(7 * d.K, 3 * d.M) + 255) / 256, 256, 0, st>>>(d, h->d_cams0, h->d_pts0, h->d_cams_out, h->d_pts_out);
+  h->timer.mark(st);
+  h->launches += 4;
+  CMOS_CUDA_OK(cudaGetLastError());
+  return CMOS_OK;
+}
+
+int cmos_ba_run_global(cmos_ba_t h, int32_t n_iterations, int32_t robust, const uint8_t* stop_flag, void* stream) {
+  CMOS_REQUIRE(h, "null handle");
+  if (!h->has_problem) { set_error("cmos_ba_set_problem must be called first"); return CMOS_ERR_STATE; }
+  CMOS_REQUIRE(n_iterations >= 0 && n_iterations + 1 < h->trace_rows, "bad iteration count");
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  int rc = map_stop_flag(h, stop_flag, &h->d.stop_flag);
+  if (rc) return rc;
+  if ((rc = restore_and_prepare(h, st))) return rc;
+  h->ran = true;
+  BaDev& d = h->d;
+  h->timer.begin(st);
+  k_set_mode<<<(d.N + 255) / 256, 256, 0, st>>>(d, robust ? 1 : 2);
+  if ((rc = enqueue_solve(h, n_iterations, 0, st))) return rc;
+  k_gather_result<<<(std::max(7 * d.K, 3 * d.M) + 255) / 256, 256, 0, st>>>(d, h->d_cams0, h->d_pts0, h->d_cams_out, h->d_pts_out);
+  h->timer.mark(st);
+  h->launches += 2;
+  CMOS_CUDA_OK(cudaGetLastError());
+  return CMOS_OK;
+}
+
+int cmos_ba_get_results(cmos_ba_t h, double* cams, double* points, uint8_t* erase, cmos_ba_summary* summaries,
+                        void* stream) {
+  CMOS_REQUIRE(h, "null handle");
+  if (!h->ran) { set_error("no solve has run"); return CMOS_ERR_STATE; }
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const BaDev& d = h->d;
+  if (cams) CMOS_CUDA_OK(cudaMemcpyAsync(cams, h->d_cams_out, 7 * (size_t)d.K * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (points) CMOS_CUDA_OK(cudaMemcpyAsync(points, h->d_pts_out, 3 * (size_t)d.M * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (erase) CMOS_CUDA_OK(cudaMemcpyAsync(erase, h->d_erase, d.N, cudaMemcpyDeviceToHost, st));
+  if (summaries) CMOS_CUDA_OK(cudaMemcpyAsync(summaries, h->d_summaries, 2 * sizeof(cmos_ba_summary), cudaMemcpyDeviceToHost, st));
+  CMOS_CUDA_OK(cudaStreamSynchronize(st));
+  return CMOS_OK;
+}
+
+int cmos_ba_local_bundle_adjustment(cmos_ba_t h, int32_t n_cams, double* cams, const uint8_t* cam_flags, int32_t n_points,
+                                    double* points, int32_t n_obs, const int32_t* obs_cam, const int32_t* obs_pt,
+                                    const float* uv, const float* inv_sigma2, const float* K4, const uint8_t* stop_flag,
+                                    uint8_t* erase, cmos_ba_summary* summaries) {
+  int rc = cmos_ba_set_problem(h, n_cams, cams, cam_flags, n_points, points, n_obs, obs_cam, obs_pt, uv, inv_sigma2, K4);
+  if (rc) return rc;
+  if ((rc = cmos_ba_run_local(h, 5, 10, stop_flag, nullptr))) return rc;   // CeresOptimizer.cc:517-519
+  return cmos_ba_get_results(h, cams, points, erase, summaries, nullptr);
+}
+
+int cmos_ba_bundle_adjustment(cmos_ba_t h, int32_t n_cams, double* cams, const uint8_t* cam_const, int32_t n_points,
+                              double* points, int32_t n_obs, const int32_t* obs_cam, const int32_t* obs_pt,
+                              const float* uv, const float* inv_sigma2, const float* K4, int32_t n_iterations,
+                              int32_t robust, const uint8_t* stop_flag, cmos_ba_summary* summary) {
+  int rc = cmos_ba_set_problem(h, n_cams, cams, cam_const, n_points, points, n_obs, obs_cam, obs_pt, uv, inv_sigma2, K4);
+  if (rc) return rc;
+  if ((rc = cmos_ba_run_global(h, n_iterations, robust, stop_flag, nullptr))) return rc;
+  cmos_ba_summary s2[2];
+  rc = cmos_ba_get_results(h, cams, points, nullptr, s2, nullptr);
+  if (summary) *summary = s2[0];
+  return rc;
+}
+
+int cmos_ba_debug_trace(cmos_ba_t h, int32_t pass, double* trace, int32_t rows) {
+  CMOS_REQUIRE(h && trace && (pass == 0 || pass == 1) && rows >= 1 && rows <= h->trace_rows, "bad argument");
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  CMOS_CUDA_OK(cudaDeviceSynchronize());
+  CMOS_CUDA_OK(cudaMemcpy(trace, h->d_trace + (size_t)pass * h->trace_rows * kTraceCols,
+                          (size_t)rows * kTraceCols * sizeof(double), cudaMemcpyDeviceToHost));
+  return CMOS_OK;
+}
+
+int cmos_ba_last_launch_count(cmos_ba_t h, int32_t* n) {
+  CMOS_REQUIRE(h && n, "null argument");
+  *n = h->launches;
+  return CMOS_OK;
+}
+
+int cmos_ba_set_profiling(cmos_ba_t h, int32_t enable) {
+  CMOS_REQUIRE(h, "null handle");
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  h->timer.reset();
+  h->timer.enabled = enable != 0;
+  return CMOS_OK;
+}
+
+int cmos_ba_solve_time(cmos_ba_t h, double* ms, int64_t* calls) {
+  CMOS_REQUIRE(h && ms && calls, "null argument");
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  h->timer.fold();
+  *ms = h->timer.total_ms[0];
+  *calls = h->timer.calls;
+  return CMOS_OK;
+}
+
+}  // extern "C"

@@ -224,6 +224,98 @@ int cmos_match_stage_times(cmos_match_t h, double* ms, int64_t* calls);
 /* Number of kernels launched by the last cmos_match_* call. */
 int cmos_match_last_launch_count(cmos_match_t h, int32_t* n);
 
+/* ------------------------------------------------------------------------------------------------
+ * Path 2: CeresOptimizer  (replaces CeresOptimizer::PoseOptimization / LocalBundleAdjustment / BundleAdjustment /
+ * GlobalBundleAdjustemnt, reference include/CeresOptimizer.h:353-387, src/CeresOptimizer.cc:49-342,344-599).
+ * Pointer graphs are flattened: a keyframe pose is the reference's 7-vector [t(3), q(x,y,z,w)]
+ * (MatEigenConverter.cc:68-77, camera-from-world), a map point is double[3], an observation is
+ * (keyframe index, point index, undistorted keypoint u,v as float, inv_level_sigma2 of its octave as float).
+ * Intrinsics are the keyframes' float fx, fy, cx, cy (one camera: monocular).  All arithmetic is fp64.
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct {
+  int32_t max_cams;            /* keyframes per problem (constant ones included) */
+  int32_t max_points;
+  int32_t max_obs;
+  int32_t max_pairs_per_obs;   /* capacity of the co-observation lists: sum over points of n_obs(point)^2 / 2 is
+                                  bounded by max_obs * max_pairs_per_obs; 0 = default 8 */
+  int32_t max_pose_batch;      /* frames per cmos_ba_pose_optimization call with host buffers */
+  int32_t max_pose_corr;       /* correspondences per frame (stride) for the same */
+  int32_t device;
+} cmos_ba_params;
+
+/* What the callers / tests read out of ceres::Solver::Summary. */
+typedef struct {
+  int32_t iterations;            /* LM iterations performed: successful + unsuccessful + invalid */
+  int32_t successful_steps;
+  int32_t termination;           /* 0 max iterations, 1 function tolerance, 2 parameter tolerance, 3 gradient
+                                    tolerance, 4 stop flag, 5 failure, 6 minimum trust-region radius */
+  int32_t jacobian_evaluations;
+  double initial_cost, final_cost;
+} cmos_ba_summary;
+
+typedef struct cmos_ba* cmos_ba_t;
+
+int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out);
+int cmos_ba_destroy(cmos_ba_t h);
+
+/* CeresOptimizer::PoseOptimization(Frame*) for a batch of frames (CeresOptimizer.cc:275-342).
+ *   pose7       [n_frames][7] in/out: frame->Tcw_ as [t, q_xyzw]; q is normalised on output (:335)
+ *   n_corr      [n_frames]: matched keypoints with a map point; fewer than 3 -> n_inliers 0, pose untouched (:330)
+ *   xw          [n_frames][stride][3] map_point->GetWorldPos();  uv [..][2], inv_sigma2 [..] of the keypoints
+ *   K4          fx, fy, cx, cy (float, widened like MatEigenConverter::MatToMatrix3d)
+ *   max_iterations  the reference passes 100 (:300)
+ *   is_outlier  [n_frames][stride] out = frame->is_outliers_ after CheckOutliers (:243-269)
+ *   n_inliers   [n_frames] out = the function's return value
+ * With on_device != 0 every array is a device pointer, no capacity limit applies, and the call does not
+ * synchronise; with host pointers it is synchronous. */
+int cmos_ba_pose_optimization(cmos_ba_t h, int32_t n_frames, double* pose7, const int32_t* n_corr, const double* xw,
+                              const float* uv, const float* inv_sigma2, int32_t stride, const float* K4,
+                              int32_t max_iterations, uint8_t* is_outlier, int32_t* n_inliers,
+                              cmos_ba_summary* summaries, int32_t on_device, void* stream);
+
+/* Uploads a keyframe / map-point graph and builds its block structure (host pointers; synchronous).
+ *   cam_flags [n_cams]: bit0 = constant (a fixed keyframe, or keyframe id 0 — CeresOptimizer.cc:115-120,476-502),
+ *                       bit1 = not a local keyframe: its observations are never scanned for outliers (:545). */
+int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const uint8_t* cam_flags, int32_t n_points,
+                        const double* points, int32_t n_obs, const int32_t* obs_cam, const int32_t* obs_pt,
+                        const float* uv, const float* inv_sigma2, const float* K4);
+
+/* Enqueues LocalBundleAdjustment on the uploaded graph, starting from the uploaded values: Huber pass
+ * (iterations_pass0, reference 5), outlier scan, pass with the Huber blocks kept and the inliers added again
+ * without loss (iterations_pass1, reference 10 — quirk Q2), outlier scan.  Asynchronous on `stream`.
+ * stop_flag: host byte polled from the device once per LM iteration (StopFlagCallback) and at the start of
+ * each pass, where a raised flag means "return, nothing written" (:509-512); may be NULL. */
+int cmos_ba_run_local(cmos_ba_t h, int32_t iterations_pass0, int32_t iterations_pass1, const uint8_t* stop_flag,
+                      void* stream);
+/* Enqueues BundleAdjustment / GlobalBundleAdjustemnt: one solve of n_iterations, Huber iff robust. */
+int cmos_ba_run_global(cmos_ba_t h, int32_t n_iterations, int32_t robust, const uint8_t* stop_flag, void* stream);
+/* Waits for the enqueued solve and copies out: cams [n_cams][7], points [n_points][3], erase [n_obs] (LocalBA:
+ * observations the reference erases from the map, :573-581; in the caller's observation order), summaries[2]
+ * (pass 0, pass 1; global BA fills [0]).  Any pointer may be NULL. */
+int cmos_ba_get_results(cmos_ba_t h, double* cams, double* points, uint8_t* erase, cmos_ba_summary* summaries,
+                        void* stream);
+
+/* One-shot forms with the reference's defaults (what the C++ adapters call). */
+int cmos_ba_local_bundle_adjustment(cmos_ba_t h, int32_t n_cams, double* cams, const uint8_t* cam_flags, int32_t n_points,
+                                    double* points, int32_t n_obs, const int32_t* obs_cam, const int32_t* obs_pt,
+                                    const float* uv, const float* inv_sigma2, const float* K4, const uint8_t* stop_flag,
+                                    uint8_t* erase, cmos_ba_summary* summaries);
+int cmos_ba_bundle_adjustment(cmos_ba_t h, int32_t n_cams, double* cams, const uint8_t* cam_const, int32_t n_points,
+                              double* points, int32_t n_obs, const int32_t* obs_cam, const int32_t* obs_pt,
+                              const float* uv, const float* inv_sigma2, const float* K4, int32_t n_iterations,
+                              int32_t robust, const uint8_t* stop_flag, cmos_ba_summary* summary);
+
+/* Verification taps: per-iteration trace rows [iteration][8] = cost, cost_change, gradient_max_norm, step_norm,
+ * relative_decrease, trust-region radius, accepted, valid (row 0 = initial evaluation). */
+int cmos_ba_debug_trace(cmos_ba_t h, int32_t pass, double* trace, int32_t rows);
+int cmos_ba_debug_pose_trace(cmos_ba_t h, int32_t frame, double* trace, int32_t rows);
+/* Kernels launched by the last cmos_ba_run_* / cmos_ba_pose_optimization call. */
+int cmos_ba_last_launch_count(cmos_ba_t h, int32_t* n);
+/* Device time of the solves (CUDA events on the launching stream), as cmos_orb_set_profiling. */
+int cmos_ba_set_profiling(cmos_ba_t h, int32_t enable);
+int cmos_ba_solve_time(cmos_ba_t h, double* ms, int64_t* calls);
+
 #ifdef __cplusplus
 }
 #endif
