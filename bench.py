@@ -212,6 +212,33 @@ def cpu_orb_throughput(n_frames: int, threads: int, seed: int, repeats: int = 1)
     return feats / best / 1e6, best, feats
 
 
+def cpu_ba_baseline():
+    """The restated Ceres path (oracle/ba_oracle.cpp, one thread) on configs[2] and configs[3]."""
+    from oracle import pyoracle as po
+    from ceres_mono_orb_slam2_b200 import synth
+    out = {"cores": 1, "kind": "port", "unit": "Mresid/s"}
+    P = synth.make_pose_problem(1500, seed=3)
+    best = None
+    for _ in range(5):
+        t0 = time.perf_counter()
+        _, _, _, s, _ = po.ba_pose_optimization(P["pose"], P["Xw"], P["uv"], P["inv_sigma2"], P["K"], 4)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    out["pose_optimization"] = {"value": 1500 * (s["iterations"] + 1) / best / 1e6, "ms_per_solve": best * 1e3,
+                                "sample": "configs[2], best of 5"}
+    G = synth.make_ba_problem(20, 3000, 4, seed=4)
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        _, _, _, ss = po.ba_local(G["poses"], G["fixed"], G["points"], G["obs_cam"], G["obs_pt"], G["uv"], G["inv_sigma2"],
+                                  G["K"])
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    ev = 12000 * sum(x["iterations"] + 1 for x in ss)
+    out["local_ba"] = {"value": ev / best / 1e6, "ms_per_solve": best * 1e3, "sample": "configs[3], best of 3"}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -431,18 +458,14 @@ def run_b200(args):
                                     "sample": f"{n_s} frames of the same workload, {cores} threads, best of 2 "
                                               f"({dt:.2f} s per pass)"}
         if not args.no_ba:
-            try:
-                from ceres_mono_orb_slam2_b200 import ba_bench
-                line["ba"] = ba_bench.run(local_rank, world, args)
-            except ImportError:
-                pass
+            from ceres_mono_orb_slam2_b200 import ba_bench
+            line["ba"] = ba_bench.run(local_rank, world, args)
+            if world == 1 and not args.no_cpu:
+                line["ba"]["cpu_baseline"] = cpu_ba_baseline()
         print(json.dumps(line), flush=True)
     elif not args.no_ba:
-        try:
-            from ceres_mono_orb_slam2_b200 import ba_bench
-            ba_bench.run(local_rank, world, args)
-        except ImportError:
-            pass
+        from ceres_mono_orb_slam2_b200 import ba_bench
+        ba_bench.run(local_rank, world, args)
     if world > 1:
         dist.destroy_process_group()
 
@@ -456,6 +479,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ba", action="store_true", help="skip the bundle-adjustment section")
+    ap.add_argument("--no-global", action="store_true", help="skip the 1000-keyframe global BA case")
+    ap.add_argument("--global-iters", type=int, default=10, help="LM iterations of the global BA case")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

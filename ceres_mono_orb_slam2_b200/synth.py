@@ -251,3 +251,59 @@ def project_many(poses: np.ndarray, X: np.ndarray, K):
         zz = pc[2] if abs(pc[2]) > 1e-9 else 1e-9
         uv[i] = (fx * pc[0] / zz + cx, fy * pc[1] / zz + cy)
     return uv, z
+
+
+def make_ba_problem_fast(n_cams: int, n_points: int, obs_per_point: int, seed: int, window: int = 10, K=KITTI_K,
+                         outlier_frac: float = 0.05, pose_noise=(0.01, 0.05), point_noise: float = 0.05):
+    """Vectorised generator for large windowed graphs (C5: 1000 keyframes x 100k points x 500k observations).
+    Cameras drive along a straight line looking sideways (+z of the camera is world +z), 0.5 m apart; a point
+    anchored at camera a is seen by `obs_per_point` cameras of the window [a-window, a+window].  Same output keys
+    as make_ba_problem."""
+    rng = np.random.default_rng(seed)
+    Kf = np.array(K, np.float32).astype(np.float64)
+    fx, fy, cx, cy = Kf
+    step = 0.5
+    poses = np.zeros((n_cams, 7)); poses[:, 6] = 1.0
+    centre_x = step * np.arange(n_cams)
+    poses[:, 0] = -centre_x                       # t = -R c with R = I
+    # points: anchor camera, depth, pixel in the anchor
+    a = rng.integers(0, n_cams, n_points)
+    z = rng.uniform(8, 40, n_points)
+    u = rng.uniform(300, 941, n_points); v = rng.uniform(60, 316, n_points)
+    Xw = np.stack([(u - cx) / fx * z + centre_x[a], (v - cy) / fy * z, z], 1)
+    # visible cameras: |fx * (X - c_k)/z + cx| inside the image; choose obs_per_point offsets inside the window
+    offs = np.arange(-window, window + 1)
+    cam_idx = np.empty((n_points, obs_per_point), np.int64)
+    cand = a[:, None] + offs[None, :]
+    uu = fx * (Xw[:, 0:1] - step * cand) / z[:, None] + cx
+    ok = (cand >= 0) & (cand < n_cams) & (uu > 5) & (uu < 1236)
+    score = rng.random(cand.shape)
+    score[~ok] = 2.0
+    order = np.argsort(score, axis=1)[:, :obs_per_point]
+    chosen_ok = np.take_along_axis(ok, order, 1)
+    assert chosen_ok.all(), "window too small for obs_per_point visible cameras"
+    cam_idx = np.sort(np.take_along_axis(cand, order, 1), axis=1)
+    obs_cam = cam_idx.reshape(-1).astype(np.int32)
+    obs_pt = np.repeat(np.arange(n_points, dtype=np.int32), obs_per_point)
+    n_obs = obs_cam.size
+    octv = _octaves(rng, n_obs)
+    inv_s2 = inv_sigma2_table()[octv]
+    sigma = 1.0 / np.sqrt(inv_s2.astype(np.float64))
+    pc = Xw[obs_pt].copy(); pc[:, 0] -= centre_x[obs_cam]
+    uv = np.stack([fx * pc[:, 0] / pc[:, 2] + cx, fy * pc[:, 1] / pc[:, 2] + cy], 1)
+    uv += rng.normal(0, 1.0, uv.shape) * sigma[:, None]
+    n_out = int(outlier_frac * n_obs)
+    idx = rng.choice(n_obs, n_out, replace=False)
+    uv[idx] += rng.uniform(-50, 50, (n_out, 2))
+    fixed = np.zeros(n_cams, np.uint8); fixed[0] = 1
+    init_poses = poses.copy()
+    dt = rng.normal(0, pose_noise[1] / np.sqrt(3), (n_cams, 3))
+    dr = rng.normal(0, pose_noise[0] / np.sqrt(3), (n_cams, 3))
+    dt[0] = 0; dr[0] = 0
+    init_poses[:, :3] += dt
+    th = np.linalg.norm(dr, axis=1); th_safe = np.where(th > 0, th, 1.0)
+    init_poses[:, 3:6] = dr / th_safe[:, None] * np.sin(th / 2)[:, None]
+    init_poses[:, 6] = np.cos(th / 2)
+    init_pts = Xw + rng.normal(0, point_noise / np.sqrt(3), Xw.shape)
+    return dict(poses=init_poses, true_poses=poses, fixed=fixed, points=init_pts, true_points=Xw, obs_cam=obs_cam,
+                obs_pt=obs_pt, uv=uv.astype(np.float32), inv_sigma2=inv_s2, K=Kf)
