@@ -1,0 +1,96 @@
+// POD views that stand in for the reference's pointer graph at the drop-in boundary.
+// A maintainer of b51/ceres_mono_orb_slam2 fills these from Frame / KeyFrame / MapPoint (INTEGRATION.md shows
+// the few lines per call site); with OpenCV / Eigen available the same adapters accept cv::Mat / cv::KeyPoint
+// because the layouts are identical (cmos_keypoint == cv::KeyPoint, 28 bytes; poses are row-major doubles).
+#ifndef ORB_SLAM2_CMOS_VIEWS_H
+#define ORB_SLAM2_CMOS_VIEWS_H
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../cmos_b200.h"
+
+namespace ORB_SLAM2 {
+
+typedef cmos_keypoint KeyPoint;   // same layout as cv::KeyPoint
+
+struct ImageView {                // cv::Mat of type CV_8UC1
+  const uint8_t* data = nullptr;
+  int rows = 0, cols = 0;
+  size_t step = 0;
+  bool empty() const { return !data || rows == 0 || cols == 0; }
+};
+
+struct DescriptorMat {            // cv::Mat(N, 32, CV_8U)
+  std::vector<uint8_t> data;
+  int rows = 0;
+  static const int cols = 32;
+  void create(int n) { rows = n; data.assign((size_t)n * 32, 0); }
+  uint8_t* ptr(int r) { return data.data() + (size_t)r * 32; }
+  const uint8_t* ptr(int r) const { return data.data() + (size_t)r * 32; }
+};
+
+// What ORBmatcher reads from a Frame (Frame.h:158-214) and writes back (map_points_ as indices).
+struct FrameView {
+  cmos_camera camera;                       // bounds, grid pitch, intrinsics, scale factors
+  const KeyPoint* undistort_keypoints = nullptr;
+  const uint8_t* descriptors = nullptr;     // N x 32
+  int N = 0;
+  double Tcw[16];                           // row-major Tcw_
+  std::vector<int32_t> map_points;          // per keypoint: map-point id or -1  (F.map_points_)
+  std::vector<uint8_t> claimed;             // per keypoint: map_points_[i] && Observations() > 0
+};
+
+// The last frame as SearchByProjection(CurrentFrame, LastFrame, th) reads it (ORBmatcher.cc:1176-1200).
+struct LastFrameView {
+  const KeyPoint* undistort_keypoints = nullptr;
+  int N = 0;
+  const uint8_t* flags = nullptr;           // bit0: map point present and not outlier; bit1: Observations() > 0
+  const double* world_pos = nullptr;        // N x 3, MapPoint::GetWorldPos()
+  const uint8_t* descriptors = nullptr;     // N x 32, MapPoint::GetDescriptor()
+};
+
+// Local map points as SearchByProjection(F, vpMapPoints, th) reads them after Frame::isInFrustum.
+struct MapPointsView {
+  int n = 0;
+  const uint8_t* in_view = nullptr;         // is_track_in_view_ && !isBad()
+  const int32_t* level = nullptr;           // track_scale_level_
+  const float* view_cos = nullptr;          // track_view_cos_
+  const float* proj_xy = nullptr;           // track_proj_x_, track_proj_y_
+  const uint8_t* descriptors = nullptr;     // n x 32
+  const uint8_t* has_obs = nullptr;         // Observations() > 0
+};
+
+// PoseOptimization(Frame*): the matched keypoints of one frame.
+struct FramePoseView {
+  double pose7[7];                          // Tcw_ as [t, q_xyzw] (MatEigenConverter::Matrix4dToMatrix_7_1)
+  int n = 0;                                // keypoints with a map point
+  const double* world_pos = nullptr;        // n x 3
+  const float* uv = nullptr;                // n x 2, undistort_keypoints_[i].pt
+  const float* inv_sigma2 = nullptr;        // n, inv_level_sigma2s_[octave]
+  float K4[4];                              // fx, fy, cx, cy
+  std::vector<uint8_t> is_outlier;          // out: is_outliers_
+};
+
+// LocalBundleAdjustment / BundleAdjustment: keyframes, map points, observations.
+struct GraphView {
+  int n_keyframes = 0, n_points = 0, n_obs = 0;
+  double* keyframe_pose7 = nullptr;         // in/out, n_keyframes x 7
+  const uint8_t* keyframe_flags = nullptr;  // bit0 constant (fixed keyframe or id 0), bit1 not a local keyframe
+  double* point_pos = nullptr;              // in/out, n_points x 3
+  const int32_t* obs_keyframe = nullptr;
+  const int32_t* obs_point = nullptr;
+  const float* obs_uv = nullptr;            // n_obs x 2
+  const float* obs_inv_sigma2 = nullptr;
+  float K4[4];
+  std::vector<uint8_t> erase;               // out (LocalBA): observations to erase from the map
+};
+
+inline void cmos_throw_if(int status, const char* what) {
+  if (status != CMOS_OK) throw std::runtime_error(std::string(what) + ": " + cmos_last_error());
+}
+
+}  // namespace ORB_SLAM2
+#endif
