@@ -445,7 +445,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(h_kps_u8.numel() + h_desc.numel() + h_counts.numel() * 4 +
                                               h_match.numel() * 4 + h_nm.numel() * 4),
                     "ms_per_step": e2e_ms_max / args.steps},
-            "gpu_launches": (ext.launch_count() + 2) * args.steps,
+            "gpu_launches": (ext.launch_count() + 1 + matcher.launch_count()) * args.steps,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

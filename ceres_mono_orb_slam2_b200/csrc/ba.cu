@@ -39,7 +39,7 @@ constexpr int kPoseThreads = 256;
 constexpr int kLinThreads = 128;
 constexpr int kCamThreads = 128;
 constexpr int kSolveThreads = 1024;
-constexpr int kSmallMaxN = 234;      // packed lower triangle (+ rhs row) of 234x234 doubles = 221 840 B of shared memory
+constexpr int kSmallMaxN = 228;      // packed lower triangle + rhs row + panel buffer of a 228-column system = 223.5 KB
 constexpr int kNB = 64;              // panel width of the blocked factorisation
 constexpr int kTraceCols = 8;
 constexpr size_t kPanelSmem = 2 * kNB * (kNB + 1) * sizeof(double);   // two 64 x 65 fp64 tiles
@@ -452,12 +452,15 @@ __device__ __forceinline__ void load_jp_scaled(const BaDev& d, int p, int j, dou
   Jp[0] = v0.x * s0; Jp[1] = v0.y * s1; Jp[2] = v1.x * s2; Jp[3] = v1.y * s0; Jp[4] = v2.x * s1; Jp[5] = v2.y * s2;
 }
 
-// warp per non-zero block (a,b), a <= b (variable-keyframe indices); writes the lower-triangle copy S[b][a]
-__global__ void __launch_bounds__(128) k_schur(BaDev d) {
+// CTA (4 warps) per non-zero block (a,b), a <= b (variable-keyframe indices): threads stride over the block's
+// observation pairs, warp shuffles + a fixed-order cross-warp sum reduce the 6x6 (+ rhs); writes the
+// lower-triangle copy S[b][a].
+constexpr int kSchurThreads = 128;
+__global__ void __launch_bounds__(kSchurThreads) k_schur(BaDev d) {
+  __shared__ double s_part[kSchurThreads / 32][42];
   const LmState& st = *d.st;
   if (st.done) return;
-  const int blk = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (blk >= d.n_blocks) return;
+  const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int a = d.blk_a[blk], b = d.blk_b[blk];
   double sca[6], scb[6];
 #pragma unroll
@@ -467,7 +470,7 @@ __global__ void __launch_bounds__(128) k_schur(BaDev d) {
   for (int k = 0; k < 36; k++) acc[k] = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; k++) racc[k] = 0.0;
-  for (int e = d.blk_start[blk] + lane; e < d.blk_start[blk + 1]; e += 32) {
+  for (int e = d.blk_start[blk] + tid; e < d.blk_start[blk + 1]; e += kSchurThreads) {
     const int pa = d.pair_a[e], pb = d.pair_b[e];
     const int j = d.o_pt[pa];
     double Jca[12], Jpa[6], Jpb[6], U[12];
@@ -507,20 +510,26 @@ __global__ void __launch_bounds__(128) k_schur(BaDev d) {
       for (int c = 0; c < 6; c++) acc[r * 6 + c] += Jca[r] * U0[c] + Jca[6 + r] * U1[c];
   }
 #pragma unroll
-  for (int k = 0; k < 36; k++) acc[k] = warp_sum(acc[k]);
+  for (int k = 0; k < 36; k++) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) s_part[warp][k] = v;
+  }
   if (a == b) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) racc[k] = warp_sum(racc[k]);
+    for (int k = 0; k < 6; k++) {
+      const double v = warp_sum(racc[k]);
+      if (lane == 0) s_part[warp][36 + k] = v;
+    }
   }
-  // lane l writes entries l and l+32 (36 values); diagonal blocks add H_cc + D^2 and emit the rhs
-  const double* Hc = d.Hcc + 21 * (size_t)a;
-  for (int idx = lane; idx < 36; idx += 32) {
-    const int r = idx / 6, c = idx - 6 * r;
+  __syncthreads();
+  if (tid < 36) {
+    const int r = tid / 6, c = tid - 6 * r;
     double v = 0.0;
 #pragma unroll
-    for (int k = 0; k < 36; k++) if (k == idx) v = acc[k];
+    for (int w = 0; w < kSchurThreads / 32; w++) v += s_part[w][tid];
     v = -v;
     if (a == b) {
+      const double* Hc = d.Hcc + 21 * (size_t)a;
       const int lo = r < c ? r : c, hi = r < c ? c : r;
       const double h = sca[r] * sca[c] * Hc[SYM6(lo, hi)];
       v += h;
@@ -528,12 +537,12 @@ __global__ void __launch_bounds__(128) k_schur(BaDev d) {
     }
     // value is S[a-block row r][b-block col c]; store transposed into the lower triangle
     d.S[(size_t)(6 * b + c) * d.nc + 6 * a + r] = v;
-  }
-  if (a == b && lane < 6) {
+  } else if (tid < 42 && a == b) {
+    const int k = tid - 36;
     double v = 0.0;
 #pragma unroll
-    for (int k = 0; k < 6; k++) if (k == lane) v = racc[k];
-    d.rhs[6 * a + lane] = sca[lane] * d.gc[6 * (size_t)a + lane] - v;
+    for (int w = 0; w < kSchurThreads / 32; w++) v += s_part[w][36 + k];
+    d.rhs[6 * a + k] = sca[k] * d.gc[6 * (size_t)a + k] - v;
   }
 }
 
@@ -562,56 +571,114 @@ __device__ void cam_candidate(const BaDev& d, const LmState& st, int cam) {
   d.part[d.o_cam_sn2 + a] = sn2;
 }
 
-// Cholesky of the reduced camera system in shared memory (packed lower triangle, rhs as an extra row so the
-// forward substitution rides on the factorisation), back substitution by one warp, then candidate poses.
+// Cholesky of the reduced camera system in shared memory: packed lower triangle, the rhs carried as row n so
+// that the forward substitution rides on the factorisation.  Right-looking in panels of 6 columns (one keyframe
+// block): the 6x6 diagonal block is factored by one warp with shuffles, every row below solves its 6 entries
+// against it independently, the trailing update is a rank-6 update with one warp per row.  Back substitution by
+// one warp, then the candidate keyframe poses.
+constexpr int kPB = 6;
 __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
-  extern __shared__ double L[];   // rows 0..n (row n = rhs), row i at i*(i+1)/2
+  extern __shared__ double smem_d[];
   LmState& st = *d.st;
   if (st.done) return;
-  const int n = d.nc, tid = threadIdx.x;
+  const int n = d.nc, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = kSolveThreads / 32;
+  double* L = smem_d;                                   // rows 0..n, row i at i*(i+1)/2
+  const int ps = n + 2;
+  double* P = L + (size_t)(n + 1) * (n + 2) / 2;        // [kPB][ps]: the current panel's columns, by row
+  double* rdiag = P + kPB * ps;                         // 1 / L[j][j]
+  __shared__ double s_D[kPB][kPB + 1];
   __shared__ int s_fail;
   if (tid == 0) s_fail = st.solve_failed;
-  for (int idx = tid; idx < n * n; idx += kSolveThreads) {
-    const int i = idx / n, k = idx - i * n;
-    if (k <= i) L[i * (i + 1) / 2 + k] = d.S[(size_t)i * n + k];
-  }
-  for (int k = tid; k < n; k += kSolveThreads) L[n * (n + 1) / 2 + k] = d.rhs[k];
-  __syncthreads();
-  for (int j = 0; j < n; j++) {
-    const double djj = L[j * (j + 1) / 2 + j];
-    if (!(djj > 0.0) || !isfinite(djj)) { if (tid == 0) s_fail = 1; break; }   // uniform: all threads read the same value
-    const double ljj = sqrt(djj);
-    __syncthreads();
-    for (int i = j + tid; i <= n; i += kSolveThreads) {
-      if (i == j) L[j * (j + 1) / 2 + j] = ljj; else L[i * (i + 1) / 2 + j] /= ljj;
-    }
-    __syncthreads();
-    const int m = n - j;   // rows j+1 .. n
-    for (int idx = tid; idx < m * m; idx += kSolveThreads) {
-      const int ii = idx / m, kk = idx - ii * m;
-      const int i = j + 1 + ii, k = j + 1 + kk;
-      if (k <= i && k < n) L[i * (i + 1) / 2 + k] -= L[i * (i + 1) / 2 + j] * L[k * (k + 1) / 2 + j];
-    }
-    __syncthreads();
+  for (int i = warp; i <= n; i += nw) {
+    const double* src = i < n ? d.S + (size_t)i * n : d.rhs;
+    const int cnt = i < n ? i + 1 : n;
+    double* dst = L + i * (i + 1) / 2;
+    for (int k = lane; k < cnt; k += 32) dst[k] = src[k];
   }
   __syncthreads();
-  if (tid < 32) {
-    // back substitution L' x = y, y = row n
-    double* y = L + n * (n + 1) / 2;
+  for (int k0 = 0; k0 < n; k0 += kPB) {
+    if (warp == 0) {
+      const int r = lane, row = k0 + r;
+      double a[kPB];
+#pragma unroll
+      for (int c = 0; c < kPB; c++) a[c] = (r < kPB && c <= r) ? L[row * (row + 1) / 2 + k0 + c] : 0.0;
+      bool ok = true;
+      double rinv = 0.0;
+#pragma unroll
+      for (int jj = 0; jj < kPB; jj++) {
+        const double djj = __shfl_sync(0xffffffffu, a[jj], jj);
+        if (!(djj > 0.0) || !isfinite(djj)) ok = false;
+        // one reciprocal square root per pivot (fp64 sqrt and divide are long software sequences and sit on
+        // the critical path of the whole solve); l_jj = d * rsqrt(d)
+        const double inv = rsqrt(djj);
+        if (r == jj) { a[jj] = djj * inv; rinv = inv; } else if (r > jj) a[jj] *= inv;
+#pragma unroll
+        for (int c = jj + 1; c < kPB; c++) {
+          const double lcj = __shfl_sync(0xffffffffu, a[jj], c);
+          if (r >= c) a[c] -= a[jj] * lcj;
+        }
+      }
+      if (r < kPB) {
+#pragma unroll
+        for (int c = 0; c < kPB; c++)
+          if (c <= r) { L[row * (row + 1) / 2 + k0 + c] = a[c]; s_D[r][c] = a[c]; }
+        rdiag[row] = rinv;
+      }
+      if (lane == 0 && !ok) s_fail = 1;
+    }
+    __syncthreads();
+    if (s_fail) break;
+    const int t0 = k0 + kPB;
+    for (int i = t0 + tid; i <= n; i += kSolveThreads) {
+      double* rowp = L + i * (i + 1) / 2 + k0;
+      double x[kPB];
+#pragma unroll
+      for (int c = 0; c < kPB; c++) {
+        double v = rowp[c];
+#pragma unroll
+        for (int q = 0; q < c; q++) v -= x[q] * s_D[c][q];
+        x[c] = v * rdiag[k0 + c];
+        rowp[c] = x[c];
+        P[c * ps + i] = x[c];
+      }
+    }
+    __syncthreads();
+    for (int i = t0 + warp; i <= n; i += nw) {
+      double li[kPB];
+#pragma unroll
+      for (int q = 0; q < kPB; q++) li[q] = P[q * ps + i];
+      const int cmax = i < n ? i : n - 1;
+      double* rowp = L + i * (i + 1) / 2;
+      for (int c = t0 + lane; c <= cmax; c += 32) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < kPB; q++) v += li[q] * P[q * ps + c];
+        rowp[c] -= v;
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double* y = L + n * (n + 1) / 2;      // forward-substituted rhs
     if (!s_fail) {
       for (int j = n - 1; j >= 0; j--) {
-        const double xj = y[j] / L[j * (j + 1) / 2 + j];
+        const double xj = y[j] * rdiag[j];
         __syncwarp();
-        if (tid == 0) y[j] = xj;
-        for (int k = tid; k < j; k += 32) y[k] -= L[j * (j + 1) / 2 + k] * xj;
+        if (lane == 0) y[j] = xj;
+        const double* rowj = L + j * (j + 1) / 2;
+        for (int k = lane; k < j; k += 32) y[k] -= rowj[k] * xj;
         __syncwarp();
       }
     }
-    for (int k = tid; k < n; k += 32) {
+    int bad = 0;
+    for (int k = lane; k < n; k += 32) {
       const double v = s_fail ? 0.0 : y[k];
       d.yc[k] = v;
-      if (!isfinite(v)) s_fail = 1;
+      bad |= !isfinite(v);
     }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0 && bad) s_fail = 1;
   }
   __syncthreads();
   if (tid == 0) st.solve_failed = s_fail;
@@ -993,7 +1060,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
   d.trace = h->d_trace + (size_t)pass * h->trace_rows * kTraceCols;
   const int nlb = d.n_lin_blocks;
   const bool small = d.nc <= kSmallMaxN;
-  const size_t small_smem = (size_t)(d.nc + 1) * (d.nc + 2) / 2 * sizeof(double);
+  const size_t small_smem = ((size_t)(d.nc + 1) * (d.nc + 2) / 2 + (size_t)kPB * (d.nc + 2) + d.nc) * sizeof(double);
   k_lm_init<<<1, 1, 0, st>>>(d, max_iterations);
   h->launches++;
   for (int it = 0; it < max_iterations; it++) {
@@ -1004,7 +1071,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
     h->launches += 4;
     if (d.Kv > 0) {
       if (!small) { CMOS_CUDA_OK(cudaMemsetAsync(d.S, 0, (size_t)d.nc * d.nc * sizeof(double), st)); }
-      k_schur<<<(d.n_blocks + 3) / 4, 128, 0, st>>>(d);
+      k_schur<<<d.n_blocks, kSchurThreads, 0, st>>>(d);
       h->launches++;
       if (small) {
         k_solve_small<<<1, kSolveThreads, small_smem, st>>>(d);

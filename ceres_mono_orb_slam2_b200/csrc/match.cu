@@ -186,21 +186,94 @@ __device__ __forceinline__ QueryFrame project_last(const cmos_camera& cam, const
   return q;
 }
 
-__global__ void __launch_bounds__(kSearchThreads) k_search_frame(cmos_camera cam, const cmos_keypoint* __restrict__ kps,
-                                                                const uint8_t* __restrict__ desc,
-                                                                const int* __restrict__ counts, int stride,
-                                                                const int* __restrict__ grid_start,
-                                                                const int* __restrict__ grid_idx, int max_kp,
-                                                                SearchFrameArgs a) {
+// Phase 1 — one warp per last-frame keypoint (query), the whole batch in one launch: project, walk the grid
+// window in the reference's candidate order, Hamming against every candidate; leaves in global memory the
+// ordered list of candidates with distance <= TH_HIGH (first kListCap), their count, and the first minimum.
+constexpr int kSfWarps = 8;
+constexpr uint32_t kNoBest = 0x7fffffffu;   // low 31 bits of a best word when the query has no candidate
+
+__global__ void __launch_bounds__(kSfWarps * 32) k_sf_lists(cmos_camera cam, const cmos_keypoint* __restrict__ kps,
+                                                           const uint8_t* __restrict__ desc,
+                                                           const int* __restrict__ counts, int stride,
+                                                           const int* __restrict__ grid_start,
+                                                           const int* __restrict__ grid_idx, int max_kp,
+                                                           SearchFrameArgs a, uint32_t* __restrict__ g_lists,
+                                                           uint32_t* __restrict__ g_best, uint16_t* __restrict__ g_cnt) {
+  const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * kSfWarps + warp;
+  const int nq = min(a.last_counts[f], a.last_stride);
+  if (q >= nq) return;
+  const int n = min(counts[f], stride);
+  FrameDev F{kps + (long long)f * stride, desc + (long long)f * stride * 32,
+             grid_start + (long long)f * (kCells + 1), grid_idx + (long long)f * max_kp, n};
+  const cmos_keypoint* last = a.last_kps + (long long)f * a.last_stride;
+  const uint8_t flag = a.last_flags[(long long)f * a.last_stride + q];
+  const size_t slot = (size_t)f * a.last_stride + q;
+  int total = 0, bd = 256, bi = 0;
+  if (flag & 1) {
+    const int oct = last[q].octave;
+    QueryFrame Q = project_last(cam, a.Tcw + (long long)f * 16, a.last_xw + ((long long)f * a.last_stride + q) * 3, oct);
+    if (Q.ok) {
+      const float radius = a.th * cam.scale_factors[oct];
+      const Window w = make_window(cam, Q.u, Q.v, radius);
+      if (w.ok) {
+        uint32_t dq[8];
+        const uint32_t* dsrc = (const uint32_t*)(a.last_desc + ((long long)f * a.last_stride + q) * 32);
+#pragma unroll
+        for (int i = 0; i < 8; i++) dq[i] = __ldg(dsrc + i);
+        walk_window(F, w, Q.u, Q.v, radius, oct - 1, oct + 1, lane, [&](int idx, bool pass) {
+          int d = 256;
+          if (pass) d = hamming256(dq, F.desc + 32 * (size_t)idx);
+          const bool keep = pass && d <= CMOS_TH_HIGH;
+          const unsigned m = __ballot_sync(0xffffffffu, keep);
+          if (m) {
+            const int pos = total + __popc(m & ((1u << lane) - 1));
+            if (keep && pos < kListCap) g_lists[slot * kListCap + pos] = ((uint32_t)d << 16) | (uint32_t)idx;
+            total += __popc(m);
+            // first strict minimum in candidate order
+            unsigned key = ((unsigned)(keep ? d : 256) << 8) | (unsigned)lane, mk = key;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) mk = min(mk, __shfl_xor_sync(0xffffffffu, mk, o));
+            const int cd = (int)(mk >> 8);
+            const int ci = __shfl_sync(0xffffffffu, idx, mk & 31);
+            if (cd < bd) { bd = cd; bi = ci; }
+          }
+        });
+      }
+    }
+  }
+  if (lane == 0) {
+    g_cnt[slot] = (uint16_t)min(total, 65535);
+    g_best[slot] = (total > 0 ? (((uint32_t)bd << 16) | (uint32_t)bi) : kNoBest) | ((uint32_t)((flag >> 1) & 1) << 31);
+  }
+}
+
+// Phase 2 — one CTA per frame pair replays the queries in the reference's order against the `claimed` bytes
+// (ORBmatcher.cc:1176-1250).  Lane 0 of warp 0 runs ahead alone while a query's first minimum is unclaimed (then
+// that candidate is the reference's answer); otherwise the warp re-evaluates the query's list — or walks the
+// window again when the list overflowed.  The rotation histogram is built afterwards in parallel.
+constexpr int kReplayThreads = 256;
+
+__global__ void __launch_bounds__(kReplayThreads) k_sf_replay(cmos_camera cam, const cmos_keypoint* __restrict__ kps,
+                                                             const uint8_t* __restrict__ desc,
+                                                             const int* __restrict__ counts, int stride,
+                                                             const int* __restrict__ grid_start,
+                                                             const int* __restrict__ grid_idx, int max_kp,
+                                                             SearchFrameArgs a, const uint32_t* __restrict__ g_lists,
+                                                             const uint32_t* __restrict__ g_best,
+                                                             const uint16_t* __restrict__ g_cnt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = min(counts[f], stride);
   const int nq = min(a.last_counts[f], a.last_stride);
-  // carve: lists[nq][kListCap] u32 | match[n] i32 | ev_idx[nq] u16 | cnt[nq] u16 | claimed[n] u8 | ev_bin[nq] u8
+  // carve: lists[nq][kListCap] u32 | best[nq] u32 | match[n] i32 | ev_idx[nq] u16 | ev_q[nq] u16 | cnt[nq] u16 |
+  //        claimed[n] u8 | ev_bin[nq] u8
   uint32_t* lists = (uint32_t*)smem_raw;
-  int* s_match = (int*)(lists + (size_t)a.last_stride * kListCap);
+  uint32_t* s_best = lists + (size_t)a.last_stride * kListCap;
+  int* s_match = (int*)(s_best + a.last_stride);
   uint16_t* ev_idx = (uint16_t*)(s_match + stride);
-  uint16_t* cnt = ev_idx + a.last_stride;
+  uint16_t* ev_q = ev_idx + a.last_stride;
+  uint16_t* cnt = ev_q + a.last_stride;
   uint8_t* s_claimed = (uint8_t*)(cnt + a.last_stride);
   uint8_t* ev_bin = s_claimed + stride;
   __shared__ int s_nmatch, s_nev, s_hist[CMOS_HISTO_LENGTH], s_keep[3];
@@ -208,55 +281,49 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_frame(cmos_camera cam
   FrameDev F{kps + (long long)f * stride, desc + (long long)f * stride * 32,
              grid_start + (long long)f * (kCells + 1), grid_idx + (long long)f * max_kp, n};
   const cmos_keypoint* last = a.last_kps + (long long)f * a.last_stride;
-  const uint8_t* lflags = a.last_flags + (long long)f * a.last_stride;
   const double* lxw = a.last_xw + (long long)f * a.last_stride * 3;
   const uint8_t* ldesc = a.last_desc + (long long)f * a.last_stride * 32;
   const double* T = a.Tcw + (long long)f * 16;
+  const size_t base = (size_t)f * a.last_stride;
 
-  for (int i = tid; i < n; i += kSearchThreads) {
+  {
+    const uint4* src = (const uint4*)(g_lists + base * kListCap);
+    uint4* dst = (uint4*)lists;
+    for (int i = tid; i < nq * kListCap / 4; i += kReplayThreads) dst[i] = src[i];
+  }
+  for (int i = tid; i < nq; i += kReplayThreads) { s_best[i] = g_best[base + i]; cnt[i] = g_cnt[base + i]; }
+  for (int i = tid; i < n; i += kReplayThreads) {
     s_match[i] = -1;
     s_claimed[i] = a.claimed ? a.claimed[(long long)f * stride + i] : 0;
   }
   if (tid < CMOS_HISTO_LENGTH) s_hist[tid] = 0;
   if (tid == 0) { s_nmatch = 0; s_nev = 0; }
-
-  // ---- parallel part: ordered candidate lists (distance <= TH_HIGH) ----
-  for (int q = warp; q < nq; q += kSearchThreads / 32) {
-    int total = 0;
-    if (lflags[q] & 1) {
-      const int oct = last[q].octave;
-      QueryFrame Q = project_last(cam, T, lxw + 3 * q, oct);
-      if (Q.ok) {
-        const float radius = a.th * cam.scale_factors[oct];
-        const Window w = make_window(cam, Q.u, Q.v, radius);
-        if (w.ok) {
-          uint32_t dq[8];
-#pragma unroll
-          for (int i = 0; i < 8; i++) dq[i] = __ldg((const uint32_t*)(ldesc + 32 * (size_t)q) + i);
-          walk_window(F, w, Q.u, Q.v, radius, oct - 1, oct + 1, lane, [&](int idx, bool pass) {
-            int d = 256;
-            if (pass) d = hamming256(dq, F.desc + 32 * (size_t)idx);
-            const bool keep = pass && d <= CMOS_TH_HIGH;
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            const int pos = total + __popc(m & ((1u << lane) - 1));
-            if (keep && pos < kListCap) lists[(size_t)q * kListCap + pos] = ((uint32_t)d << 16) | (uint32_t)idx;
-            total += __popc(m);
-          });
-        }
-      }
-    }
-    if (lane == 0) cnt[q] = (uint16_t)min(total, 65535);
-  }
   __syncthreads();
 
-  // ---- sequential replay by one warp (ORBmatcher.cc:1176-1250) ----
   if (warp == 0) {
-    const float factor = 1.0f / CMOS_HISTO_LENGTH;
-    for (int q = 0; q < nq; q++) {
+    int q = 0, nev = 0;
+    for (;;) {
+      int stop = nq;
+      if (lane == 0) {
+        while (q < nq) {
+          const uint32_t bw = s_best[q];
+          if ((bw & 0x7fffffffu) != kNoBest) {
+            const int idx = bw & 0xffff;
+            if (s_claimed[idx]) break;
+            s_match[idx] = q;
+            s_claimed[idx] = (uint8_t)(bw >> 31);
+            ev_idx[nev] = (uint16_t)idx; ev_q[nev] = (uint16_t)q; nev++;
+          }
+          q++;
+        }
+        stop = q;
+      }
+      q = __shfl_sync(0xffffffffu, stop, 0);
+      if (q >= nq) break;
+      __syncwarp();
+      // ---- the first minimum is claimed: best unclaimed candidate of query q ----
       const int c = cnt[q];
-      if (c == 0) continue;
-      unsigned best = 0xffffffffu;   // (dist << 16 | order) then idx separately
-      int best_idx = -1;
+      int best_d = 256, best_idx = -1;
       if (c <= kListCap) {
         unsigned key = 0xffffffffu;
         int idx = -1;
@@ -268,11 +335,9 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_frame(cmos_camera cam
         unsigned mk = key;
 #pragma unroll
         for (int o = 16; o; o >>= 1) mk = min(mk, __shfl_xor_sync(0xffffffffu, mk, o));
-        best = mk;
         const unsigned who = __ballot_sync(0xffffffffu, key == mk && key != 0xffffffffu);
-        if (who) best_idx = __shfl_sync(0xffffffffu, idx, __ffs(who) - 1);
+        if (who) { best_idx = __shfl_sync(0xffffffffu, idx, __ffs(who) - 1); best_d = (int)(mk >> 16); }
       } else {
-        // list overflowed: walk the window again, now against the claimed bytes
         const int oct = last[q].octave;
         QueryFrame Q = project_last(cam, T, lxw + 3 * q, oct);
         const float radius = a.th * cam.scale_factors[oct];
@@ -284,37 +349,39 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_frame(cmos_camera cam
         walk_window(F, w, Q.u, Q.v, radius, oct - 1, oct + 1, lane, [&](int idx, bool pass) {
           int d = 256;
           if (pass && !s_claimed[idx]) d = hamming256(dq, F.desc + 32 * (size_t)idx);
-          // first strict minimum in candidate order: lanes are in order inside a chunk, chunks in order
-          unsigned key = ((unsigned)d << 8) | (unsigned)lane;
-          unsigned mk = key;
+          unsigned key = ((unsigned)d << 8) | (unsigned)lane, mk = key;
 #pragma unroll
           for (int o = 16; o; o >>= 1) mk = min(mk, __shfl_xor_sync(0xffffffffu, mk, o));
           const int cd = (int)(mk >> 8);
           if (cd < bd) { bd = cd; bi = __shfl_sync(0xffffffffu, idx, mk & 31); }
         });
-        if (bd <= CMOS_TH_HIGH) { best = (unsigned)bd << 16; best_idx = bi; }
+        if (bd <= CMOS_TH_HIGH) { best_d = bd; best_idx = bi; }
       }
-      if (best_idx >= 0 && (best >> 16) <= CMOS_TH_HIGH) {
-        if (lane == 0) {
-          s_match[best_idx] = q;
-          s_claimed[best_idx] = (lflags[q] >> 1) & 1;
-          s_nmatch++;
-          if (a.check_ori) {
-            float rot = last[q].angle - F.kps[best_idx].angle;
-            if (rot < 0.0f) rot += 360.0f;
-            int bin = (int)roundf(rot * factor);
-            if (bin == CMOS_HISTO_LENGTH) bin = 0;
-            const int e = s_nev++;
-            ev_idx[e] = (uint16_t)best_idx;
-            ev_bin[e] = (uint8_t)bin;
-            s_hist[bin]++;
-          }
-        }
-        __syncwarp();
+      if (best_idx >= 0 && best_d <= CMOS_TH_HIGH && lane == 0) {
+        s_match[best_idx] = q;
+        s_claimed[best_idx] = (uint8_t)(s_best[q] >> 31);
+        ev_idx[nev] = (uint16_t)best_idx; ev_q[nev] = (uint16_t)q; nev++;
       }
+      __syncwarp();
+      q++;
     }
+    if (lane == 0) { s_nev = nev; s_nmatch = nev; }
+  }
+  __syncthreads();
+  const int nev = s_nev;
+  if (a.check_ori) {
+    const float factor = 1.0f / CMOS_HISTO_LENGTH;
+    for (int e = tid; e < nev; e += kReplayThreads) {
+      float rot = last[ev_q[e]].angle - F.kps[ev_idx[e]].angle;
+      if (rot < 0.0f) rot += 360.0f;
+      int bin = (int)roundf(rot * factor);
+      if (bin == CMOS_HISTO_LENGTH) bin = 0;
+      ev_bin[e] = (uint8_t)bin;
+      atomicAdd(&s_hist[bin], 1);
+    }
+    __syncthreads();
     // ComputeThreeMaxima (ORBmatcher.cc:1386-1418)
-    if (lane == 0 && a.check_ori) {
+    if (tid == 0) {
       int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
       for (int i = 0; i < CMOS_HISTO_LENGTH; i++) {
         const int s = s_hist[i];
@@ -326,23 +393,20 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_frame(cmos_camera cam
       else if (max3 < 0.1f * (float)max1) { i3 = -1; }
       s_keep[0] = i1; s_keep[1] = i2; s_keep[2] = i3;
     }
-  }
-  __syncthreads();
-  if (a.check_ori) {
-    const int nev = s_nev;
+    __syncthreads();
     int removed = 0;
-    for (int e = tid; e < nev; e += kSearchThreads) {
+    for (int e = tid; e < nev; e += kReplayThreads) {
       const int b = ev_bin[e];
       if (b != s_keep[0] && b != s_keep[1] && b != s_keep[2]) { s_match[ev_idx[e]] = -1; removed++; }
     }
     if (removed) atomicSub(&s_nmatch, removed);
     __syncthreads();
   }
-  for (int i = tid; i < n; i += kSearchThreads) {
+  for (int i = tid; i < n; i += kReplayThreads) {
     a.match[(long long)f * stride + i] = s_match[i];
     if (a.claimed) a.claimed[(long long)f * stride + i] = s_claimed[i];
   }
-  for (int i = n + tid; i < stride; i += kSearchThreads) a.match[(long long)f * stride + i] = -1;
+  for (int i = n + tid; i < stride; i += kReplayThreads) a.match[(long long)f * stride + i] = -1;
   if (tid == 0) a.nmatches[f] = s_nmatch;
 }
 
@@ -562,6 +626,8 @@ struct cmos_match {
   int launches = 0;
   // own device buffers
   int *d_grid_start = nullptr, *d_grid_idx = nullptr;
+  uint32_t *d_lists = nullptr, *d_best = nullptr;   // SearchByProjection(frame,last) phase-1 results
+  uint16_t* d_cnt = nullptr;
   // staging for host callers
   cmos_keypoint *s_kps = nullptr, *s_last_kps = nullptr;
   uint8_t *s_desc = nullptr, *s_last_desc = nullptr, *s_last_flags = nullptr, *s_claimed = nullptr;
@@ -587,7 +653,8 @@ int d2h(T* dst, const T* src, size_t n, cudaStream_t st) {
   return CMOS_OK;
 }
 size_t search_frame_smem(int last_stride, int stride) {
-  return (size_t)last_stride * kListCap * 4 + (size_t)stride * 4 + (size_t)last_stride * 2 * 2 + stride + last_stride + 16;
+  // lists + best | match | ev_idx, ev_q, cnt | claimed | ev_bin
+  return (size_t)last_stride * (kListCap + 1) * 4 + (size_t)stride * 4 + (size_t)last_stride * 3 * 2 + stride + last_stride + 16;
 }
 size_t search_points_smem(int point_stride, int stride) {
   return (size_t)point_stride * kListCapPts * 4 + (size_t)stride * 4 + (size_t)point_stride * 2 + stride + 16;
@@ -633,6 +700,9 @@ int cmos_match_create(const cmos_match_params* params, cmos_match_t* out) {
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) err = cudaErrorUnknown;
   h->d_grid_start = dev_alloc<int>(B * (kCells + 1), &err);
   h->d_grid_idx = dev_alloc<int>(B * K, &err);
+  h->d_lists = dev_alloc<uint32_t>(B * K * kListCap, &err);
+  h->d_best = dev_alloc<uint32_t>(B * K, &err);
+  h->d_cnt = dev_alloc<uint16_t>(B * K, &err);
   h->s_kps = dev_alloc<cmos_keypoint>(B * K, &err);
   h->s_last_kps = dev_alloc<cmos_keypoint>(B * K, &err);
   h->s_desc = dev_alloc<uint8_t>(B * K * 32, &err);
@@ -662,7 +732,7 @@ int cmos_match_create(const cmos_match_params* params, cmos_match_t* out) {
     cmos_match_destroy(h);
     return CMOS_ERR_CUDA;
   }
-  cudaFuncSetAttribute(k_search_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  cudaFuncSetAttribute(k_sf_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(k_search_points, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(k_build_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   CMOS_CUDA_OK(cudaGetLastError());
@@ -673,7 +743,7 @@ int cmos_match_create(const cmos_match_params* params, cmos_match_t* out) {
 int cmos_match_destroy(cmos_match_t h) {
   if (!h) return CMOS_OK;
   cudaSetDevice(h->p.device);
-  void* bufs[] = {h->d_grid_start, h->d_grid_idx, h->s_kps, h->s_last_kps, h->s_desc, h->s_last_desc, h->s_last_flags,
+  void* bufs[] = {h->d_grid_start, h->d_grid_idx, h->d_lists, h->d_best, h->d_cnt, h->s_kps, h->s_last_kps, h->s_desc, h->s_last_desc, h->s_last_flags,
                   h->s_claimed, h->s_counts, h->s_last_counts, h->s_match, h->s_nmatches, h->s_last_xw, h->s_T,
                   h->s_np, h->s_level, h->s_in_view, h->s_pdesc, h->s_has_obs, h->s_view_cos, h->s_proj, h->s_mind,
                   h->s_maxd, h->s_pxw, h->s_pnormal, h->s_pose};
@@ -765,11 +835,15 @@ int cmos_match_search_by_projection_frame(cmos_match_t h, const double* Tcw, con
     a.match = h->s_match; a.nmatches = h->s_nmatches;
   }
   h->timer[1].begin(st);
-  k_search_frame<<<B, kSearchThreads, search_frame_smem(last_stride, h->stride), st>>>(
-      h->cam, h->kps, h->desc, h->counts, h->stride, h->d_grid_start, h->d_grid_idx, h->p.max_keypoints, a);
+  k_sf_lists<<<dim3((last_stride + kSfWarps - 1) / kSfWarps, B), kSfWarps * 32, 0, st>>>(
+      h->cam, h->kps, h->desc, h->counts, h->stride, h->d_grid_start, h->d_grid_idx, h->p.max_keypoints, a, h->d_lists,
+      h->d_best, h->d_cnt);
+  k_sf_replay<<<B, kReplayThreads, search_frame_smem(last_stride, h->stride), st>>>(
+      h->cam, h->kps, h->desc, h->counts, h->stride, h->d_grid_start, h->d_grid_idx, h->p.max_keypoints, a, h->d_lists,
+      h->d_best, h->d_cnt);
   h->timer[1].mark(st);
   CMOS_CUDA_OK(cudaGetLastError());
-  h->launches = 1;
+  h->launches = 2;
   if (!on_device) {
     int rc;
     if ((rc = d2h(match, h->s_match, nc, st))) return rc;
