@@ -597,34 +597,34 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
   }
   __syncthreads();
   for (int k0 = 0; k0 < n; k0 += kPB) {
-    if (warp == 0) {
-      const int r = lane, row = k0 + r;
-      double a[kPB];
+    if (tid == 0) {
+      // 6x6 diagonal block in registers of one thread (fully unrolled); one rsqrt per pivot — fp64 sqrt and
+      // divide are long software sequences and this is the critical path of the whole solve
+      double A[kPB][kPB];
 #pragma unroll
-      for (int c = 0; c < kPB; c++) a[c] = (r < kPB && c <= r) ? L[row * (row + 1) / 2 + k0 + c] : 0.0;
+      for (int r = 0; r < kPB; r++)
+#pragma unroll
+        for (int c = 0; c <= r; c++) A[r][c] = L[(k0 + r) * (k0 + r + 1) / 2 + k0 + c];
       bool ok = true;
-      double rinv = 0.0;
 #pragma unroll
       for (int jj = 0; jj < kPB; jj++) {
-        const double djj = __shfl_sync(0xffffffffu, a[jj], jj);
+        const double djj = A[jj][jj];
         if (!(djj > 0.0) || !isfinite(djj)) ok = false;
-        // one reciprocal square root per pivot (fp64 sqrt and divide are long software sequences and sit on
-        // the critical path of the whole solve); l_jj = d * rsqrt(d)
         const double inv = rsqrt(djj);
-        if (r == jj) { a[jj] = djj * inv; rinv = inv; } else if (r > jj) a[jj] *= inv;
+        A[jj][jj] = djj * inv;
+        rdiag[k0 + jj] = inv;
 #pragma unroll
-        for (int c = jj + 1; c < kPB; c++) {
-          const double lcj = __shfl_sync(0xffffffffu, a[jj], c);
-          if (r >= c) a[c] -= a[jj] * lcj;
-        }
-      }
-      if (r < kPB) {
+        for (int r = jj + 1; r < kPB; r++) A[r][jj] *= inv;
 #pragma unroll
-        for (int c = 0; c < kPB; c++)
-          if (c <= r) { L[row * (row + 1) / 2 + k0 + c] = a[c]; s_D[r][c] = a[c]; }
-        rdiag[row] = rinv;
+        for (int c = jj + 1; c < kPB; c++)
+#pragma unroll
+          for (int r = c; r < kPB; r++) A[r][c] -= A[r][jj] * A[c][jj];
       }
-      if (lane == 0 && !ok) s_fail = 1;
+#pragma unroll
+      for (int r = 0; r < kPB; r++)
+#pragma unroll
+        for (int c = 0; c <= r; c++) { L[(k0 + r) * (k0 + r + 1) / 2 + k0 + c] = A[r][c]; s_D[r][c] = A[r][c]; }
+      if (!ok) s_fail = 1;
     }
     __syncthreads();
     if (s_fail) break;
@@ -662,12 +662,28 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
   if (warp == 0) {
     double* y = L + n * (n + 1) / 2;      // forward-substituted rhs
     if (!s_fail) {
-      for (int j = n - 1; j >= 0; j--) {
-        const double xj = y[j] * rdiag[j];
-        __syncwarp();
-        if (lane == 0) y[j] = xj;
-        const double* rowj = L + j * (j + 1) / 2;
-        for (int k = lane; k < j; k += 32) y[k] -= rowj[k] * xj;
+      // blocked back substitution L' x = y: lane 0 solves the 6x6 triangle, the warp updates the rows above
+      for (int k0 = n - kPB; k0 >= 0; k0 -= kPB) {
+        double x[kPB];
+        if (lane == 0) {
+#pragma unroll
+          for (int r = kPB - 1; r >= 0; r--) {
+            double v = y[k0 + r];
+#pragma unroll
+            for (int q = r + 1; q < kPB; q++) v -= L[(k0 + q) * (k0 + q + 1) / 2 + k0 + r] * x[q];
+            x[r] = v * rdiag[k0 + r];
+          }
+#pragma unroll
+          for (int r = 0; r < kPB; r++) y[k0 + r] = x[r];
+        }
+#pragma unroll
+        for (int r = 0; r < kPB; r++) x[r] = __shfl_sync(0xffffffffu, x[r], 0);
+        for (int k = lane; k < k0; k += 32) {
+          double v = y[k];
+#pragma unroll
+          for (int r = 0; r < kPB; r++) v -= L[(k0 + r) * (k0 + r + 1) / 2 + k] * x[r];
+          y[k] = v;
+        }
         __syncwarp();
       }
     }

@@ -209,7 +209,9 @@ __global__ void __launch_bounds__(kSfWarps * 32) k_sf_lists(cmos_camera cam, con
   const cmos_keypoint* last = a.last_kps + (long long)f * a.last_stride;
   const uint8_t flag = a.last_flags[(long long)f * a.last_stride + q];
   const size_t slot = (size_t)f * a.last_stride + q;
-  int total = 0, bd = 256, bi = 0;
+  // lanes 0..kListCap-1 keep the kListCap smallest (distance, candidate order) keys seen so far, ascending
+  uint32_t tkey = 0xffffffffu;
+  int tidx = 0, total = 0;
   if (flag & 1) {
     const int oct = last[q].octave;
     QueryFrame Q = project_last(cam, a.Tcw + (long long)f * 16, a.last_xw + ((long long)f * a.last_stride + q) * 3, oct);
@@ -228,23 +230,33 @@ __global__ void __launch_bounds__(kSfWarps * 32) k_sf_lists(cmos_camera cam, con
           const unsigned m = __ballot_sync(0xffffffffu, keep);
           if (m) {
             const int pos = total + __popc(m & ((1u << lane) - 1));
-            if (keep && pos < kListCap) g_lists[slot * kListCap + pos] = ((uint32_t)d << 16) | (uint32_t)idx;
             total += __popc(m);
-            // first strict minimum in candidate order
-            unsigned key = ((unsigned)(keep ? d : 256) << 8) | (unsigned)lane, mk = key;
+            uint32_t nkey = keep ? (((uint32_t)d << 16) | (uint32_t)min(pos, 0xffff)) : 0xffffffffu;
+            uint32_t okey = 0xffffffffu;
+            int oidx = 0;
 #pragma unroll
-            for (int o = 16; o; o >>= 1) mk = min(mk, __shfl_xor_sync(0xffffffffu, mk, o));
-            const int cd = (int)(mk >> 8);
-            const int ci = __shfl_sync(0xffffffffu, idx, mk & 31);
-            if (cd < bd) { bd = cd; bi = ci; }
+            for (int r = 0; r < kListCap; r++) {
+              const uint32_t mine = min(nkey, tkey);
+              uint32_t wm = mine;
+#pragma unroll
+              for (int o = 16; o; o >>= 1) wm = min(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+              if (wm == 0xffffffffu) break;
+              const int owner = __ffs(__ballot_sync(0xffffffffu, mine == wm)) - 1;
+              const int from_new = __shfl_sync(0xffffffffu, (int)(nkey == wm), owner);
+              const int sel = __shfl_sync(0xffffffffu, from_new ? idx : tidx, owner);
+              if (lane == owner) { if (from_new) nkey = 0xffffffffu; else tkey = 0xffffffffu; }
+              if (lane == r) { okey = wm; oidx = sel; }
+            }
+            tkey = okey; tidx = oidx;
           }
         });
       }
     }
   }
+  if (lane < kListCap && lane < total) g_lists[slot * kListCap + lane] = ((tkey >> 16) << 16) | (uint32_t)tidx;
   if (lane == 0) {
     g_cnt[slot] = (uint16_t)min(total, 65535);
-    g_best[slot] = (total > 0 ? (((uint32_t)bd << 16) | (uint32_t)bi) : kNoBest) | ((uint32_t)((flag >> 1) & 1) << 31);
+    g_best[slot] = (total > 0 ? (((tkey >> 16) << 16) | (uint32_t)tidx) : kNoBest) | ((uint32_t)((flag >> 1) & 1) << 31);
   }
 }
 
@@ -305,14 +317,23 @@ __global__ void __launch_bounds__(kReplayThreads) k_sf_replay(cmos_camera cam, c
     for (;;) {
       int stop = nq;
       if (lane == 0) {
+        // lists are sorted by (distance, candidate order): the first unclaimed entry is the reference's answer
         while (q < nq) {
-          const uint32_t bw = s_best[q];
-          if ((bw & 0x7fffffffu) != kNoBest) {
-            const int idx = bw & 0xffff;
-            if (s_claimed[idx]) break;
-            s_match[idx] = q;
-            s_claimed[idx] = (uint8_t)(bw >> 31);
-            ev_idx[nev] = (uint16_t)idx; ev_q[nev] = (uint16_t)q; nev++;
+          const int c = cnt[q];
+          if (c > 0) {
+            const uint32_t claim = s_best[q] >> 31;
+            const int lim = min(c, kListCap);
+            int k = 0;
+            for (; k < lim; k++) {
+              const int idx = lists[(size_t)q * kListCap + k] & 0xffff;
+              if (!s_claimed[idx]) {
+                s_match[idx] = q;
+                s_claimed[idx] = (uint8_t)claim;
+                ev_idx[nev] = (uint16_t)idx; ev_q[nev] = (uint16_t)q; nev++;
+                break;
+              }
+            }
+            if (k == lim && c > kListCap) break;   // every listed candidate is claimed and there are more: walk again
           }
           q++;
         }
@@ -320,24 +341,9 @@ __global__ void __launch_bounds__(kReplayThreads) k_sf_replay(cmos_camera cam, c
       }
       q = __shfl_sync(0xffffffffu, stop, 0);
       if (q >= nq) break;
+      nev = __shfl_sync(0xffffffffu, nev, 0);
       __syncwarp();
-      // ---- the first minimum is claimed: best unclaimed candidate of query q ----
-      const int c = cnt[q];
-      int best_d = 256, best_idx = -1;
-      if (c <= kListCap) {
-        unsigned key = 0xffffffffu;
-        int idx = -1;
-        if (lane < c) {
-          const uint32_t e = lists[(size_t)q * kListCap + lane];
-          idx = e & 0xffff;
-          if (!s_claimed[idx]) key = ((e >> 16) << 16) | (unsigned)lane;
-        }
-        unsigned mk = key;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) mk = min(mk, __shfl_xor_sync(0xffffffffu, mk, o));
-        const unsigned who = __ballot_sync(0xffffffffu, key == mk && key != 0xffffffffu);
-        if (who) { best_idx = __shfl_sync(0xffffffffu, idx, __ffs(who) - 1); best_d = (int)(mk >> 16); }
-      } else {
+      {
         const int oct = last[q].octave;
         QueryFrame Q = project_last(cam, T, lxw + 3 * q, oct);
         const float radius = a.th * cam.scale_factors[oct];
@@ -355,12 +361,12 @@ __global__ void __launch_bounds__(kReplayThreads) k_sf_replay(cmos_camera cam, c
           const int cd = (int)(mk >> 8);
           if (cd < bd) { bd = cd; bi = __shfl_sync(0xffffffffu, idx, mk & 31); }
         });
-        if (bd <= CMOS_TH_HIGH) { best_d = bd; best_idx = bi; }
-      }
-      if (best_idx >= 0 && best_d <= CMOS_TH_HIGH && lane == 0) {
-        s_match[best_idx] = q;
-        s_claimed[best_idx] = (uint8_t)(s_best[q] >> 31);
-        ev_idx[nev] = (uint16_t)best_idx; ev_q[nev] = (uint16_t)q; nev++;
+        if (bd <= CMOS_TH_HIGH && bi >= 0 && lane == 0) {
+          s_match[bi] = q;
+          s_claimed[bi] = (uint8_t)(s_best[q] >> 31);
+          ev_idx[nev] = (uint16_t)bi; ev_q[nev] = (uint16_t)q;
+        }
+        if (bd <= CMOS_TH_HIGH && bi >= 0) nev++;
       }
       __syncwarp();
       q++;
