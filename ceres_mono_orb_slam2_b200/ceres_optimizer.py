@@ -137,6 +137,34 @@ class CeresOptimizer:
 
     GlobalBundleAdjustemnt = BundleAdjustment   # [sic] the reference's spelling
 
+    # ---- multi-GPU global BA (no reference counterpart) ----
+    def comm_init(self, world: int, rank: int, device=None):
+        """Collective: creates the engine's NCCL communicator; the 128-byte id travels over torch.distributed."""
+        import torch
+        import torch.distributed as dist
+        idbuf = np.zeros(128, np.uint8)
+        if rank == 0:
+            check(self._L.cmos_ba_comm_unique_id(ptr(idbuf)))
+        t = torch.from_numpy(idbuf)
+        if device is not None:
+            t = t.to(device)
+        dist.broadcast(t, src=0)
+        idbuf = np.ascontiguousarray(t.cpu().numpy())
+        check(self._L.cmos_ba_comm_init(self._h, ptr(idbuf), world, rank))
+        self.world, self.rank = world, rank
+
+    def GlobalBundleAdjustemntSharded(self, cams, cam_const, points, obs_cam, obs_pt, uv, inv_sigma2, K4,
+                                      n_iterations: int, world: int, rank: int, is_robust: bool = True, device=None):
+        """Every rank passes the full graph; points/observations are partitioned here, keyframes replicated.
+        Returns (cams, points, summary) with the full point array on every rank."""
+        from . import sharding
+        part = sharding.partition_graph(len(points), obs_cam, obs_pt, uv, inv_sigma2, world, rank)
+        local_pts = np.ascontiguousarray(np.asarray(points, np.float64)[part["lo"]:part["hi"]])
+        self.set_problem(cams, cam_const, local_pts, part["obs_cam"], part["obs_pt"], part["uv"], part["inv_sigma2"], K4)
+        self.run_global(n_iterations, is_robust)
+        cams_o, pts_o, _, summ = self.get_results()
+        return cams_o, sharding.gather_points(pts_o, len(points), world, rank, device), summ[0]
+
     def launch_count(self) -> int:
         n = C.c_int32()
         check(self._L.cmos_ba_last_launch_count(self._h, C.byref(n)))

@@ -250,6 +250,10 @@ struct BaDev {
   double *Hpp, *gp, *Hinv, *tp, *scale_p;   // [M][6], [M][3], [M][6], [M][3], [M][3]
   double *Hcc, *gc, *scale_c;               // [Kv][21], [Kv][6], [Kv][6]
   double *S, *rhs, *yc;                     // [nc][nc] lower, [nc], [nc]
+  double *Sblk;                             // [n_blocks][36] reduced-system blocks (a,b) as assembled by k_schur
+  const int* var_cam;                       // [Kv] variable index -> keyframe
+  double* red;                              // [8] locally reduced scalars (all-reduced across ranks when multi)
+  int multi, is_root;                       // multi: points are sharded over ranks; is_root: adds the keyframe-only terms
   double *part;                             // partial sums, see offsets
   int n_lin_blocks;
   // offsets into part
@@ -329,6 +333,18 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize(BaDev d) {
   }
 }
 
+__device__ void cam_finish(const BaDev& d, const LmState& st, int a) {
+  const double* Hc = d.Hcc + 21 * (size_t)a;
+  const double* g = d.gc + 6 * (size_t)a;
+  if (st.first)
+    for (int k = 0; k < 6; k++) d.scale_c[6 * (size_t)a + k] = 1.0 / (1.0 + sqrt(Hc[SYM6(k, k)]));
+  const double* c = d.cams[st.cur] + 7 * (size_t)d.var_cam[a];
+  double xn2 = 0.0;
+  for (int k = 0; k < 7; k++) xn2 += c[k] * c[k];
+  d.part[d.o_cam_gmax + a] = pose_gradient_max(c, g);
+  d.part[d.o_cam_xn2 + a] = xn2;
+}
+
 __global__ void __launch_bounds__(kCamThreads) k_cam_blocks(BaDev d) {
   __shared__ double s_red[kCamThreads / 32][27];
   const LmState& st = *d.st;
@@ -357,29 +373,21 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_blocks(BaDev d) {
     if (lane == 0) s_red[warp][k] = v;
   }
   __syncthreads();
-  __shared__ double s_out[27];
   if (tid < 27) {
     double t = 0.0;
     for (int w = 0; w < kCamThreads / 32; w++) t += s_red[w][tid];
-    s_out[tid] = t;
     if (tid < 21) d.Hcc[21 * (size_t)a + tid] = t; else d.gc[6 * (size_t)a + tid - 21] = t;
   }
   __syncthreads();
-  if (tid == 0) {
-    if (st.first)
-      for (int k = 0; k < 6; k++) d.scale_c[6 * (size_t)a + k] = 1.0 / (1.0 + sqrt(s_out[SYM6(k, k)]));
-    // the variable keyframe's pose: find it through the first observation (every variable keyframe has one)
-    int cam = -1;
-    if (d.cam_start[a + 1] > d.cam_start[a]) cam = d.o_cam[d.cam_obs[d.cam_start[a]]];
-    double gm = 0.0, xn2 = 0.0;
-    if (cam >= 0) {
-      const double* c = d.cams[st.cur] + 7 * (size_t)cam;
-      gm = pose_gradient_max(c, s_out + 21);
-      for (int k = 0; k < 7; k++) xn2 += c[k] * c[k];
-    }
-    d.part[d.o_cam_gmax + a] = gm;
-    d.part[d.o_cam_xn2 + a] = xn2;
-  }
+  if (tid == 0 && !d.multi) cam_finish(d, st, a);
+}
+
+// Jacobi scale, gradient norm and parameter norm of one variable keyframe from its (global) H_cc, g_c
+__global__ void __launch_bounds__(128) k_cam_finish(BaDev d) {
+  const LmState& st = *d.st;
+  if (st.done || !st.need_lin) return;
+  const int a = blockIdx.x * 128 + threadIdx.x;
+  if (a < d.Kv) cam_finish(d, st, a);
 }
 
 // strided, fixed-order sum / max of a partial array by one CTA
@@ -394,18 +402,26 @@ __device__ double part_max(const double* p, int n, double* scratch) {
   return block_max(v, scratch);
 }
 
-__global__ void __launch_bounds__(256) k_post_lin(BaDev d) {
+// phase 1: reduce this rank's per-CTA partials into red[0..2] = cost, |x|^2 of the points, gradient max;
+// phase 2: add the keyframes' share and run the state machine; phase 0: both (single GPU)
+__global__ void __launch_bounds__(256) k_post_lin(BaDev d, int phase) {
   __shared__ double scratch[33];
   LmState& st = *d.st;
   if (st.done || !st.need_lin) return;
-  const double cost = part_sum(d.part + d.o_lin_cost, d.n_lin_blocks, scratch);
-  const double g1 = part_max(d.part + d.o_lin_gmax, d.n_lin_blocks, scratch);
-  const double g2 = part_max(d.part + d.o_cam_gmax, d.Kv, scratch);
-  const double x1 = part_sum(d.part + d.o_lin_xn2, d.n_lin_blocks, scratch);
-  const double x2 = part_sum(d.part + d.o_cam_xn2, d.Kv, scratch);
-  if (threadIdx.x == 0) {
-    lm_after_linearize(st, cost, fmax(g1, g2), sqrt(x1 + x2), d.trace);
-    if (!st.done && d.stop_flag && *d.stop_flag) { st.done = 1; st.termination = TERM_USER; }   // StopFlagCallback
+  if (phase != 2) {
+    const double cost = part_sum(d.part + d.o_lin_cost, d.n_lin_blocks, scratch);
+    const double x1 = part_sum(d.part + d.o_lin_xn2, d.n_lin_blocks, scratch);
+    const double g1 = part_max(d.part + d.o_lin_gmax, d.n_lin_blocks, scratch);
+    if (threadIdx.x == 0) { d.red[0] = cost; d.red[1] = x1; d.red[2] = g1; }
+    __syncthreads();
+  }
+  if (phase != 1) {
+    const double g2 = part_max(d.part + d.o_cam_gmax, d.Kv, scratch);
+    const double x2 = part_sum(d.part + d.o_cam_xn2, d.Kv, scratch);
+    if (threadIdx.x == 0) {
+      lm_after_linearize(st, d.red[0], fmax(d.red[2], g2), sqrt(d.red[1] + x2), d.trace);
+      if (!st.done && d.stop_flag && *d.stop_flag) { st.done = 1; st.termination = TERM_USER; }   // StopFlagCallback
+    }
   }
 }
 
@@ -528,21 +544,20 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(BaDev d) {
 #pragma unroll
     for (int w = 0; w < kSchurThreads / 32; w++) v += s_part[w][tid];
     v = -v;
-    if (a == b) {
+    if (a == b && d.is_root) {   // keyframe-only terms are added once (by the root rank when points are sharded)
       const double* Hc = d.Hcc + 21 * (size_t)a;
       const int lo = r < c ? r : c, hi = r < c ? c : r;
       const double h = sca[r] * sca[c] * Hc[SYM6(lo, hi)];
       v += h;
       if (r == c) v += fmin(fmax(h, kMinLmDiag), kMaxLmDiag) / st.radius;
     }
-    // value is S[a-block row r][b-block col c]; store transposed into the lower triangle
-    d.S[(size_t)(6 * b + c) * d.nc + 6 * a + r] = v;
+    d.Sblk[(size_t)blk * 36 + tid] = v;   // entry (r, c) of block (a, b)
   } else if (tid < 42 && a == b) {
     const int k = tid - 36;
     double v = 0.0;
 #pragma unroll
     for (int w = 0; w < kSchurThreads / 32; w++) v += s_part[w][36 + k];
-    d.rhs[6 * a + k] = sca[k] * d.gc[6 * (size_t)a + k] - v;
+    d.rhs[6 * a + k] = (d.is_root ? sca[k] * d.gc[6 * (size_t)a + k] : 0.0) - v;
   }
 }
 
@@ -589,11 +604,13 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
   __shared__ double s_D[kPB][kPB + 1];
   __shared__ int s_fail;
   if (tid == 0) s_fail = st.solve_failed;
-  for (int i = warp; i <= n; i += nw) {
-    const double* src = i < n ? d.S + (size_t)i * n : d.rhs;
-    const int cnt = i < n ? i + 1 : n;
-    double* dst = L + i * (i + 1) / 2;
-    for (int k = lane; k < cnt; k += 32) dst[k] = src[k];
+  for (int i = tid; i < n * (n + 1) / 2; i += kSolveThreads) L[i] = 0.0;
+  for (int k = tid; k < n; k += kSolveThreads) L[n * (n + 1) / 2 + k] = d.rhs[k];
+  __syncthreads();
+  for (int e = tid; e < d.n_blocks * 36; e += kSolveThreads) {
+    const int blk = e / 36, rc = e - 36 * blk, r = rc / 6, c = rc - 6 * r;
+    const int row = 6 * d.blk_b[blk] + c, col = 6 * d.blk_a[blk] + r;   // lower-triangle copy of block (a,b), a <= b
+    if (col <= row) L[row * (row + 1) / 2 + col] = d.Sblk[e];
   }
   __syncthreads();
   for (int k0 = 0; k0 < n; k0 += kPB) {
@@ -763,21 +780,31 @@ __global__ void __launch_bounds__(kLinThreads) k_backsub(BaDev d) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_decide(BaDev d) {
+// phase 1: red[3..5] = candidate cost, model cost change, |step|^2 of this rank's points; phase 2: add the
+// keyframes' share and decide; phase 0: both
+__global__ void __launch_bounds__(256) k_decide(BaDev d, int phase) {
   __shared__ double scratch[33];
   LmState& st = *d.st;
   if (st.done) return;
-  const bool ok = !st.solve_failed;
-  double cost = 0, mcc = 0, sn2 = 0;
-  if (ok) {
-    cost = part_sum(d.part + d.o_bs_cost, d.n_lin_blocks, scratch);
-    mcc = part_sum(d.part + d.o_bs_mcc, d.n_lin_blocks, scratch) + part_sum(d.part + d.o_cam_mcc, d.Kv, scratch);
-    sn2 = part_sum(d.part + d.o_bs_sn2, d.n_lin_blocks, scratch) + part_sum(d.part + d.o_cam_sn2, d.Kv, scratch);
+  if (phase != 2) {
+    const double cost = part_sum(d.part + d.o_bs_cost, d.n_lin_blocks, scratch);
+    const double mcc = part_sum(d.part + d.o_bs_mcc, d.n_lin_blocks, scratch);
+    const double sn2 = part_sum(d.part + d.o_bs_sn2, d.n_lin_blocks, scratch);
+    if (threadIdx.x == 0) { d.red[3] = cost; d.red[4] = mcc; d.red[5] = sn2; d.red[6] = st.solve_failed ? 1.0 : 0.0; }
+    __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    lm_decide(st, ok, mcc, cost, sqrt(sn2), d.trace);
-    st.solve_failed = 0;
-    if (!st.done && d.stop_flag && *d.stop_flag) { st.done = 1; st.termination = TERM_USER; }
+  if (phase != 1) {
+    const bool ok = !(d.red[6] > 0.0);
+    double mcc = 0, sn2 = 0;
+    if (ok) {
+      mcc = d.red[4] + part_sum(d.part + d.o_cam_mcc, d.Kv, scratch);
+      sn2 = d.red[5] + part_sum(d.part + d.o_cam_sn2, d.Kv, scratch);
+    }
+    if (threadIdx.x == 0) {
+      lm_decide(st, ok, mcc, d.red[3], sqrt(sn2), d.trace);
+      st.solve_failed = 0;
+      if (!st.done && d.stop_flag && *d.stop_flag) { st.done = 1; st.termination = TERM_USER; }
+    }
   }
 }
 
@@ -821,6 +848,15 @@ __global__ void k_gather_result(BaDev d, const double* cams0, const double* pts0
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i < 7 * d.K) cams_out[i] = aborted ? cams0[i] : d.cams[cur][i];
   if (i < 3 * d.M) pts_out[i] = aborted ? pts0[i] : d.pts[cur][i];
+}
+
+__global__ void __launch_bounds__(256) k_scatter_S(BaDev d) {
+  if (d.st->done) return;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= d.n_blocks * 36) return;
+  const int blk = e / 36, rc = e - 36 * blk, r = rc / 6, c = rc - 6 * r;
+  const int row = 6 * d.blk_b[blk] + c, col = 6 * d.blk_a[blk] + r;
+  if (col <= row) d.S[(size_t)row * d.nc + col] = d.Sblk[e];
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1004,8 +1040,45 @@ using namespace cmos;
 // =================================================================================================
 // Host side
 // =================================================================================================
+// NCCL is bound at run time (dlopen) so that the library loads on hosts without it; only the sharded
+// global bundle adjustment needs it.
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (lib) return true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy && GetErrorString;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclDouble = 8, kNcclSum = 0, kNcclMax = 2;   // ncclFloat64, ncclSum, ncclMax (nccl.h)
+}  // namespace
+
 struct cmos_ba {
   cmos_ba_params p{};
+  ncclComm_t comm = nullptr;
+  int n_ranks = 1, rank = 0;
+  int* d_var_cam = nullptr;
+  double* d_red = nullptr;
+  double* d_HG = nullptr;          // [Kv][21] H_cc then [Kv][6] g_c, contiguous (one all-reduce)
+  double* d_Sblk = nullptr;        // [n_blocks][36] then rhs [nc], contiguous (one all-reduce)
   cudaStream_t stream = nullptr;
   // capacities
   size_t cap_pairs = 0, cap_blocks = 0, cap_S = 0;
@@ -1077,23 +1150,53 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
   const int nlb = d.n_lin_blocks;
   const bool small = d.nc <= kSmallMaxN;
   const size_t small_smem = ((size_t)(d.nc + 1) * (d.nc + 2) / 2 + (size_t)kPB * (d.nc + 2) + d.nc) * sizeof(double);
+  const bool multi = d.multi != 0;
+  auto allreduce = [&](double* buf, size_t count, int op) -> int {
+    const int rc = g_nccl.AllReduce(buf, buf, count, kNcclDouble, op, h->comm, st);
+    if (rc != 0) { set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString(rc)); return CMOS_ERR_CUDA; }
+    return CMOS_OK;
+  };
+  auto linearize = [&]() -> int {
+    k_linearize<<<nlb, kLinThreads, 0, st>>>(d);
+    if (d.Kv > 0) k_cam_blocks<<<d.Kv, kCamThreads, 0, st>>>(d);
+    h->launches += 2;
+    if (!multi) {
+      k_post_lin<<<1, 256, 0, st>>>(d, 0);
+      h->launches++;
+      return CMOS_OK;
+    }
+    int rc;
+    if (d.Kv > 0) {
+      if ((rc = allreduce(h->d_HG, (size_t)27 * d.Kv, kNcclSum))) return rc;      // H_cc and g_c of every keyframe
+      k_cam_finish<<<(d.Kv + 127) / 128, 128, 0, st>>>(d);
+    }
+    k_post_lin<<<1, 256, 0, st>>>(d, 1);
+    if ((rc = allreduce(d.red, 2, kNcclSum))) return rc;                          // cost, |x|^2
+    if ((rc = allreduce(d.red + 2, 1, kNcclMax))) return rc;                      // gradient max norm
+    k_post_lin<<<1, 256, 0, st>>>(d, 2);
+    h->launches += 3;
+    return CMOS_OK;
+  };
   k_lm_init<<<1, 1, 0, st>>>(d, max_iterations);
   h->launches++;
   for (int it = 0; it < max_iterations; it++) {
-    k_linearize<<<nlb, kLinThreads, 0, st>>>(d);
-    if (d.Kv > 0) k_cam_blocks<<<d.Kv, kCamThreads, 0, st>>>(d);
-    k_post_lin<<<1, 256, 0, st>>>(d);
+    int rc;
+    if ((rc = linearize())) return rc;
     k_point_prep<<<nlb, kLinThreads, 0, st>>>(d);
-    h->launches += 4;
+    h->launches++;
     if (d.Kv > 0) {
-      if (!small) { CMOS_CUDA_OK(cudaMemsetAsync(d.S, 0, (size_t)d.nc * d.nc * sizeof(double), st)); }
       k_schur<<<d.n_blocks, kSchurThreads, 0, st>>>(d);
       h->launches++;
+      // the one exchange step of the sharded solve: partial reduced camera system + rhs summed over ranks
+      if (multi && (rc = allreduce(d.Sblk, (size_t)d.n_blocks * 36 + d.nc, kNcclSum))) return rc;
       if (small) {
         k_solve_small<<<1, kSolveThreads, small_smem, st>>>(d);
         h->launches++;
       } else {
         const int n = d.nc;
+        CMOS_CUDA_OK(cudaMemsetAsync(d.S, 0, (size_t)n * n * sizeof(double), st));
+        k_scatter_S<<<(d.n_blocks * 36 + 255) / 256, 256, 0, st>>>(d);
+        h->launches++;
         for (int k0 = 0; k0 < n; k0 += kNB) {
           const int kb = std::min(kNB, n - k0);
           k_potrf_diag<<<1, 256, kPanelSmem, st>>>(d, k0, kb, h->d_Linv);
@@ -1116,14 +1219,20 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
       }
     }
     k_backsub<<<nlb, kLinThreads, 0, st>>>(d);
-    k_decide<<<1, 256, 0, st>>>(d);
-    h->launches += 2;
+    h->launches++;
+    if (!multi) {
+      k_decide<<<1, 256, 0, st>>>(d, 0);
+      h->launches++;
+    } else {
+      k_decide<<<1, 256, 0, st>>>(d, 1);
+      if ((rc = allreduce(d.red + 3, 4, kNcclSum))) return rc;                    // candidate cost, model change, |step|^2, failure
+      k_decide<<<1, 256, 0, st>>>(d, 2);
+      h->launches += 2;
+    }
   }
   if (max_iterations == 0) {   // Ceres still evaluates iteration 0
-    k_linearize<<<nlb, kLinThreads, 0, st>>>(d);
-    if (d.Kv > 0) k_cam_blocks<<<d.Kv, kCamThreads, 0, st>>>(d);
-    k_post_lin<<<1, 256, 0, st>>>(d);
-    h->launches += 3;
+    int rc;
+    if ((rc = linearize())) return rc;
   }
   k_summary<<<1, 1, 0, st>>>(d, h->d_summaries + pass);
   h->launches++;
@@ -1166,8 +1275,9 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
        alloc(&h->d_o_uv, N) && alloc(&h->d_o_w, N) && alloc(&h->d_o_mode, N) && alloc(&h->d_cam_flags, K) &&
        alloc(&h->d_erase, N);
   ok = ok && alloc(&d.Jc, 12 * N) && alloc(&d.Jp, 6 * N) && alloc(&d.res, 2 * N) && alloc(&d.Hpp, 6 * M) && alloc(&d.gp, 3 * M) &&
-       alloc(&d.Hinv, 6 * M) && alloc(&d.tp, 3 * M) && alloc(&d.scale_p, 3 * M) && alloc(&d.Hcc, 21 * K) &&
-       alloc(&d.gc, 6 * K) && alloc(&d.scale_c, 6 * K) && alloc(&d.S, h->cap_S) && alloc(&d.rhs, 6 * K + 8) &&
+       alloc(&d.Hinv, 6 * M) && alloc(&d.tp, 3 * M) && alloc(&d.scale_p, 3 * M) && alloc(&h->d_HG, 27 * K) &&
+       alloc(&h->d_var_cam, K) && alloc(&h->d_red, 8) && alloc(&h->d_Sblk, h->cap_blocks * 36 + 6 * K + 8) &&
+       alloc(&d.scale_c, 6 * K) && alloc(&d.S, h->cap_S) &&
        alloc(&d.yc, 6 * K + 8) && alloc(&d.part, 6 * nlb + 4 * K + 16) && alloc(&d.st, 1) &&
        alloc(&h->d_Linv, ((6 * K + kNB - 1) / kNB) * kNB * kNB) && alloc(&h->d_trace, 2 * (size_t)h->trace_rows * kTraceCols) &&
        alloc(&h->d_summaries, 2);
@@ -1197,12 +1307,13 @@ int cmos_ba_destroy(cmos_ba_t h) {
   void* bufs[] = {d.cams[0], d.cams[1], d.pts[0], d.pts[1], h->d_cams0, h->d_pts0, h->d_cams_out, h->d_pts_out, h->d_cam_var,
                   h->d_o_cam, h->d_o_cv, h->d_o_pt, h->d_pt_start, h->d_cam_start, h->d_cam_obs, h->d_blk_a, h->d_blk_b,
                   h->d_blk_start, h->d_pair_a, h->d_pair_b, h->d_perm, h->d_o_uv, h->d_o_w, h->d_o_mode, h->d_cam_flags,
-                  h->d_erase, d.Jc, d.Jp, d.res, d.Hpp, d.gp, d.Hinv, d.tp, d.scale_p, d.Hcc, d.gc, d.scale_c, d.S, d.rhs,
+                  h->d_erase, d.Jc, d.Jp, d.res, d.Hpp, d.gp, d.Hinv, d.tp, d.scale_p, h->d_HG, h->d_var_cam, h->d_red, h->d_Sblk, d.scale_c, d.S,
                   d.yc, d.part, d.st, h->d_Linv, h->d_trace, h->d_summaries, h->dp_pose, h->dp_xw, h->dp_uv, h->dp_w,
                   h->dp_n, h->dp_inl, h->dp_out, h->dp_sum, h->dp_trace};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (h->stop_registered_by_us && h->stop_host_page) cudaHostUnregister((void*)h->stop_host_page);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   if (h->stream) cudaStreamDestroy(h->stream);
   h->timer.destroy();
   delete h;
@@ -1296,10 +1407,10 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
     o_uv[p] = make_float2(uv[2 * i], uv[2 * i + 1]); o_w[p] = inv_sigma2[i];
     if (o_cv[p] >= 0) cam_start[o_cv[p] + 1]++;
   }
-  for (int a = 0; a < Kv; a++) {
-    CMOS_REQUIRE(cam_start[a + 1] > 0, "a variable keyframe has no observation");
-    cam_start[a + 1] += cam_start[a];
-  }
+  for (int a = 0; a < Kv; a++) cam_start[a + 1] += cam_start[a];
+  std::vector<int> var_cam(std::max(Kv, 1), 0);
+  for (int k = 0; k < K; k++)
+    if (cam_var[k] >= 0) var_cam[cam_var[k]] = k;
   std::vector<int> cam_obs(std::max(cam_start[Kv], 1));
   {
     std::vector<int> f2(cam_start.begin(), cam_start.end() - 1);
@@ -1359,6 +1470,7 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
   CMOS_CUDA_OK(up(h->d_cams0, cams, 7 * (size_t)K * sizeof(double)));
   CMOS_CUDA_OK(up(h->d_pts0, points, 3 * (size_t)M * sizeof(double)));
   CMOS_CUDA_OK(up(h->d_cam_var, cam_var.data(), K * sizeof(int)));
+  CMOS_CUDA_OK(up(h->d_var_cam, var_cam.data(), var_cam.size() * sizeof(int)));
   CMOS_CUDA_OK(up(h->d_cam_flags, cam_flags, K));
   CMOS_CUDA_OK(up(h->d_o_cam, o_cam.data(), N * sizeof(int)));
   CMOS_CUDA_OK(up(h->d_o_cv, o_cv.data(), N * sizeof(int)));
@@ -1380,6 +1492,10 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
   d.o_w = h->d_o_w; d.o_mode = h->d_o_mode; d.pt_start = h->d_pt_start; d.cam_start = h->d_cam_start;
   d.cam_obs = h->d_cam_obs; d.blk_a = h->d_blk_a; d.blk_b = h->d_blk_b; d.blk_start = h->d_blk_start;
   d.pair_a = h->d_pair_a; d.pair_b = h->d_pair_b;
+  d.var_cam = h->d_var_cam; d.red = h->d_red;
+  d.Hcc = h->d_HG; d.gc = h->d_HG + 21 * (size_t)Kv;
+  d.Sblk = h->d_Sblk; d.rhs = h->d_Sblk + (size_t)nb * 36;
+  d.multi = h->n_ranks > 1; d.is_root = h->rank == 0;
   const int nlb = (M + kLinThreads - 1) / kLinThreads;
   d.n_lin_blocks = nlb;
   int o = 0;
@@ -1388,7 +1504,7 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
   d.o_cam_gmax = o; o += Kv; d.o_cam_xn2 = o; o += Kv; d.o_cam_mcc = o; o += Kv; d.o_cam_sn2 = o; o += Kv;
   d.trace = nullptr; d.stop_flag = nullptr;
   CMOS_CUDA_OK(cudaMemsetAsync(d.part, 0, (size_t)o * sizeof(double), st));
-  if (d.nc <= kSmallMaxN && d.nc > 0) CMOS_CUDA_OK(cudaMemsetAsync(d.S, 0, (size_t)d.nc * d.nc * sizeof(double), st));
+  CMOS_CUDA_OK(cudaMemsetAsync(d.red, 0, 8 * sizeof(double), st));
   CMOS_CUDA_OK(cudaStreamSynchronize(st));   // the host vectors die here
   h->has_problem = true;
   h->ran = false;
@@ -1415,6 +1531,7 @@ int cmos_ba_run_local(cmos_ba_t h, int32_t iterations_pass0, int32_t iterations_
   if (!h->has_problem) { set_error("cmos_ba_set_problem must be called first"); return CMOS_ERR_STATE; }
   CMOS_REQUIRE(iterations_pass0 >= 0 && iterations_pass1 >= 0 && iterations_pass0 + 1 < h->trace_rows &&
                iterations_pass1 + 1 < h->trace_rows, "bad iteration counts");
+  CMOS_REQUIRE(h->n_ranks == 1, "LocalBundleAdjustment runs on one GPU (replicas only, SURVEY.md 8e)");
   CMOS_CUDA_OK(cudaSetDevice(h->p.device));
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   int rc = map_stop_flag(h, stop_flag, &h->d.stop_flag);
@@ -1493,6 +1610,31 @@ int cmos_ba_bundle_adjustment(cmos_ba_t h, int32_t n_cams, double* cams, const u
   rc = cmos_ba_get_results(h, cams, points, nullptr, s2, nullptr);
   if (summary) *summary = s2[0];
   return rc;
+}
+
+int cmos_ba_comm_unique_id(uint8_t* id128) {
+  CMOS_REQUIRE(id128, "null argument");
+  if (!g_nccl.load()) { set_error("NCCL (libnccl.so.2) is not available: %s", dlerror()); return CMOS_ERR_STATE; }
+  ncclUniqueId id;
+  const int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) { set_error("ncclGetUniqueId failed: %s", g_nccl.GetErrorString(rc)); return CMOS_ERR_CUDA; }
+  std::memcpy(id128, id.internal, 128);
+  return CMOS_OK;
+}
+
+int cmos_ba_comm_init(cmos_ba_t h, const uint8_t* id128, int32_t n_ranks, int32_t rank) {
+  CMOS_REQUIRE(h && id128 && n_ranks >= 1 && rank >= 0 && rank < n_ranks, "bad argument");
+  if (!g_nccl.load()) { set_error("NCCL (libnccl.so.2) is not available: %s", dlerror()); return CMOS_ERR_STATE; }
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+  ncclUniqueId id;
+  std::memcpy(id.internal, id128, 128);
+  const int rc = g_nccl.CommInitRank(&h->comm, n_ranks, id, rank);
+  if (rc != 0) { set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(rc)); h->comm = nullptr; return CMOS_ERR_CUDA; }
+  h->n_ranks = n_ranks;
+  h->rank = rank;
+  h->has_problem = false;
+  return CMOS_OK;
 }
 
 int cmos_ba_debug_trace(cmos_ba_t h, int32_t pass, double* trace, int32_t rows) {

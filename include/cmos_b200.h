@@ -306,6 +306,19 @@ int cmos_ba_bundle_adjustment(cmos_ba_t h, int32_t n_cams, double* cams, const u
                               const float* uv, const float* inv_sigma2, const float* K4, int32_t n_iterations,
                               int32_t robust, const uint8_t* stop_flag, cmos_ba_summary* summary);
 
+/* Multi-GPU global bundle adjustment (no counterpart in the reference, which is single process).
+ * One process per GPU.  Map points — and with them their observations — are partitioned over the ranks;
+ * keyframes are replicated.  Each rank uploads ALL keyframes but only ITS points/observations with
+ * cmos_ba_set_problem, then every rank calls cmos_ba_run_global with the same arguments.  Per LM iteration the
+ * ranks exchange, with NCCL all-reduces enqueued on the solve's stream: the keyframe blocks H_cc/g_c, the partial
+ * reduced camera system S + rhs (the one large message), and three short vectors of scalars (cost, norms, step
+ * statistics).  The reduced system is then factorised redundantly on every rank, so keyframe poses stay
+ * replicated bit for bit and the points never leave their rank.  NCCL is bound with dlopen("libnccl.so.2").
+ *   cmos_ba_comm_unique_id: rank 0 creates the 128-byte NCCL id; the caller ships it to the other ranks
+ *   cmos_ba_comm_init:      collective over all ranks; after it the handle's solves are sharded */
+int cmos_ba_comm_unique_id(uint8_t* id128);
+int cmos_ba_comm_init(cmos_ba_t h, const uint8_t* id128, int32_t n_ranks, int32_t rank);
+
 /* Verification taps: per-iteration trace rows [iteration][8] = cost, cost_change, gradient_max_norm, step_norm,
  * relative_decrease, trust-region radius, accepted, valid (row 0 = initial evaluation). */
 int cmos_ba_debug_trace(cmos_ba_t h, int32_t pass, double* trace, int32_t rows);
