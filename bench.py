@@ -333,18 +333,19 @@ def run_b200(args):
         matcher.SearchByProjectionFrame(d_T, d_lk, d_lcounts, d_flags, d_xw, d_mdesc, cap, TH_PROJ, claimed=None,
                                         out=(d_match, d_nm), on_device=True, stream=sp)
 
+    # end to end: ONE public call with host (page-locked) buffers — images + last-frame views in, keypoints,
+    # descriptors and matches out; chunks of the batch are pipelined over CUDA streams inside the library
+    from ceres_mono_orb_slam2_b200 import TrackingFrontEnd
+    front = TrackingFrontEnd(cam, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, lanes=args.lanes,
+                             chunk_frames=args.chunk, device=local_rank)
+    h_lk_u8 = pin((B, cap * 28), torch.uint8); h_lk_u8.numpy()[:] = lk.view(np.uint8).reshape(B, cap * 28)
+    h_lk = h_lk_u8.numpy().view(KP_DTYPE).reshape(B, cap)
+    h_lcounts = pin((B,), torch.int32); h_lcounts.numpy()[:] = lcounts
+    e2e_out = (h_kps, h_desc.numpy(), h_counts.numpy(), h_match.numpy(), h_nm.numpy())
+    e2e_in = (h_images.numpy(), h_T.numpy(), h_lk, h_lcounts.numpy(), h_flags.numpy(), h_xw.numpy(), h_mdesc.numpy())
+
     def step_e2e():
-        # host images in, host keypoints/descriptors/matches out; the map-point views come from host memory too
-        ext.extract_batch(h_images.numpy(), out=out_bufs)                       # H2D images, D2H kps/desc/counts
-        with torch.cuda.stream(stream):
-            d_flags.copy_(h_flags, non_blocking=True); d_xw.copy_(h_xw, non_blocking=True)
-            d_mdesc.copy_(h_mdesc, non_blocking=True); d_T.copy_(h_T, non_blocking=True)
-        matcher.set_frames(cam, kp_ptr, desc_ptr, cnt_ptr, B, cap, on_device=True, stream=sp)
-        matcher.SearchByProjectionFrame(d_T, d_lk, d_lcounts, d_flags, d_xw, d_mdesc, cap, TH_PROJ, claimed=None,
-                                        out=(d_match, d_nm), on_device=True, stream=sp)
-        with torch.cuda.stream(stream):
-            h_match.copy_(d_match, non_blocking=True); h_nm.copy_(d_nm, non_blocking=True)
-        stream.synchronize()
+        front.track(*e2e_in, TH_PROJ, out=e2e_out)
 
     def barrier():
         if world > 1:
@@ -441,10 +442,12 @@ def run_b200(args):
                                         "frac": alg["frame_total"] * B / (step_ms * 1e-3) / 1e9 / peak}},
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(h_images.numel() + h_flags.numel() + h_xw.numel() * 8 +
-                                              h_mdesc.numel() + h_T.numel() * 8),
+                                              h_mdesc.numel() + h_T.numel() * 8 + h_lk_u8.numel() + h_lcounts.numel() * 4),
                     "d2h_bytes_per_step": int(h_kps_u8.numel() + h_desc.numel() + h_counts.numel() * 4 +
                                               h_match.numel() * 4 + h_nm.numel() * 4),
-                    "ms_per_step": e2e_ms_max / args.steps},
+                    "ms_per_step": e2e_ms_max / args.steps,
+                    "call": f"cmos_track_frames: {args.lanes} stream lanes x chunks of {args.chunk} frames, pinned host buffers",
+                    "gpu_launches_per_step": front.launch_count()},
             "gpu_launches": (ext.launch_count() + 1 + matcher.launch_count()) * args.steps,
             "clocks": clocks,
         }
@@ -476,6 +479,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--lanes", type=int, default=4, help="stream lanes of the end-to-end front-end call")
+    ap.add_argument("--chunk", type=int, default=16, help="frames per pipelined chunk of the end-to-end call")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ba", action="store_true", help="skip the bundle-adjustment section")

@@ -8,5 +8,6 @@ from ._lib import KP_DTYPE, CmosError, LIB_PATH  # noqa: F401
 from .orb_extractor import ORBextractor  # noqa: F401
 from .orb_matcher import ORBmatcher, Camera  # noqa: F401
 from .ceres_optimizer import CeresOptimizer  # noqa: F401
+from .tracking import TrackingFrontEnd  # noqa: F401
 
-__all__ = ["ORBextractor", "ORBmatcher", "Camera", "CeresOptimizer", "KP_DTYPE", "CmosError", "LIB_PATH"]
+__all__ = ["ORBextractor", "ORBmatcher", "Camera", "CeresOptimizer", "TrackingFrontEnd", "KP_DTYPE", "CmosError", "LIB_PATH"]

@@ -136,14 +136,22 @@ __global__ void __launch_bounds__(256) k_build_grid(cmos_camera cam, const cmos_
   __syncthreads();
   int* gs = grid_start + (long long)f * (kCells + 1);
   for (int i = tid; i <= kCells; i += 256) gs[i] = cnt[i];
-  // position inside the cell = number of earlier keypoints in the same cell (insertion order)
+  __syncthreads();   // cnt[] becomes the per-cell cursor below
+  // Stable scatter (insertion order inside a cell, Frame.cc:166-172): warp 0 walks the keypoints 32 at a time in
+  // index order; lanes that share a cell take consecutive slots from that cell's cursor.
   int* gi = grid_idx + (long long)f * max_kp;
-  for (int i = tid; i < n; i += 256) {
-    const short c = cell_of[i];
-    if (c < 0) continue;
-    int r = 0;
-    for (int j = 0; j < i; j++) r += cell_of[j] == c;
-    gi[cnt[c] + r] = i;
+  if (tid < 32) {
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + tid;
+      const int c = i < n ? (int)cell_of[i] : -1;
+      const unsigned peers = __match_any_sync(0xffffffffu, c);
+      const int leader = __ffs(peers) - 1;
+      int cur = 0;
+      if (c >= 0 && tid == leader) { cur = cnt[c]; cnt[c] = cur + __popc(peers); }
+      cur = __shfl_sync(0xffffffffu, cur, leader);
+      if (c >= 0) gi[cur + __popc(peers & ((1u << tid) - 1))] = i;
+      __syncwarp();
+    }
   }
 }
 
@@ -260,10 +268,16 @@ __global__ void __launch_bounds__(kSfWarps * 32) k_sf_lists(cmos_camera cam, con
   }
 }
 
-// Phase 2 — one CTA per frame pair replays the queries in the reference's order against the `claimed` bytes
-// (ORBmatcher.cc:1176-1250).  Lane 0 of warp 0 runs ahead alone while a query's first minimum is unclaimed (then
-// that candidate is the reference's answer); otherwise the warp re-evaluates the query's list — or walks the
-// window again when the list overflowed.  The rotation histogram is built afterwards in parallel.
+// Phase 2 — one CTA per frame pair resolves the greedy, order-dependent assignment (ORBmatcher.cc:1176-1250).
+// Sequentially, query q takes the first entry of its (distance, order)-sorted list that no CLAIMING query j < q
+// holds (a claiming query is one whose map point has Observations() > 0, :1220-1221).  That is a fixed point and
+// is computed in parallel: every query points at a list entry; owner[idx] = lowest claiming query that ever
+// pointed at idx (atomicMin — a query only leaves an entry when a lower one owns it, so "ever" == "currently");
+// queries whose entry is owned by a lower query advance; repeat until nothing moves.  match[idx] is the highest
+// query that ends on idx (the last writer), every final pick is one rotation-histogram event and one nmatches++.
+// A query that exhausts a truncated list (more than kListCap candidates, all taken) re-walks its window for the best
+// keypoint no lower query holds, so the result never depends on the list capacity.  After kMaxRounds rounds
+// (pathological chains) the frame is replayed sequentially by one warp instead — the same answer, slowly.
 constexpr int kReplayThreads = 256;
 
 __global__ void __launch_bounds__(kReplayThreads) k_sf_replay(cmos_camera cam, const cmos_keypoint* __restrict__ kps,
@@ -288,7 +302,10 @@ __global__ void __launch_bounds__(kReplayThreads) k_sf_replay(cmos_camera cam, c
   uint16_t* cnt = ev_q + a.last_stride;
   uint8_t* s_claimed = (uint8_t*)(cnt + a.last_stride);
   uint8_t* ev_bin = s_claimed + stride;
-  __shared__ int s_nmatch, s_nev, s_hist[CMOS_HISTO_LENGTH], s_keep[3];
+  uint8_t* ptr = ev_bin + a.last_stride;                                   // [nq] current list position, 0xff = none
+  int* owner = (int*)(((uintptr_t)(ptr + a.last_stride) + 3) & ~(uintptr_t)3);   // [n]
+  uint16_t* ext = (uint16_t*)(owner + stride);                             // [nq] pick found by a window re-walk
+  __shared__ int s_nmatch, s_nev, s_hist[CMOS_HISTO_LENGTH], s_keep[3], s_changed, s_nover;
 
   FrameDev F{kps + (long long)f * stride, desc + (long long)f * stride * 32,
              grid_start + (long long)f * (kCells + 1), grid_idx + (long long)f * max_kp, n};
@@ -312,7 +329,93 @@ __global__ void __launch_bounds__(kReplayThreads) k_sf_replay(cmos_camera cam, c
   if (tid == 0) { s_nmatch = 0; s_nev = 0; }
   __syncthreads();
 
-  if (warp == 0) {
+  // ---- parallel fixed point ----
+  // ptr[q]: 0..kListCap-1 = position in the stored list, kExt = pick found by re-walking the window (ext[q]),
+  // kNone = no candidate left (final: the set of blocked keypoints only grows).
+  constexpr int kExt = 0xfe, kNone = 0xff, kMaxRounds = 64;
+  for (int i = tid; i < n; i += kReplayThreads) owner[i] = s_claimed[i] ? -1 : 0x7fffffff;
+  for (int q = tid; q < nq; q += kReplayThreads) ptr[q] = cnt[q] > 0 ? 0 : kNone;
+  uint16_t* over = ev_q;            // queries that must re-walk their window this round (ev_q is free until the end)
+  bool sequential = false;
+  for (int round = 0;; round++) {
+    __syncthreads();
+    if (tid == 0) { s_changed = 0; s_nover = 0; }
+    // A: every claiming query stamps the keypoint it points at
+    for (int q = tid; q < nq; q += kReplayThreads) {
+      const int k = ptr[q];
+      if (k == kNone || !(s_best[q] >> 31)) continue;
+      atomicMin(&owner[k == kExt ? (int)ext[q] : (int)(lists[(size_t)q * kListCap + k] & 0xffff)], q);
+    }
+    __syncthreads();
+    // B: queries whose keypoint belongs to a lower query move on
+    for (int q = tid; q < nq; q += kReplayThreads) {
+      int k = ptr[q];
+      if (k == kNone) continue;
+      if (k == kExt) {
+        if (owner[ext[q]] < q) over[atomicAdd(&s_nover, 1)] = (uint16_t)q;
+        continue;
+      }
+      const int c = cnt[q], lim = min(c, kListCap), k0 = k;
+      while (k < lim && owner[lists[(size_t)q * kListCap + k] & 0xffff] < q) k++;
+      if (k == lim) {
+        if (c > kListCap) { over[atomicAdd(&s_nover, 1)] = (uint16_t)q; continue; }   // truncated list exhausted
+        k = kNone;
+      }
+      if (k != k0) { ptr[q] = (uint8_t)k; s_changed = 1; }
+    }
+    __syncthreads();
+    // C: one warp per exhausted query walks its window again: best keypoint not held by a lower query
+    const int nover = s_nover;
+    for (int i = warp; i < nover; i += kReplayThreads / 32) {
+      const int q = over[i];
+      const int oct = last[q].octave;
+      QueryFrame Q = project_last(cam, T, lxw + 3 * q, oct);
+      const float radius = a.th * cam.scale_factors[oct];
+      const Window w = make_window(cam, Q.u, Q.v, radius);
+      uint32_t dq[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) dq[j] = __ldg((const uint32_t*)(ldesc + 32 * (size_t)q) + j);
+      int bd = 256, bi = -1;
+      walk_window(F, w, Q.u, Q.v, radius, oct - 1, oct + 1, lane, [&](int idx, bool pass) {
+        int d = 256;
+        if (pass && owner[idx] >= q) d = hamming256(dq, F.desc + 32 * (size_t)idx);
+        unsigned key = ((unsigned)d << 8) | (unsigned)lane, mk = key;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mk = min(mk, __shfl_xor_sync(0xffffffffu, mk, o));
+        const int cd = (int)(mk >> 8);
+        if (cd < bd) { bd = cd; bi = __shfl_sync(0xffffffffu, idx, mk & 31); }
+      });
+      if (lane == 0) {
+        if (bd <= CMOS_TH_HIGH && bi >= 0) { ptr[q] = kExt; ext[q] = (uint16_t)bi; }
+        else ptr[q] = kNone;
+        s_changed = 1;
+      }
+    }
+    __syncthreads();
+    if (!s_changed) break;
+    if (round >= kMaxRounds) { sequential = true; break; }   // pathological chains: exact sequential replay instead
+  }
+  if (!sequential) {
+    for (int q = tid; q < nq; q += kReplayThreads) {
+      const int k = ptr[q];
+      if (k == kNone) continue;
+      const int idx = k == kExt ? (int)ext[q] : (int)(lists[(size_t)q * kListCap + k] & 0xffff);
+      atomicMax(&s_match[idx], q);
+      if (s_best[q] >> 31) s_claimed[idx] = 1;
+    }
+    __syncthreads();     // `over` aliases ev_q: events are written only after the last round has finished with it
+    for (int q = tid; q < nq; q += kReplayThreads) {
+      const int k = ptr[q];
+      if (k == kNone) continue;
+      const int idx = k == kExt ? (int)ext[q] : (int)(lists[(size_t)q * kListCap + k] & 0xffff);
+      const int e = atomicAdd(&s_nev, 1);
+      ev_idx[e] = (uint16_t)idx; ev_q[e] = (uint16_t)q;
+    }
+    __syncthreads();
+    if (tid == 0) s_nmatch = s_nev;
+  }
+
+  if (sequential && warp == 0) {
     int q = 0, nev = 0;
     for (;;) {
       int stop = nq;
@@ -660,7 +763,8 @@ int d2h(T* dst, const T* src, size_t n, cudaStream_t st) {
 }
 size_t search_frame_smem(int last_stride, int stride) {
   // lists + best | match | ev_idx, ev_q, cnt | claimed | ev_bin
-  return (size_t)last_stride * (kListCap + 1) * 4 + (size_t)stride * 4 + (size_t)last_stride * 3 * 2 + stride + last_stride + 16;
+  return (size_t)last_stride * (kListCap + 1) * 4 + (size_t)stride * 4 + (size_t)last_stride * 3 * 2 + stride + last_stride +
+         last_stride + 4 + (size_t)stride * 4 + (size_t)last_stride * 2 + 16;   // + ptr | owner | ext
 }
 size_t search_points_smem(int point_stride, int stride) {
   return (size_t)point_stride * kListCapPts * 4 + (size_t)stride * 4 + (size_t)point_stride * 2 + stride + 16;

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -95,119 +96,141 @@ __global__ void __launch_bounds__(256) k_resize(OrbGeom g, int level, const shor
 }
 
 // -------------------------------------------------------------------------------------------------
-// FAST-9/16 arc score: max over the 16 arcs of 9 contiguous ring pixels of min(ring - c) and of
-// min(c - ring) (cv::FAST's cornerScore, Appendix A.3).  Returns 0 when the pixel cannot be a corner
-// above `tmin` (cheap compass rejection), else the exact value.
-__device__ __forceinline__ int fast_arc_max(const uint8_t* __restrict__ p, int tw, int tmin) {
-  const int c = p[0];
-  int d[16];
-  d[0] = (int)p[3 * tw] - c;
-  d[4] = (int)p[3] - c;
-  d[8] = (int)p[-3 * tw] - c;
-  d[12] = (int)p[-3] - c;
-  // a 9-arc contains at least one pixel of every opposing pair
-  const bool bright = (d[0] > tmin || d[8] > tmin) && (d[4] > tmin || d[12] > tmin);
-  const bool dark = (d[0] < -tmin || d[8] < -tmin) && (d[4] < -tmin || d[12] < -tmin);
-  if (!bright && !dark) return 0;
-  d[1] = (int)p[3 * tw + 1] - c;
-  d[2] = (int)p[2 * tw + 2] - c;
-  d[3] = (int)p[tw + 3] - c;
-  d[5] = (int)p[-tw + 3] - c;
-  d[6] = (int)p[-2 * tw + 2] - c;
-  d[7] = (int)p[-3 * tw + 1] - c;
-  d[9] = (int)p[-3 * tw - 1] - c;
-  d[10] = (int)p[-2 * tw - 2] - c;
-  d[11] = (int)p[-tw - 3] - c;
-  d[13] = (int)p[tw - 3] - c;
-  d[14] = (int)p[2 * tw - 2] - c;
-  d[15] = (int)p[3 * tw - 1] - c;
-  int lo2[16], hi2[16];
-#pragma unroll
-  for (int k = 0; k < 16; k++) {
-    lo2[k] = min(d[k], d[(k + 1) & 15]);
-    hi2[k] = max(d[k], d[(k + 1) & 15]);
-  }
-  int lo4[16], hi4[16];
-#pragma unroll
-  for (int k = 0; k < 16; k++) {
-    lo4[k] = min(lo2[k], lo2[(k + 2) & 15]);
-    hi4[k] = max(hi2[k], hi2[(k + 2) & 15]);
-  }
-  // brightest arc = max over arcs of the arc minimum; darkest arc = min over arcs of the arc maximum
-  int bright_best = -255, dark_best = 255;
-#pragma unroll
-  for (int k = 0; k < 16; k++) {
-    int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
-    int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
-    bright_best = max(bright_best, lo9);
-    dark_best = min(dark_best, hi9);
-  }
-  return max(0, max(bright_best, -dark_best));
+// FAST-9/16 (cv::FAST's cornerScore, Appendix A.3): m = max over the 16 arcs of 9 contiguous ring pixels of
+// min(ring - c) and of min(c - ring); corner iff m > t, score m - 1.
+//
+// Both polarities travel in one register as two unsigned 16-bit halves, low = 256 + (ring - c),
+// high = 256 - (ring - c), built by one multiply-add per ring pixel:  K - 65535*ring with
+// K = 0x01000100 + 65535*c  (the integer value (256-x)*65536 + (256+x) has exactly those base-65536 digits since
+// both are in [1,511]).  Arc minima are then packed VIMNMX.U16x2 / VIMNMX3.U16x2 chains — 56 min/max
+// instructions per pixel instead of ~160 scalar ones, and no negation (an earlier scalar version tripped a ptxas
+// VIMNMX3 negation fold).
+__device__ __forceinline__ unsigned fast_pack(const uint8_t* __restrict__ p, unsigned K) {
+  return K - 65535u * (unsigned)p[0];
 }
 
-// One CTA per (cell, frame): stage the (w_cell+6) x (h_cell+6) tile in shared memory, score the
-// detection area, 3x3 strict NMS with zero outside the cell, threshold fallback ini -> min decided per
-// cell after NMS (ORBextractor.cc:789-829), append survivors to the (frame, level) candidate list.
-__global__ void __launch_bounds__(kFastThreads) k_fast(OrbGeom g, const int4* __restrict__ cells,
-                                                      const uint8_t* __restrict__ pyr,
-                                                      uint32_t* __restrict__ cand,
-                                                      int* __restrict__ cand_count, int* __restrict__ overflow,
-                                                      uint8_t* __restrict__ dbg, int dbg_cell) {
+// Cheap necessary condition: a 9-arc contains two adjacent compass points (0,4,8,12), so both polarities need
+// (d0 | d8) & (d4 | d12) above t.  Returns true when the pixel may have m > t.
+__device__ __forceinline__ bool fast_compass(const uint8_t* __restrict__ p, int tw, int t) {
+  const unsigned K = 0x01000100u + 65535u * (unsigned)p[0];
+  const unsigned a = __vmaxu2(fast_pack(p + 3 * tw, K), fast_pack(p - 3 * tw, K));
+  const unsigned b = __vmaxu2(fast_pack(p + 3, K), fast_pack(p - 3, K));
+  const unsigned m = __vminu2(a, b);
+  return max(m & 0xffffu, m >> 16) > (unsigned)(256 + t);
+}
+
+__device__ __forceinline__ int fast_arc_max(const uint8_t* __restrict__ p, int tw) {
+  const unsigned K = 0x01000100u + 65535u * (unsigned)p[0];
+  unsigned v[16];
+  v[0] = fast_pack(p + 3 * tw, K);
+  v[1] = fast_pack(p + 3 * tw + 1, K);
+  v[2] = fast_pack(p + 2 * tw + 2, K);
+  v[3] = fast_pack(p + tw + 3, K);
+  v[4] = fast_pack(p + 3, K);
+  v[5] = fast_pack(p - tw + 3, K);
+  v[6] = fast_pack(p - 2 * tw + 2, K);
+  v[7] = fast_pack(p - 3 * tw + 1, K);
+  v[8] = fast_pack(p - 3 * tw, K);
+  v[9] = fast_pack(p - 3 * tw - 1, K);
+  v[10] = fast_pack(p - 2 * tw - 2, K);
+  v[11] = fast_pack(p - tw - 3, K);
+  v[12] = fast_pack(p - 3, K);
+  v[13] = fast_pack(p + tw - 3, K);
+  v[14] = fast_pack(p + 2 * tw - 2, K);
+  v[15] = fast_pack(p + 3 * tw - 1, K);
+  unsigned lo2[16], lo4[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) lo2[k] = __vminu2(v[k], v[(k + 1) & 15]);
+#pragma unroll
+  for (int k = 0; k < 16; k++) lo4[k] = __vminu2(lo2[k], lo2[(k + 2) & 15]);
+  unsigned best = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    unsigned a = __vimin3_u16x2(lo4[k], lo4[(k + 4) & 15], v[(k + 8) & 15]);
+    unsigned b = __vimin3_u16x2(lo4[k + 1], lo4[(k + 5) & 15], v[(k + 9) & 15]);
+    best = __vimax3_u16x2(best, a, b);
+  }
+  return max((int)max(best & 0xffffu, best >> 16) - 256, 0);
+}
+
+// One CTA per (cell, frame): stage the (w_cell+6) x (h_cell+6) tile in shared memory; then per threshold
+// (iniThFAST, and minThFAST only when the cell came out empty — ORBextractor.cc:808-816):
+//   A  compass test over the detection area, survivors compacted into a pixel list (warp ballot);
+//   B  exact packed arc score over the list (dense: no lane idles on a rejected pixel), scores > t into the map;
+//   C  3x3 strict NMS over the list with zero outside the cell, survivors appended to the (frame, level) list.
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) k_fast(OrbGeom g, const int4* __restrict__ cells,
+                                                  const uint8_t* __restrict__ pyr, uint32_t* __restrict__ cand,
+                                                  int* __restrict__ cand_count, int* __restrict__ overflow,
+                                                  uint8_t* __restrict__ dbg, int dbg_cell) {
   __shared__ __align__(16) uint8_t tile[kTileH * kTileW];
   __shared__ __align__(16) uint8_t score[kTileH * kTileW];
+  __shared__ uint16_t s_px[(kTileH - 6) * (kTileW - 4 - 6)];
   __shared__ uint32_t s_list[kCellListCap];
-  __shared__ int s_n, s_base;
+  __shared__ int s_n, s_base, s_npx;
 
   const int4 ce = __ldg(cells + blockIdx.x);
   const int level = ce.x & 0xff, ci = (ce.x >> 8) & 0xfff, cj = (ce.x >> 20) & 0xfff;
   const int x0 = ce.y & 0xffff, y0 = ce.y >> 16, cw = ce.z & 0xffff, ch = ce.z >> 16;
   const LevelGeom& L = g.lv[level];
-  const int f = blockIdx.y, tid = threadIdx.x;
+  const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const uint8_t* plane = pyr + (long long)f * g.frame_bytes + L.plane_off;
   const long long org = (long long)(y0 + kBorder) * L.pitch + kXOff + x0;
   const int shift = (int)(org & 3);
   const int words = (shift + cw + 3) >> 2;
+  const unsigned wmagic = ((1u << 20) + words - 1) / words;      // i / words == (i * wmagic) >> 20 for i < 2^13
 
-  for (int i = tid; i < ch * words; i += kFastThreads) {
-    int r = i / words, w = i - r * words;
+  for (int i = tid; i < ch * words; i += kThreads) {
+    int r = (int)(((unsigned)i * wmagic) >> 20), w = i - r * words;
     uint32_t v = __ldg((const uint32_t*)(plane + org - shift + (long long)r * L.pitch) + w);
     *(uint32_t*)(tile + r * kTileW + 4 * w) = v;
   }
-  for (int i = tid; i < (kTileH * kTileW) / 4; i += kFastThreads) ((uint32_t*)score)[i] = 0;
-  if (tid == 0) s_n = 0;
+  for (int i = tid; i < ch * (kTileW / 4); i += kThreads) ((uint32_t*)score)[i] = 0;
+  if (tid == 0) { s_n = 0; s_npx = 0; }
   __syncthreads();
 
   const int dw = cw - 6, dh = ch - 6;   // detection area
   const int npx = dw > 0 && dh > 0 ? dw * dh : 0;
-  for (int i = tid; i < npx; i += kFastThreads) {
-    int y = i / dw, x = i - y * dw;
-    int m = fast_arc_max(tile + (y + 3) * kTileW + shift + x + 3, kTileW, g.min_th);
-    score[(y + 3) * kTileW + x + 3] = (uint8_t)(m > g.min_th ? m : 0);
-  }
-  __syncthreads();
-
-  if (dbg && (int)blockIdx.x == dbg_cell && f == 0) {   // verification tap
-    for (int i = tid; i < kTileH * kTileW; i += kFastThreads) { dbg[i] = tile[i]; dbg[kTileH * kTileW + i] = score[i]; }
-    if (tid == 0) { int* q = (int*)(dbg + 2 * kTileH * kTileW); q[0] = x0; q[1] = y0; q[2] = cw; q[3] = ch; q[4] = shift; q[5] = level; q[6] = g.ini_th; q[7] = g.min_th; }
-  }
+  const unsigned dmagic = dw > 0 ? ((1u << 20) + dw - 1) / dw : 0;   // exact for i < 4620, dw <= 70
   int th = g.ini_th;
   for (int pass = 0; pass < 2; pass++) {
+    // A: compass test, compaction
+    for (int base = 0; base < npx; base += kThreads) {
+      const int i = base + tid;
+      bool ok = false;
+      int y = 0, x = 0;
+      if (i < npx) {
+        y = (int)(((unsigned)i * dmagic) >> 20);
+        x = i - y * dw;
+        ok = fast_compass(tile + (y + 3) * kTileW + shift + x + 3, kTileW, th);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (bal) {
+        int off = 0;
+        if (lane == 0) off = atomicAdd(&s_npx, __popc(bal));
+        off = __shfl_sync(0xffffffffu, off, 0);
+        if (ok) s_px[off + __popc(bal & ((1u << lane) - 1))] = (uint16_t)((y << 8) | x);
+      }
+    }
+    __syncthreads();
+    const int nl = s_npx;
+    // B: exact scores of the survivors
+    for (int j = tid; j < nl; j += kThreads) {
+      const int q = s_px[j], y = q >> 8, x = q & 0xff;
+      const int m = fast_arc_max(tile + (y + 3) * kTileW + shift + x + 3, kTileW);
+      if (m > th) score[(y + 3) * kTileW + x + 3] = (uint8_t)m;
+    }
+    __syncthreads();
+    // C: strict 3x3 non-max suppression (scores <= th are 0 in the map)
     int kept = 0;
-    for (int i = tid; i < npx; i += kFastThreads) {
-      int y = i / dw, x = i - y * dw;
+    for (int j = tid; j < nl; j += kThreads) {
+      const int q = s_px[j], y = q >> 8, x = q & 0xff;
       const uint8_t* s = score + (y + 3) * kTileW + x + 3;
-      int m = s[0];
+      const int m = s[0];
       if (m <= th) continue;
-      bool keep = true;
-#pragma unroll
-      for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-        for (int dx = -1; dx <= 1; dx++) {
-          if (dx == 0 && dy == 0) continue;
-          int n = s[dy * kTileW + dx];
-          keep = keep && (n <= th || n < m);
-        }
-      if (keep) {
+      const int n = max(max(max((int)s[-kTileW - 1], (int)s[-kTileW]), max((int)s[-kTileW + 1], (int)s[-1])),
+                        max(max((int)s[1], (int)s[kTileW - 1]), max((int)s[kTileW], (int)s[kTileW + 1])));
+      if (n < m) {
         int slot = atomicAdd(&s_n, 1);
         // reference coordinates: cell-local + (j*wCell, i*hCell), relative to minBorder (:820-825)
         if (slot < kCellListCap)
@@ -218,6 +241,12 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(OrbGeom g, const int4* __
     }
     if (__syncthreads_count(kept) > 0 || th == g.min_th) break;
     th = g.min_th;
+    if (tid == 0) s_npx = 0;
+    __syncthreads();
+  }
+  if (dbg && (int)blockIdx.x == dbg_cell && f == 0) {   // verification tap
+    for (int i = tid; i < kTileH * kTileW; i += kThreads) { dbg[i] = tile[i]; dbg[kTileH * kTileW + i] = score[i]; }
+    if (tid == 0) { int* q = (int*)(dbg + 2 * kTileH * kTileW); q[0] = x0; q[1] = y0; q[2] = cw; q[3] = ch; q[4] = shift; q[5] = level; q[6] = g.ini_th; q[7] = g.min_th; }
   }
   const int n = s_n;
   if (n == 0) return;
@@ -229,7 +258,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(OrbGeom g, const int4* __
     if (tid == 0) atomicExch(overflow, 1);
     return;
   }
-  for (int i = tid; i < n; i += kFastThreads) out[base + i] = s_list[i];
+  for (int i = tid; i < n; i += kThreads) out[base + i] = s_list[i];
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -508,17 +537,22 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(OrbGeom g, const uint32_
 // -------------------------------------------------------------------------------------------------
 // cv::GaussianBlur 7x7 sigma 2 (Appendix A.2) of every level's interior; reads the reflect-101 border
 // that the pyramid planes already carry (equivalent to blurring the un-bordered clone, :1085-1086).
+// Q8 kernel [18,34,48,56,48,34,18]: the row pass is two DP4A per pixel (byte windows cut out of three words with
+// funnel shifts); its 16-bit sums are stored as (row 2p, row 2p+1) pairs so the column pass is four DP2A per
+// pixel, and one thread produces a 4-column x 2-row block from the same four pair loads.
 __global__ void __launch_bounds__(256) k_blur(OrbGeom g, const int2* __restrict__ tiles,
                                               const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
+  constexpr int kPairs = (kBlurTH + 6) / 2;                          // 19 row pairs = tile rows y0-3 .. y0+TH+2
+  static_assert(kBlurTH % 2 == 0 && kBlurTW % 4 == 0, "tile shape");
   __shared__ __align__(16) uint8_t in[(kBlurTH + 6) * kBlurInPitch];
-  __shared__ __align__(16) uint16_t hs[(kBlurTH + 6) * kBlurTW];
+  __shared__ __align__(16) uint32_t hp[kPairs * kBlurTW];            // (h[2p][x] | h[2p+1][x] << 16)
   const int2 te = __ldg(tiles + blockIdx.x);
   const int level = te.x & 0xff, x0 = (te.x >> 8) * kBlurTW, y0 = te.y * kBlurTH;
   const LevelGeom& L = g.lv[level];
   const int f = blockIdx.y, tid = threadIdx.x;
   const uint8_t* plane = pyr + (long long)f * g.frame_bytes + L.plane_off;
   // input rows y0-3 .. y0+TH+2, columns x0-4 .. x0+TW+3 (word aligned: kXOff + x0 - 4 is a multiple of 4)
-  const int in_words = kBlurInPitch / 4;
+  constexpr int in_words = kBlurInPitch / 4;
   for (int i = tid; i < (kBlurTH + 6) * in_words; i += 256) {
     int r = i / in_words, w = i - r * in_words;
     int row = y0 - 3 + r + kBorder, col = kXOff + x0 - 4 + 4 * w;
@@ -527,27 +561,47 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, const int2* __restrict_
     *(uint32_t*)(in + r * kBlurInPitch + 4 * w) = v;
   }
   __syncthreads();
-  for (int i = tid; i < (kBlurTH + 6) * kBlurTW; i += 256) {
-    int r = i / kBlurTW, x = i - r * kBlurTW;
-    const uint8_t* s = in + r * kBlurInPitch + x + 1;   // s[0] is pixel x-3
-    hs[i] = (uint16_t)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
+  constexpr unsigned kWA = 0x38302212u, kWB = 0x00122230u;           // taps 0..3 and 4..6 (+ a zero)
+  for (int i = tid; i < kPairs * (kBlurTW / 4); i += 256) {
+    const int p = i / (kBlurTW / 4), x4 = (i - p * (kBlurTW / 4)) * 4;
+    uint32_t h[2][4];
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+      const uint32_t* s = (const uint32_t*)(in + (2 * p + rr) * kBlurInPitch + x4);   // s[0] byte 1 is pixel x4-3
+      const uint32_t w0 = s[0], w1 = s[1], w2 = s[2];
+      h[rr][0] = __dp4a(__funnelshift_r(w0, w1, 8), kWA, __dp4a(__funnelshift_r(w1, w2, 8), kWB, 0u));
+      h[rr][1] = __dp4a(__funnelshift_r(w0, w1, 16), kWA, __dp4a(__funnelshift_r(w1, w2, 16), kWB, 0u));
+      h[rr][2] = __dp4a(__funnelshift_r(w0, w1, 24), kWA, __dp4a(__funnelshift_r(w1, w2, 24), kWB, 0u));
+      h[rr][3] = __dp4a(w1, kWA, __dp4a(w2, kWB, 0u));
+    }
+    *(uint4*)(hp + p * kBlurTW + x4) = make_uint4(h[0][0] | (h[1][0] << 16), h[0][1] | (h[1][1] << 16),
+                                                  h[0][2] | (h[1][2] << 16), h[0][3] | (h[1][3] << 16));
   }
   __syncthreads();
   uint8_t* dst = blur + (long long)f * g.frame_bytes + L.plane_off;
-  for (int i = tid; i < kBlurTH * (kBlurTW / 4); i += 256) {
-    int r = i / (kBlurTW / 4), x4 = (i - r * (kBlurTW / 4)) * 4;
-    int y = y0 + r, x = x0 + x4;
+  // output rows r = 2j (taps = tile rows r..r+6) and r+1 (taps r+1..r+7) read the same pairs j..j+3
+  constexpr unsigned kE01 = 0x2212u, kE23 = 0x3830u, kE45 = 0x2230u, kE67 = 0x0012u;    // even row: 18,34 | 48,56 | 48,34 | 18,0
+  constexpr unsigned kO01 = 0x1200u, kO23 = 0x3022u, kO45 = 0x3038u, kO67 = 0x1222u;    // odd row:  0,18 | 34,48 | 56,48 | 34,18
+  for (int i = tid; i < (kBlurTH / 2) * (kBlurTW / 4); i += 256) {
+    const int j = i / (kBlurTW / 4), x4 = (i - j * (kBlurTW / 4)) * 4;
+    const int y = y0 + 2 * j, x = x0 + x4;
     if (y >= L.h || x >= L.w) continue;
-    uint32_t word = 0;
+    const uint4 a = *(const uint4*)(hp + j * kBlurTW + x4), b = *(const uint4*)(hp + (j + 1) * kBlurTW + x4);
+    const uint4 c = *(const uint4*)(hp + (j + 2) * kBlurTW + x4), d = *(const uint4*)(hp + (j + 3) * kBlurTW + x4);
+    const uint32_t pa[4] = {a.x, a.y, a.z, a.w}, pb[4] = {b.x, b.y, b.z, b.w}, pc[4] = {c.x, c.y, c.z, c.w},
+                   pd[4] = {d.x, d.y, d.z, d.w};
+    uint32_t even = 0, odd = 0;
 #pragma unroll
-    for (int b = 0; b < 4; b++) {
-      const uint16_t* h = hs + r * kBlurTW + x4 + b;
-      uint32_t acc = 18u * (h[0] + h[6 * kBlurTW]) + 34u * (h[kBlurTW] + h[5 * kBlurTW]) +
-                     48u * (h[2 * kBlurTW] + h[4 * kBlurTW]) + 56u * h[3 * kBlurTW];
-      word |= ((acc + 32768u) >> 16) << (8 * b);
+    for (int k = 0; k < 4; k++) {
+      const uint32_t e = __dp2a_lo(pa[k], kE01, __dp2a_lo(pb[k], kE23, __dp2a_lo(pc[k], kE45, __dp2a_lo(pd[k], kE67, 32768u))));
+      const uint32_t o = __dp2a_lo(pa[k], kO01, __dp2a_lo(pb[k], kO23, __dp2a_lo(pc[k], kO45, __dp2a_lo(pd[k], kO67, 32768u))));
+      even |= (e >> 16) << (8 * k);
+      odd |= (o >> 16) << (8 * k);
     }
     // bytes past the interior width land in the border columns of the blurred plane, which nothing reads
-    *(uint32_t*)(dst + (long long)(y + kBorder) * L.pitch + kXOff + x) = word;
+    uint8_t* o0 = dst + (long long)(y + kBorder) * L.pitch + kXOff + x;
+    *(uint32_t*)o0 = even;
+    if (y + 1 < L.h) *(uint32_t*)(o0 + L.pitch) = odd;
   }
 }
 
@@ -666,6 +720,7 @@ struct cmos_orb {
   uint32_t *d_cand = nullptr, *d_stage = nullptr;
   uint16_t* d_pnode = nullptr;
   int *d_cand_count = nullptr, *d_level_counts = nullptr, *d_counts = nullptr, *d_overflow = nullptr;
+  int* h_overflow = nullptr;    // pinned landing slot of d_overflow
   cmos_keypoint* d_kps = nullptr;
   int4* d_cells = nullptr;
   int2* d_tiles = nullptr;
@@ -676,6 +731,7 @@ struct cmos_orb {
   std::vector<int> xtab_off, ytab_off;
   size_t images_cap = 0;
   int last_frames = 0, launches = 0;
+  int fast_threads = 128;   // CMOS_FAST_THREADS=256 selects the wider CTA (tuning knob)
   bool has_result = false;
   StageTimer timer;
 };
@@ -843,8 +899,12 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
   }
   h->timer.mark(st);   // stage 0: pyramid
   if (h->n_cells > 0) {
-    k_fast<<<dim3(h->n_cells, n_frames), kFastThreads, 0, st>>>(g, h->d_cells, h->d_pyr, h->d_cand, h->d_cand_count,
-                                                              h->d_overflow, h->d_dbg, h->dbg_cell);
+    if (h->fast_threads == 128)
+      k_fast<128><<<dim3(h->n_cells, n_frames), 128, 0, st>>>(g, h->d_cells, h->d_pyr, h->d_cand, h->d_cand_count,
+                                                            h->d_overflow, h->d_dbg, h->dbg_cell);
+    else
+      k_fast<256><<<dim3(h->n_cells, n_frames), 256, 0, st>>>(g, h->d_cells, h->d_pyr, h->d_cand, h->d_cand_count,
+                                                            h->d_overflow, h->d_dbg, h->dbg_cell);
     launches++;
   }
   h->timer.mark(st);   // stage 1: FAST
@@ -887,6 +947,7 @@ int cmos_orb_create(const cmos_orb_params* params, cmos_orb_t* out) {
   cmos_orb* h = new cmos_orb();
   h->p = *params;
   h->device = params->device;
+  if (const char* e = std::getenv("CMOS_FAST_THREADS")) h->fast_threads = std::atoi(e) == 256 ? 256 : 128;
   // tables of the constructor, ORBextractor.cc:410-470 (scaleFactor member is double, ORBextractor.h:95)
   const int nl = params->nlevels;
   const double scale_d = (double)params->scale_factor;
@@ -973,6 +1034,7 @@ int cmos_orb_destroy(cmos_orb_t h) {
                   h->d_tab, h->d_pattern};
   for (void* b : bufs)
     if (b) cudaFree(b);
+  if (h->h_overflow) cudaFreeHost(h->h_overflow);
   if (h->stream) cudaStreamDestroy(h->stream);
   h->timer.destroy();
   delete h;
@@ -1038,6 +1100,44 @@ int cmos_orb_extract_device(cmos_orb_t h, const uint8_t* d_images, int64_t frame
   return enqueue_extract(h, d_images, frame_stride, pitch, n_frames, stream ? (cudaStream_t)stream : h->stream);
 }
 
+namespace {
+// D2H of the last extraction's results, enqueued on st (no synchronisation).
+int enqueue_download(cmos_orb* h, int n_frames, cmos_keypoint* keypoints, uint8_t* descriptors, int* counts,
+                     int capacity, cudaStream_t st) {
+  if (!h->h_overflow) CMOS_CUDA_OK(cudaHostAlloc((void**)&h->h_overflow, sizeof(int), cudaHostAllocDefault));
+  CMOS_CUDA_OK(cudaMemcpyAsync(counts, h->d_counts, n_frames * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CMOS_CUDA_OK(cudaMemcpyAsync(h->h_overflow, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+  const size_t krow = (size_t)h->kp_cap * sizeof(cmos_keypoint), drow = (size_t)h->kp_cap * 32;
+  if (keypoints) {
+    if (capacity == h->kp_cap)
+      CMOS_CUDA_OK(cudaMemcpyAsync(keypoints, h->d_kps, krow * n_frames, cudaMemcpyDeviceToHost, st));
+    else
+      CMOS_CUDA_OK(cudaMemcpy2DAsync(keypoints, (size_t)capacity * sizeof(cmos_keypoint), h->d_kps, krow, krow, n_frames,
+                                     cudaMemcpyDeviceToHost, st));
+  }
+  if (descriptors) {
+    if (capacity == h->kp_cap)
+      CMOS_CUDA_OK(cudaMemcpyAsync(descriptors, h->d_desc, drow * n_frames, cudaMemcpyDeviceToHost, st));
+    else
+      CMOS_CUDA_OK(cudaMemcpy2DAsync(descriptors, (size_t)capacity * 32, h->d_desc, drow, drow, n_frames,
+                                     cudaMemcpyDeviceToHost, st));
+  }
+  return CMOS_OK;
+}
+}  // namespace
+
+int cmos_orb_finish(cmos_orb_t h, void* stream) {
+  CMOS_REQUIRE(h, "null handle");
+  CMOS_CUDA_OK(cudaSetDevice(h->device));
+  CMOS_CUDA_OK(cudaStreamSynchronize(stream ? (cudaStream_t)stream : h->stream));
+  if (h->h_overflow && *h->h_overflow) {
+    *h->h_overflow = 0;
+    set_error("FAST candidate buffer overflow");
+    return CMOS_ERR_CAPACITY;
+  }
+  return CMOS_OK;
+}
+
 int cmos_orb_download(cmos_orb_t h, int32_t n_frames, cmos_keypoint* keypoints, uint8_t* descriptors,
                       int32_t* counts, int32_t capacity, void* stream) {
   CMOS_REQUIRE(h && counts, "null argument");
@@ -1046,22 +1146,35 @@ int cmos_orb_download(cmos_orb_t h, int32_t n_frames, cmos_keypoint* keypoints, 
   CMOS_REQUIRE(capacity >= h->kp_cap, "capacity %d < cmos_orb_keypoint_capacity %d", capacity, h->kp_cap);
   CMOS_CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-  int overflow = 0;
-  CMOS_CUDA_OK(cudaMemcpyAsync(counts, h->d_counts, n_frames * sizeof(int), cudaMemcpyDeviceToHost, st));
-  CMOS_CUDA_OK(cudaMemcpyAsync(&overflow, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (keypoints)
-    CMOS_CUDA_OK(cudaMemcpy2DAsync(keypoints, (size_t)capacity * sizeof(cmos_keypoint), h->d_kps,
-                                   (size_t)h->kp_cap * sizeof(cmos_keypoint), (size_t)h->kp_cap * sizeof(cmos_keypoint),
-                                   n_frames, cudaMemcpyDeviceToHost, st));
-  if (descriptors)
-    CMOS_CUDA_OK(cudaMemcpy2DAsync(descriptors, (size_t)capacity * 32, h->d_desc, (size_t)h->kp_cap * 32,
-                                   (size_t)h->kp_cap * 32, n_frames, cudaMemcpyDeviceToHost, st));
-  CMOS_CUDA_OK(cudaStreamSynchronize(st));
-  if (overflow) {
-    set_error("FAST candidate buffer overflow");
-    return CMOS_ERR_CAPACITY;
+  int rc = enqueue_download(h, n_frames, keypoints, descriptors, counts, capacity, st);
+  if (rc) return rc;
+  return cmos_orb_finish(h, st);
+}
+
+int cmos_orb_extract_async(cmos_orb_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
+                           int32_t height, int32_t n_frames, cmos_keypoint* keypoints, uint8_t* descriptors,
+                           int32_t* counts, int32_t capacity, void* stream) {
+  CMOS_REQUIRE(h && counts && images, "null argument");
+  CMOS_REQUIRE(n_frames >= 1 && n_frames <= h->p.max_batch, "n_frames %d outside 1..%d", n_frames, h->p.max_batch);
+  CMOS_REQUIRE(width > 0 && height > 0 && width <= h->p.max_width && height <= h->p.max_height && pitch >= width,
+               "bad image size %dx%d pitch %d", width, height, pitch);
+  CMOS_REQUIRE(capacity >= h->kp_cap, "capacity %d < cmos_orb_keypoint_capacity %d", capacity, h->kp_cap);
+  CMOS_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const int64_t frame_bytes = (int64_t)width * height;
+  if (pitch == width && (n_frames == 1 || frame_stride == frame_bytes)) {
+    CMOS_CUDA_OK(cudaMemcpyAsync(h->d_images, images, (size_t)frame_bytes * n_frames, cudaMemcpyHostToDevice, st));
+  } else if (n_frames == 1 || frame_stride == (int64_t)pitch * height) {
+    CMOS_CUDA_OK(cudaMemcpy2DAsync(h->d_images, width, images, pitch, width, (size_t)height * n_frames,
+                                   cudaMemcpyHostToDevice, st));
+  } else {
+    for (int f = 0; f < n_frames; f++)
+      CMOS_CUDA_OK(cudaMemcpy2DAsync(h->d_images + (size_t)f * frame_bytes, width, images + f * frame_stride, pitch,
+                                     width, (size_t)height, cudaMemcpyHostToDevice, st));
   }
-  return CMOS_OK;
+  int rc = cmos_orb_extract_device(h, h->d_images, frame_bytes, width, width, height, n_frames, st);
+  if (rc) return rc;
+  return enqueue_download(h, n_frames, keypoints, descriptors, counts, capacity, st);
 }
 
 int cmos_orb_extract(cmos_orb_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
@@ -1073,18 +1186,10 @@ int cmos_orb_extract(cmos_orb_t h, const uint8_t* images, int64_t frame_stride, 
     for (int f = 0; f < n_frames; f++) counts[f] = 0;
     return CMOS_OK;
   }
-  CMOS_REQUIRE(width > 0 && height > 0 && width <= h->p.max_width && height <= h->p.max_height && pitch >= width,
-               "bad image size %dx%d pitch %d", width, height, pitch);
-  CMOS_REQUIRE(capacity >= h->kp_cap, "capacity %d < cmos_orb_keypoint_capacity %d", capacity, h->kp_cap);
-  CMOS_CUDA_OK(cudaSetDevice(h->device));
-  CMOS_CUDA_OK(cudaMemcpy2DAsync(h->d_images, width, images, pitch, width, (size_t)height, cudaMemcpyHostToDevice,
-                                 h->stream));
-  for (int f = 1; f < n_frames; f++)
-    CMOS_CUDA_OK(cudaMemcpy2DAsync(h->d_images + (size_t)f * width * height, width, images + f * frame_stride, pitch,
-                                   width, (size_t)height, cudaMemcpyHostToDevice, h->stream));
-  int rc = cmos_orb_extract_device(h, h->d_images, (int64_t)width * height, width, width, height, n_frames, h->stream);
+  int rc = cmos_orb_extract_async(h, images, frame_stride, pitch, width, height, n_frames, keypoints, descriptors, counts,
+                                  capacity, h->stream);
   if (rc) return rc;
-  return cmos_orb_download(h, n_frames, keypoints, descriptors, counts, capacity, h->stream);
+  return cmos_orb_finish(h, h->stream);
 }
 
 int cmos_orb_device_results(cmos_orb_t h, cmos_keypoint** d_keypoints, uint8_t** d_descriptors, int32_t** d_counts,

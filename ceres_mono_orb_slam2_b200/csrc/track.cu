@@ -1,0 +1,158 @@
+// Tracking front-end: Frame construction + the motion-model search, pipelined over CUDA streams.
+//
+// What the reference does per frame on the Tracking thread (GrabImageMonocular -> Frame::Frame, src/Frame.cc:98-156:
+// ExtractORB :116 -> ORBextractor::operator() :175-177, AssignFeaturesToGrid :155; then TrackWithMotionModel ->
+// ORBmatcher::SearchByProjection(current_frame_, last_frame_, th), src/Tracking.cc:632, src/ORBmatcher.cc:1161-1271) is one call here for a
+// batch of frames with HOST buffers.  The batch is cut into chunks; chunk c runs on lane c % lanes (one stream,
+// one extractor handle, one matcher handle per lane), so the host->device copy of chunk c+1, the kernels of chunk c
+// and the device->host copy of chunk c-1 overlap.  Only public entry points of the same C ABI are used.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+#include "cmos_common.h"
+
+using namespace cmos;
+
+namespace {
+struct Lane {
+  cudaStream_t st = nullptr;
+  cmos_orb_t orb = nullptr;
+  cmos_match_t match = nullptr;
+  double *d_T = nullptr, *d_xw = nullptr;
+  cmos_keypoint* d_last_kps = nullptr;
+  int *d_last_counts = nullptr, *d_match = nullptr, *d_nm = nullptr;
+  uint8_t *d_flags = nullptr, *d_last_desc = nullptr;
+};
+}  // namespace
+
+struct cmos_track {
+  cmos_track_params p{};
+  cmos_camera cam{};
+  int kp_cap = 0;
+  std::vector<Lane> lanes;
+  int launches = 0;
+};
+
+extern "C" {
+
+int cmos_track_destroy(cmos_track_t h) {
+  if (!h) return CMOS_OK;
+  cudaSetDevice(h->p.orb.device);
+  for (Lane& L : h->lanes) {
+    if (L.orb) cmos_orb_destroy(L.orb);
+    if (L.match) cmos_match_destroy(L.match);
+    void* bufs[] = {L.d_T, L.d_xw, L.d_last_kps, L.d_last_counts, L.d_match, L.d_nm, L.d_flags, L.d_last_desc};
+    for (void* b : bufs)
+      if (b) cudaFree(b);
+    if (L.st) cudaStreamDestroy(L.st);
+  }
+  delete h;
+  return CMOS_OK;
+}
+
+int cmos_track_create(const cmos_track_params* params, const cmos_camera* cam, cmos_track_t* out) {
+  CMOS_REQUIRE(params && cam && out, "null argument");
+  CMOS_REQUIRE(params->lanes >= 1 && params->lanes <= 16 && params->chunk_frames >= 1, "lanes must be 1..16, chunk_frames >= 1");
+  cmos_track* h = new cmos_track();
+  h->p = *params;
+  h->cam = *cam;
+  h->lanes.resize(params->lanes);
+  cmos_orb_params op = params->orb;
+  op.max_batch = params->chunk_frames;
+  int rc = CMOS_OK;
+  for (Lane& L : h->lanes) {
+    if ((rc = cmos_orb_create(&op, &L.orb))) break;
+    if ((rc = cmos_orb_keypoint_capacity(L.orb, &h->kp_cap))) break;
+    cmos_match_params mp{params->chunk_frames, h->kp_cap, 1, op.device};
+    if ((rc = cmos_match_create(&mp, &L.match))) break;
+    if (cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking) != cudaSuccess) { rc = CMOS_ERR_CUDA; break; }
+    cudaError_t err = cudaSuccess;
+    const size_t n = (size_t)params->chunk_frames * h->kp_cap;
+    L.d_T = dev_alloc<double>((size_t)params->chunk_frames * 16, &err);
+    L.d_xw = dev_alloc<double>(n * 3, &err);
+    L.d_last_kps = dev_alloc<cmos_keypoint>(n, &err);
+    L.d_last_counts = dev_alloc<int>(params->chunk_frames, &err);
+    L.d_match = dev_alloc<int>(n, &err);
+    L.d_nm = dev_alloc<int>(params->chunk_frames, &err);
+    L.d_flags = dev_alloc<uint8_t>(n, &err);
+    L.d_last_desc = dev_alloc<uint8_t>(n * 32, &err);
+    if (err != cudaSuccess) { set_error("device allocation failed: %s", cudaGetErrorString(err)); rc = CMOS_ERR_CUDA; break; }
+  }
+  if (rc) { cmos_track_destroy(h); return rc; }
+  *out = h;
+  return CMOS_OK;
+}
+
+int cmos_track_keypoint_capacity(cmos_track_t h, int32_t* cap) {
+  CMOS_REQUIRE(h && cap, "null argument");
+  *cap = h->kp_cap;
+  return CMOS_OK;
+}
+
+int cmos_track_frames(cmos_track_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
+                      int32_t height, int32_t n_frames, const double* Tcw, const cmos_keypoint* last_keypoints,
+                      const int32_t* last_counts, const uint8_t* last_flags, const double* last_xw,
+                      const uint8_t* last_descriptors, int32_t last_stride, float th, int32_t check_orientation,
+                      cmos_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int32_t capacity, int32_t* match,
+                      int32_t* nmatches) {
+  CMOS_REQUIRE(h && images && Tcw && last_keypoints && last_counts && last_flags && last_xw && last_descriptors &&
+               keypoints && descriptors && counts && match && nmatches, "null argument");
+  CMOS_REQUIRE(n_frames >= 1, "n_frames must be positive");
+  CMOS_REQUIRE(capacity >= h->kp_cap, "capacity %d < cmos_track_keypoint_capacity %d", capacity, h->kp_cap);
+  CMOS_REQUIRE(last_stride >= 1 && last_stride <= h->kp_cap, "last_stride %d outside 1..%d", last_stride, h->kp_cap);
+  CMOS_CUDA_OK(cudaSetDevice(h->p.orb.device));
+  const int cf = h->p.chunk_frames, nl = (int)h->lanes.size();
+  int launches = 0, rc = CMOS_OK;
+  for (int f0 = 0, c = 0; f0 < n_frames && !rc; f0 += cf, c++) {
+    Lane& L = h->lanes[c % nl];
+    const int n = std::min(cf, n_frames - f0);
+    const size_t nq = (size_t)n * last_stride, o = (size_t)f0 * last_stride;
+    CMOS_CUDA_OK(cudaMemcpyAsync(L.d_T, Tcw + (size_t)f0 * 16, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, L.st));
+    CMOS_CUDA_OK(cudaMemcpyAsync(L.d_last_kps, last_keypoints + o, nq * sizeof(cmos_keypoint), cudaMemcpyHostToDevice, L.st));
+    CMOS_CUDA_OK(cudaMemcpyAsync(L.d_last_counts, last_counts + f0, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, L.st));
+    CMOS_CUDA_OK(cudaMemcpyAsync(L.d_flags, last_flags + o, nq, cudaMemcpyHostToDevice, L.st));
+    CMOS_CUDA_OK(cudaMemcpyAsync(L.d_xw, last_xw + o * 3, nq * 3 * sizeof(double), cudaMemcpyHostToDevice, L.st));
+    CMOS_CUDA_OK(cudaMemcpyAsync(L.d_last_desc, last_descriptors + o * 32, nq * 32, cudaMemcpyHostToDevice, L.st));
+    if ((rc = cmos_orb_extract_async(L.orb, images + (size_t)f0 * frame_stride, frame_stride, pitch, width, height, n,
+                                     keypoints + (size_t)f0 * capacity, descriptors + (size_t)f0 * capacity * 32,
+                                     counts + f0, capacity, L.st))) break;
+    cmos_keypoint* d_kps; uint8_t* d_desc; int32_t* d_counts;
+    if ((rc = cmos_orb_device_results(L.orb, &d_kps, &d_desc, &d_counts, nullptr, nullptr))) break;
+    if ((rc = cmos_match_set_frames(L.match, &h->cam, d_kps, d_desc, d_counts, n, h->kp_cap, 1, L.st))) break;
+    if ((rc = cmos_match_search_by_projection_frame(L.match, L.d_T, L.d_last_kps, L.d_last_counts, L.d_flags, L.d_xw,
+                                                    L.d_last_desc, last_stride, th, check_orientation, nullptr, L.d_match,
+                                                    L.d_nm, 1, L.st))) break;
+    const size_t row = (size_t)h->kp_cap * sizeof(int);
+    if (capacity == h->kp_cap)
+      CMOS_CUDA_OK(cudaMemcpyAsync(match + (size_t)f0 * capacity, L.d_match, row * n, cudaMemcpyDeviceToHost, L.st));
+    else
+      CMOS_CUDA_OK(cudaMemcpy2DAsync(match + (size_t)f0 * capacity, (size_t)capacity * sizeof(int), L.d_match, row, row, n,
+                                     cudaMemcpyDeviceToHost, L.st));
+    CMOS_CUDA_OK(cudaMemcpyAsync(nmatches + f0, L.d_nm, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, L.st));
+    int a = 0, b = 0;
+    cmos_orb_last_launch_count(L.orb, &a);
+    cmos_match_last_launch_count(L.match, &b);
+    launches += a + 1 + b;   // + the grid kernel of set_frames
+  }
+  // drain every lane even after an error, so no copy into caller memory is still in flight on return
+  for (Lane& L : h->lanes) {
+    int r2 = cmos_orb_finish(L.orb, L.st);
+    if (!rc) rc = r2;
+  }
+  if (capacity > h->kp_cap)   // rows are kp_cap wide on the device: pad the tail like the unfused call does
+    for (int f = 0; f < n_frames; f++)
+      for (int i = h->kp_cap; i < capacity; i++) match[(size_t)f * capacity + i] = -1;
+  h->launches = launches;
+  return rc;
+}
+
+int cmos_track_last_launch_count(cmos_track_t h, int32_t* n) {
+  CMOS_REQUIRE(h && n, "null argument");
+  *n = h->launches;
+  return CMOS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+"""Host-side mirror of the per-frame work of the reference's Tracking thread — Frame::Frame (ExtractORB,
+AssignFeaturesToGrid; src/Frame.cc:98-156) followed by ORBmatcher::SearchByProjection(current, last, th)
+(src/Tracking.cc:632) — as ONE batched call over host buffers (cmos_track_* in include/cmos_b200.h).  The library
+pipelines chunks of the batch over CUDA streams; this file only marshals buffers."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import KP_DTYPE, OrbParams, check, ptr
+from .orb_matcher import Camera
+
+
+class TrackParams(C.Structure):
+    _fields_ = [("orb", OrbParams), ("lanes", C.c_int32), ("chunk_frames", C.c_int32)]
+
+
+class TrackingFrontEnd:
+    def __init__(self, cam: Camera, nfeatures: int, scaleFactor: float, nlevels: int, iniThFAST: int, minThFAST: int,
+                 max_width: int = 1241, max_height: int = 376, lanes: int = 3, chunk_frames: int = 8, device: int = 0,
+                 checkOri: bool = True):
+        self._L = _lib.lib()
+        p = TrackParams(OrbParams(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_width, max_height,
+                                  chunk_frames, device), lanes, chunk_frames)
+        self._h = C.c_void_p()
+        self._cam = cam
+        check(self._L.cmos_track_create(C.byref(p), C.byref(cam), C.byref(self._h)))
+        cap = C.c_int32()
+        check(self._L.cmos_track_keypoint_capacity(self._h, C.byref(cap)))
+        self.capacity = cap.value
+        self.check_ori = bool(checkOri)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.cmos_track_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def track(self, images, Tcw, last_keypoints, last_counts, last_flags, last_xw, last_descriptors, th: float,
+              out=None):
+        """images [B,H,W] uint8; Tcw [B,16]; last_* [B,S]...; -> (keypoints [B,cap], descriptors [B,cap,32],
+        counts [B], match [B,cap], nmatches [B]).  All host arrays (numpy or pinned torch tensors)."""
+        B, H, W = images.shape
+        S = last_flags.shape[1]
+        if out is None:
+            cap = self.capacity
+            out = (np.zeros((B, cap), KP_DTYPE), np.zeros((B, cap, 32), np.uint8), np.zeros(B, np.int32),
+                   np.full((B, cap), -1, np.int32), np.zeros(B, np.int32))
+        kps, desc, counts, match, nm = out
+        cap = match.shape[1]
+        check(self._L.cmos_track_frames(self._h, ptr(images), C.c_int64(H * W), W, W, H, B, ptr(Tcw), ptr(last_keypoints),
+                                        ptr(last_counts), ptr(last_flags), ptr(last_xw), ptr(last_descriptors), S,
+                                        C.c_float(th), int(self.check_ori), ptr(kps), ptr(desc), ptr(counts), cap,
+                                        ptr(match), ptr(nm)))
+        return out
+
+    def launch_count(self) -> int:
+        n = C.c_int32()
+        check(self._L.cmos_track_last_launch_count(self._h, C.byref(n)))
+        return n.value

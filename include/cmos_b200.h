@@ -93,6 +93,15 @@ int cmos_orb_extract(cmos_orb_t h, const uint8_t* images, int64_t frame_stride, 
 int cmos_orb_extract_device(cmos_orb_t h, const uint8_t* d_images, int64_t frame_stride, int32_t pitch,
                             int32_t width, int32_t height, int32_t n_frames, void* stream);
 
+/* Host buffers like cmos_orb_extract, but only ENQUEUES on `stream` (NULL = the handle's stream): the image upload,
+ * the kernels and the download of keypoints / descriptors / counts.  The caller's buffers must stay valid — and should
+ * be page-locked, otherwise the copies serialise — until cmos_orb_finish returns.  cmos_orb_finish waits for the
+ * stream and returns CMOS_ERR_CAPACITY if a candidate buffer overflowed (results invalid). */
+int cmos_orb_extract_async(cmos_orb_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch,
+                           int32_t width, int32_t height, int32_t n_frames, cmos_keypoint* keypoints,
+                           uint8_t* descriptors, int32_t* counts, int32_t capacity, void* stream);
+int cmos_orb_finish(cmos_orb_t h, void* stream);
+
 /* Device views of the last extraction: keypoints [max_batch][cap], descriptors [max_batch][cap][32],
  * counts [max_batch], level_counts [max_batch][CMOS_MAX_LEVELS]. */
 int cmos_orb_device_results(cmos_orb_t h, cmos_keypoint** d_keypoints, uint8_t** d_descriptors,
@@ -223,6 +232,38 @@ int cmos_match_set_profiling(cmos_match_t h, int32_t enable);
 int cmos_match_stage_times(cmos_match_t h, double* ms, int64_t* calls);
 /* Number of kernels launched by the last cmos_match_* call. */
 int cmos_match_last_launch_count(cmos_match_t h, int32_t* n);
+
+/* ------------------------------------------------------------------------------------------------
+ * Path 1a+1b fused for a batch of frames with HOST buffers: what the Tracking thread does per frame —
+ * Frame::Frame (src/Frame.cc:98-156: ExtractORB at :116 -> ORBextractor::operator() at :175-177, AssignFeaturesToGrid
+ * at :155) followed by TrackWithMotionModel's ORBmatcher::SearchByProjection(current_frame_, last_frame_, th)
+ * (src/Tracking.cc:632; src/ORBmatcher.cc:1161-1271).  The batch is cut into chunks of `chunk_frames` that travel
+ * down `lanes` CUDA streams, so uploads, kernels and downloads of neighbouring chunks overlap; results are
+ * identical to cmos_orb_extract + cmos_match_set_frames + cmos_match_search_by_projection_frame.
+ * Pass page-locked host memory for the overlap to happen.  Synchronous: everything is complete on return.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  cmos_orb_params orb;      /* max_batch is ignored (each lane is sized for chunk_frames) */
+  int32_t lanes;            /* streams / handle sets, 1..16 */
+  int32_t chunk_frames;     /* frames per chunk */
+} cmos_track_params;
+
+typedef struct cmos_track* cmos_track_t;
+
+int cmos_track_create(const cmos_track_params* params, const cmos_camera* cam, cmos_track_t* out);
+int cmos_track_destroy(cmos_track_t h);
+int cmos_track_keypoint_capacity(cmos_track_t h, int32_t* cap);
+/* images as cmos_orb_extract; Tcw / last_* / th / check_orientation as cmos_match_search_by_projection_frame with
+ * [n_frames][last_stride] host arrays (last_stride <= capacity of the handle); keypoints / descriptors / counts as
+ * cmos_orb_extract ([n_frames][capacity]...); match [n_frames][capacity], nmatches [n_frames]. */
+int cmos_track_frames(cmos_track_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
+                      int32_t height, int32_t n_frames, const double* Tcw, const cmos_keypoint* last_keypoints,
+                      const int32_t* last_counts, const uint8_t* last_flags, const double* last_xw,
+                      const uint8_t* last_descriptors, int32_t last_stride, float th, int32_t check_orientation,
+                      cmos_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int32_t capacity,
+                      int32_t* match, int32_t* nmatches);
+/* Kernels launched by the last cmos_track_frames call. */
+int cmos_track_last_launch_count(cmos_track_t h, int32_t* n);
 
 /* ------------------------------------------------------------------------------------------------
  * Path 2: CeresOptimizer  (replaces CeresOptimizer::PoseOptimization / LocalBundleAdjustment / BundleAdjustment /

@@ -108,6 +108,51 @@ def test_search_frame_overflow_and_reclaim():
     assert nm[0] == onm and np.array_equal(match[0], om)
 
 
+@pytest.mark.parametrize("th,palette,obs_frac", [(6.0, 3, 0.9), (10.0, 40, 0.5), (15.0, 8, 1.0)])
+def test_search_frame_contention_chains(th, palette, obs_frac):
+    """Clustered keypoints with descriptors drawn from a small palette: many queries want the same candidates, so
+    the claim chains of the greedy assignment are long (the parallel fixed point needs many rounds) while most
+    lists stay within the list capacity."""
+    rng = np.random.default_rng(int(th) * 100 + palette)
+    n = 1800
+    centres = np.stack([rng.uniform(60, W - 60, 40), rng.uniform(40, H - 40, 40)], 1)
+    which = rng.integers(0, 40, n)
+    kps = np.zeros(n, KP_DTYPE)
+    kps["x"] = np.clip(centres[which, 0] + rng.normal(0, 14, n), 1, W - 2).astype(np.float32)
+    kps["y"] = np.clip(centres[which, 1] + rng.normal(0, 9, n), 1, H - 2).astype(np.float32)
+    kps["octave"] = rng.integers(0, 2, n); kps["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    pal = rng.integers(0, 256, (palette, 32)).astype(np.uint8)
+    desc = pal[rng.integers(0, palette, n)].copy()
+    flip = rng.random(n) < 0.5
+    desc[flip, rng.integers(0, 32, flip.sum())] ^= np.uint8(1) << rng.integers(0, 8, flip.sum()).astype(np.uint8)
+    o = po.OrbOracle(2000, 1.2, 8, 20, 7)
+    cam = Camera.create(W, H, K, o.scale_factors)
+    # last frame = a permutation of the same keypoints, slightly moved
+    perm = rng.permutation(n)
+    lk = kps[perm].copy()
+    ldesc = desc[perm].copy()
+    flags = (1 | ((rng.random(n) < obs_frac).astype(np.uint8) << 1)).astype(np.uint8)
+    flags[rng.random(n) < 0.1] &= 2
+    z = rng.uniform(5, 30, n)
+    fx, fy, cx, cy = [float(np.float32(v)) for v in K]
+    u = lk["x"] + rng.normal(0, 1.5, n); v = lk["y"] + rng.normal(0, 1.5, n)
+    xw = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    T = identity_T()[None]
+    claimed0 = (rng.random(n) < 0.03).astype(np.uint8)
+    m = ORBmatcher(0.9, True, max_batch=1, max_keypoints=n)
+    m.set_frames(cam, kps[None], desc[None], np.array([n], np.int32), 1, n)
+    claimed = claimed0[None].copy()
+    match, nm = m.SearchByProjectionFrame(T, lk[None], np.array([n], np.int32), flags[None], xw[None], ldesc[None], n, th,
+                                          claimed=claimed)
+    gs, gi = po.build_grid(kps, cam.bounds6())
+    om, onm, ocl = po.search_by_projection_frame(kps, desc, gs, gi, cam.bounds6(), cam.K4(), o.scale_factors, T[0], lk,
+                                                 flags, xw, ldesc, th, True, claimed=claimed0.copy())
+    assert nm[0] == onm
+    assert np.array_equal(match[0], om), f"{(match[0] != om).sum()} keypoints differ"
+    assert np.array_equal(claimed[0], ocl)
+    assert onm > 200
+
+
 @pytest.mark.parametrize("th,ratio", [(1.0, 0.8), (5.0, 0.8), (3.0, 0.6)])
 def test_search_by_projection_points_batch(seq, th, ratio):
     offs, ext, o = seq
@@ -207,3 +252,37 @@ def test_is_in_frustum(seq):
     assert np.array_equal(iv[0], oiv)
     sel = oiv.astype(bool)
     assert np.array_equal(pj[0][sel], opj[sel]) and np.array_equal(lv[0][sel], olv[sel]) and np.array_equal(vc[0][sel], ovc[sel])
+
+
+@pytest.mark.parametrize("lanes,chunk", [(1, 8), (2, 2), (3, 1)])
+def test_tracking_front_end_equals_unfused_calls(lanes, chunk):
+    """cmos_track_frames (chunks pipelined over streams, host buffers) == extract + grid + SearchByProjection."""
+    from ceres_mono_orb_slam2_b200 import ORBextractor, TrackingFrontEnd
+    w, h, B = 640, 480, 5
+    frames, offs = synth.make_sequence(w, h, B, 21, return_offsets=True)
+    ext = ORBextractor(1000, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    kps, desc, counts = ext.extract_batch(frames)
+    cap = ext.capacity
+    cam = Camera.create(w, h, synth.TUM2_K, ext.GetScaleFactors())
+    lk = np.zeros((B, cap), KP_DTYPE); lcounts = np.zeros(B, np.int32)
+    flags = np.zeros((B, cap), np.uint8); xw = np.zeros((B, cap, 3)); mdesc = np.zeros((B, cap, 32), np.uint8)
+    T = np.tile(identity_T(), (B, 1))
+    for f in range(B):
+        l = (f - 1) % B
+        nl = int(counts[l])
+        fl, x, md = synth.make_last_frame_view(kps[l, :nl], desc[l, :nl], (offs[l] - offs[f]).astype(float), 50 + f,
+                                               K=synth.TUM2_K)
+        lk[f, :nl] = kps[l, :nl]; lcounts[f] = nl; flags[f, :nl] = fl; xw[f, :nl] = x; mdesc[f, :nl] = md
+    m = ORBmatcher(0.9, True, max_batch=B, max_keypoints=cap)
+    m.set_frames(cam, kps, desc, counts, B, cap)
+    match, nm = m.SearchByProjectionFrame(T, lk, lcounts, flags, xw, mdesc, cap, 15.0)
+    fe = TrackingFrontEnd(cam, 1000, 1.2, 8, 20, 7, max_width=w, max_height=h, lanes=lanes, chunk_frames=chunk)
+    assert fe.capacity == cap
+    for _ in range(2):      # the second pass reuses every lane's buffers
+        k2, d2, c2, m2, n2 = fe.track(frames, T, lk, lcounts, flags, xw, mdesc, 15.0)
+        assert np.array_equal(c2, counts) and np.array_equal(n2, nm)
+        for f in range(B):
+            n = int(counts[f])
+            assert np.array_equal(k2[f, :n], kps[f, :n]) and np.array_equal(d2[f, :n], desc[f, :n])
+            assert np.array_equal(m2[f, :n], match[f, :n])
+    assert nm.sum() > 100 * B and fe.launch_count() > 0
