@@ -60,7 +60,15 @@ __global__ void __launch_bounds__(256) k_level0(OrbGeom g, const uint8_t* __rest
 }
 
 // Level l from level l-1: cv::resize INTER_LINEAR fixed-point (Appendix A.1) fused with the
-// reflect-101 border (ORBextractor.cc:1120-1123).  tab entries: {src offset, coeff0, coeff1, 0}.
+// reflect-101 border (ORBextractor.cc:1120-1123).  xtab entries: {coeff0, coeff1, src x, 0}; ytab: {src y, coeff0,
+// coeff1, 0}.  One thread writes one aligned 4-byte word.  Interior words take the fast path: the four source
+// pairs lie within 12 bytes, so each source row is three aligned word loads, every pair is cut out with a funnel
+// shift and the horizontal pass is one DP2A (coeff pair x byte pair).
+__device__ __forceinline__ uint32_t resize_vpass(int t0, int t1, int b0, int b1) {
+  int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+  return (uint32_t)min(max(v, 0), 255);
+}
+
 __global__ void __launch_bounds__(256) k_resize(OrbGeom g, int level, const short4* __restrict__ xtab,
                                                 const short4* __restrict__ ytab, uint8_t* __restrict__ pyr) {
   const LevelGeom& L = g.lv[level];
@@ -78,18 +86,37 @@ __global__ void __launch_bounds__(256) k_resize(OrbGeom g, int level, const shor
   const uint8_t* r1 = src + (long long)sy1 * S.pitch;
   int b0 = ty.y, b1 = ty.z;
   uint32_t word = 0;
+  const int bx0 = c4 * 4 - kXOff;
+  if (bx0 >= 0 && bx0 + 3 < L.w) {
+    const int4 ta = __ldg((const int4*)(xtab + bx0)), tb = __ldg((const int4*)(xtab + bx0) + 1);
+    const unsigned coef[4] = {(unsigned)ta.x, (unsigned)ta.z, (unsigned)tb.x, (unsigned)tb.z};
+    const int sx[4] = {ta.y & 0xffff, ta.w & 0xffff, tb.y & 0xffff, tb.w & 0xffff};
+    const int wb = sx[0] >> 2;
+    const uint32_t* p0 = (const uint32_t*)r0 + wb;
+    const uint32_t* p1 = (const uint32_t*)r1 + wb;
+    const uint32_t u0 = p0[0], u1 = p0[1], u2 = p0[2], v0 = p1[0], v1 = p1[1], v2 = p1[2];
 #pragma unroll
-  for (int b = 0; b < 4; b++) {
-    int bx = c4 * 4 + b - kXOff;
-    if (bx >= -kBorder && bx < L.w + kBorder) {
-      int dx = reflect101(bx, L.w);
-      short4 tx = __ldg(xtab + dx);
-      int sx0 = tx.x, sx1 = min(sx0 + 1, S.w - 1);
-      int t0 = r0[sx0] * (int)tx.y + r0[sx1] * (int)tx.z;
-      int t1 = r1[sx0] * (int)tx.y + r1[sx1] * (int)tx.z;
-      int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
-      v = min(max(v, 0), 255);
-      word |= (uint32_t)v << (8 * b);
+    for (int b = 0; b < 4; b++) {
+      const int o = sx[b] - 4 * wb;           // 0..8
+      const bool hi = o >= 4;
+      const unsigned sh = 8u * (unsigned)(o & 3);
+      const uint32_t w0 = __funnelshift_r(hi ? u1 : u0, hi ? u2 : u1, sh);
+      const uint32_t w1 = __funnelshift_r(hi ? v1 : v0, hi ? v2 : v1, sh);
+      const int t0 = (int)__dp2a_lo(coef[b], w0, 0u), t1 = (int)__dp2a_lo(coef[b], w1, 0u);
+      word |= resize_vpass(t0, t1, b0, b1) << (8 * b);
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      int bx = bx0 + b;
+      if (bx >= -kBorder && bx < L.w + kBorder) {
+        int dx = reflect101(bx, L.w);
+        short4 tx = __ldg(xtab + dx);
+        int sx0 = tx.z, sx1 = min(sx0 + 1, S.w - 1);
+        int t0 = r0[sx0] * (int)tx.x + r0[sx1] * (int)tx.y;
+        int t1 = r1[sx0] * (int)tx.x + r1[sx1] * (int)tx.y;
+        word |= resize_vpass(t0, t1, b0, b1) << (8 * b);
+      }
     }
   }
   *(uint32_t*)(frame + L.plane_off + (long long)row * L.pitch + c4 * 4) = word;
@@ -191,25 +218,52 @@ __global__ void __launch_bounds__(kThreads) k_fast(OrbGeom g, const int4* __rest
 
   const int dw = cw - 6, dh = ch - 6;   // detection area
   const int npx = dw > 0 && dh > 0 ? dw * dh : 0;
-  const unsigned dmagic = dw > 0 ? ((1u << 20) + dw - 1) / dw : 0;   // exact for i < 4620, dw <= 70
   int th = g.ini_th;
   for (int pass = 0; pass < 2; pass++) {
-    // A: compass test, compaction
-    for (int base = 0; base < npx; base += kThreads) {
-      const int i = base + tid;
-      bool ok = false;
-      int y = 0, x = 0;
-      if (i < npx) {
-        y = (int)(((unsigned)i * dmagic) >> 20);
-        x = i - y * dw;
-        ok = fast_compass(tile + (y + 3) * kTileW + shift + x + 3, kTileW, th);
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, ok);
-      if (bal) {
-        int off = 0;
-        if (lane == 0) off = atomicAdd(&s_npx, __popc(bal));
-        off = __shfl_sync(0xffffffffu, off, 0);
-        if (ok) s_px[off + __popc(bal & ((1u << lane) - 1))] = (uint16_t)((y << 8) | x);
+    // A: compass filter on four pixels at a time (one aligned tile word), compaction.  Only a NECESSARY condition is
+    // needed here (B is exact): |ring - c| > t on (0 or 8) and on (4 or 12), polarity ignored, thresholded on
+    // |d| >> 1 so that the test is an add into bit 7 of every byte.
+    {
+      const int c0 = shift + 3, w_first = c0 >> 2, nw = ((c0 + dw - 1) >> 2) - w_first + 1;
+      const int items = npx > 0 ? dh * nw : 0;
+      const unsigned nmagic = ((1u << 20) + nw - 1) / nw;
+      const unsigned addc = (0x80u - (unsigned)((th + 1) >> 1)) * 0x01010101u;
+      const uint32_t* t32 = (const uint32_t*)tile;
+      for (int base = 0; base < items; base += kThreads) {
+        const int i = base + tid;
+        unsigned hit = 0;
+        int y = 0, xb = 0;
+        if (i < items) {
+          y = (int)(((unsigned)i * nmagic) >> 20);
+          const int wc = w_first + (i - y * nw);
+          const uint32_t* row = t32 + (y + 3) * (kTileW / 4) + wc;
+          const uint32_t C = row[0], Lw = row[-1], Rw = row[1];
+          const uint32_t U = row[-3 * (kTileW / 4)], D = row[3 * (kTileW / 4)];
+          const unsigned a0 = __vabsdiffu4(D, C), a8 = __vabsdiffu4(U, C);
+          const unsigned a4 = __vabsdiffu4(__funnelshift_r(C, Rw, 24), C), a12 = __vabsdiffu4(__funnelshift_r(Lw, C, 8), C);
+          const unsigned g0 = ((a0 >> 1) & 0x7f7f7f7fu) + addc, g8 = ((a8 >> 1) & 0x7f7f7f7fu) + addc;
+          const unsigned g4 = ((a4 >> 1) & 0x7f7f7f7fu) + addc, g12 = ((a12 >> 1) & 0x7f7f7f7fu) + addc;
+          hit = (g0 | g8) & (g4 | g12) & 0x80808080u;
+          xb = 4 * wc - c0;                       // detection-area x of byte 0 of this word
+          // bytes outside [0, dw) are not detection pixels
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if ((unsigned)(xb + j) >= (unsigned)dw) hit &= ~(0x80u << (8 * j));
+        }
+        if (__any_sync(0xffffffffu, hit != 0)) {
+          const unsigned b0 = __ballot_sync(0xffffffffu, hit & 0x80u), b1 = __ballot_sync(0xffffffffu, hit & 0x8000u);
+          const unsigned b2 = __ballot_sync(0xffffffffu, hit & 0x800000u), b3 = __ballot_sync(0xffffffffu, hit & 0x80000000u);
+          const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
+          int off = 0;
+          if (lane == 0) off = atomicAdd(&s_npx, n0 + n1 + n2 + n3);
+          off = __shfl_sync(0xffffffffu, off, 0);
+          const unsigned lt = (1u << lane) - 1;
+          const int yx = (y << 8) + xb;           // + j >= y << 8 for every byte that survived the range mask
+          if (hit & 0x80u) s_px[off + __popc(b0 & lt)] = (uint16_t)yx;
+          if (hit & 0x8000u) s_px[off + n0 + __popc(b1 & lt)] = (uint16_t)(yx + 1);
+          if (hit & 0x800000u) s_px[off + n0 + n1 + __popc(b2 & lt)] = (uint16_t)(yx + 2);
+          if (hit & 0x80000000u) s_px[off + n0 + n1 + n2 + __popc(b3 & lt)] = (uint16_t)(yx + 3);
+        }
       }
     }
     __syncthreads();
@@ -821,6 +875,7 @@ bool build_geometry(const cmos_orb* h, int w, int ht, GeomBuild* out) {
     // resize tables for level l (from l-1): Appendix A.1
     if (l > 0) {
       const LevelGeom& S = g.lv[l - 1];
+      if (out->tab.size() & 1) out->tab.push_back(make_short4(0, 0, 0, 0));   // x tables are read as int4 pairs
       out->xoff[l] = (int)out->tab.size();
       const double scale_x = (double)S.w / L.w, scale_y = (double)S.h / L.h;
       for (int dx = 0; dx < L.w; dx++) {
@@ -829,7 +884,7 @@ bool build_geometry(const cmos_orb* h, int w, int ht, GeomBuild* out) {
         fx -= sx;
         if (sx < 0) { fx = 0; sx = 0; }
         if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
-        out->tab.push_back(make_short4((short)sx, (short)cv_round_f((1.f - fx) * 2048.f), (short)cv_round_f(fx * 2048.f), 0));
+        out->tab.push_back(make_short4((short)cv_round_f((1.f - fx) * 2048.f), (short)cv_round_f(fx * 2048.f), (short)sx, 0));
       }
       out->yoff[l] = (int)out->tab.size();
       for (int dy = 0; dy < L.h; dy++) {
