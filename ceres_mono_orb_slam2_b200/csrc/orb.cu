@@ -69,57 +69,75 @@ __device__ __forceinline__ uint32_t resize_vpass(int t0, int t1, int b0, int b1)
   return (uint32_t)min(max(v, 0), 255);
 }
 
+// kRows output rows per thread: the column set-up (tables, window selectors) is paid once per thread
+template <int kResizeRows>
 __global__ void __launch_bounds__(256) k_resize(OrbGeom g, int level, const short4* __restrict__ xtab,
                                                 const short4* __restrict__ ytab, uint8_t* __restrict__ pyr) {
   const LevelGeom& L = g.lv[level];
   const LevelGeom& S = g.lv[level - 1];
-  int c4 = blockIdx.x * blockDim.x + threadIdx.x;
-  int row = blockIdx.y * blockDim.y + threadIdx.y;
-  int f = blockIdx.z;
-  if (c4 * 4 >= L.pitch || row >= L.rows) return;
+  const int c4 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row_first = (blockIdx.y * blockDim.y + threadIdx.y) * kResizeRows;
+  const int f = blockIdx.z;
+  if (c4 * 4 >= L.pitch || row_first >= L.rows) return;
+  const int row_end = min(row_first + kResizeRows, L.rows);
   uint8_t* frame = pyr + (long long)f * g.frame_bytes;
   const uint8_t* src = frame + S.plane_off + (long long)kBorder * S.pitch + kXOff;
-  int dy = reflect101(row - kBorder, L.h);
-  short4 ty = __ldg(ytab + dy);
-  int sy0 = min(max((int)ty.x, 0), S.h - 1), sy1 = min(max((int)ty.x + 1, 0), S.h - 1);
-  const uint8_t* r0 = src + (long long)sy0 * S.pitch;
-  const uint8_t* r1 = src + (long long)sy1 * S.pitch;
-  int b0 = ty.y, b1 = ty.z;
-  uint32_t word = 0;
+  uint8_t* dst = frame + L.plane_off + c4 * 4;
   const int bx0 = c4 * 4 - kXOff;
   if (bx0 >= 0 && bx0 + 3 < L.w) {
     const int4 ta = __ldg((const int4*)(xtab + bx0)), tb = __ldg((const int4*)(xtab + bx0) + 1);
     const unsigned coef[4] = {(unsigned)ta.x, (unsigned)ta.z, (unsigned)tb.x, (unsigned)tb.z};
     const int sx[4] = {ta.y & 0xffff, ta.w & 0xffff, tb.y & 0xffff, tb.w & 0xffff};
     const int wb = sx[0] >> 2;
-    const uint32_t* p0 = (const uint32_t*)r0 + wb;
-    const uint32_t* p1 = (const uint32_t*)r1 + wb;
-    const uint32_t u0 = p0[0], u1 = p0[1], u2 = p0[2], v0 = p1[0], v1 = p1[1], v2 = p1[2];
+    bool hi[4];
+    unsigned sh[4];
 #pragma unroll
     for (int b = 0; b < 4; b++) {
       const int o = sx[b] - 4 * wb;           // 0..8
-      const bool hi = o >= 4;
-      const unsigned sh = 8u * (unsigned)(o & 3);
-      const uint32_t w0 = __funnelshift_r(hi ? u1 : u0, hi ? u2 : u1, sh);
-      const uint32_t w1 = __funnelshift_r(hi ? v1 : v0, hi ? v2 : v1, sh);
-      const int t0 = (int)__dp2a_lo(coef[b], w0, 0u), t1 = (int)__dp2a_lo(coef[b], w1, 0u);
-      word |= resize_vpass(t0, t1, b0, b1) << (8 * b);
+      hi[b] = o >= 4;
+      sh[b] = 8u * (unsigned)(o & 3);
+    }
+#pragma unroll
+    for (int rr = 0; rr < kResizeRows; rr++) {
+      const int row = row_first + rr;
+      if (row >= row_end) break;
+      const short4 ty = __ldg(ytab + reflect101(row - kBorder, L.h));
+      const int sy0 = min(max((int)ty.x, 0), S.h - 1), sy1 = min(max((int)ty.x + 1, 0), S.h - 1);
+      const uint32_t* p0 = (const uint32_t*)(src + (long long)sy0 * S.pitch) + wb;
+      const uint32_t* p1 = (const uint32_t*)(src + (long long)sy1 * S.pitch) + wb;
+      const uint32_t u0 = p0[0], u1 = p0[1], u2 = p0[2], v0 = p1[0], v1 = p1[1], v2 = p1[2];
+      uint32_t word = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const uint32_t w0 = __funnelshift_r(hi[b] ? u1 : u0, hi[b] ? u2 : u1, sh[b]);
+        const uint32_t w1 = __funnelshift_r(hi[b] ? v1 : v0, hi[b] ? v2 : v1, sh[b]);
+        const int t0 = (int)__dp2a_lo(coef[b], w0, 0u), t1 = (int)__dp2a_lo(coef[b], w1, 0u);
+        word |= resize_vpass(t0, t1, ty.y, ty.z) << (8 * b);
+      }
+      *(uint32_t*)(dst + (long long)row * L.pitch) = word;
     }
   } else {
+    for (int row = row_first; row < row_end; row++) {
+      const short4 ty = __ldg(ytab + reflect101(row - kBorder, L.h));
+      const int sy0 = min(max((int)ty.x, 0), S.h - 1), sy1 = min(max((int)ty.x + 1, 0), S.h - 1);
+      const uint8_t* r0 = src + (long long)sy0 * S.pitch;
+      const uint8_t* r1 = src + (long long)sy1 * S.pitch;
+      uint32_t word = 0;
 #pragma unroll
-    for (int b = 0; b < 4; b++) {
-      int bx = bx0 + b;
-      if (bx >= -kBorder && bx < L.w + kBorder) {
-        int dx = reflect101(bx, L.w);
-        short4 tx = __ldg(xtab + dx);
-        int sx0 = tx.z, sx1 = min(sx0 + 1, S.w - 1);
-        int t0 = r0[sx0] * (int)tx.x + r0[sx1] * (int)tx.y;
-        int t1 = r1[sx0] * (int)tx.x + r1[sx1] * (int)tx.y;
-        word |= resize_vpass(t0, t1, b0, b1) << (8 * b);
+      for (int b = 0; b < 4; b++) {
+        int bx = bx0 + b;
+        if (bx >= -kBorder && bx < L.w + kBorder) {
+          int dx = reflect101(bx, L.w);
+          short4 tx = __ldg(xtab + dx);
+          int sx0 = tx.z, sx1 = min(sx0 + 1, S.w - 1);
+          int t0 = r0[sx0] * (int)tx.x + r0[sx1] * (int)tx.y;
+          int t1 = r1[sx0] * (int)tx.x + r1[sx1] * (int)tx.y;
+          word |= resize_vpass(t0, t1, ty.y, ty.z) << (8 * b);
+        }
       }
+      *(uint32_t*)(dst + (long long)row * L.pitch) = word;
     }
   }
-  *(uint32_t*)(frame + L.plane_off + (long long)row * L.pitch + c4 * 4) = word;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -786,6 +804,7 @@ struct cmos_orb {
   size_t images_cap = 0;
   int last_frames = 0, launches = 0;
   int fast_threads = 128;   // CMOS_FAST_THREADS=256 selects the wider CTA (tuning knob)
+  int resize_rows = 2;      // CMOS_RESIZE_ROWS=1|2|4 output rows per thread of k_resize (tuning knob)
   bool has_result = false;
   StageTimer timer;
 };
@@ -948,8 +967,11 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
   }
   for (int l = 1; l < g.nlevels; l++) {
     const LevelGeom& L = g.lv[l];
-    dim3 grid((L.pitch / 4 + 63) / 64, (L.rows + 3) / 4, n_frames);
-    k_resize<<<grid, blk, 0, st>>>(g, l, h->d_tab + h->xtab_off[l], h->d_tab + h->ytab_off[l], h->d_pyr);
+    const int rr = h->resize_rows;
+    dim3 grid((L.pitch / 4 + 63) / 64, (L.rows + 4 * rr - 1) / (4 * rr), n_frames);
+    if (rr == 1) k_resize<1><<<grid, blk, 0, st>>>(g, l, h->d_tab + h->xtab_off[l], h->d_tab + h->ytab_off[l], h->d_pyr);
+    else if (rr == 2) k_resize<2><<<grid, blk, 0, st>>>(g, l, h->d_tab + h->xtab_off[l], h->d_tab + h->ytab_off[l], h->d_pyr);
+    else k_resize<4><<<grid, blk, 0, st>>>(g, l, h->d_tab + h->xtab_off[l], h->d_tab + h->ytab_off[l], h->d_pyr);
     launches++;
   }
   h->timer.mark(st);   // stage 0: pyramid
@@ -1003,6 +1025,7 @@ int cmos_orb_create(const cmos_orb_params* params, cmos_orb_t* out) {
   h->p = *params;
   h->device = params->device;
   if (const char* e = std::getenv("CMOS_FAST_THREADS")) h->fast_threads = std::atoi(e) == 256 ? 256 : 128;
+  if (const char* e = std::getenv("CMOS_RESIZE_ROWS")) { int r = std::atoi(e); h->resize_rows = r == 2 ? 2 : r == 4 ? 4 : 1; }
   // tables of the constructor, ORBextractor.cc:410-470 (scaleFactor member is double, ORBextractor.h:95)
   const int nl = params->nlevels;
   const double scale_d = (double)params->scale_factor;

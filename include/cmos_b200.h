@@ -234,6 +234,98 @@ int cmos_match_stage_times(cmos_match_t h, double* ms, int64_t* calls);
 int cmos_match_last_launch_count(cmos_match_t h, int32_t* n);
 
 /* ------------------------------------------------------------------------------------------------
+ * Path 1c: the remaining ORBmatcher searches: relocalisation / loop-closing projections,
+ * the two SearchByBoW, SearchForInitialization, SearchForTriangulation, both Fuse and SearchBySim3
+ * (reference include/ORBmatcher.h:50-96, src/ORBmatcher.cc:128-1159,1273-1384).  One problem per call, HOST
+ * pointers, synchronous.  A Frame / KeyFrame is bound to one of two view slots first (keypoints, descriptors, the
+ * grid of Frame::AssignFeaturesToGrid).  For a KeyFrame the searches use KeyFrame::GetFeaturesInArea / IsInImage,
+ * whose image bounds are the Frame's truncated to int (KeyFrame.h:179-182, KeyFrame.cc:575-626); the grid itself
+ * is the Frame's (KeyFrame.cc:98-104).
+ * Pointer graphs are flattened like Path 1b.  Predicates that cannot change during a call are bytes prepared by the
+ * caller.  The map-mutating Fuse functions return DECISIONS (best keypoint per map point); the host adapter applies
+ * Replace / AddObservation in the reference's order (include/orb_slam2/ORBmatcher.h).
+ * A DBoW2::FeatureVector (map<NodeId, vector<unsigned>>) is passed flattened: node ids ascending, start[n_nodes+1],
+ * feature indices in insertion order.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t max_keypoints;   /* keypoints per view, <= 16384 */
+  int32_t max_points;      /* map points per call */
+  int32_t max_nodes;       /* FeatureVector nodes per view */
+  int32_t device;
+} cmos_kfmatch_params;
+
+typedef struct cmos_kfmatch* cmos_kfmatch_t;
+
+typedef struct {           /* flattened DBoW2::FeatureVector */
+  int32_t n_nodes;
+  const int32_t* node_ids;   /* [n_nodes] ascending */
+  const int32_t* start;      /* [n_nodes + 1] */
+  const int32_t* features;   /* [start[n_nodes]] */
+} cmos_feature_vector;
+
+int cmos_kfmatch_create(const cmos_kfmatch_params* params, cmos_kfmatch_t* out);
+int cmos_kfmatch_destroy(cmos_kfmatch_t h);
+/* Binds view `slot` (0 or 1): undistort_keypoints_, descriptors_, N_, and builds the grid.  is_keyframe != 0 selects
+ * the KeyFrame flavour of GetFeaturesInArea / IsInImage (int-truncated bounds). */
+int cmos_kfmatch_set_view(cmos_kfmatch_t h, int32_t slot, const cmos_camera* cam, int32_t is_keyframe,
+                          const cmos_keypoint* keypoints, const uint8_t* descriptors, int32_t n);
+
+/* SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)
+ * (ORBmatcher.cc:1273-1384).  Slot 0 = CurrentFrame.  Per keyframe keypoint i (n_kf of them): kf_valid = pMP &&
+ * !isBad && !sAlreadyFound.count(pMP); world position, raw min/max distance (the 0.8 / 1.2 factors are applied
+ * inside), MapPoint::GetDescriptor(), angle of pKF->undistort_keypoints_[i].
+ *   cur_has_point [n] in/out: CurrentFrame.map_points_[i2] != NULL;  cur_match [n] out: i or -1 */
+int cmos_kfmatch_search_by_projection_reloc(cmos_kfmatch_t h, const double* Tcw16, int32_t n_kf, const uint8_t* kf_valid,
+                                            const double* kf_xw, const float* kf_min_distance,
+                                            const float* kf_max_distance, const uint8_t* kf_descriptors,
+                                            const float* kf_angle, float th, int32_t orb_dist,
+                                            int32_t check_orientation, uint8_t* cur_has_point, int32_t* cur_match,
+                                            int32_t* nmatches);
+/* SearchByProjection(KeyFrame* pKF, Scw, vpPoints, vpMatched, th) (ORBmatcher.cc:258-361).  Slot 0 = pKF.
+ *   pt_skip = isBad || spAlreadyFound.count;  matched [n] in/out: vpMatched[idx] != NULL;  assign [n] out: point or -1 */
+int cmos_kfmatch_search_by_projection_sim3(cmos_kfmatch_t h, const double* Scw16, int32_t n_points,
+                                           const uint8_t* pt_skip, const double* xw, const double* normal,
+                                           const float* min_distance, const float* max_distance,
+                                           const uint8_t* pt_descriptors, int32_t th, uint8_t* matched, int32_t* assign,
+                                           int32_t* nmatches);
+/* Fuse(KeyFrame*, vpMapPoints, th) (ORBmatcher.cc:724-842; sim3 == 0, pose = Rcw row-major (9), tcw (3), Ow (3)) and
+ * Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint) (:844-954; sim3 == 1, pose = Scw row-major 4x4).  Slot 0 = pKF.
+ *   pt_skip = !pMP || isBad || IsInKeyFrame(pKF) (resp. spAlreadyFound.count);  inv_level_sigma2 = pKF's table.
+ *   best_idx [n_points] out: keypoint to fuse with or -1;  best_dist [n_points];  n_fused = decisions made */
+int cmos_kfmatch_fuse(cmos_kfmatch_t h, int32_t sim3, const double* pose, const float* inv_level_sigma2,
+                      int32_t n_points, const uint8_t* pt_skip, const double* xw, const double* normal,
+                      const float* min_distance, const float* max_distance, const uint8_t* pt_descriptors, float th,
+                      int32_t* best_idx, int32_t* best_dist, int32_t* n_fused);
+/* SearchBySim3 (ORBmatcher.cc:956-1159).  Slot 0 = pKF1, slot 1 = pKF2.  pose{1,2} = R (9) + t (3) of the keyframes.
+ * Per keypoint of each keyframe: valid = pMP && !isBad, already = vbAlreadyMatched, world position, raw min/max
+ * distance, MapPoint descriptor.  match12 [n1] out: idx2 or -1 (the mutual matches). */
+int cmos_kfmatch_search_by_sim3(cmos_kfmatch_t h, const double* pose1, const double* pose2, float s12,
+                                const double* R12, const double* t12, const uint8_t* valid1, const uint8_t* already1,
+                                const double* xw1, const float* min_distance1, const float* max_distance1,
+                                const uint8_t* mp_descriptors1, const uint8_t* valid2, const uint8_t* already2,
+                                const double* xw2, const float* min_distance2, const float* max_distance2,
+                                const uint8_t* mp_descriptors2, float th, int32_t* match12, int32_t* n_found);
+/* SearchByBoW(KeyFrame*, Frame&, matches) (ORBmatcher.cc:151-256; mode 0: slot 0 = pKF, slot 1 = F, match [n2] out:
+ * keyframe keypoint whose map point F's keypoint receives) and SearchByBoW(KeyFrame*, KeyFrame*, matches12)
+ * (:470-580; mode 1: match [n1] out: idx2).  valid = pMP && !isBad per keypoint (valid2 unused in mode 0). */
+int cmos_kfmatch_search_by_bow(cmos_kfmatch_t h, int32_t mode, const uint8_t* valid1, const cmos_feature_vector* fv1,
+                               const uint8_t* valid2, const cmos_feature_vector* fv2, float nn_ratio,
+                               int32_t check_orientation, int32_t* match, int32_t* nmatches);
+/* SearchForTriangulation (ORBmatcher.cc:582-722, monocular).  Slot 0 = pKF1, slot 1 = pKF2.  has_point = GetMapPoint(i)
+ * != NULL.  F12 row-major 3x3; Cw = pKF1->GetCameraCenter(); R2w, t2w of pKF2; level_sigma2_2 = pKF2's table.
+ *   match12 [n1] out: idx2 or -1 (vMatchedPairs = the non-negative entries in index order) */
+int cmos_kfmatch_search_for_triangulation(cmos_kfmatch_t h, const uint8_t* has_point1, const cmos_feature_vector* fv1,
+                                          const uint8_t* has_point2, const cmos_feature_vector* fv2, const double* F12,
+                                          const double* Cw, const double* R2w, const double* t2w,
+                                          const float* level_sigma2_2, int32_t check_orientation, int32_t* match12,
+                                          int32_t* nmatches);
+/* SearchForInitialization (ORBmatcher.cc:363-468).  Slot 0 = F1, slot 1 = F2.  prev_matched [n1][2] in/out. */
+int cmos_kfmatch_search_for_initialization(cmos_kfmatch_t h, float* prev_matched, int32_t window_size, float nn_ratio,
+                                           int32_t check_orientation, int32_t* matches12, int32_t* nmatches);
+/* Kernels launched by the last cmos_kfmatch_* call. */
+int cmos_kfmatch_last_launch_count(cmos_kfmatch_t h, int32_t* n);
+
+/* ------------------------------------------------------------------------------------------------
  * Path 1a+1b fused for a batch of frames with HOST buffers: what the Tracking thread does per frame —
  * Frame::Frame (src/Frame.cc:98-156: ExtractORB at :116 -> ORBextractor::operator() at :175-177, AssignFeaturesToGrid
  * at :155) followed by TrackWithMotionModel's ORBmatcher::SearchByProjection(current_frame_, last_frame_, th)

@@ -347,3 +347,128 @@ def ba_global(cams, cam_const, pts, obs_cam, obs_pt, uv, inv_sigma2, K4, n_itera
     lib().ba_oracle_global(len(cams), _p(cams), _p(cc), len(pts), _p(pts), len(oc), _p(oc), _p(op), _p(uv), _p(w),
                            _p(K4), int(n_iterations), int(robust), C.byref(s), _p(trace), cap)
     return cams, pts, s.as_dict(), trace[:s.iterations + 1]
+
+
+# ---------------------------------------------------------------------------------------------------
+# The remaining ORBmatcher searches (oracle/matcher2_oracle.cpp)
+
+class View:
+    """A Frame or KeyFrame as the searches read it: keypoints, descriptors, the Frame's grid, and the 12 floats
+    {min_x, max_x, min_y, max_y, grid inv w, grid inv h, fx, fy, cx, cy, log scale factor, n levels}.  A KeyFrame's
+    bounds are truncated to int for the look-ups (KeyFrame.h:179-182); the grid is always the Frame's."""
+
+    def __init__(self, kps, desc, bounds6, K4, scale_factors, scale_factor=1.2, is_keyframe=False):
+        self.kps = np.ascontiguousarray(kps); self.desc = np.ascontiguousarray(desc, np.uint8)
+        self.n = len(self.kps)
+        b = np.asarray(bounds6, np.float32).copy()
+        self.gs, gi = build_grid(self.kps, b)
+        self.gi = np.ascontiguousarray(np.concatenate([gi, np.zeros(1, np.int32)]))
+        if is_keyframe:
+            b[:4] = np.trunc(b[:4])
+        self.sf = np.ascontiguousarray(scale_factors, np.float32)
+        log_sf = np.float32(np.log(np.float64(np.float32(scale_factor))))
+        self.v12 = np.concatenate([b, np.asarray(K4, np.float32), [log_sf, np.float32(len(self.sf))]]).astype(np.float32)
+
+    def args(self):
+        return (_p(self.kps), _p(self.desc), self.n, _p(self.gs), _p(self.gi), _p(self.v12))
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dt)
+
+
+def search_by_projection_reloc(V: View, Tcw, kf_valid, kf_xw, kf_min_d, kf_max_d, kf_desc, kf_angle, th, orb_dist,
+                               check_ori, cur_has_point):
+    hp = _c(cur_has_point, np.uint8).copy(); match = np.full(max(V.n, 1), -1, np.int32)
+    T = _c(Tcw, np.float64); va = _c(kf_valid, np.uint8); xw = _c(kf_xw, np.float64)
+    mn = _c(kf_min_d, np.float32); mx = _c(kf_max_d, np.float32); kd = _c(kf_desc, np.uint8); an = _c(kf_angle, np.float32)
+    nm = lib().match2_oracle_search_by_projection_reloc(*V.args(), _p(V.sf), _p(T), len(va), _p(va), _p(xw), _p(mn), _p(mx),
+                                                        _p(kd), _p(an), C.c_float(th), int(orb_dist), int(check_ori),
+                                                        _p(hp), _p(match))
+    return match[:V.n], nm, hp
+
+
+def search_by_projection_sim3(V: View, Scw, pt_skip, xw, normal, min_d, max_d, pt_desc, th, matched):
+    m = _c(matched, np.uint8).copy(); assign = np.full(max(V.n, 1), -1, np.int32)
+    S = _c(Scw, np.float64); sk = _c(pt_skip, np.uint8); x = _c(xw, np.float64); nr = _c(normal, np.float64)
+    mn = _c(min_d, np.float32); mx = _c(max_d, np.float32); pd = _c(pt_desc, np.uint8)
+    nm = lib().match2_oracle_search_by_projection_sim3(*V.args(), _p(V.sf), _p(S), len(sk), _p(sk), _p(x), _p(nr), _p(mn),
+                                                       _p(mx), _p(pd), int(th), _p(m), _p(assign))
+    return assign[:V.n], nm, m
+
+
+def fuse(V: View, inv_sigma2, sim3, pose, pt_skip, xw, normal, min_d, max_d, pt_desc, th):
+    n = len(pt_skip)
+    bi = np.full(max(n, 1), -1, np.int32); bd = np.full(max(n, 1), 256, np.int32)
+    P = _c(pose, np.float64); sk = _c(pt_skip, np.uint8); x = _c(xw, np.float64); nr = _c(normal, np.float64)
+    mn = _c(min_d, np.float32); mx = _c(max_d, np.float32); pd = _c(pt_desc, np.uint8); iv = _c(inv_sigma2, np.float32)
+    nf = lib().match2_oracle_fuse(*V.args(), _p(V.sf), _p(iv), int(sim3), _p(P), n, _p(sk), _p(x), _p(nr), _p(mn), _p(mx),
+                                  _p(pd), C.c_float(th), _p(bi), _p(bd))
+    return bi[:n], bd[:n], nf
+
+
+def search_by_sim3(V1: View, V2: View, pose1, pose2, s12, R12, t12, side1, side2, th):
+    """side = (valid, already, xw, min_d, max_d, mp_desc) per keypoint of that keyframe."""
+    m12 = np.full(max(V1.n, 1), -1, np.int32)
+    a = []
+    for s in (side1, side2):
+        a += [_c(s[0], np.uint8), _c(s[1], np.uint8), _c(s[2], np.float64), _c(s[3], np.float32), _c(s[4], np.float32),
+              _c(s[5], np.uint8)]
+    p1 = _c(pose1, np.float64); p2 = _c(pose2, np.float64); R = _c(R12, np.float64); t = _c(t12, np.float64)
+    nf = lib().match2_oracle_search_by_sim3(*V1.args(), *V2.args(), _p(V1.sf), _p(p1), _p(p2), C.c_float(s12), _p(R), _p(t),
+                                            *[_p(x) for x in a], C.c_float(th), _p(m12))
+    return m12[:V1.n], nf
+
+
+def flatten_feature_vector(node_of_feature, order=None):
+    """node id per feature (-1 = not in the vector) -> (node_ids ascending, start, features in insertion order)."""
+    node_of_feature = np.asarray(node_of_feature)
+    idx = np.arange(len(node_of_feature)) if order is None else np.asarray(order)
+    idx = idx[node_of_feature[idx] >= 0]
+    nodes = np.unique(node_of_feature[idx])
+    start = [0]; feats = []
+    for nd in nodes:
+        f = idx[node_of_feature[idx] == nd]
+        feats.extend(f.tolist()); start.append(len(feats))
+    return nodes.astype(np.int32), np.array(start, np.int32), np.array(feats, np.int32)
+
+
+def _fv(fv):
+    nodes, start, feats = (_c(fv[0], np.int32), _c(fv[1], np.int32), _c(np.concatenate([fv[2], [0]]), np.int32))
+    return nodes, start, feats
+
+
+def search_by_bow(mode, desc1, angle1, valid1, fv1, desc2, angle2, valid2, fv2, nn_ratio, check_ori):
+    d1 = _c(desc1, np.uint8); d2 = _c(desc2, np.uint8); a1 = _c(angle1, np.float32); a2 = _c(angle2, np.float32)
+    v1 = _c(valid1, np.uint8); v2 = _c(valid2 if valid2 is not None else np.ones(len(d2)), np.uint8)
+    n1, s1, f1 = _fv(fv1); n2, s2, f2 = _fv(fv2)
+    n_out = len(d2) if mode == 0 else len(d1)
+    match = np.full(max(n_out, 1), -1, np.int32)
+    nm = lib().match2_oracle_search_by_bow(int(mode), _p(d1), _p(a1), len(d1), _p(v1), len(n1), _p(n1), _p(s1), _p(f1),
+                                           _p(d2), _p(a2), len(d2), _p(v2), len(n2), _p(n2), _p(s2), _p(f2),
+                                           C.c_float(nn_ratio), int(check_ori), _p(match))
+    return match[:n_out], nm
+
+
+def search_for_triangulation(kps1, desc1, has1, fv1, kps2, desc2, has2, fv2, F12, Cw, R2w, t2w, K4_2, sf2, sigma2_2,
+                             check_ori):
+    k1 = _c(kps1, KP_DTYPE); k2 = _c(kps2, KP_DTYPE); d1 = _c(desc1, np.uint8); d2 = _c(desc2, np.uint8)
+    h1 = _c(has1, np.uint8); h2 = _c(has2, np.uint8)
+    n1, s1, f1 = _fv(fv1); n2, s2, f2 = _fv(fv2)
+    F = _c(F12, np.float64); c = _c(Cw, np.float64); R = _c(R2w, np.float64); t = _c(t2w, np.float64)
+    K = _c(K4_2, np.float32); sf = _c(sf2, np.float32); sg = _c(sigma2_2, np.float32)
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    nm = lib().match2_oracle_search_for_triangulation(_p(k1), _p(d1), len(k1), _p(h1), len(n1), _p(n1), _p(s1), _p(f1),
+                                                      _p(k2), _p(d2), len(k2), _p(h2), len(n2), _p(n2), _p(s2), _p(f2),
+                                                      _p(F), _p(c), _p(R), _p(t), _p(K), _p(sf), _p(sg), int(check_ori),
+                                                      _p(m12))
+    return m12[:len(k1)], nm
+
+
+def search_for_initialization(kps1, desc1, V2: View, prev_matched, window_size, nn_ratio, check_ori):
+    k1 = _c(kps1, KP_DTYPE); d1 = _c(desc1, np.uint8)
+    prev = _c(prev_matched, np.float32).copy()
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    nm = lib().match2_oracle_search_for_initialization(_p(k1), _p(d1), len(k1), *V2.args(), _p(prev), int(window_size),
+                                                       C.c_float(nn_ratio), int(check_ori), _p(m12))
+    return m12[:len(k1)], nm, prev

@@ -38,3 +38,87 @@ def points_view(last_kps, last_desc, shift_xy, seed, n_levels=8, th_noise=1.0):
         desc[np.arange(n), byte] ^= (1 << bit).astype(np.uint8)
     has_obs = (rng.random(n) < 0.95).astype(np.uint8)
     return in_view, level, view_cos, proj, desc, has_obs
+
+
+# ---------------------------------------------------------------------------------------------------
+# Two keyframes that see the same map points (for the relocalisation / loop / BoW / fuse / Sim3 searches)
+
+def _rot(rv):
+    th = np.linalg.norm(rv)
+    if th < 1e-12:
+        return np.eye(3)
+    k = rv / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+
+
+def make_two_views(n=1200, seed=0, width=1241, height=376, K=synth.KITTI_K, n_levels=8, scale=1.2, n_extra=300,
+                   flip_bits=12, n_nodes=60):
+    """Returns a dict: view 1 / view 2 keypoints + descriptors, the map points (world = camera-1 frame shifted),
+    poses, vocabulary node per feature.  View-2 keypoint j observes point p2[j] (or -1)."""
+    from ceres_mono_orb_slam2_b200 import KP_DTYPE
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = [float(np.float32(v)) for v in K]
+    sf = np.empty(n_levels, np.float32); sf[0] = 1.0
+    for i in range(1, n_levels):
+        sf[i] = np.float32(np.float64(sf[i - 1]) * np.float64(np.float32(scale)))
+    # camera 1
+    R1 = _rot(rng.normal(0, 0.02, 3)); t1 = rng.normal(0, 0.1, 3)
+    R2 = _rot(rng.normal(0, 0.03, 3)) @ R1; t2 = t1 + np.array([0.3, 0.02, 0.1]) + rng.normal(0, 0.02, 3)
+    k1 = np.zeros(n, KP_DTYPE)
+    k1["x"] = rng.uniform(5, width - 5, n).astype(np.float32); k1["y"] = rng.uniform(5, height - 5, n).astype(np.float32)
+    k1["octave"] = np.minimum(rng.geometric(0.35, n) - 1, n_levels - 1); k1["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    k1["size"] = 31 * sf[k1["octave"]]; k1["class_id"] = -1
+    z = rng.uniform(4, 40, n)
+    Xc1 = np.stack([(k1["x"] - cx) / fx * z, (k1["y"] - cy) / fy * z, z], 1)
+    Xw = (Xc1 - t1) @ R1          # R1^T (Xc - t1)
+    Ow1 = -R1.T @ t1; Ow2 = -R2.T @ t2
+    d1 = np.linalg.norm(Xw - Ow1, axis=1)
+    max_d = (d1 * sf[k1["octave"]]).astype(np.float32); min_d = (max_d / sf[-1]).astype(np.float32)
+    normal = (Xw - Ow1) / d1[:, None] + rng.normal(0, 0.05, (n, 3))   # MapPoint::UpdateNormalAndDepth: camera -> point; normal /= np.linalg.norm(normal, axis=1)[:, None]
+    desc1 = rng.integers(0, 256, (n, 32)).astype(np.uint8)
+    mp_desc = desc1.copy()
+    for _ in range(4):
+        mp_desc[np.arange(n), rng.integers(0, 32, n)] ^= (1 << rng.integers(0, 8, n)).astype(np.uint8)
+    # camera 2 observations
+    Xc2 = Xw @ R2.T + t2
+    u2 = fx * Xc2[:, 0] / Xc2[:, 2] + cx + rng.normal(0, 0.8, n); v2 = fy * Xc2[:, 1] / Xc2[:, 2] + cy + rng.normal(0, 0.8, n)
+    seen = (Xc2[:, 2] > 0) & (u2 > 2) & (u2 < width - 2) & (v2 > 2) & (v2 < height - 2) & (rng.random(n) < 0.85)
+    src = np.nonzero(seen)[0]
+    n2 = len(src) + n_extra
+    k2 = np.zeros(n2, KP_DTYPE); p2 = np.full(n2, -1, np.int64)
+    k2["x"][:len(src)] = u2[src]; k2["y"][:len(src)] = v2[src]
+    k2["octave"][:len(src)] = np.clip(k1["octave"][src] + rng.integers(-1, 2, len(src)) * (rng.random(len(src)) < 0.3), 0,
+                                      n_levels - 1)
+    k2["angle"][:len(src)] = (k1["angle"][src] + rng.normal(0, 4, len(src))) % 360
+    p2[:len(src)] = src
+    k2["x"][len(src):] = rng.uniform(5, width - 5, n_extra); k2["y"][len(src):] = rng.uniform(5, height - 5, n_extra)
+    k2["octave"][len(src):] = np.minimum(rng.geometric(0.35, n_extra) - 1, n_levels - 1)
+    k2["angle"][len(src):] = rng.uniform(0, 360, n_extra)
+    k2["size"] = 31 * sf[k2["octave"]]; k2["class_id"] = -1
+    desc2 = rng.integers(0, 256, (n2, 32)).astype(np.uint8)
+    d = desc1[src].copy()
+    nflip = rng.integers(0, flip_bits + 1, len(src))
+    for b in range(flip_bits):
+        on = nflip > b
+        d[np.nonzero(on)[0], rng.integers(0, 32, on.sum())] ^= (1 << rng.integers(0, 8, on.sum())).astype(np.uint8)
+    desc2[:len(src)] = d
+    perm = rng.permutation(n2)
+    k2, desc2, p2 = k2[perm], desc2[perm], p2[perm]
+    # vocabulary nodes: matching features mostly share a node
+    node1 = rng.integers(0, n_nodes, n) * 7 + 3
+    node2 = np.where(p2 >= 0, node1[np.maximum(p2, 0)], rng.integers(0, n_nodes, n2) * 7 + 3)
+    stray = rng.random(n2) < 0.1
+    node2[stray] = rng.integers(0, n_nodes, stray.sum()) * 7 + 3
+    return dict(width=width, height=height, K=K, sf=sf, scale=scale, n_levels=n_levels, k1=k1, desc1=desc1, k2=k2,
+                desc2=desc2, p2=p2, Xw=Xw, normal=normal, min_d=min_d, max_d=max_d, mp_desc=mp_desc, R1=R1, t1=t1, R2=R2,
+                t2=t2, Ow1=Ow1, Ow2=Ow2, node1=node1, node2=node2, rng=rng)
+
+
+def pose15(R, t):
+    return np.concatenate([R.reshape(-1), t, -R.T @ t])
+
+
+def T44(R, t, s=1.0):
+    T = np.eye(4); T[:3, :3] = s * R; T[:3, 3] = s * t if s != 1.0 else t
+    return T
