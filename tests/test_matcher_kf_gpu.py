@@ -45,7 +45,7 @@ def test_search_by_projection_reloc(request, matcher, scn, check_ori, th, orb_di
     m, nm, hp = kc.gpu_reloc(matcher, S, c)
     matcher.check_ori = True
     assert nm == onm and np.array_equal(m, om) and np.array_equal(hp[:len(om)], ohp[:len(om)])
-    assert onm > 200
+    assert onm > (200 if scn == "S" else 50)
 
 
 @pytest.mark.parametrize("scn", ["S", "S_dense"])
@@ -55,7 +55,7 @@ def test_search_by_projection_sim3(request, matcher, scn):
     oa, onm, omt = kc.oracle_proj_sim3(S, c)
     a, nm, mt = kc.gpu_proj_sim3(matcher, S, c)
     assert nm == onm and np.array_equal(a, oa) and np.array_equal(mt[:len(oa)], omt[:len(oa)])
-    assert onm > 200
+    assert onm > (200 if scn == "S" else 50)
 
 
 @pytest.mark.parametrize("scn", ["S", "S_dense"])
@@ -66,7 +66,7 @@ def test_fuse(request, matcher, scn, sim3):
     obi, obd, onf = kc.oracle_fuse(S, c, sim3)
     bi, bd, nf = kc.gpu_fuse(matcher, S, c, sim3)
     assert nf == onf and np.array_equal(bi, obi) and np.array_equal(bd, obd)
-    assert onf > 100
+    assert onf > (100 if scn == "S" else 20)
 
 
 @pytest.mark.parametrize("scn,s12", [("S", 1.0), ("S_dense", 1.0), ("S", 1.03)])
@@ -76,7 +76,7 @@ def test_search_by_sim3(request, matcher, scn, s12):
     om, onf = kc.oracle_sim3(S, c)
     m, nf = kc.gpu_sim3(matcher, S, c)
     assert nf == onf and np.array_equal(m, om)
-    assert onf > 50
+    assert onf > (50 if scn == "S" else 5)
 
 
 @pytest.mark.parametrize("scn", ["S", "S_dense"])
@@ -111,7 +111,7 @@ def test_search_for_initialization(request, matcher, scn, window):
     m, nm, prev = kc.gpu_init(matcher, S, c, window=window)
     matcher.nnratio = 0.75
     assert nm == onm and np.array_equal(m, om) and np.array_equal(prev, oprev)
-    assert onm > 20
+    assert onm > (20 if scn == "S" else 3)
 
 
 def test_empty_inputs_and_errors(matcher):
