@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../cmos_b200.h"
@@ -41,6 +42,7 @@ struct FrameView {
   double Tcw[16];                           // row-major Tcw_
   std::vector<int32_t> map_points;          // per keypoint: map-point id or -1  (F.map_points_)
   std::vector<uint8_t> claimed;             // per keypoint: map_points_[i] && Observations() > 0
+  cmos_feature_vector feature_vector = {0, nullptr, nullptr, nullptr};   // F.feature_vector_ (SearchByBoW)
 };
 
 // The last frame as SearchByProjection(CurrentFrame, LastFrame, th) reads it (ORBmatcher.cc:1176-1200).
@@ -61,6 +63,43 @@ struct MapPointsView {
   const float* proj_xy = nullptr;           // track_proj_x_, track_proj_y_
   const uint8_t* descriptors = nullptr;     // n x 32
   const uint8_t* has_obs = nullptr;         // Observations() > 0
+};
+
+// A KeyFrame (or a Frame used as one side of a two-view search) as the remaining searches read it: keypoints,
+// descriptors, per-keypoint map point data (GetMapPointMatches()), pose, BoW feature vector, scale tables.
+struct KeyFrameView {
+  cmos_camera camera;                       // the Frame's bounds; the KeyFrame's int truncation is applied inside
+  bool is_keyframe = true;
+  const KeyPoint* undistort_keypoints = nullptr;
+  const uint8_t* descriptors = nullptr;     // N x 32
+  int N = 0;
+  const uint8_t* mp_valid = nullptr;        // per keypoint: pMP && !pMP->isBad()
+  const uint8_t* mp_present = nullptr;      // per keypoint: GetMapPoint(i) != NULL (SearchForTriangulation)
+  const double* mp_world_pos = nullptr;     // N x 3
+  const float* mp_min_distance = nullptr;   // raw min_distance_ / max_distance_ (0.8 / 1.2 applied inside)
+  const float* mp_max_distance = nullptr;
+  const uint8_t* mp_descriptors = nullptr;  // N x 32, MapPoint::GetDescriptor()
+  cmos_feature_vector feature_vector = {0, nullptr, nullptr, nullptr};
+  double Rcw[9], tcw[3], Ow[3];             // GetRotation(), GetTranslation(), GetCameraCenter()
+  const float* level_sigma2 = nullptr;      // level_sigma2s_
+  const float* inv_level_sigma2 = nullptr;  // inv_level_sigma2s_
+};
+
+// Candidate map points of Fuse / SearchByProjection(KeyFrame*, Scw, ...).
+struct PointsView {
+  int n = 0;
+  const uint8_t* skip = nullptr;            // the reference's "continue" predicates that do not depend on the search
+  const double* world_pos = nullptr;        // n x 3
+  const double* normal = nullptr;           // n x 3, GetNormal()
+  const float* min_distance = nullptr;
+  const float* max_distance = nullptr;
+  const uint8_t* descriptors = nullptr;     // n x 32
+};
+
+// Fuse returns decisions: point p should be fused with keypoint best_idx[p] (or -1).  The caller walks them in
+// order and applies Replace / AddObservation exactly as ORBmatcher.cc:822-836 / 938-947.
+struct FuseDecisions {
+  std::vector<int32_t> best_idx, best_dist;
 };
 
 // PoseOptimization(Frame*): the matched keypoints of one frame.

@@ -45,6 +45,46 @@ int main() {
     const int nm = matcher.SearchByProjection(F, L, 15.f);
     std::printf("SearchByProjection(cur,last): %d matches of %d\n", nm, F.N);
     if (nm < F.N / 2) return 3;
+    // the keyframe searches: BoW of the frame against itself (every feature in node = octave), Fuse decisions
+    {
+      KeyFrameView KF;
+      KF.camera = F.camera; KF.undistort_keypoints = kps.data(); KF.descriptors = desc.data.data(); KF.N = (int)kps.size();
+      std::vector<uint8_t> valid(kps.size(), 1);
+      KF.mp_valid = valid.data(); KF.mp_present = valid.data(); KF.mp_world_pos = X.data(); KF.mp_descriptors = desc.data.data();
+      std::vector<float> mind(kps.size()), maxd(kps.size()), sig(sf.size()), isig(sf.size());
+      for (size_t i = 0; i < kps.size(); i++) { maxd[i] = 10.0f * sf[kps[i].octave]; mind[i] = maxd[i] / sf.back(); }
+      for (size_t l = 0; l < sf.size(); l++) { sig[l] = sf[l] * sf[l]; isig[l] = 1.0f / sig[l]; }
+      KF.mp_min_distance = mind.data(); KF.mp_max_distance = maxd.data(); KF.level_sigma2 = sig.data(); KF.inv_level_sigma2 = isig.data();
+      for (int i = 0; i < 9; i++) KF.Rcw[i] = (i % 4 == 0) ? 1.0 : 0.0;
+      for (int i = 0; i < 3; i++) { KF.tcw[i] = 0.0; KF.Ow[i] = 0.0; }
+      std::vector<int32_t> nodes, start(1, 0), feats;
+      for (int l = 0; l < (int)sf.size(); l++) {
+        for (size_t i = 0; i < kps.size(); i++) if (kps[i].octave == l) feats.push_back((int32_t)i);
+        if ((int)feats.size() > start.back()) { nodes.push_back(l); start.push_back((int32_t)feats.size()); }
+      }
+      KF.feature_vector.n_nodes = (int32_t)nodes.size(); KF.feature_vector.node_ids = nodes.data();
+      KF.feature_vector.start = start.data(); KF.feature_vector.features = feats.data();
+      std::vector<int32_t> m12;
+      const int nb = matcher.SearchByBoW(KF, KF, m12);
+      int self = 0;
+      for (size_t i = 0; i < m12.size(); i++) self += m12[i] == (int)i;
+      std::printf("SearchByBoW(KF,KF): %d matches, %d onto themselves\n", nb, self);
+      if (nb < F.N / 2 || self != nb) return 5;
+      std::vector<double> normal(kps.size() * 3);
+      for (size_t i = 0; i < kps.size(); i++) {
+        const double n = std::sqrt(X[3 * i] * X[3 * i] + X[3 * i + 1] * X[3 * i + 1] + X[3 * i + 2] * X[3 * i + 2]);
+        for (int k = 0; k < 3; k++) normal[3 * i + k] = X[3 * i + k] / n;
+      }
+      std::vector<uint8_t> skip(kps.size(), 0);
+      PointsView pts; pts.n = (int)kps.size(); pts.skip = skip.data(); pts.world_pos = X.data(); pts.normal = normal.data();
+      pts.min_distance = mind.data(); pts.max_distance = maxd.data(); pts.descriptors = desc.data.data();
+      FuseDecisions fd;
+      const int nf = matcher.Fuse(KF, pts, 3.0f, fd);
+      int own = 0;
+      for (size_t i = 0; i < fd.best_idx.size(); i++) own += fd.best_idx[i] == (int)i;
+      std::printf("Fuse: %d decisions, %d onto the point's own keypoint\n", nf, own);
+      if (nf < F.N / 2 || own < nf * 9 / 10) return 6;
+    }
     // pose optimisation on exact correspondences perturbed by a small translation
     FramePoseView P;
     const double pose0[7] = {0.05, -0.03, 0.02, 0, 0, 0, 1};
