@@ -269,7 +269,7 @@ def run_reference(args):
         "note": "the reference's own C++ (OpenCV + Ceres) cannot be built in this image; this arm times the CPU "
                 "restatement in oracle/ (bit-identical to OpenCV 4.13 semantics)",
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -465,12 +465,45 @@ def run_b200(args):
             line["ba"] = ba_bench.run(local_rank, world, args)
             if world == 1 and not args.no_cpu:
                 line["ba"]["cpu_baseline"] = cpu_ba_baseline()
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     elif not args.no_ba:
         from ceres_mono_orb_slam2_b200 import ba_bench
         ba_bench.run(local_rank, world, args)
     if world > 1:
         dist.destroy_process_group()
+
+
+class _QuietStdout:
+    """Libraries loaded during the run (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on
+    stdout, so fd 1 points at stderr while the benchmark runs and is restored for the final print."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text: str):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        print(text, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
+_OUT = None
+
+
+def emit(text: str):
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text, flush=True)
 
 
 def main():
@@ -487,10 +520,14 @@ def main():
     ap.add_argument("--no-global", action="store_true", help="skip the 1000-keyframe global BA case")
     ap.add_argument("--global-iters", type=int, default=10, help="LM iterations of the global BA case")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    global _OUT
+    with _QuietStdout() as q:
+        _OUT = q
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+        _OUT = None
 
 
 if __name__ == "__main__":

@@ -1068,7 +1068,7 @@ struct NcclApi {
   }
 };
 NcclApi g_nccl;
-constexpr int kNcclDouble = 8, kNcclSum = 0, kNcclMax = 2;   // ncclFloat64, ncclSum, ncclMax (nccl.h)
+constexpr int kNcclDouble = 8, kNcclUint8 = 1, kNcclSum = 0, kNcclMax = 2;   // ncclFloat64, ncclUint8, ncclSum, ncclMax (nccl.h)
 }  // namespace
 
 struct cmos_ba {
@@ -1431,12 +1431,27 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
     }
   CMOS_REQUIRE(n_pairs <= h->cap_pairs, "%zu co-observation pairs exceed the handle's capacity %zu (raise max_pairs_per_obs)",
                n_pairs, h->cap_pairs);
+  // Sharded solve: the reduced camera system is summed block by block over the ranks, so every rank needs the
+  // SAME block list — the union of the co-visibility patterns (a rank's contiguous point range only covers part of
+  // the trajectory).  One byte-mask all-reduce (max); blocks without local pairs simply contribute zero.
+  std::vector<uint8_t> present((size_t)Kv * Kv, 0);
+  for (size_t i = 0; i < present.size(); i++) present[i] = table[i] > 0;
+  if (h->n_ranks > 1 && Kv > 0) {
+    uint8_t* d_mask = nullptr;
+    CMOS_CUDA_OK(cudaMalloc(&d_mask, present.size()));
+    CMOS_CUDA_OK(cudaMemcpyAsync(d_mask, present.data(), present.size(), cudaMemcpyHostToDevice, h->stream));
+    const int nrc = g_nccl.AllReduce(d_mask, d_mask, present.size(), kNcclUint8, kNcclMax, h->comm, h->stream);
+    if (nrc != 0) { cudaFree(d_mask); set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString(nrc)); return CMOS_ERR_CUDA; }
+    CMOS_CUDA_OK(cudaMemcpyAsync(present.data(), d_mask, present.size(), cudaMemcpyDeviceToHost, h->stream));
+    CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_mask);
+  }
   std::vector<int> blk_a, blk_b, blk_start;
   blk_start.push_back(0);
   for (int a = 0; a < Kv; a++)
     for (int b = a; b < Kv; b++) {
       int& t = table[(size_t)a * Kv + b];
-      if (t > 0) {
+      if (t > 0 || (a != b && present[(size_t)a * Kv + b])) {
         blk_a.push_back(a); blk_b.push_back(b);
         blk_start.push_back(blk_start.back() + t);
         t = (int)blk_a.size();      // 1-based block id

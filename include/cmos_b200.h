@@ -445,7 +445,9 @@ int cmos_ba_bundle_adjustment(cmos_ba_t h, int32_t n_cams, double* cams, const u
  * cmos_ba_set_problem, then every rank calls cmos_ba_run_global with the same arguments.  Per LM iteration the
  * ranks exchange, with NCCL all-reduces enqueued on the solve's stream: the keyframe blocks H_cc/g_c, the partial
  * reduced camera system S + rhs (the one large message), and three short vectors of scalars (cost, norms, step
- * statistics).  The reduced system is then factorised redundantly on every rank, so keyframe poses stay
+ * statistics).  Once the communicator exists cmos_ba_set_problem is collective too: one byte-mask all-reduce makes
+ * every rank adopt the union of the ranks' co-visibility block patterns, so the per-block sums line up.
+ * The reduced system is then factorised redundantly on every rank, so keyframe poses stay
  * replicated bit for bit and the points never leave their rank.  NCCL is bound with dlopen("libnccl.so.2").
  *   cmos_ba_comm_unique_id: rank 0 creates the 128-byte NCCL id; the caller ships it to the other ranks
  *   cmos_ba_comm_init:      collective over all ranks; after it the handle's solves are sharded */

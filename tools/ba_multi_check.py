@@ -16,8 +16,13 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 K4 = np.array(synth.KITTI_K, np.float32)
 ok = True
-for n_cams, n_points, window, iters in [(12, 400, None, 8), (60, 2500, 6, 8)]:
-    G = synth.make_ba_problem(n_cams, n_points, 5, seed=31 + n_cams, window=window)
+# the third case takes the blocked (out-of-shared-memory) Cholesky path and has co-visibility blocks that only one
+# rank's points touch: the ranks must agree on the union block list
+for n_cams, n_points, window, iters in [(12, 400, None, 8), (60, 2500, 6, 8), (150, 3000, 10, 6)]:
+    if n_cams >= 100:
+        G = synth.make_ba_problem_fast(n_cams, n_points, 5, seed=31 + n_cams, window=window)
+    else:
+        G = synth.make_ba_problem(n_cams, n_points, 5, seed=31 + n_cams, window=window)
     opt = CeresOptimizer(max_cams=n_cams, max_points=n_points, max_obs=len(G["obs_cam"]), device=local)
     opt.comm_init(world, rank, dev)
     cams, pts, s = opt.GlobalBundleAdjustemntSharded(G["poses"], G["fixed"], G["points"], G["obs_cam"], G["obs_pt"], G["uv"],
