@@ -865,39 +865,47 @@ __global__ void __launch_bounds__(256) k_scatter_S(BaDev d) {
 // The rhs is carried as row n (so the forward substitution is part of the factorisation); the inverses of
 // the diagonal panels are kept so that the panel solve and the back substitution are plain products.
 // -------------------------------------------------------------------------------------------------
-// factor the kb x kb diagonal block at (k0,k0) in place and store inv(L11) (lower) into Linv[panel]
+// factor the kb x kb diagonal block at (k0,k0) in place and store inv(L11) (lower) into Linv[panel].
+// Right-looking on the UNSCALED columns — A[i][k] -= A[i][j] A[k][j] / A[j][j] needs one barrier per column and no
+// square root on the critical path; column j is scaled by rsqrt(A[j][j]) once, at the end.
 __global__ void __launch_bounds__(256) k_potrf_diag(BaDev d, int k0, int kb, double* Linv) {
   extern __shared__ double dyn_smem[];
   double (*A)[kNB + 1] = (double (*)[kNB + 1])dyn_smem;
   double (*Li)[kNB + 1] = (double (*)[kNB + 1])(dyn_smem + kNB * (kNB + 1));
-  __shared__ int s_fail;
   LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
   const int n = d.nc, tid = threadIdx.x;
-  if (tid == 0) s_fail = 0;
   for (int idx = tid; idx < kb * kb; idx += 256) {
     const int i = idx / kb, k = idx - i * kb;
     A[i][k] = k <= i ? d.S[(size_t)(k0 + i) * n + k0 + k] : 0.0;
     Li[i][k] = 0.0;
   }
   __syncthreads();
+  bool fail = false;
   for (int j = 0; j < kb; j++) {
-    const double djj = A[j][j];
-    if (!(djj > 0.0) || !isfinite(djj)) { if (tid == 0) s_fail = 1; break; }
-    const double ljj = sqrt(djj);
-    __syncthreads();
-    for (int i = j + tid; i < kb; i += 256) { if (i == j) A[j][j] = ljj; else A[i][j] /= ljj; }
-    __syncthreads();
+    const double djj = A[j][j];                 // final: every update of column j happened before the last barrier
+    if (!(djj > 0.0) || !isfinite(djj)) { fail = true; break; }    // uniform over the CTA
+    const double inv = 1.0 / djj;
     const int m = kb - j - 1;
-    for (int idx = tid; idx < m * m; idx += 256) {
-      const int ii = idx / m, kk = idx - ii * m;
+    // lower triangle of the trailing m x m block: element e -> (ii, kk) with kk <= ii
+    for (int e = tid; e < m * (m + 1) / 2; e += 256) {
+      int ii = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while ((ii + 1) * (ii + 2) / 2 <= e) ii++;
+      while (ii * (ii + 1) / 2 > e) ii--;
+      const int kk = e - ii * (ii + 1) / 2;
       const int i = j + 1 + ii, k = j + 1 + kk;
-      if (k <= i) A[i][k] -= A[i][j] * A[k][j];
+      A[i][k] -= A[i][j] * A[k][j] * inv;
     }
     __syncthreads();
   }
+  if (fail) { if (tid == 0) st.solve_failed = 1; return; }
+  for (int idx = tid; idx < kb * kb; idx += 256) {     // L[i][j] = A[i][j] / sqrt(A[j][j]); the diagonal is only read here
+    const int i = idx / kb, j = idx - i * kb;
+    if (j < i) A[i][j] *= rsqrt(A[j][j]);
+  }
   __syncthreads();
-  if (s_fail) { if (tid == 0) st.solve_failed = 1; return; }
+  if (tid < kb) A[tid][tid] = sqrt(A[tid][tid]);
+  __syncthreads();
   // inverse of the lower-triangular factor: column c by forward substitution, one thread per column
   if (tid < kb) {
     const int c = tid;
@@ -916,7 +924,11 @@ __global__ void __launch_bounds__(256) k_potrf_diag(BaDev d, int k0, int kb, dou
 }
 
 // panel solve: rows i > k0+kb (and the rhs row): L21[i][:] = A21[i][:] * inv(L11)'  -> L21[i][c] = sum_k A21[i][k] Linv[c][k]
-__global__ void __launch_bounds__(256) k_trsm_panel(BaDev d, int k0, int kb, const double* __restrict__ Linv) {
+// Only the ACTIVE 64-row tiles of the panel are touched: tiles (relative to the first row below the panel) whose
+// rows reach into or before the panel's columns — the row envelope of the reduced system, inside which all fill
+// of the factorisation stays.  For a windowed co-visibility graph that is a handful of tiles per panel.
+__global__ void __launch_bounds__(256) k_trsm_panel(BaDev d, int k0, int kb, const double* __restrict__ Linv,
+                                                    const int* __restrict__ tiles) {
   extern __shared__ double dyn_smem[];
   double (*Li)[kNB + 1] = (double (*)[kNB + 1])dyn_smem;
   double (*Arow)[kNB + 1] = (double (*)[kNB + 1])(dyn_smem + kNB * (kNB + 1));
@@ -925,7 +937,7 @@ __global__ void __launch_bounds__(256) k_trsm_panel(BaDev d, int k0, int kb, con
   const int n = d.nc, tid = threadIdx.x;
   const double* Lp = Linv + (size_t)(k0 / kNB) * kNB * kNB;
   for (int idx = tid; idx < kNB * kNB; idx += 256) Li[idx / kNB][idx % kNB] = Lp[idx];
-  const int row0 = k0 + kb + blockIdx.x * 32;   // rows row0..row0+31; logical row n = rhs
+  const int row0 = k0 + kb + tiles[blockIdx.x >> 1] * 64 + (blockIdx.x & 1) * 32;   // rows row0..row0+31; logical row n = rhs
   for (int idx = tid; idx < 32 * kb; idx += 256) {
     const int r = idx / kb, k = idx - r * kb;
     const int i = row0 + r;
@@ -946,7 +958,7 @@ __global__ void __launch_bounds__(256) k_trsm_panel(BaDev d, int k0, int kb, con
 }
 
 // trailing update: A22 -= L21 L21' on 64x64 tiles of the lower triangle (and the rhs row), 256 threads, 4x4 per thread
-__global__ void __launch_bounds__(256) k_syrk_tile(BaDev d, int k0, int kb) {
+__global__ void __launch_bounds__(256) k_syrk_tile(BaDev d, int k0, int kb, const int* __restrict__ tiles) {
   extern __shared__ double dyn_smem[];
   double (*As)[64 + 1] = (double (*)[64 + 1])dyn_smem;                      // [k][i]
   double (*Bs)[64 + 1] = (double (*)[64 + 1])(dyn_smem + kNB * (64 + 1));   // [k][j]
@@ -959,7 +971,7 @@ __global__ void __launch_bounds__(256) k_syrk_tile(BaDev d, int k0, int kb) {
   while ((bi + 1) * (bi + 2) / 2 <= (int)blockIdx.x) bi++;
   while (bi * (bi + 1) / 2 > (int)blockIdx.x) bi--;
   const int bj = blockIdx.x - bi * (bi + 1) / 2;
-  const int i0 = t0 + bi * 64, j0 = t0 + bj * 64;
+  const int i0 = t0 + tiles[bi] * 64, j0 = t0 + tiles[bj] * 64;     // bi, bj index the panel's active-tile list
   for (int idx = tid; idx < 64 * kb; idx += 256) {
     const int r = idx / kb, k = idx - r * kb;
     const int i = i0 + r, j = j0 + r;
@@ -994,7 +1006,7 @@ __global__ void __launch_bounds__(256) k_syrk_tile(BaDev d, int k0, int kb) {
 }
 
 // back substitution, panel by panel from the last: x_k = inv(L_kk)' y_k, then y_i -= L_ki' x_k for i < k0
-__global__ void __launch_bounds__(256) k_backsolve_panel(BaDev d, int k0, int kb, const double* __restrict__ Linv) {
+__global__ void __launch_bounds__(256) k_backsolve_panel(BaDev d, int k0, int kb, const double* __restrict__ Linv, int c_begin) {
   __shared__ double xk[kNB];
   LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
@@ -1007,7 +1019,7 @@ __global__ void __launch_bounds__(256) k_backsolve_panel(BaDev d, int k0, int kb
   }
   __syncthreads();
   if (blockIdx.x == 0 && tid < kb) d.yc[k0 + tid] = xk[tid];
-  const int c = blockIdx.x * 256 + tid;   // columns c < k0
+  const int c = c_begin + blockIdx.x * 256 + tid;   // columns c_begin <= c < k0 (the panel rows are zero left of c_begin)
   if (c < k0) {
     double s = 0.0;
     for (int r = 0; r < kb; r++) s += d.S[(size_t)(k0 + r) * n + c] * xk[r];
@@ -1093,6 +1105,9 @@ struct cmos_ba {
   float* d_o_w = nullptr;
   uint8_t *d_o_mode = nullptr, *d_cam_flags = nullptr, *d_erase = nullptr;
   double* d_Linv = nullptr;
+  int* d_pan_tiles = nullptr;               // active row tiles of every panel of the blocked factorisation
+  std::vector<int> pan_start, pan_first_col; // [n_panels + 1], [n_panels]
+  size_t cap_pan_tiles = 0;
   double* d_trace = nullptr;       // [2][trace_rows][8]
   int trace_rows = 0;
   cmos_ba_summary* d_summaries = nullptr;   // [2]
@@ -1197,21 +1212,22 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
         CMOS_CUDA_OK(cudaMemsetAsync(d.S, 0, (size_t)n * n * sizeof(double), st));
         k_scatter_S<<<(d.n_blocks * 36 + 255) / 256, 256, 0, st>>>(d);
         h->launches++;
-        for (int k0 = 0; k0 < n; k0 += kNB) {
+        for (int k0 = 0, p = 0; k0 < n; k0 += kNB, p++) {
           const int kb = std::min(kNB, n - k0);
           k_potrf_diag<<<1, 256, kPanelSmem, st>>>(d, k0, kb, h->d_Linv);
-          const int rows_below = n + 1 - (k0 + kb);   // incl. the rhs row
-          if (rows_below > 0) {
-            k_trsm_panel<<<(rows_below + 31) / 32, 256, kPanelSmem, st>>>(d, k0, kb, h->d_Linv);
-            const int nt = (rows_below + 63) / 64;
-            k_syrk_tile<<<nt * (nt + 1) / 2, 256, kPanelSmem, st>>>(d, k0, kb);
+          const int na = h->pan_start[p + 1] - h->pan_start[p];   // active tiles below this panel (rhs row included)
+          if (na > 0) {
+            const int* tiles = h->d_pan_tiles + h->pan_start[p];
+            k_trsm_panel<<<2 * na, 256, kPanelSmem, st>>>(d, k0, kb, h->d_Linv, tiles);
+            k_syrk_tile<<<na * (na + 1) / 2, 256, kPanelSmem, st>>>(d, k0, kb, tiles);
             h->launches += 2;
           }
           h->launches++;
         }
         for (int k0 = ((n - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {
           const int kb = std::min(kNB, n - k0);
-          k_backsolve_panel<<<std::max(1, (k0 + 255) / 256), 256, 0, st>>>(d, k0, kb, h->d_Linv);
+          const int c0 = std::min(h->pan_first_col[k0 / kNB], k0);
+          k_backsolve_panel<<<std::max(1, (k0 - c0 + 255) / 256), 256, 0, st>>>(d, k0, kb, h->d_Linv, c0);
           h->launches++;
         }
         k_cam_candidates<<<(d.K + 255) / 256, 256, 0, st>>>(d);
@@ -1262,6 +1278,7 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
   h->cap_pairs = N * pairs_per_obs;
   h->cap_blocks = std::min<size_t>(K * (K + 1) / 2, h->cap_pairs) + 1;
   h->cap_S = (6 * K) * (6 * K);
+  { const size_t np = (6 * K + kNB) / kNB + 2; h->cap_pan_tiles = np * np; }
   h->trace_rows = 256;
   bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
   BaDev& d = h->d;
@@ -1279,7 +1296,7 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
        alloc(&h->d_var_cam, K) && alloc(&h->d_red, 8) && alloc(&h->d_Sblk, h->cap_blocks * 36 + 6 * K + 8) &&
        alloc(&d.scale_c, 6 * K) && alloc(&d.S, h->cap_S) &&
        alloc(&d.yc, 6 * K + 8) && alloc(&d.part, 6 * nlb + 4 * K + 16) && alloc(&d.st, 1) &&
-       alloc(&h->d_Linv, ((6 * K + kNB - 1) / kNB) * kNB * kNB) && alloc(&h->d_trace, 2 * (size_t)h->trace_rows * kTraceCols) &&
+       alloc(&h->d_Linv, ((6 * K + kNB - 1) / kNB) * kNB * kNB) && alloc(&h->d_pan_tiles, h->cap_pan_tiles) && alloc(&h->d_trace, 2 * (size_t)h->trace_rows * kTraceCols) &&
        alloc(&h->d_summaries, 2);
   const size_t PB = std::max(params->max_pose_batch, 1), PC = std::max(params->max_pose_corr, 1);
   ok = ok && alloc(&h->dp_pose, 7 * PB) && alloc(&h->dp_xw, 3 * PB * PC) && alloc(&h->dp_uv, 2 * PB * PC) &&
@@ -1308,7 +1325,7 @@ int cmos_ba_destroy(cmos_ba_t h) {
                   h->d_o_cam, h->d_o_cv, h->d_o_pt, h->d_pt_start, h->d_cam_start, h->d_cam_obs, h->d_blk_a, h->d_blk_b,
                   h->d_blk_start, h->d_pair_a, h->d_pair_b, h->d_perm, h->d_o_uv, h->d_o_w, h->d_o_mode, h->d_cam_flags,
                   h->d_erase, d.Jc, d.Jp, d.res, d.Hpp, d.gp, d.Hinv, d.tp, d.scale_p, h->d_HG, h->d_var_cam, h->d_red, h->d_Sblk, d.scale_c, d.S,
-                  d.yc, d.part, d.st, h->d_Linv, h->d_trace, h->d_summaries, h->dp_pose, h->dp_xw, h->dp_uv, h->dp_w,
+                  d.yc, d.part, d.st, h->d_Linv, h->d_pan_tiles, h->d_trace, h->d_summaries, h->dp_pose, h->dp_xw, h->dp_uv, h->dp_w,
                   h->dp_n, h->dp_inl, h->dp_out, h->dp_sum, h->dp_trace};
   for (void* b : bufs)
     if (b) cudaFree(b);
@@ -1462,6 +1479,36 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
       }
     }
   const int nb = (int)blk_a.size();
+  // Row envelope of the reduced system for the blocked factorisation (systems too large for one CTA): per panel of
+  // kNB columns the 64-row tiles below it (relative to the first row under the panel) that have an entry in or left
+  // of the panel.  Fill stays inside the row envelope, so TRSM / SYRK only visit these tiles.  The rhs row (row n) is
+  // dense.
+  h->pan_start.assign(1, 0);
+  h->pan_first_col.clear();
+  if (6 * Kv > kSmallMaxN) {
+    const int n = 6 * Kv;
+    std::vector<int> first_blk(Kv);
+    for (int b = 0; b < Kv; b++) first_blk[b] = b;
+    for (int i = 0; i < nb; i++) first_blk[blk_b[i]] = std::min(first_blk[blk_b[i]], blk_a[i]);
+    std::vector<int> tiles;
+    for (int k0 = 0; k0 < n; k0 += kNB) {
+      const int kb = std::min(kNB, n - k0), t0 = k0 + kb;
+      int fc = k0;
+      for (int r = k0; r < k0 + kb; r++) fc = std::min(fc, 6 * first_blk[r / 6]);
+      h->pan_first_col.push_back(fc);
+      for (int t = 0; t0 + 64 * t <= n; t++) {
+        const int r0 = t0 + 64 * t, r1 = std::min(r0 + 63, n);
+        bool active = r1 == n;                                   // the rhs row
+        for (int r = r0; r <= std::min(r1, n - 1) && !active; r += 6 - r % 6) active = 6 * first_blk[r / 6] < t0;
+        if (active) tiles.push_back(t);
+      }
+      h->pan_start.push_back((int)tiles.size());
+    }
+    CMOS_REQUIRE(tiles.size() <= h->cap_pan_tiles, "panel tile list %zu exceeds capacity %zu", tiles.size(), h->cap_pan_tiles);
+    if (!tiles.empty())
+      CMOS_CUDA_OK(cudaMemcpyAsync(h->d_pan_tiles, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));
+  }
   CMOS_REQUIRE((size_t)nb <= h->cap_blocks, "%d reduced-system blocks exceed the handle's capacity %zu", nb, h->cap_blocks);
   std::vector<int> pair_a(std::max<size_t>(n_pairs, 1)), pair_b(std::max<size_t>(n_pairs, 1));
   {
