@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -593,7 +594,7 @@ __device__ void cam_candidate(const BaDev& d, const LmState& st, int cam) {
 // one warp, then the candidate keyframe poses.
 constexpr int kPB = 6;
 __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
-  extern __shared__ double smem_d[];
+  extern __shared__ __align__(16) double smem_d[];
   LmState& st = *d.st;
   if (st.done) return;
   const int n = d.nc, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = kSolveThreads / 32;
@@ -1027,6 +1028,293 @@ __global__ void __launch_bounds__(256) k_backsolve_panel(BaDev d, int k0, int kb
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Banded reduced systems (GlobalBundleAdjustemnt over a windowed co-visibility graph: keyframes a, b share points only
+// when |a - b| <= W): ONE persistent CTA walks down the block columns with the (W+1) x (W+1)-block active window of
+// the trailing matrix in shared memory, addressed circularly (block b lives in slot b mod (W+1), so the block row
+// that enters when column j retires takes column j's slots).  Per block column: 6x6 diagonal factor in the registers
+// of one thread, the <= W block rows below solve against it, rank-6 update of the window, the rhs rides along
+// (forward substitution), the L block column goes to HBM for the back substitution at the end.  No dense S, no
+// memset, one launch per LM iteration instead of ~380.
+struct BandArgs {
+  int W;                    // block half-bandwidth
+  const int* band_blk;      // [Kv][W+1]: id of block (b - off, b), or -1
+  double* Lcol;             // [Kv][(W+1)*6][6] L block columns (row slot-major), reuses the dense-S allocation
+};
+constexpr int kBandThreads = 512;
+constexpr int kBandMaxW = 24;
+inline size_t band_smem_bytes(int W) {
+  const size_t NW = 6 * (size_t)(W + 1);
+  return (NW * (NW + 1) + NW * 6 + NW) * sizeof(double) + (size_t)(W * (W + 1) / 2 + 4) * sizeof(uint16_t);
+}
+
+// 6x6 Cholesky of the block at window slot sj (lower triangle in Wm) + forward substitution of its rhs block, in the
+// registers of the calling thread.  Leaves L11 in s_D, 1/diag in s_rd, y in s_y; returns false if not positive definite.
+__device__ __forceinline__ bool band_diag(const double* Wm, int ld, int sj, const double* r6, double (*s_D)[7], double* s_rd,
+                                          double* s_y) {
+  double A[6][6];
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+#pragma unroll
+    for (int c = 0; c <= r; c++) A[r][c] = Wm[(size_t)(sj + r) * ld + sj + c];
+  bool ok = true;
+#pragma unroll
+  for (int jj = 0; jj < 6; jj++) {
+    const double djj = A[jj][jj];
+    if (!(djj > 0.0) || !isfinite(djj)) ok = false;
+    const double inv = rsqrt(djj);
+    A[jj][jj] = djj * inv;
+    s_rd[jj] = inv;
+#pragma unroll
+    for (int r = jj + 1; r < 6; r++) A[r][jj] *= inv;
+#pragma unroll
+    for (int c = jj + 1; c < 6; c++)
+#pragma unroll
+      for (int r = c; r < 6; r++) A[r][c] -= A[r][jj] * A[c][jj];
+  }
+  double y[6];
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    double v = r6[r];
+#pragma unroll
+    for (int q = 0; q < r; q++) v -= A[r][q] * y[q];
+    y[r] = v * s_rd[r];
+    s_y[r] = y[r];
+  }
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+#pragma unroll
+    for (int c = 0; c < 6; c++) s_D[r][c] = c <= r ? A[r][c] : 0.0;
+  return ok;
+}
+
+__global__ void __launch_bounds__(kBandThreads) k_solve_band(BaDev d, BandArgs ba) {
+  extern __shared__ __align__(16) double smem_d[];
+  LmState& st = *d.st;
+  if (st.done) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Kv = d.Kv, W = ba.W, NB = W + 1, NW = 6 * NB, ld = NW + 1;
+  double* Wm = smem_d;                       // [NW][ld] window, entry (i, k) at [i % NW][k % NW], lower triangle
+  double* X = Wm + (size_t)NW * ld;          // [NW][6] solved block column, by row slot
+  double* s_r = X + (size_t)NW * 6;          // [NW] rhs of the window rows, by row slot
+  uint16_t* s_pair = (uint16_t*)(s_r + NW);  // [W(W+1)/2] block pairs (bi << 8 | bk), bk <= bi, of the rank-6 update
+  // double-buffered per-column results of the look-ahead diagonal factorisation
+  __shared__ double s_D[2][6][7], s_rd[2][6], s_y[2][6];
+  __shared__ int s_slot[2][kBandMaxW + 1];   // row slot of block j + 1 + b, per column parity (no runtime modulo inside)
+  __shared__ int s_fail;
+  const int n_pairs = W * (W + 1) / 2;
+  for (int e = tid; e < n_pairs; e += kBandThreads) {
+    int bi = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+    while ((bi + 1) * (bi + 2) / 2 <= e) bi++;
+    while (bi * (bi + 1) / 2 > e) bi--;
+    s_pair[e] = (uint16_t)((bi << 8) | (e - bi * (bi + 1) / 2));
+  }
+  if (tid == 0) s_fail = st.solve_failed;
+  if (tid <= W) s_slot[0][tid] = ((1 + tid) % NB) * 6;
+  // initial window: block rows 0..W.  Sblk entry (r, c) of block (a = b - off, b) -> window (row 6b + c, col 6a + r)
+  for (int b = 0; b < min(NB, Kv); b++) {
+    for (int e = tid; e < NB * 36; e += kBandThreads) {
+      const int off = e / 36, rc = e - 36 * off, r = rc / 6, c = rc - 6 * r, a2 = b - off;
+      if (a2 < 0 || (a2 == b && c < r)) continue;
+      const int id = ba.band_blk[(size_t)b * NB + off];
+      Wm[(size_t)((b % NB) * 6 + c) * ld + (a2 % NB) * 6 + r] = id >= 0 ? d.Sblk[(size_t)id * 36 + rc] : 0.0;
+    }
+    if (tid < 6) s_r[(b % NB) * 6 + tid] = d.rhs[6 * b + tid];
+  }
+  __syncthreads();
+  if (tid == 0 && !s_fail && !band_diag(Wm, ld, 0, s_r, s_D[0], s_rd[0], s_y[0])) s_fail = 1;
+  // per-thread constants of the entering block row (elements e = tid, tid + 512 of its (W+1) x 36 entries)
+  int pf_off[2], pf_r[2], pf_c[2];
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const int e = tid + q * kBandThreads;
+    pf_off[q] = e < NB * 36 ? e / 36 : -1;
+    const int rc = e - 36 * (e / 36);
+    pf_r[q] = rc / 6; pf_c[q] = rc - 6 * (rc / 6);
+  }
+  // the rank-6 update: threads 32.. own one (r, c) of the 6x6 blocks and stride over the block pairs
+  const int u = tid - 32;
+  const int up_rc = u % 36, up_r = up_rc / 6, up_c = up_rc - 6 * up_r, up_p0 = u / 36;
+  constexpr int kPairStride = (kBandThreads - 32) / 36;       // 13 pairs in flight
+  int row_slot = ((6 + tid) % NW);                            // slot of row 6 (j + 1) + tid for the row solves
+  int sj = 0;
+  __syncthreads();
+  for (int j = 0; j < Kv && !s_fail; j++) {
+    const int cur = j & 1;
+    const int nbelow = min(W, Kv - 1 - j);
+    const int* slot = s_slot[cur];
+    // the block row that enters when column j retires: fetch early, the loads fly during the row solves
+    const int bn = j + NB;
+    double pre[2] = {0.0, 0.0}, pre_r = 0.0;
+    if (bn < Kv) {
+#pragma unroll
+      for (int q = 0; q < 2; q++)
+        if (pf_off[q] >= 0) {
+          const int id = ba.band_blk[(size_t)bn * NB + pf_off[q]];
+          if (id >= 0) pre[q] = d.Sblk[(size_t)id * 36 + pf_r[q] * 6 + pf_c[q]];
+        }
+      if (tid < 6) pre_r = d.rhs[6 * bn + tid];
+    }
+    // rows below: x = w * L11^-T (6 entries per row), one thread per row; the rhs follows
+    double* Lc = ba.Lcol + (size_t)j * NW * 6;
+    if (tid < 6 * nbelow) {
+      const int si = row_slot;
+      double x[6], dot = 0.0;
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        double v = Wm[(size_t)si * ld + sj + c];
+#pragma unroll
+        for (int q = 0; q < c; q++) v -= x[q] * s_D[cur][c][q];
+        x[c] = v * s_rd[cur][c];
+        dot += x[c] * s_y[cur][c];
+      }
+      double2* xo = (double2*)(X + si * 6);
+      xo[0] = make_double2(x[0], x[1]); xo[1] = make_double2(x[2], x[3]); xo[2] = make_double2(x[4], x[5]);
+      double2* lo = (double2*)(Lc + (size_t)tid * 6);
+      lo[0] = make_double2(x[0], x[1]); lo[1] = make_double2(x[2], x[3]); lo[2] = make_double2(x[4], x[5]);
+      s_r[si] -= dot;
+    }
+    row_slot += 6; if (row_slot >= NW) row_slot -= NW;
+    if (tid >= kBandThreads - 36) {              // the diagonal block (reciprocal diagonal) and y_j, for the back substitution
+      const int q = tid - (kBandThreads - 36), r = q / 6, c = q - 6 * r;
+      Lc[(size_t)(6 * W + r) * 6 + c] = r == c ? s_rd[cur][r] : s_D[cur][r][c];
+      if (c == 0) d.rhs[6 * j + r] = s_y[cur][r];
+    } else if (tid >= 256 && tid <= 256 + W) {   // slots of the next column's rows
+      int v = slot[tid - 256] + 6; if (v >= NW) v -= NW;
+      s_slot[cur ^ 1][tid - 256] = v;
+    }
+    __syncthreads();
+    // rank-6 update of the window rows below.  Warp 0 takes the next diagonal block first and then factors it
+    // (look-ahead) while the other warps update the rest.
+    if (warp == 0) {
+      if (nbelow > 0) {
+        const int s1 = slot[0];
+        for (int rc = lane; rc < 36; rc += 32) {
+          const int r = rc / 6, c = rc - 6 * r;
+          double v = 0.0;
+#pragma unroll
+          for (int q = 0; q < 6; q++) v += X[(s1 + r) * 6 + q] * X[(s1 + c) * 6 + q];
+          Wm[(size_t)(s1 + r) * ld + s1 + c] -= v;
+        }
+        __syncwarp();
+        if (lane == 0 && !band_diag(Wm, ld, s1, s_r + s1, s_D[cur ^ 1], s_rd[cur ^ 1], s_y[cur ^ 1])) s_fail = 1;
+      }
+    } else if (up_p0 < kPairStride) {
+      const int np = nbelow * (nbelow + 1) / 2;
+      for (int p = 1 + up_p0; p < np; p += kPairStride) {       // pair 0 = (0,0) is warp 0's
+        const int pr = s_pair[p];
+        const int si = slot[pr >> 8] + up_r, sk = slot[pr & 0xff] + up_c;
+        const double2* xi = (const double2*)(X + si * 6);
+        const double2* xk = (const double2*)(X + sk * 6);
+        const double2 a0 = xi[0], a1 = xi[1], a2 = xi[2], b0 = xk[0], b1 = xk[1], b2 = xk[2];
+        const double v = ((a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y)) + (a2.x * b2.x + a2.y * b2.y);
+        Wm[(size_t)si * ld + sk] -= v;
+      }
+    }
+    // place the prefetched block row (its slots are those of the retired block j: nobody else touches them)
+    if (bn < Kv) {
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int off = pf_off[q];
+        if (off < 0 || (off == 0 && pf_c[q] < pf_r[q])) continue;
+        const int col = off == 0 ? sj : slot[W - off];           // block a = bn - off = j + 1 + (W - off)
+        Wm[(size_t)(sj + pf_c[q]) * ld + col + pf_r[q]] = pre[q];
+      }
+      if (tid < 6) s_r[sj + tid] = pre_r;
+    }
+    sj += 6; if (sj >= NW) sj -= NW;
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid == 0) st.solve_failed = s_fail;
+}
+
+// Back substitution L' x = y of the banded factor, from the last block column up: one warp, lane = row below (up to
+// four rows of six entries per lane, prefetched one step ahead), x lives in a circular shared array.  Then the
+// candidate keyframe poses.
+constexpr int kBandBackRows = (6 * kBandMaxW + 31) / 32;     // rows per lane
+__global__ void __launch_bounds__(32) k_band_backsub(BaDev d, BandArgs ba) {
+  __shared__ double s_x[6 * (kBandMaxW + 1)];
+  LmState& st = *d.st;
+  if (st.done || st.solve_failed) return;
+  const int lane = threadIdx.x, Kv = d.Kv, W = ba.W, NB = W + 1, NW = 6 * NB;
+  double2 nxt[kBandBackRows][3];
+  double dnx[21], ynx = 0.0;
+  auto prefetch = [&](int j) {
+    const double* Lc = ba.Lcol + (size_t)j * NW * 6;
+    const int rows = 6 * min(W, Kv - 1 - j);
+#pragma unroll
+    for (int q = 0; q < kBandBackRows; q++) {
+      const int t = lane + 32 * q;
+      if (t < rows) {
+        const double2* p = (const double2*)(Lc + (size_t)t * 6);
+        nxt[q][0] = p[0]; nxt[q][1] = p[1]; nxt[q][2] = p[2];
+      } else {
+        nxt[q][0] = nxt[q][1] = nxt[q][2] = make_double2(0.0, 0.0);
+      }
+    }
+    if (lane == 0) {
+      int k = 0;
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c <= r; c++) dnx[k++] = Lc[(size_t)(6 * W + r) * 6 + c];
+    }
+    if (lane < 6) ynx = d.rhs[6 * j + lane];
+  };
+  for (int i = lane; i < NW; i += 32) s_x[i] = 0.0;
+  __syncwarp();
+  prefetch(Kv - 1);
+  int bad = 0;
+  int sj = ((Kv - 1) % NB) * 6;               // slot of block j
+  for (int j = Kv - 1; j >= 0; j--) {
+    double2 cur[kBandBackRows][3];
+    double dcur[21];
+#pragma unroll
+    for (int q = 0; q < kBandBackRows; q++) { cur[q][0] = nxt[q][0]; cur[q][1] = nxt[q][1]; cur[q][2] = nxt[q][2]; }
+#pragma unroll
+    for (int k = 0; k < 21; k++) dcur[k] = dnx[k];
+    const double yj = ynx;
+    if (j > 0) prefetch(j - 1);
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    int sx = sj + 6 + lane;                    // slot of row 6 (j + 1) + lane
+    if (sx >= NW) sx -= NW;
+#pragma unroll
+    for (int q = 0; q < kBandBackRows; q++) {
+      const double xi = s_x[sx];               // rows past the band hold zeros in cur[], any finite x will do
+      acc[0] += cur[q][0].x * xi; acc[1] += cur[q][0].y * xi; acc[2] += cur[q][1].x * xi;
+      acc[3] += cur[q][1].y * xi; acc[4] += cur[q][2].x * xi; acc[5] += cur[q][2].y * xi;
+      sx += 32;
+      while (sx >= NW) sx -= NW;
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++)
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    double y[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) y[r] = __shfl_sync(0xffffffffu, yj, r);
+    if (lane == 0) {
+      double x[6];
+#pragma unroll
+      for (int r = 5; r >= 0; r--) {
+        double v = y[r] - acc[r];
+#pragma unroll
+        for (int q = r + 1; q < 6; q++) v -= dcur[q * (q + 1) / 2 + r] * x[q];
+        x[r] = v * dcur[r * (r + 1) / 2 + r];       // reciprocal diagonal
+      }
+#pragma unroll
+      for (int r = 0; r < 6; r++) { s_x[sj + r] = x[r]; d.yc[6 * j + r] = x[r]; bad |= !isfinite(x[r]); }
+    }
+    sj -= 6; if (sj < 0) sj += NW;
+    __syncwarp();
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (bad) { if (lane == 0) st.solve_failed = 1; return; }
+  __syncwarp();
+  for (int cam = lane; cam < d.K; cam += 32) cam_candidate(d, st, cam);
+}
+
 __global__ void __launch_bounds__(256) k_cam_candidates(BaDev d) {
   LmState& st = *d.st;
   if (st.done) return;
@@ -1108,6 +1396,8 @@ struct cmos_ba {
   int* d_pan_tiles = nullptr;               // active row tiles of every panel of the blocked factorisation
   std::vector<int> pan_start, pan_first_col; // [n_panels + 1], [n_panels]
   size_t cap_pan_tiles = 0;
+  int band_W = 0;                            // > 0: banded reduced system, solved by k_solve_band
+  int* d_band_blk = nullptr;                 // [Kv][band_W + 1]
   double* d_trace = nullptr;       // [2][trace_rows][8]
   int trace_rows = 0;
   cmos_ba_summary* d_summaries = nullptr;   // [2]
@@ -1207,6 +1497,11 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
       if (small) {
         k_solve_small<<<1, kSolveThreads, small_smem, st>>>(d);
         h->launches++;
+      } else if (h->band_W > 0) {
+        BandArgs ba{h->band_W, h->d_band_blk, d.S};
+        k_solve_band<<<1, kBandThreads, band_smem_bytes(h->band_W), st>>>(d, ba);
+        k_band_backsub<<<1, 32, 0, st>>>(d, ba);
+        h->launches += 2;
       } else {
         const int n = d.nc;
         CMOS_CUDA_OK(cudaMemsetAsync(d.S, 0, (size_t)n * n * sizeof(double), st));
@@ -1296,7 +1591,7 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
        alloc(&h->d_var_cam, K) && alloc(&h->d_red, 8) && alloc(&h->d_Sblk, h->cap_blocks * 36 + 6 * K + 8) &&
        alloc(&d.scale_c, 6 * K) && alloc(&d.S, h->cap_S) &&
        alloc(&d.yc, 6 * K + 8) && alloc(&d.part, 6 * nlb + 4 * K + 16) && alloc(&d.st, 1) &&
-       alloc(&h->d_Linv, ((6 * K + kNB - 1) / kNB) * kNB * kNB) && alloc(&h->d_pan_tiles, h->cap_pan_tiles) && alloc(&h->d_trace, 2 * (size_t)h->trace_rows * kTraceCols) &&
+       alloc(&h->d_Linv, ((6 * K + kNB - 1) / kNB) * kNB * kNB) && alloc(&h->d_pan_tiles, h->cap_pan_tiles) && alloc(&h->d_band_blk, (size_t)K * (kBandMaxW + 1)) && alloc(&h->d_trace, 2 * (size_t)h->trace_rows * kTraceCols) &&
        alloc(&h->d_summaries, 2);
   const size_t PB = std::max(params->max_pose_batch, 1), PC = std::max(params->max_pose_corr, 1);
   ok = ok && alloc(&h->dp_pose, 7 * PB) && alloc(&h->dp_xw, 3 * PB * PC) && alloc(&h->dp_uv, 2 * PB * PC) &&
@@ -1309,6 +1604,7 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
   }
   cudaMemset(d.st, 0, sizeof(LmState));
   cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+  cudaFuncSetAttribute(k_solve_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
   cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
   cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
   cudaFuncSetAttribute(k_syrk_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
@@ -1325,7 +1621,7 @@ int cmos_ba_destroy(cmos_ba_t h) {
                   h->d_o_cam, h->d_o_cv, h->d_o_pt, h->d_pt_start, h->d_cam_start, h->d_cam_obs, h->d_blk_a, h->d_blk_b,
                   h->d_blk_start, h->d_pair_a, h->d_pair_b, h->d_perm, h->d_o_uv, h->d_o_w, h->d_o_mode, h->d_cam_flags,
                   h->d_erase, d.Jc, d.Jp, d.res, d.Hpp, d.gp, d.Hinv, d.tp, d.scale_p, h->d_HG, h->d_var_cam, h->d_red, h->d_Sblk, d.scale_c, d.S,
-                  d.yc, d.part, d.st, h->d_Linv, h->d_pan_tiles, h->d_trace, h->d_summaries, h->dp_pose, h->dp_xw, h->dp_uv, h->dp_w,
+                  d.yc, d.part, d.st, h->d_Linv, h->d_pan_tiles, h->d_band_blk, h->d_trace, h->d_summaries, h->dp_pose, h->dp_xw, h->dp_uv, h->dp_w,
                   h->dp_n, h->dp_inl, h->dp_out, h->dp_sum, h->dp_trace};
   for (void* b : bufs)
     if (b) cudaFree(b);
@@ -1485,7 +1781,23 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
   // dense.
   h->pan_start.assign(1, 0);
   h->pan_first_col.clear();
+  h->band_W = 0;
   if (6 * Kv > kSmallMaxN) {
+    int Wmax = 0;
+    for (int i = 0; i < nb; i++) Wmax = std::max(Wmax, blk_b[i] - blk_a[i]);
+    const char* no_band = std::getenv("CMOS_BA_NO_BAND");
+    const size_t NWb = 6 * (size_t)(Wmax + 1);
+    if (Wmax >= 1 && Wmax <= kBandMaxW && !(no_band && no_band[0] == '1') &&
+        band_smem_bytes(Wmax) <= 227 * 1024 - 2048 &&
+        (size_t)Kv * NWb * 6 <= h->cap_S) {
+      std::vector<int> band((size_t)Kv * (Wmax + 1), -1);
+      for (int i = 0; i < nb; i++) band[(size_t)blk_b[i] * (Wmax + 1) + (blk_b[i] - blk_a[i])] = i;
+      CMOS_CUDA_OK(cudaMemcpyAsync(h->d_band_blk, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));
+      h->band_W = Wmax;
+    }
+  }
+  if (6 * Kv > kSmallMaxN && h->band_W == 0) {
     const int n = 6 * Kv;
     std::vector<int> first_blk(Kv);
     for (int b = 0; b < Kv; b++) first_blk[b] = b;
@@ -1648,6 +1960,14 @@ int cmos_ba_get_results(cmos_ba_t h, double* cams, double* points, uint8_t* eras
   if (erase) CMOS_CUDA_OK(cudaMemcpyAsync(erase, h->d_erase, d.N, cudaMemcpyDeviceToHost, st));
   if (summaries) CMOS_CUDA_OK(cudaMemcpyAsync(summaries, h->d_summaries, 2 * sizeof(cmos_ba_summary), cudaMemcpyDeviceToHost, st));
   CMOS_CUDA_OK(cudaStreamSynchronize(st));
+  // The caller's stop-flag page is page-locked only while a solve can read it: a stale registration would make later
+  // copies from unrelated heap memory that shares the page fail ("invalid argument": a partly pinned source range).
+  if (h->stop_registered_by_us && h->stop_host_page) {
+    cudaHostUnregister((void*)h->stop_host_page);
+    h->stop_registered_by_us = false;
+    h->stop_host_page = nullptr;
+    h->stop_dev_page = nullptr;
+  }
   return CMOS_OK;
 }
 
