@@ -1132,10 +1132,6 @@ __global__ void __launch_bounds__(kBandThreads) k_solve_band(BaDev d, BandArgs b
     const int rc = e - 36 * (e / 36);
     pf_r[q] = rc / 6; pf_c[q] = rc - 6 * (rc / 6);
   }
-  // the rank-6 update: threads 32.. own one (r, c) of the 6x6 blocks and stride over the block pairs
-  const int u = tid - 32;
-  const int up_rc = u % 36, up_r = up_rc / 6, up_c = up_rc - 6 * up_r, up_p0 = u / 36;
-  constexpr int kPairStride = (kBandThreads - 32) / 36;       // 13 pairs in flight
   int row_slot = ((6 + tid) % NW);                            // slot of row 6 (j + 1) + tid for the row solves
   int sj = 0;
   __syncthreads();
@@ -1199,16 +1195,30 @@ __global__ void __launch_bounds__(kBandThreads) k_solve_band(BaDev d, BandArgs b
         __syncwarp();
         if (lane == 0 && !band_diag(Wm, ld, s1, s_r + s1, s_D[cur ^ 1], s_rd[cur ^ 1], s_y[cur ^ 1])) s_fail = 1;
       }
-    } else if (up_p0 < kPairStride) {
+    } else {
+      // work item = (block pair, 3x3 quadrant): 54 independent FMAs on 12 vector loads, enough ILP for the 15 warps
       const int np = nbelow * (nbelow + 1) / 2;
-      for (int p = 1 + up_p0; p < np; p += kPairStride) {       // pair 0 = (0,0) is warp 0's
-        const int pr = s_pair[p];
-        const int si = slot[pr >> 8] + up_r, sk = slot[pr & 0xff] + up_c;
-        const double2* xi = (const double2*)(X + si * 6);
-        const double2* xk = (const double2*)(X + sk * 6);
-        const double2 a0 = xi[0], a1 = xi[1], a2 = xi[2], b0 = xk[0], b1 = xk[1], b2 = xk[2];
-        const double v = ((a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y)) + (a2.x * b2.x + a2.y * b2.y);
-        Wm[(size_t)si * ld + sk] -= v;
+      for (int w = tid - 32; w < 4 * (np - 1); w += kBandThreads - 32) {     // pair 0 = (0,0) is warp 0's
+        const int pr = s_pair[1 + (w >> 2)], qd = w & 3;
+        const int si = slot[pr >> 8] + 3 * (qd >> 1), sk = slot[pr & 0xff] + 3 * (qd & 1);
+        double xi[3][6];
+#pragma unroll
+        for (int a2 = 0; a2 < 3; a2++) {
+          const double2* px = (const double2*)(X + (si + a2) * 6);
+          const double2 t0 = px[0], t1 = px[1], t2 = px[2];
+          xi[a2][0] = t0.x; xi[a2][1] = t0.y; xi[a2][2] = t1.x; xi[a2][3] = t1.y; xi[a2][4] = t2.x; xi[a2][5] = t2.y;
+        }
+#pragma unroll
+        for (int b2 = 0; b2 < 3; b2++) {
+          const double2* px = (const double2*)(X + (sk + b2) * 6);
+          const double2 t0 = px[0], t1 = px[1], t2 = px[2];
+#pragma unroll
+          for (int a2 = 0; a2 < 3; a2++) {
+            const double v = ((xi[a2][0] * t0.x + xi[a2][1] * t0.y) + (xi[a2][2] * t1.x + xi[a2][3] * t1.y)) +
+                             (xi[a2][4] * t2.x + xi[a2][5] * t2.y);
+            Wm[(size_t)(si + a2) * ld + sk + b2] -= v;
+          }
+        }
       }
     }
     // place the prefetched block row (its slots are those of the retired block j: nobody else touches them)
