@@ -10,5 +10,6 @@ from .orb_matcher import ORBmatcher, Camera  # noqa: F401
 from .ceres_optimizer import CeresOptimizer  # noqa: F401
 from .tracking import TrackingFrontEnd  # noqa: F401
 from .kf_matcher import KeyFrameMatcher, FeatureVector  # noqa: F401
+from .map_points import MapPointOps  # noqa: F401
 
-__all__ = ["ORBextractor", "ORBmatcher", "Camera", "CeresOptimizer", "TrackingFrontEnd", "KeyFrameMatcher", "FeatureVector", "KP_DTYPE", "CmosError", "LIB_PATH"]
+__all__ = ["ORBextractor", "ORBmatcher", "Camera", "CeresOptimizer", "TrackingFrontEnd", "KeyFrameMatcher", "FeatureVector", "MapPointOps", "KP_DTYPE", "CmosError", "LIB_PATH"]

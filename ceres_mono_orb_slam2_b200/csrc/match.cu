@@ -659,6 +659,49 @@ __global__ void __launch_bounds__(256) k_in_frustum(cmos_camera cam, const doubl
   view_cos[i] = vc;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Frame::UndistortKeyPoints (Frame.cc:329-355): cv::undistortPoints(mat, mat, K, dist, Mat(), K) on the keypoint
+// coordinates — five fixed-point iterations of the inverse Brown model in double (OpenCV 4.13
+// cvUndistortPointsInternal, criteria MAX_ITER 5), R = I, P = K.  One thread per keypoint; the other keypoint fields
+// are copied.  This translation unit is compiled without FMA contraction, as the CPU code is.
+struct UndistortArgs { double fx, fy, cx, cy, k[14]; };
+
+__device__ __forceinline__ void undistort_point(const UndistortArgs& a, float xin, float yin, float* xo, float* yo) {
+  double x = xin, y = yin;
+  const double u = x, v = y, ifx = 1. / a.fx, ify = 1. / a.fy;
+  x = (x - a.cx) * ifx;
+  y = (y - a.cy) * ify;
+  const double x0 = x, y0 = y;
+  const double* k = a.k;
+  for (int j = 0; j < 5; j++) {
+    const double r2 = x * x + y * y;
+    const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+    if (icdist < 0) { x = (u - a.cx) * ifx; y = (v - a.cy) * ify; break; }
+    const double dx = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+    const double dy = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  const double xx = a.fx * x + 0 * y + a.cx, yy = 0 * x + a.fy * y + a.cy, ww = 1. / (0 * x + 0 * y + 1);
+  *xo = (float)(xx * ww);
+  *yo = (float)(yy * ww);
+}
+
+__global__ void __launch_bounds__(256) k_undistort(UndistortArgs a, const cmos_keypoint* __restrict__ in,
+                                                   const int* __restrict__ counts, int stride,
+                                                   cmos_keypoint* __restrict__ out) {
+  const int f = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= min(counts[f], stride)) return;
+  cmos_keypoint kp = in[(size_t)f * stride + i];
+  undistort_point(a, kp.x, kp.y, &kp.x, &kp.y);
+  out[(size_t)f * stride + i] = kp;
+}
+
+__global__ void k_undistort_xy(UndistortArgs a, const float* __restrict__ in, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) undistort_point(a, in[2 * i], in[2 * i + 1], out + 2 * i, out + 2 * i + 1);
+}
+
 }  // namespace cmos
 
 using namespace cmos;
@@ -1030,6 +1073,80 @@ int cmos_match_stage_times(cmos_match_t h, double* ms, int64_t* calls) {
 int cmos_match_last_launch_count(cmos_match_t h, int32_t* n) {
   CMOS_REQUIRE(h && n, "null argument");
   *n = h->launches;
+  return CMOS_OK;
+}
+
+static UndistortArgs undistort_args(const float* K4, const float* dist, int n_dist) {
+  UndistortArgs a{};
+  a.fx = K4[0]; a.fy = K4[1]; a.cx = K4[2]; a.cy = K4[3];
+  for (int i = 0; i < n_dist && i < 14; i++) a.k[i] = dist[i];
+  return a;
+}
+
+int cmos_match_undistort_keypoints(cmos_match_t h, const float* K4, const float* dist_coef, int32_t n_dist,
+                                   const cmos_keypoint* keypoints, const int32_t* counts, int32_t n_frames, int32_t stride,
+                                   cmos_keypoint* undistorted, int32_t on_device, void* stream) {
+  CMOS_REQUIRE(h && K4 && dist_coef && keypoints && counts && undistorted, "null argument");
+  CMOS_REQUIRE(n_dist >= 4 && n_dist <= 14, "n_dist %d outside 4..14", n_dist);
+  CMOS_REQUIRE(n_frames >= 1 && n_frames <= h->p.max_batch && stride >= 1 && stride <= h->p.max_keypoints, "bad sizes");
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const size_t n = (size_t)n_frames * stride;
+  const cmos_keypoint* src = keypoints;
+  const int* cnt = counts;
+  cmos_keypoint* dst = undistorted;
+  if (!on_device) {
+    int rc;
+    if ((rc = h2d(h->s_last_kps, keypoints, n, st))) return rc;
+    if ((rc = h2d(h->s_counts, counts, n_frames, st))) return rc;
+    src = h->s_last_kps; cnt = h->s_counts; dst = h->s_kps;
+  }
+  h->launches = 0;
+  if (dist_coef[0] == 0.0f) {     // Frame.cc:330-333: undistort_keypoints_ = keypoints_
+    if (dst != src) CMOS_CUDA_OK(cudaMemcpyAsync(dst, src, n * sizeof(cmos_keypoint), cudaMemcpyDeviceToDevice, st));
+  } else {
+    k_undistort<<<dim3((stride + 255) / 256, n_frames), 256, 0, st>>>(undistort_args(K4, dist_coef, n_dist), src, cnt, stride, dst);
+    CMOS_CUDA_OK(cudaGetLastError());
+    h->launches = 1;
+  }
+  if (!on_device) {
+    int rc;
+    if ((rc = d2h(undistorted, h->s_kps, n, st))) return rc;
+    CMOS_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return CMOS_OK;
+}
+
+int cmos_camera_init_distorted(cmos_camera* cam, int32_t width, int32_t height, float fx, float fy, float cx, float cy,
+                               const float* dist_coef, int32_t n_dist, const float* scale_factors, int32_t nlevels,
+                               float scale_factor, int32_t device) {
+  int rc = cmos_camera_init(cam, width, height, fx, fy, cx, cy, scale_factors, nlevels, scale_factor);
+  if (rc) return rc;
+  CMOS_REQUIRE(dist_coef && n_dist >= 4 && n_dist <= 14, "bad distortion coefficients");
+  if (dist_coef[0] == 0.0f) return CMOS_OK;
+  // Frame::ComputeImageBounds (Frame.cc:357-385): the four image corners through cv::undistortPoints
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: this library has no CPU fallback");
+    return CMOS_ERR_CUDA;
+  }
+  CMOS_CUDA_OK(cudaSetDevice(device));
+  const float corners[8] = {0.f, 0.f, (float)width, 0.f, 0.f, (float)height, (float)width, (float)height};
+  float out[8];
+  float* d = nullptr;
+  CMOS_CUDA_OK(cudaMalloc(&d, 16 * sizeof(float)));
+  const float K4[4] = {fx, fy, cx, cy};
+  cudaMemcpy(d, corners, sizeof(corners), cudaMemcpyHostToDevice);
+  k_undistort_xy<<<1, 32>>>(undistort_args(K4, dist_coef, n_dist), d, 4, d + 8);
+  cudaError_t e = cudaMemcpy(out, d + 8, sizeof(out), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CMOS_CUDA_OK(e);
+  cam->min_x = std::min(out[0], out[4]);
+  cam->max_x = std::max(out[2], out[6]);
+  cam->min_y = std::min(out[1], out[3]);
+  cam->max_y = std::max(out[5], out[7]);
+  cam->grid_element_width_inv = static_cast<float>(CMOS_GRID_COLS) / static_cast<float>(cam->max_x - cam->min_x);
+  cam->grid_element_height_inv = static_cast<float>(CMOS_GRID_ROWS) / static_cast<float>(cam->max_y - cam->min_y);
   return CMOS_OK;
 }
 

@@ -29,6 +29,17 @@ class Camera(C.Structure):
                                           C.c_float(scale_factor)))
         return cam
 
+    @classmethod
+    def create_distorted(cls, width, height, K, dist_coef, scale_factors, scale_factor=1.2, device=0):
+        """Camera with lens distortion: bounds = undistorted image corners (Frame::ComputeImageBounds)."""
+        cam = cls()
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        dc = np.ascontiguousarray(dist_coef, np.float32)
+        check(_lib.lib().cmos_camera_init_distorted(C.byref(cam), width, height, C.c_float(K[0]), C.c_float(K[1]),
+                                                    C.c_float(K[2]), C.c_float(K[3]), ptr(dc), len(dc), ptr(sf), len(sf),
+                                                    C.c_float(scale_factor), device))
+        return cam
+
     def bounds6(self):
         return np.array([self.min_x, self.max_x, self.min_y, self.max_y, self.grid_element_width_inv,
                          self.grid_element_height_inv], np.float32)
@@ -77,6 +88,21 @@ class ORBmatcher:
         check(self._L.cmos_match_set_frames(self._h, C.byref(cam), ptr(keypoints), ptr(descriptors), ptr(counts),
                                             n_frames, stride, int(on_device), C.c_void_p(stream)))
         self.n_frames, self.stride = n_frames, stride
+
+    # ---- Frame::UndistortKeyPoints (Frame.cc:329-355) for a batch ----
+    def UndistortKeyPoints(self, K4, dist_coef, keypoints, counts, out=None, on_device: bool = False, stream: int = 0):
+        """keypoints [B, stride] (KP_DTYPE) -> undistorted keypoints, same layout."""
+        k4 = np.ascontiguousarray(K4, np.float32); dc = np.ascontiguousarray(dist_coef, np.float32)
+        if on_device:
+            n_frames, stride = out[1]
+            dst = out[0]
+        else:
+            keypoints = np.ascontiguousarray(keypoints); counts = np.ascontiguousarray(counts, np.int32)
+            n_frames, stride = keypoints.shape
+            dst = np.zeros_like(keypoints) if out is None else out
+        check(self._L.cmos_match_undistort_keypoints(self._h, ptr(k4), ptr(dc), len(dc), ptr(keypoints), ptr(counts),
+                                                     n_frames, stride, ptr(dst), int(on_device), C.c_void_p(stream)))
+        return dst
 
     def debug_grid(self, frame: int):
         gs = np.zeros(GRID_COLS * GRID_ROWS + 1, np.int32)

@@ -169,6 +169,12 @@ typedef struct {
 int cmos_camera_init(cmos_camera* cam, int32_t width, int32_t height, float fx, float fy, float cx, float cy,
                      const float* scale_factors, int32_t nlevels, float scale_factor);
 
+/* Same for a camera with lens distortion (k1 != 0): the bounds are the undistorted image corners
+ * (Frame::ComputeImageBounds, Frame.cc:357-385); dist_coef = k1, k2, p1, p2[, k3] as in the settings file. */
+int cmos_camera_init_distorted(cmos_camera* cam, int32_t width, int32_t height, float fx, float fy, float cx, float cy,
+                               const float* dist_coef, int32_t n_dist, const float* scale_factors, int32_t nlevels,
+                               float scale_factor, int32_t device);
+
 typedef struct {
   int32_t max_batch;       /* frames per call */
   int32_t max_keypoints;   /* keypoints per frame (stride upper bound), <= 65535 */
@@ -187,6 +193,13 @@ int cmos_match_destroy(cmos_match_t h);
 int cmos_match_set_frames(cmos_match_t h, const cmos_camera* cam, const cmos_keypoint* keypoints,
                           const uint8_t* descriptors, const int32_t* counts, int32_t n_frames, int32_t stride,
                           int32_t on_device, void* stream);
+
+/* Frame::UndistortKeyPoints (Frame.cc:329-355) for a batch: keypoints [n_frames][stride] -> undistorted (same layout;
+ * pt replaced, every other field copied).  cv::undistortPoints(mat, mat, K, dist, Mat(), K) semantics of OpenCV 4.13
+ * (5 iterations, double arithmetic); k1 == 0 copies.  May run in place (undistorted == keypoints) with on_device. */
+int cmos_match_undistort_keypoints(cmos_match_t h, const float* K4, const float* dist_coef, int32_t n_dist,
+                                   const cmos_keypoint* keypoints, const int32_t* counts, int32_t n_frames,
+                                   int32_t stride, cmos_keypoint* undistorted, int32_t on_device, void* stream);
 
 /* Verification tap: CSR grid of one frame, cell = ix*48+iy: grid_start[64*48+1], grid_idx[stride]. Host out. */
 int cmos_match_debug_grid(cmos_match_t h, int32_t frame, int32_t* grid_start, int32_t* grid_idx);
@@ -324,6 +337,37 @@ int cmos_kfmatch_search_for_initialization(cmos_kfmatch_t h, float* prev_matched
                                            int32_t check_orientation, int32_t* matches12, int32_t* nmatches);
 /* Kernels launched by the last cmos_kfmatch_* call. */
 int cmos_kfmatch_last_launch_count(cmos_kfmatch_t h, int32_t* n);
+
+/* ------------------------------------------------------------------------------------------------
+ * MapPoint maintenance, batched over map points: what the reference runs for every touched
+ * point after tracking, fusing and bundle adjustment.  Observations are passed as a CSR over points, in the iteration
+ * order of each point's std::map<KeyFrame*, size_t> (tie-breaks and fp64 sums depend on it), bad keyframes dropped.
+ * HOST pointers, synchronous.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t max_points;
+  int32_t max_observations;   /* total over the points of one call */
+  int32_t max_keyframes;
+  int32_t device;
+} cmos_map_params;
+typedef struct cmos_map* cmos_map_t;
+int cmos_map_create(const cmos_map_params* params, cmos_map_t* out);
+int cmos_map_destroy(cmos_map_t h);
+/* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:256-315): descriptors [obs_start[n_points]][32] are the
+ * observed keypoint descriptors;  best_index [n_points] out: position inside the point's list of the descriptor with
+ * the least median Hamming distance to the others (-1 for a point without observations: descriptor_ untouched);
+ * best_descriptor [n_points][32] out (may be NULL) = the new descriptor_.  At most 1024 observations per point. */
+int cmos_map_distinctive_descriptors(cmos_map_t h, int32_t n_points, const int32_t* obs_start, const uint8_t* descriptors,
+                                     int32_t* best_index, uint8_t* best_descriptor);
+/* MapPoint::UpdateNormalAndDepth (MapPoint.cc:335-378): obs_keyframe = keyframe index of every observation,
+ * camera_centers [n_keyframes][3] = GetCameraCenter(), world_pos [n_points][3], per point the reference keyframe and the
+ * octave of its keypoint there, scale_factors = the keyframes' table.  normal [n_points][3], min_distance, max_distance
+ * in/out: points without observations keep their values. */
+int cmos_map_update_normal_and_depth(cmos_map_t h, int32_t n_points, const int32_t* obs_start, const int32_t* obs_keyframe,
+                                     int32_t n_keyframes, const double* camera_centers, const double* world_pos,
+                                     const int32_t* ref_keyframe, const int32_t* ref_level, const float* scale_factors,
+                                     int32_t n_levels, double* normal, float* min_distance, float* max_distance);
+int cmos_map_last_launch_count(cmos_map_t h, int32_t* n);
 
 /* ------------------------------------------------------------------------------------------------
  * Path 1a+1b fused for a batch of frames with HOST buffers: what the Tracking thread does per frame —

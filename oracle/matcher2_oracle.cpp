@@ -11,6 +11,7 @@
 //   SearchBySim3                                                          /root/reference/src/ORBmatcher.cc:956-1159
 //   KeyFrame::GetFeaturesInArea / IsInImage                               /root/reference/src/KeyFrame.cc:575-626
 //   MapPoint::PredictScale, Get{Min,Max}DistanceInvariance                /root/reference/src/MapPoint.cc:380-420
+//   MapPoint::ComputeDistinctiveDescriptors, UpdateNormalAndDepth         /root/reference/src/MapPoint.cc:256-315,335-378
 // Own code of the reference, integer Hamming + float32/float64 geometry.  The reference has no tests for any of it:
 // PARITY UNPINNED by the reference; this restatement follows the source statement by statement and is checked
 // against hand-built known answers and brute force in tests/test_oracle_matcher2.py.
@@ -538,6 +539,60 @@ int match2_oracle_search_for_initialization(const void* kps1, const uint8_t* des
   for (int i1 = 0; i1 < n1; i1++)
     if (matches12[i1] >= 0) { prev_matched[2 * i1] = F2.kps[matches12[i1]].x; prev_matched[2 * i1 + 1] = F2.kps[matches12[i1]].y; }
   return nmatches;
+}
+
+// ---- MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:256-315) for a batch of map points ---------------------------
+//   Point p owns the descriptors obs_start[p] .. obs_start[p+1]-1 (rows of `desc`), in the iteration order of its
+//   std::map<KeyFrame*, size_t> with bad keyframes already dropped.  best[p] = index inside the point's list of the
+//   descriptor with the least median distance to the others (first wins ties), -1 for an empty list (the reference
+//   returns without touching descriptor_).  median = sorted row [ (int)(0.5 * (N - 1)) ], the row includes its own 0.
+void map_oracle_distinctive_descriptors(int n_points, const int32_t* obs_start, const uint8_t* desc, int32_t* best) {
+  std::vector<int> dists;
+  for (int p = 0; p < n_points; p++) {
+    const int o = obs_start[p], N = obs_start[p + 1] - o;
+    best[p] = -1;
+    if (N <= 0) continue;
+    int best_median = INT_MAX, best_index = 0;
+    for (int i = 0; i < N; i++) {
+      dists.resize(N);
+      for (int j = 0; j < N; j++) dists[j] = i == j ? 0 : hamming256(desc + 32 * (size_t)(o + i), desc + 32 * (size_t)(o + j));
+      std::sort(dists.begin(), dists.end());
+      const int median = dists[(size_t)(0.5 * (N - 1))];
+      if (median < best_median) { best_median = median; best_index = i; }
+    }
+    best[p] = best_index;
+  }
+}
+
+// ---- MapPoint::UpdateNormalAndDepth (MapPoint.cc:335-378) for a batch of map points -----------------------------------
+//   obs_kf: keyframe index of every observation (CSR by point, map order); Ow [K][3] camera centres; per point the
+//   reference keyframe and the octave of its keypoint there; sf = scale_factors_.  Points without observations keep
+//   their outputs untouched.
+void map_oracle_update_normal_and_depth(int n_points, const int32_t* obs_start, const int32_t* obs_kf, const double* Ow,
+                                        const double* pos, const int32_t* ref_kf, const int32_t* ref_level,
+                                        const float* sf, int n_levels, double* normal, float* min_distance,
+                                        float* max_distance) {
+  for (int p = 0; p < n_points; p++) {
+    const int o = obs_start[p], N = obs_start[p + 1] - o;
+    if (N <= 0) continue;
+    const double* X = pos + 3 * p;
+    double nrm[3] = {0.0, 0.0, 0.0};
+    int n = 0;
+    for (int k = 0; k < N; k++) {
+      const double* C = Ow + 3 * (size_t)obs_kf[o + k];
+      const double d[3] = {X[0] - C[0], X[1] - C[1], X[2] - C[2]};
+      const double len = norm3(d);
+      for (int a = 0; a < 3; a++) nrm[a] = nrm[a] + d[a] / len;
+      n++;
+    }
+    const double* C = Ow + 3 * (size_t)ref_kf[p];
+    const double PC[3] = {X[0] - C[0], X[1] - C[1], X[2] - C[2]};
+    const float dist = (float)norm3(PC);
+    const float level_scale_factor = sf[ref_level[p]];
+    max_distance[p] = dist * level_scale_factor;
+    min_distance[p] = max_distance[p] / sf[n_levels - 1];
+    for (int a = 0; a < 3; a++) normal[3 * p + a] = nrm[a] / n;
+  }
 }
 
 }  // extern "C"

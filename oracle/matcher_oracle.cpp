@@ -283,4 +283,37 @@ void match_oracle_is_in_frustum(const double* pose15, const float* K4, const flo
   }
 }
 
+// Frame::UndistortKeyPoints (Frame.cc:329-355) = cv::undistortPoints(mat, mat, K_, dist_coef_, cv::Mat(), K_) on the
+// keypoint coordinates.  OpenCV (un-vendored, unpinned in the reference; restated from OpenCV 4.13
+// modules/calib3d/src/undistort.dispatch.cpp: cvUndistortPointsInternal with the public wrapper's criteria
+// TermCriteria(MAX_ITER, 5, 0.01), i.e. exactly five fixed-point iterations, R = I, P = K): all arithmetic in double,
+// inputs and outputs float.  PINNED: tests/test_oracle_matcher.py compares it bit for bit with cv2.undistortPoints.
+//   K4 = fx, fy, cx, cy (CV_32F in the reference, widened); dist = k1, k2, p1, p2[, k3] (n_dist = 4 or 5)
+void frame_oracle_undistort_points(const float* K4, const float* dist, int n_dist, const float* xy_in, int n,
+                                   float* xy_out) {
+  const double fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3];
+  double k[14] = {0};
+  for (int i = 0; i < n_dist && i < 14; i++) k[i] = dist[i];
+  const double ifx = 1. / fx, ify = 1. / fy;
+  for (int i = 0; i < n; i++) {
+    double x = xy_in[2 * i], y = xy_in[2 * i + 1];
+    const double u = x, v = y;
+    x = (x - cx) * ifx;
+    y = (y - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; j++) {
+      const double r2 = x * x + y * y;
+      const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+      if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+      const double dx = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+      const double dy = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+      x = (x0 - dx) * icdist;
+      y = (y0 - dy) * icdist;
+    }
+    const double xx = fx * x + 0 * y + cx, yy = 0 * x + fy * y + cy, ww = 1. / (0 * x + 0 * y + 1);
+    xy_out[2 * i] = (float)(xx * ww);
+    xy_out[2 * i + 1] = (float)(yy * ww);
+  }
+}
+
 }  // extern "C"

@@ -268,6 +268,22 @@ def is_in_frustum(pose15, K4, bounds4, log_scale_factor, n_levels, cos_limit, xw
     return in_view, proj, level, vcos
 
 
+def undistort_points(K4, dist, xy):
+    """Frame::UndistortKeyPoints' cv::undistortPoints(mat, mat, K, dist, Mat(), K) restated (oracle/matcher_oracle.cpp)."""
+    k = np.ascontiguousarray(K4, np.float32); dc = np.ascontiguousarray(dist, np.float32)
+    a = np.ascontiguousarray(xy, np.float32); out = np.zeros_like(a)
+    lib().frame_oracle_undistort_points(_p(k), _p(dc), len(dc), _p(a), len(a), _p(out))
+    return out
+
+
+def image_bounds(K4, dist, width, height):
+    """Frame::ComputeImageBounds (Frame.cc:357-385) -> min_x, max_x, min_y, max_y (float32)."""
+    if np.float32(dist[0]) == 0.0:
+        return np.array([0.0, width, 0.0, height], np.float32)
+    c = undistort_points(K4, dist, np.array([[0, 0], [width, 0], [0, height], [width, height]], np.float32))
+    return np.array([min(c[0, 0], c[2, 0]), max(c[1, 0], c[3, 0]), min(c[0, 1], c[1, 1]), max(c[2, 1], c[3, 1])], np.float32)
+
+
 # ---------------------------------------------------------------------------------------------------
 # Bundle-adjustment oracle (oracle/ba_oracle.cpp)
 
@@ -472,3 +488,19 @@ def search_for_initialization(kps1, desc1, V2: View, prev_matched, window_size, 
     nm = lib().match2_oracle_search_for_initialization(_p(k1), _p(d1), len(k1), *V2.args(), _p(prev), int(window_size),
                                                        C.c_float(nn_ratio), int(check_ori), _p(m12))
     return m12[:len(k1)], nm, prev
+
+
+def distinctive_descriptors(obs_start, desc):
+    st = _c(obs_start, np.int32); d = _c(desc, np.uint8)
+    best = np.full(max(len(st) - 1, 1), -1, np.int32)
+    lib().map_oracle_distinctive_descriptors(len(st) - 1, _p(st), _p(d), _p(best))
+    return best[:len(st) - 1]
+
+
+def update_normal_and_depth(obs_start, obs_kf, Ow, pos, ref_kf, ref_level, sf, normal, min_d, max_d):
+    st = _c(obs_start, np.int32); ok = _c(obs_kf, np.int32); ow = _c(Ow, np.float64); x = _c(pos, np.float64)
+    rk = _c(ref_kf, np.int32); rl = _c(ref_level, np.int32); s = _c(sf, np.float32)
+    nr = _c(normal, np.float64).copy(); mn = _c(min_d, np.float32).copy(); mx = _c(max_d, np.float32).copy()
+    lib().map_oracle_update_normal_and_depth(len(st) - 1, _p(st), _p(ok), _p(ow), _p(x), _p(rk), _p(rl), _p(s), len(s),
+                                             _p(nr), _p(mn), _p(mx))
+    return nr, mn, mx

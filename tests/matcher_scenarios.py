@@ -122,3 +122,30 @@ def pose15(R, t):
 def T44(R, t, s=1.0):
     T = np.eye(4); T[:3, :3] = s * R; T[:3, 3] = s * t if s != 1.0 else t
     return T
+
+
+def make_map_observations(n_points=3000, n_keyframes=40, seed=0, max_obs=30):
+    """CSR of observations for batched MapPoint maintenance: descriptors cluster around a per-point prototype (with a
+    few outliers so medians differ), keyframe centres on a path, some points without observations."""
+    rng = np.random.default_rng(seed)
+    nobs = np.minimum(rng.geometric(0.15, n_points), max_obs)
+    nobs[rng.random(n_points) < 0.03] = 0
+    nobs[:3] = [1, 2, max_obs]
+    start = np.concatenate([[0], np.cumsum(nobs)]).astype(np.int32)
+    total = int(start[-1])
+    proto = rng.integers(0, 256, (n_points, 32)).astype(np.uint8)
+    pt = np.repeat(np.arange(n_points), nobs)
+    desc = proto[pt].copy()
+    for _ in range(10):
+        on = rng.random(total) < 0.5
+        desc[np.nonzero(on)[0], rng.integers(0, 32, on.sum())] ^= (1 << rng.integers(0, 8, on.sum())).astype(np.uint8)
+    wild = rng.random(total) < 0.08
+    desc[wild] = rng.integers(0, 256, (wild.sum(), 32)).astype(np.uint8)
+    obs_kf = rng.integers(0, n_keyframes, total).astype(np.int32)
+    Ow = np.stack([0.4 * np.arange(n_keyframes), rng.normal(0, 0.05, n_keyframes), rng.normal(0, 0.05, n_keyframes)], 1)
+    pos = np.stack([rng.uniform(-5, 0.4 * n_keyframes + 5, n_points), rng.uniform(-3, 3, n_points), rng.uniform(4, 40, n_points)], 1)
+    ref_kf = np.where(nobs > 0, obs_kf[np.minimum(start[:-1], max(total - 1, 0))], 0).astype(np.int32)
+    ref_level = rng.integers(0, 8, n_points).astype(np.int32)
+    return dict(start=start, desc=desc, obs_kf=obs_kf, Ow=Ow, pos=pos, ref_kf=ref_kf, ref_level=ref_level,
+                normal0=rng.normal(0, 1, (n_points, 3)), min0=rng.uniform(1, 2, n_points).astype(np.float32),
+                max0=rng.uniform(20, 30, n_points).astype(np.float32))

@@ -286,3 +286,39 @@ def test_tracking_front_end_equals_unfused_calls(lanes, chunk):
             assert np.array_equal(k2[f, :n], kps[f, :n]) and np.array_equal(d2[f, :n], desc[f, :n])
             assert np.array_equal(m2[f, :n], match[f, :n])
     assert nm.sum() > 100 * B and fe.launch_count() > 0
+
+
+def test_undistort_keypoints_and_distorted_bounds():
+    """cmos_match_undistort_keypoints / cmos_camera_init_distorted == the oracle (itself bit-exact vs cv2.undistortPoints)."""
+    rng = np.random.default_rng(9)
+    K4 = np.array([520.908620, 521.007327, 325.141442, 249.701764], np.float32)
+    dist = np.array([0.231222, -0.784899, -0.003257, -0.000105, 0.917205], np.float32)
+    B, stride = 3, 1200
+    kps = np.zeros((B, stride), KP_DTYPE)
+    kps["x"] = rng.uniform(0, 640, (B, stride)).astype(np.float32); kps["y"] = rng.uniform(0, 480, (B, stride)).astype(np.float32)
+    kps["octave"] = rng.integers(0, 8, (B, stride)); kps["angle"] = rng.uniform(0, 360, (B, stride)).astype(np.float32)
+    kps["response"] = rng.uniform(0, 200, (B, stride)).astype(np.float32); kps["size"] = 31; kps["class_id"] = -1
+    counts = np.array([stride, 700, 0], np.int32)
+    m = ORBmatcher(0.9, True, max_batch=B, max_keypoints=stride)
+    und = m.UndistortKeyPoints(K4, dist, kps, counts)
+    for f in range(B):
+        n = counts[f]
+        xy = po.undistort_points(K4, dist, np.stack([kps["x"][f, :n], kps["y"][f, :n]], 1))
+        assert np.array_equal(und["x"][f, :n], xy[:, 0]) and np.array_equal(und["y"][f, :n], xy[:, 1])
+        for fld in ("size", "angle", "response", "octave", "class_id"):
+            assert np.array_equal(und[fld][f, :n], kps[fld][f, :n])
+    try:
+        import cv2
+        K = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], np.float32)
+        ref = cv2.undistortPoints(np.stack([kps["x"][0], kps["y"][0]], 1).reshape(-1, 1, 2), K, dist, None, K).reshape(-1, 2)
+        assert np.array_equal(und["x"][0], ref[:, 0]) and np.array_equal(und["y"][0], ref[:, 1])
+    except ImportError:
+        pass
+    # no distortion: plain copy
+    same = m.UndistortKeyPoints(K4, np.zeros(5, np.float32), kps, counts)
+    assert np.array_equal(same[0], kps[0])
+    sf = po.OrbOracle(1000, 1.2, 8, 20, 7).scale_factors
+    cam = Camera.create_distorted(640, 480, K4, dist, sf)
+    assert np.array_equal(cam.bounds6()[:4], po.image_bounds(K4, dist, 640, 480))
+    b = cam.bounds6()
+    assert b[4] == np.float32(64) / np.float32(b[1] - b[0]) and b[5] == np.float32(48) / np.float32(b[3] - b[2])

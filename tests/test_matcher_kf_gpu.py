@@ -131,3 +131,30 @@ def test_empty_inputs_and_errors(matcher):
     with pytest.raises(CmosError):        # node ids must ascend
         matcher.SearchByBoW(1, np.zeros(0, np.uint8), FeatureVector.create([5, 3], [0, 0, 0], []),
                             np.ones(len(S["k2"]), np.uint8), fv2)
+
+
+def test_map_point_maintenance():
+    """cmos_map_distinctive_descriptors / cmos_map_update_normal_and_depth == the oracle, bit for bit."""
+    from ceres_mono_orb_slam2_b200 import MapPointOps
+    from oracle import pyoracle as po
+    from tests.matcher_scenarios import make_map_observations
+    M = make_map_observations(n_points=4000, n_keyframes=60, seed=7, max_obs=40)
+    ops = MapPointOps(max_points=4000, max_observations=len(M["desc"]), max_keyframes=60)
+    best, desc = ops.ComputeDistinctiveDescriptors(M["start"], M["desc"])
+    obest = po.distinctive_descriptors(M["start"], M["desc"])
+    assert np.array_equal(best, obest)
+    has = obest >= 0
+    assert np.array_equal(desc[has], M["desc"][M["start"][:-1][has] + obest[has]])
+    sf = np.empty(8, np.float32); sf[0] = 1
+    for i in range(1, 8):
+        sf[i] = np.float32(np.float64(sf[i - 1]) * np.float64(np.float32(1.2)))
+    got = ops.UpdateNormalAndDepth(M["start"], M["obs_kf"], M["Ow"], M["pos"], M["ref_kf"], M["ref_level"], sf, M["normal0"],
+                                   M["min0"], M["max0"])
+    ref = po.update_normal_and_depth(M["start"], M["obs_kf"], M["Ow"], M["pos"], M["ref_kf"], M["ref_level"], sf, M["normal0"],
+                                     M["min0"], M["max0"])
+    for g, r in zip(got, ref):
+        assert np.array_equal(g, r)
+    # empty batch, and a point list with only empty points
+    b, _ = ops.ComputeDistinctiveDescriptors(np.zeros(4, np.int32), np.zeros((0, 32), np.uint8))
+    assert list(b) == [-1, -1, -1]
+    ops.close()

@@ -186,3 +186,23 @@ def test_descriptor_distance_popcount():
         assert po.descriptor_distance(a, b2) == ham(a, b2)
     a = np.zeros(32, np.uint8)
     assert po.descriptor_distance(a, ~a) == 256 and po.descriptor_distance(a, a) == 0
+
+
+def test_undistort_points_is_cv2_bit_exact():
+    """Frame::UndistortKeyPoints / ComputeImageBounds call cv::undistortPoints(mat, mat, K, dist, Mat(), K); the
+    restatement is pinned to OpenCV 4.13 through cv2 on the TUM1/TUM2 distortion models and a 4-coefficient one."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    cases = [((520.908620, 521.007327, 325.141442, 249.701764), (0.231222, -0.784899, -0.003257, -0.000105, 0.917205)),   # TUM2.yaml
+             ((517.306408, 516.469215, 318.643040, 255.313989), (0.262383, -0.953104, -0.005358, 0.002628, 1.163314)),   # TUM1.yaml
+             ((458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05))]              # 4 coefficients
+    for K4, dist in cases:
+        K = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], np.float32)
+        D = np.array(dist, np.float32)
+        pts = np.stack([rng.uniform(-30, 780, 40000), rng.uniform(-30, 520, 40000)], 1).astype(np.float32)
+        ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
+        got = po.undistort_points(np.array(K4, np.float32), D, pts)
+        assert np.array_equal(got, ref)
+    # k1 == 0: Frame.cc:330-333 copies, bounds are the image rectangle
+    assert np.array_equal(po.image_bounds(np.array(cases[0][0], np.float32), np.zeros(5, np.float32), 640, 480),
+                          np.array([0, 640, 0, 480], np.float32))

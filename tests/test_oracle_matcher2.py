@@ -149,3 +149,31 @@ def test_initialization_displacement():
     m12, nm, prev = po.search_for_initialization(k1, d1, V2, np.stack([k1["x"], k1["y"]], 1), 50, 0.9, False)
     assert nm == 1 and list(m12) == [-1, 0]
     assert np.array_equal(prev[1], [102, 100]) and np.array_equal(prev[0], [100, 100])
+
+
+def test_distinctive_descriptor_and_normal_depth_known_answers():
+    """MapPoint::ComputeDistinctiveDescriptors / UpdateNormalAndDepth against numpy on small inputs."""
+    from tests.matcher_scenarios import make_map_observations
+    M = make_map_observations(n_points=200, n_keyframes=12, seed=4, max_obs=12)
+    best = po.distinctive_descriptors(M["start"], M["desc"])
+    bits = np.unpackbits(M["desc"], axis=1).astype(np.int32)
+    for p in range(200):
+        o, e = M["start"][p], M["start"][p + 1]
+        if e == o:
+            assert best[p] == -1
+            continue
+        D = (bits[o:e, None, :] != bits[None, o:e, :]).sum(2)
+        med = np.sort(D, axis=1)[:, int(0.5 * (e - o - 1))]
+        assert best[p] == int(np.argmin(med))                       # first minimum
+    sf = (1.2 ** np.arange(8)).astype(np.float32)
+    nr, mn, mx = po.update_normal_and_depth(M["start"], M["obs_kf"], M["Ow"], M["pos"], M["ref_kf"], M["ref_level"], sf,
+                                            M["normal0"], M["min0"], M["max0"])
+    for p in range(200):
+        o, e = M["start"][p], M["start"][p + 1]
+        if e == o:
+            assert np.array_equal(nr[p], M["normal0"][p]) and mn[p] == M["min0"][p] and mx[p] == M["max0"][p]
+            continue
+        d = M["pos"][p] - M["Ow"][M["obs_kf"][o:e]]
+        assert np.allclose(nr[p], (d / np.linalg.norm(d, axis=1)[:, None]).mean(0), rtol=1e-12, atol=1e-15)
+        dist = np.float32(np.linalg.norm(M["pos"][p] - M["Ow"][M["ref_kf"][p]]))
+        assert mx[p] == dist * sf[M["ref_level"][p]] and mn[p] == mx[p] / sf[7]
