@@ -11,5 +11,6 @@ from .ceres_optimizer import CeresOptimizer  # noqa: F401
 from .tracking import TrackingFrontEnd  # noqa: F401
 from .kf_matcher import KeyFrameMatcher, FeatureVector  # noqa: F401
 from .map_points import MapPointOps  # noqa: F401
+from .vocabulary import ORBVocabulary  # noqa: F401
 
-__all__ = ["ORBextractor", "ORBmatcher", "Camera", "CeresOptimizer", "TrackingFrontEnd", "KeyFrameMatcher", "FeatureVector", "MapPointOps", "KP_DTYPE", "CmosError", "LIB_PATH"]
+__all__ = ["ORBextractor", "ORBmatcher", "Camera", "CeresOptimizer", "TrackingFrontEnd", "KeyFrameMatcher", "FeatureVector", "MapPointOps", "ORBVocabulary", "KP_DTYPE", "CmosError", "LIB_PATH"]

@@ -370,6 +370,27 @@ int cmos_map_update_normal_and_depth(cmos_map_t h, int32_t n_points, const int32
 int cmos_map_last_launch_count(cmos_map_t h, int32_t* n);
 
 /* ------------------------------------------------------------------------------------------------
+ * DBoW2 vocabulary transform: Frame::ComputeBoW / KeyFrame::ComputeBoW call
+ * orb_vocabulary_->transform(descriptors, bow_vector_, feature_vector_, 4) (Frame.cc:322-327, KeyFrame.cc:107-117;
+ * lib/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1260) with ORBvoc's TF_IDF weighting and L1 scoring.
+ * The vocabulary tree is uploaded once, flattened: node 0 = root, the children of node i are
+ * children[child_start[i] .. child_start[i+1]) in stored order (m_nodes[i].children), a node without children is a
+ * word (node_word_ids[i], node_weights[i] = its idf); inner nodes carry word id -1.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cmos_voc* cmos_voc_t;
+int cmos_voc_create(int32_t n_nodes, const int32_t* child_start, const int32_t* children, const uint8_t* node_descriptors,
+                    const double* node_weights, const int32_t* node_word_ids, int32_t depth_levels, int32_t device,
+                    cmos_voc_t* out);
+int cmos_voc_destroy(cmos_voc_t h);
+/* descriptors [n][32], n <= 8192.  BowVector out: bow_words / bow_values [n] (ascending word id, L1-normalised), *n_words;
+ * FeatureVector out (cmos_feature_vector layout): fv_nodes [n], fv_start [n + 1], fv_features [n], *n_fv_nodes.  Features
+ * whose word has weight 0 (stop words) appear in neither. */
+int cmos_voc_transform(cmos_voc_t h, const uint8_t* descriptors, int32_t n, int32_t levelsup, int32_t* bow_words,
+                       double* bow_values, int32_t* n_words, int32_t* fv_nodes, int32_t* fv_start, int32_t* fv_features,
+                       int32_t* n_fv_nodes);
+int cmos_voc_last_launch_count(cmos_voc_t h, int32_t* n);
+
+/* ------------------------------------------------------------------------------------------------
  * Path 1a+1b fused for a batch of frames with HOST buffers: what the Tracking thread does per frame —
  * Frame::Frame (src/Frame.cc:98-156: ExtractORB at :116 -> ORBextractor::operator() at :175-177, AssignFeaturesToGrid
  * at :155) followed by TrackWithMotionModel's ORBmatcher::SearchByProjection(current_frame_, last_frame_, th)

@@ -504,3 +504,63 @@ def update_normal_and_depth(obs_start, obs_kf, Ow, pos, ref_kf, ref_level, sf, n
     lib().map_oracle_update_normal_and_depth(len(st) - 1, _p(st), _p(ok), _p(ow), _p(x), _p(rk), _p(rl), _p(s), len(s),
                                              _p(nr), _p(mn), _p(mx))
     return nr, mn, mx
+
+
+# ---------------------------------------------------------------------------------------------------
+# DBoW2 vocabulary transform (oracle/bow_oracle.cpp)
+
+def make_vocabulary(k=10, L=3, seed=0, stop_frac=0.02):
+    """Synthetic vocabulary tree with DBoW2's shape (branching k, depth L, leaves = words): child descriptors are the
+    parent's with random bit flips, idf-like weights, a few stop words (weight 0).  Returns the flattened arrays."""
+    rng = np.random.default_rng(seed)
+    desc = [rng.integers(0, 256, 32).astype(np.uint8)]
+    child_start = [0]; children = []; level = [0]
+    weight = [0.0]; word = [-1]
+    frontier = [0]
+    for lev in range(1, L + 1):
+        nxt = []
+        for parent in frontier:
+            ids = list(range(len(desc), len(desc) + k))
+            for _ in ids:
+                d = desc[parent].copy()
+                nb = max(2, 48 >> (lev - 1))
+                d[rng.integers(0, 32, nb)] ^= (1 << rng.integers(0, 8, nb)).astype(np.uint8)
+                desc.append(d); level.append(lev); weight.append(0.0); word.append(-1)
+            nxt += ids
+            while len(child_start) <= parent + 1:
+                child_start.append(len(children))
+            children += ids
+            child_start[parent + 1] = len(children)
+        frontier = nxt
+    n = len(desc)
+    cs = np.zeros(n + 1, np.int32)
+    # children were appended parent by parent in id order: rebuild the CSR
+    kids = {}
+    pos = 0
+    order = sorted(set(range(n)) - set(frontier))
+    for p_ in order:
+        kids[p_] = children[pos:pos + k]; pos += k
+    flat = []
+    for i in range(n):
+        cs[i] = len(flat)
+        flat += kids.get(i, [])
+    cs[n] = len(flat)
+    w = np.zeros(n); wd = np.full(n, -1, np.int32)
+    for j, leaf in enumerate(frontier):
+        wd[leaf] = j
+        w[leaf] = 0.0 if rng.random() < stop_frac else float(rng.uniform(0.5, 9.0))
+    return dict(child_start=cs, children=np.array(flat, np.int32), desc=np.stack(desc), weight=w, word=wd, L=L, k=k)
+
+
+def bow_transform(voc, features, levelsup=4):
+    f = _c(features, np.uint8); n = len(f)
+    bw = np.zeros(max(n, 1), np.int32); bv = np.zeros(max(n, 1)); fn = np.zeros(max(n, 1), np.int32)
+    fs = np.zeros(n + 2, np.int32); ff = np.zeros(max(n, 1), np.int32); nfn = C.c_int32()
+    fw = np.zeros(max(n, 1), np.int32); fnode = np.zeros(max(n, 1), np.int32)
+    cs = _c(voc["child_start"], np.int32); ch = _c(voc["children"], np.int32); d = _c(voc["desc"], np.uint8)
+    w = _c(voc["weight"], np.float64); wd = _c(voc["word"], np.int32)
+    nw = lib().bow_oracle_transform(len(cs) - 1, _p(cs), _p(ch), _p(d), _p(w), _p(wd), int(voc["L"]), _p(f), n, int(levelsup),
+                                    _p(bw), _p(bv), _p(fn), _p(fs), _p(ff), C.byref(nfn), _p(fw), _p(fnode))
+    m = nfn.value
+    return dict(words=bw[:nw], values=bv[:nw], fv_nodes=fn[:m], fv_start=fs[:m + 1], fv_features=ff[:fs[m]],
+                feat_word=fw[:n], feat_node=fnode[:n])

@@ -158,3 +158,28 @@ def test_map_point_maintenance():
     b, _ = ops.ComputeDistinctiveDescriptors(np.zeros(4, np.int32), np.zeros((0, 32), np.uint8))
     assert list(b) == [-1, -1, -1]
     ops.close()
+
+
+@pytest.mark.parametrize("k,L,levelsup,n", [(10, 4, 2, 2000), (10, 3, 4, 500), (6, 5, 3, 3000), (33, 2, 1, 100)])
+def test_vocabulary_transform(k, L, levelsup, n):
+    """cmos_voc_transform == DBoW2's transform as restated by the oracle: word ids, L1-normalised values (bit for bit) and
+    the feature vector; stop words, repeated words, levelsup beyond the depth (node 0) and branching > 32 included."""
+    from ceres_mono_orb_slam2_b200 import ORBVocabulary
+    from oracle import pyoracle as po
+    voc = po.make_vocabulary(k=k, L=L, seed=k * 10 + L, stop_frac=0.03)
+    rng = np.random.default_rng(n)
+    leaves = np.nonzero(voc["word"] >= 0)[0]
+    f = voc["desc"][rng.choice(leaves, n)].copy()
+    for _ in range(3):
+        f[np.arange(n), rng.integers(0, 32, n)] ^= (1 << rng.integers(0, 8, n)).astype(np.uint8)
+    f[: n // 10] = f[n // 10: 2 * (n // 10)]
+    f[-5:] = rng.integers(0, 256, (5, 32)).astype(np.uint8)
+    V = ORBVocabulary(voc["child_start"], voc["children"], voc["desc"], voc["weight"], voc["word"], L)
+    got = V.transform(f, levelsup)
+    ref = po.bow_transform(voc, f, levelsup)
+    for key in ("words", "values", "fv_nodes", "fv_start", "fv_features"):
+        assert np.array_equal(got[key], ref[key]), key
+    assert len(ref["words"]) > 10 and V.launch_count() == 2
+    empty = V.transform(np.zeros((0, 32), np.uint8), levelsup)
+    assert len(empty["words"]) == 0 and len(empty["fv_nodes"]) == 0
+    V.close()

@@ -177,3 +177,37 @@ def test_distinctive_descriptor_and_normal_depth_known_answers():
         assert np.allclose(nr[p], (d / np.linalg.norm(d, axis=1)[:, None]).mean(0), rtol=1e-12, atol=1e-15)
         dist = np.float32(np.linalg.norm(M["pos"][p] - M["Ow"][M["ref_kf"][p]]))
         assert mx[p] == dist * sf[M["ref_level"][p]] and mn[p] == mx[p] / sf[7]
+
+
+def test_bow_transform_against_brute_force():
+    """DBoW2 transform restated (oracle/bow_oracle.cpp) vs a brute-force numpy descent on a synthetic vocabulary."""
+    voc = po.make_vocabulary(k=7, L=3, seed=3, stop_frac=0.05)
+    rng = np.random.default_rng(5)
+    leaves = np.nonzero(voc["word"] >= 0)[0]
+    f = voc["desc"][rng.choice(leaves, 400)].copy()
+    f[np.arange(400), rng.integers(0, 32, 400)] ^= (1 << rng.integers(0, 8, 400)).astype(np.uint8)
+    f[:40] = f[40:80]                                             # repeated words
+    r = po.bow_transform(voc, f, levelsup=2)
+    bits = np.unpackbits(voc["desc"], axis=1).astype(np.int16)
+    fb = np.unpackbits(f, axis=1).astype(np.int16)
+    words, nodes, weights = [], [], []
+    for i in range(400):
+        node, level, nid = 0, 0, 0
+        while voc["child_start"][node + 1] > voc["child_start"][node]:
+            level += 1
+            ch = voc["children"][voc["child_start"][node]:voc["child_start"][node + 1]]
+            node = int(ch[np.argmin((bits[ch] != fb[i]).sum(1))])     # argmin = first minimum
+            if level == voc["L"] - 2:
+                nid = node
+        words.append(voc["word"][node]); nodes.append(nid); weights.append(voc["weight"][node])
+    words, nodes, weights = np.array(words), np.array(nodes), np.array(weights)
+    assert np.array_equal(r["feat_word"], words) and np.array_equal(r["feat_node"], nodes)
+    keep = weights > 0
+    uw = np.unique(words[keep])
+    assert np.array_equal(r["words"], uw)
+    val = np.array([weights[keep][words[keep] == w].sum() for w in uw])
+    assert np.allclose(r["values"], val / val.sum(), rtol=1e-13) and abs(r["values"].sum() - 1) < 1e-12
+    un = np.unique(nodes[keep])
+    assert np.array_equal(r["fv_nodes"], un)
+    for j, nd in enumerate(un):
+        assert np.array_equal(r["fv_features"][r["fv_start"][j]:r["fv_start"][j + 1]], np.nonzero(keep & (nodes == nd))[0])
