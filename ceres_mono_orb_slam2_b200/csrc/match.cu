@@ -231,15 +231,16 @@ __global__ void __launch_bounds__(kReplayThreads) k_sf_replay(cmos_camera cam, c
                                                              const int* __restrict__ grid_idx, int max_kp,
                                                              SearchFrameArgs a, const uint32_t* __restrict__ g_lists,
                                                              const uint32_t* __restrict__ g_best,
-                                                             const uint16_t* __restrict__ g_cnt) {
+                                                             const uint16_t* __restrict__ g_cnt, int stage_lists) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = min(counts[f], stride);
   const int nq = min(a.last_counts[f], a.last_stride);
   // carve: lists[nq][kListCap] u32 | best[nq] u32 | match[n] i32 | ev_idx[nq] u16 | ev_q[nq] u16 | cnt[nq] u16 |
   //        claimed[n] u8 | ev_bin[nq] u8
-  uint32_t* lists = (uint32_t*)smem_raw;
-  uint32_t* s_best = lists + (size_t)a.last_stride * kListCap;
+  // (large keypoint counts: the lists stay in global memory / L2 and only the small per-query state is staged)
+  const uint32_t* lists = stage_lists ? (const uint32_t*)smem_raw : g_lists + (size_t)f * a.last_stride * kListCap;
+  uint32_t* s_best = (uint32_t*)smem_raw + (stage_lists ? (size_t)a.last_stride * kListCap : 0);
   int* s_match = (int*)(s_best + a.last_stride);
   uint16_t* ev_idx = (uint16_t*)(s_match + stride);
   uint16_t* ev_q = ev_idx + a.last_stride;
@@ -259,9 +260,9 @@ __global__ void __launch_bounds__(kReplayThreads) k_sf_replay(cmos_camera cam, c
   const double* T = a.Tcw + (long long)f * 16;
   const size_t base = (size_t)f * a.last_stride;
 
-  {
+  if (stage_lists) {
     const uint4* src = (const uint4*)(g_lists + base * kListCap);
-    uint4* dst = (uint4*)lists;
+    uint4* dst = (uint4*)smem_raw;
     for (int i = tid; i < nq * kListCap / 4; i += kReplayThreads) dst[i] = src[i];
   }
   for (int i = tid; i < nq; i += kReplayThreads) { s_best[i] = g_best[base + i]; cnt[i] = g_cnt[base + i]; }
@@ -748,9 +749,10 @@ int d2h(T* dst, const T* src, size_t n, cudaStream_t st) {
   CMOS_CUDA_OK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
   return CMOS_OK;
 }
-size_t search_frame_smem(int last_stride, int stride) {
+constexpr size_t kSearchSmemLimit = 220 * 1024;
+size_t search_frame_smem(int last_stride, int stride, bool stage_lists = true) {
   // lists + best | match | ev_idx, ev_q, cnt | claimed | ev_bin
-  return (size_t)last_stride * (kListCap + 1) * 4 + (size_t)stride * 4 + (size_t)last_stride * 3 * 2 + stride + last_stride +
+  return (size_t)last_stride * ((stage_lists ? kListCap : 0) + 1) * 4 + (size_t)stride * 4 + (size_t)last_stride * 3 * 2 + stride + last_stride +
          last_stride + 4 + (size_t)stride * 4 + (size_t)last_stride * 2 + 16;   // + ptr | owner | ext
 }
 size_t search_points_smem(int point_stride, int stride) {
@@ -786,7 +788,7 @@ int cmos_match_create(const cmos_match_params* params, cmos_match_t* out) {
   }
   CMOS_REQUIRE(params->device >= 0 && params->device < ndev, "device %d out of range", params->device);
   CMOS_CUDA_OK(cudaSetDevice(params->device));
-  if (search_frame_smem(params->max_keypoints, params->max_keypoints) > 220 * 1024) {
+  if (search_frame_smem(params->max_keypoints, params->max_keypoints, false) > kSearchSmemLimit) {
     set_error("max_keypoints too large for the search kernels' shared memory");
     return CMOS_ERR_ARG;
   }
@@ -935,9 +937,10 @@ int cmos_match_search_by_projection_frame(cmos_match_t h, const double* Tcw, con
   k_sf_lists<<<dim3((last_stride + kSfWarps - 1) / kSfWarps, B), kSfWarps * 32, 0, st>>>(
       h->cam, h->kps, h->desc, h->counts, h->stride, h->d_grid_start, h->d_grid_idx, h->p.max_keypoints, a, h->d_lists,
       h->d_best, h->d_cnt);
-  k_sf_replay<<<B, kReplayThreads, search_frame_smem(last_stride, h->stride), st>>>(
+  const bool stage = search_frame_smem(last_stride, h->stride, true) <= kSearchSmemLimit;
+  k_sf_replay<<<B, kReplayThreads, search_frame_smem(last_stride, h->stride, stage), st>>>(
       h->cam, h->kps, h->desc, h->counts, h->stride, h->d_grid_start, h->d_grid_idx, h->p.max_keypoints, a, h->d_lists,
-      h->d_best, h->d_cnt);
+      h->d_best, h->d_cnt, stage ? 1 : 0);
   h->timer[1].mark(st);
   CMOS_CUDA_OK(cudaGetLastError());
   h->launches = 2;

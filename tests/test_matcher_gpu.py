@@ -108,13 +108,13 @@ def test_search_frame_overflow_and_reclaim():
     assert nm[0] == onm and np.array_equal(match[0], om)
 
 
-@pytest.mark.parametrize("th,palette,obs_frac", [(6.0, 3, 0.9), (10.0, 40, 0.5), (15.0, 8, 1.0)])
-def test_search_frame_contention_chains(th, palette, obs_frac):
+@pytest.mark.parametrize("th,palette,obs_frac,n", [(6.0, 3, 0.9, 1800), (10.0, 40, 0.5, 1800), (15.0, 8, 1.0, 1800),
+                                                   (8.0, 60, 0.9, 4500)])     # 4500 > what the list staging fits
+def test_search_frame_contention_chains(th, palette, obs_frac, n):
     """Clustered keypoints with descriptors drawn from a small palette: many queries want the same candidates, so
     the claim chains of the greedy assignment are long (the parallel fixed point needs many rounds) while most
     lists stay within the list capacity."""
     rng = np.random.default_rng(int(th) * 100 + palette)
-    n = 1800
     centres = np.stack([rng.uniform(60, W - 60, 40), rng.uniform(40, H - 40, 40)], 1)
     which = rng.integers(0, 40, n)
     kps = np.zeros(n, KP_DTYPE)

@@ -16,11 +16,12 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 2
   python bench.py --steps 2 --warmup 3 --no-ba --no-cpu > $O/ncu_orb.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_ba_local.csv \
   python tools/ba_profile.py local > $O/ncu_ba_local.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/launches_ba_global.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_ba_global.csv \
   python tools/ba_profile.py global 2 > $O/ncu_ba_global.log 2>&1
 # full captures: one step of the ORB+match path, every kernel once
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ -s 75 -c 18 -o $O/full_orb \
-  python bench.py --steps 1 --warmup 3 --no-ba --no-cpu > $O/ncu_full_orb.log 2>&1
+# (pre-pass extraction 12 launches + 3 warm-up steps x 15 = 57 launches before the first timed 64-frame step)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ -s 57 -c 15 -o $O/full_orb \
+  python bench.py --steps 2 --warmup 3 --no-ba --no-cpu > $O/ncu_full_orb.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ -s 30 -c 12 -o $O/full_ba_local \
   python tools/ba_profile.py local > $O/ncu_full_ba_local.log 2>&1
 ls -la $O

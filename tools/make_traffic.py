@@ -1,0 +1,20 @@
+"""profiles/traffic.json from an ncu --set full summary (tools/ncu_summary.py output) of ONE 64-frame step:
+per bench stage, DRAM bytes read + written per launch (summed over the stage's kernels)."""
+import json
+import sys
+
+STAGE = {"k_level0": "pyramid", "k_resize": "pyramid", "k_fast": "fast", "k_octree": "quadtree", "k_blur": "blur",
+         "k_describe": "describe", "k_build_grid": "grid", "k_sf_lists": "search_frame", "k_sf_replay": "search_frame"}
+d = json.load(open(sys.argv[1]))
+out, dur = {}, {}
+for r in d["launches"]:
+    name = r["kernel"].split("::")[-1].split("<")[0].replace("void ", "").strip()
+    st = STAGE.get(name)
+    if st is None or "dram_traffic" not in r:
+        continue
+    out[st] = out.get(st, 0) + int(r["dram_traffic"])
+    dur[st] = dur.get(st, 0.0) + r.get("duration_us", 0.0)
+out["_source"] = f"{d['report']}: dram__bytes_read.sum + dram__bytes_write.sum per launch, one 64-frame step"
+out["_ncu_duration_us"] = {k: round(v, 1) for k, v in dur.items()}
+json.dump(out, open(sys.argv[2], "w"), indent=1)
+print(json.dumps(out, indent=1))
