@@ -92,6 +92,24 @@ class CeresOptimizer:
         return t
 
     # ---- graph upload ----
+    # ---- OptimizeSim3(keyframe_1, keyframe_2, matches12, S12, th2, bFixScale), CeresOptimizer.h:372-375 ----
+    def OptimizeSim3(self, s12, R12, t12, K1, K2, obs1, inv_sigma1, P3D2c, obs2, inv_sigma2, P3D1c, th2: float = 10.0,
+                     max_iterations: int = 100):
+        """-> dict(ret, s, R, t, lie, is_bad, summary).  Per correspondence: keypoint of keyframe 1 + its inv_level_sigma2 +
+        keyframe 2's map point in camera-2 coordinates, and the same the other way round."""
+        n = len(obs1)
+        s = C.c_double(float(s12)); R = np.ascontiguousarray(R12, np.float64).reshape(-1).copy()
+        t = np.ascontiguousarray(t12, np.float64).copy()
+        k1 = np.ascontiguousarray(K1, np.float32); k2 = np.ascontiguousarray(K2, np.float32)
+        a = (np.ascontiguousarray(obs1, np.float32), np.ascontiguousarray(inv_sigma1, np.float32),
+             np.ascontiguousarray(P3D2c, np.float64), np.ascontiguousarray(obs2, np.float32),
+             np.ascontiguousarray(inv_sigma2, np.float32), np.ascontiguousarray(P3D1c, np.float64))
+        bad = np.zeros(max(n, 1), np.uint8); lie = np.zeros(7); ninl = C.c_int32(); summ = BaSummary()
+        check(self._L.cmos_ba_optimize_sim3(self._h, n, C.byref(s), ptr(R), ptr(t), ptr(k1), ptr(k2), *[ptr(x) for x in a],
+                                            C.c_float(th2), int(max_iterations), ptr(bad), ptr(lie), C.byref(ninl),
+                                            C.byref(summ)))
+        return dict(ret=ninl.value, s=s.value, R=R.reshape(3, 3), t=t, lie=lie, is_bad=bad[:n], summary=summ.as_dict())
+
     def set_problem(self, cams, cam_flags, points, obs_cam, obs_pt, uv, inv_sigma2, K4):
         cams = np.ascontiguousarray(cams, np.float64); points = np.ascontiguousarray(points, np.float64)
         cf = np.ascontiguousarray(cam_flags, np.uint8)

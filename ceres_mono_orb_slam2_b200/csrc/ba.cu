@@ -231,6 +231,234 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose_opt(PoseArgs a) {
 }
 
 // =================================================================================================
+// OptimizeSim3 (CeresOptimizer.cc:601-735): one CTA runs the whole LM solve over the 7-vector sim12
+// =================================================================================================
+struct Sim3Args {
+  int n;                       // correspondences (2 residual blocks each)
+  double s12, R12[9], t12[3];  // initial S12
+  double K1[4], K2[4];
+  const float* obs1; const float* inv_sigma1; const double* P3D2c;
+  const float* obs2; const float* inv_sigma2; const double* P3D1c;
+  double huber_a;
+  int max_iterations;
+  uint8_t* is_bad;             // [n]
+  double* out;                 // [24]: lie(7), s, R(9), t(3), return value, iterations, successful, termination
+  cmos_ba_summary* summary;
+  double* trace;
+};
+
+template <int N>
+__device__ bool chol_solve_n(double (*A)[N], double* b) {
+  for (int j = 0; j < N; j++) {
+    double d = A[j][j];
+    for (int k = 0; k < j; k++) d -= A[j][k] * A[j][k];
+    if (!(d > 0.0) || !isfinite(d)) return false;
+    d = sqrt(d);
+    A[j][j] = d;
+    for (int i = j + 1; i < N; i++) {
+      double s = A[i][j];
+      for (int k = 0; k < j; k++) s -= A[i][k] * A[j][k];
+      A[i][j] = s / d;
+    }
+  }
+  for (int i = 0; i < N; i++) {
+    double s = b[i];
+    for (int k = 0; k < i; k++) s -= A[i][k] * b[k];
+    b[i] = s / A[i][i];
+  }
+  for (int i = N - 1; i >= 0; i--) {
+    double s = b[i];
+    for (int k = i + 1; k < N; k++) s -= A[k][i] * b[k];
+    b[i] = s / A[i][i];
+  }
+  return true;
+}
+
+#define SYM7(r, c) ((r) * 7 - (r) * ((r) - 1) / 2 + ((c) - (r)))   // packed upper triangle of a 7x7, r <= c
+
+__device__ __forceinline__ double huber_eval(double s, double a, double* w) {
+  const double b = a * a;
+  if (s > b) { const double r = sqrt(s); *w = fmax(2.2250738585072014e-308, a / r); return 0.5 * (2.0 * a * r - b); }
+  *w = 1.0;
+  return 0.5 * s;
+}
+
+__global__ void __launch_bounds__(kPoseThreads) k_sim3_opt(Sim3Args a) {
+  __shared__ double s_x[2][7];
+  __shared__ Sim3D s_S, s_Si;            // exp(x) and its inverse for the point being evaluated
+  __shared__ double s_red[kPoseThreads / 32][36];
+  __shared__ double s_acc[36];           // 28 H (packed upper) | 7 g | cost
+  __shared__ double s_scale[7];
+  __shared__ double s_scratch[33];
+  __shared__ LmState st;
+  __shared__ double s_mcc, s_step_norm;
+  __shared__ int s_ok;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = a.n;
+  if (tid == 0) {
+    Sim3D S0; S0.s = a.s12;
+    for (int i = 0; i < 9; i++) S0.R[i] = a.R12[i];
+    for (int i = 0; i < 3; i++) S0.t[i] = a.t12[i];
+    sim3_log(S0, s_x[0]);
+    lm_init(st, a.max_iterations, 0);
+  }
+  __syncthreads();
+  auto set_point = [&](const double* x) {          // thread 0
+    sim3_exp(x, s_S);
+    sim3_inverse(s_S, s_Si);
+  };
+  auto block_eval = [&](int b, double* r, double* J) {
+    const int i = b >> 1;
+    if ((b & 1) == 0)
+      sim3_error_term(s_S, a.P3D2c + 3 * i, a.K1[0], a.K1[1], a.K1[2], a.K1[3], (double)a.obs1[2 * i], (double)a.obs1[2 * i + 1],
+                      (double)a.inv_sigma1[i], r, J);
+    else
+      sim3_error_term(s_Si, a.P3D1c + 3 * i, a.K2[0], a.K2[1], a.K2[2], a.K2[3], (double)a.obs2[2 * i], (double)a.obs2[2 * i + 1],
+                      (double)a.inv_sigma2[i], r, J);
+  };
+  for (;;) {
+    if (st.need_lin) {
+      if (tid == 0) set_point(s_x[st.cur]);
+      __syncthreads();
+      double acc[36];
+#pragma unroll
+      for (int k = 0; k < 36; k++) acc[k] = 0.0;
+      for (int b = tid; b < 2 * n; b += kPoseThreads) {
+        double r[2], J[14], w;
+        block_eval(b, r, J);
+        acc[35] += huber_eval(r[0] * r[0] + r[1] * r[1], a.huber_a, &w);
+#pragma unroll
+        for (int p = 0; p < 7; p++) {
+          const double j0 = w * J[p], j1 = w * J[7 + p];
+#pragma unroll
+          for (int c = p; c < 7; c++) acc[SYM7(p, c)] += j0 * J[c] + j1 * J[7 + c];
+          acc[28 + p] += j0 * r[0] + j1 * r[1];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 36; k++) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) s_red[warp][k] = v;
+      }
+      __syncthreads();
+      if (tid < 36) {
+        double t = 0.0;
+        for (int w2 = 0; w2 < kPoseThreads / 32; w2++) t += s_red[w2][tid];
+        s_acc[tid] = t;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        const double* x = s_x[st.cur];
+        if (st.first)
+          for (int k = 0; k < 7; k++) s_scale[k] = 1.0 / (1.0 + sqrt(s_acc[SYM7(k, k)]));
+        double ng[7], xp[7], xn = 0.0, gm = 0.0;
+        for (int k = 0; k < 7; k++) { ng[k] = -s_acc[28 + k]; xn += x[k] * x[k]; }
+        sim3_plus(x, ng, xp);
+        for (int k = 0; k < 7; k++) gm = fmax(gm, fabs(x[k] - xp[k]));
+        lm_after_linearize(st, s_acc[35], gm, sqrt(xn), a.trace);
+      }
+      __syncthreads();
+    }
+    if (st.done) break;
+    if (tid == 0) {
+      const double* x = s_x[st.cur];
+      double* cand = s_x[st.cur ^ 1];
+      double A[7][7], b[7], D2[7], gs[7];
+      for (int r = 0; r < 7; r++) {
+        D2[r] = fmin(fmax(s_scale[r] * s_scale[r] * s_acc[SYM7(r, r)], kMinLmDiag), kMaxLmDiag) / st.radius;
+        gs[r] = s_scale[r] * s_acc[28 + r];
+        b[r] = gs[r];
+        for (int c = 0; c < 7; c++) {
+          const int lo = r < c ? r : c, hi = r < c ? c : r;
+          A[r][c] = s_scale[r] * s_scale[c] * s_acc[SYM7(lo, hi)] + (r == c ? D2[r] : 0.0);
+        }
+      }
+      bool ok = chol_solve_n<7>(A, b);
+      double mcc = 0.0, delta[7];
+      for (int r = 0; r < 7; r++) {
+        const double step = -b[r];
+        if (!isfinite(step)) ok = false;
+        mcc += step * (D2[r] * step - gs[r]);
+        delta[r] = step * s_scale[r];
+      }
+      mcc *= 0.5;
+      double sn = 0.0;
+      if (ok) {
+        sim3_plus(x, delta, cand);
+        for (int k = 0; k < 7; k++) sn += (x[k] - cand[k]) * (x[k] - cand[k]);
+        set_point(cand);
+      }
+      s_ok = ok; s_mcc = mcc; s_step_norm = sqrt(sn);
+    }
+    __syncthreads();
+    double cand_cost = 0.0;
+    if (s_ok && s_mcc > 0.0) {
+      double c = 0.0, w;
+      for (int b = tid; b < 2 * n; b += kPoseThreads) {
+        double r[2];
+        block_eval(b, r, nullptr);
+        c += huber_eval(r[0] * r[0] + r[1] * r[1], a.huber_a, &w);
+      }
+      cand_cost = block_sum(c, s_scratch);
+    }
+    if (tid == 0) lm_decide(st, s_ok != 0, s_mcc, cand_cost, s_step_norm, a.trace);
+    __syncthreads();
+    if (st.done) break;
+  }
+  // S12 = exp(sim12); CheckOutlier with Eigen::Quaterniond(s R) — Eigen's matrix -> quaternion conversion applied to the
+  // SCALED rotation, then its unit-quaternion rotation polynomial (CeresOptimizer.cc:702-726, 227-241)
+  if (tid == 0) set_point(s_x[st.cur]);
+  __syncthreads();
+  auto check = [&](const Sim3D& T, const double* K4, double u, double v, double inv_sigma, const double* P) {
+    double M[9], q[4];
+    for (int i = 0; i < 9; i++) M[i] = T.s * T.R[i];
+    const double tr = M[0] + M[4] + M[8];
+    if (tr > 0) {
+      double t = sqrt(tr + 1.0);
+      q[3] = 0.5 * t; t = 0.5 / t;
+      q[0] = (M[7] - M[5]) * t; q[1] = (M[2] - M[6]) * t; q[2] = (M[3] - M[1]) * t;
+    } else {
+      int i = 0;
+      if (M[4] > M[0]) i = 1;
+      if (M[8] > M[4 * i]) i = 2;
+      const int j = (i + 1) % 3, k = (j + 1) % 3;
+      double t = sqrt(M[4 * i] - M[4 * j] - M[4 * k] + 1.0);
+      q[i] = 0.5 * t; t = 0.5 / t;
+      q[3] = (M[3 * k + j] - M[3 * j + k]) * t; q[j] = (M[3 * j + i] + M[3 * i + j]) * t; q[k] = (M[3 * k + i] + M[3 * i + k]) * t;
+    }
+    const double uv0 = 2 * (q[1] * P[2] - q[2] * P[1]), uv1 = 2 * (q[2] * P[0] - q[0] * P[2]), uv2 = 2 * (q[0] * P[1] - q[1] * P[0]);
+    const double p0 = P[0] + q[3] * uv0 + (q[1] * uv2 - q[2] * uv1) + T.t[0];
+    const double p1 = P[1] + q[3] * uv1 + (q[2] * uv0 - q[0] * uv2) + T.t[1];
+    const double p2 = P[2] + q[3] * uv2 + (q[0] * uv1 - q[1] * uv0) + T.t[2];
+    const double px = K4[0] * p0 + K4[2] * p2, py = K4[1] * p1 + K4[3] * p2;
+    const double eu = u - px / p2, ev = v - py / p2;
+    return (eu * eu + ev * ev) * inv_sigma > a.huber_a * a.huber_a;
+  };
+  int bad = 0;
+  for (int i = tid; i < n; i += kPoseThreads) {
+    const bool b12 = check(s_S, a.K1, (double)a.obs1[2 * i], (double)a.obs1[2 * i + 1], (double)a.inv_sigma1[i], a.P3D2c + 3 * i);
+    const bool b21 = check(s_Si, a.K2, (double)a.obs2[2 * i], (double)a.obs2[2 * i + 1], (double)a.inv_sigma2[i], a.P3D1c + 3 * i);
+    a.is_bad[i] = b12 || b21;
+    bad += b12 || b21;
+  }
+  const double nbad = block_sum((double)bad, s_scratch);
+  if (tid == 0) {
+    const double* x = s_x[st.cur];
+    for (int k = 0; k < 7; k++) a.out[k] = x[k];
+    a.out[7] = s_S.s;
+    for (int k = 0; k < 9; k++) a.out[8 + k] = s_S.R[k];
+    for (int k = 0; k < 3; k++) a.out[17 + k] = s_S.t[k];
+    const int good = n - (int)nbad;
+    a.out[20] = good < 10 ? 0.0 : (double)good;
+    if (a.summary) {
+      cmos_ba_summary s;
+      s.iterations = st.iteration; s.successful_steps = st.successful; s.termination = st.termination;
+      s.jacobian_evaluations = st.jac_evals; s.initial_cost = st.initial_cost; s.final_cost = st.x_cost;
+      *a.summary = s;
+    }
+  }
+}
+
+// =================================================================================================
 // General engine (LocalBundleAdjustment / BundleAdjustment)
 // =================================================================================================
 struct BaDev {
@@ -1403,6 +1631,11 @@ struct cmos_ba {
   float* d_o_w = nullptr;
   uint8_t *d_o_mode = nullptr, *d_cam_flags = nullptr, *d_erase = nullptr;
   double* d_Linv = nullptr;
+  // OptimizeSim3 staging (allocated on first use)
+  size_t sim3_cap = 0;
+  float *ds_obs = nullptr, *ds_sig = nullptr;   // [2][cap][2], [2][cap]
+  double *ds_pts = nullptr, *ds_out = nullptr;   // [2][cap][3], [24]
+  uint8_t* ds_bad = nullptr;
   int* d_pan_tiles = nullptr;               // active row tiles of every panel of the blocked factorisation
   std::vector<int> pan_start, pan_first_col; // [n_panels + 1], [n_panels]
   size_t cap_pan_tiles = 0;
@@ -1634,6 +1867,8 @@ int cmos_ba_destroy(cmos_ba_t h) {
                   d.yc, d.part, d.st, h->d_Linv, h->d_pan_tiles, h->d_band_blk, h->d_trace, h->d_summaries, h->dp_pose, h->dp_xw, h->dp_uv, h->dp_w,
                   h->dp_n, h->dp_inl, h->dp_out, h->dp_sum, h->dp_trace};
   for (void* b : bufs)
+    if (b) cudaFree(b);
+  for (void* b : {(void*)h->ds_obs, (void*)h->ds_sig, (void*)h->ds_pts, (void*)h->ds_out, (void*)h->ds_bad})
     if (b) cudaFree(b);
   if (h->stop_registered_by_us && h->stop_host_page) cudaHostUnregister((void*)h->stop_host_page);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -2058,6 +2293,61 @@ int cmos_ba_solve_time(cmos_ba_t h, double* ms, int64_t* calls) {
   h->timer.fold();
   *ms = h->timer.total_ms[0];
   *calls = h->timer.calls;
+  return CMOS_OK;
+}
+
+int cmos_ba_optimize_sim3(cmos_ba_t h, int32_t n, double* s12, double* R12, double* t12, const float* K1, const float* K2,
+                          const float* obs1, const float* inv_sigma1, const double* P3D2c, const float* obs2,
+                          const float* inv_sigma2, const double* P3D1c, float th2, int32_t max_iterations,
+                          uint8_t* is_bad, double* lie7, int32_t* n_inliers, cmos_ba_summary* summary) {
+  CMOS_REQUIRE(h && s12 && R12 && t12 && K1 && K2 && n_inliers, "null argument");
+  CMOS_REQUIRE(n >= 0 && (n == 0 || (obs1 && inv_sigma1 && P3D2c && obs2 && inv_sigma2 && P3D1c && is_bad)), "null argument");
+  CMOS_REQUIRE(max_iterations >= 0 && max_iterations + 1 < h->trace_rows, "max_iterations %d too large", max_iterations);
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  cudaStream_t st = h->stream;
+  const size_t cap = std::max<size_t>(n, 1);
+  if (cap > h->sim3_cap) {
+    for (void* b : {(void*)h->ds_obs, (void*)h->ds_sig, (void*)h->ds_pts, (void*)h->ds_out, (void*)h->ds_bad})
+      if (b) cudaFree(b);
+    h->ds_obs = nullptr; h->ds_sig = nullptr; h->ds_pts = nullptr; h->ds_out = nullptr; h->ds_bad = nullptr; h->sim3_cap = 0;
+    if (!alloc(&h->ds_obs, 4 * cap) || !alloc(&h->ds_sig, 2 * cap) || !alloc(&h->ds_pts, 6 * cap) || !alloc(&h->ds_out, 24) ||
+        !alloc(&h->ds_bad, cap)) {
+      set_error("device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return CMOS_ERR_CUDA;
+    }
+    h->sim3_cap = cap;
+  }
+  const size_t c = h->sim3_cap;
+  auto up = [&](void* dst, const void* src, size_t bytes) { return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
+  CMOS_CUDA_OK(up(h->ds_obs, obs1, (size_t)n * 2 * sizeof(float)));
+  CMOS_CUDA_OK(up(h->ds_obs + 2 * c, obs2, (size_t)n * 2 * sizeof(float)));
+  CMOS_CUDA_OK(up(h->ds_sig, inv_sigma1, (size_t)n * sizeof(float)));
+  CMOS_CUDA_OK(up(h->ds_sig + c, inv_sigma2, (size_t)n * sizeof(float)));
+  CMOS_CUDA_OK(up(h->ds_pts, P3D2c, (size_t)n * 3 * sizeof(double)));
+  CMOS_CUDA_OK(up(h->ds_pts + 3 * c, P3D1c, (size_t)n * 3 * sizeof(double)));
+  Sim3Args a{};
+  a.n = n; a.s12 = *s12;
+  for (int i = 0; i < 9; i++) a.R12[i] = R12[i];
+  for (int i = 0; i < 3; i++) a.t12[i] = t12[i];
+  for (int i = 0; i < 4; i++) { a.K1[i] = (double)K1[i]; a.K2[i] = (double)K2[i]; }
+  a.obs1 = h->ds_obs; a.obs2 = h->ds_obs + 2 * c; a.inv_sigma1 = h->ds_sig; a.inv_sigma2 = h->ds_sig + c;
+  a.P3D2c = h->ds_pts; a.P3D1c = h->ds_pts + 3 * c;
+  a.huber_a = std::sqrt((double)th2);
+  a.max_iterations = max_iterations;
+  a.is_bad = h->ds_bad; a.out = h->ds_out; a.summary = h->dp_sum; a.trace = h->dp_trace;
+  k_sim3_opt<<<1, kPoseThreads, 0, st>>>(a);
+  CMOS_CUDA_OK(cudaGetLastError());
+  h->launches = 1;
+  double out[24];
+  CMOS_CUDA_OK(cudaMemcpyAsync(out, h->ds_out, sizeof(out), cudaMemcpyDeviceToHost, st));
+  if (n) CMOS_CUDA_OK(cudaMemcpyAsync(is_bad, h->ds_bad, n, cudaMemcpyDeviceToHost, st));
+  if (summary) CMOS_CUDA_OK(cudaMemcpyAsync(summary, h->dp_sum, sizeof(cmos_ba_summary), cudaMemcpyDeviceToHost, st));
+  CMOS_CUDA_OK(cudaStreamSynchronize(st));
+  if (lie7) for (int i = 0; i < 7; i++) lie7[i] = out[i];
+  *s12 = out[7];
+  for (int i = 0; i < 9; i++) R12[i] = out[8 + i];
+  for (int i = 0; i < 3; i++) t12[i] = out[17 + i];
+  *n_inliers = (int)out[20];
   return CMOS_OK;
 }
 

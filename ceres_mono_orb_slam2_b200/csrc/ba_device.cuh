@@ -259,3 +259,185 @@ __device__ __forceinline__ double block_max(double v, double* scratch) {
 }
 
 }  // namespace cmos
+
+// ---- Sim3 (OptimizeSim3: include/CeresOptimizer.h:168-268, src/CeresOptimizer.cc:24-47) -----------------------------
+// Lie algebra vector [upsilon(3), omega(3), sigma]; group element as scale, rotation matrix, translation.  exp / log
+// are Sophus' closed forms (sim3.hpp, sim_details.hpp: calcW / calcWInv with the 1e-10 small-angle branches); the
+// rotation goes through Rodrigues' formula here (the CPU oracle goes through the quaternion exponential).
+namespace cmos {
+
+struct Sim3D { double s, R[9], t[3]; };
+
+__device__ __forceinline__ void hat3(const double* w, double* O) {
+  O[0] = 0; O[1] = -w[2]; O[2] = w[1]; O[3] = w[2]; O[4] = 0; O[5] = -w[0]; O[6] = -w[1]; O[7] = w[0]; O[8] = 0;
+}
+__device__ __forceinline__ void mul33(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+__device__ __forceinline__ void mul3v(const double* A, const double* v, double* o) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) o[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
+}
+
+__device__ inline void sim3_calc_w(const double* O, const double* O2, double theta, double sigma, double scale, double* W) {
+  const double eps = 1e-10;
+  double A, B, C;
+  if (fabs(sigma) < eps) {
+    C = 1.0;
+    if (fabs(theta) < eps) { A = 0.5; B = 1.0 / 6.0; }
+    else { const double t2 = theta * theta; A = (1.0 - cos(theta)) / t2; B = (theta - sin(theta)) / (t2 * theta); }
+  } else {
+    C = (scale - 1.0) / sigma;
+    if (fabs(theta) < eps) {
+      const double s2 = sigma * sigma;
+      A = ((sigma - 1.0) * scale + 1.0) / s2;
+      B = (scale * 0.5 * s2 + scale - 1.0 - sigma * scale) / (s2 * sigma);
+    } else {
+      const double t2 = theta * theta, a = scale * sin(theta), b = scale * cos(theta), c = t2 + sigma * sigma;
+      A = (a * sigma + (1.0 - b) * theta) / (theta * c);
+      B = (C - ((b - 1.0) * sigma + a * theta) / c) * 1.0 / t2;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; i++) W[i] = A * O[i] + B * O2[i] + ((i % 4 == 0) ? C : 0.0);
+}
+
+__device__ inline void sim3_calc_w_inv(const double* O, const double* O2, double theta, double sigma, double scale, double* W) {
+  const double eps = 1e-10;
+  const double scale_sq = scale * scale, t2 = theta * theta, st = sin(theta), ct = cos(theta);
+  double a, b, c;
+  if (fabs(sigma * sigma) < eps) {
+    c = 1.0 - 0.5 * sigma;
+    a = -0.5;
+    if (fabs(t2) < eps) b = 1.0 / 12.0;
+    else b = (theta * st + 2.0 * ct - 2.0) / (2.0 * t2 * (ct - 1.0));
+  } else {
+    const double scale_cu = scale_sq * scale;
+    c = sigma / (scale - 1.0);
+    if (fabs(t2) < eps) {
+      a = (-sigma * scale + scale - 1.0) / ((scale - 1.0) * (scale - 1.0));
+      b = (scale_sq * sigma - 2.0 * scale_sq + scale * sigma + 2.0 * scale) / (2.0 * scale_cu - 6.0 * scale_sq + 6.0 * scale - 2.0);
+    } else {
+      const double ss = scale * st, sc = scale * ct;
+      a = (theta * sc - theta - sigma * ss) / (theta * (scale_sq - 2.0 * sc + 1.0));
+      b = -scale * (theta * ss - theta * st + sigma * sc - scale * sigma + sigma * ct - sigma) /
+          (t2 * (scale_cu - 2.0 * scale * sc - scale_sq + 2.0 * sc + scale - 1.0));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; i++) W[i] = a * O[i] + b * O2[i] + ((i % 4 == 0) ? c : 0.0);
+}
+
+__device__ inline void sim3_exp(const double* v, Sim3D& S) {
+  const double* w = v + 3;
+  const double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], theta = sqrt(t2);
+  double O[9], O2[9], A, B;
+  hat3(w, O);
+  mul33(O, O, O2);
+  if (t2 < 1e-20) { A = 1.0 - t2 / 6.0; B = 0.5 - t2 / 24.0; }
+  else { A = sin(theta) / theta; B = (1.0 - cos(theta)) / t2; }
+#pragma unroll
+  for (int i = 0; i < 9; i++) S.R[i] = A * O[i] + B * O2[i] + ((i % 4 == 0) ? 1.0 : 0.0);
+  S.s = exp(v[6]);
+  double W[9];
+  sim3_calc_w(O, O2, theta, v[6], S.s, W);
+  mul3v(W, v, S.t);
+}
+
+__device__ inline void sim3_log(const Sim3D& S, double* v) {
+  // rotation -> unit quaternion (Shepperd) -> rotation vector (2 atan2(|q_v|, q_w) / |q_v|) q_v
+  const double* R = S.R;
+  double q[4];
+  const double tr = R[0] + R[4] + R[8];
+  if (tr > 0) {
+    double t = sqrt(tr + 1.0);
+    q[3] = 0.5 * t; t = 0.5 / t;
+    q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+    q[i] = 0.5 * t; t = 0.5 / t;
+    q[3] = (R[3 * k + j] - R[3 * j + k]) * t; q[j] = (R[3 * j + i] + R[3 * i + j]) * t; q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+  }
+  const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; i++) q[i] /= qn;
+  const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2], qw = q[3];
+  double two_atan, theta;
+  if (n2 < 1e-20) { two_atan = 2.0 / qw - 2.0 / 3.0 * n2 / (qw * qw * qw); theta = 2.0 * n2 / qw; }
+  else {
+    const double n = sqrt(n2);
+    two_atan = 2.0 * (qw < 0 ? -atan2(n, -qw) : atan2(n, qw)) / n;
+    if (fabs(qw) < 1e-10) two_atan = (qw >= 0 ? 3.14159265358979323846 : -3.14159265358979323846) / n;
+    theta = two_atan * n;
+  }
+  v[3] = two_atan * q[0]; v[4] = two_atan * q[1]; v[5] = two_atan * q[2];
+  v[6] = log(S.s);
+  double O[9], O2[9], W[9];
+  hat3(v + 3, O);
+  mul33(O, O, O2);
+  sim3_calc_w_inv(O, O2, theta, v[6], S.s, W);
+  mul3v(W, S.t, v);
+}
+
+__device__ inline void sim3_mul(const Sim3D& a, const Sim3D& b, Sim3D& o) {
+  o.s = a.s * b.s;
+  mul33(a.R, b.R, o.R);
+  double r[3];
+  mul3v(a.R, b.t, r);
+#pragma unroll
+  for (int i = 0; i < 3; i++) o.t[i] = a.s * r[i] + a.t[i];
+}
+
+__device__ inline void sim3_inverse(const Sim3D& a, Sim3D& o) {
+  o.s = 1.0 / a.s;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) o.R[3 * i + j] = a.R[3 * j + i];
+  double r[3];
+  mul3v(o.R, a.t, r);
+#pragma unroll
+  for (int i = 0; i < 3; i++) o.t[i] = -o.s * r[i];
+}
+
+// Sim3Parameterization::Plus (CeresOptimizer.cc:24-41)
+__device__ inline void sim3_plus(const double* x, const double* delta, double* out) {
+  double d[7];
+#pragma unroll
+  for (int i = 0; i < 7; i++) d[i] = delta[i];
+  d[6] = fmax(d[6], -20.0);
+  Sim3D a, b, c;
+  sim3_exp(x, a);
+  sim3_exp(d, b);
+  sim3_mul(a, b, c);
+  sim3_log(c, out);
+}
+
+// Sim3ErrorTerm::Evaluate for p = S * P (or S^-1 * P): residual and, if J != null, the 2x7 Jacobian, times inv_sigma
+__device__ __forceinline__ void sim3_error_term(const Sim3D& T, const double* __restrict__ P, double fx, double fy, double cx,
+                                                double cy, double u, double v, double inv_sigma, double* r, double* J) {
+  double rp[3];
+  mul3v(T.R, P, rp);
+  const double X = T.s * rp[0] + T.t[0], Y = T.s * rp[1] + T.t[1], Z = T.s * rp[2] + T.t[2];
+  const double pr0 = fx * X + cx * Z, pr1 = fy * Y + cy * Z;
+  r[0] = inv_sigma * (pr0 / Z - u);
+  r[1] = inv_sigma * (pr1 / Z - v);
+  if (!J) return;
+  const double Z2 = Z * Z;
+  const double a00 = fx / Z, a02 = -X * fx / Z2, a11 = fy / Z, a12 = -fy * Y / Z2;
+  // J_camera * [I | -hat(p) | p]
+  J[0] = inv_sigma * a00; J[1] = 0.0; J[2] = inv_sigma * a02;
+  J[3] = inv_sigma * (a02 * Y); J[4] = inv_sigma * (a00 * Z - a02 * X); J[5] = inv_sigma * (-a00 * Y);
+  J[6] = inv_sigma * (a00 * X + a02 * Z);
+  J[7] = 0.0; J[8] = inv_sigma * a11; J[9] = inv_sigma * a12;
+  J[10] = inv_sigma * (-a11 * Z + a12 * Y); J[11] = inv_sigma * (-a12 * X); J[12] = inv_sigma * (a11 * X);
+  J[13] = inv_sigma * (a11 * Y + a12 * Z);
+}
+
+}  // namespace cmos

@@ -307,3 +307,41 @@ def make_ba_problem_fast(n_cams: int, n_points: int, obs_per_point: int, seed: i
     init_pts = Xw + rng.normal(0, point_noise / np.sqrt(3), Xw.shape)
     return dict(poses=init_poses, true_poses=poses, fixed=fixed, points=init_pts, true_points=Xw, obs_cam=obs_cam,
                 obs_pt=obs_pt, uv=uv.astype(np.float32), inv_sigma2=inv_s2, K=Kf)
+
+
+def make_sim3_problem(n: int = 300, seed: int = 6, K=KITTI_K, scale: float = 1.08, outlier_frac: float = 0.1,
+                      init_noise=(0.03, 0.1, 0.03)):
+    """OptimizeSim3 inputs: n map points seen by two keyframes whose maps differ by a similarity S12 (camera-1 point =
+    s12 R12 * camera-2 point + t12).  Returns the per-correspondence arrays of cmos_ba_optimize_sim3, the true S12 and a
+    perturbed initial one."""
+    rng = np.random.default_rng(seed)
+    Kf = np.array(K, np.float32).astype(np.float64)
+    fx, fy, cx, cy = Kf
+    # points in camera-1 coordinates (metric of map 1)
+    z = rng.uniform(4, 40, n)
+    u1 = rng.uniform(60, 1180, n); v1 = rng.uniform(40, 336, n)
+    P1 = np.stack([(u1 - cx) / fx * z, (v1 - cy) / fy * z, z], 1)
+    rv = rng.normal(0, 0.06, 3)
+    th = np.linalg.norm(rv); k = rv / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R12 = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+    t12 = np.array([0.4, -0.05, 0.2]) + rng.normal(0, 0.05, 3)
+    P2 = ((P1 - t12) @ R12) / scale                      # S12^-1 * P1
+    u2 = fx * P2[:, 0] / P2[:, 2] + cx; v2 = fy * P2[:, 1] / P2[:, 2] + cy
+    oc1 = _octaves(rng, n); oc2 = _octaves(rng, n)
+    is1 = inv_sigma2_table()[oc1]; is2 = inv_sigma2_table()[oc2]
+    obs1 = np.stack([u1, v1], 1) + rng.normal(0, 1.0, (n, 2)) / np.sqrt(is1.astype(np.float64))[:, None]
+    obs2 = np.stack([u2, v2], 1) + rng.normal(0, 1.0, (n, 2)) / np.sqrt(is2.astype(np.float64))[:, None]
+    n_out = int(outlier_frac * n)
+    idx = rng.choice(n, n_out, replace=False)
+    obs1[idx[: n_out // 2]] += rng.uniform(-40, 40, (n_out // 2, 2))
+    obs2[idx[n_out // 2:]] += rng.uniform(-40, 40, (n_out - n_out // 2, 2))
+    # the two maps' own (noisy) point estimates
+    P1n = P1 + rng.normal(0, 0.02, P1.shape); P2n = P2 + rng.normal(0, 0.02, P2.shape)
+    rv0 = rng.normal(0, init_noise[0] / np.sqrt(3), 3)
+    th0 = np.linalg.norm(rv0); k0 = rv0 / th0
+    K0 = np.array([[0, -k0[2], k0[1]], [k0[2], 0, -k0[0]], [-k0[1], k0[0], 0]])
+    R0 = (np.eye(3) + np.sin(th0) * K0 + (1 - np.cos(th0)) * K0 @ K0) @ R12
+    return dict(obs1=obs1.astype(np.float32), inv_sigma1=is1, P3D2c=P2n, obs2=obs2.astype(np.float32), inv_sigma2=is2, P3D1c=P1n,
+                K=np.array(K, np.float32), s_true=scale, R_true=R12, t_true=t12, s0=scale * float(np.exp(rng.normal(0, init_noise[2]))),
+                R0=R0, t0=t12 + rng.normal(0, init_noise[1] / np.sqrt(3), 3))

@@ -504,6 +504,21 @@ int cmos_ba_bundle_adjustment(cmos_ba_t h, int32_t n_cams, double* cams, const u
                               const float* uv, const float* inv_sigma2, const float* K4, int32_t n_iterations,
                               int32_t robust, const uint8_t* stop_flag, cmos_ba_summary* summary);
 
+/* CeresOptimizer::OptimizeSim3(keyframe_1, keyframe_2, matches12, S12, th2, bFixScale) (CeresOptimizer.cc:601-735;
+ * Sim3ErrorTerm / Sim3Parameterization include/CeresOptimizer.h:168-268, CeresOptimizer.cc:24-47).
+ *   S12 in/out as scale, rotation (row-major 3x3), translation — Sophus::Sim3d's scale(), rotationMatrix(), translation()
+ *   K1, K2          fx, fy, cx, cy of the two keyframes (float, widened)
+ *   per correspondence (the reference's n_correspondences loop, :646-693): obs1 = keypoint of keyframe 1, inv_sigma1 =
+ *   its inv_level_sigma2, P3D2c = keyframe 2's map point in camera-2 coordinates (R2cw * Xw + t2cw); obs2, inv_sigma2,
+ *   P3D1c likewise
+ *   th2             squared Huber width (LoopClosing passes 10); max_iterations: the reference uses 100
+ *   is_bad [n] out  is_outlier_12 || is_outlier_21 (:702-726);  lie7 out (may be NULL) = the optimised sim12
+ *   n_inliers out   the function's return value (0 when fewer than 10 remain); bFixScale is ignored by the reference */
+int cmos_ba_optimize_sim3(cmos_ba_t h, int32_t n, double* s12, double* R12, double* t12, const float* K1, const float* K2,
+                          const float* obs1, const float* inv_sigma1, const double* P3D2c, const float* obs2,
+                          const float* inv_sigma2, const double* P3D1c, float th2, int32_t max_iterations,
+                          uint8_t* is_bad, double* lie7, int32_t* n_inliers, cmos_ba_summary* summary);
+
 /* Multi-GPU global bundle adjustment (no counterpart in the reference, which is single process).
  * One process per GPU.  Map points — and with them their observations — are partitioned over the ranks;
  * keyframes are replicated.  Each rank uploads ALL keyframes but only ITS points/observations with

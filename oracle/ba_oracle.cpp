@@ -663,4 +663,370 @@ void ba_oracle_global(int K, double* cams, const uint8_t* cam_const, int M, doub
                   summary, trace, trace_cap);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// CeresOptimizer::OptimizeSim3 (CeresOptimizer.cc:601-735): one 7-vector (Sim3 Lie algebra, [upsilon, omega, sigma]) is
+// optimised over 2 x n reprojection residuals — keyframe-2 points seen in keyframe 1 through S12, keyframe-1 points seen
+// in keyframe 2 through S12^-1 (Sim3ErrorTerm, include/CeresOptimizer.h:168-255) — with HuberLoss(sqrt(th2)),
+// Sim3Parameterization (Plus = log(exp(x) * exp(delta)), sigma step clamped at -20, identity local Jacobian,
+// CeresOptimizer.cc:24-47), max 100 iterations, Ceres defaults otherwise.  The cost functor's Jacobian is the LEFT
+// perturbation formula for both directions while Plus multiplies on the right; that is the reference's behaviour and is
+// reproduced.  sqrt_information = inv_sigma * I with inv_sigma = inv_level_sigma2s_ (quirk Q1 again).
+// Sophus (un-vendored, unpinned) provides Sim3d::exp / log / inverse; they are restated from Sophus' published
+// closed forms (so3.hpp, rxso3.hpp, sim3.hpp, sim_details.hpp: quaternion exponential, calcW / calcWInv with the
+// 1e-10 small-angle branches).  PARITY UNPINNED.
+}  // extern "C" (the helpers below have C++ linkage: their names — exp, log — must not collide with libm's)
+
+namespace sim3o {
+constexpr double kEps = 1e-10;
+struct Sim3 { double s, q[4] /*x y z w, unit*/, t[3]; };
+
+void hat(const double* w, double* O) { O[0] = 0; O[1] = -w[2]; O[2] = w[1]; O[3] = w[2]; O[4] = 0; O[5] = -w[0]; O[6] = -w[1]; O[7] = w[0]; O[8] = 0; }
+void mat3mul(const double* A, const double* B, double* C) {
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double a = 0; for (int k = 0; k < 3; k++) a += A[3 * i + k] * B[3 * k + j]; C[3 * i + j] = a; }
+}
+void quat_mul(const double* a, const double* b, double* o) {
+  o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  o[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  o[1] = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+  o[2] = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+}
+void quat_rot(const double* q, const double* v, double* o) {        // unit quaternion: q v q*
+  const double uv0 = 2 * (q[1] * v[2] - q[2] * v[1]), uv1 = 2 * (q[2] * v[0] - q[0] * v[2]), uv2 = 2 * (q[0] * v[1] - q[1] * v[0]);
+  o[0] = v[0] + q[3] * uv0 + (q[1] * uv2 - q[2] * uv1);
+  o[1] = v[1] + q[3] * uv1 + (q[2] * uv0 - q[0] * uv2);
+  o[2] = v[2] + q[3] * uv2 + (q[0] * uv1 - q[1] * uv0);
+}
+void so3_exp(const double* w, double* q, double* theta) {
+  const double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  double imag, real;
+  *theta = std::sqrt(t2);
+  if (t2 < kEps * kEps) { const double t4 = t2 * t2; imag = 0.5 - t2 / 48.0 + t4 / 3840.0; real = 1.0 - t2 / 8.0 + t4 / 384.0; }
+  else { const double h = 0.5 * *theta; imag = std::sin(h) / *theta; real = std::cos(h); }
+  q[0] = imag * w[0]; q[1] = imag * w[1]; q[2] = imag * w[2]; q[3] = real;
+}
+void so3_log(const double* q, double* w, double* theta) {
+  const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2], qw = q[3];
+  double two_atan;
+  if (n2 < kEps * kEps) { two_atan = 2.0 / qw - 2.0 / 3.0 * n2 / (qw * qw * qw); *theta = 2.0 * n2 / qw; }
+  else {
+    const double n = std::sqrt(n2);
+    // atan(n / w) chosen so that the rotation angle lies in (-pi, pi]
+    two_atan = 2.0 * (qw < 0 ? -std::atan2(n, -qw) : std::atan2(n, qw)) / n;
+    if (std::fabs(qw) < kEps) two_atan = (qw >= 0 ? M_PI : -M_PI) / n;
+    *theta = two_atan * n;
+  }
+  w[0] = two_atan * q[0]; w[1] = two_atan * q[1]; w[2] = two_atan * q[2];
+}
+void calcW(const double* w, double theta, double sigma, double scale, double* W) {
+  double O[9], O2[9];
+  hat(w, O); mat3mul(O, O, O2);
+  double A, B, C;
+  if (std::fabs(sigma) < kEps) {
+    C = 1.0;
+    if (std::fabs(theta) < kEps) { A = 0.5; B = 1.0 / 6.0; }
+    else { const double t2 = theta * theta; A = (1.0 - std::cos(theta)) / t2; B = (theta - std::sin(theta)) / (t2 * theta); }
+  } else {
+    C = (scale - 1.0) / sigma;
+    if (std::fabs(theta) < kEps) {
+      const double s2 = sigma * sigma;
+      A = ((sigma - 1.0) * scale + 1.0) / s2;
+      B = (scale * 0.5 * s2 + scale - 1.0 - sigma * scale) / (s2 * sigma);
+    } else {
+      const double t2 = theta * theta, a = scale * std::sin(theta), b = scale * std::cos(theta), c = t2 + sigma * sigma;
+      A = (a * sigma + (1.0 - b) * theta) / (theta * c);
+      B = (C - ((b - 1.0) * sigma + a * theta) / c) * 1.0 / t2;
+    }
+  }
+  for (int i = 0; i < 9; i++) W[i] = A * O[i] + B * O2[i] + ((i % 4 == 0) ? C : 0.0);
+}
+void calcWInv(const double* w, double theta, double sigma, double scale, double* W) {
+  double O[9], O2[9];
+  hat(w, O); mat3mul(O, O, O2);
+  const double scale_sq = scale * scale, t2 = theta * theta, st = std::sin(theta), ct = std::cos(theta);
+  double a, b, c;
+  if (std::fabs(sigma * sigma) < kEps) {
+    c = 1.0 - 0.5 * sigma;
+    a = -0.5;
+    if (std::fabs(t2) < kEps) b = 1.0 / 12.0;
+    else b = (theta * st + 2.0 * ct - 2.0) / (2.0 * t2 * (ct - 1.0));
+  } else {
+    const double scale_cu = scale_sq * scale;
+    c = sigma / (scale - 1.0);
+    if (std::fabs(t2) < kEps) {
+      a = (-sigma * scale + scale - 1.0) / ((scale - 1.0) * (scale - 1.0));
+      b = (scale_sq * sigma - 2.0 * scale_sq + scale * sigma + 2.0 * scale) / (2.0 * scale_cu - 6.0 * scale_sq + 6.0 * scale - 2.0);
+    } else {
+      const double ss = scale * st, sc = scale * ct;
+      a = (theta * sc - theta - sigma * ss) / (theta * (scale_sq - 2.0 * sc + 1.0));
+      b = -scale * (theta * ss - theta * st + sigma * sc - scale * sigma + sigma * ct - sigma) /
+          (t2 * (scale_cu - 2.0 * scale * sc - scale_sq + 2.0 * sc + scale - 1.0));
+    }
+  }
+  for (int i = 0; i < 9; i++) W[i] = a * O[i] + b * O2[i] + ((i % 4 == 0) ? c : 0.0);
+}
+Sim3 exp(const double* v) {
+  Sim3 S;
+  double theta;
+  so3_exp(v + 3, S.q, &theta);
+  S.s = std::exp(v[6]);
+  double W[9];
+  calcW(v + 3, theta, v[6], S.s, W);
+  for (int i = 0; i < 3; i++) S.t[i] = W[3 * i] * v[0] + W[3 * i + 1] * v[1] + W[3 * i + 2] * v[2];
+  return S;
+}
+void log(const Sim3& S, double* v) {
+  double theta;
+  so3_log(S.q, v + 3, &theta);
+  v[6] = std::log(S.s);
+  double W[9];
+  calcWInv(v + 3, theta, v[6], S.s, W);
+  for (int i = 0; i < 3; i++) v[i] = W[3 * i] * S.t[0] + W[3 * i + 1] * S.t[1] + W[3 * i + 2] * S.t[2];
+}
+Sim3 mul(const Sim3& a, const Sim3& b) {
+  Sim3 o;
+  o.s = a.s * b.s;
+  quat_mul(a.q, b.q, o.q);
+  const double n = std::sqrt(o.q[0] * o.q[0] + o.q[1] * o.q[1] + o.q[2] * o.q[2] + o.q[3] * o.q[3]);
+  for (int i = 0; i < 4; i++) o.q[i] /= n;
+  double r[3];
+  quat_rot(a.q, b.t, r);
+  for (int i = 0; i < 3; i++) o.t[i] = a.s * r[i] + a.t[i];
+  return o;
+}
+Sim3 inverse(const Sim3& a) {
+  Sim3 o;
+  o.s = 1.0 / a.s;
+  o.q[0] = -a.q[0]; o.q[1] = -a.q[1]; o.q[2] = -a.q[2]; o.q[3] = a.q[3];
+  double r[3];
+  quat_rot(o.q, a.t, r);
+  for (int i = 0; i < 3; i++) o.t[i] = -o.s * r[i];
+  return o;
+}
+void act(const Sim3& S, const double* P, double* o) {
+  double r[3];
+  quat_rot(S.q, P, r);
+  for (int i = 0; i < 3; i++) o[i] = S.s * r[i] + S.t[i];
+}
+void rotation_matrix(const double* q, double* R) {
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = 1 - 2 * (x * x + y * y);
+}
+void quat_from_matrix(const double* R, double* q) {   // unit quaternion of a rotation matrix (Shepperd)
+  const double tr = R[0] + R[4] + R[8];
+  if (tr > 0) { double t = std::sqrt(tr + 1.0); q[3] = 0.5 * t; t = 0.5 / t; q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t; }
+  else {
+    int i = 0; if (R[4] > R[0]) i = 1; if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double t = std::sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+    q[i] = 0.5 * t; t = 0.5 / t;
+    q[3] = (R[3 * k + j] - R[3 * j + k]) * t; q[j] = (R[3 * j + i] + R[3 * i + j]) * t; q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+  }
+}
+void plus(const double* x, const double* delta, double* out) {     // Sim3Parameterization::Plus
+  double d[7];
+  for (int i = 0; i < 7; i++) d[i] = delta[i];
+  d[6] = std::max(d[6], -20.);
+  log(mul(exp(x), exp(d)), out);
+}
+// Sim3ErrorTerm::Evaluate: residual (2) and Jacobian (2x7 row-major), both already multiplied by inv_sigma
+void error_term(const double* lie, const double* K4, const double* obs, const double* P, double inv_sigma, bool do_inverse,
+                double* r, double* J) {
+  const Sim3 S = exp(lie);
+  double p[3];
+  if (!do_inverse) act(S, P, p); else act(inverse(S), P, p);
+  const double fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3];
+  const double pr0 = fx * p[0] + cx * p[2], pr1 = fy * p[1] + cy * p[2], pr2 = p[2];
+  r[0] = inv_sigma * (pr0 / pr2 - obs[0]);
+  r[1] = inv_sigma * (pr1 / pr2 - obs[1]);
+  if (!J) return;
+  const double X = p[0], Y = p[1], Z = p[2], Z2 = Z * Z;
+  const double Jc[6] = {fx / Z, 0., -X * fx / Z2, 0, fy / Z, -fy * Y / Z2};
+  const double L[21] = {1, 0, 0, 0, Z, -Y, X,      // [I | -hat(p) | p]
+                        0, 1, 0, -Z, 0, X, Y,
+                        0, 0, 1, Y, -X, 0, Z};
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 7; j++) {
+      double a = 0;
+      for (int k = 0; k < 3; k++) a += Jc[3 * i + k] * L[7 * k + j];
+      J[7 * i + j] = inv_sigma * a;
+    }
+}
+}  // namespace sim3o
+
+extern "C" {
+
+void ba_oracle_sim3_exp(const double* lie, double* s, double* R9, double* t3) {
+  const sim3o::Sim3 S = sim3o::exp(lie);
+  *s = S.s; sim3o::rotation_matrix(S.q, R9); std::memcpy(t3, S.t, 24);
+}
+void ba_oracle_sim3_log(double s, const double* R9, const double* t3, double* lie) {
+  sim3o::Sim3 S; S.s = s; sim3o::quat_from_matrix(R9, S.q); std::memcpy(S.t, t3, 24);
+  sim3o::log(S, lie);
+}
+void ba_oracle_sim3_plus(const double* x, const double* delta, double* out) { sim3o::plus(x, delta, out); }
+void ba_oracle_sim3_error_term(const double* lie, const double* K4, const double* obs, const double* P, double inv_sigma,
+                               int do_inverse, double* r, double* J) {
+  sim3o::error_term(lie, K4, obs, P, inv_sigma, do_inverse != 0, r, J);
+}
+
+// OptimizeSim3.  S12 in/out as scale, rotation (row-major), translation; per correspondence: obs1 (keypoint of keyframe 1),
+// inv_sigma1, P3D2c (keyframe 2's map point in camera-2 coordinates), obs2, inv_sigma2, P3D1c.  is_bad[n] out.
+// Returns the reference's return value (0 when fewer than 10 inliers remain).  lie7 out = the optimised log.
+int ba_oracle_optimize_sim3(int n, double* s12, double* R12, double* t12, const double* K1, const double* K2,
+                            const float* obs1, const float* inv_sigma1, const double* P3D2c, const float* obs2,
+                            const float* inv_sigma2, const double* P3D1c, float th2, int max_iterations, uint8_t* is_bad,
+                            double* lie7, ba_oracle_summary* out, double* trace, int trace_cap) {
+  using namespace sim3o;
+  double x[7];
+  { Sim3 S; S.s = *s12; quat_from_matrix(R12, S.q); std::memcpy(S.t, t12, 24); log(S, x); }
+  const double huber_a = std::sqrt((double)th2), huber_b = huber_a * huber_a;
+  ba_oracle_summary sum{};
+  const int m = 2 * n;      // residual blocks
+  std::vector<double> r(2 * (size_t)m), J(14 * (size_t)m);
+  double scale[7], grad[7], H[49];
+  double x_cost = 0, x_norm = 0, gmax = 0, radius = 1e4, decrease_factor = 2.0;
+  int consecutive_invalid = 0, tr = 0;
+  auto put_trace = [&](double cost, double dc, double gm, double sn, double rd, double rad, double acc, double valid) {
+    if (trace && tr < trace_cap) { double* t = trace + 8 * tr; t[0] = cost; t[1] = dc; t[2] = gm; t[3] = sn; t[4] = rd; t[5] = rad; t[6] = acc; t[7] = valid; }
+    tr++;
+  };
+  auto block = [&](const double* lie, int b, double* rr, double* JJ) {
+    const int i = b >> 1;
+    const double o1[2] = {obs1[2 * i], obs1[2 * i + 1]}, o2[2] = {obs2[2 * i], obs2[2 * i + 1]};
+    if ((b & 1) == 0) error_term(lie, K1, o1, P3D2c + 3 * i, inv_sigma1[i], false, rr, JJ);
+    else error_term(lie, K2, o2, P3D1c + 3 * i, inv_sigma2[i], true, rr, JJ);
+  };
+  auto rho = [&](double s, double* w) {
+    if (s > huber_b) { const double rt = std::sqrt(s); *w = std::max(std::numeric_limits<double>::min(), huber_a / rt); return 2.0 * huber_a * rt - huber_b; }
+    *w = 1.0; return s;
+  };
+  auto cost_only = [&](const double* lie) {
+    double c = 0;
+    for (int b = 0; b < m; b++) { double rr[2], w; block(lie, b, rr, nullptr); c += 0.5 * rho(rr[0] * rr[0] + rr[1] * rr[1], &w); }
+    return c;
+  };
+  auto evaluate = [&](bool first) {
+    double c = 0;
+    std::fill(grad, grad + 7, 0.0); std::fill(H, H + 49, 0.0);
+    for (int b = 0; b < m; b++) {
+      double* rr = &r[2 * (size_t)b]; double* JJ = &J[14 * (size_t)b];
+      block(x, b, rr, JJ);
+      double w;
+      c += 0.5 * rho(rr[0] * rr[0] + rr[1] * rr[1], &w);
+      const double sw = std::sqrt(w);             // Corrector with rho'' <= 0: residual and Jacobian scaled by sqrt(rho')
+      rr[0] *= sw; rr[1] *= sw;
+      for (int k = 0; k < 14; k++) JJ[k] *= sw;
+      for (int a = 0; a < 7; a++) {
+        grad[a] += JJ[a] * rr[0] + JJ[7 + a] * rr[1];
+        for (int d = 0; d < 7; d++) H[7 * a + d] += JJ[a] * JJ[d] + JJ[7 + a] * JJ[7 + d];
+      }
+    }
+    x_cost = c;
+    sum.jacobian_evaluations++;
+    if (first) for (int a = 0; a < 7; a++) scale[a] = 1.0 / (1.0 + std::sqrt(H[8 * a]));
+    double ng[7], xp[7];
+    for (int a = 0; a < 7; a++) ng[a] = -grad[a];
+    plus(x, ng, xp);
+    gmax = 0; x_norm = 0;
+    for (int a = 0; a < 7; a++) { gmax = std::max(gmax, std::fabs(x[a] - xp[a])); x_norm += x[a] * x[a]; }
+    x_norm = std::sqrt(x_norm);
+  };
+  evaluate(true);
+  sum.initial_cost = x_cost;
+  put_trace(x_cost, 0, gmax, 0, 0, radius, 0, 0);
+  int iteration = 0;
+  sum.termination = 0;
+  if (max_iterations == 0) {}
+  else if (gmax <= 1e-10) sum.termination = 3;
+  else for (;;) {
+    iteration++;
+    // LevenbergMarquardtStrategy::ComputeStep on the Jacobi-scaled system
+    std::vector<double> A(49), b(7);
+    double D2[7], gs[7];
+    for (int a = 0; a < 7; a++) {
+      D2[a] = std::min(std::max(scale[a] * scale[a] * H[8 * a], 1e-6), 1e32) / radius;
+      gs[a] = scale[a] * grad[a];
+      b[a] = gs[a];
+      for (int d = 0; d < 7; d++) A[7 * a + d] = scale[a] * scale[d] * H[7 * a + d] + (a == d ? D2[a] : 0.0);
+    }
+    bool ok = cholesky_solve(A, 7, b);
+    double step[7], delta[7], mcc = 0.0;
+    for (int a = 0; a < 7; a++) { step[a] = -b[a]; if (!std::isfinite(step[a])) ok = false; }
+    if (ok) {
+      for (int bb = 0; bb < m; bb++)
+        for (int row = 0; row < 2; row++) {
+          double mm = 0;
+          for (int a = 0; a < 7; a++) mm += J[14 * (size_t)bb + 7 * row + a] * scale[a] * step[a];
+          mcc -= mm * (r[2 * (size_t)bb + row] + mm / 2.0);
+        }
+      if (!(mcc > 0.0)) ok = false;
+    }
+    if (!ok) {
+      consecutive_invalid++;
+      radius = radius / decrease_factor; decrease_factor *= 2.0;
+      put_trace(x_cost, 0, gmax, 0, 0, radius, 0, 0);
+      if (consecutive_invalid >= 5) { sum.termination = 5; break; }
+      if (iteration >= max_iterations) { sum.termination = 0; break; }
+      if (radius < 1e-32) { sum.termination = 6; break; }
+      continue;
+    }
+    consecutive_invalid = 0;
+    for (int a = 0; a < 7; a++) delta[a] = step[a] * scale[a];
+    double cand[7];
+    plus(x, delta, cand);
+    const double cand_cost = cost_only(cand);
+    double sn = 0;
+    for (int a = 0; a < 7; a++) sn += (x[a] - cand[a]) * (x[a] - cand[a]);
+    const double step_norm = std::sqrt(sn);
+    if (step_norm <= 1e-8 * (x_norm + 1e-8)) { sum.termination = 2; put_trace(x_cost, 0, gmax, step_norm, 0, radius, 0, 1); break; }
+    const double cost_change = x_cost - cand_cost;
+    if (std::fabs(cost_change) <= 1e-6 * x_cost) { sum.termination = 1; put_trace(x_cost, cost_change, gmax, step_norm, 0, radius, 0, 1); break; }
+    const double rd = cost_change / mcc;
+    const bool accepted = rd > 1e-3;
+    if (accepted) {
+      std::memcpy(x, cand, sizeof(x));
+      evaluate(false);
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rd - 1.0, 3));
+      radius = std::min(1e16, radius);
+      decrease_factor = 2.0;
+      sum.successful_steps++;
+    } else {
+      radius = radius / decrease_factor; decrease_factor *= 2.0;
+    }
+    put_trace(x_cost, cost_change, gmax, step_norm, rd, radius, accepted ? 1 : 0, 1);
+    if (iteration >= max_iterations) { sum.termination = 0; break; }
+    if (gmax <= 1e-10) { sum.termination = 3; break; }
+    if (radius < 1e-32) { sum.termination = 6; break; }
+  }
+  sum.iterations = iteration;
+  sum.final_cost = x_cost;
+  if (out) *out = sum;
+  if (lie7) std::memcpy(lie7, x, sizeof(x));
+  // S12 = exp(sim12); outlier scan with Eigen::Quaterniond(s * R) fed to CheckOutlier (:702-726)
+  const Sim3 S = exp(x), Si = inverse(S);
+  *s12 = S.s; rotation_matrix(S.q, R12); std::memcpy(t12, S.t, 24);
+  auto check = [&](const Sim3& T, const double* K4, const float* obs, float inv_sigma, const double* P) {
+    double R[9], sR[9], q[4], p[3];
+    rotation_matrix(T.q, R);
+    for (int i = 0; i < 9; i++) sR[i] = T.s * R[i];
+    quat_from_matrix(sR, q);                       // Eigen's conversion applied to a scaled rotation: not a unit quaternion
+    quat_rot(q, P, p);                             // Eigen's _transformVector polynomial, unit-norm not enforced
+    for (int i = 0; i < 3; i++) p[i] += T.t[i];
+    const double px = K4[0] * p[0] + K4[2] * p[2], py = K4[1] * p[1] + K4[3] * p[2], pz = p[2];
+    const double eu = obs[0] - px / pz, ev = obs[1] - py / pz;
+    return (eu * eu + ev * ev) * inv_sigma > huber_a * huber_a;
+  };
+  int n_bad = 0;
+  for (int i = 0; i < n; i++) {
+    const bool b12 = check(S, K1, obs1 + 2 * i, inv_sigma1[i], P3D2c + 3 * i);
+    const bool b21 = check(Si, K2, obs2 + 2 * i, inv_sigma2[i], P3D1c + 3 * i);
+    is_bad[i] = b12 || b21;
+    n_bad += is_bad[i];
+  }
+  if (n - n_bad < 10) return 0;
+  return n - n_bad;
+}
+
 }  // extern "C"

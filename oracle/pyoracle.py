@@ -564,3 +564,47 @@ def bow_transform(voc, features, levelsup=4):
     m = nfn.value
     return dict(words=bw[:nw], values=bv[:nw], fv_nodes=fn[:m], fv_start=fs[:m + 1], fv_features=ff[:fs[m]],
                 feat_word=fw[:n], feat_node=fnode[:n])
+
+
+# ---------------------------------------------------------------------------------------------------
+# OptimizeSim3 (oracle/ba_oracle.cpp, namespace sim3o)
+
+def sim3_exp(lie):
+    v = _c(lie, np.float64); s = C.c_double(); R = np.zeros(9); t = np.zeros(3)
+    lib().ba_oracle_sim3_exp(_p(v), C.byref(s), _p(R), _p(t))
+    return s.value, R.reshape(3, 3), t
+
+
+def sim3_log(s, R, t):
+    out = np.zeros(7)
+    lib().ba_oracle_sim3_log(C.c_double(s), _p(_c(R, np.float64)), _p(_c(t, np.float64)), _p(out))
+    return out
+
+
+def sim3_plus(x, delta):
+    out = np.zeros(7)
+    lib().ba_oracle_sim3_plus(_p(_c(x, np.float64)), _p(_c(delta, np.float64)), _p(out))
+    return out
+
+
+def sim3_error_term(lie, K4, obs, P, inv_sigma, do_inverse):
+    r = np.zeros(2); J = np.zeros(14)
+    lib().ba_oracle_sim3_error_term(_p(_c(lie, np.float64)), _p(_c(K4, np.float64)), _p(_c(obs, np.float64)),
+                                    _p(_c(P, np.float64)), C.c_double(inv_sigma), int(do_inverse), _p(r), _p(J))
+    return r, J.reshape(2, 7)
+
+
+def optimize_sim3(s12, R12, t12, K1, K2, obs1, inv_sigma1, P3D2c, obs2, inv_sigma2, P3D1c, th2=10.0, max_iterations=100):
+    n = len(obs1)
+    s = C.c_double(s12); R = _c(R12, np.float64).reshape(-1).copy(); t = _c(t12, np.float64).copy()
+    k1 = _c(K1, np.float64); k2 = _c(K2, np.float64)
+    a = (_c(obs1, np.float32), _c(inv_sigma1, np.float32), _c(P3D2c, np.float64), _c(obs2, np.float32), _c(inv_sigma2, np.float32),
+         _c(P3D1c, np.float64))
+    bad = np.zeros(max(n, 1), np.uint8); lie = np.zeros(7); summ = BaSummary(); trace = np.zeros((max_iterations + 2, 8))
+    fn = lib().ba_oracle_optimize_sim3
+    fn.restype = C.c_int
+    ret = fn(n, C.byref(s), _p(R), _p(t), _p(k1), _p(k2), *[_p(x) for x in a], C.c_float(th2), int(max_iterations), _p(bad),
+             _p(lie), C.byref(summ), _p(trace), len(trace))
+    return dict(ret=ret, s=s.value, R=R.reshape(3, 3), t=t, lie=lie, is_bad=bad[:n], iterations=summ.iterations,
+                successful_steps=summ.successful_steps, termination=summ.termination, initial_cost=summ.initial_cost,
+                final_cost=summ.final_cost, trace=trace)

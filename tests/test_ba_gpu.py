@@ -111,3 +111,25 @@ def test_stop_flag_semantics():
     cams, pts, erase, summ = opt.LocalBundleAdjustment(G["poses"], G["fixed"], G["points"], G["obs_cam"], G["obs_pt"],
                                                        G["uv"], G["inv_sigma2"], K4, stop_flag=flag)
     assert summ[0]["iterations"] == 5 and not np.array_equal(cams, G["poses"])
+
+
+@pytest.mark.parametrize("kw,w2", [(dict(init_noise=(0.002, 0.01, 0.002)), 1.0), (dict(init_noise=(0.002, 0.01, 0.002)), 1e-3),
+                                   (dict(init_noise=(0.01, 0.05, 0.01), scale=1.0), 1e-3), (dict(init_noise=(0.03, 0.1, 0.03)), 1.0),
+                                   (dict(init_noise=(0.03, 0.1, 0.03), n=40), 1e-3)])
+def test_optimize_sim3_matches_oracle(kw, w2):
+    """cmos_ba_optimize_sim3 == the restated OptimizeSim3: same iterations / accepted steps / termination, per-iteration
+    cost, sim12 within 1e-7 (north_star asks 1e-4), identical outlier flags and return value — on inputs where the
+    reference's solver accepts no step (both directions at full weight, quirk Q6) and where it converges."""
+    P = synth.make_sim3_problem(seed=6, **kw)
+    args = (P["s0"], P["R0"], P["t0"], P["K"], P["K"], P["obs1"], P["inv_sigma1"], P["P3D2c"], P["obs2"],
+            P["inv_sigma2"] * np.float32(w2), P["P3D1c"])
+    ref = po.optimize_sim3(*args)
+    opt = CeresOptimizer(max_cams=2, max_points=8, max_obs=8)
+    got = opt.OptimizeSim3(*args)
+    s = got["summary"]
+    assert (s["iterations"], s["successful_steps"], s["termination"]) == (ref["iterations"], ref["successful_steps"], ref["termination"])
+    assert abs(s["final_cost"] - ref["final_cost"]) <= 1e-9 * ref["final_cost"] and abs(s["initial_cost"] - ref["initial_cost"]) <= 1e-9 * ref["initial_cost"]
+    assert np.abs(got["lie"] - ref["lie"]).max() <= 1e-7 * max(1.0, np.abs(ref["lie"]).max())
+    assert abs(got["s"] - ref["s"]) <= 1e-7 and np.abs(got["R"] - ref["R"]).max() <= 1e-7 and np.abs(got["t"] - ref["t"]).max() <= 1e-7
+    assert got["ret"] == ref["ret"] and np.array_equal(got["is_bad"], ref["is_bad"])
+    opt.close()

@@ -120,3 +120,64 @@ def test_global_ba_without_loss_equals_gauss_newton_minimum():
     for _ in range(5):
         d = rng.normal(0, 1e-3, p.shape)
         assert cost(p + d) >= c0 * (1 - 1e-6)
+
+
+# ---- OptimizeSim3 (oracle/ba_oracle.cpp, namespace sim3o) ------------------------------------------------------------
+
+def _sim3_mul(a, b):
+    return a[0] * b[0], a[1] @ b[1], a[0] * a[1] @ b[2] + a[2]
+
+
+def test_sim3_exp_log_plus_and_jacobian():
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        v = np.concatenate([rng.normal(0, 1, 3), rng.normal(0, 0.8, 3), [rng.normal(0, 0.3)]])
+        s, R, t = po.sim3_exp(v)
+        assert abs(np.linalg.det(R) - 1) < 1e-13 and np.abs(R @ R.T - np.eye(3)).max() < 1e-13 and abs(s - np.exp(v[6])) < 1e-15
+        assert np.abs(po.sim3_log(s, R, t) - v).max() < 1e-12
+    for v in ([0.1, 0.2, 0.3, 0, 0, 0, 0], [0.1, 0.2, 0.3, 1e-12, 0, 0, 0.2], [0.1, 0.2, 0.3, 0.3, 0.1, 0, 1e-13]):   # small-angle branches
+        s, R, t = po.sim3_exp(np.array(v, float))
+        assert np.abs(po.sim3_log(s, R, t) - v).max() < 1e-12
+    # exp is a homomorphism along one generator; Plus is right multiplication with the sigma clamp
+    v = np.array([0.3, -0.2, 0.5, 0.2, -0.1, 0.3, 0.1])
+    a, b = po.sim3_exp(0.3 * v), po.sim3_exp(0.7 * v)
+    ab = _sim3_mul(a, b); full = po.sim3_exp(v)
+    assert abs(ab[0] - full[0]) < 1e-14 and np.abs(ab[1] - full[1]).max() < 1e-14 and np.abs(ab[2] - full[2]).max() < 1e-14
+    x = np.array([0.1, -0.05, 0.2, 0.02, -0.03, 0.01, 0.05]); d = np.array([0.01, 0.02, -0.01, 0.003, 0.001, -0.002, 0.004])
+    prod = _sim3_mul(po.sim3_exp(x), po.sim3_exp(d))
+    assert np.abs(po.sim3_plus(x, d) - po.sim3_log(*prod)).max() < 1e-14
+    dd = d.copy(); dd[6] = -50.0
+    clamped = d.copy(); clamped[6] = -20.0
+    assert np.abs(po.sim3_plus(x, dd) - po.sim3_plus(x, clamped)).max() < 1e-12
+    # Sim3ErrorTerm's Jacobian is the LEFT-perturbation derivative of the forward residual (CeresOptimizer.h:196-219)
+    K4 = np.array([718.856, 718.856, 607.19, 185.2]); P = np.array([1.0, -0.5, 9.0]); obs = np.array([650.0, 170.0])
+    r, J = po.sim3_error_term(x, K4, obs, P, 0.7, 0)
+    S = po.sim3_exp(x)
+    num = np.zeros((2, 7)); eps = 1e-6
+    for k in range(7):
+        e = np.zeros(7); e[k] = eps
+        rp, _ = po.sim3_error_term(po.sim3_log(*_sim3_mul(po.sim3_exp(e), S)), K4, obs, P, 0.7, 0)
+        rm, _ = po.sim3_error_term(po.sim3_log(*_sim3_mul(po.sim3_exp(-e), S)), K4, obs, P, 0.7, 0)
+        num[:, k] = (rp - rm) / (2 * eps)
+    assert np.abs(num - J).max() < 1e-5 * np.abs(J).max()
+
+
+def test_optimize_sim3_behaviour():
+    """As written in the reference the inverse-direction terms use the forward Jacobian formula, so with both directions at
+    full weight no step is accepted and S12 comes back unchanged (quirk Q6); with the inverse terms down-weighted the same
+    solver converges.  Either way the cost never increases and the outlier scan follows the final S12."""
+    P = synth.make_sim3_problem(n=300, seed=6, init_noise=(0.002, 0.01, 0.002))
+    args = lambda w2: (P["s0"], P["R0"], P["t0"], P["K"], P["K"], P["obs1"], P["inv_sigma1"], P["P3D2c"], P["obs2"],
+                       P["inv_sigma2"] * np.float32(w2), P["P3D1c"])
+    r = po.optimize_sim3(*args(1.0))
+    assert r["successful_steps"] == 0 and r["final_cost"] == r["initial_cost"]
+    assert abs(r["s"] - P["s0"]) < 1e-12 and np.abs(r["t"] - P["t0"]).max() < 1e-12
+    assert r["ret"] == 300 - r["is_bad"].sum() >= 10
+    r2 = po.optimize_sim3(*args(1e-3))
+    assert r2["successful_steps"] >= 3 and r2["final_cost"] < 0.9 * r2["initial_cost"]
+    costs = r2["trace"][: r2["iterations"] + 1, 0]
+    assert np.all(np.diff(costs) <= 1e-9 * costs[0])
+    far = synth.make_sim3_problem(n=300, seed=6, init_noise=(0.03, 0.1, 0.03))
+    r3 = po.optimize_sim3(far["s0"], far["R0"], far["t0"], far["K"], far["K"], far["obs1"], far["inv_sigma1"], far["P3D2c"],
+                          far["obs2"], far["inv_sigma2"], far["P3D1c"])
+    assert r3["ret"] == 0 and r3["is_bad"].sum() > 290         # fewer than 10 inliers -> 0 (:731)
