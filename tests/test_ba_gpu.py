@@ -113,16 +113,15 @@ def test_stop_flag_semantics():
     assert summ[0]["iterations"] == 5 and not np.array_equal(cams, G["poses"])
 
 
-@pytest.mark.parametrize("kw,w2", [(dict(init_noise=(0.002, 0.01, 0.002)), 1.0), (dict(init_noise=(0.002, 0.01, 0.002)), 1e-3),
-                                   (dict(init_noise=(0.01, 0.05, 0.01), scale=1.0), 1e-3), (dict(init_noise=(0.03, 0.1, 0.03)), 1.0),
-                                   (dict(init_noise=(0.03, 0.1, 0.03), n=40), 1e-3)])
-def test_optimize_sim3_matches_oracle(kw, w2):
-    """cmos_ba_optimize_sim3 == the restated OptimizeSim3: same iterations / accepted steps / termination, per-iteration
-    cost, sim12 within 1e-7 (north_star asks 1e-4), identical outlier flags and return value — on inputs where the
-    reference's solver accepts no step (both directions at full weight, quirk Q6) and where it converges."""
+@pytest.mark.parametrize("kw", [dict(init_noise=(0.002, 0.01, 0.002)), dict(init_noise=(0.03, 0.1, 0.03)),
+                                dict(init_noise=(0.01, 0.05, 0.01), scale=1.0, n=80)])
+def test_optimize_sim3_matches_oracle(kw):
+    """cmos_ba_optimize_sim3 == the restated OptimizeSim3 on the reference's own inputs (both directions at full weight):
+    same iterations / accepted steps / termination, costs to 1e-9, sim12 within 1e-7 (north_star asks 1e-4), identical
+    outlier flags and return value.  In this regime the reference's solver accepts no step (quirk Q6: the inverse-direction
+    terms use the forward Jacobian), so the trajectory is well conditioned."""
     P = synth.make_sim3_problem(seed=6, **kw)
-    args = (P["s0"], P["R0"], P["t0"], P["K"], P["K"], P["obs1"], P["inv_sigma1"], P["P3D2c"], P["obs2"],
-            P["inv_sigma2"] * np.float32(w2), P["P3D1c"])
+    args = (P["s0"], P["R0"], P["t0"], P["K"], P["K"], P["obs1"], P["inv_sigma1"], P["P3D2c"], P["obs2"], P["inv_sigma2"], P["P3D1c"])
     ref = po.optimize_sim3(*args)
     opt = CeresOptimizer(max_cams=2, max_points=8, max_obs=8)
     got = opt.OptimizeSim3(*args)
@@ -132,4 +131,43 @@ def test_optimize_sim3_matches_oracle(kw, w2):
     assert np.abs(got["lie"] - ref["lie"]).max() <= 1e-7 * max(1.0, np.abs(ref["lie"]).max())
     assert abs(got["s"] - ref["s"]) <= 1e-7 and np.abs(got["R"] - ref["R"]).max() <= 1e-7 and np.abs(got["t"] - ref["t"]).max() <= 1e-7
     assert got["ret"] == ref["ret"] and np.array_equal(got["is_bad"], ref["is_bad"])
+    opt.close()
+
+
+@pytest.mark.parametrize("kw", [dict(init_noise=(0.002, 0.01, 0.002)), dict(init_noise=(0.01, 0.05, 0.01), scale=1.0),
+                                dict(init_noise=(0.03, 0.1, 0.03), n=40)])
+def test_optimize_sim3_converging_regime(kw):
+    """With the inverse-direction terms down-weighted the reference's solver does accept steps — and then its scale
+    component is rounding noise: column 6 of Sim3ErrorTerm's Jacobian is J_camera * p_cp, analytically zero
+    (CeresOptimizer.h:206-219), so H_66 ~ 1e-25 and the LM step along the scale is g_6 / (1e-6 / radius) with g_6 ~ 1e-13 of
+    cancellation residue (quirk Q7).  tests/test_oracle_ba.py::test_optimize_sim3_scale_step_is_rounding_noise shows the
+    oracle's own trajectory changing (iterations, accepted steps, 1 % of scale) under a 2e-16 relative change of the inputs,
+    so there is no trajectory to match.  What is well defined is asserted: the first evaluation (cost, gradient norm), the
+    rotation the solve converges to, monotone cost, a final cost / translation / scale inside the band the oracle itself
+    spans, and the outlier scan being consistent with the returned S12."""
+    P = synth.make_sim3_problem(seed=6, **kw)
+    base = [P["s0"], P["R0"], P["t0"], P["K"], P["K"], P["obs1"], P["inv_sigma1"], P["P3D2c"], P["obs2"],
+            P["inv_sigma2"] * np.float32(1e-3), P["P3D1c"]]
+    refs = []
+    for eps in (0.0, 2e-16, 1e-15, -1e-15):
+        a = list(base); a[7] = P["P3D2c"] * (1 + eps)
+        refs.append(po.optimize_sim3(*a))
+    opt = CeresOptimizer(max_cams=2, max_points=8, max_obs=8)
+    got = opt.OptimizeSim3(*base)
+    s = got["summary"]
+    tr = opt.pose_trace(0, s["iterations"] + 1)
+    ref = refs[0]
+    assert abs(s["initial_cost"] - ref["initial_cost"]) <= 1e-9 * ref["initial_cost"]
+    assert abs(tr[0, 2] - ref["trace"][0, 2]) <= 1e-6 * ref["trace"][0, 2]            # gradient max norm through Plus(x, -g)
+    assert s["termination"] == ref["termination"] == 1 and s["successful_steps"] >= 3
+    assert np.all(np.diff(tr[: s["iterations"] + 1, 0]) <= 1e-9 * tr[0, 0])
+    lies = np.stack([r["lie"] for r in refs]); costs = np.array([r["final_cost"] for r in refs])
+    assert np.abs(got["lie"][3:6] - ref["lie"][3:6]).max() <= 1e-4                    # rotation: observable, converged
+    spread_t = np.ptp(lies[:, :3], 0).max(); spread_s = np.ptp(lies[:, 6])
+    assert np.abs(got["lie"][:3] - ref["lie"][:3]).max() <= max(5e-3, 3 * spread_t)
+    assert abs(got["lie"][6] - ref["lie"][6]) <= max(2e-2, 3 * spread_s)
+    assert abs(s["final_cost"] - ref["final_cost"]) <= max(1e-4 * ref["final_cost"], 3 * np.ptp(costs))
+    # the scan is a pure function of the returned S12: replay it through the oracle with zero iterations
+    chk = po.optimize_sim3(got["s"], got["R"], got["t"], *base[3:], max_iterations=0)
+    assert np.array_equal(got["is_bad"], chk["is_bad"]) and got["ret"] == chk["ret"]
     opt.close()
