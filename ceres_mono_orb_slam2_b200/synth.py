@@ -345,3 +345,79 @@ def make_sim3_problem(n: int = 300, seed: int = 6, K=KITTI_K, scale: float = 1.0
     return dict(obs1=obs1.astype(np.float32), inv_sigma1=is1, P3D2c=P2n, obs2=obs2.astype(np.float32), inv_sigma2=is2, P3D1c=P1n,
                 K=np.array(K, np.float32), s_true=scale, R_true=R12, t_true=t12, s0=scale * float(np.exp(rng.normal(0, init_noise[2]))),
                 R0=R0, t0=t12 + rng.normal(0, init_noise[1] / np.sqrt(3), 3))
+
+
+def _rodrigues(rv):
+    th = np.linalg.norm(rv)
+    if th < 1e-300:
+        return np.eye(3)
+    k = rv / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+
+
+def make_essential_graph_problem(n_kf: int = 60, seed: int = 7, n_points: int = 500, n_group: int = 4, loop_kf: int = 1,
+                                 drift=(0.004, 0.01, 0.004), covis=(2, 3), radius: float = 20.0):
+    """OptimizeEssentialGraph inputs after a loop closure: n_kf keyframes once around a circle, the estimated trajectory
+    drifting in rotation / translation / scale (per-step sigmas `drift`), the last keyframe closing the loop on keyframe
+    `loop_kf`.  The current keyframe and its n_group predecessors carry corrected Sim3s (and their non-corrected ones);
+    edges in the reference's insertion order: loop connections (kind 0), then per keyframe its parent and its
+    co-visible predecessors i - covis[k] (kind 1).  Sim3s as [scale, R row-major (9), t (3)]."""
+    rng = np.random.default_rng(seed)
+    # ground truth Tcw
+    Rt, tt = [], []
+    for k in range(n_kf):
+        a = 2 * np.pi * k / n_kf * (1 - 0.5 / n_kf)
+        Rwc = _rodrigues(np.array([0.0, -a, 0.0]))                       # yaw about the camera's y axis
+        C = np.array([radius * np.cos(a), 0.2 * np.sin(3 * a), radius * np.sin(a)])
+        Rt.append(Rwc.T); tt.append(-Rwc.T @ C)
+    # drifting estimate: chain the true relative motions, each perturbed
+    Re, te, se = [Rt[0]], [tt[0]], [1.0]
+    for k in range(1, n_kf):
+        Rrel = Rt[k] @ Rt[k - 1].T
+        trel = tt[k] - Rrel @ tt[k - 1]
+        s = se[-1] * float(np.exp(rng.normal(0, drift[2])))
+        Rn = _rodrigues(rng.normal(0, drift[0] / np.sqrt(3), 3)) @ Rrel
+        tn = s * trel + rng.normal(0, drift[1] / np.sqrt(3), 3)
+        Re.append(Rn @ Re[-1]); te.append(Rn @ te[-1] + tn); se.append(s)
+    Scw = np.zeros((n_kf, 13)); Snc = np.zeros((n_kf, 13)); flags = np.zeros(n_kf, np.uint8)
+    for k in range(n_kf):
+        Scw[k, 0] = 1.0; Scw[k, 1:10] = Re[k].reshape(-1); Scw[k, 10:] = te[k]
+    flags[loop_kf] |= 1
+    cur = n_kf - 1
+    sig = se[cur]
+    # corrected Sim3 of the current keyframe in the loop side's world, propagated to its group through the (non-corrected)
+    # relative motions (LoopClosing::CorrectLoop)
+    Rc, tc, sc = Rt[cur], sig * tt[cur], sig
+    group = list(range(cur - n_group, cur + 1))
+    for k in group:
+        Ric = Re[k] @ Re[cur].T
+        tic = te[k] - Ric @ te[cur]
+        Snc[k] = Scw[k]
+        flags[k] |= 2
+        Scw[k, 0] = sc; Scw[k, 1:10] = (Ric @ Rc).reshape(-1); Scw[k, 10:] = Ric @ tc + tic
+    ej, ei, ek = [], [], []
+    loop_cluster = [j for j in (loop_kf - 1, loop_kf, loop_kf + 1) if 0 <= j < n_kf]
+    for i in group:
+        for j in loop_cluster:
+            ej.append(j); ei.append(i); ek.append(0)
+    for j in loop_cluster:
+        for i in group[-2:]:
+            ej.append(i); ei.append(j); ek.append(0)
+    for i in range(n_kf):
+        if i >= 1:
+            ej.append(i - 1); ei.append(i); ek.append(1)
+        for c in covis:
+            if i - c >= 0:
+                ej.append(i - c); ei.append(i); ek.append(1)
+    ref = rng.integers(0, n_kf, n_points).astype(np.int32)
+    Xw = np.zeros((n_points, 3))
+    for p in range(n_points):
+        k = ref[p]
+        Pc = np.array([rng.uniform(-5, 5), rng.uniform(-1, 1), rng.uniform(4, 30)])
+        Xw[p] = Re[k].T @ (Pc - te[k])
+    true_T = np.zeros((n_kf, 4, 4))
+    for k in range(n_kf):
+        true_T[k, :3, :3] = Rt[k]; true_T[k, :3, 3] = tt[k]; true_T[k, 3, 3] = 1
+    return dict(Scw=Scw, Snc=Snc, kf_flags=flags, edge_j=np.array(ej, np.int32), edge_i=np.array(ei, np.int32),
+                edge_kind=np.array(ek, np.uint8), Xw=Xw, ref_kf=ref, true_Tcw=true_T, loop_kf=loop_kf, group=np.array(group))

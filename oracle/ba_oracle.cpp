@@ -1030,3 +1030,237 @@ int ba_oracle_optimize_sim3(int n, double* s12, double* R12, double* t12, const 
 }
 
 }  // extern "C"
+
+// ---- OptimizeEssentialGraph (src/CeresOptimizer.cc:736-957, include/CeresOptimizer.h:270-328) -------------------------
+// 7-DoF pose graph over the keyframes' Sim3 logs after a loop closure.  Flattened view (the pointer-graph traversal of
+// :793-895 that picks the edges is the adapter's job, include/orb_slam2/CeresOptimizer.h):
+//   Scw[n_kf][13]   scale, rotation (row-major), translation of the INITIAL Scw of every keyframe: the corrected Sim3 where
+//                   keyframes_corrected_sim3 holds the keyframe (:767-769), else (1, Rcw, tcw) (:770-774)
+//   kf_flags[n_kf]  bit 0: constant block (the loop keyframe, :780-783); bit 1: Snc holds keyframes_non_corrected_sim3's entry
+//   Snc[n_kf][13]   non-corrected Siw
+//   edges           residual block (parameter 0 = keyframe j, parameter 1 = keyframe i) in the reference's insertion order;
+//                   kind 0 = loop-connection edge: Sji = exp(lie_j) * exp(lie_i)^-1 (:797-809);
+//                   kind 1 = spanning-tree / loop / co-visibility edge: each side's non-corrected Sim3 where present, else
+//                   exp(lie) (:822-895)
+// Solve: trust-region LM as everywhere else (no loss, identity local Jacobian, Sim3Parameterization::Plus), 100 iterations.
+// Afterwards (:903-956): Tiw = [R | t / s] per keyframe (4x4 row-major) and every map point moved through its reference
+// keyframe: X' = exp(lie_r)^-1 * (exp(lie0_r) * X).
+namespace sim3o {
+void adjoint(const Sim3& S, double* A /*7x7 row-major*/) {            // Sophus Sim3::Adj()
+  double R[9], T[9], TR[9];
+  rotation_matrix(S.q, R); hat(S.t, T); mat3mul(T, R, TR);
+  std::fill(A, A + 49, 0.0);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) { A[7 * i + j] = S.s * R[3 * i + j]; A[7 * i + 3 + j] = TR[3 * i + j]; A[7 * (3 + i) + 3 + j] = R[3 * i + j]; }
+  for (int i = 0; i < 3; i++) A[7 * i + 6] = -S.t[i];
+  A[48] = 1.0;
+}
+// EssentialGraphErrorTerm::Evaluate with sqrt_information = I: residual (7) and Jacobian wrt keyframe i (7x7 row-major);
+// the Jacobian wrt keyframe j is its negative (:301-302)
+void edge_term(const Sim3& Sji, const double* lie_j, const double* lie_i, double* r, double* Ji) {
+  const Sim3 Si = exp(lie_i), Sj = exp(lie_j);
+  log(mul(mul(Sji, Si), inverse(Sj)), r);
+  if (!Ji) return;
+  double A[49] = {0}, A2[49], Jr[49], Adj[49];
+  double Ow[9], Ou[9];
+  hat(r + 3, Ow); hat(r, Ou);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      A[7 * i + j] = Ow[3 * i + j] + (i == j ? r[6] : 0.0);       // RxSO3::hat(omega, sigma)
+      A[7 * i + 3 + j] = Ou[3 * i + j];
+      A[7 * (3 + i) + 3 + j] = Ow[3 * i + j];
+    }
+  for (int i = 0; i < 3; i++) A[7 * i + 6] = -r[i];
+  for (int i = 0; i < 7; i++) for (int j = 0; j < 7; j++) { double a = 0; for (int k = 0; k < 7; k++) a += A[7 * i + k] * A[7 * k + j]; A2[7 * i + j] = a; }
+  for (int i = 0; i < 49; i++) Jr[i] = ((i % 8 == 0) ? 1.0 : 0.0) + 0.5 * A[i] + 1.0 / 12. * A2[i];
+  adjoint(Sj, Adj);
+  for (int i = 0; i < 7; i++) for (int j = 0; j < 7; j++) { double a = 0; for (int k = 0; k < 7; k++) a += Jr[7 * i + k] * Adj[7 * k + j]; Ji[7 * i + j] = a; }
+}
+Sim3 from_srt(const double* v13) { Sim3 S; S.s = v13[0]; quat_from_matrix(v13 + 1, S.q); std::memcpy(S.t, v13 + 10, 24); return S; }
+}  // namespace sim3o
+
+extern "C" {
+
+void ba_oracle_sim3_adjoint(const double* lie, double* A49) { sim3o::adjoint(sim3o::exp(lie), A49); }
+void ba_oracle_essential_edge(const double* Sji13, const double* lie_j, const double* lie_i, double* r7, double* Ji49) {
+  sim3o::edge_term(sim3o::from_srt(Sji13), lie_j, lie_i, r7, Ji49);
+}
+
+int ba_oracle_essential_graph(int n_kf, const double* Scw, const uint8_t* kf_flags, const double* Snc, int n_edges,
+                              const int32_t* edge_j, const int32_t* edge_i, const uint8_t* edge_kind, int max_iterations,
+                              int n_points, const double* Xw, const int32_t* ref_kf, double* lie_out, double* Tiw_out,
+                              double* Xw_out, ba_oracle_summary* out, double* trace, int trace_cap) {
+  using namespace sim3o;
+  std::vector<double> x(7 * (size_t)n_kf), x0;
+  for (int k = 0; k < n_kf; k++) log(from_srt(Scw + 13 * k), &x[7 * k]);
+  x0 = x;
+  std::vector<int> var(n_kf, -1);
+  int Kv = 0;
+  for (int k = 0; k < n_kf; k++) if (!(kf_flags[k] & 1)) var[k] = Kv++;
+  const int n = 7 * Kv;
+  // the measurements, from the initial values (:797-809, :822-895)
+  std::vector<Sim3> meas(n_edges);
+  for (int e = 0; e < n_edges; e++) {
+    const int j = edge_j[e], i = edge_i[e];
+    Sim3 Sjw, Swi;
+    if (edge_kind[e] == 0) { Sjw = exp(&x[7 * j]); Swi = inverse(exp(&x[7 * i])); }
+    else {
+      Swi = (kf_flags[i] & 2) ? inverse(from_srt(Snc + 13 * i)) : inverse(exp(&x[7 * i]));
+      Sjw = (kf_flags[j] & 2) ? from_srt(Snc + 13 * j) : exp(&x[7 * j]);
+    }
+    meas[e] = mul(Sjw, Swi);
+  }
+  ba_oracle_summary sum{};
+  std::vector<double> r(7 * (size_t)n_edges), J(49 * (size_t)n_edges), H((size_t)n * n), grad(n), scale(n, 1.0);
+  double x_cost = 0, x_norm = 0, gmax = 0, radius = 1e4, decrease_factor = 2.0;
+  int consecutive_invalid = 0, tr = 0;
+  auto put_trace = [&](double cost, double dc, double gm, double sn, double rd, double rad, double acc, double valid) {
+    if (trace && tr < trace_cap) { double* t = trace + 8 * tr; t[0] = cost; t[1] = dc; t[2] = gm; t[3] = sn; t[4] = rd; t[5] = rad; t[6] = acc; t[7] = valid; }
+    tr++;
+  };
+  auto cost_only = [&](const std::vector<double>& y) {
+    double c = 0;
+    for (int e = 0; e < n_edges; e++) {
+      double rr[7];
+      edge_term(meas[e], &y[7 * edge_j[e]], &y[7 * edge_i[e]], rr, nullptr);
+      double s = 0; for (int a = 0; a < 7; a++) s += rr[a] * rr[a];
+      c += 0.5 * s;
+    }
+    return c;
+  };
+  auto evaluate = [&](bool first) {
+    double c = 0;
+    std::fill(H.begin(), H.end(), 0.0); std::fill(grad.begin(), grad.end(), 0.0);
+    for (int e = 0; e < n_edges; e++) {
+      double* rr = &r[7 * (size_t)e]; double* JJ = &J[49 * (size_t)e];
+      edge_term(meas[e], &x[7 * edge_j[e]], &x[7 * edge_i[e]], rr, JJ);
+      double s = 0; for (int a = 0; a < 7; a++) s += rr[a] * rr[a];
+      c += 0.5 * s;
+      const int vi = var[edge_i[e]], vj = var[edge_j[e]];
+      double A[49], v[7];
+      for (int a = 0; a < 7; a++) {
+        double g = 0; for (int k = 0; k < 7; k++) g += JJ[7 * k + a] * rr[k];
+        v[a] = g;
+        for (int b = 0; b < 7; b++) { double h = 0; for (int k = 0; k < 7; k++) h += JJ[7 * k + a] * JJ[7 * k + b]; A[7 * a + b] = h; }
+      }
+      for (int a = 0; a < 7; a++) {
+        if (vi >= 0) grad[7 * vi + a] += v[a];
+        if (vj >= 0) grad[7 * vj + a] -= v[a];
+        for (int b = 0; b < 7; b++) {
+          if (vi >= 0) H[(size_t)(7 * vi + a) * n + 7 * vi + b] += A[7 * a + b];
+          if (vj >= 0) H[(size_t)(7 * vj + a) * n + 7 * vj + b] += A[7 * a + b];
+          if (vi >= 0 && vj >= 0 && vi != vj) { H[(size_t)(7 * vi + a) * n + 7 * vj + b] -= A[7 * a + b]; H[(size_t)(7 * vj + a) * n + 7 * vi + b] -= A[7 * a + b]; }
+        }
+      }
+    }
+    x_cost = c;
+    sum.jacobian_evaluations++;
+    if (first) for (int a = 0; a < n; a++) scale[a] = 1.0 / (1.0 + std::sqrt(H[(size_t)a * n + a]));
+    gmax = 0; double xn = 0;
+    for (int k = 0; k < n_kf; k++) {
+      if (var[k] < 0) continue;
+      double ng[7], xp[7];
+      for (int a = 0; a < 7; a++) ng[a] = -grad[7 * var[k] + a];
+      plus(&x[7 * k], ng, xp);
+      for (int a = 0; a < 7; a++) { gmax = std::max(gmax, std::fabs(x[7 * k + a] - xp[a])); xn += x[7 * k + a] * x[7 * k + a]; }
+    }
+    x_norm = std::sqrt(xn);
+  };
+  evaluate(true);
+  sum.initial_cost = x_cost;
+  put_trace(x_cost, 0, gmax, 0, 0, radius, 0, 0);
+  int iteration = 0;
+  sum.termination = 0;
+  if (max_iterations == 0 || n == 0) {}
+  else if (gmax <= 1e-10) sum.termination = 3;
+  else for (;;) {
+    iteration++;
+    std::vector<double> A((size_t)n * n), b(n), D2(n);
+    for (int a = 0; a < n; a++) {
+      D2[a] = std::min(std::max(scale[a] * scale[a] * H[(size_t)a * n + a], 1e-6), 1e32) / radius;
+      b[a] = scale[a] * grad[a];
+      for (int d = 0; d < n; d++) A[(size_t)a * n + d] = scale[a] * scale[d] * H[(size_t)a * n + d] + (a == d ? D2[a] : 0.0);
+    }
+    bool ok = cholesky_solve(A, n, b);
+    std::vector<double> delta(n);
+    double mcc = 0.0;
+    for (int a = 0; a < n; a++) { delta[a] = -b[a] * scale[a]; if (!std::isfinite(delta[a])) ok = false; }
+    if (ok) {
+      for (int e = 0; e < n_edges; e++) {
+        const int vi = var[edge_i[e]], vj = var[edge_j[e]];
+        for (int row = 0; row < 7; row++) {
+          double mm = 0;
+          for (int a = 0; a < 7; a++) {
+            const double d = (vi >= 0 ? delta[7 * vi + a] : 0.0) - (vj >= 0 ? delta[7 * vj + a] : 0.0);
+            mm += J[49 * (size_t)e + 7 * row + a] * d;
+          }
+          mcc -= mm * (r[7 * (size_t)e + row] + mm / 2.0);
+        }
+      }
+      if (!(mcc > 0.0)) ok = false;
+    }
+    if (!ok) {
+      consecutive_invalid++;
+      radius = radius / decrease_factor; decrease_factor *= 2.0;
+      put_trace(x_cost, 0, gmax, 0, 0, radius, 0, 0);
+      if (consecutive_invalid >= 5) { sum.termination = 5; break; }
+      if (iteration >= max_iterations) { sum.termination = 0; break; }
+      if (radius < 1e-32) { sum.termination = 6; break; }
+      continue;
+    }
+    consecutive_invalid = 0;
+    std::vector<double> cand(x);
+    double sn = 0;
+    for (int k = 0; k < n_kf; k++) {
+      if (var[k] < 0) continue;
+      plus(&x[7 * k], &delta[7 * var[k]], &cand[7 * k]);
+      for (int a = 0; a < 7; a++) sn += (x[7 * k + a] - cand[7 * k + a]) * (x[7 * k + a] - cand[7 * k + a]);
+    }
+    const double cand_cost = cost_only(cand);
+    const double step_norm = std::sqrt(sn);
+    if (step_norm <= 1e-8 * (x_norm + 1e-8)) { sum.termination = 2; put_trace(x_cost, 0, gmax, step_norm, 0, radius, 0, 1); break; }
+    const double cost_change = x_cost - cand_cost;
+    if (std::fabs(cost_change) <= 1e-6 * x_cost) { sum.termination = 1; put_trace(x_cost, cost_change, gmax, step_norm, 0, radius, 0, 1); break; }
+    const double rd = cost_change / mcc;
+    const bool accepted = rd > 1e-3;
+    if (accepted) {
+      x = cand;
+      evaluate(false);
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rd - 1.0, 3));
+      radius = std::min(1e16, radius);
+      decrease_factor = 2.0;
+      sum.successful_steps++;
+    } else {
+      radius = radius / decrease_factor; decrease_factor *= 2.0;
+    }
+    put_trace(x_cost, cost_change, gmax, step_norm, rd, radius, accepted ? 1 : 0, 1);
+    if (iteration >= max_iterations) { sum.termination = 0; break; }
+    if (gmax <= 1e-10) { sum.termination = 3; break; }
+    if (radius < 1e-32) { sum.termination = 6; break; }
+  }
+  sum.iterations = iteration;
+  sum.final_cost = x_cost;
+  if (out) *out = sum;
+  if (lie_out) std::memcpy(lie_out, x.data(), x.size() * sizeof(double));
+  std::vector<Sim3> Swc(n_kf);
+  for (int k = 0; k < n_kf; k++) {
+    const Sim3 S = exp(&x[7 * k]);
+    Swc[k] = inverse(S);
+    if (Tiw_out) {
+      double R[9]; rotation_matrix(S.q, R);
+      double* T = Tiw_out + 16 * k;
+      for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) T[4 * i + j] = R[3 * i + j]; T[4 * i + 3] = (1. / S.s) * S.t[i]; }
+      T[12] = T[13] = T[14] = 0.0; T[15] = 1.0;
+    }
+  }
+  for (int p = 0; p < n_points; p++) {
+    const int rk = ref_kf[p];
+    const Sim3 Srw = exp(&x0[7 * rk]);
+    double Pc[3];
+    act(Srw, Xw + 3 * p, Pc);
+    act(Swc[rk], Pc, Xw_out + 3 * p);
+  }
+  return 0;
+}
+
+}  // extern "C"

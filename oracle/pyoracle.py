@@ -608,3 +608,35 @@ def optimize_sim3(s12, R12, t12, K1, K2, obs1, inv_sigma1, P3D2c, obs2, inv_sigm
     return dict(ret=ret, s=s.value, R=R.reshape(3, 3), t=t, lie=lie, is_bad=bad[:n], iterations=summ.iterations,
                 successful_steps=summ.successful_steps, termination=summ.termination, initial_cost=summ.initial_cost,
                 final_cost=summ.final_cost, trace=trace)
+
+
+# ---------------------------------------------------------------------------------------------------
+# OptimizeEssentialGraph (oracle/ba_oracle.cpp)
+
+def sim3_adjoint(lie):
+    A = np.zeros(49)
+    lib().ba_oracle_sim3_adjoint(_p(_c(lie, np.float64)), _p(A))
+    return A.reshape(7, 7)
+
+
+def essential_edge(Sji13, lie_j, lie_i):
+    r = np.zeros(7); J = np.zeros(49)
+    lib().ba_oracle_essential_edge(_p(_c(Sji13, np.float64)), _p(_c(lie_j, np.float64)), _p(_c(lie_i, np.float64)), _p(r), _p(J))
+    return r, J.reshape(7, 7)
+
+
+def essential_graph(Scw, kf_flags, Snc, edge_j, edge_i, edge_kind, Xw, ref_kf, max_iterations=100):
+    """Scw / Snc: [n_kf][13] = scale, rotation (row-major), translation."""
+    Scw = _c(Scw, np.float64); Snc = _c(Snc, np.float64); fl = _c(kf_flags, np.uint8)
+    ej = _c(edge_j, np.int32); ei = _c(edge_i, np.int32); ek = _c(edge_kind, np.uint8)
+    X = _c(Xw, np.float64).reshape(-1, 3); rk = _c(ref_kf, np.int32)
+    n = len(Scw); m = len(X)
+    lie = np.zeros((n, 7)); T = np.zeros((n, 16)); Xo = np.zeros((max(m, 1), 3)); summ = BaSummary()
+    trace = np.zeros((max_iterations + 2, 8))
+    fn = lib().ba_oracle_essential_graph
+    fn.restype = C.c_int
+    fn(n, _p(Scw), _p(fl), _p(Snc), len(ej), _p(ej), _p(ei), _p(ek), int(max_iterations), m, _p(X), _p(rk), _p(lie), _p(T), _p(Xo),
+       C.byref(summ), _p(trace), len(trace))
+    return dict(lie=lie, Tiw=T.reshape(n, 4, 4), Xw=Xo[:m], iterations=summ.iterations, successful_steps=summ.successful_steps,
+                termination=summ.termination, initial_cost=summ.initial_cost, final_cost=summ.final_cost,
+                jacobian_evaluations=summ.jacobian_evaluations, trace=trace)

@@ -209,3 +209,80 @@ def test_optimize_sim3_scale_step_is_rounding_noise():
     assert np.ptp(scales) > 1e-3                                   # the last bit of the input moves the scale by > 0.1 %
     rots = np.stack([r["lie"][3:6] for r in runs])
     assert np.ptp(rots, 0).max() < 1e-4                            # ... while the observable part agrees
+
+
+# ---- OptimizeEssentialGraph (oracle/ba_oracle.cpp) -------------------------------------------------------------------
+
+def _srt(S):
+    return np.concatenate([[S[0]], np.asarray(S[1]).reshape(-1), S[2]])
+
+
+def _sim3_inv(S):
+    s, R, t = S
+    return 1.0 / s, R.T, -(R.T @ t) / s
+
+
+def test_sim3_adjoint_and_essential_edge_jacobian():
+    """Sophus is not vendored by the reference (find_package(Sophus), unpinned): Sim3::Adj() is restated from its published
+    form and pinned by the defining identity S exp(v) S^-1 = exp(Adj(S) v); EssentialGraphErrorTerm's Jacobians
+    (CeresOptimizer.h:286-309: second-order BCH series times Sj.Adj()) by differences through Sim3Parameterization::Plus."""
+    rng = np.random.default_rng(5)
+    for _ in range(5):
+        x = rng.normal(0, 0.4, 7); v = rng.normal(0, 0.3, 7)
+        S = po.sim3_exp(x)
+        lhs = _sim3_mul(_sim3_mul(S, po.sim3_exp(v)), _sim3_inv(S))
+        rhs = po.sim3_exp(po.sim3_adjoint(x) @ v)
+        assert abs(lhs[0] - rhs[0]) < 1e-12 and np.abs(lhs[1] - rhs[1]).max() < 1e-12 and np.abs(lhs[2] - rhs[2]).max() < 1e-11
+    for mag in (1e-3, 1e-1):
+        xi = rng.normal(0, 0.5, 7); xj = rng.normal(0, 0.5, 7)
+        Si, Sj = po.sim3_exp(xi), po.sim3_exp(xj)
+        noise = po.sim3_exp(rng.normal(0, mag, 7))
+        Sji = _sim3_mul(noise, _sim3_mul(Sj, _sim3_inv(Si)))       # residual = log(noise) at (xj, xi)
+        r, Ji = po.essential_edge(_srt(Sji), xj, xi)
+        assert np.abs(r - po.sim3_log(*noise)).max() < 1e-12
+        eps = 1e-6
+        num_i = np.zeros((7, 7)); num_j = np.zeros((7, 7))
+        for k in range(7):
+            e = np.zeros(7); e[k] = eps
+            num_i[:, k] = (po.essential_edge(_srt(Sji), xj, po.sim3_plus(xi, e))[0] - po.essential_edge(_srt(Sji), xj, po.sim3_plus(xi, -e))[0]) / (2 * eps)
+            num_j[:, k] = (po.essential_edge(_srt(Sji), po.sim3_plus(xj, e), xi)[0] - po.essential_edge(_srt(Sji), po.sim3_plus(xj, -e), xi)[0]) / (2 * eps)
+        tol = 10 * mag ** 4 + 1e-6                                   # series truncated after the second-order term (the
+                                                                     # third vanishes); 1e-6 = difference-quotient noise
+        assert np.abs(num_i - Ji).max() < tol * np.abs(Ji).max() and np.abs(num_j + Ji).max() < tol * np.abs(Ji).max()
+
+
+def test_essential_graph_behaviour():
+    """The loop error is spread over the trajectory: cost falls monotonically by orders of magnitude, the constant (loop)
+    keyframe and the corrected current keyframe stay where the loop closure put them, the mid-loop keyframes move towards
+    the truth, poses come back as [R | t / s] and the points ride along with their reference keyframe."""
+    G = synth.make_essential_graph_problem(60, seed=7)
+    a = (G["Scw"], G["kf_flags"], G["Snc"], G["edge_j"], G["edge_i"], G["edge_kind"], G["Xw"], G["ref_kf"])
+    r = po.essential_graph(*a)
+    assert r["successful_steps"] >= 3 and r["final_cost"] < 1e-2 * r["initial_cost"] and r["termination"] in (1, 2, 3)
+    costs = r["trace"][: r["iterations"] + 1, 0]
+    assert np.all(np.diff(costs) <= 1e-12)
+    L = G["loop_kf"]
+    lie0 = po.sim3_log(G["Scw"][L, 0], G["Scw"][L, 1:10].reshape(3, 3), G["Scw"][L, 10:])
+    assert np.array_equal(r["lie"][L], lie0)
+    centres = lambda T: np.stack([-T[k, :3, :3].T @ T[k, :3, 3] for k in range(len(T))])
+    T0 = np.zeros_like(G["true_Tcw"])
+    for k in range(60):
+        S = G["Snc"][k] if G["kf_flags"][k] & 2 else G["Scw"][k]
+        T0[k, :3, :3] = S[1:10].reshape(3, 3); T0[k, :3, 3] = S[10:]; T0[k, 3, 3] = 1
+    e0 = np.linalg.norm(centres(T0) - centres(G["true_Tcw"]), axis=1)
+    e1 = np.linalg.norm(centres(r["Tiw"]) - centres(G["true_Tcw"]), axis=1)
+    assert e1[59] < 0.01 < e0[59] and e1[25:45].mean() < 0.6 * e0[25:45].mean()
+    for k in (0, 17, 59):
+        s, R, t = po.sim3_exp(r["lie"][k])
+        assert np.abs(r["Tiw"][k, :3, :3] - R).max() < 1e-15 and np.abs(r["Tiw"][k, :3, 3] - t / s).max() < 1e-12
+        assert np.abs(R @ R.T - np.eye(3)).max() < 1e-12
+    # a point keeps its coordinates in its reference keyframe's (Sim3) camera frame
+    for p in (0, 100, 499):
+        k = G["ref_kf"][p]
+        S0 = po.sim3_exp(po.sim3_log(G["Scw"][k, 0], G["Scw"][k, 1:10].reshape(3, 3), G["Scw"][k, 10:]))
+        S1 = po.sim3_exp(r["lie"][k])
+        pc0 = S0[0] * S0[1] @ G["Xw"][p] + S0[2]; pc1 = S1[0] * S1[1] @ r["Xw"][p] + S1[2]
+        assert np.abs(pc0 - pc1).max() < 1e-9
+    # zero iterations: nothing moves, the cost is the initial one
+    z = po.essential_graph(*a, max_iterations=0)
+    assert z["iterations"] == 0 and z["final_cost"] == z["initial_cost"] == r["initial_cost"]
