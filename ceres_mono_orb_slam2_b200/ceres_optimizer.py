@@ -110,6 +110,21 @@ class CeresOptimizer:
                                             C.byref(summ)))
         return dict(ret=ninl.value, s=s.value, R=R.reshape(3, 3), t=t, lie=lie, is_bad=bad[:n], summary=summ.as_dict())
 
+    def OptimizeEssentialGraph(self, Scw, kf_flags, Snc, edge_j, edge_i, edge_kind, Xw, ref_kf, max_iterations: int = 100):
+        """CeresOptimizer::OptimizeEssentialGraph over the flattened graph (see include/cmos_b200.h) ->
+        dict(lie [n_kf][7], Tiw [n_kf][4][4], Xw [n_points][3], summary)."""
+        Scw = np.ascontiguousarray(Scw, np.float64); Snc = np.ascontiguousarray(Snc, np.float64)
+        fl = np.ascontiguousarray(kf_flags, np.uint8)
+        ej = np.ascontiguousarray(edge_j, np.int32); ei = np.ascontiguousarray(edge_i, np.int32)
+        ek = np.ascontiguousarray(edge_kind, np.uint8)
+        X = np.ascontiguousarray(Xw, np.float64).reshape(-1, 3); rk = np.ascontiguousarray(ref_kf, np.int32)
+        n, m = len(Scw), len(X)
+        lie = np.zeros((n, 7)); T = np.zeros((n, 16)); Xo = np.zeros((max(m, 1), 3)); summ = BaSummary()
+        check(self._L.cmos_ba_optimize_essential_graph(self._h, n, ptr(Scw), ptr(fl), ptr(Snc), len(ej), ptr(ej), ptr(ei), ptr(ek),
+                                                       int(max_iterations), m, ptr(X), ptr(rk), ptr(lie), ptr(T), ptr(Xo),
+                                                       C.byref(summ)))
+        return dict(lie=lie, Tiw=T.reshape(n, 4, 4), Xw=Xo[:m], summary=summ.as_dict())
+
     def set_problem(self, cams, cam_flags, points, obs_cam, obs_pt, uv, inv_sigma2, K4):
         cams = np.ascontiguousarray(cams, np.float64); points = np.ascontiguousarray(points, np.float64)
         cf = np.ascontiguousarray(cam_flags, np.uint8)

@@ -1573,6 +1573,8 @@ __global__ void __launch_bounds__(256) k_cam_candidates(BaDev d) {
 
 }  // namespace cmos
 
+#include "posegraph.cuh"
+
 using namespace cmos;
 
 // =================================================================================================
@@ -1636,6 +1638,29 @@ struct cmos_ba {
   float *ds_obs = nullptr, *ds_sig = nullptr;   // [2][cap][2], [2][cap]
   double *ds_pts = nullptr, *ds_out = nullptr;   // [2][cap][3], [24]
   uint8_t* ds_bad = nullptr;
+  // OptimizeEssentialGraph storage (allocated on first use, grown on demand)
+  struct EgStore {
+    size_t cap_kf = 0, cap_e = 0, cap_n = 0, cap_pts = 0, cap_tiles = 0;
+    double *x0 = nullptr, *x1 = nullptr, *x_init = nullptr, *Scw = nullptr, *Snc = nullptr, *lie_out = nullptr, *Tiw = nullptr;
+    uint8_t *flags = nullptr, *kind = nullptr;
+    int *var = nullptr, *var_kf = nullptr, *ej = nullptr, *ei = nullptr, *inc_start = nullptr, *inc_edge = nullptr, *inc_other = nullptr,
+        *inc_sign = nullptr, *tiles = nullptr, *ref = nullptr;
+    Sim3D *meas = nullptr, *Swc = nullptr;
+    double *r = nullptr, *J = nullptr, *A = nullptr, *v = nullptr, *Hd = nullptr, *g = nullptr, *scale = nullptr, *delta = nullptr,
+           *S = nullptr, *rhs = nullptr, *yc = nullptr, *Linv = nullptr, *pe = nullptr, *pk = nullptr, *Xw = nullptr, *Xo = nullptr;
+    LmState* st = nullptr;
+    int* done_host = nullptr;      // page-locked
+    void release() {
+      for (void* b : {(void*)x0, (void*)x1, (void*)x_init, (void*)Scw, (void*)Snc, (void*)lie_out, (void*)Tiw, (void*)flags, (void*)kind,
+                      (void*)var, (void*)var_kf, (void*)ej, (void*)ei, (void*)inc_start, (void*)inc_edge, (void*)inc_other, (void*)inc_sign,
+                      (void*)tiles, (void*)ref, (void*)meas, (void*)Swc, (void*)r, (void*)J, (void*)A, (void*)v, (void*)Hd, (void*)g,
+                      (void*)scale, (void*)delta, (void*)S, (void*)rhs, (void*)yc, (void*)Linv, (void*)pe, (void*)pk, (void*)Xw, (void*)Xo,
+                      (void*)st})
+        if (b) cudaFree(b);
+      if (done_host) cudaFreeHost(done_host);
+      *this = EgStore();
+    }
+  } eg;
   int* d_pan_tiles = nullptr;               // active row tiles of every panel of the blocked factorisation
   std::vector<int> pan_start, pan_first_col; // [n_panels + 1], [n_panels]
   size_t cap_pan_tiles = 0;
@@ -1870,6 +1895,7 @@ int cmos_ba_destroy(cmos_ba_t h) {
     if (b) cudaFree(b);
   for (void* b : {(void*)h->ds_obs, (void*)h->ds_sig, (void*)h->ds_pts, (void*)h->ds_out, (void*)h->ds_bad})
     if (b) cudaFree(b);
+  h->eg.release();
   if (h->stop_registered_by_us && h->stop_host_page) cudaHostUnregister((void*)h->stop_host_page);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -2348,6 +2374,160 @@ int cmos_ba_optimize_sim3(cmos_ba_t h, int32_t n, double* s12, double* R12, doub
   for (int i = 0; i < 9; i++) R12[i] = out[8 + i];
   for (int i = 0; i < 3; i++) t12[i] = out[17 + i];
   *n_inliers = (int)out[20];
+  return CMOS_OK;
+}
+
+int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Scw, const uint8_t* kf_flags, const double* Snc,
+                                     int32_t n_edges, const int32_t* edge_j, const int32_t* edge_i, const uint8_t* edge_kind,
+                                     int32_t max_iterations, int32_t n_points, const double* Xw, const int32_t* ref_kf,
+                                     double* lie_out, double* Tiw_out, double* Xw_out, cmos_ba_summary* summary) {
+  CMOS_REQUIRE(h && Scw && kf_flags && Snc && n_kf > 0, "null argument");
+  CMOS_REQUIRE(n_edges >= 0 && (n_edges == 0 || (edge_j && edge_i && edge_kind)), "null edge arrays");
+  CMOS_REQUIRE(n_points >= 0 && (n_points == 0 || (Xw && ref_kf && Xw_out)), "null point arrays");
+  CMOS_REQUIRE(max_iterations >= 0 && max_iterations + 1 < h->trace_rows, "max_iterations %d too large", max_iterations);
+  for (int e = 0; e < n_edges; e++)
+    CMOS_REQUIRE(edge_j[e] >= 0 && edge_j[e] < n_kf && edge_i[e] >= 0 && edge_i[e] < n_kf, "edge %d references keyframe out of range", e);
+  for (int p = 0; p < n_points; p++) CMOS_REQUIRE(ref_kf[p] >= 0 && ref_kf[p] < n_kf, "point %d references keyframe out of range", p);
+  CMOS_CUDA_OK(cudaSetDevice(h->p.device));
+  cudaStream_t st = h->stream;
+  auto& g = h->eg;
+  // ---- structure: variable keyframes, incidence CSR, row envelope -----------------------------------------------------
+  std::vector<int> var(n_kf, -1), var_kf;
+  for (int k = 0; k < n_kf; k++) if (!(kf_flags[k] & 1)) { var[k] = (int)var_kf.size(); var_kf.push_back(k); }
+  const int Kv = (int)var_kf.size(), n = 7 * Kv;
+  std::vector<int> inc_start(Kv + 1, 0);
+  for (int e = 0; e < n_edges; e++) {
+    if (var[edge_i[e]] >= 0) inc_start[var[edge_i[e]] + 1]++;
+    if (var[edge_j[e]] >= 0) inc_start[var[edge_j[e]] + 1]++;
+  }
+  for (int a = 0; a < Kv; a++) inc_start[a + 1] += inc_start[a];
+  const int n_inc = inc_start[Kv];
+  std::vector<int> inc_edge(std::max(n_inc, 1)), inc_other(std::max(n_inc, 1)), inc_sign(std::max(n_inc, 1)), fill(inc_start.begin(), inc_start.end() - 1);
+  std::vector<int> first_blk(Kv);
+  for (int a = 0; a < Kv; a++) first_blk[a] = a;
+  for (int e = 0; e < n_edges; e++) {       // edge order is kept inside every keyframe's list: the sums follow the reference's insertion order
+    const int vi = var[edge_i[e]], vj = var[edge_j[e]];
+    if (vi >= 0) { const int q = fill[vi]++; inc_edge[q] = e; inc_other[q] = vj; inc_sign[q] = 1; }
+    if (vj >= 0) { const int q = fill[vj]++; inc_edge[q] = e; inc_other[q] = vi; inc_sign[q] = -1; }
+    if (vi >= 0 && vj >= 0) { first_blk[std::max(vi, vj)] = std::min(first_blk[std::max(vi, vj)], std::min(vi, vj)); }
+  }
+  std::vector<int> tiles, pan_start(1, 0), pan_first_col;
+  for (int k0 = 0; k0 < n; k0 += kNB) {
+    const int kb = std::min(kNB, n - k0), t0 = k0 + kb;
+    int fc = k0;
+    for (int r = k0; r < k0 + kb; r++) fc = std::min(fc, 7 * first_blk[r / 7]);
+    pan_first_col.push_back(fc);
+    for (int t = 0; t0 + 64 * t <= n; t++) {
+      const int r0 = t0 + 64 * t, r1 = std::min(r0 + 63, n);
+      bool active = r1 == n;                                   // the rhs row
+      for (int r = r0; r <= std::min(r1, n - 1) && !active; r++) active = 7 * first_blk[r / 7] < t0;
+      if (active) tiles.push_back(t);
+    }
+    pan_start.push_back((int)tiles.size());
+  }
+  // ---- storage --------------------------------------------------------------------------------------------------------
+  const size_t n_panels = (n + kNB - 1) / kNB;
+  if ((size_t)n_kf > g.cap_kf || (size_t)n_edges > g.cap_e || (size_t)n > g.cap_n || (size_t)n_points > g.cap_pts || tiles.size() > g.cap_tiles) {
+    const size_t ck = std::max<size_t>(n_kf, g.cap_kf), ce = std::max<size_t>(std::max(n_edges, 1), g.cap_e), cn = std::max<size_t>(std::max(n, 7), g.cap_n),
+                 cp = std::max<size_t>(std::max(n_points, 1), g.cap_pts), ct = std::max<size_t>(std::max<size_t>(tiles.size(), 1), g.cap_tiles);
+    g.release();
+    const size_t cpan = (cn + kNB - 1) / kNB;
+    bool ok = alloc(&g.x0, 7 * ck) && alloc(&g.x1, 7 * ck) && alloc(&g.x_init, 7 * ck) && alloc(&g.Scw, 13 * ck) && alloc(&g.Snc, 13 * ck) &&
+              alloc(&g.lie_out, 7 * ck) && alloc(&g.Tiw, 16 * ck) && alloc(&g.flags, ck) && alloc(&g.kind, ce) && alloc(&g.var, ck) &&
+              alloc(&g.var_kf, ck) && alloc(&g.ej, ce) && alloc(&g.ei, ce) && alloc(&g.inc_start, ck + 1) && alloc(&g.inc_edge, 2 * ce) &&
+              alloc(&g.inc_other, 2 * ce) && alloc(&g.inc_sign, 2 * ce) && alloc(&g.tiles, ct) && alloc(&g.ref, cp) && alloc(&g.meas, ce) &&
+              alloc(&g.Swc, ck) && alloc(&g.r, 7 * ce) && alloc(&g.J, 49 * ce) && alloc(&g.A, 49 * ce) && alloc(&g.v, 7 * ce) &&
+              alloc(&g.Hd, 49 * ck) && alloc(&g.g, cn) && alloc(&g.scale, cn) && alloc(&g.delta, cn) && alloc(&g.S, cn * cn) &&
+              alloc(&g.rhs, cn) && alloc(&g.yc, cn) && alloc(&g.Linv, cpan * kNB * kNB) && alloc(&g.pe, 3 * ce) && alloc(&g.pk, 3 * ck) &&
+              alloc(&g.Xw, 3 * cp) && alloc(&g.Xo, 3 * cp) && alloc(&g.st, 1) &&
+              cudaMallocHost((void**)&g.done_host, sizeof(int)) == cudaSuccess;
+    if (!ok) {
+      set_error("device allocation failed for a %d-keyframe essential graph: %s", n_kf, cudaGetErrorString(cudaGetLastError()));
+      g.release();
+      return CMOS_ERR_CUDA;
+    }
+    g.cap_kf = ck; g.cap_e = ce; g.cap_n = cn; g.cap_pts = cp; g.cap_tiles = ct;
+  }
+  auto up = [&](void* dst, const void* src, size_t bytes) { return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
+  CMOS_CUDA_OK(up(g.Scw, Scw, (size_t)n_kf * 13 * sizeof(double)));
+  CMOS_CUDA_OK(up(g.Snc, Snc, (size_t)n_kf * 13 * sizeof(double)));
+  CMOS_CUDA_OK(up(g.flags, kf_flags, n_kf));
+  CMOS_CUDA_OK(up(g.var, var.data(), (size_t)n_kf * sizeof(int)));
+  CMOS_CUDA_OK(up(g.var_kf, var_kf.data(), (size_t)Kv * sizeof(int)));
+  CMOS_CUDA_OK(up(g.ej, edge_j, (size_t)n_edges * sizeof(int)));
+  CMOS_CUDA_OK(up(g.ei, edge_i, (size_t)n_edges * sizeof(int)));
+  CMOS_CUDA_OK(up(g.kind, edge_kind, n_edges));
+  CMOS_CUDA_OK(up(g.inc_start, inc_start.data(), (size_t)(Kv + 1) * sizeof(int)));
+  CMOS_CUDA_OK(up(g.inc_edge, inc_edge.data(), (size_t)n_inc * sizeof(int)));
+  CMOS_CUDA_OK(up(g.inc_other, inc_other.data(), (size_t)n_inc * sizeof(int)));
+  CMOS_CUDA_OK(up(g.inc_sign, inc_sign.data(), (size_t)n_inc * sizeof(int)));
+  CMOS_CUDA_OK(up(g.tiles, tiles.data(), tiles.size() * sizeof(int)));
+  CMOS_CUDA_OK(up(g.Xw, Xw, (size_t)n_points * 3 * sizeof(double)));
+  CMOS_CUDA_OK(up(g.ref, ref_kf, (size_t)n_points * sizeof(int)));
+  EgDev d{};
+  d.n_kf = n_kf; d.Kv = Kv; d.E = n_edges; d.n = n;
+  d.x[0] = g.x0; d.x[1] = g.x1; d.x0 = g.x_init; d.Scw = g.Scw; d.Snc = g.Snc; d.kf_flags = g.flags; d.var = g.var; d.var_kf = g.var_kf;
+  d.edge_j = g.ej; d.edge_i = g.ei; d.edge_kind = g.kind; d.meas = g.meas; d.r = g.r; d.J = g.J; d.A = g.A; d.v = g.v;
+  d.inc_start = g.inc_start; d.inc_edge = g.inc_edge; d.inc_other = g.inc_other; d.inc_sign = g.inc_sign;
+  d.Hd = g.Hd; d.g = g.g; d.scale = g.scale; d.delta = g.delta; d.S = g.S; d.rhs = g.rhs; d.yc = g.yc;
+  d.p_cost = g.pe; d.p_mcc = g.pe + g.cap_e; d.p_cand = g.pe + 2 * g.cap_e;
+  d.p_gmax = g.pk; d.p_xn2 = g.pk + g.cap_kf; d.p_sn2 = g.pk + 2 * g.cap_kf;
+  d.st = g.st; d.trace = h->dp_trace;
+  BaDev dv{};                       // the view the blocked Cholesky kernels read: S, rhs, yc, nc, st
+  dv.S = g.S; dv.rhs = g.rhs; dv.yc = g.yc; dv.nc = n; dv.st = g.st;
+  const int eff_iterations = Kv > 0 ? max_iterations : 0;
+  h->launches = 0;
+  const int gk = (n_kf + 127) / 128, ge = std::max(1, (n_edges + 63) / 64), gw = std::max(1, (Kv + 3) / 4);
+  k_eg_logs<<<gk, 128, 0, st>>>(d, eff_iterations);
+  k_eg_meas<<<std::max(1, (n_edges + 127) / 128), 128, 0, st>>>(d);
+  h->launches += 2;
+  auto linearize = [&]() {
+    k_eg_linearize<<<ge, 64, 0, st>>>(d);
+    k_eg_assemble<<<gw, 128, 0, st>>>(d);
+    k_eg_post_lin<<<1, 256, 0, st>>>(d);
+    h->launches += 3;
+  };
+  for (int it = 0; it < eff_iterations; it++) {
+    linearize();
+    CMOS_CUDA_OK(cudaMemsetAsync(g.S, 0, (size_t)n * n * sizeof(double), st));
+    k_eg_build<<<gw, 128, 0, st>>>(d);
+    h->launches++;
+    for (int k0 = 0, p = 0; k0 < n; k0 += kNB, p++) {
+      const int kb = std::min(kNB, n - k0);
+      k_potrf_diag<<<1, 256, kPanelSmem, st>>>(dv, k0, kb, g.Linv);
+      const int na = pan_start[p + 1] - pan_start[p];
+      if (na > 0) {
+        const int* tl = g.tiles + pan_start[p];
+        k_trsm_panel<<<2 * na, 256, kPanelSmem, st>>>(dv, k0, kb, g.Linv, tl);
+        k_syrk_tile<<<na * (na + 1) / 2, 256, kPanelSmem, st>>>(dv, k0, kb, tl);
+        h->launches += 2;
+      }
+      h->launches++;
+    }
+    for (int k0 = ((n - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {
+      const int kb = std::min(kNB, n - k0);
+      const int c0 = std::min(pan_first_col[k0 / kNB], k0);
+      k_backsolve_panel<<<std::max(1, (k0 - c0 + 255) / 256), 256, 0, st>>>(dv, k0, kb, g.Linv, c0);
+      h->launches++;
+    }
+    k_eg_step<<<gk, 128, 0, st>>>(d);
+    k_eg_eval<<<ge, 64, 0, st>>>(d);
+    k_eg_decide<<<1, 256, 0, st>>>(d, g.done_host);
+    h->launches += 3;
+    CMOS_CUDA_OK(cudaStreamSynchronize(st));         // one word: has the device-side state machine terminated?
+    if (*g.done_host) break;
+  }
+  if (eff_iterations == 0) linearize();              // Ceres still evaluates iteration 0
+  k_eg_summary<<<1, 1, 0, st>>>(d, h->dp_sum);
+  k_eg_finish<<<gk, 128, 0, st>>>(d, g.lie_out, g.Tiw, g.Swc);
+  h->launches += 2;
+  if (n_points > 0) { k_eg_points<<<(n_points + 255) / 256, 256, 0, st>>>(d, n_points, g.Xw, g.ref, g.Swc, g.Xo); h->launches++; }
+  CMOS_CUDA_OK(cudaGetLastError());
+  if (lie_out) CMOS_CUDA_OK(cudaMemcpyAsync(lie_out, g.lie_out, (size_t)n_kf * 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (Tiw_out) CMOS_CUDA_OK(cudaMemcpyAsync(Tiw_out, g.Tiw, (size_t)n_kf * 16 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (n_points > 0) CMOS_CUDA_OK(cudaMemcpyAsync(Xw_out, g.Xo, (size_t)n_points * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (summary) CMOS_CUDA_OK(cudaMemcpyAsync(summary, h->dp_sum, sizeof(cmos_ba_summary), cudaMemcpyDeviceToHost, st));
+  CMOS_CUDA_OK(cudaStreamSynchronize(st));
   return CMOS_OK;
 }
 

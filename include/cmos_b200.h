@@ -519,6 +519,28 @@ int cmos_ba_optimize_sim3(cmos_ba_t h, int32_t n, double* s12, double* R12, doub
                           const float* inv_sigma2, const double* P3D1c, float th2, int32_t max_iterations,
                           uint8_t* is_bad, double* lie7, int32_t* n_inliers, cmos_ba_summary* summary);
 
+/* CeresOptimizer::OptimizeEssentialGraph(map, loop_keyframe, current_keyframe, keyframes_non_corrected_sim3,
+ * keyframes_corrected_sim3, loop_connections, is_fixed_scale) (CeresOptimizer.cc:736-957; EssentialGraphErrorTerm
+ * include/CeresOptimizer.h:270-328).  The adapter flattens the pointer graph in the reference's insertion order:
+ *   Scw [n_kf][13]    scale, rotation (row-major 3x3), translation of every keyframe's initial Scw: its entry of
+ *                     keyframes_corrected_sim3 where present (:767-769), else (1, Rcw, tcw) (:770-774)
+ *   kf_flags [n_kf]   bit 0: constant block = the loop keyframe (:780-783); bit 1: Snc holds the keyframe's entry of
+ *                     keyframes_non_corrected_sim3
+ *   Snc [n_kf][13]    non-corrected Siw (read only where bit 1 is set)
+ *   edges             one per residual block, parameter block 0 = keyframe edge_j, block 1 = keyframe edge_i;
+ *                     edge_kind 0 = loop-connection edge, measured between the initial (corrected) values (:797-809);
+ *                     edge_kind 1 = spanning-tree, loop or co-visibility edge, each side's non-corrected Sim3 where it has
+ *                     one (:822-895)
+ *   max_iterations    the reference uses 100 (:747)
+ *   points            Xw [n_points][3] + ref_kf [n_points] (corrected_reference_ or the reference keyframe, :939-946)
+ * Out (any may be NULL except Xw_out when n_points > 0): lie_out [n_kf][7] optimised logs (upsilon, omega, sigma);
+ * Tiw_out [n_kf][16] row-major [R | t / s; 0 0 0 1] for KeyFrame::SetPose (:918-926); Xw_out [n_points][3] corrected
+ * positions (:948-953).  Synchronous; host pointers.  is_fixed_scale is ignored by the reference. */
+int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Scw, const uint8_t* kf_flags, const double* Snc,
+                                     int32_t n_edges, const int32_t* edge_j, const int32_t* edge_i, const uint8_t* edge_kind,
+                                     int32_t max_iterations, int32_t n_points, const double* Xw, const int32_t* ref_kf,
+                                     double* lie_out, double* Tiw_out, double* Xw_out, cmos_ba_summary* summary);
+
 /* Multi-GPU global bundle adjustment (no counterpart in the reference, which is single process).
  * One process per GPU.  Map points — and with them their observations — are partitioned over the ranks;
  * keyframes are replicated.  Each rank uploads ALL keyframes but only ITS points/observations with

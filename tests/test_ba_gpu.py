@@ -171,3 +171,58 @@ def test_optimize_sim3_converging_regime(kw):
     chk = po.optimize_sim3(got["s"], got["R"], got["t"], *base[3:], max_iterations=0)
     assert np.array_equal(got["is_bad"], chk["is_bad"]) and got["ret"] == chk["ret"]
     opt.close()
+
+
+@pytest.mark.parametrize("n_kf,kw", [(60, dict(seed=7)), (150, dict(seed=8, n_group=6, covis=(2, 3, 5))),
+                                     (24, dict(seed=9, n_group=2, n_points=0, drift=(0.01, 0.03, 0.01)))])
+def test_optimize_essential_graph_matches_oracle(n_kf, kw):
+    """cmos_ba_optimize_essential_graph == the restated OptimizeEssentialGraph: same iterations / accepted steps /
+    termination, per-iteration cost and radius, Sim3 logs within 1e-7 (north_star asks 1e-4 relative), SE3 poses and corrected
+    map points within 1e-7."""
+    G = synth.make_essential_graph_problem(n_kf, **kw)
+    a = (G["Scw"], G["kf_flags"], G["Snc"], G["edge_j"], G["edge_i"], G["edge_kind"], G["Xw"], G["ref_kf"])
+    ref = po.essential_graph(*a)
+    opt = CeresOptimizer(max_cams=2, max_points=8, max_obs=8)
+    got = opt.OptimizeEssentialGraph(*a)
+    s = got["summary"]
+    assert (s["iterations"], s["successful_steps"], s["termination"]) == (ref["iterations"], ref["successful_steps"], ref["termination"])
+    assert s["jacobian_evaluations"] == ref["jacobian_evaluations"]
+    tr = opt.pose_trace(0, s["iterations"] + 1)
+    rt = ref["trace"][: s["iterations"] + 1]
+    assert np.abs(tr[:, 0] - rt[:, 0]).max() <= 1e-7 * rt[0, 0] and np.array_equal(tr[:, 6], rt[:, 6])
+    assert np.abs(tr[:, 5] / rt[:, 5] - 1).max() <= 1e-4
+    scale = max(1.0, np.abs(ref["lie"]).max())
+    assert np.abs(got["lie"] - ref["lie"]).max() <= 1e-7 * scale < REL
+    assert np.abs(got["Tiw"] - ref["Tiw"]).max() <= 1e-7 * scale
+    if len(G["Xw"]):
+        assert np.abs(got["Xw"] - ref["Xw"]).max() <= 1e-7 * max(1.0, np.abs(ref["Xw"]).max())
+    L = G["loop_kf"]
+    lie0 = po.sim3_log(G["Scw"][L, 0], G["Scw"][L, 1:10].reshape(3, 3), G["Scw"][L, 10:])
+    assert np.abs(got["lie"][L] - lie0).max() <= 1e-12 * scale             # the constant block is the log of its input, untouched
+    # zero iterations: Ceres still evaluates the cost; nothing moves
+    z = opt.OptimizeEssentialGraph(*a, max_iterations=0)
+    zr = po.essential_graph(*a, max_iterations=0)
+    assert z["summary"]["iterations"] == 0 and abs(z["summary"]["initial_cost"] - zr["initial_cost"]) <= 1e-9 * zr["initial_cost"]
+    assert np.abs(z["lie"] - zr["lie"]).max() <= 1e-12 * scale
+    opt.close()
+
+
+def test_optimize_essential_graph_edge_cases():
+    """Every keyframe constant -> no solve, poses recovered from the inputs; duplicate edges between one pair accumulate;
+    out-of-range indices are rejected with an error, not a crash."""
+    G = synth.make_essential_graph_problem(12, seed=3, n_group=2, n_points=20)
+    opt = CeresOptimizer(max_cams=2, max_points=8, max_obs=8)
+    allc = G["kf_flags"] | 1
+    a = (G["Scw"], allc, G["Snc"], G["edge_j"], G["edge_i"], G["edge_kind"], G["Xw"], G["ref_kf"])
+    got = opt.OptimizeEssentialGraph(*a); ref = po.essential_graph(*a)
+    assert got["summary"]["iterations"] == 0 and np.abs(got["Tiw"] - ref["Tiw"]).max() < 1e-12
+    assert np.abs(got["Xw"] - ref["Xw"]).max() < 1e-9
+    ej = np.concatenate([G["edge_j"], G["edge_j"][-5:]]); ei = np.concatenate([G["edge_i"], G["edge_i"][-5:]])
+    ek = np.concatenate([G["edge_kind"], G["edge_kind"][-5:]])
+    b = (G["Scw"], G["kf_flags"], G["Snc"], ej, ei, ek, G["Xw"], G["ref_kf"])
+    got = opt.OptimizeEssentialGraph(*b); ref = po.essential_graph(*b)
+    assert got["summary"]["iterations"] == ref["iterations"] and np.abs(got["lie"] - ref["lie"]).max() < 1e-7
+    bad = ei.copy(); bad[0] = 99
+    with pytest.raises(Exception):
+        opt.OptimizeEssentialGraph(G["Scw"], G["kf_flags"], G["Snc"], ej, bad, ek, G["Xw"], G["ref_kf"])
+    opt.close()
