@@ -1,9 +1,13 @@
 // Drop-in for ORB_SLAM2::CeresOptimizer::{PoseOptimization, LocalBundleAdjustment, BundleAdjustment,
 // GlobalBundleAdjustemnt, CheckOutlier} (include/CeresOptimizer.h:353-387) over POD views.  Static methods like
 // the reference; each calling thread gets its own engine context (SURVEY.md §8b "Threading").
-// OptimizeSim3 / OptimizeEssentialGraph are "next" rows and stay on the reference's Ceres code.
+// OptimizeSim3 / OptimizeEssentialGraph are covered as well.
 #ifndef ORB_SLAM2_CMOS_CERESOPTIMIZER_H
 #define ORB_SLAM2_CMOS_CERESOPTIMIZER_H
+
+#include <algorithm>
+#include <set>
+#include <utility>
 
 #include "views.h"
 
@@ -52,6 +56,71 @@ class CeresOptimizer {
                                             frame->n, frame->K4, 100, frame->is_outlier.data(), &inliers, nullptr, 0,
                                             nullptr), "CeresOptimizer::PoseOptimization");
     return inliers;
+  }
+
+  // returns n_correspondences - n_bad, 0 when fewer than 10 remain (CeresOptimizer.cc:731-734); S12 in/out
+  static int OptimizeSim3(Sim3MatchesView& m, Sim3POD& S12, const float th2, const bool /*bFixScale: unused by the reference*/) {
+    m.is_bad.assign(std::max(m.n, 1), 0);
+    int32_t inliers = 0;
+    cmos_throw_if(cmos_ba_optimize_sim3(ctx(), m.n, &S12.s, S12.R, S12.t, m.K1, m.K2, m.obs1, m.inv_sigma1, m.P3D2c, m.obs2,
+                                        m.inv_sigma2, m.P3D1c, th2, 100, m.is_bad.data(), nullptr, &inliers, nullptr),
+                  "CeresOptimizer::OptimizeSim3");
+    m.is_bad.resize(m.n);
+    return inliers;
+  }
+
+  // Collects the residual blocks exactly as CeresOptimizer.cc:793-895 does (loop connections first, then per keyframe its
+  // parent, its older loop edges and its older co-visible keyframes that are neither parent, child, loop edge nor already
+  // inserted), solves on the device and fills g.Tiw / g.corrected_pos.  Where the reference iterates a std::set /
+  // std::map keyed by KeyFrame* (heap-address order) the index order of the view is used.
+  static void OptimizeEssentialGraph(EssentialGraphView& g, const bool& /*is_fixed_scale: unused by the reference*/ = false) {
+    const int min_weight = 100;
+    const int n = g.n_keyframes;
+    std::vector<double> Scw(13 * (size_t)n), Snc(13 * (size_t)n, 0.0);
+    std::vector<uint8_t> flags(n, 0);
+    for (int k = 0; k < n; k++) {
+      const Sim3POD& S = g.has_corrected[k] ? g.corrected[k] : g.pose[k];
+      Scw[13 * k] = S.s; std::copy(S.R, S.R + 9, &Scw[13 * k + 1]); std::copy(S.t, S.t + 3, &Scw[13 * k + 10]);
+      if (g.has_non_corrected[k]) {
+        const Sim3POD& N = g.non_corrected[k];
+        Snc[13 * k] = N.s; std::copy(N.R, N.R + 9, &Snc[13 * k + 1]); std::copy(N.t, N.t + 3, &Snc[13 * k + 10]);
+        flags[k] |= 2;
+      }
+      if (k == g.loop_keyframe) flags[k] |= 1;
+    }
+    std::vector<int32_t> ej, ei;
+    std::vector<uint8_t> ek;
+    std::set<std::pair<unsigned long, unsigned long> > inserted;
+    for (int i = 0; i < n; i++)
+      for (size_t c = 0; c < g.loop_connections[i].size(); c++) {
+        const int j = g.loop_connections[i][c];
+        if ((i != g.current_keyframe || j != g.loop_keyframe) && g.loop_connection_weight[i][c] < min_weight) continue;
+        ej.push_back(j); ei.push_back(i); ek.push_back(0);
+        inserted.insert(std::make_pair(std::min(g.id[i], g.id[j]), std::max(g.id[i], g.id[j])));
+      }
+    for (int i = 0; i < n; i++) {
+      const int parent = g.parent[i];
+      if (parent >= 0) { ej.push_back(parent); ei.push_back(i); ek.push_back(1); }
+      const std::vector<int>& le = g.loop_edges[i];
+      for (size_t c = 0; c < le.size(); c++)
+        if (g.id[le[c]] < g.id[i]) { ej.push_back(le[c]); ei.push_back(i); ek.push_back(1); }
+      for (size_t c = 0; c < g.covisibles[i].size(); c++) {
+        const int kn = g.covisibles[i][c];
+        if (kn < 0 || kn == parent) continue;
+        if (std::find(g.children[i].begin(), g.children[i].end(), kn) != g.children[i].end()) continue;
+        if (std::find(le.begin(), le.end(), kn) != le.end()) continue;
+        if (!(g.id[kn] < g.id[i])) continue;
+        if (inserted.count(std::make_pair(std::min(g.id[i], g.id[kn]), std::max(g.id[i], g.id[kn])))) continue;
+        ej.push_back(kn); ei.push_back(i); ek.push_back(1);
+      }
+    }
+    g.Tiw.assign(16 * (size_t)n, 0.0);
+    g.corrected_pos.assign(3 * (size_t)std::max(g.n_points, 1), 0.0);
+    cmos_throw_if(cmos_ba_optimize_essential_graph(ctx(), n, Scw.data(), flags.data(), Snc.data(), (int32_t)ej.size(), ej.data(),
+                                                   ei.data(), ek.data(), 100, g.n_points, g.point_pos, g.point_ref, nullptr,
+                                                   g.Tiw.data(), g.corrected_pos.data(), nullptr),
+                  "CeresOptimizer::OptimizeEssentialGraph");
+    g.corrected_pos.resize(3 * (size_t)g.n_points);
   }
 
   // chi2 test of one observation (CeresOptimizer.cc:227-241); host arithmetic, it is 20 flops

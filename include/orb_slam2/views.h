@@ -127,6 +127,49 @@ struct GraphView {
   std::vector<uint8_t> erase;               // out (LocalBA): observations to erase from the map
 };
 
+// Sophus::Sim3d as scale(), rotationMatrix() (row-major), translation() — 13 doubles, the layout the C ABI reads.
+struct Sim3POD {
+  double s = 1.0;
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  double t[3] = {0, 0, 0};
+};
+
+// OptimizeSim3(keyframe_1, keyframe_2, matches12, S12, th2, bFixScale): the correspondences that pass the tests of
+// CeresOptimizer.cc:646-654, in matches12 order.
+struct Sim3MatchesView {
+  int n = 0;
+  float K1[4], K2[4];                       // fx, fy, cx, cy
+  const float* obs1 = nullptr;              // n x 2, keyframe_1->undistort_keypoints_[i].pt
+  const float* inv_sigma1 = nullptr;        // n, keyframe_1->inv_level_sigma2s_[octave]
+  const double* P3D2c = nullptr;            // n x 3, R2cw * map_point_2 + t2cw
+  const float* obs2 = nullptr;
+  const float* inv_sigma2 = nullptr;
+  const double* P3D1c = nullptr;
+  std::vector<uint8_t> is_bad;              // out: is_outlier_12 || is_outlier_21 per correspondence
+};
+
+// OptimizeEssentialGraph(map, loop_keyframe, current_keyframe, non_corrected, corrected, loop_connections, fixed_scale):
+// the map's non-bad keyframes (map->GetAllKeyFrames()) by index, with the accessors the function calls.
+struct EssentialGraphView {
+  int n_keyframes = 0;
+  std::vector<unsigned long> id;                    // id_
+  std::vector<Sim3POD> pose;                        // (1, GetRotation(), GetTranslation())
+  std::vector<int> parent;                          // GetParent() or -1
+  std::vector<std::vector<int> > children;          // hasChild
+  std::vector<std::vector<int> > loop_edges;        // GetLoopEdges()
+  std::vector<std::vector<int> > covisibles;        // GetCovisiblesByWeight(100), in its (weight-sorted) order
+  std::vector<std::vector<int> > loop_connections;  // loop_connections[keyframe], empty when the keyframe has no entry
+  std::vector<std::vector<int> > loop_connection_weight;   // GetWeight(keyframe, connected) of every entry above
+  std::vector<uint8_t> has_corrected, has_non_corrected;
+  std::vector<Sim3POD> corrected, non_corrected;    // keyframes_corrected_sim3 / keyframes_non_corrected_sim3 entries
+  int loop_keyframe = -1, current_keyframe = -1;    // indices
+  int n_points = 0;                                 // map->GetAllMapPoints() that are not bad
+  const double* point_pos = nullptr;                // n_points x 3
+  const int32_t* point_ref = nullptr;               // index of corrected_reference_ / GetReferenceKeyFrame() (:939-946)
+  std::vector<double> Tiw;                          // out: n_keyframes x 16 for SetPose
+  std::vector<double> corrected_pos;                // out: n_points x 3 for SetWorldPos
+};
+
 inline void cmos_throw_if(int status, const char* what) {
   if (status != CMOS_OK) throw std::runtime_error(std::string(what) + ": " + cmos_last_error());
 }
