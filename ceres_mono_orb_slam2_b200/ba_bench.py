@@ -103,6 +103,32 @@ def _bench_graph(opt, G, K4, steps, warmup, local: bool, iters, label):
             "gpu_launches_per_solve": launches}
 
 
+def bench_essential_graph(device: int, steps: int, n_kf: int = 1000, n_points: int = 100000):
+    """CeresOptimizer::OptimizeEssentialGraph after a loop closure over n_kf keyframes (spanning tree + three co-visibility
+    edges per keyframe + loop connections) and the correction of n_points map points; the call is synchronous over host
+    buffers, so this is an end-to-end time."""
+    G = synth.make_essential_graph_problem(n_kf, seed=8, n_group=10, covis=(2, 3, 5), n_points=n_points)
+    a = (G["Scw"], G["kf_flags"], G["Snc"], G["edge_j"], G["edge_i"], G["edge_kind"], G["Xw"], G["ref_kf"])
+    opt = CeresOptimizer(max_cams=2, max_points=8, max_obs=8, device=device)
+    got = opt.OptimizeEssentialGraph(*a)               # warm-up: allocates the storage
+    best = None
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        got = opt.OptimizeEssentialGraph(*a)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    launches = opt.launch_count()
+    s = got["summary"]
+    opt.close()
+    E = len(G["edge_j"])
+    return {"config": f"OptimizeEssentialGraph, {n_kf} keyframes x {E} edges (7 residuals each), {n_points} map points corrected, "
+                      f"max 100 LM iterations", "ms_per_solve": best * 1e3, "iterations": s["iterations"],
+            "successful_steps": s["successful_steps"], "termination": s["termination"],
+            "cost": [s["initial_cost"], s["final_cost"]], "unknowns": 7 * (n_kf - 1),
+            "value": E * s["jacobian_evaluations"] / best / 1e6, "unit": "M edge linearisations/s",
+            "gpu_launches_per_solve": launches, "timing": "wall clock around the synchronous C-ABI call, host buffers, best of %d" % steps}
+
+
 def run(device: int, world: int, args):
     """Returns the "ba" object of bench.py's JSON line (rank 0 formats it; every rank runs its replica)."""
     steps = max(3, min(args.steps, 20)); warmup = 3
@@ -116,6 +142,7 @@ def run(device: int, world: int, args):
                                    "configs[3]: LocalBundleAdjustment, 20 keyframes x 3000 points x 12000 observations, "
                                    "5 Huber + 10 LM iterations")
     opt.close()
+    out["essential_graph"] = bench_essential_graph(device, max(2, min(steps, 5)))
     if not getattr(args, "no_global", False):
         G = synth.make_ba_problem_fast(1000, 100000, 5, seed=5)
         opt = CeresOptimizer(max_cams=1000, max_points=100000, max_obs=500000, device=device)
