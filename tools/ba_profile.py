@@ -20,6 +20,22 @@ elif which == "pose":
     opt = CeresOptimizer(max_pose_batch=1, max_pose_corr=1500)
     for _ in range(3):
         print(opt.PoseOptimization(P["pose"][None], P["Xw"][None], P["uv"][None], P["inv_sigma2"][None], K4, max_iterations=4)[3])
+elif which == "essential":
+    import time
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+    E = synth.make_essential_graph_problem(n, seed=8, n_group=10, covis=(2, 3, 5), n_points=100000)
+    opt = CeresOptimizer(max_cams=2, max_points=8, max_obs=8)
+    a = (E["Scw"], E["kf_flags"], E["Snc"], E["edge_j"], E["edge_i"], E["edge_kind"], E["Xw"], E["ref_kf"])
+    for _ in range(2):
+        t0 = time.perf_counter()
+        r = opt.OptimizeEssentialGraph(*a)
+        print(r["summary"], opt.launch_count(), "launches", (time.perf_counter() - t0) * 1e3, "ms")
+elif which == "sim3":
+    P = synth.make_sim3_problem(n=300, seed=6)
+    opt = CeresOptimizer(max_cams=2, max_points=8, max_obs=8)
+    for _ in range(3):
+        print(opt.OptimizeSim3(P["s0"], P["R0"], P["t0"], P["K"], P["K"], P["obs1"], P["inv_sigma1"], P["P3D2c"], P["obs2"],
+                               P["inv_sigma2"], P["P3D1c"])["summary"])
 else:
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     G = synth.make_ba_problem_fast(1000, 100000, 5, seed=5)
