@@ -39,7 +39,18 @@ namespace cmos {
 constexpr int kPoseThreads = 256;
 constexpr int kLinThreads = 128;
 constexpr int kCamThreads = 128;
-constexpr int kSolveThreads = 1024;
+#ifndef CMOS_SOLVE_THREADS
+#define CMOS_SOLVE_THREADS 512
+#endif
+// Trailing-update variants measured on B200 at configs[3] (tools/ab_solve.py): row-per-warp 1.768 ms per LocalBA solve,
+// 4x4 register tiles 1.796 ms, tiles that skip empty column groups 1.95 ms; 1024 threads row-per-warp 1.799 ms.
+#ifndef CMOS_SOLVE_TILE
+#define CMOS_SOLVE_TILE 0
+#endif
+#ifndef CMOS_SOLVE_NU
+#define CMOS_SOLVE_NU 0
+#endif
+constexpr int kSolveThreads = CMOS_SOLVE_THREADS;
 constexpr int kSmallMaxN = 228;      // packed lower triangle + rhs row + panel buffer of a 228-column system = 223.5 KB
 constexpr int kNB = 64;              // panel width of the blocked factorisation
 constexpr int kTraceCols = 8;
@@ -482,6 +493,7 @@ struct BaDev {
   double *Sblk;                             // [n_blocks][36] reduced-system blocks (a,b) as assembled by k_schur
   const int* var_cam;                       // [Kv] variable index -> keyframe
   double* red;                              // [8] locally reduced scalars (all-reduced across ranks when multi)
+  unsigned int* ticket;                     // [2] arrival counters of the fused reduce-and-decide tails (single GPU)
   int multi, is_root;                       // multi: points are sharded over ranks; is_root: adds the keyframe-only terms
   double *part;                             // partial sums, see offsets
   int n_lin_blocks;
@@ -500,6 +512,10 @@ __global__ void k_lm_init(BaDev d, int max_iterations) {
   d.st->pad = aborted;
   if (aborted || (d.stop_flag && *d.stop_flag)) { d.st->pad = 1; d.st->done = 1; d.st->termination = TERM_USER; }
 }
+
+__device__ bool last_cta_arrives(unsigned int* ticket, unsigned int n_ctas);
+__device__ void post_lin_body(const BaDev& d, LmState& st, int phase, double* scratch);
+__device__ void decide_body(const BaDev& d, LmState& st, int phase, double* scratch);
 
 __global__ void __launch_bounds__(kLinThreads) k_linearize(BaDev d) {
   __shared__ double scratch[33];
@@ -575,7 +591,7 @@ __device__ void cam_finish(const BaDev& d, const LmState& st, int a) {
 }
 
 __global__ void __launch_bounds__(kCamThreads) k_cam_blocks(BaDev d) {
-  __shared__ double s_red[kCamThreads / 32][27];
+  __shared__ double s_red[kCamThreads / 32][27];     // 108 doubles; reused as the 33-double scratch of the fused tail
   const LmState& st = *d.st;
   if (st.done || !st.need_lin) return;
   const int a = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -608,7 +624,9 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_blocks(BaDev d) {
     if (tid < 21) d.Hcc[21 * (size_t)a + tid] = t; else d.gc[6 * (size_t)a + tid - 21] = t;
   }
   __syncthreads();
-  if (tid == 0 && !d.multi) cam_finish(d, st, a);
+  if (d.multi) return;
+  if (tid == 0) cam_finish(d, st, a);
+  if (last_cta_arrives(d.ticket, gridDim.x)) post_lin_body(d, *d.st, 0, &s_red[0][0]);
 }
 
 // Jacobi scale, gradient norm and parameter norm of one variable keyframe from its (global) H_cc, g_c
@@ -620,23 +638,37 @@ __global__ void __launch_bounds__(128) k_cam_finish(BaDev d) {
 }
 
 // strided, fixed-order sum / max of a partial array by one CTA
+// (ld.cg: the partials may have been written by other CTAs of the same launch — see last_cta_arrives)
 __device__ double part_sum(const double* p, int n, double* scratch) {
   double v = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) v += p[i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += __ldcg(p + i);
   return block_sum(v, scratch);
 }
 __device__ double part_max(const double* p, int n, double* scratch) {
   double v = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) v = fmax(v, p[i]);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v = fmax(v, __ldcg(p + i));
   return block_max(v, scratch);
+}
+// Reduce-and-decide tails run inside the producing kernel on a single GPU: every CTA publishes its partials, fences and
+// takes a ticket; the CTA that draws the last one sees all of them (threadfence reduction) and runs the tail.  One launch
+// less per stage, and the order of every sum is unchanged.
+__device__ bool last_cta_arrives(unsigned int* ticket, unsigned int n_ctas) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == n_ctas - 1);
+    if (s_last) *ticket = 0;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
 }
 
 // phase 1: reduce this rank's per-CTA partials into red[0..2] = cost, |x|^2 of the points, gradient max;
 // phase 2: add the keyframes' share and run the state machine; phase 0: both (single GPU)
-__global__ void __launch_bounds__(256) k_post_lin(BaDev d, int phase) {
-  __shared__ double scratch[33];
-  LmState& st = *d.st;
-  if (st.done || !st.need_lin) return;
+__device__ void post_lin_body(const BaDev& d, LmState& st, int phase, double* scratch) {
   if (phase != 2) {
     const double cost = part_sum(d.part + d.o_lin_cost, d.n_lin_blocks, scratch);
     const double x1 = part_sum(d.part + d.o_lin_xn2, d.n_lin_blocks, scratch);
@@ -652,6 +684,12 @@ __global__ void __launch_bounds__(256) k_post_lin(BaDev d, int phase) {
       if (!st.done && d.stop_flag && *d.stop_flag) { st.done = 1; st.termination = TERM_USER; }   // StopFlagCallback
     }
   }
+}
+__global__ void __launch_bounds__(256) k_post_lin(BaDev d, int phase) {
+  __shared__ double scratch[33];
+  LmState& st = *d.st;
+  if (st.done || !st.need_lin) return;
+  post_lin_body(d, st, phase, scratch);
 }
 
 __global__ void __launch_bounds__(kLinThreads) k_point_prep(BaDev d) {
@@ -821,6 +859,88 @@ __device__ void cam_candidate(const BaDev& d, const LmState& st, int cam) {
 // against it independently, the trailing update is a rank-6 update with one warp per row.  Back substitution by
 // one warp, then the candidate keyframe poses.
 constexpr int kPB = 6;
+// generated straight-line code (tools: see DESIGN.md §4): arrays indexed in nested unrolled loops were kept in local memory by nvcc
+__device__ __forceinline__ void factor_diag6(double* __restrict__ L, int k0, int* s_fail) {
+  double* const row0 = L + (k0 + 0) * (k0 + 0 + 1) / 2 + k0;
+  double* const row1 = L + (k0 + 1) * (k0 + 1 + 1) / 2 + k0;
+  double* const row2 = L + (k0 + 2) * (k0 + 2 + 1) / 2 + k0;
+  double* const row3 = L + (k0 + 3) * (k0 + 3 + 1) / 2 + k0;
+  double* const row4 = L + (k0 + 4) * (k0 + 4 + 1) / 2 + k0;
+  double* const row5 = L + (k0 + 5) * (k0 + 5 + 1) / 2 + k0;
+  double a00 = row0[0];
+  double a10 = row1[0], a11 = row1[1];
+  double a20 = row2[0], a21 = row2[1], a22 = row2[2];
+  double a30 = row3[0], a31 = row3[1], a32 = row3[2], a33 = row3[3];
+  double a40 = row4[0], a41 = row4[1], a42 = row4[2], a43 = row4[3], a44 = row4[4];
+  double a50 = row5[0], a51 = row5[1], a52 = row5[2], a53 = row5[3], a54 = row5[4], a55 = row5[5];
+  bool ok = true;
+  ok = ok && (a00 > 0.0) && isfinite(a00);
+  { const double inv = __drcp_rn(a00);
+    { const double t = a10 * inv; a11 -= a10 * t; a21 -= a20 * t; a31 -= a30 * t; a41 -= a40 * t; a51 -= a50 * t; }
+    { const double t = a20 * inv; a22 -= a20 * t; a32 -= a30 * t; a42 -= a40 * t; a52 -= a50 * t; }
+    { const double t = a30 * inv; a33 -= a30 * t; a43 -= a40 * t; a53 -= a50 * t; }
+    { const double t = a40 * inv; a44 -= a40 * t; a54 -= a50 * t; }
+    { const double t = a50 * inv; a55 -= a50 * t; }
+  }
+  ok = ok && (a11 > 0.0) && isfinite(a11);
+  { const double inv = __drcp_rn(a11);
+    { const double t = a21 * inv; a22 -= a21 * t; a32 -= a31 * t; a42 -= a41 * t; a52 -= a51 * t; }
+    { const double t = a31 * inv; a33 -= a31 * t; a43 -= a41 * t; a53 -= a51 * t; }
+    { const double t = a41 * inv; a44 -= a41 * t; a54 -= a51 * t; }
+    { const double t = a51 * inv; a55 -= a51 * t; }
+  }
+  ok = ok && (a22 > 0.0) && isfinite(a22);
+  { const double inv = __drcp_rn(a22);
+    { const double t = a32 * inv; a33 -= a32 * t; a43 -= a42 * t; a53 -= a52 * t; }
+    { const double t = a42 * inv; a44 -= a42 * t; a54 -= a52 * t; }
+    { const double t = a52 * inv; a55 -= a52 * t; }
+  }
+  ok = ok && (a33 > 0.0) && isfinite(a33);
+  { const double inv = __drcp_rn(a33);
+    { const double t = a43 * inv; a44 -= a43 * t; a54 -= a53 * t; }
+    { const double t = a53 * inv; a55 -= a53 * t; }
+  }
+  ok = ok && (a44 > 0.0) && isfinite(a44);
+  { const double inv = __drcp_rn(a44);
+    { const double t = a54 * inv; a55 -= a54 * t; }
+  }
+  ok = ok && (a55 > 0.0) && isfinite(a55);
+  const double rs0 = rsqrt(a00), rs1 = rsqrt(a11), rs2 = rsqrt(a22), rs3 = rsqrt(a33), rs4 = rsqrt(a44), rs5 = rsqrt(a55);
+  a10 *= rs0;
+  a20 *= rs0; a21 *= rs1;
+  a30 *= rs0; a31 *= rs1; a32 *= rs2;
+  a40 *= rs0; a41 *= rs1; a42 *= rs2; a43 *= rs3;
+  a50 *= rs0; a51 *= rs1; a52 *= rs2; a53 *= rs3; a54 *= rs4;
+  { const double d0 = rs0; row0[0] = d0;
+    const double d1 = -(a10 * d0) * rs1; row1[0] = d1;
+    const double d2 = -(a20 * d0 + a21 * d1) * rs2; row2[0] = d2;
+    const double d3 = -(a30 * d0 + a31 * d1 + a32 * d2) * rs3; row3[0] = d3;
+    const double d4 = -(a40 * d0 + a41 * d1 + a42 * d2 + a43 * d3) * rs4; row4[0] = d4;
+    const double d5 = -(a50 * d0 + a51 * d1 + a52 * d2 + a53 * d3 + a54 * d4) * rs5; row5[0] = d5;
+  }
+  { const double d1 = rs1; row1[1] = d1;
+    const double d2 = -(a21 * d1) * rs2; row2[1] = d2;
+    const double d3 = -(a31 * d1 + a32 * d2) * rs3; row3[1] = d3;
+    const double d4 = -(a41 * d1 + a42 * d2 + a43 * d3) * rs4; row4[1] = d4;
+    const double d5 = -(a51 * d1 + a52 * d2 + a53 * d3 + a54 * d4) * rs5; row5[1] = d5;
+  }
+  { const double d2 = rs2; row2[2] = d2;
+    const double d3 = -(a32 * d2) * rs3; row3[2] = d3;
+    const double d4 = -(a42 * d2 + a43 * d3) * rs4; row4[2] = d4;
+    const double d5 = -(a52 * d2 + a53 * d3 + a54 * d4) * rs5; row5[2] = d5;
+  }
+  { const double d3 = rs3; row3[3] = d3;
+    const double d4 = -(a43 * d3) * rs4; row4[3] = d4;
+    const double d5 = -(a53 * d3 + a54 * d4) * rs5; row5[3] = d5;
+  }
+  { const double d4 = rs4; row4[4] = d4;
+    const double d5 = -(a54 * d4) * rs5; row5[4] = d5;
+  }
+  { const double d5 = rs5; row5[5] = d5;
+  }
+  if (!ok) *s_fail = 1;
+}
+
 __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
   extern __shared__ __align__(16) double smem_d[];
   LmState& st = *d.st;
@@ -829,8 +949,6 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
   double* L = smem_d;                                   // rows 0..n, row i at i*(i+1)/2
   const int ps = n + 2;
   double* P = L + (size_t)(n + 1) * (n + 2) / 2;        // [kPB][ps]: the current panel's columns, by row
-  double* rdiag = P + kPB * ps;                         // 1 / L[j][j]
-  __shared__ double s_D[kPB][kPB + 1];
   __shared__ int s_fail;
   if (tid == 0) s_fail = st.solve_failed;
   for (int i = tid; i < n * (n + 1) / 2; i += kSolveThreads) L[i] = 0.0;
@@ -842,93 +960,154 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
     if (col <= row) L[row * (row + 1) / 2 + col] = d.Sblk[e];
   }
   __syncthreads();
+  // 6x6 diagonal block in registers of ONE thread (fully unrolled).  The pivot chain is the critical path of the whole
+  // solve, so it carries one reciprocal per pivot and nothing else: the elimination runs on the unscaled columns
+  // (A[r][c] -= A[r][j] A[c][j] / A[j][j]), the six rsqrt that turn them into Cholesky columns are independent and issued
+  // together at the end, and what is stored in the block's place is the INVERSE of its Cholesky factor: the panel solve
+  // and the back substitution then are short independent dot products instead of dependent substitution chains.
+#ifdef CMOS_SOLVE_TIMING
+  long long tk[8] = {0,0,0,0,0,0,0,0}; long long tprev = clock64(); const long long tstart = tprev;
+#define TK(i) { const long long tn = clock64(); tk[i] += tn - tprev; tprev = tn; }
+#else
+#define TK(i)
+#endif
+  if (tid == 0 && n > 0) factor_diag6(L, 0, &s_fail);
+  __syncthreads();
+  TK(0)
   for (int k0 = 0; k0 < n; k0 += kPB) {
-    if (tid == 0) {
-      // 6x6 diagonal block in registers of one thread (fully unrolled); one rsqrt per pivot — fp64 sqrt and
-      // divide are long software sequences and this is the critical path of the whole solve
-      double A[kPB][kPB];
-#pragma unroll
-      for (int r = 0; r < kPB; r++)
-#pragma unroll
-        for (int c = 0; c <= r; c++) A[r][c] = L[(k0 + r) * (k0 + r + 1) / 2 + k0 + c];
-      bool ok = true;
-#pragma unroll
-      for (int jj = 0; jj < kPB; jj++) {
-        const double djj = A[jj][jj];
-        if (!(djj > 0.0) || !isfinite(djj)) ok = false;
-        const double inv = rsqrt(djj);
-        A[jj][jj] = djj * inv;
-        rdiag[k0 + jj] = inv;
-#pragma unroll
-        for (int r = jj + 1; r < kPB; r++) A[r][jj] *= inv;
-#pragma unroll
-        for (int c = jj + 1; c < kPB; c++)
-#pragma unroll
-          for (int r = c; r < kPB; r++) A[r][c] -= A[r][jj] * A[c][jj];
-      }
-#pragma unroll
-      for (int r = 0; r < kPB; r++)
-#pragma unroll
-        for (int c = 0; c <= r; c++) { L[(k0 + r) * (k0 + r + 1) / 2 + k0 + c] = A[r][c]; s_D[r][c] = A[r][c]; }
-      if (!ok) s_fail = 1;
-    }
-    __syncthreads();
     if (s_fail) break;
     const int t0 = k0 + kPB;
+    // panel solve: row i of the panel times inv(L11)'
     for (int i = t0 + tid; i <= n; i += kSolveThreads) {
       double* rowp = L + i * (i + 1) / 2 + k0;
-      double x[kPB];
+      double a[kPB], x[kPB];
+#pragma unroll
+      for (int c = 0; c < kPB; c++) a[c] = rowp[c];
 #pragma unroll
       for (int c = 0; c < kPB; c++) {
-        double v = rowp[c];
-#pragma unroll
-        for (int q = 0; q < c; q++) v -= x[q] * s_D[c][q];
-        x[c] = v * rdiag[k0 + c];
-        rowp[c] = x[c];
-        P[c * ps + i] = x[c];
-      }
-    }
-    __syncthreads();
-    for (int i = t0 + warp; i <= n; i += nw) {
-      double li[kPB];
-#pragma unroll
-      for (int q = 0; q < kPB; q++) li[q] = P[q * ps + i];
-      const int cmax = i < n ? i : n - 1;
-      double* rowp = L + i * (i + 1) / 2;
-      for (int c = t0 + lane; c <= cmax; c += 32) {
+        const double* di = L + (k0 + c) * (k0 + c + 1) / 2 + k0;
         double v = 0.0;
 #pragma unroll
-        for (int q = 0; q < kPB; q++) v += li[q] * P[q * ps + c];
-        rowp[c] -= v;
+        for (int q = 0; q <= c; q++) v += a[q] * di[q];
+        x[c] = v;
+      }
+#pragma unroll
+      for (int c = 0; c < kPB; c++) { rowp[c] = x[c]; P[c * ps + i] = x[c]; }
+    }
+    TK(1)
+    __syncthreads();
+    TK(2)
+    // trailing update.  Look-ahead: warp 0 updates the NEXT diagonal block (rows t0..t0+5 lie entirely inside it) and its
+    // lane 0 factors it at once, while the other warps update the rows below — the next round starts with its panel solve.
+    if (warp == 0) {
+      if (t0 < n) {
+        if (lane < kPB * (kPB + 1) / 2) {
+          int r = 0, c = lane;
+          while (c > r) { c -= r + 1; r++; }
+          const int i = t0 + r, cc = t0 + c;
+          double v = 0.0;
+#pragma unroll
+          for (int q = 0; q < kPB; q++) v += P[q * ps + i] * P[q * ps + cc];
+          L[i * (i + 1) / 2 + cc] -= v;
+        }
+        __syncwarp();
+        if (lane == 0) factor_diag6(L, t0, &s_fail);
+      }
+    } else {
+#if CMOS_SOLVE_TILE
+      // Register-tiled rank-6 update: a warp takes 4 consecutive rows, its lanes 4 column groups (c, c+32, c+64, c+96) —
+      // 16 accumulators per thread.  The update is bound by shared-memory wavefronts, not by fp64 (one SM, 64 fp64 lanes);
+      // the tile reads each panel value once per 4 rows / 4 columns instead of once per FMA.
+      const int first = t0 + kPB;
+      for (int i0 = first + 4 * (warp - 1); i0 <= n; i0 += 4 * (nw - 1)) {
+        const int top = min(i0 + 3, n);                       // last row of the tile
+        const int cend = top < n ? top : n - 1;               // widest row's last column
+        for (int cb = t0 + lane; cb <= cend; cb += 128) {
+          const int nu = min(4, (cend - (cb - lane)) / 32 + 1);
+          double v[4][4];
+#pragma unroll
+          for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[r][u] = 0.0;
+#pragma unroll
+          for (int q = 0; q < kPB; q++) {
+            const double* pq = P + q * ps;
+            double li[4], pc[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) li[r] = pq[min(i0 + r, n)];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+              if (!CMOS_SOLVE_NU || u < nu) {                                     // warp-uniform: column groups past the tile's widest row
+                pc[u] = pq[min(cb + 32 * u, n)];
+#pragma unroll
+                for (int r = 0; r < 4; r++) v[r][u] += li[r] * pc[u];
+              }
+          }
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            const int i = i0 + r;
+            if (i > n) break;
+            const int cmax = i < n ? i : n - 1;
+            double* rowp = L + i * (i + 1) / 2;
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int c = cb + 32 * u; if (c <= cmax) rowp[c] -= v[r][u]; }
+          }
+        }
       }
     }
+#else
+      for (int i = t0 + kPB + warp - 1; i <= n; i += nw - 1) {
+        double li[kPB];
+#pragma unroll
+        for (int q = 0; q < kPB; q++) li[q] = P[q * ps + i];
+        const int cmax = i < n ? i : n - 1;
+        double* rowp = L + i * (i + 1) / 2;
+        for (int cb = t0 + lane; cb <= cmax; cb += 128) {
+          double v[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int q = 0; q < kPB; q++) {
+            const double* pq = P + q * ps;
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int c = cb + 32 * u; if (c <= cmax) v[u] += li[q] * pq[c]; }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) { const int c = cb + 32 * u; if (c <= cmax) rowp[c] -= v[u]; }
+        }
+      }
+    }
+#endif
+    TK(3)
     __syncthreads();
+    TK(4)
   }
   __syncthreads();
   if (warp == 0) {
     double* y = L + n * (n + 1) / 2;      // forward-substituted rhs
     if (!s_fail) {
-      // blocked back substitution L' x = y: lane 0 solves the 6x6 triangle, the warp updates the rows above
+      // blocked back substitution L' x = y: x_block = inv(L11)' y_block (lanes 0..5, one dot product each), then the warp
+      // updates the rows above
       for (int k0 = n - kPB; k0 >= 0; k0 -= kPB) {
+        double xr = 0.0;
+        if (lane < kPB) {
+#pragma unroll
+          for (int q = 0; q < kPB; q++)
+            if (q >= lane) xr += L[(k0 + q) * (k0 + q + 1) / 2 + k0 + lane] * y[k0 + q];
+        }
+        __syncwarp();
+        if (lane < kPB) y[k0 + lane] = xr;
         double x[kPB];
-        if (lane == 0) {
 #pragma unroll
-          for (int r = kPB - 1; r >= 0; r--) {
-            double v = y[k0 + r];
+        for (int r = 0; r < kPB; r++) x[r] = __shfl_sync(0xffffffffu, xr, r);
+        for (int kb = lane; kb < k0; kb += 128) {
+          double v[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int q = r + 1; q < kPB; q++) v -= L[(k0 + q) * (k0 + q + 1) / 2 + k0 + r] * x[q];
-            x[r] = v * rdiag[k0 + r];
+          for (int r = 0; r < kPB; r++) {
+            const double* lr = L + (k0 + r) * (k0 + r + 1) / 2;
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int k = kb + 32 * u; if (k < k0) v[u] += lr[k] * x[r]; }
           }
 #pragma unroll
-          for (int r = 0; r < kPB; r++) y[k0 + r] = x[r];
-        }
-#pragma unroll
-        for (int r = 0; r < kPB; r++) x[r] = __shfl_sync(0xffffffffu, x[r], 0);
-        for (int k = lane; k < k0; k += 32) {
-          double v = y[k];
-#pragma unroll
-          for (int r = 0; r < kPB; r++) v -= L[(k0 + r) * (k0 + r + 1) / 2 + k] * x[r];
-          y[k] = v;
+          for (int u = 0; u < 4; u++) { const int k = kb + 32 * u; if (k < k0) y[k] -= v[u]; }
         }
         __syncwarp();
       }
@@ -943,9 +1122,15 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
     if (lane == 0 && bad) s_fail = 1;
   }
   __syncthreads();
+  TK(5)
   if (tid == 0) st.solve_failed = s_fail;
   if (!s_fail)
     for (int cam = tid; cam < d.K; cam += kSolveThreads) cam_candidate(d, st, cam);
+  TK(6)
+#ifdef CMOS_SOLVE_TIMING
+  if ((tid == 0 || tid == 32 || tid == 1023) && st.iteration == 1)
+    printf("solve_small tid %d n %d: setup+diag0 %lld | P2 %lld bar %lld P3 %lld bar %lld | backsub %lld cand %lld | total %lld\n", tid, n, tk[0], tk[1], tk[2], tk[3], tk[4], tk[5], tk[6], clock64() - tstart);
+#endif
 }
 
 __global__ void __launch_bounds__(kLinThreads) k_backsub(BaDev d) {
@@ -1007,14 +1192,13 @@ __global__ void __launch_bounds__(kLinThreads) k_backsub(BaDev d) {
     d.part[d.o_bs_mcc + blockIdx.x] = mcc;
     d.part[d.o_bs_sn2 + blockIdx.x] = sn2;
   }
+  if (d.multi) return;
+  if (last_cta_arrives(d.ticket + 1, gridDim.x)) decide_body(d, *d.st, 0, scratch);
 }
 
 // phase 1: red[3..5] = candidate cost, model cost change, |step|^2 of this rank's points; phase 2: add the
 // keyframes' share and decide; phase 0: both
-__global__ void __launch_bounds__(256) k_decide(BaDev d, int phase) {
-  __shared__ double scratch[33];
-  LmState& st = *d.st;
-  if (st.done) return;
+__device__ void decide_body(const BaDev& d, LmState& st, int phase, double* scratch) {
   if (phase != 2) {
     const double cost = part_sum(d.part + d.o_bs_cost, d.n_lin_blocks, scratch);
     const double mcc = part_sum(d.part + d.o_bs_mcc, d.n_lin_blocks, scratch);
@@ -1035,6 +1219,12 @@ __global__ void __launch_bounds__(256) k_decide(BaDev d, int phase) {
       if (!st.done && d.stop_flag && *d.stop_flag) { st.done = 1; st.termination = TERM_USER; }
     }
   }
+}
+__global__ void __launch_bounds__(256) k_decide(BaDev d, int phase) {
+  __shared__ double scratch[33];
+  LmState& st = *d.st;
+  if (st.done) return;
+  decide_body(d, st, phase, scratch);
 }
 
 // CheckOutlier (:227-241) + the z <= 0 test (:558-564) over the observations of local keyframes; also sets the
@@ -1734,8 +1924,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
     if (d.Kv > 0) k_cam_blocks<<<d.Kv, kCamThreads, 0, st>>>(d);
     h->launches += 2;
     if (!multi) {
-      k_post_lin<<<1, 256, 0, st>>>(d, 0);
-      h->launches++;
+      if (d.Kv == 0) { k_post_lin<<<1, 256, 0, st>>>(d, 0); h->launches++; }   // otherwise the last CTA of k_cam_blocks ran it
       return CMOS_OK;
     }
     int rc;
@@ -1800,8 +1989,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
     k_backsub<<<nlb, kLinThreads, 0, st>>>(d);
     h->launches++;
     if (!multi) {
-      k_decide<<<1, 256, 0, st>>>(d, 0);
-      h->launches++;
+      // the last CTA of k_backsub decides
     } else {
       k_decide<<<1, 256, 0, st>>>(d, 1);
       if ((rc = allreduce(d.red + 3, 4, kNcclSum))) return rc;                    // candidate cost, model change, |step|^2, failure
@@ -1856,7 +2044,7 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
        alloc(&h->d_erase, N);
   ok = ok && alloc(&d.Jc, 12 * N) && alloc(&d.Jp, 6 * N) && alloc(&d.res, 2 * N) && alloc(&d.Hpp, 6 * M) && alloc(&d.gp, 3 * M) &&
        alloc(&d.Hinv, 6 * M) && alloc(&d.tp, 3 * M) && alloc(&d.scale_p, 3 * M) && alloc(&h->d_HG, 27 * K) &&
-       alloc(&h->d_var_cam, K) && alloc(&h->d_red, 8) && alloc(&h->d_Sblk, h->cap_blocks * 36 + 6 * K + 8) &&
+       alloc(&h->d_var_cam, K) && alloc(&h->d_red, 16) && alloc(&h->d_Sblk, h->cap_blocks * 36 + 6 * K + 8) &&
        alloc(&d.scale_c, 6 * K) && alloc(&d.S, h->cap_S) &&
        alloc(&d.yc, 6 * K + 8) && alloc(&d.part, 6 * nlb + 4 * K + 16) && alloc(&d.st, 1) &&
        alloc(&h->d_Linv, ((6 * K + kNB - 1) / kNB) * kNB * kNB) && alloc(&h->d_pan_tiles, h->cap_pan_tiles) && alloc(&h->d_band_blk, (size_t)K * (kBandMaxW + 1)) && alloc(&h->d_trace, 2 * (size_t)h->trace_rows * kTraceCols) &&
@@ -1876,6 +2064,7 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
   cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
   cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
   cudaFuncSetAttribute(k_syrk_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
+  CMOS_CUDA_OK(cudaMemset(h->d_red, 0, 16 * sizeof(double)));      // incl. the arrival tickets
   CMOS_CUDA_OK(cudaGetLastError());
   *out = h;
   return CMOS_OK;
@@ -2138,6 +2327,7 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
   d.cam_obs = h->d_cam_obs; d.blk_a = h->d_blk_a; d.blk_b = h->d_blk_b; d.blk_start = h->d_blk_start;
   d.pair_a = h->d_pair_a; d.pair_b = h->d_pair_b;
   d.var_cam = h->d_var_cam; d.red = h->d_red;
+  d.ticket = (unsigned int*)(h->d_red + 8);
   d.Hcc = h->d_HG; d.gc = h->d_HG + 21 * (size_t)Kv;
   d.Sblk = h->d_Sblk; d.rhs = h->d_Sblk + (size_t)nb * 36;
   d.multi = h->n_ranks > 1; d.is_root = h->rank == 0;
