@@ -1294,29 +1294,32 @@ __global__ void __launch_bounds__(256) k_potrf_diag(BaDev d, int k0, int kb, dou
   LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
   const int n = d.nc, tid = threadIdx.x;
+#ifdef CMOS_SOLVE_TIMING
+  long long tq[6]; tq[0] = clock64();
+#define TQ(i) tq[i] = clock64();
+#else
+#define TQ(i)
+#endif
   for (int idx = tid; idx < kb * kb; idx += 256) {
     const int i = idx / kb, k = idx - i * kb;
     A[i][k] = k <= i ? d.S[(size_t)(k0 + i) * n + k0 + k] : 0.0;
     Li[i][k] = 0.0;
   }
   __syncthreads();
+  TQ(1)
   bool fail = false;
+  const int tx = tid & 15, ty = tid >> 4;       // 16 x 16 threads over the trailing block: rows by ty, columns by tx
   for (int j = 0; j < kb; j++) {
     const double djj = A[j][j];                 // final: every update of column j happened before the last barrier
     if (!(djj > 0.0) || !isfinite(djj)) { fail = true; break; }    // uniform over the CTA
-    const double inv = 1.0 / djj;
-    const int m = kb - j - 1;
-    // lower triangle of the trailing m x m block: element e -> (ii, kk) with kk <= ii
-    for (int e = tid; e < m * (m + 1) / 2; e += 256) {
-      int ii = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-      while ((ii + 1) * (ii + 2) / 2 <= e) ii++;
-      while (ii * (ii + 1) / 2 > e) ii--;
-      const int kk = e - ii * (ii + 1) / 2;
-      const int i = j + 1 + ii, k = j + 1 + kk;
-      A[i][k] -= A[i][j] * A[k][j] * inv;
+    const double inv = __drcp_rn(djj);
+    for (int i = j + 1 + ty; i < kb; i += 16) {
+      const double aij = A[i][j] * inv;
+      for (int k = j + 1 + tx; k <= i; k += 16) A[i][k] -= aij * A[k][j];
     }
     __syncthreads();
   }
+  TQ(2)
   if (fail) { if (tid == 0) st.solve_failed = 1; return; }
   for (int idx = tid; idx < kb * kb; idx += 256) {     // L[i][j] = A[i][j] / sqrt(A[j][j]); the diagonal is only read here
     const int i = idx / kb, j = idx - i * kb;
@@ -1325,21 +1328,32 @@ __global__ void __launch_bounds__(256) k_potrf_diag(BaDev d, int k0, int kb, dou
   __syncthreads();
   if (tid < kb) A[tid][tid] = sqrt(A[tid][tid]);
   __syncthreads();
-  // inverse of the lower-triangular factor: column c by forward substitution, one thread per column
+  TQ(3)
+  // inverse of the lower-triangular factor: column c by forward substitution, one thread per column, the dot product of
+  // every row in four independent partial sums
   if (tid < kb) {
     const int c = tid;
     for (int i = c; i < kb; i++) {
-      double s = (i == c) ? 1.0 : 0.0;
-      for (int k = c; k < i; k++) s -= A[i][k] * Li[k][c];
-      Li[i][c] = s / A[i][i];
+      double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int k = c;
+      for (; k + 3 < i; k += 4) {
+        s0 -= A[i][k] * Li[k][c]; s1 -= A[i][k + 1] * Li[k + 1][c]; s2 -= A[i][k + 2] * Li[k + 2][c]; s3 -= A[i][k + 3] * Li[k + 3][c];
+      }
+      for (; k < i; k++) s0 -= A[i][k] * Li[k][c];
+      Li[i][c] = ((s0 + s1) + (s2 + s3)) / A[i][i];
     }
   }
   __syncthreads();
+  TQ(4)
   for (int idx = tid; idx < kb * kb; idx += 256) {
     const int i = idx / kb, k = idx - i * kb;
     if (k <= i) d.S[(size_t)(k0 + i) * n + k0 + k] = A[i][k];
     Linv[(size_t)(k0 / kNB) * kNB * kNB + i * kNB + k] = Li[i][k];
   }
+  TQ(5)
+#ifdef CMOS_SOLVE_TIMING
+  if (tid == 0 && k0 == 640 && st.iteration == 1) printf("potrf: load %lld factor %lld scale %lld inverse %lld store %lld\n", tq[1]-tq[0], tq[2]-tq[1], tq[3]-tq[2], tq[4]-tq[3], tq[5]-tq[4]);
+#endif
 }
 
 // panel solve: rows i > k0+kb (and the rhs row): L21[i][:] = A21[i][:] * inv(L11)'  -> L21[i][c] = sum_k A21[i][k] Linv[c][k]
@@ -1443,6 +1457,61 @@ __global__ void __launch_bounds__(256) k_backsolve_panel(BaDev d, int k0, int kb
     double s = 0.0;
     for (int r = 0; r < kb; r++) s += d.S[(size_t)(k0 + r) * n + c] * xk[r];
     d.rhs[c] -= s;
+  }
+}
+
+// The whole back substitution in ONE launch (one CTA, the forward-substituted rhs in shared memory): per panel, from the last,
+// x_k = inv(L_kk)' y_k by 16 threads per unknown, then y_c -= L_kc' x_k for the columns c in the panel's row envelope by
+// 16 row groups x 64 columns with a fixed-order reduction.  Replaces one k_backsolve_panel launch per panel.
+constexpr int kBackAllMaxN = 12288;
+inline size_t back_all_smem(int n) { return ((size_t)n + kNB + 16 * 64) * sizeof(double); }
+__global__ void __launch_bounds__(1024) k_backsolve_all(BaDev d, const double* __restrict__ Linv, const int* __restrict__ first_col) {
+  extern __shared__ double dyn_smem[];
+  double* y = dyn_smem;                       // [n]
+  double* xk = y + d.nc;                      // [kNB]
+  double* red = xk + kNB;                     // [16][64]
+  LmState& st = *d.st;
+  if (st.done || st.solve_failed) return;
+  const int n = d.nc, tid = threadIdx.x;
+  for (int i = tid; i < n; i += 1024) y[i] = d.rhs[i];
+  __syncthreads();
+  for (int k0 = ((n - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {
+    const int kb = min(kNB, n - k0);
+    const double* Lp = Linv + (size_t)(k0 / kNB) * kNB * kNB;
+    {
+      const int t = tid >> 4, part = tid & 15;          // unknown t of the panel, 16 partial sums over r
+      double s = 0.0;
+      if (t < kb)
+        for (int r = t + part; r < kb; r += 16) s += Lp[r * kNB + t] * y[k0 + r];
+#pragma unroll
+      for (int o = 8; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (part == 0 && t < kb) xk[t] = s;
+    }
+    __syncthreads();
+    if (tid < kb) { y[k0 + tid] = xk[tid]; d.yc[k0 + tid] = xk[tid]; }
+    const int c0 = min(first_col[k0 / kNB], k0);
+    const int cl = tid & 63, rg = tid >> 6;             // column lane, row group (4 rows each)
+    for (int cb = c0; cb < k0; cb += 64) {
+      const int c = cb + cl;
+      double s = 0.0;
+      if (c < k0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int r = 4 * rg + q;
+          if (r < kb) s += d.S[(size_t)(k0 + r) * n + c] * xk[r];
+        }
+      }
+      red[rg * 64 + cl] = s;
+      __syncthreads();
+      if (tid < 64 && cb + tid < k0) {
+        double t = 0.0;
+#pragma unroll
+        for (int g = 0; g < 16; g++) t += red[g * 64 + tid];
+        y[cb + tid] -= t;
+      }
+      __syncthreads();
+    }
+    __syncthreads();
   }
 }
 
@@ -1834,7 +1903,7 @@ struct cmos_ba {
     double *x0 = nullptr, *x1 = nullptr, *x_init = nullptr, *Scw = nullptr, *Snc = nullptr, *lie_out = nullptr, *Tiw = nullptr;
     uint8_t *flags = nullptr, *kind = nullptr;
     int *var = nullptr, *var_kf = nullptr, *ej = nullptr, *ei = nullptr, *inc_start = nullptr, *inc_edge = nullptr, *inc_other = nullptr,
-        *inc_sign = nullptr, *tiles = nullptr, *ref = nullptr;
+        *inc_sign = nullptr, *tiles = nullptr, *ref = nullptr, *first_col = nullptr;
     Sim3D *meas = nullptr, *Swc = nullptr;
     double *r = nullptr, *J = nullptr, *A = nullptr, *v = nullptr, *Hd = nullptr, *g = nullptr, *scale = nullptr, *delta = nullptr,
            *S = nullptr, *rhs = nullptr, *yc = nullptr, *Linv = nullptr, *pe = nullptr, *pk = nullptr, *Xw = nullptr, *Xo = nullptr;
@@ -1843,7 +1912,7 @@ struct cmos_ba {
     void release() {
       for (void* b : {(void*)x0, (void*)x1, (void*)x_init, (void*)Scw, (void*)Snc, (void*)lie_out, (void*)Tiw, (void*)flags, (void*)kind,
                       (void*)var, (void*)var_kf, (void*)ej, (void*)ei, (void*)inc_start, (void*)inc_edge, (void*)inc_other, (void*)inc_sign,
-                      (void*)tiles, (void*)ref, (void*)meas, (void*)Swc, (void*)r, (void*)J, (void*)A, (void*)v, (void*)Hd, (void*)g,
+                      (void*)tiles, (void*)first_col, (void*)ref, (void*)meas, (void*)Swc, (void*)r, (void*)J, (void*)A, (void*)v, (void*)Hd, (void*)g,
                       (void*)scale, (void*)delta, (void*)S, (void*)rhs, (void*)yc, (void*)Linv, (void*)pe, (void*)pk, (void*)Xw, (void*)Xo,
                       (void*)st})
         if (b) cudaFree(b);
@@ -1852,6 +1921,7 @@ struct cmos_ba {
     }
   } eg;
   int* d_pan_tiles = nullptr;               // active row tiles of every panel of the blocked factorisation
+  int* d_pan_first = nullptr;               // [n_panels] first column of every panel's row envelope (k_backsolve_all)
   std::vector<int> pan_start, pan_first_col; // [n_panels + 1], [n_panels]
   size_t cap_pan_tiles = 0;
   int band_W = 0;                            // > 0: banded reduced system, solved by k_solve_band
@@ -1976,12 +2046,16 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
           }
           h->launches++;
         }
-        for (int k0 = ((n - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {
-          const int kb = std::min(kNB, n - k0);
-          const int c0 = std::min(h->pan_first_col[k0 / kNB], k0);
-          k_backsolve_panel<<<std::max(1, (k0 - c0 + 255) / 256), 256, 0, st>>>(d, k0, kb, h->d_Linv, c0);
+        if (n <= kBackAllMaxN) {
+          k_backsolve_all<<<1, 1024, back_all_smem(n), st>>>(d, h->d_Linv, h->d_pan_first);
           h->launches++;
-        }
+        } else
+          for (int k0 = ((n - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {
+            const int kb = std::min(kNB, n - k0);
+            const int c0 = std::min(h->pan_first_col[k0 / kNB], k0);
+            k_backsolve_panel<<<std::max(1, (k0 - c0 + 255) / 256), 256, 0, st>>>(d, k0, kb, h->d_Linv, c0);
+            h->launches++;
+          }
         k_cam_candidates<<<(d.K + 255) / 256, 256, 0, st>>>(d);
         h->launches++;
       }
@@ -2047,7 +2121,7 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
        alloc(&h->d_var_cam, K) && alloc(&h->d_red, 16) && alloc(&h->d_Sblk, h->cap_blocks * 36 + 6 * K + 8) &&
        alloc(&d.scale_c, 6 * K) && alloc(&d.S, h->cap_S) &&
        alloc(&d.yc, 6 * K + 8) && alloc(&d.part, 6 * nlb + 4 * K + 16) && alloc(&d.st, 1) &&
-       alloc(&h->d_Linv, ((6 * K + kNB - 1) / kNB) * kNB * kNB) && alloc(&h->d_pan_tiles, h->cap_pan_tiles) && alloc(&h->d_band_blk, (size_t)K * (kBandMaxW + 1)) && alloc(&h->d_trace, 2 * (size_t)h->trace_rows * kTraceCols) &&
+       alloc(&h->d_Linv, ((6 * K + kNB - 1) / kNB) * kNB * kNB) && alloc(&h->d_pan_tiles, h->cap_pan_tiles) && alloc(&h->d_pan_first, (6 * K + kNB) / kNB + 2) && alloc(&h->d_band_blk, (size_t)K * (kBandMaxW + 1)) && alloc(&h->d_trace, 2 * (size_t)h->trace_rows * kTraceCols) &&
        alloc(&h->d_summaries, 2);
   const size_t PB = std::max(params->max_pose_batch, 1), PC = std::max(params->max_pose_corr, 1);
   ok = ok && alloc(&h->dp_pose, 7 * PB) && alloc(&h->dp_xw, 3 * PB * PC) && alloc(&h->dp_uv, 2 * PB * PC) &&
@@ -2064,6 +2138,7 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
   cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
   cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
   cudaFuncSetAttribute(k_syrk_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
+  cudaFuncSetAttribute(k_backsolve_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)back_all_smem(kBackAllMaxN));
   CMOS_CUDA_OK(cudaMemset(h->d_red, 0, 16 * sizeof(double)));      // incl. the arrival tickets
   CMOS_CUDA_OK(cudaGetLastError());
   *out = h;
@@ -2078,7 +2153,7 @@ int cmos_ba_destroy(cmos_ba_t h) {
                   h->d_o_cam, h->d_o_cv, h->d_o_pt, h->d_pt_start, h->d_cam_start, h->d_cam_obs, h->d_blk_a, h->d_blk_b,
                   h->d_blk_start, h->d_pair_a, h->d_pair_b, h->d_perm, h->d_o_uv, h->d_o_w, h->d_o_mode, h->d_cam_flags,
                   h->d_erase, d.Jc, d.Jp, d.res, d.Hpp, d.gp, d.Hinv, d.tp, d.scale_p, h->d_HG, h->d_var_cam, h->d_red, h->d_Sblk, d.scale_c, d.S,
-                  d.yc, d.part, d.st, h->d_Linv, h->d_pan_tiles, h->d_band_blk, h->d_trace, h->d_summaries, h->dp_pose, h->dp_xw, h->dp_uv, h->dp_w,
+                  d.yc, d.part, d.st, h->d_Linv, h->d_pan_tiles, h->d_pan_first, h->d_band_blk, h->d_trace, h->d_summaries, h->dp_pose, h->dp_xw, h->dp_uv, h->dp_w,
                   h->dp_n, h->dp_inl, h->dp_out, h->dp_sum, h->dp_trace};
   for (void* b : bufs)
     if (b) cudaFree(b);
@@ -2279,6 +2354,7 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
     CMOS_REQUIRE(tiles.size() <= h->cap_pan_tiles, "panel tile list %zu exceeds capacity %zu", tiles.size(), h->cap_pan_tiles);
     if (!tiles.empty())
       CMOS_CUDA_OK(cudaMemcpyAsync(h->d_pan_tiles, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CMOS_CUDA_OK(cudaMemcpyAsync(h->d_pan_first, h->pan_first_col.data(), h->pan_first_col.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));
   }
   CMOS_REQUIRE((size_t)nb <= h->cap_blocks, "%d reduced-system blocks exceed the handle's capacity %zu", nb, h->cap_blocks);
@@ -2625,7 +2701,7 @@ int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Sc
     bool ok = alloc(&g.x0, 7 * ck) && alloc(&g.x1, 7 * ck) && alloc(&g.x_init, 7 * ck) && alloc(&g.Scw, 13 * ck) && alloc(&g.Snc, 13 * ck) &&
               alloc(&g.lie_out, 7 * ck) && alloc(&g.Tiw, 16 * ck) && alloc(&g.flags, ck) && alloc(&g.kind, ce) && alloc(&g.var, ck) &&
               alloc(&g.var_kf, ck) && alloc(&g.ej, ce) && alloc(&g.ei, ce) && alloc(&g.inc_start, ck + 1) && alloc(&g.inc_edge, 2 * ce) &&
-              alloc(&g.inc_other, 2 * ce) && alloc(&g.inc_sign, 2 * ce) && alloc(&g.tiles, ct) && alloc(&g.ref, cp) && alloc(&g.meas, ce) &&
+              alloc(&g.inc_other, 2 * ce) && alloc(&g.inc_sign, 2 * ce) && alloc(&g.tiles, ct) && alloc(&g.first_col, cpan + 1) && alloc(&g.ref, cp) && alloc(&g.meas, ce) &&
               alloc(&g.Swc, ck) && alloc(&g.r, 7 * ce) && alloc(&g.J, 49 * ce) && alloc(&g.A, 49 * ce) && alloc(&g.v, 7 * ce) &&
               alloc(&g.Hd, 49 * ck) && alloc(&g.g, cn) && alloc(&g.scale, cn) && alloc(&g.delta, cn) && alloc(&g.S, cn * cn) &&
               alloc(&g.rhs, cn) && alloc(&g.yc, cn) && alloc(&g.Linv, cpan * kNB * kNB) && alloc(&g.pe, 3 * ce) && alloc(&g.pk, 3 * ck) &&
@@ -2652,6 +2728,7 @@ int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Sc
   CMOS_CUDA_OK(up(g.inc_other, inc_other.data(), (size_t)n_inc * sizeof(int)));
   CMOS_CUDA_OK(up(g.inc_sign, inc_sign.data(), (size_t)n_inc * sizeof(int)));
   CMOS_CUDA_OK(up(g.tiles, tiles.data(), tiles.size() * sizeof(int)));
+  CMOS_CUDA_OK(up(g.first_col, pan_first_col.data(), pan_first_col.size() * sizeof(int)));
   CMOS_CUDA_OK(up(g.Xw, Xw, (size_t)n_points * 3 * sizeof(double)));
   CMOS_CUDA_OK(up(g.ref, ref_kf, (size_t)n_points * sizeof(int)));
   EgDev d{};
@@ -2694,12 +2771,16 @@ int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Sc
       }
       h->launches++;
     }
-    for (int k0 = ((n - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {
-      const int kb = std::min(kNB, n - k0);
-      const int c0 = std::min(pan_first_col[k0 / kNB], k0);
-      k_backsolve_panel<<<std::max(1, (k0 - c0 + 255) / 256), 256, 0, st>>>(dv, k0, kb, g.Linv, c0);
+    if (n <= kBackAllMaxN) {
+      k_backsolve_all<<<1, 1024, back_all_smem(n), st>>>(dv, g.Linv, g.first_col);
       h->launches++;
-    }
+    } else
+      for (int k0 = ((n - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {
+        const int kb = std::min(kNB, n - k0);
+        const int c0 = std::min(pan_first_col[k0 / kNB], k0);
+        k_backsolve_panel<<<std::max(1, (k0 - c0 + 255) / 256), 256, 0, st>>>(dv, k0, kb, g.Linv, c0);
+        h->launches++;
+      }
     k_eg_step<<<gk, 128, 0, st>>>(d);
     k_eg_eval<<<ge, 64, 0, st>>>(d);
     k_eg_decide<<<1, 256, 0, st>>>(d, g.done_host);
