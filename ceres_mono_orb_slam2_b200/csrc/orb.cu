@@ -778,6 +778,9 @@ struct cmos_orb {
   cmos_orb_params p{};
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;            // the blur runs here, beside the quadtree (both only need what FAST / the pyramid left)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap = true;                    // CMOS_ORB_NO_OVERLAP=1 keeps every kernel on one stream
   std::vector<float> sf, inv_sf, sigma2, inv_sigma2;
   std::vector<int> quota;
   int umax[16];
@@ -985,11 +988,22 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
     launches++;
   }
   h->timer.mark(st);   // stage 1: FAST
+  // The quadtree (one CTA per frame and level, sequential rounds, 60 us of latency) and the blur (every SM busy, reads only
+  // the pyramid) are independent: the blur goes to a side stream and the two overlap.  In profiling mode stage 2 then is the quadtree with the
+  // blur running beside it and stage 3 the part of the blur that was not hidden.
+  const bool fork = h->overlap && h->side && h->ev_fork && h->ev_join;
+  if (fork) {
+    CMOS_CUDA_OK(cudaEventRecord(h->ev_fork, st));
+    CMOS_CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    k_blur<<<dim3(h->n_tiles, n_frames), 256, 0, h->side>>>(g, h->d_tiles, h->d_pyr, h->d_blur);
+    CMOS_CUDA_OK(cudaEventRecord(h->ev_join, h->side));
+  }
   k_octree<<<dim3(g.nlevels, n_frames), kOctThreads, oct_smem_bytes(h->oct_maxn), st>>>(
       g, h->d_cand, h->d_pnode, h->d_cand_count, h->d_stage, h->d_level_counts, h->oct_maxn);
   launches++;
   h->timer.mark(st);   // stage 2: quadtree
-  k_blur<<<dim3(h->n_tiles, n_frames), 256, 0, st>>>(g, h->d_tiles, h->d_pyr, h->d_blur);
+  if (fork) CMOS_CUDA_OK(cudaStreamWaitEvent(st, h->ev_join, 0));
+  else k_blur<<<dim3(h->n_tiles, n_frames), 256, 0, st>>>(g, h->d_tiles, h->d_pyr, h->d_blur);
   launches++;
   h->timer.mark(st);   // stage 3: blur
   k_describe<<<dim3((g.kp_cap + kDescThreads / 32 - 1) / (kDescThreads / 32), n_frames), kDescThreads, 0, st>>>(
@@ -1073,6 +1087,10 @@ int cmos_orb_create(const cmos_orb_params* params, cmos_orb_t* out) {
   h->images_cap = (size_t)params->max_width * params->max_height * B;
   cudaError_t err = cudaSuccess;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) err = cudaErrorUnknown;
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) err = cudaErrorUnknown;
+  if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) err = cudaErrorUnknown;
+  if (cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) err = cudaErrorUnknown;
+  { const char* e = std::getenv("CMOS_ORB_NO_OVERLAP"); h->overlap = !(e && e[0] == '1'); }
   h->d_images = dev_alloc<uint8_t>(h->images_cap, &err);
   h->d_pyr = dev_alloc<uint8_t>(h->cap_frame_bytes * B, &err);
   h->d_blur = dev_alloc<uint8_t>(h->cap_frame_bytes * B, &err);
@@ -1113,6 +1131,9 @@ int cmos_orb_destroy(cmos_orb_t h) {
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (h->h_overflow) cudaFreeHost(h->h_overflow);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->stream) cudaStreamDestroy(h->stream);
   h->timer.destroy();
   delete h;
