@@ -1287,10 +1287,13 @@ __global__ void __launch_bounds__(256) k_scatter_S(BaDev d) {
 // factor the kb x kb diagonal block at (k0,k0) in place and store inv(L11) (lower) into Linv[panel].
 // Right-looking on the UNSCALED columns — A[i][k] -= A[i][j] A[k][j] / A[j][j] needs one barrier per column and no
 // square root on the critical path; column j is scaled by rsqrt(A[j][j]) once, at the end.
-__global__ void __launch_bounds__(256) k_potrf_diag(BaDev d, int k0, int kb, double* Linv) {
+constexpr int kPotrfThreads = 1024;
+__global__ void __launch_bounds__(kPotrfThreads) k_potrf_diag(BaDev d, int k0, int kb, double* Linv) {
   extern __shared__ double dyn_smem[];
   double (*A)[kNB + 1] = (double (*)[kNB + 1])dyn_smem;
   double (*Li)[kNB + 1] = (double (*)[kNB + 1])(dyn_smem + kNB * (kNB + 1));
+  __shared__ double s_inv[kNB];                 // 1 / pivot (unscaled columns), then 1 / L[i][i]
+  __shared__ int s_bad;
   LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
   const int n = d.nc, tid = threadIdx.x;
@@ -1300,52 +1303,70 @@ __global__ void __launch_bounds__(256) k_potrf_diag(BaDev d, int k0, int kb, dou
 #else
 #define TQ(i)
 #endif
-  for (int idx = tid; idx < kb * kb; idx += 256) {
-    const int i = idx / kb, k = idx - i * kb;
-    A[i][k] = k <= i ? d.S[(size_t)(k0 + i) * n + k0 + k] : 0.0;
+  for (int idx = tid; idx < kNB * kNB; idx += kPotrfThreads) {
+    const int i = idx / kNB, k = idx - i * kNB;
+    A[i][k] = (k <= i && i < kb) ? d.S[(size_t)(k0 + i) * n + k0 + k] : 0.0;
     Li[i][k] = 0.0;
+  }
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  if (tid == 0) {
+    const double d0 = A[0][0];
+    if (!(d0 > 0.0) || !isfinite(d0)) s_bad = 1;
+    s_inv[0] = __drcp_rn(d0);
   }
   __syncthreads();
   TQ(1)
-  bool fail = false;
-  const int tx = tid & 15, ty = tid >> 4;       // 16 x 16 threads over the trailing block: rows by ty, columns by tx
+  // Right-looking on the unscaled columns, 32 x 32 threads over the trailing block (rows by ty, columns by tx).  The thread
+  // that owns the next pivot updates it first and takes its reciprocal at once, so the reciprocal is off the other
+  // threads' path: one barrier per column.
+  const int tx = tid & 31, ty = tid >> 5;
   for (int j = 0; j < kb; j++) {
-    const double djj = A[j][j];                 // final: every update of column j happened before the last barrier
-    if (!(djj > 0.0) || !isfinite(djj)) { fail = true; break; }    // uniform over the CTA
-    const double inv = __drcp_rn(djj);
-    for (int i = j + 1 + ty; i < kb; i += 16) {
+    if (s_bad) break;                            // uniform: written before the last barrier
+    const double inv = s_inv[j];
+    for (int i = j + 1 + ty; i < kb; i += 32) {
       const double aij = A[i][j] * inv;
-      for (int k = j + 1 + tx; k <= i; k += 16) A[i][k] -= aij * A[k][j];
+      for (int k = j + 1 + tx; k <= i; k += 32) {
+        const double v = A[i][k] - aij * A[k][j];
+        A[i][k] = v;
+        if (i == j + 1 && k == j + 1) {          // the next pivot is final now
+          if (!(v > 0.0) || !isfinite(v)) s_bad = 1;
+          s_inv[j + 1] = __drcp_rn(v);
+        }
+      }
     }
     __syncthreads();
   }
   TQ(2)
-  if (fail) { if (tid == 0) st.solve_failed = 1; return; }
-  for (int idx = tid; idx < kb * kb; idx += 256) {     // L[i][j] = A[i][j] / sqrt(A[j][j]); the diagonal is only read here
+  if (s_bad) { if (tid == 0) st.solve_failed = 1; return; }
+  __syncthreads();
+  if (tid < kb) s_inv[tid] = rsqrt(A[tid][tid]);        // 1 / L[j][j]
+  __syncthreads();
+  for (int idx = tid; idx < kb * kb; idx += kPotrfThreads) {     // L[i][j] = A[i][j] / sqrt(A[j][j])
     const int i = idx / kb, j = idx - i * kb;
-    if (j < i) A[i][j] *= rsqrt(A[j][j]);
+    if (j < i) A[i][j] *= s_inv[j];
   }
   __syncthreads();
-  if (tid < kb) A[tid][tid] = sqrt(A[tid][tid]);
+  if (tid < kb) A[tid][tid] = A[tid][tid] * s_inv[tid];
   __syncthreads();
   TQ(3)
-  // inverse of the lower-triangular factor: column c by forward substitution, one thread per column, the dot product of
-  // every row in four independent partial sums
-  if (tid < kb) {
-    const int c = tid;
-    for (int i = c; i < kb; i++) {
-      double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int k = c;
-      for (; k + 3 < i; k += 4) {
-        s0 -= A[i][k] * Li[k][c]; s1 -= A[i][k + 1] * Li[k + 1][c]; s2 -= A[i][k + 2] * Li[k + 2][c]; s3 -= A[i][k + 3] * Li[k + 3][c];
-      }
-      for (; k < i; k++) s0 -= A[i][k] * Li[k][c];
-      Li[i][c] = ((s0 + s1) + (s2 + s3)) / A[i][i];
+  // inverse of the lower-triangular factor by forward substitution: 4 lanes per column split every row's dot product,
+  // two shuffles add the parts in a fixed order; the 8 columns of a warp advance row by row together
+  if (tid < 4 * kNB) {
+    const int c = tid >> 2, part = tid & 3;
+    for (int i = 0; i < kb; i++) {
+      double s = 0.0;
+      if (c < kb && i > c)
+        for (int k = c + part; k < i; k += 4) s += A[i][k] * Li[k][c];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (part == 0 && c < kb && i >= c) Li[i][c] = ((i == c ? 1.0 : 0.0) - s) * s_inv[i];
+      __syncwarp();
     }
   }
   __syncthreads();
   TQ(4)
-  for (int idx = tid; idx < kb * kb; idx += 256) {
+  for (int idx = tid; idx < kb * kb; idx += kPotrfThreads) {
     const int i = idx / kb, k = idx - i * kb;
     if (k <= i) d.S[(size_t)(k0 + i) * n + k0 + k] = A[i][k];
     Linv[(size_t)(k0 / kNB) * kNB * kNB + i * kNB + k] = Li[i][k];
@@ -1465,6 +1486,10 @@ __global__ void __launch_bounds__(256) k_backsolve_panel(BaDev d, int k0, int kb
 // 16 row groups x 64 columns with a fixed-order reduction.  Replaces one k_backsolve_panel launch per panel.
 constexpr int kBackAllMaxN = 12288;
 inline size_t back_all_smem(int n) { return ((size_t)n + kNB + 16 * 64) * sizeof(double); }
+inline bool use_back_all(int n) {      // CMOS_BA_PANEL_BACKSOLVE=1 forces the per-panel kernels (the path of systems beyond kBackAllMaxN)
+  const char* e = std::getenv("CMOS_BA_PANEL_BACKSOLVE");
+  return n <= kBackAllMaxN && !(e && e[0] == '1');
+}
 __global__ void __launch_bounds__(1024) k_backsolve_all(BaDev d, const double* __restrict__ Linv, const int* __restrict__ first_col) {
   extern __shared__ double dyn_smem[];
   double* y = dyn_smem;                       // [n]
@@ -2036,7 +2061,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
         h->launches++;
         for (int k0 = 0, p = 0; k0 < n; k0 += kNB, p++) {
           const int kb = std::min(kNB, n - k0);
-          k_potrf_diag<<<1, 256, kPanelSmem, st>>>(d, k0, kb, h->d_Linv);
+          k_potrf_diag<<<1, kPotrfThreads, kPanelSmem, st>>>(d, k0, kb, h->d_Linv);
           const int na = h->pan_start[p + 1] - h->pan_start[p];   // active tiles below this panel (rhs row included)
           if (na > 0) {
             const int* tiles = h->d_pan_tiles + h->pan_start[p];
@@ -2046,7 +2071,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
           }
           h->launches++;
         }
-        if (n <= kBackAllMaxN) {
+        if (use_back_all(n)) {
           k_backsolve_all<<<1, 1024, back_all_smem(n), st>>>(d, h->d_Linv, h->d_pan_first);
           h->launches++;
         } else
@@ -2761,7 +2786,7 @@ int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Sc
     h->launches++;
     for (int k0 = 0, p = 0; k0 < n; k0 += kNB, p++) {
       const int kb = std::min(kNB, n - k0);
-      k_potrf_diag<<<1, 256, kPanelSmem, st>>>(dv, k0, kb, g.Linv);
+      k_potrf_diag<<<1, kPotrfThreads, kPanelSmem, st>>>(dv, k0, kb, g.Linv);
       const int na = pan_start[p + 1] - pan_start[p];
       if (na > 0) {
         const int* tl = g.tiles + pan_start[p];
@@ -2771,7 +2796,7 @@ int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Sc
       }
       h->launches++;
     }
-    if (n <= kBackAllMaxN) {
+    if (use_back_all(n)) {
       k_backsolve_all<<<1, 1024, back_all_smem(n), st>>>(dv, g.Linv, g.first_col);
       h->launches++;
     } else

@@ -226,3 +226,20 @@ def test_optimize_essential_graph_edge_cases():
     with pytest.raises(Exception):
         opt.OptimizeEssentialGraph(G["Scw"], G["kf_flags"], G["Snc"], ej, bad, ek, G["Xw"], G["ref_kf"])
     opt.close()
+
+
+def test_essential_graph_per_panel_back_substitution(monkeypatch):
+    """Systems beyond 12288 unknowns fall back from the one-launch back substitution to one launch per panel; the knob forces
+    that path on a small graph: both must give the oracle's result."""
+    G = synth.make_essential_graph_problem(40, seed=12, n_points=10)
+    a = (G["Scw"], G["kf_flags"], G["Snc"], G["edge_j"], G["edge_i"], G["edge_kind"], G["Xw"], G["ref_kf"])
+    ref = po.essential_graph(*a)
+    opt = CeresOptimizer(max_cams=2, max_points=8, max_obs=8)
+    one = opt.OptimizeEssentialGraph(*a)
+    monkeypatch.setenv("CMOS_BA_PANEL_BACKSOLVE", "1")
+    per = opt.OptimizeEssentialGraph(*a)
+    monkeypatch.delenv("CMOS_BA_PANEL_BACKSOLVE")
+    for got in (one, per):
+        assert got["summary"]["iterations"] == ref["iterations"] and np.abs(got["lie"] - ref["lie"]).max() <= 1e-7
+    assert np.abs(one["lie"] - per["lie"]).max() <= 1e-9
+    opt.close()
