@@ -612,34 +612,80 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(OrbGeom g, const uint32_
 // Q8 kernel [18,34,48,56,48,34,18]: the row pass is two DP4A per pixel (byte windows cut out of three words with
 // funnel shifts); its 16-bit sums are stored as (row 2p, row 2p+1) pairs so the column pass is four DP2A per
 // pixel, and one thread produces a 4-column x 2-row block from the same four pair loads.
+// ---- TMA helpers: threads arm an mbarrier with the byte count and issue bulk copies, the CTA waits on the barrier -------
+// Only the descriptor-less bulk copy (cp.async.bulk, SASS UBLKCP) is used: on this pool's B200s every tensor-map copy
+// (cp.async.bulk.tensor / UTMALDG, also the CUDA programming guide's own cde:: example) raises "illegal instruction"
+// although cuTensorMapEncodeTiled succeeds — tools/micro/tma.cu, tma2.cu.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {   // 16-byte aligned
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+
+// kTma: every row of the (TH+6)-row input tile arrives by one 160-byte bulk copy (TMA engine, completion on an mbarrier)
+// from the 16-byte aligned column x0 - 16 instead of 5-6 bounds-checked word loads per thread; the arithmetic is the same.
+template <bool kTma>
 __global__ void __launch_bounds__(256) k_blur(OrbGeom g, const int2* __restrict__ tiles,
                                               const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
   constexpr int kPairs = (kBlurTH + 6) / 2;                          // 19 row pairs = tile rows y0-3 .. y0+TH+2
-  static_assert(kBlurTH % 2 == 0 && kBlurTW % 4 == 0, "tile shape");
-  __shared__ __align__(16) uint8_t in[(kBlurTH + 6) * kBlurInPitch];
+  constexpr int kPitch = kTma ? kBlurTW + 32 : kBlurInPitch;         // bytes per staged row
+  constexpr int kLead = kTma ? 12 : 0;                               // staged byte of column x0 - 4
+  static_assert(kBlurTH % 2 == 0 && kBlurTW % 4 == 0 && kPitch % 16 == 0, "tile shape");
+  __shared__ __align__(128) uint8_t in[(kBlurTH + 6) * kPitch];
   __shared__ __align__(16) uint32_t hp[kPairs * kBlurTW];            // (h[2p][x] | h[2p+1][x] << 16)
+  __shared__ __align__(8) uint64_t s_bar;
   const int2 te = __ldg(tiles + blockIdx.x);
   const int level = te.x & 0xff, x0 = (te.x >> 8) * kBlurTW, y0 = te.y * kBlurTH;
   const LevelGeom& L = g.lv[level];
   const int f = blockIdx.y, tid = threadIdx.x;
   const uint8_t* plane = pyr + (long long)f * g.frame_bytes + L.plane_off;
   // input rows y0-3 .. y0+TH+2, columns x0-4 .. x0+TW+3 (word aligned: kXOff + x0 - 4 is a multiple of 4)
-  constexpr int in_words = kBlurInPitch / 4;
-  for (int i = tid; i < (kBlurTH + 6) * in_words; i += 256) {
-    int r = i / in_words, w = i - r * in_words;
-    int row = y0 - 3 + r + kBorder, col = kXOff + x0 - 4 + 4 * w;
-    uint32_t v = 0;
-    if (row < L.rows && col + 3 < L.pitch) v = __ldg((const uint32_t*)(plane + (long long)row * L.pitch + col));
-    *(uint32_t*)(in + r * kBlurInPitch + 4 * w) = v;
+  if (kTma) {
+    const int row0 = y0 - 3 + kBorder;
+    const int n_valid = min(max(L.rows - row0, 0), kBlurTH + 6);    // rows below the plane read as zero
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) mbar_expect_tx(&s_bar, (unsigned)n_valid * kPitch);
+    if (tid < kBlurTH + 6) {
+      if (tid < n_valid) bulk_load(in + tid * kPitch, plane + (long long)(row0 + tid) * L.pitch + (kXOff + x0 - 16), kPitch, &s_bar);
+      else
+        for (int w = 0; w < kPitch / 4; w++) ((uint32_t*)(in + tid * kPitch))[w] = 0;
+    }
+    __syncthreads();                 // zero rows written
+    mbar_wait(&s_bar, 0);
+  } else {
+    constexpr int in_words = kBlurInPitch / 4;
+    for (int i = tid; i < (kBlurTH + 6) * in_words; i += 256) {
+      int r = i / in_words, w = i - r * in_words;
+      int row = y0 - 3 + r + kBorder, col = kXOff + x0 - 4 + 4 * w;
+      uint32_t v = 0;
+      if (row < L.rows && col + 3 < L.pitch) v = __ldg((const uint32_t*)(plane + (long long)row * L.pitch + col));
+      *(uint32_t*)(in + r * kBlurInPitch + 4 * w) = v;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   constexpr unsigned kWA = 0x38302212u, kWB = 0x00122230u;           // taps 0..3 and 4..6 (+ a zero)
   for (int i = tid; i < kPairs * (kBlurTW / 4); i += 256) {
     const int p = i / (kBlurTW / 4), x4 = (i - p * (kBlurTW / 4)) * 4;
     uint32_t h[2][4];
 #pragma unroll
     for (int rr = 0; rr < 2; rr++) {
-      const uint32_t* s = (const uint32_t*)(in + (2 * p + rr) * kBlurInPitch + x4);   // s[0] byte 1 is pixel x4-3
+      const uint32_t* s = (const uint32_t*)(in + (2 * p + rr) * kPitch + kLead + x4);   // s[0] byte 1 is pixel x4-3
       const uint32_t w0 = s[0], w1 = s[1], w2 = s[2];
       h[rr][0] = __dp4a(__funnelshift_r(w0, w1, 8), kWA, __dp4a(__funnelshift_r(w1, w2, 8), kWB, 0u));
       h[rr][1] = __dp4a(__funnelshift_r(w0, w1, 16), kWA, __dp4a(__funnelshift_r(w1, w2, 16), kWB, 0u));
@@ -819,6 +865,7 @@ struct cmos_orb {
   cudaStream_t side = nullptr;            // the blur runs here, beside the quadtree (both only need what FAST / the pyramid left)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap = true;                    // CMOS_ORB_NO_OVERLAP=1 keeps every kernel on one stream
+  bool blur_tma = true;                   // CMOS_BLUR_NO_TMA=1: word loads instead of bulk copies
   std::vector<float> sf, inv_sf, sigma2, inv_sigma2;
   std::vector<int> quota;
   int umax[16];
@@ -1033,7 +1080,8 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
   if (fork) {
     CMOS_CUDA_OK(cudaEventRecord(h->ev_fork, st));
     CMOS_CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    k_blur<<<dim3(h->n_tiles, n_frames), 256, 0, h->side>>>(g, h->d_tiles, h->d_pyr, h->d_blur);
+    if (h->blur_tma) k_blur<true><<<dim3(h->n_tiles, n_frames), 256, 0, h->side>>>(g, h->d_tiles, h->d_pyr, h->d_blur);
+    else k_blur<false><<<dim3(h->n_tiles, n_frames), 256, 0, h->side>>>(g, h->d_tiles, h->d_pyr, h->d_blur);
     CMOS_CUDA_OK(cudaEventRecord(h->ev_join, h->side));
   }
   k_octree<<<dim3(g.nlevels, n_frames), kOctThreads, oct_smem_bytes(h->oct_maxn), st>>>(
@@ -1041,7 +1089,8 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
   launches++;
   h->timer.mark(st);   // stage 2: quadtree
   if (fork) CMOS_CUDA_OK(cudaStreamWaitEvent(st, h->ev_join, 0));
-  else k_blur<<<dim3(h->n_tiles, n_frames), 256, 0, st>>>(g, h->d_tiles, h->d_pyr, h->d_blur);
+  else if (h->blur_tma) k_blur<true><<<dim3(h->n_tiles, n_frames), 256, 0, st>>>(g, h->d_tiles, h->d_pyr, h->d_blur);
+  else k_blur<false><<<dim3(h->n_tiles, n_frames), 256, 0, st>>>(g, h->d_tiles, h->d_pyr, h->d_blur);
   launches++;
   h->timer.mark(st);   // stage 3: blur
   k_describe<<<dim3((g.kp_cap + kDescThreads / 32 - 1) / (kDescThreads / 32), n_frames), kDescThreads, 0, st>>>(
@@ -1129,6 +1178,7 @@ int cmos_orb_create(const cmos_orb_params* params, cmos_orb_t* out) {
   if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) err = cudaErrorUnknown;
   if (cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) err = cudaErrorUnknown;
   { const char* e = std::getenv("CMOS_ORB_NO_OVERLAP"); h->overlap = !(e && e[0] == '1'); }
+  { const char* e = std::getenv("CMOS_BLUR_NO_TMA"); h->blur_tma = !(e && e[0] == '1'); }
   h->d_images = dev_alloc<uint8_t>(h->images_cap, &err);
   h->d_pyr = dev_alloc<uint8_t>(h->cap_frame_bytes * B, &err);
   h->d_blur = dev_alloc<uint8_t>(h->cap_frame_bytes * B, &err);
