@@ -128,6 +128,34 @@ int main() {
       if (std::fabs(c0) > 1e-9 || std::fabs(c11 - 11.1730) > 1e-3 || std::fabs(c6 - 6.0576) > 1e-3) return 7;
       if (std::fabs(g.corrected_pos[3] - (-g.Tiw[16 * 4 + 3])) > 0.05 || std::fabs(g.corrected_pos[5] - 5.0) > 0.5) return 8;
     }
+    {
+      // OptimizeSim3 on exact correspondences of two identical cameras one metre apart: as in the reference the solver
+      // accepts no step from a consistent start (quirk Q6), every correspondence is an inlier and S12 comes back unchanged.
+      const int n = 60;
+      std::vector<float> o1(2 * n), o2(2 * n), w(n, 1.0f);
+      std::vector<double> p2c(3 * n), p1c(3 * n);
+      Sim3MatchesView m;
+      const float K[4] = {520.9f, 521.0f, 325.1f, 249.7f};
+      for (int k = 0; k < 4; k++) { m.K1[k] = K[k]; m.K2[k] = K[k]; }
+      unsigned r = 777;
+      for (int i = 0; i < n; i++) {
+        r = r * 1664525u + 1013904223u; const double x = ((r >> 8) % 2000) / 1000.0 - 1.0;
+        r = r * 1664525u + 1013904223u; const double y = ((r >> 8) % 1000) / 1000.0 - 0.5;
+        r = r * 1664525u + 1013904223u; const double z = 4.0 + ((r >> 8) % 6000) / 1000.0;
+        p1c[3 * i] = x; p1c[3 * i + 1] = y; p1c[3 * i + 2] = z;              // camera-1 coordinates
+        p2c[3 * i] = x - 1.0; p2c[3 * i + 1] = y; p2c[3 * i + 2] = z;        // camera 2 sits at x = +1: P1 = P2 + (1,0,0)
+        o1[2 * i] = (float)(K[0] * x / z + K[2]); o1[2 * i + 1] = (float)(K[1] * y / z + K[3]);
+        o2[2 * i] = (float)(K[0] * (x - 1.0) / z + K[2]); o2[2 * i + 1] = (float)(K[1] * y / z + K[3]);
+      }
+      m.n = n; m.obs1 = o1.data(); m.inv_sigma1 = w.data(); m.P3D2c = p2c.data(); m.obs2 = o2.data(); m.inv_sigma2 = w.data();
+      m.P3D1c = p1c.data();
+      Sim3POD S12; S12.t[0] = 1.0;
+      const int inl = CeresOptimizer::OptimizeSim3(m, S12, 10.0f, false);
+      int bad = 0;
+      for (size_t i = 0; i < m.is_bad.size(); i++) bad += m.is_bad[i];
+      std::printf("OptimizeSim3: %d inliers, %d outliers, s = %.6f, t = %.4f %.4f %.4f\n", inl, bad, S12.s, S12.t[0], S12.t[1], S12.t[2]);
+      if (inl != n || bad != 0 || std::fabs(S12.s - 1.0) > 1e-6 || std::fabs(S12.t[0] - 1.0) > 1e-6) return 9;
+    }
     CeresOptimizer::release();
     std::printf("ADAPTERS_OK\n");
     return 0;

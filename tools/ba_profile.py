@@ -30,6 +30,12 @@ elif which == "essential":
         t0 = time.perf_counter()
         r = opt.OptimizeEssentialGraph(*a)
         print(r["summary"], opt.launch_count(), "launches", (time.perf_counter() - t0) * 1e3, "ms")
+elif which == "global_time":
+    from ceres_mono_orb_slam2_b200.ba_bench import _bench_graph
+    G = synth.make_ba_problem_fast(1000, 100000, 5, seed=5)
+    opt = CeresOptimizer(max_cams=1000, max_points=100000, max_obs=500000)
+    r = _bench_graph(opt, G, K4, 3, 1, False, 10, "x")
+    print("global BA: %.2f ms per 10-iteration solve, %.1f Mresid/s, %d launches" % (r["ms_per_solve"], r["value"], r["gpu_launches_per_solve"]))
 elif which == "sim3":
     P = synth.make_sim3_problem(n=300, seed=6)
     opt = CeresOptimizer(max_cams=2, max_points=8, max_obs=8)
