@@ -1,5 +1,6 @@
 // Bundle-adjustment engine for sm_100a behind CeresOptimizer::{PoseOptimization, LocalBundleAdjustment,
-// BundleAdjustment / GlobalBundleAdjustemnt} (reference src/CeresOptimizer.cc:59-225,275-342,344-599).
+// BundleAdjustment / GlobalBundleAdjustemnt, OptimizeSim3, OptimizeEssentialGraph} (reference
+// src/CeresOptimizer.cc:59-225,275-342,344-599,601-957).
 //
 // What the reference does per ceres::Solve — autodiff residual blocks, Huber corrector, quaternion manifold,
 // SPARSE_NORMAL_CHOLESKY inside a Levenberg-Marquardt trust region — is restated here as a fixed sequence of
@@ -12,11 +13,18 @@
 //   k_point_prep     (H_pp + D_p^2)^-1 and (H_pp + D_p^2)^-1 g_p per point
 //   k_schur          warp per non-zero 6x6 block (a,b) of the reduced camera system: S_ab = [a==b](H_cc + D_c^2)
 //                    - sum over co-observing points of Jc_a' (Jp_a Hpp^-1 Jp_b') Jc_b; no atomics, fixed order
-//   k_solve_small /  Cholesky of the 6Kv x 6Kv reduced system (one CTA in shared memory up to Kv = 40, a blocked
-//   blocked path     right-looking factorisation in HBM above that), candidate keyframe poses
+//   k_solve_small    Cholesky of the 6Kv x 6Kv reduced system in the shared memory of one CTA (Kv <= 38): look-ahead
+//                    factorisation of the next 6x6 diagonal block, stored as its inverse; candidate keyframe poses
+//   k_solve_band     larger systems of a windowed co-visibility graph: persistent CTA over the block band
+//   blocked path     anything else (loop-closure edges; also OptimizeEssentialGraph, posegraph.cuh): right-looking
+//                    factorisation in HBM inside the row envelope (k_potrf_diag / k_trsm_panel / k_syrk_tile), the whole
+//                    back substitution in one launch (k_backsolve_all)
 //   k_backsub        thread per point: back-substitution, candidate point, candidate cost of its observations
-//   k_decide         step quality, radius schedule, termination tests (device-side LM state machine)
-// PoseOptimization (6 unknowns, constant points) is one persistent CTA per frame that runs the whole solve.
+//   post_lin_body /  gradient / cost reductions and the LM state machine (step quality, radius schedule, termination
+//   decide_body      tests): on one GPU they run in the LAST CTA of k_cam_blocks / k_backsub (threadfence + ticket),
+//                    sharded solves run them as k_post_lin / k_decide around the NCCL all-reduces
+// PoseOptimization (6 unknowns, constant points) and OptimizeSim3 (7 unknowns) are one persistent CTA per problem that
+// runs the whole solve.
 //
 // Everything is deterministic (no floating-point atomics), so 1-GPU and N-GPU runs and repeated runs agree.
 #include <cuda_runtime.h>
