@@ -243,3 +243,23 @@ def test_essential_graph_per_panel_back_substitution(monkeypatch):
         assert got["summary"]["iterations"] == ref["iterations"] and np.abs(got["lie"] - ref["lie"]).max() <= 1e-7
     assert np.abs(one["lie"] - per["lie"]).max() <= 2e-7          # different summation orders on a loop-closure graph (translations ~20)
     opt.close()
+
+
+def test_loop_closing_solves_degenerate_inputs():
+    """Fewer than 10 inliers -> OptimizeSim3 returns 0 (CeresOptimizer.cc:731); no correspondences at all; an essential graph
+    without edges terminates on the gradient tolerance at iteration 0 with every pose recovered from its input."""
+    opt = CeresOptimizer(max_cams=2, max_points=8, max_obs=8)
+    P = synth.make_sim3_problem(n=8, seed=2)
+    a = (P["s0"], P["R0"], P["t0"], P["K"], P["K"], P["obs1"], P["inv_sigma1"], P["P3D2c"], P["obs2"], P["inv_sigma2"], P["P3D1c"])
+    got = opt.OptimizeSim3(*a); ref = po.optimize_sim3(*a)
+    assert got["ret"] == ref["ret"] == 0 and np.array_equal(got["is_bad"], ref["is_bad"])
+    e = (P["s0"], P["R0"], P["t0"], P["K"], P["K"], np.zeros((0, 2), np.float32), np.zeros(0, np.float32), np.zeros((0, 3)),
+         np.zeros((0, 2), np.float32), np.zeros(0, np.float32), np.zeros((0, 3)))
+    got = opt.OptimizeSim3(*e)
+    assert got["ret"] == 0 and abs(got["s"] - P["s0"]) < 1e-12 and np.abs(got["t"] - P["t0"]).max() < 1e-12
+    G = synth.make_essential_graph_problem(10, seed=1, n_group=2, n_points=5)
+    z = (G["Scw"], G["kf_flags"], G["Snc"], np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint8), G["Xw"], G["ref_kf"])
+    got = opt.OptimizeEssentialGraph(*z); ref = po.essential_graph(*z)
+    assert got["summary"]["iterations"] == 0 and got["summary"]["termination"] == ref["termination"] == 3
+    assert np.abs(got["Tiw"] - ref["Tiw"]).max() < 1e-12 and np.abs(got["Xw"] - G["Xw"]).max() < 1e-9
+    opt.close()
