@@ -463,11 +463,11 @@ def run_b200(args):
             import __graft_entry__ as ge
             ge.build_oracle()
             cores = os.cpu_count() or 1
-            n_s = max(cores, 8)
+            n_s = B                       # the whole 64-frame batch of one GPU step: ~10-20 s of CPU work in two passes
             v, dt, _ = cpu_orb_throughput(n_s, cores, seed=1000, repeats=2)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{n_s} frames of the same workload, {cores} threads, best of 2 "
-                                              f"({dt:.2f} s per pass)"}
+                                    "sample": f"{n_s} frames (one full step of the same workload), {cores} threads, best of 2 "
+                                              f"({dt:.2f} s per pass, {2 * dt * cores:.0f} core-seconds)"}
         if not args.no_ba:
             from ceres_mono_orb_slam2_b200 import ba_bench
             line["ba"] = ba_bench.run(local_rank, world, args)
