@@ -1,0 +1,74 @@
+"""BASELINE.json's full sizes through the C ABI, checked by properties that do not need the CPU oracle at that size (plus the
+oracle on a sample): configs[1] = 64 frames of 1241x376 / 2000 features, configs[4] = 1000 keyframes x 100 000 points x
+500 000 observations."""
+import numpy as np
+import pytest
+
+from ceres_mono_orb_slam2_b200 import CeresOptimizer, ORBextractor, synth
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def test_orb_full_batch_properties():
+    """One 64-frame launch: every frame's result is independent of its batch position (three sampled frames equal their
+    single-frame extraction and the CPU oracle bit for bit), repeated runs are identical, counts stay inside the quota band
+    (sum of per-level quotas .. + the quadtree's overshoot), keypoints lie inside the image minus the 19-px edge at their level,
+    levels are concatenated in order."""
+    B = 64
+    frames = np.stack([synth.make_image(1241, 376, 1000 + f) for f in range(B)])
+    ext = ORBextractor(2000, 1.2, 8, 20, 7, max_width=1241, max_height=376, max_batch=B)
+    kps, desc, counts = ext.extract_batch(frames)
+    k2, d2, c2 = ext.extract_batch(frames)
+    assert np.array_equal(counts, c2) and np.array_equal(kps, k2) and np.array_equal(desc, d2)
+    oracle = po.OrbOracle(2000, 1.2, 8, 20, 7)
+    quota = int(oracle.quota.sum())
+    assert (counts >= quota - 8).all() and (counts <= quota + 24).all(), (counts.min(), counts.max(), quota)
+    for f in (0, 29, 63):
+        n = int(counts[f])
+        ks, ds, cs = ext.extract_batch(frames[f:f + 1])
+        assert int(cs[0]) == n and np.array_equal(ks[0, :n], kps[f, :n]) and np.array_equal(ds[0, :n], desc[f, :n])
+        ok, od = oracle.extract(frames[f])
+        assert len(ok) == n and np.array_equal(kps[f, :n], ok) and np.array_equal(desc[f, :n], od)
+    sf = oracle.scale_factors
+    for f in range(B):
+        k = kps[f, :int(counts[f])]
+        assert (np.diff(k["octave"]) >= 0).all() and k["octave"].min() == 0 and k["octave"].max() == 7
+        x = k["x"] / sf[k["octave"]]; y = k["y"] / sf[k["octave"]]
+        for l in range(8):
+            lw, lh = oracle.level_size(l)
+            m = k["octave"] == l
+            assert (x[m] > 18.5).all() and (x[m] < lw - 18.5).all() and (y[m] > 18.5).all() and (y[m] < lh - 18.5).all()
+        assert (k["angle"] >= 0).all() and (k["angle"] < 360).all() and (k["response"] >= 7).all()
+
+
+def test_global_bundle_adjustment_full_size_properties(monkeypatch):
+    """configs[4] at full size: the solve is deterministic (two runs bit-identical), the cost never increases along the
+    accepted steps and falls by an order of magnitude, the constant keyframe does not move, and two different linear solvers —
+    the banded persistent-CTA Cholesky and the blocked envelope Cholesky (CMOS_BA_NO_BAND=1) — give the same trajectory."""
+    G = synth.make_ba_problem_fast(1000, 100000, 5, seed=5)
+    K4 = np.array(synth.KITTI_K, np.float32)
+    assert len(G["obs_cam"]) == 500000
+
+    def solve():
+        opt = CeresOptimizer(max_cams=1000, max_points=100000, max_obs=500000)
+        cams, pts, s = opt.BundleAdjustment(G["poses"], G["fixed"], G["points"], G["obs_cam"], G["obs_pt"], G["uv"], G["inv_sigma2"],
+                                            K4, n_iterations=6, is_robust=True)
+        tr = opt.trace(0, int(s["iterations"]) + 1)
+        opt.close()
+        return cams, pts, s, tr
+
+    c1, p1, s1, t1 = solve()
+    c2, p2, s2, t2 = solve()
+    assert np.array_equal(c1, c2) and np.array_equal(p1, p2) and np.array_equal(t1, t2)
+    assert s1["iterations"] == 6 and s1["successful_steps"] >= 4
+    cost = t1[:, 0]
+    assert np.all(np.diff(cost) <= 1e-9 * cost[0]) and s1["final_cost"] < 0.1 * s1["initial_cost"]
+    fixed = G["fixed"].astype(bool)
+    assert np.array_equal(c1[fixed], G["poses"][fixed])
+    assert np.abs(np.linalg.norm(c1[:, 3:], axis=1) - 1).max() < 1e-9          # quaternions stay on the manifold
+    monkeypatch.setenv("CMOS_BA_NO_BAND", "1")
+    c3, p3, s3, t3 = solve()
+    assert (s3["iterations"], s3["successful_steps"]) == (s1["iterations"], s1["successful_steps"])
+    assert np.abs(t3[:, 0] / t1[:, 0] - 1).max() < 1e-9
+    assert np.abs(c3 - c1).max() < 1e-7 and np.abs(p3 - p1).max() < 1e-5 * max(1.0, np.abs(p1).max())
