@@ -72,3 +72,46 @@ def test_global_bundle_adjustment_full_size_properties(monkeypatch):
     assert (s3["iterations"], s3["successful_steps"]) == (s1["iterations"], s1["successful_steps"])
     assert np.abs(t3[:, 0] / t1[:, 0] - 1).max() < 1e-9
     assert np.abs(c3 - c1).max() < 1e-7 and np.abs(p3 - p1).max() < 1e-5 * max(1.0, np.abs(p1).max())
+
+
+def test_extract_and_search_full_batch_properties():
+    """configs[1] end to end at full size (64 ring-paired frames, th = 15): every match index is valid and used at most once
+    per frame, the number of matched keypoints is the match count minus the re-assigned ones, matched descriptors are within TH_HIGH = 100 of
+    their map point's, the host-buffer pipeline (cmos_track_frames) returns the same matches as the unfused device calls, and
+    three sampled frames equal the CPU oracle index for index."""
+    import bench
+    from ceres_mono_orb_slam2_b200 import Camera, ORBmatcher, TrackingFrontEnd
+    B, W, H = 64, bench.W, bench.H
+    frames, offs = bench.make_batch(B, 1000)
+    ext = ORBextractor(2000, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    kps, desc, counts = ext.extract_batch(frames)
+    cap = ext.capacity
+    lk, lcounts, flags, xw, mdesc, T = bench.make_last_views(kps, desc, counts, offs, cap, seed=5000)
+    cam = Camera.create(W, H, synth.KITTI_K, ext.GetScaleFactors(), 1.2)
+    m = ORBmatcher(0.9, True, max_batch=B, max_keypoints=cap)
+    m.set_frames(cam, kps, desc, counts, B, cap)
+    match, nm = m.SearchByProjectionFrame(T, lk, lcounts, flags, xw, mdesc, cap, 15.0)
+    assert int(nm.sum()) > 500 * B
+    popcnt = np.unpackbits(np.arange(256, dtype=np.uint8)[:, None], axis=1).sum(1)
+    for f in range(B):
+        n = int(counts[f]); mf = match[f, :n]
+        hit = mf >= 0
+        # nmatches counts assignments: a keypoint holding a point without observations may be re-assigned (ORBmatcher.cc:1219-1221)
+        assert int(nm[f]) - 64 <= int(hit.sum()) <= int(nm[f]) and (match[f, n:] == -1).all()
+        assert (mf[hit] < lcounts[f]).all() and len(np.unique(mf[hit])) == int(hit.sum())      # one keypoint per map point
+        assert flags[f][mf[hit]].all()                                                          # only valid map points
+        d = popcnt[desc[f, :n][hit] ^ mdesc[f][mf[hit]]].sum(1)
+        assert (d <= 100).all()
+    b = cam.bounds6()
+    for f in (0, 31, 63):
+        n = int(counts[f]); nl = int(lcounts[f])
+        gs, gi = po.build_grid(kps[f, :n], b)
+        om, onm, _ = po.search_by_projection_frame(kps[f, :n], desc[f, :n], gs, gi, b, cam.K4(), ext.GetScaleFactors(), T[f],
+                                                   lk[f, :nl], flags[f, :nl], xw[f, :nl], mdesc[f, :nl], 15.0, True)
+        assert onm == nm[f] and np.array_equal(match[f, :n], om)
+    front = TrackingFrontEnd(cam, 2000, 1.2, 8, 20, 7, max_width=W, max_height=H, lanes=4, chunk_frames=16)
+    k2, d2, c2, m2, nm2 = front.track(frames, T, lk, lcounts, flags, xw, mdesc, 15.0)
+    assert np.array_equal(c2, counts) and np.array_equal(nm2, nm)
+    for f in range(B):
+        n = int(counts[f])
+        assert np.array_equal(m2[f, :n], match[f, :n]) and np.array_equal(d2[f, :n], desc[f, :n])
