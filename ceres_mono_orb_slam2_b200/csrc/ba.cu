@@ -46,6 +46,7 @@ namespace cmos {
 
 constexpr int kPoseThreads = 256;
 constexpr int kLinThreads = 128;
+constexpr int kPointLanes = 4;       // lanes per map point in k_linearize / k_backsub (a power of two <= 32)
 constexpr int kCamThreads = 128;
 #ifndef CMOS_SOLVE_THREADS
 #define CMOS_SOLVE_THREADS 512
@@ -529,14 +530,18 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize(BaDev d) {
   __shared__ double scratch[33];
   const LmState& st = *d.st;
   if (st.done || !st.need_lin) return;
-  const int j = blockIdx.x * kLinThreads + threadIdx.x;
+  // kPointLanes lanes share a map point: each takes every kPointLanes-th observation (the dependent loads and the fp64
+  // chain of a point's 4-5 observations run side by side instead of one after the other), two shuffles add the parts
+  const int gt = blockIdx.x * kLinThreads + threadIdx.x;
+  const int j = gt / kPointLanes, q = gt % kPointLanes;
   const double* cams = d.cams[st.cur];
   const double* pts = d.pts[st.cur];
   double cost = 0.0, gmax = 0.0, xn2 = 0.0;
+  double H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+  double X[3] = {0, 0, 0};
   if (j < d.M) {
-    const double X[3] = {pts[3 * j], pts[3 * j + 1], pts[3 * j + 2]};
-    double H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
-    for (int p = d.pt_start[j]; p < d.pt_start[j + 1]; p++) {
+    X[0] = pts[3 * j]; X[1] = pts[3 * j + 1]; X[2] = pts[3 * j + 2];
+    for (int p = d.pt_start[j] + q; p < d.pt_start[j + 1]; p += kPointLanes) {
       const int cam = d.o_cam[p];
       const float2 uv = d.o_uv[p];
       const double w = (double)d.o_w[p];
@@ -564,6 +569,15 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize(BaDev d) {
         for (int k = 0; k < 6; k++) jc[k] = make_double2(sw * Jc[2 * k], sw * Jc[2 * k + 1]);
       }
     }
+  }
+#pragma unroll
+  for (int o = 1; o < kPointLanes; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) H[k] += __shfl_xor_sync(0xffffffffu, H[k], o);
+#pragma unroll
+    for (int k = 0; k < 3; k++) g[k] += __shfl_xor_sync(0xffffffffu, g[k], o);
+  }
+  if (j < d.M && q == 0) {
 #pragma unroll
     for (int k = 0; k < 6; k++) d.Hpp[6 * (size_t)j + k] = H[k];
 #pragma unroll
@@ -1145,13 +1159,13 @@ __global__ void __launch_bounds__(kLinThreads) k_backsub(BaDev d) {
   __shared__ double scratch[33];
   const LmState& st = *d.st;
   if (st.done) return;
-  const int j = blockIdx.x * kLinThreads + threadIdx.x;
+  const int gt = blockIdx.x * kLinThreads + threadIdx.x;
+  const int j = gt / kPointLanes, q = gt % kPointLanes;
   double cost = 0.0, mcc = 0.0, sn2 = 0.0;
-  if (j < d.M && !st.solve_failed) {
-    const double* cams_c = d.cams[st.cur ^ 1];
-    const double* X = d.pts[st.cur] + 3 * (size_t)j;
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-    for (int p = d.pt_start[j]; p < d.pt_start[j + 1]; p++) {
+  const bool live = j < d.M && !st.solve_failed;       // solve_failed is uniform over the launch
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+  if (live) {
+    for (int p = d.pt_start[j] + q; p < d.pt_start[j + 1]; p += kPointLanes) {
       const int a = d.o_cv[p];
       if (a < 0) continue;
       double Jc[12], Jp[6];
@@ -1163,6 +1177,16 @@ __global__ void __launch_bounds__(kLinThreads) k_backsub(BaDev d) {
       for (int k = 0; k < 6; k++) { v0 += Jc[k] * y[k]; v1 += Jc[6 + k] * y[k]; }
       acc0 += Jp[0] * v0 + Jp[3] * v1; acc1 += Jp[1] * v0 + Jp[4] * v1; acc2 += Jp[2] * v0 + Jp[5] * v1;
     }
+  }
+#pragma unroll
+  for (int o = 1; o < kPointLanes; o <<= 1) {
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+    acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+  }
+  if (live) {
+    const double* cams_c = d.cams[st.cur ^ 1];
+    const double* X = d.pts[st.cur] + 3 * (size_t)j;
     const double* Hi = d.Hinv + 6 * (size_t)j;
     const double* t = d.tp + 3 * (size_t)j;
     // y_p = Hpp^-1 (g_p - W' y_c) ; step = -y_p
@@ -1182,9 +1206,11 @@ __global__ void __launch_bounds__(kLinThreads) k_backsub(BaDev d) {
       sn2 += (X[k] - Xc[k]) * (X[k] - Xc[k]);
     }
     mcc *= 0.5;
-    double* Xo = d.pts[st.cur ^ 1] + 3 * (size_t)j;
-    Xo[0] = Xc[0]; Xo[1] = Xc[1]; Xo[2] = Xc[2];
-    for (int p = d.pt_start[j]; p < d.pt_start[j + 1]; p++) {
+    if (q == 0) {
+      double* Xo = d.pts[st.cur ^ 1] + 3 * (size_t)j;
+      Xo[0] = Xc[0]; Xo[1] = Xc[1]; Xo[2] = Xc[2];
+    } else { mcc = 0.0; sn2 = 0.0; }               // the point's model change and step norm are counted once
+    for (int p = d.pt_start[j] + q; p < d.pt_start[j + 1]; p += kPointLanes) {
       const float2 uv = d.o_uv[p];
       const Proj P = project_obs(cams_c + 7 * (size_t)d.o_cam[p], Xc, d.fx, d.fy, d.cx, d.cy, (double)uv.x, (double)uv.y,
                                  (double)d.o_w[p]);
@@ -2047,7 +2073,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
   for (int it = 0; it < max_iterations; it++) {
     int rc;
     if ((rc = linearize())) return rc;
-    k_point_prep<<<nlb, kLinThreads, 0, st>>>(d);
+    k_point_prep<<<(d.M + kLinThreads - 1) / kLinThreads, kLinThreads, 0, st>>>(d);
     h->launches++;
     if (d.Kv > 0) {
       k_schur<<<d.n_blocks, kSchurThreads, 0, st>>>(d);
@@ -2140,7 +2166,7 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
   h->trace_rows = 256;
   bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
   BaDev& d = h->d;
-  const size_t nlb = (M + kLinThreads - 1) / kLinThreads;
+  const size_t nlb = ((size_t)M * kPointLanes + kLinThreads - 1) / kLinThreads;
   ok = ok && alloc(&d.cams[0], 7 * K) && alloc(&d.cams[1], 7 * K) && alloc(&d.pts[0], 3 * M) && alloc(&d.pts[1], 3 * M);
   ok = ok && alloc(&h->d_cams0, 7 * K) && alloc(&h->d_pts0, 3 * M) && alloc(&h->d_cams_out, 7 * K) && alloc(&h->d_pts_out, 3 * M);
   ok = ok && alloc(&h->d_cam_var, K) && alloc(&h->d_o_cam, N) && alloc(&h->d_o_cv, N) && alloc(&h->d_o_pt, N) &&
@@ -2440,7 +2466,7 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
   d.Hcc = h->d_HG; d.gc = h->d_HG + 21 * (size_t)Kv;
   d.Sblk = h->d_Sblk; d.rhs = h->d_Sblk + (size_t)nb * 36;
   d.multi = h->n_ranks > 1; d.is_root = h->rank == 0;
-  const int nlb = (M + kLinThreads - 1) / kLinThreads;
+  const int nlb = (int)(((size_t)M * kPointLanes + kLinThreads - 1) / kLinThreads);
   d.n_lin_blocks = nlb;
   int o = 0;
   d.o_lin_cost = o; o += nlb; d.o_lin_gmax = o; o += nlb; d.o_lin_xn2 = o; o += nlb;
