@@ -1789,24 +1789,69 @@ __global__ void __launch_bounds__(kBandThreads) k_solve_band(BaDev d, BandArgs b
 // four rows of six entries per lane, prefetched one step ahead), x lives in a circular shared array.  Then the
 // candidate keyframe poses.
 constexpr int kBandBackRows = (6 * kBandMaxW + 31) / 32;     // rows per lane
+// TMA bulk copy + mbarrier helpers (descriptor-less cp.async.bulk; see orb.cu for why not the tensor-map form)
+__device__ __forceinline__ uint32_t ba_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ba_mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ba_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ba_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ba_bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {   // 16-byte aligned
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(ba_smem_u32(dst)), "l"(src), "r"(bytes), "r"(ba_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ba_mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(ba_smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+
+// Back substitution L' x = y over the band factor, one warp, block column by block column from the last.  The 1000 steps
+// are a dependent chain, and with the column fetched from global memory only one step ahead every step waited out an L2
+// round trip: the columns now arrive through a ring of kBackRing TMA bulk copies (one contiguous 6(W+1) x 6 panel each,
+// completion on an mbarrier), issued kBackRing steps before they are used.
+constexpr int kBackRing = 4;
 __global__ void __launch_bounds__(32) k_band_backsub(BaDev d, BandArgs ba) {
   __shared__ double s_x[6 * (kBandMaxW + 1)];
+  __shared__ __align__(128) double s_ring[kBackRing][6 * (kBandMaxW + 1) * 6];
+  __shared__ __align__(8) uint64_t s_bar[kBackRing];
   LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
   const int lane = threadIdx.x, Kv = d.Kv, W = ba.W, NB = W + 1, NW = 6 * NB;
-  double2 nxt[kBandBackRows][3];
-  double dnx[21], ynx = 0.0;
-  auto prefetch = [&](int j) {
-    const double* Lc = ba.Lcol + (size_t)j * NW * 6;
+  const unsigned col_bytes = (unsigned)(NW * 6 * sizeof(double));
+  if (lane == 0) {
+    for (int r = 0; r < kBackRing; r++) ba_mbar_init(&s_bar[r], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int r = 0; r < kBackRing && Kv - 1 - r >= 0; r++) {
+      ba_mbar_expect_tx(&s_bar[r], col_bytes);
+      ba_bulk_load(s_ring[r], ba.Lcol + (size_t)(Kv - 1 - r) * NW * 6, col_bytes, &s_bar[r]);
+    }
+  }
+  for (int i = lane; i < NW; i += 32) s_x[i] = 0.0;
+  double ynx = (lane < 6) ? d.rhs[6 * (Kv - 1) + lane] : 0.0;
+  __syncwarp();
+  int bad = 0;
+  int sj = ((Kv - 1) % NB) * 6;               // slot of block j
+  int slot = 0;
+  unsigned phase = 0;
+  for (int j = Kv - 1; j >= 0; j--) {
+    ba_mbar_wait(&s_bar[slot], phase);
+    const double* Lc = s_ring[slot];
     const int rows = 6 * min(W, Kv - 1 - j);
+    double2 cur[kBandBackRows][3];
+    double dcur[21];
 #pragma unroll
     for (int q = 0; q < kBandBackRows; q++) {
       const int t = lane + 32 * q;
       if (t < rows) {
         const double2* p = (const double2*)(Lc + (size_t)t * 6);
-        nxt[q][0] = p[0]; nxt[q][1] = p[1]; nxt[q][2] = p[2];
+        cur[q][0] = p[0]; cur[q][1] = p[1]; cur[q][2] = p[2];
       } else {
-        nxt[q][0] = nxt[q][1] = nxt[q][2] = make_double2(0.0, 0.0);
+        cur[q][0] = cur[q][1] = cur[q][2] = make_double2(0.0, 0.0);
       }
     }
     if (lane == 0) {
@@ -1814,24 +1859,16 @@ __global__ void __launch_bounds__(32) k_band_backsub(BaDev d, BandArgs ba) {
 #pragma unroll
       for (int r = 0; r < 6; r++)
 #pragma unroll
-        for (int c = 0; c <= r; c++) dnx[k++] = Lc[(size_t)(6 * W + r) * 6 + c];
+        for (int c = 0; c <= r; c++) dcur[k++] = Lc[(size_t)(6 * W + r) * 6 + c];
     }
-    if (lane < 6) ynx = d.rhs[6 * j + lane];
-  };
-  for (int i = lane; i < NW; i += 32) s_x[i] = 0.0;
-  __syncwarp();
-  prefetch(Kv - 1);
-  int bad = 0;
-  int sj = ((Kv - 1) % NB) * 6;               // slot of block j
-  for (int j = Kv - 1; j >= 0; j--) {
-    double2 cur[kBandBackRows][3];
-    double dcur[21];
-#pragma unroll
-    for (int q = 0; q < kBandBackRows; q++) { cur[q][0] = nxt[q][0]; cur[q][1] = nxt[q][1]; cur[q][2] = nxt[q][2]; }
-#pragma unroll
-    for (int k = 0; k < 21; k++) dcur[k] = dnx[k];
     const double yj = ynx;
-    if (j > 0) prefetch(j - 1);
+    if (j > 0 && lane < 6) ynx = d.rhs[6 * (j - 1) + lane];
+    __syncwarp();                               // every lane has read its part of the ring slot
+    if (lane == 0 && j - kBackRing >= 0) {      // refill the slot with the column kBackRing steps ahead
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      ba_mbar_expect_tx(&s_bar[slot], col_bytes);
+      ba_bulk_load(s_ring[slot], ba.Lcol + (size_t)(j - kBackRing) * NW * 6, col_bytes, &s_bar[slot]);
+    }
     double acc[6] = {0, 0, 0, 0, 0, 0};
     int sx = sj + 6 + lane;                    // slot of row 6 (j + 1) + lane
     if (sx >= NW) sx -= NW;
@@ -1863,6 +1900,7 @@ __global__ void __launch_bounds__(32) k_band_backsub(BaDev d, BandArgs ba) {
       for (int r = 0; r < 6; r++) { s_x[sj + r] = x[r]; d.yc[6 * j + r] = x[r]; bad |= !isfinite(x[r]); }
     }
     sj -= 6; if (sj < 0) sj += NW;
+    if (++slot == kBackRing) { slot = 0; phase ^= 1u; }
     __syncwarp();
   }
   bad = __any_sync(0xffffffffu, bad);
