@@ -963,6 +963,23 @@ __device__ __forceinline__ void factor_diag6(double* __restrict__ L, int k0, int
   if (!ok) *s_fail = 1;
 }
 
+// rank-6 update of kGroups x 32 columns of one row of the packed triangle (lane = column within a group)
+template <int kGroups>
+__device__ __forceinline__ void solve_row_update(const double* li, const double* __restrict__ P, int ps, double* __restrict__ rowp,
+                                                 int cb, int cmax) {
+  double v[kGroups];
+#pragma unroll
+  for (int u = 0; u < kGroups; u++) v[u] = 0.0;
+#pragma unroll
+  for (int q = 0; q < kPB; q++) {
+    const double* pq = P + q * ps;
+#pragma unroll
+    for (int u = 0; u < kGroups; u++) { const int c = cb + 32 * u; if (c <= cmax) v[u] += li[q] * pq[c]; }
+  }
+#pragma unroll
+  for (int u = 0; u < kGroups; u++) { const int c = cb + 32 * u; if (c <= cmax) rowp[c] -= v[u]; }
+}
+
 __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
   extern __shared__ __align__(16) double smem_d[];
   LmState& st = *d.st;
@@ -1084,16 +1101,13 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
         for (int q = 0; q < kPB; q++) li[q] = P[q * ps + i];
         const int cmax = i < n ? i : n - 1;
         double* rowp = L + i * (i + 1) / 2;
-        for (int cb = t0 + lane; cb <= cmax; cb += 128) {
-          double v[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-          for (int q = 0; q < kPB; q++) {
-            const double* pq = P + q * ps;
-#pragma unroll
-            for (int u = 0; u < 4; u++) { const int c = cb + 32 * u; if (c <= cmax) v[u] += li[q] * pq[c]; }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; u++) { const int c = cb + 32 * u; if (c <= cmax) rowp[c] -= v[u]; }
+        // column groups of 32 the row really has (warp-uniform): short rows do not issue the other groups' instructions
+        for (int c0 = t0; c0 <= cmax; c0 += 128) {
+          const int ng = min(4, (cmax - c0) / 32 + 1);
+          if (ng == 4) solve_row_update<4>(li, P, ps, rowp, c0 + lane, cmax);
+          else if (ng == 3) solve_row_update<3>(li, P, ps, rowp, c0 + lane, cmax);
+          else if (ng == 2) solve_row_update<2>(li, P, ps, rowp, c0 + lane, cmax);
+          else solve_row_update<1>(li, P, ps, rowp, c0 + lane, cmax);
         }
       }
     }
