@@ -236,14 +236,17 @@ def cpu_ba_baseline():
         best = dt if best is None else min(best, dt)
     ev = 12000 * sum(x["iterations"] + 1 for x in ss)
     out["local_ba"] = {"value": ev / best / 1e6, "ms_per_solve": best * 1e3, "sample": "configs[3], best of 3"}
-    G = synth.make_essential_graph_problem(150, seed=8, n_group=6, covis=(2, 3, 5))
-    t0 = time.perf_counter()
-    r = po.essential_graph(G["Scw"], G["kf_flags"], G["Snc"], G["edge_j"], G["edge_i"], G["edge_kind"], G["Xw"], G["ref_kf"])
-    dt = time.perf_counter() - t0
-    out["essential_graph"] = {"value": len(G["edge_j"]) * r["jacobian_evaluations"] / dt / 1e6, "unit": "M edge linearisations/s",
-                              "ms_per_solve": dt * 1e3,
-                              "sample": "150 keyframes x %d edges (the GPU line uses 1000 keyframes); the port solves DENSE normal "
-                                        "equations, the reference's Ceres uses sparse Cholesky" % len(G["edge_j"])}
+    G = synth.make_essential_graph_problem(1000, seed=8, n_group=10, covis=(2, 3, 5), n_points=100000)
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        r = po.essential_graph(G["Scw"], G["kf_flags"], G["Snc"], G["edge_j"], G["edge_i"], G["edge_kind"], G["Xw"], G["ref_kf"])
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    out["essential_graph"] = {"value": len(G["edge_j"]) * r["jacobian_evaluations"] / best / 1e6, "unit": "M edge linearisations/s",
+                              "ms_per_solve": best * 1e3,
+                              "sample": "the GPU line's workload (1000 keyframes x %d edges, 100000 points), best of 2; sparse "
+                                        "(row-envelope) Cholesky, one thread" % len(G["edge_j"])}
     return out
 
 

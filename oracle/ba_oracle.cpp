@@ -1111,7 +1111,25 @@ int ba_oracle_essential_graph(int n_kf, const double* Scw, const uint8_t* kf_fla
     meas[e] = mul(Sjw, Swi);
   }
   ba_oracle_summary sum{};
-  std::vector<double> r(7 * (size_t)n_edges), J(49 * (size_t)n_edges), H((size_t)n * n), grad(n), scale(n, 1.0);
+  // Normal equations in row-envelope (skyline) storage: row i holds columns fc[i]..i.  Cholesky fill stays inside the row
+  // envelope, so this is an exact sparse factorisation for the essential graph (a band from the spanning tree and the
+  // co-visibility edges plus a few full rows from the loop edges) — the role CHOLMOD plays under SPARSE_NORMAL_CHOLESKY.
+  // BA_ORACLE_EG_DENSE=1 widens every row to column 0 (a dense factorisation, used by the tests as a cross-check).
+  std::vector<int> fc(std::max(n, 1), 0);
+  {
+    std::vector<int> first_blk(std::max(Kv, 1));
+    for (int a = 0; a < Kv; a++) first_blk[a] = a;
+    for (int e = 0; e < n_edges; e++) {
+      const int vi = var[edge_i[e]], vj = var[edge_j[e]];
+      if (vi >= 0 && vj >= 0) first_blk[std::max(vi, vj)] = std::min(first_blk[std::max(vi, vj)], std::min(vi, vj));
+    }
+    const char* dense = std::getenv("BA_ORACLE_EG_DENSE");
+    for (int i = 0; i < n; i++) fc[i] = (dense && dense[0] == '1') ? 0 : 7 * first_blk[i / 7];
+  }
+  std::vector<size_t> rp(n + 1, 0);
+  for (int i = 0; i < n; i++) rp[i + 1] = rp[i] + (size_t)(i - fc[i] + 1);
+  std::vector<double> r(7 * (size_t)n_edges), J(49 * (size_t)n_edges), H(std::max<size_t>(rp[n], 1)), grad(n), scale(n, 1.0);
+  auto Hat = [&](std::vector<double>& M, int i, int j) -> double& { return M[rp[i] + (size_t)(j - fc[i])]; };   // fc[i] <= j <= i
   double x_cost = 0, x_norm = 0, gmax = 0, radius = 1e4, decrease_factor = 2.0;
   int consecutive_invalid = 0, tr = 0;
   auto put_trace = [&](double cost, double dc, double gm, double sn, double rd, double rad, double acc, double valid) {
@@ -1147,15 +1165,15 @@ int ba_oracle_essential_graph(int n_kf, const double* Scw, const uint8_t* kf_fla
         if (vi >= 0) grad[7 * vi + a] += v[a];
         if (vj >= 0) grad[7 * vj + a] -= v[a];
         for (int b = 0; b < 7; b++) {
-          if (vi >= 0) H[(size_t)(7 * vi + a) * n + 7 * vi + b] += A[7 * a + b];
-          if (vj >= 0) H[(size_t)(7 * vj + a) * n + 7 * vj + b] += A[7 * a + b];
-          if (vi >= 0 && vj >= 0 && vi != vj) { H[(size_t)(7 * vi + a) * n + 7 * vj + b] -= A[7 * a + b]; H[(size_t)(7 * vj + a) * n + 7 * vi + b] -= A[7 * a + b]; }
+          if (vi >= 0 && b <= a) Hat(H, 7 * vi + a, 7 * vi + b) += A[7 * a + b];
+          if (vj >= 0 && b <= a) Hat(H, 7 * vj + a, 7 * vj + b) += A[7 * a + b];
+          if (vi >= 0 && vj >= 0 && vi != vj) { const int hi = std::max(vi, vj), lo = std::min(vi, vj); Hat(H, 7 * hi + a, 7 * lo + b) -= A[7 * a + b]; }
         }
       }
     }
     x_cost = c;
     sum.jacobian_evaluations++;
-    if (first) for (int a = 0; a < n; a++) scale[a] = 1.0 / (1.0 + std::sqrt(H[(size_t)a * n + a]));
+    if (first) for (int a = 0; a < n; a++) scale[a] = 1.0 / (1.0 + std::sqrt(Hat(H, a, a)));
     gmax = 0; double xn = 0;
     for (int k = 0; k < n_kf; k++) {
       if (var[k] < 0) continue;
@@ -1175,13 +1193,26 @@ int ba_oracle_essential_graph(int n_kf, const double* Scw, const uint8_t* kf_fla
   else if (gmax <= 1e-10) sum.termination = 3;
   else for (;;) {
     iteration++;
-    std::vector<double> A((size_t)n * n), b(n), D2(n);
+    std::vector<double> A(H.size()), b(n), D2(n);
     for (int a = 0; a < n; a++) {
-      D2[a] = std::min(std::max(scale[a] * scale[a] * H[(size_t)a * n + a], 1e-6), 1e32) / radius;
+      D2[a] = std::min(std::max(scale[a] * scale[a] * Hat(H, a, a), 1e-6), 1e32) / radius;
       b[a] = scale[a] * grad[a];
-      for (int d = 0; d < n; d++) A[(size_t)a * n + d] = scale[a] * scale[d] * H[(size_t)a * n + d] + (a == d ? D2[a] : 0.0);
+      for (int d = fc[a]; d <= a; d++) Hat(A, a, d) = scale[a] * scale[d] * Hat(H, a, d) + (a == d ? D2[a] : 0.0);
     }
-    bool ok = cholesky_solve(A, n, b);
+    // envelope Cholesky A = L L' in place, then L y = b, L' x = y
+    bool ok = true;
+    for (int i = 0; i < n && ok; i++) {
+      for (int j = fc[i]; j <= i; j++) {
+        double sacc = Hat(A, i, j);
+        for (int k = std::max(fc[i], fc[j]); k < j; k++) sacc -= Hat(A, i, k) * Hat(A, j, k);
+        if (j < i) Hat(A, i, j) = sacc / Hat(A, j, j);
+        else { if (!(sacc > 0.0) || !std::isfinite(sacc)) { ok = false; break; } Hat(A, i, i) = std::sqrt(sacc); }
+      }
+    }
+    if (ok) {
+      for (int i = 0; i < n; i++) { double sacc = b[i]; for (int k = fc[i]; k < i; k++) sacc -= Hat(A, i, k) * b[k]; b[i] = sacc / Hat(A, i, i); }
+      for (int i = n - 1; i >= 0; i--) { b[i] /= Hat(A, i, i); for (int k = fc[i]; k < i; k++) b[k] -= Hat(A, i, k) * b[i]; }
+    }
     std::vector<double> delta(n);
     double mcc = 0.0;
     for (int a = 0; a < n; a++) { delta[a] = -b[a] * scale[a]; if (!std::isfinite(delta[a])) ok = false; }

@@ -174,7 +174,8 @@ def test_optimize_sim3_converging_regime(kw):
 
 
 @pytest.mark.parametrize("n_kf,kw", [(60, dict(seed=7)), (150, dict(seed=8, n_group=6, covis=(2, 3, 5))),
-                                     (24, dict(seed=9, n_group=2, n_points=0, drift=(0.01, 0.03, 0.01)))])
+                                     (24, dict(seed=9, n_group=2, n_points=0, drift=(0.01, 0.03, 0.01))),
+                                     (1000, dict(seed=8, n_group=10, covis=(2, 3, 5), n_points=20000))])      # the bench size
 def test_optimize_essential_graph_matches_oracle(n_kf, kw):
     """cmos_ba_optimize_essential_graph == the restated OptimizeEssentialGraph: same iterations / accepted steps /
     termination, per-iteration cost and radius, Sim3 logs within 1e-7 (north_star asks 1e-4 relative), SE3 poses and corrected
@@ -221,7 +222,8 @@ def test_optimize_essential_graph_edge_cases():
     ek = np.concatenate([G["edge_kind"], G["edge_kind"][-5:]])
     b = (G["Scw"], G["kf_flags"], G["Snc"], ej, ei, ek, G["Xw"], G["ref_kf"])
     got = opt.OptimizeEssentialGraph(*b); ref = po.essential_graph(*b)
-    assert got["summary"]["iterations"] == ref["iterations"] and np.abs(got["lie"] - ref["lie"]).max() < 1e-7
+    assert got["summary"]["iterations"] == ref["iterations"]
+    assert np.abs(got["lie"] - ref["lie"]).max() < 1e-7 * max(1.0, np.abs(ref["lie"]).max())
     bad = ei.copy(); bad[0] = 99
     with pytest.raises(Exception):
         opt.OptimizeEssentialGraph(G["Scw"], G["kf_flags"], G["Snc"], ej, bad, ek, G["Xw"], G["ref_kf"])
@@ -240,8 +242,9 @@ def test_essential_graph_per_panel_back_substitution(monkeypatch):
     per = opt.OptimizeEssentialGraph(*a)
     monkeypatch.delenv("CMOS_BA_PANEL_BACKSOLVE")
     for got in (one, per):
-        assert got["summary"]["iterations"] == ref["iterations"] and np.abs(got["lie"] - ref["lie"]).max() <= 1e-7
-    assert np.abs(one["lie"] - per["lie"]).max() <= 2e-7          # different summation orders on a loop-closure graph (translations ~20)
+        assert got["summary"]["iterations"] == ref["iterations"]
+        assert np.abs(got["lie"] - ref["lie"]).max() <= 1e-7 * max(1.0, np.abs(ref["lie"]).max())       # relative, as above
+    assert np.abs(one["lie"] - per["lie"]).max() <= 1e-7 * max(1.0, np.abs(ref["lie"]).max())          # different summation orders on a loop-closure graph (translations ~20)
     opt.close()
 
 

@@ -286,3 +286,17 @@ def test_essential_graph_behaviour():
     # zero iterations: nothing moves, the cost is the initial one
     z = po.essential_graph(*a, max_iterations=0)
     assert z["iterations"] == 0 and z["final_cost"] == z["initial_cost"] == r["initial_cost"]
+
+
+def test_essential_graph_envelope_factorisation_equals_dense(monkeypatch):
+    """The oracle factorises the normal equations inside their row envelope (exact: Cholesky fill never leaves it); widening
+    every row to column 0 — a dense factorisation — must give the same iterations and the same result."""
+    for n_kf, kw in ((60, dict(seed=7)), (120, dict(seed=8, n_group=6, covis=(2, 3, 5)))):
+        G = synth.make_essential_graph_problem(n_kf, **kw)
+        a = (G["Scw"], G["kf_flags"], G["Snc"], G["edge_j"], G["edge_i"], G["edge_kind"], G["Xw"], G["ref_kf"])
+        env = po.essential_graph(*a)
+        monkeypatch.setenv("BA_ORACLE_EG_DENSE", "1")
+        dense = po.essential_graph(*a)
+        monkeypatch.delenv("BA_ORACLE_EG_DENSE")
+        assert env["iterations"] == dense["iterations"] and env["successful_steps"] == dense["successful_steps"]
+        assert np.abs(env["lie"] - dense["lie"]).max() <= 1e-10 and abs(env["final_cost"] - dense["final_cost"]) <= 1e-12 * dense["final_cost"]
