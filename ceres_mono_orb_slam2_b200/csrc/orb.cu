@@ -203,15 +203,19 @@ __device__ __forceinline__ int fast_arc_max(const uint8_t* __restrict__ p, int t
 //   A  compass test over the detection area, survivors compacted into a pixel list (warp ballot);
 //   B  exact packed arc score over the list (dense: no lane idles on a rejected pixel), scores > t into the map;
 //   C  3x3 strict NMS over the list with zero outside the cell, survivors appended to the (frame, level) list.
-template <int kThreads>
+// kTW x kTH: tile pitch / rows in shared memory, kCap: candidates kept per cell.  The 48 x 48 variant serves grids whose
+// cells are at most 44 x 48 (KITTI / TUM: 37 x 46): 9 KB of shared memory per CTA instead of 25 KB, so 16 CTAs (all 64
+// warps) are resident per SM instead of 9 — the kernel stalls on barriers and on the tile's global loads, which more
+// resident warps cover.
+template <int kThreads, int kTW, int kTH, int kCap>
 __global__ void __launch_bounds__(kThreads) k_fast(OrbGeom g, const int4* __restrict__ cells,
                                                   const uint8_t* __restrict__ pyr, uint32_t* __restrict__ cand,
                                                   int* __restrict__ cand_count, int* __restrict__ overflow,
                                                   uint8_t* __restrict__ dbg, int dbg_cell) {
-  __shared__ __align__(16) uint8_t tile[kTileH * kTileW];
-  __shared__ __align__(16) uint8_t score[kTileH * kTileW];
-  __shared__ uint16_t s_px[(kTileH - 6) * (kTileW - 4 - 6)];
-  __shared__ uint32_t s_list[kCellListCap];
+  __shared__ __align__(16) uint8_t tile[kTH * kTW];
+  __shared__ __align__(16) uint8_t score[kTH * kTW];
+  __shared__ uint16_t s_px[(kTH - 6) * (kTW - 4 - 6)];
+  __shared__ uint32_t s_list[kCap];
   __shared__ int s_n, s_base, s_npx;
 
   const int4 ce = __ldg(cells + blockIdx.x);
@@ -228,9 +232,9 @@ __global__ void __launch_bounds__(kThreads) k_fast(OrbGeom g, const int4* __rest
   for (int i = tid; i < ch * words; i += kThreads) {
     int r = (int)(((unsigned)i * wmagic) >> 20), w = i - r * words;
     uint32_t v = __ldg((const uint32_t*)(plane + org - shift + (long long)r * L.pitch) + w);
-    *(uint32_t*)(tile + r * kTileW + 4 * w) = v;
+    *(uint32_t*)(tile + r * kTW + 4 * w) = v;
   }
-  for (int i = tid; i < ch * (kTileW / 4); i += kThreads) ((uint32_t*)score)[i] = 0;
+  for (int i = tid; i < ch * (kTW / 4); i += kThreads) ((uint32_t*)score)[i] = 0;
   if (tid == 0) { s_n = 0; s_npx = 0; }
   __syncthreads();
 
@@ -254,9 +258,9 @@ __global__ void __launch_bounds__(kThreads) k_fast(OrbGeom g, const int4* __rest
         if (i < items) {
           y = (int)(((unsigned)i * nmagic) >> 20);
           const int wc = w_first + (i - y * nw);
-          const uint32_t* row = t32 + (y + 3) * (kTileW / 4) + wc;
+          const uint32_t* row = t32 + (y + 3) * (kTW / 4) + wc;
           const uint32_t C = row[0], Lw = row[-1], Rw = row[1];
-          const uint32_t U = row[-3 * (kTileW / 4)], D = row[3 * (kTileW / 4)];
+          const uint32_t U = row[-3 * (kTW / 4)], D = row[3 * (kTW / 4)];
           const unsigned a0 = __vabsdiffu4(D, C), a8 = __vabsdiffu4(U, C);
           const unsigned a4 = __vabsdiffu4(__funnelshift_r(C, Rw, 24), C), a12 = __vabsdiffu4(__funnelshift_r(Lw, C, 8), C);
           const unsigned g0 = ((a0 >> 1) & 0x7f7f7f7fu) + addc, g8 = ((a8 >> 1) & 0x7f7f7f7fu) + addc;
@@ -289,23 +293,23 @@ __global__ void __launch_bounds__(kThreads) k_fast(OrbGeom g, const int4* __rest
     // B: exact scores of the survivors
     for (int j = tid; j < nl; j += kThreads) {
       const int q = s_px[j], y = q >> 8, x = q & 0xff;
-      const int m = fast_arc_max(tile + (y + 3) * kTileW + shift + x + 3, kTileW);
-      if (m > th) score[(y + 3) * kTileW + x + 3] = (uint8_t)m;
+      const int m = fast_arc_max(tile + (y + 3) * kTW + shift + x + 3, kTW);
+      if (m > th) score[(y + 3) * kTW + x + 3] = (uint8_t)m;
     }
     __syncthreads();
     // C: strict 3x3 non-max suppression (scores <= th are 0 in the map)
     int kept = 0;
     for (int j = tid; j < nl; j += kThreads) {
       const int q = s_px[j], y = q >> 8, x = q & 0xff;
-      const uint8_t* s = score + (y + 3) * kTileW + x + 3;
+      const uint8_t* s = score + (y + 3) * kTW + x + 3;
       const int m = s[0];
       if (m <= th) continue;
-      const int n = max(max(max((int)s[-kTileW - 1], (int)s[-kTileW]), max((int)s[-kTileW + 1], (int)s[-1])),
-                        max(max((int)s[1], (int)s[kTileW - 1]), max((int)s[kTileW], (int)s[kTileW + 1])));
+      const int n = max(max(max((int)s[-kTW - 1], (int)s[-kTW]), max((int)s[-kTW + 1], (int)s[-1])),
+                        max(max((int)s[1], (int)s[kTW - 1]), max((int)s[kTW], (int)s[kTW + 1])));
       if (n < m) {
         int slot = atomicAdd(&s_n, 1);
         // reference coordinates: cell-local + (j*wCell, i*hCell), relative to minBorder (:820-825)
-        if (slot < kCellListCap)
+        if (slot < kCap)
           s_list[slot] = (uint32_t)(x + 3 + cj * L.w_cell) | ((uint32_t)(y + 3 + ci * L.h_cell) << 12) |
                          ((uint32_t)(m - 1) << 24);
         kept++;
@@ -317,8 +321,8 @@ __global__ void __launch_bounds__(kThreads) k_fast(OrbGeom g, const int4* __rest
     __syncthreads();
   }
   if (dbg && (int)blockIdx.x == dbg_cell && f == 0) {   // verification tap
-    for (int i = tid; i < kTileH * kTileW; i += kThreads) { dbg[i] = tile[i]; dbg[kTileH * kTileW + i] = score[i]; }
-    if (tid == 0) { int* q = (int*)(dbg + 2 * kTileH * kTileW); q[0] = x0; q[1] = y0; q[2] = cw; q[3] = ch; q[4] = shift; q[5] = level; q[6] = g.ini_th; q[7] = g.min_th; }
+    for (int i = tid; i < kTH * kTW; i += kThreads) { dbg[i] = tile[i]; dbg[kTH * kTW + i] = score[i]; }
+    if (tid == 0) { int* q = (int*)(dbg + 2 * kTH * kTW); q[0] = x0; q[1] = y0; q[2] = cw; q[3] = ch; q[4] = shift; q[5] = level; q[6] = g.ini_th; q[7] = g.min_th; }
   }
   const int n = s_n;
   if (n == 0) return;
@@ -326,7 +330,7 @@ __global__ void __launch_bounds__(kThreads) k_fast(OrbGeom g, const int4* __rest
   __syncthreads();
   const int base = s_base;
   uint32_t* out = cand + (long long)f * g.cand_frame + L.cand_off;
-  if (n > kCellListCap || base + n > L.cand_cap) {
+  if (n > kCap || base + n > L.cand_cap) {
     if (tid == 0) atomicExch(overflow, 1);
     return;
   }
@@ -892,6 +896,7 @@ struct cmos_orb {
   size_t images_cap = 0;
   int last_frames = 0, launches = 0;
   int fast_threads = 128;   // CMOS_FAST_THREADS=256 selects the wider CTA (tuning knob)
+  bool fast_small_cells = false;   // every cell of the current geometry fits the 48 x 48 tile (CMOS_FAST_LARGE_TILE=1 disables)
   int resize_rows = 2;      // CMOS_RESIZE_ROWS=1|2|4 output rows per thread of k_resize (tuning knob)
   bool has_result = false;
   StageTimer timer;
@@ -1030,6 +1035,15 @@ int ensure_geometry(cmos_orb* h, int w, int ht) {
   CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));   // host vectors die with gb
   h->geom = gb.g;
   h->n_cells = (int)gb.cells.size();
+  {
+    bool small = true;
+    for (const int4& ce : gb.cells) {
+      const int cw = ce.z & 0xffff, ch = ce.z >> 16;
+      if (cw > kSmallTileW - 4 || ch > kSmallTileH) { small = false; break; }
+    }
+    const char* e = std::getenv("CMOS_FAST_LARGE_TILE");
+    h->fast_small_cells = small && !(e && e[0] == '1');
+  }
   h->n_tiles = (int)gb.tiles.size();
   h->xtab_off = gb.xoff;
   h->ytab_off = gb.yoff;
@@ -1064,12 +1078,13 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
   }
   h->timer.mark(st);   // stage 0: pyramid
   if (h->n_cells > 0) {
-    if (h->fast_threads == 128)
-      k_fast<128><<<dim3(h->n_cells, n_frames), 128, 0, st>>>(g, h->d_cells, h->d_pyr, h->d_cand, h->d_cand_count,
-                                                            h->d_overflow, h->d_dbg, h->dbg_cell);
-    else
-      k_fast<256><<<dim3(h->n_cells, n_frames), 256, 0, st>>>(g, h->d_cells, h->d_pyr, h->d_cand, h->d_cand_count,
-                                                            h->d_overflow, h->d_dbg, h->dbg_cell);
+    const dim3 fg(h->n_cells, n_frames);
+#define CMOS_FAST_LAUNCH(T, TW, TH, CAP) \
+  k_fast<T, TW, TH, CAP><<<fg, T, 0, st>>>(g, h->d_cells, h->d_pyr, h->d_cand, h->d_cand_count, h->d_overflow, h->d_dbg, h->dbg_cell)
+    const bool small = h->fast_small_cells && h->dbg_cell < 0;      // the debug dump has the large tile's layout
+    if (h->fast_threads == 128) { if (small) CMOS_FAST_LAUNCH(128, kSmallTileW, kSmallTileH, kSmallListCap); else CMOS_FAST_LAUNCH(128, kTileW, kTileH, kCellListCap); }
+    else { if (small) CMOS_FAST_LAUNCH(256, kSmallTileW, kSmallTileH, kSmallListCap); else CMOS_FAST_LAUNCH(256, kTileW, kTileH, kCellListCap); }
+#undef CMOS_FAST_LAUNCH
     launches++;
   }
   h->timer.mark(st);   // stage 1: FAST

@@ -12,6 +12,7 @@ constexpr int kMaxLevels = 16;    // == CMOS_MAX_LEVELS
 constexpr int kFastThreads = 256;
 constexpr int kTileW = 80, kTileH = 72;   // FAST cell tile in shared memory (cell <= 60+6, +3 misalignment)
 constexpr int kCellListCap = 1024;
+constexpr int kSmallTileW = 48, kSmallTileH = 48, kSmallListCap = 512;   // cells up to 44 x 48: (44-6)*(48-6)/4 = 399 survivors at most
 constexpr int kOctThreads = 512;
 constexpr int kBlurTW = 128, kBlurTH = 32, kBlurInPitch = kBlurTW + 16;   // input tile row: 4 + 128 + 4 used, 144 = a multiple of 16 (TMA box)
 constexpr int kDescThreads = 256;
