@@ -207,8 +207,16 @@ __device__ __forceinline__ int fast_arc_max(const uint8_t* __restrict__ p, int t
 // cells are at most 44 x 48 (KITTI / TUM: 37 x 46): 9 KB of shared memory per CTA instead of 25 KB, so 16 CTAs (all 64
 // warps) are resident per SM instead of 9 — the kernel stalls on barriers and on the tile's global loads, which more
 // resident warps cover.
+#ifndef CMOS_FAST_MINBLOCKS
+#define CMOS_FAST_MINBLOCKS 12     // resident 128-thread CTAs per SM asked of the compiler: 40 registers, 0.273 -> 0.262 ms per 64 frames (16: 32 registers with spills, 0.259)
+#endif
 template <int kThreads, int kTW, int kTH, int kCap>
-__global__ void __launch_bounds__(kThreads) k_fast(OrbGeom g, const int4* __restrict__ cells,
+#if CMOS_FAST_MINBLOCKS > 0
+__global__ void __launch_bounds__(kThreads, CMOS_FAST_MINBLOCKS * 128 / kThreads) k_fast(
+#else
+__global__ void __launch_bounds__(kThreads) k_fast(
+#endif
+    OrbGeom g, const int4* __restrict__ cells,
                                                   const uint8_t* __restrict__ pyr, uint32_t* __restrict__ cand,
                                                   int* __restrict__ cand_count, int* __restrict__ overflow,
                                                   uint8_t* __restrict__ dbg, int dbg_cell) {
