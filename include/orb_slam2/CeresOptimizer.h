@@ -69,27 +69,14 @@ class CeresOptimizer {
     return inliers;
   }
 
-  // Collects the residual blocks exactly as CeresOptimizer.cc:793-895 does (loop connections first, then per keyframe its
-  // parent, its older loop edges and its older co-visible keyframes that are neither parent, child, loop edge nor already
-  // inserted), solves on the device and fills g.Tiw / g.corrected_pos.  Where the reference iterates a std::set /
-  // std::map keyed by KeyFrame* (heap-address order) the index order of the view is used.
-  static void OptimizeEssentialGraph(EssentialGraphView& g, const bool& /*is_fixed_scale: unused by the reference*/ = false) {
+  // The residual blocks of OptimizeEssentialGraph in the reference's insertion order (CeresOptimizer.cc:793-895): block 0 of
+  // edge e is keyframe ej[e], block 1 keyframe ei[e]; ek[e] = 0 for a loop-connection edge (:797-809), 1 otherwise.  Pure
+  // host logic (no device call), so it is testable without a GPU.
+  static void CollectEssentialGraphEdges(const EssentialGraphView& g, std::vector<int32_t>& ej, std::vector<int32_t>& ei,
+                                         std::vector<uint8_t>& ek) {
     const int min_weight = 100;
     const int n = g.n_keyframes;
-    std::vector<double> Scw(13 * (size_t)n), Snc(13 * (size_t)n, 0.0);
-    std::vector<uint8_t> flags(n, 0);
-    for (int k = 0; k < n; k++) {
-      const Sim3POD& S = g.has_corrected[k] ? g.corrected[k] : g.pose[k];
-      Scw[13 * k] = S.s; std::copy(S.R, S.R + 9, &Scw[13 * k + 1]); std::copy(S.t, S.t + 3, &Scw[13 * k + 10]);
-      if (g.has_non_corrected[k]) {
-        const Sim3POD& N = g.non_corrected[k];
-        Snc[13 * k] = N.s; std::copy(N.R, N.R + 9, &Snc[13 * k + 1]); std::copy(N.t, N.t + 3, &Snc[13 * k + 10]);
-        flags[k] |= 2;
-      }
-      if (k == g.loop_keyframe) flags[k] |= 1;
-    }
-    std::vector<int32_t> ej, ei;
-    std::vector<uint8_t> ek;
+    ej.clear(); ei.clear(); ek.clear();
     std::set<std::pair<unsigned long, unsigned long> > inserted;
     for (int i = 0; i < n; i++)
       for (size_t c = 0; c < g.loop_connections[i].size(); c++) {
@@ -114,6 +101,29 @@ class CeresOptimizer {
         ej.push_back(kn); ei.push_back(i); ek.push_back(1);
       }
     }
+  }
+
+  // Collects the residual blocks exactly as CeresOptimizer.cc:793-895 does (loop connections first, then per keyframe its
+  // parent, its older loop edges and its older co-visible keyframes that are neither parent, child, loop edge nor already
+  // inserted), solves on the device and fills g.Tiw / g.corrected_pos.  Where the reference iterates a std::set /
+  // std::map keyed by KeyFrame* (heap-address order) the index order of the view is used.
+  static void OptimizeEssentialGraph(EssentialGraphView& g, const bool& /*is_fixed_scale: unused by the reference*/ = false) {
+    const int n = g.n_keyframes;
+    std::vector<double> Scw(13 * (size_t)n), Snc(13 * (size_t)n, 0.0);
+    std::vector<uint8_t> flags(n, 0);
+    for (int k = 0; k < n; k++) {
+      const Sim3POD& S = g.has_corrected[k] ? g.corrected[k] : g.pose[k];
+      Scw[13 * k] = S.s; std::copy(S.R, S.R + 9, &Scw[13 * k + 1]); std::copy(S.t, S.t + 3, &Scw[13 * k + 10]);
+      if (g.has_non_corrected[k]) {
+        const Sim3POD& N = g.non_corrected[k];
+        Snc[13 * k] = N.s; std::copy(N.R, N.R + 9, &Snc[13 * k + 1]); std::copy(N.t, N.t + 3, &Snc[13 * k + 10]);
+        flags[k] |= 2;
+      }
+      if (k == g.loop_keyframe) flags[k] |= 1;
+    }
+    std::vector<int32_t> ej, ei;
+    std::vector<uint8_t> ek;
+    CollectEssentialGraphEdges(g, ej, ei, ek);
     g.Tiw.assign(16 * (size_t)n, 0.0);
     g.corrected_pos.assign(3 * (size_t)std::max(g.n_points, 1), 0.0);
     cmos_throw_if(cmos_ba_optimize_essential_graph(ctx(), n, Scw.data(), flags.data(), Snc.data(), (int32_t)ej.size(), ej.data(),

@@ -34,3 +34,29 @@ def test_adapters_run_on_gpu(tmp_path):
     exe = _build(str(tmp_path))
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "ADAPTERS_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_essential_graph_edge_collection_follows_the_reference_order(tmp_path):
+    """CeresOptimizer::CollectEssentialGraphEdges (host logic of the adapter) against the rules of CeresOptimizer.cc:793-895
+    worked out by hand for a map that exercises each of them: loop connections first (weight >= 100 or the current / loop
+    pair), then per keyframe in map order its parent, its OLDER loop edges, and its co-visible keyframes that are older and
+    neither parent, child, loop edge nor already inserted."""
+    exe = os.path.join(str(tmp_path), "essential_edges")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", os.path.join(ROOT, "tests", "cpp", "essential_edges.cpp"),
+                    "-o", exe, "-L" + LIBDIR, "-lcmos_b200", "-Wl,-rpath," + LIBDIR], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    got = [tuple(int(v) for v in line.split()) for line in out.strip().splitlines()]
+    expected = [
+        # loop connections, keyframes in index order (6 before 7)
+        (1, 6, 0),
+        (1, 7, 0), (0, 7, 0),
+        # per keyframe: parent, older loop edges, older co-visible keyframes
+        (0, 1, 1),                                   # keyframe 1: parent 0
+        (3, 2, 1), (3, 2, 1),                        # keyframe 2 (id 30): parent 3, loop edge to 3 (id 20, older)
+        (1, 3, 1),                                   # keyframe 3 (id 20): parent 1; loop edge 2 and co-visible 2 are younger
+        (2, 4, 1), (3, 4, 1), (1, 4, 1),             # keyframe 4: parent 2, co-visible 3 and 1 (2 parent, 5 child skipped)
+        (4, 5, 1), (0, 5, 1), (3, 5, 1),             # keyframe 5: parent 4, loop edge 0, co-visible 3 (0 loop edge, 4 parent)
+        (5, 6, 1),                                   # keyframe 6: parent 5; (1,6) already inserted, 7 is a child
+        (6, 7, 1), (5, 7, 1),                        # keyframe 7: parent 6; (0,7) already inserted; co-visible 5
+    ]
+    assert got == expected, got
