@@ -980,41 +980,16 @@ __device__ __forceinline__ void solve_row_update(const double* li, const double*
   for (int u = 0; u < kGroups; u++) { const int c = cb + 32 * u; if (c <= cmax) rowp[c] -= v[u]; }
 }
 
-__global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
-  extern __shared__ __align__(16) double smem_d[];
-  LmState& st = *d.st;
-  if (st.done) return;
-  const int n = d.nc, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = kSolveThreads / 32;
-  double* L = smem_d;                                   // rows 0..n, row i at i*(i+1)/2
-  const int ps = n + 2;
-  double* P = L + (size_t)(n + 1) * (n + 2) / 2;        // [kPB][ps]: the current panel's columns, by row
-  __shared__ int s_fail;
-  if (tid == 0) s_fail = st.solve_failed;
-  for (int i = tid; i < n * (n + 1) / 2; i += kSolveThreads) L[i] = 0.0;
-  for (int k = tid; k < n; k += kSolveThreads) L[n * (n + 1) / 2 + k] = d.rhs[k];
+// Right-looking Cholesky of a packed lower triangle in shared memory, panels of 6 columns, rows 0..n (row n = the rhs,
+// which leaves as the forward-substituted y).  On return every 6x6 diagonal block holds the INVERSE of its Cholesky
+// block (factor_diag6).  All kSolveThreads threads of the CTA call it; P is the [kPB][ps] panel buffer.
+__device__ __forceinline__ void packed_cholesky(double* __restrict__ L, double* __restrict__ P, const int n, const int ps,
+                                                int* s_fail) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = kSolveThreads / 32;
+  if (tid == 0 && n > 0) factor_diag6(L, 0, s_fail);
   __syncthreads();
-  for (int e = tid; e < d.n_blocks * 36; e += kSolveThreads) {
-    const int blk = e / 36, rc = e - 36 * blk, r = rc / 6, c = rc - 6 * r;
-    const int row = 6 * d.blk_b[blk] + c, col = 6 * d.blk_a[blk] + r;   // lower-triangle copy of block (a,b), a <= b
-    if (col <= row) L[row * (row + 1) / 2 + col] = d.Sblk[e];
-  }
-  __syncthreads();
-  // 6x6 diagonal block in registers of ONE thread (fully unrolled).  The pivot chain is the critical path of the whole
-  // solve, so it carries one reciprocal per pivot and nothing else: the elimination runs on the unscaled columns
-  // (A[r][c] -= A[r][j] A[c][j] / A[j][j]), the six rsqrt that turn them into Cholesky columns are independent and issued
-  // together at the end, and what is stored in the block's place is the INVERSE of its Cholesky factor: the panel solve
-  // and the back substitution then are short independent dot products instead of dependent substitution chains.
-#ifdef CMOS_SOLVE_TIMING
-  long long tk[8] = {0,0,0,0,0,0,0,0}; long long tprev = clock64(); const long long tstart = tprev;
-#define TK(i) { const long long tn = clock64(); tk[i] += tn - tprev; tprev = tn; }
-#else
-#define TK(i)
-#endif
-  if (tid == 0 && n > 0) factor_diag6(L, 0, &s_fail);
-  __syncthreads();
-  TK(0)
   for (int k0 = 0; k0 < n; k0 += kPB) {
-    if (s_fail) break;
+    if (*s_fail) break;
     const int t0 = k0 + kPB;
     // panel solve: row i of the panel times inv(L11)'
     for (int i = t0 + tid; i <= n; i += kSolveThreads) {
@@ -1033,9 +1008,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
 #pragma unroll
       for (int c = 0; c < kPB; c++) { rowp[c] = x[c]; P[c * ps + i] = x[c]; }
     }
-    TK(1)
     __syncthreads();
-    TK(2)
     // trailing update.  Look-ahead: warp 0 updates the NEXT diagonal block (rows t0..t0+5 lie entirely inside it) and its
     // lane 0 factors it at once, while the other warps update the rows below — the next round starts with its panel solve.
     if (warp == 0) {
@@ -1050,7 +1023,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
           L[i * (i + 1) / 2 + cc] -= v;
         }
         __syncwarp();
-        if (lane == 0) factor_diag6(L, t0, &s_fail);
+        if (lane == 0) factor_diag6(L, t0, s_fail);
       }
     } else {
 #if CMOS_SOLVE_TILE
@@ -1112,10 +1085,42 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
       }
     }
 #endif
-    TK(3)
     __syncthreads();
-    TK(4)
   }
+}
+
+__global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
+  extern __shared__ __align__(16) double smem_d[];
+  LmState& st = *d.st;
+  if (st.done) return;
+  const int n = d.nc, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* L = smem_d;                                   // rows 0..n, row i at i*(i+1)/2
+  const int ps = n + 2;
+  double* P = L + (size_t)(n + 1) * (n + 2) / 2;        // [kPB][ps]: the current panel's columns, by row
+  __shared__ int s_fail;
+  if (tid == 0) s_fail = st.solve_failed;
+  for (int i = tid; i < n * (n + 1) / 2; i += kSolveThreads) L[i] = 0.0;
+  for (int k = tid; k < n; k += kSolveThreads) L[n * (n + 1) / 2 + k] = d.rhs[k];
+  __syncthreads();
+  for (int e = tid; e < d.n_blocks * 36; e += kSolveThreads) {
+    const int blk = e / 36, rc = e - 36 * blk, r = rc / 6, c = rc - 6 * r;
+    const int row = 6 * d.blk_b[blk] + c, col = 6 * d.blk_a[blk] + r;   // lower-triangle copy of block (a,b), a <= b
+    if (col <= row) L[row * (row + 1) / 2 + col] = d.Sblk[e];
+  }
+  __syncthreads();
+  // 6x6 diagonal block in registers of ONE thread (fully unrolled).  The pivot chain is the critical path of the whole
+  // solve, so it carries one reciprocal per pivot and nothing else: the elimination runs on the unscaled columns
+  // (A[r][c] -= A[r][j] A[c][j] / A[j][j]), the six rsqrt that turn them into Cholesky columns are independent and issued
+  // together at the end, and what is stored in the block's place is the INVERSE of its Cholesky factor: the panel solve
+  // and the back substitution then are short independent dot products instead of dependent substitution chains.
+#ifdef CMOS_SOLVE_TIMING
+  long long tk[8] = {0,0,0,0,0,0,0,0}; long long tprev = clock64(); const long long tstart = tprev;
+#define TK(i) { const long long tn = clock64(); tk[i] += tn - tprev; tprev = tn; }
+#else
+#define TK(i)
+#endif
+  packed_cholesky(L, P, n, ps, &s_fail);
+  TK(4)
   __syncthreads();
   if (warp == 0) {
     double* y = L + n * (n + 1) / 2;      // forward-substituted rhs
@@ -1923,6 +1928,10 @@ __global__ void __launch_bounds__(32) k_band_backsub(BaDev d, BandArgs ba) {
   for (int cam = lane; cam < d.K; cam += 32) cam_candidate(d, st, cam);
 }
 
+}  // namespace cmos
+#include "band_cr.cuh"
+namespace cmos {
+
 __global__ void __launch_bounds__(256) k_cam_candidates(BaDev d) {
   LmState& st = *d.st;
   if (st.done) return;
@@ -2036,6 +2045,7 @@ struct cmos_ba {
   std::vector<int> pan_start, pan_first_col; // [n_panels + 1], [n_panels]
   size_t cap_pan_tiles = 0;
   int band_W = 0;                            // > 0: banded reduced system, solved by k_solve_band
+  int cr_N = 0, cr_n = 0, cr_Wb = 0, cr_levels = 0;   // cr_N > 0: banded system solved by block cyclic reduction (band_cr.cuh)
   int* d_band_blk = nullptr;                 // [Kv][band_W + 1]
   double* d_trace = nullptr;       // [2][trace_rows][8]
   int trace_rows = 0;
@@ -2134,6 +2144,30 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
       if (multi && (rc = allreduce(d.Sblk, (size_t)d.n_blocks * 36 + d.nc, kNcclSum))) return rc;
       if (small) {
         k_solve_small<<<1, kSolveThreads, small_smem, st>>>(d);
+        h->launches++;
+      } else if (h->band_W > 0 && h->cr_N > 0) {
+        // nested-dissection (block cyclic reduction) Cholesky of the banded system: log2(N) levels of dense node
+        // factorisations, all nodes of a level in parallel
+        const CrArgs ca{h->cr_n, h->cr_Wb, h->cr_N, h->band_W, h->cr_levels, h->d_band_blk, d.S};
+        const int nt = ca.n / 24, tile_ctas = (nt * nt + kCrGemmWarps - 1) / kCrGemmWarps;
+        k_cr_assemble<<<ca.N, 256, 0, st>>>(d, ca);
+        h->launches++;
+        for (int l = 1; l <= ca.levels; l++) {
+          const int cnt = ((ca.N >> (l - 1)) + 1) / 2;
+          k_cr_factor<<<cnt, kSolveThreads, cr_factor_smem(ca.n), st>>>(d, ca, l);
+          h->launches++;
+          if (l < ca.levels) {
+            k_cr_spike<<<dim3(tile_ctas, 2, cnt), 32 * kCrGemmWarps, 0, st>>>(d, ca, l);
+            k_cr_schur<<<dim3(tile_ctas, 4, cnt), 32 * kCrGemmWarps, 0, st>>>(d, ca, l);
+            h->launches += 2;
+          }
+        }
+        for (int l = ca.levels; l >= 1; l--) {
+          const int cnt = ((ca.N >> (l - 1)) + 1) / 2;
+          k_cr_back<<<cnt, 256, 0, st>>>(d, ca, l);
+          h->launches++;
+        }
+        k_cam_candidates<<<(d.K + 255) / 256, 256, 0, st>>>(d);
         h->launches++;
       } else if (h->band_W > 0) {
         BandArgs ba{h->band_W, h->d_band_blk, d.S};
@@ -2246,6 +2280,7 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
   cudaMemset(d.st, 0, sizeof(LmState));
   cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
   cudaFuncSetAttribute(k_solve_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  cudaFuncSetAttribute(k_cr_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cr_factor_smem(kCrMaxN));
   cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
   cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
   cudaFuncSetAttribute(k_syrk_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
@@ -2388,8 +2423,17 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
         if (o_cv[pa] < o_cv[pb] || (o_cv[pa] == o_cv[pb])) { table[(size_t)o_cv[pa] * Kv + o_cv[pb]]++; n_pairs++; }
       }
     }
-  CMOS_REQUIRE(n_pairs <= h->cap_pairs, "%zu co-observation pairs exceed the handle's capacity %zu (raise max_pairs_per_obs)",
-               n_pairs, h->cap_pairs);
+  // Long tracks (sum over points of L (L + 1) / 2 pairs) can exceed what create() sized from max_pairs_per_obs: the
+  // pair lists grow on demand instead of rejecting the graph (dense local windows, global BA after many revisits).
+  if (n_pairs > h->cap_pairs) {
+    const size_t want = n_pairs + n_pairs / 4;
+    CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_pair_a); cudaFree(h->d_pair_b);
+    h->d_pair_a = h->d_pair_b = nullptr; h->cap_pairs = 0;
+    CMOS_REQUIRE(alloc(&h->d_pair_a, want) && alloc(&h->d_pair_b, want),
+                 "cannot grow the co-observation pair lists to %zu entries", want);
+    h->cap_pairs = want;
+  }
   // Sharded solve: the reduced camera system is summed block by block over the ranks, so every rank needs the
   // SAME block list — the union of the co-visibility patterns (a rank's contiguous point range only covers part of
   // the trajectory).  One byte-mask all-reduce (max); blocks without local pairs simply contribute zero.
@@ -2441,6 +2485,17 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
       CMOS_CUDA_OK(cudaMemcpyAsync(h->d_band_blk, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
       CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));
       h->band_W = Wmax;
+      // Long bands: nested dissection over nodes of Wb >= W blocks (band_cr.cuh).  Wb is a multiple of 4 so the node size
+      // is a multiple of the 24 x 24 tensor-core tile; short systems (< 8 nodes) stay on the one-CTA band walk.
+      // CMOS_BA_BAND_SERIAL=1 forces the serial walk (A/B runs, tests that compare the two).
+      const char* serial = std::getenv("CMOS_BA_BAND_SERIAL");
+      const int Wb = (std::max(Wmax, 8) + 3) / 4 * 4, N = (Kv + Wb - 1) / Wb;
+      h->cr_N = 0;
+      if (!(serial && serial[0] == '1') && 6 * Wb <= kCrMaxN && N >= 8 && cr_doubles(N, 6 * Wb) <= h->cap_S) {
+        h->cr_N = N; h->cr_n = 6 * Wb; h->cr_Wb = Wb;
+        h->cr_levels = 1;
+        while ((1 << h->cr_levels) <= N) h->cr_levels++;
+      }
     }
   }
   if (6 * Kv > kSmallMaxN && h->band_W == 0) {
@@ -2468,7 +2523,16 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
     CMOS_CUDA_OK(cudaMemcpyAsync(h->d_pan_first, h->pan_first_col.data(), h->pan_first_col.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));
   }
-  CMOS_REQUIRE((size_t)nb <= h->cap_blocks, "%d reduced-system blocks exceed the handle's capacity %zu", nb, h->cap_blocks);
+  if ((size_t)nb > h->cap_blocks) {   // same policy for the block list and the block-sparse reduced system
+    const size_t want = (size_t)nb + nb / 4 + 1;
+    CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_blk_a); cudaFree(h->d_blk_b); cudaFree(h->d_blk_start); cudaFree(h->d_Sblk);
+    h->d_blk_a = h->d_blk_b = h->d_blk_start = nullptr; h->d_Sblk = nullptr; h->cap_blocks = 0;
+    CMOS_REQUIRE(alloc(&h->d_blk_a, want) && alloc(&h->d_blk_b, want) && alloc(&h->d_blk_start, want + 1) &&
+                 alloc(&h->d_Sblk, want * 36 + 6 * (size_t)h->p.max_cams + 8),
+                 "cannot grow the reduced-system block list to %zu blocks", want);
+    h->cap_blocks = want;
+  }
   std::vector<int> pair_a(std::max<size_t>(n_pairs, 1)), pair_b(std::max<size_t>(n_pairs, 1));
   {
     std::vector<int> f3(blk_start.begin(), blk_start.end() - 1);

@@ -1,0 +1,327 @@
+// Parallel Cholesky of the block-banded reduced camera system (GlobalBundleAdjustemnt, CeresOptimizer.cc:178-187 — the
+// 6K x 6K system Ceres hands to CHOLMOD): nested dissection by BLOCK CYCLIC REDUCTION instead of one CTA walking down
+// 1000 dependent block columns.
+//
+// The Kv keyframe blocks are grouped into N nodes of Wb >= W consecutive blocks (W = block half-bandwidth), so S is block
+// tridiagonal in nodes of n = 6 Wb unknowns.  Level l = 1, 2, ... eliminates the nodes i = 2^(l-1) (2t + 1) (1-based) in
+// parallel; the neighbours of i at that level are l = i - 2^(l-1) and r = i + 2^(l-1).  Eliminating i:
+//     D_i = L L',  y_i = L^-1 b_i,  V_l = L^-1 S_il,  V_r = L^-1 S_ir                       (k_cr_factor, k_cr_spike)
+//     S_ll -= V_l' V_l,  S_rr -= V_r' V_r,  S_lr = -V_l' V_r,  b_l -= V_l' y_i,  b_r -= V_r' y_i   (k_cr_schur)
+// and, from the last level back to the first,  x_i = L^-T (y_i - V_l x_l - V_r x_r)            (k_cr_back).
+// This is a Cholesky factorisation in nested-dissection order: the pivot chain is log2(N) dense n x n factorisations
+// (6 x 120 pivots at configs[4]) instead of 6 Kv = 6000.  Every accumulation has one writer and a fixed order, so repeated
+// solves are bit-identical.  The dense products run on the fp64 tensor cores (mma.sync m8n8k4, SASS DMMA).
+//
+// Node storage (in the allocation of the dense fallback S): arrays of N x n x n doubles
+//   D0    node diagonal block from Sblk (lower triangle used)
+//   AccL  sum of V_r' V_r of the nodes eliminated on i's LEFT  (i was their right neighbour)
+//   AccR  sum of V_l' V_l of the nodes eliminated on i's RIGHT (i was their left neighbour)
+//   Ep    S_{i,i-1} from Sblk (rows of i, columns of i-1)
+//   Linv  L_i^-1 (dense lower triangular, zeros above)
+//   Vl, Vr, Clr = V_l' V_r (rows of l, columns of r)
+// and vectors of N x n: bL, bR (like AccL / AccR), y, x.
+#pragma once
+
+namespace cmos {
+
+struct CrArgs {
+  int n, Wb, N, W, levels;
+  const int* band_blk;      // [Kv][W+1]: id of block (b - off, b), or -1
+  double* base;
+};
+enum { CR_D0 = 0, CR_ACCL, CR_ACCR, CR_EP, CR_LINV, CR_VL, CR_VR, CR_CLR, CR_NARR };
+enum { CR_BL = 0, CR_BR, CR_Y, CR_X, CR_NVEC };
+
+__host__ __device__ inline size_t cr_doubles(int N, int n) { return (size_t)N * n * ((size_t)CR_NARR * n + CR_NVEC); }
+__device__ __forceinline__ double* cr_arr(const CrArgs& a, int k, int node) {      // node is 1-based
+  return a.base + ((size_t)k * a.N + (node - 1)) * a.n * a.n;
+}
+__device__ __forceinline__ double* cr_vec(const CrArgs& a, int k, int node) {
+  return a.base + (size_t)CR_NARR * a.N * a.n * a.n + ((size_t)k * a.N + (node - 1)) * a.n;
+}
+__device__ __forceinline__ int cr_node_at(int level, int t) { return (1 << (level - 1)) * (2 * t + 1); }
+
+constexpr int kCrMaxN = 144;            // 6 * kBandMaxW
+inline size_t cr_factor_smem(int n) {
+  return ((size_t)(n + 1) * (n + 2) / 2 + (size_t)kPB * (n + 2) + (size_t)n * n / 4 + 8) * sizeof(double);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Assembly: one CTA per node zero-fills its arrays and scatters the Sblk blocks of its block columns.
+__global__ void __launch_bounds__(256) k_cr_assemble(BaDev d, CrArgs a) {
+  const LmState& st = *d.st;
+  if (st.done || st.solve_failed) return;
+  const int node = blockIdx.x + 1, tid = threadIdx.x, n = a.n, n2 = n * n;
+  double* D0 = cr_arr(a, CR_D0, node);
+  double* AccL = cr_arr(a, CR_ACCL, node);
+  double* AccR = cr_arr(a, CR_ACCR, node);
+  double* Ep = cr_arr(a, CR_EP, node);
+  const double2 z2 = make_double2(0.0, 0.0);
+  for (int e = tid; e < n2 / 2; e += 256) {
+    ((double2*)D0)[e] = z2; ((double2*)AccL)[e] = z2; ((double2*)AccR)[e] = z2; ((double2*)Ep)[e] = z2;
+  }
+  for (int e = tid; e < n; e += 256) { cr_vec(a, CR_BL, node)[e] = 0.0; cr_vec(a, CR_BR, node)[e] = 0.0; }
+  __syncthreads();
+  const int b0 = (node - 1) * a.Wb, NB = a.W + 1;
+  for (int e = tid; e < a.Wb * NB * 36; e += 256) {
+    const int bl = e / (NB * 36), rem = e - bl * NB * 36, off = rem / 36, rc = rem - 36 * off, r = rc / 6, c = rc - 6 * r;
+    const int b = b0 + bl, aa = b - off;
+    if (b >= d.Kv) {                                   // padding block: identity
+      if (off == 0 && r == c) D0[(size_t)(6 * bl + r) * n + 6 * bl + r] = 1.0;
+      continue;
+    }
+    if (aa < 0) continue;
+    const int id = a.band_blk[(size_t)b * NB + off];
+    if (id < 0) continue;
+    const double v = d.Sblk[(size_t)id * 36 + rc];     // S[6 aa + r][6 b + c]
+    if (aa >= b0) {
+      if (aa == b && c < r) continue;                  // lower triangle: row 6b + c >= column 6a + r
+      D0[(size_t)(6 * bl + c) * n + 6 * (aa - b0) + r] = v;
+    } else {
+      Ep[(size_t)(6 * bl + c) * n + 6 * (aa - (b0 - a.Wb)) + r] = v;   // S_{node, node-1}
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Factor one node per CTA: gather D and b, packed Cholesky in shared memory (the rhs rides as row n), explicit inverse of
+// the factor by pairwise merging of diagonal segments ([[A,0],[B,C]]^-1 = [[A^-1,0],[-C^-1 B A^-1, C^-1]]), results to HBM.
+__global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, int level) {
+  extern __shared__ __align__(16) double smem_d[];
+  LmState& st = *d.st;
+  if (st.done || st.solve_failed) return;                // (k_point_prep raises solve_failed for a singular point block)
+  const int node = cr_node_at(level, blockIdx.x), n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nw = kSolveThreads / 32, ps = n + 2, nb = n / 6;
+  double* L = smem_d;
+  double* P = L + (size_t)(n + 1) * (n + 2) / 2;
+  double* T = P + (size_t)kPB * ps;                      // [n*n/4] scratch of the inverse
+  __shared__ int s_fail;
+  if (tid == 0) s_fail = 0;
+  const double* D0 = cr_arr(a, CR_D0, node);
+  const double* AccL = cr_arr(a, CR_ACCL, node);
+  const double* AccR = cr_arr(a, CR_ACCR, node);
+  for (int r = warp; r < n; r += nw) {
+    const size_t ro = (size_t)r * n;
+    double* Lr = L + r * (r + 1) / 2;
+    for (int c = lane; c <= r; c += 32) Lr[c] = (D0[ro + c] - AccL[ro + c]) - AccR[ro + c];
+  }
+  {
+    const int b0 = (node - 1) * a.Wb;
+    const double* bL = cr_vec(a, CR_BL, node);
+    const double* bR = cr_vec(a, CR_BR, node);
+    for (int k = tid; k < n; k += kSolveThreads) {
+      const int cam = b0 + k / 6;
+      const double r0 = cam < d.Kv ? d.rhs[6 * b0 + k] : 0.0;
+      L[n * (n + 1) / 2 + k] = (r0 - bL[k]) - bR[k];
+    }
+  }
+  __syncthreads();
+  packed_cholesky(L, P, n, ps, &s_fail);
+  __syncthreads();
+  if (s_fail) {                                          // not positive definite: the LM step is invalid
+    if (tid == 0) st.solve_failed = 1;
+    return;
+  }
+  // explicit inverse M = L^-1.  Segments of s = 1, 2, 4, ... blocks; A = [2ks, (2k+1)s), C = [(2k+1)s, min((2k+2)s, nb)).
+  for (int s = 1; s < nb; s *= 2) {
+    const int np = (nb + s - 1) / (2 * s);               // pairs whose C part is not empty: (2k + 1) s < nb
+    const int pe = 36 * s * s, sa = 6 * s;
+    // T = L_CA * M_AA   (rows of C, columns of A; M_AA lower triangular)
+    for (int e = tid; e < np * pe; e += kSolveThreads) {
+      const int pr = e / pe, rem = e - pr * pe, r = rem / sa, j = rem - r * sa;
+      const int a0 = 6 * (2 * pr * s), c0 = a0 + sa, c1 = min(c0 + sa, n);
+      if (c0 + r >= c1) continue;
+      const double* Lrow = L + (c0 + r) * (c0 + r + 1) / 2 + a0;
+      double v = 0.0;
+      for (int k = j; k < sa; k++) v += Lrow[k] * L[(a0 + k) * (a0 + k + 1) / 2 + a0 + j];
+      T[(size_t)pr * pe + rem] = v;
+    }
+    __syncthreads();
+    // M_CA = -M_CC * T, written over L_CA (phase 1 is done reading it; M_CC and T are not written in this phase)
+    for (int e = tid; e < np * pe; e += kSolveThreads) {
+      const int pr = e / pe, rem = e - pr * pe, r = rem / sa, j = rem - r * sa;
+      const int a0 = 6 * (2 * pr * s), c0 = a0 + sa, c1 = min(c0 + sa, n);
+      if (c0 + r >= c1) continue;
+      const double* Mrow = L + (c0 + r) * (c0 + r + 1) / 2 + c0;
+      const double* Tc = T + (size_t)pr * pe + j;
+      double v = 0.0;
+      for (int k = 0; k <= r; k++) v += Mrow[k] * Tc[k * sa];
+      L[(c0 + r) * (c0 + r + 1) / 2 + a0 + j] = -v;
+    }
+    __syncthreads();
+  }
+  double* Linv = cr_arr(a, CR_LINV, node);
+  for (int r = warp; r < n; r += nw) {
+    const double* Lr = L + r * (r + 1) / 2;
+    for (int c = lane; c < n; c += 32) Linv[(size_t)r * n + c] = c <= r ? Lr[c] : 0.0;
+  }
+  double* y = cr_vec(a, CR_Y, node);
+  for (int k = tid; k < n; k += kSolveThreads) y[k] = L[n * (n + 1) / 2 + k];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// fp64 tensor-core tile: one warp accumulates a 24 x 24 output tile as 3 x 3 mma.m8n8k4 tiles.
+// Fragment layout (PTX ISA, mma.m8n8k4 .f64): A[row = lane / 4][col = lane % 4], B[row = lane % 4][col = lane / 4],
+// C[row = lane / 4][col = 2 (lane % 4) + {0, 1}].
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+struct CrTile { double c[3][3][2]; };
+template <typename FA, typename FB>
+__device__ __forceinline__ void cr_tile_mma(CrTile& t, const int k_begin, const int k_end, FA load_a, FB load_b) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < 3; mi++)
+#pragma unroll
+    for (int ni = 0; ni < 3; ni++) t.c[mi][ni][0] = t.c[mi][ni][1] = 0.0;
+  for (int k0 = k_begin; k0 < k_end; k0 += 4) {
+    double fa[3], fb[3];
+#pragma unroll
+    for (int mi = 0; mi < 3; mi++) fa[mi] = load_a(8 * mi + g, k0 + q);     // (row in tile, k)
+#pragma unroll
+    for (int ni = 0; ni < 3; ni++) fb[ni] = load_b(k0 + q, 8 * ni + g);     // (k, column in tile)
+#pragma unroll
+    for (int mi = 0; mi < 3; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 3; ni++) dmma_884(t.c[mi][ni][0], t.c[mi][ni][1], fa[mi], fb[ni]);
+  }
+}
+
+// The node that connected i with its level-`level` neighbour on side `right` (0 = left), and how to read S_{i,nb} from it:
+// level 1: the assembled S_{i,i-1} (left) or S_{i+1,i} transposed (right); above: -C_lr of the node eliminated between them.
+struct CrCoupling { const double* src; bool trans; double sign; };
+__device__ __forceinline__ CrCoupling cr_coupling(const CrArgs& a, int node, int level, int right) {
+  CrCoupling c;
+  if (level == 1) {
+    c.src = cr_arr(a, CR_EP, right ? node + 1 : node); c.trans = right != 0; c.sign = 1.0;
+  } else {
+    const int h = 1 << (level - 2);
+    c.src = cr_arr(a, CR_CLR, right ? node + h : node - h); c.trans = right == 0; c.sign = -1.0;
+  }
+  return c;
+}
+
+// V_side = L^-1 S_{i,side}: grid (tile groups, side, node), one warp per 24 x 24 tile of V.
+constexpr int kCrGemmWarps = 4;
+__global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_spike(BaDev d, CrArgs a, int level) {
+  const LmState& st = *d.st;
+  if (st.done || st.solve_failed) return;
+  const int node = cr_node_at(level, blockIdx.z), side = blockIdx.y, n = a.n, nt = n / 24;
+  const int nbr = side ? node + (1 << (level - 1)) : node - (1 << (level - 1));
+  if (nbr < 1 || nbr > a.N) return;
+  const int tile = blockIdx.x * kCrGemmWarps + (threadIdx.x >> 5);
+  if (tile >= nt * nt) return;
+  const int r0 = 24 * (tile / nt), j0 = 24 * (tile % nt);
+  const CrCoupling cp = cr_coupling(a, node, level, side);
+  const double* __restrict__ Linv = cr_arr(a, CR_LINV, node);
+  const double* __restrict__ src = cp.src;
+  CrTile t;
+  if (cp.trans)
+    cr_tile_mma(t, 0, r0 + 24,
+                [&](int r, int k) { return __ldg(Linv + (size_t)(r0 + r) * n + k); },
+                [&](int k, int c) { return __ldg(src + (size_t)(j0 + c) * n + k); });
+  else
+    cr_tile_mma(t, 0, r0 + 24,
+                [&](int r, int k) { return __ldg(Linv + (size_t)(r0 + r) * n + k); },
+                [&](int k, int c) { return __ldg(src + (size_t)k * n + j0 + c); });
+  double* V = cr_arr(a, side ? CR_VR : CR_VL, node);
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < 3; mi++)
+#pragma unroll
+    for (int ni = 0; ni < 3; ni++)
+      *(double2*)(V + (size_t)(r0 + 8 * mi + g) * n + j0 + 8 * ni + 2 * q) =
+          make_double2(cp.sign * t.c[mi][ni][0], cp.sign * t.c[mi][ni][1]);
+}
+
+// Schur products of an eliminated node: grid (tile groups, product, node).
+//   product 0: AccR[l] += V_l' V_l (lower tiles)   1: AccL[r] += V_r' V_r (lower tiles)   2: Clr[i] = V_l' V_r
+//   product 3: bR[l] += V_l' y_i, bL[r] += V_r' y_i
+__global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur(BaDev d, CrArgs a, int level) {
+  const LmState& st = *d.st;
+  if (st.done || st.solve_failed) return;
+  const int node = cr_node_at(level, blockIdx.z), prod = blockIdx.y, n = a.n, nt = n / 24, h = 1 << (level - 1);
+  const int l = node - h, r = node + h;
+  const bool has_l = l >= 1, has_r = r <= a.N;
+  const double* __restrict__ Vl = cr_arr(a, CR_VL, node);
+  const double* __restrict__ Vr = cr_arr(a, CR_VR, node);
+  if (prod == 3) {
+    if (blockIdx.x != 0) return;
+    const double* __restrict__ y = cr_vec(a, CR_Y, node);
+    for (int p = threadIdx.x; p < 2 * n; p += 32 * kCrGemmWarps) {
+      const int sd = p >= n, c = p - sd * n;
+      if (sd ? !has_r : !has_l) continue;
+      const double* V = sd ? Vr : Vl;
+      double v = 0.0;
+      for (int k = 0; k < n; k++) v += V[(size_t)k * n + c] * y[k];
+      double* dst = sd ? cr_vec(a, CR_BL, r) : cr_vec(a, CR_BR, l);
+      dst[c] += v;
+    }
+    return;
+  }
+  if ((prod == 0 && !has_l) || (prod == 1 && !has_r) || (prod == 2 && !(has_l && has_r))) return;
+  const int tile = blockIdx.x * kCrGemmWarps + (threadIdx.x >> 5);
+  if (tile >= nt * nt) return;
+  const int p0 = 24 * (tile / nt), q0 = 24 * (tile % nt);
+  if (prod < 2 && q0 > p0) return;                       // symmetric products: lower tiles only
+  const double* __restrict__ Va = prod == 1 ? Vr : Vl;
+  const double* __restrict__ Vb = prod == 0 ? Vl : Vr;
+  CrTile t;
+  cr_tile_mma(t, 0, n,
+              [&](int rr, int k) { return __ldg(Va + (size_t)k * n + p0 + rr); },
+              [&](int k, int c) { return __ldg(Vb + (size_t)k * n + q0 + c); });
+  double* dst = prod == 0 ? cr_arr(a, CR_ACCR, l) : prod == 1 ? cr_arr(a, CR_ACCL, r) : cr_arr(a, CR_CLR, node);
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < 3; mi++)
+#pragma unroll
+    for (int ni = 0; ni < 3; ni++) {
+      double2* o = (double2*)(dst + (size_t)(p0 + 8 * mi + g) * n + q0 + 8 * ni + 2 * q);
+      if (prod == 2) *o = make_double2(t.c[mi][ni][0], t.c[mi][ni][1]);
+      else { const double2 old = *o; *o = make_double2(old.x + t.c[mi][ni][0], old.y + t.c[mi][ni][1]); }
+    }
+}
+
+// Back substitution of one level: x_i = L^-T (y_i - V_l x_l - V_r x_r), one CTA per node.
+__global__ void __launch_bounds__(256) k_cr_back(BaDev d, CrArgs a, int level) {
+  __shared__ double s_z[kCrMaxN], s_xl[kCrMaxN], s_xr[kCrMaxN];
+  const LmState& st = *d.st;
+  if (st.done || st.solve_failed) return;
+  const int node = cr_node_at(level, blockIdx.x), n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, h = 1 << (level - 1);
+  const int l = node - h, r = node + h;
+  const bool has_l = l >= 1, has_r = r <= a.N;
+  for (int k = tid; k < n; k += 256) {
+    s_xl[k] = has_l ? cr_vec(a, CR_X, l)[k] : 0.0;
+    s_xr[k] = has_r ? cr_vec(a, CR_X, r)[k] : 0.0;
+  }
+  __syncthreads();
+  const double* __restrict__ Vl = cr_arr(a, CR_VL, node);
+  const double* __restrict__ Vr = cr_arr(a, CR_VR, node);
+  const double* __restrict__ y = cr_vec(a, CR_Y, node);
+  for (int k = warp; k < n; k += 8) {
+    double v = 0.0;
+    if (has_l) for (int j = lane; j < n; j += 32) v += Vl[(size_t)k * n + j] * s_xl[j];
+    double w = 0.0;
+    if (has_r) for (int j = lane; j < n; j += 32) w += Vr[(size_t)k * n + j] * s_xr[j];
+    v += w;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_z[k] = y[k] - v;
+  }
+  __syncthreads();
+  const double* __restrict__ Linv = cr_arr(a, CR_LINV, node);
+  double* x = cr_vec(a, CR_X, node);
+  const int b0 = (node - 1) * a.Wb;
+  for (int j = tid; j < n; j += 256) {
+    double v0 = 0.0, v1 = 0.0;
+    int k = j;
+    for (; k + 1 < n; k += 2) { v0 += Linv[(size_t)k * n + j] * s_z[k]; v1 += Linv[(size_t)(k + 1) * n + j] * s_z[k + 1]; }
+    if (k < n) v0 += Linv[(size_t)k * n + j] * s_z[k];
+    const double v = v0 + v1;
+    x[j] = v;
+    if (b0 + j / 6 < d.Kv) d.yc[6 * b0 + j] = v;
+  }
+}
+
+}  // namespace cmos

@@ -15,10 +15,14 @@ namespace ORB_SLAM2 {
 
 class CeresOptimizer {
  public:
-  // sizes of the per-thread engine; call once before the first solve if the defaults are too small
-  static void Configure(int max_keyframes, int max_points, int max_obs, int max_correspondences = 4096, int device = 0) {
+  // Sizes of the per-thread engine; call once before the first solve if the defaults are too small.
+  // max_pairs_per_obs sizes the co-observation pair lists (sum over points of L (L + 1) / 2 for track length L, divided by
+  // the observation count; 0 = the library default 8).  It is only the INITIAL size: cmos_ba_set_problem grows the lists
+  // when a graph with longer tracks arrives, so a dense local window or a global BA after many revisits does not throw.
+  static void Configure(int max_keyframes, int max_points, int max_obs, int max_correspondences = 4096, int device = 0,
+                        int max_pairs_per_obs = 0) {
     cmos_ba_params& p = params();
-    p.max_cams = max_keyframes; p.max_points = max_points; p.max_obs = max_obs; p.max_pairs_per_obs = 0;
+    p.max_cams = max_keyframes; p.max_points = max_points; p.max_obs = max_obs; p.max_pairs_per_obs = max_pairs_per_obs;
     p.max_pose_batch = 1; p.max_pose_corr = max_correspondences; p.device = device;
     release();
   }
@@ -146,24 +150,32 @@ class CeresOptimizer {
     return (eu * eu + ev * ev) * inv_sigma > thres;
   }
 
-  static void release() {
-    cmos_ba_t& h = slot();
-    if (h) { cmos_ba_destroy(h); h = nullptr; }
-  }
+  // Destroys the calling thread's engine now.  It is also destroyed when the thread exits (the slot is an RAII holder), so
+  // the reference's pattern of one std::thread per global bundle adjustment (LoopClosing.cc:590) does not leak a handle —
+  // at 1000 keyframes that is a 288 MB reduced-system buffer per loop closure.
+  static void release() { slot().reset(); }
 
  private:
   static cmos_ba_params& params() {
     static cmos_ba_params p = {128, 16384, 131072, 0, 1, 4096, 0};
     return p;
   }
-  static cmos_ba_t& slot() {
-    static thread_local cmos_ba_t h = nullptr;
-    return h;
+  struct Engine {                       // owns one cmos_ba handle; thread_local, so its destructor runs at thread exit
+    cmos_ba_t h = nullptr;
+    Engine() {}
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+    ~Engine() { reset(); }
+    void reset() { if (h) { cmos_ba_destroy(h); h = nullptr; } }
+  };
+  static Engine& slot() {
+    static thread_local Engine e;
+    return e;
   }
   static cmos_ba_t ctx() {
-    cmos_ba_t& h = slot();
-    if (!h) cmos_throw_if(cmos_ba_create(&params(), &h), "CeresOptimizer engine");
-    return h;
+    Engine& e = slot();
+    if (!e.h) cmos_throw_if(cmos_ba_create(&params(), &e.h), "CeresOptimizer engine");
+    return e.h;
   }
 };
 

@@ -74,6 +74,58 @@ def test_global_bundle_adjustment_full_size_properties(monkeypatch):
     assert np.abs(c3 - c1).max() < 1e-7 and np.abs(p3 - p1).max() < 1e-5 * max(1.0, np.abs(p1).max())
 
 
+def test_global_bundle_adjustment_full_size_matches_oracle():
+    """configs[4] at FULL size (1000 keyframes x 100 000 points x 500 000 observations) against the CPU oracle, whose
+    reduced-camera solve factorises inside the row envelope (what CHOLMOD does for Ceres, CeresOptimizer.cc:178-187): same
+    iteration count and accept / reject sequence, per-iteration cost to 1e-9, poses and points to 1e-7 (north_star asks 1e-4).
+    The GPU solve is the nested-dissection (block cyclic reduction) Cholesky of csrc/band_cr.cuh."""
+    from oracle import pyoracle as po
+    G = synth.make_ba_problem_fast(1000, 100000, 5, seed=5)
+    K4 = np.array(synth.KITTI_K, np.float32)
+    iters = 5
+    opt = CeresOptimizer(max_cams=1000, max_points=100000, max_obs=500000)
+    cams, pts, s = opt.BundleAdjustment(G["poses"], G["fixed"], G["points"], G["obs_cam"], G["obs_pt"], G["uv"], G["inv_sigma2"],
+                                        K4, n_iterations=iters, is_robust=True)
+    tr = opt.trace(0, int(s["iterations"]) + 1)
+    opt.close()
+    oc, op_, os_, otr = po.ba_global(G["poses"], G["fixed"], G["points"], G["obs_cam"], G["obs_pt"], G["uv"], G["inv_sigma2"],
+                                     G["K"], iters, True)
+    assert s["iterations"] == os_["iterations"] == iters and s["successful_steps"] == os_["successful_steps"]
+    n = os_["iterations"] + 1
+    assert np.abs(tr[:n, 0] / otr[:n, 0] - 1).max() < 1e-9, "per-iteration cost"
+    assert np.abs(cams - oc).max() / max(1.0, np.abs(oc).max()) < 1e-7
+    assert np.abs(pts - op_).max() / max(1.0, np.abs(op_).max()) < 1e-7
+
+
+@pytest.mark.parametrize("n_cams,window", [(260, 10), (150, 4), (500, 12)])
+def test_global_bundle_adjustment_cyclic_reduction_sizes(n_cams, window, monkeypatch):
+    """Nested-dissection solver at other band widths / node counts (W = 20, 8, 24 blocks; padded last node; node counts that
+    are not powers of two) against the oracle, and against the serial one-CTA band walk (CMOS_BA_BAND_SERIAL=1)."""
+    from oracle import pyoracle as po
+    G = synth.make_ba_problem_fast(n_cams, n_cams * 60, 5, seed=n_cams, window=window)
+    K4 = np.array(synth.KITTI_K, np.float32)
+
+    def solve():
+        opt = CeresOptimizer(max_cams=n_cams, max_points=n_cams * 60, max_obs=n_cams * 300)
+        cams, pts, s = opt.BundleAdjustment(G["poses"], G["fixed"], G["points"], G["obs_cam"], G["obs_pt"], G["uv"],
+                                            G["inv_sigma2"], K4, n_iterations=6, is_robust=True)
+        tr = opt.trace(0, int(s["iterations"]) + 1)
+        opt.close()
+        return cams, pts, s, tr
+
+    cams, pts, s, tr = solve()
+    oc, op_, os_, otr = po.ba_global(G["poses"], G["fixed"], G["points"], G["obs_cam"], G["obs_pt"], G["uv"], G["inv_sigma2"],
+                                     G["K"], 6, True)
+    assert s["iterations"] == os_["iterations"] and s["successful_steps"] == os_["successful_steps"]
+    n = os_["iterations"] + 1
+    assert np.abs(tr[:n, 0] / otr[:n, 0] - 1).max() < 1e-9
+    assert np.abs(cams - oc).max() < 1e-7 and np.abs(pts - op_).max() < 1e-6
+    monkeypatch.setenv("CMOS_BA_BAND_SERIAL", "1")
+    c2, p2, s2, t2 = solve()
+    assert (s2["iterations"], s2["successful_steps"]) == (s["iterations"], s["successful_steps"])
+    assert np.abs(c2 - cams).max() < 1e-8 and np.abs(p2 - pts).max() < 1e-8 * max(1.0, np.abs(pts).max())
+
+
 def test_extract_and_search_full_batch_properties():
     """configs[1] end to end at full size (64 ring-paired frames, th = 15): every match index is valid and used at most once
     per frame, the number of matched keypoints is the match count minus the re-assigned ones, matched descriptors are within TH_HIGH = 100 of
