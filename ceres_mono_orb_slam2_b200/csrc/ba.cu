@@ -2164,7 +2164,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
         }
         for (int l = ca.levels; l >= 1; l--) {
           const int cnt = ((ca.N >> (l - 1)) + 1) / 2;
-          k_cr_back<<<cnt, 256, 0, st>>>(d, ca, l);
+          k_cr_back<<<cnt, 32 * kCrBackWarps, 0, st>>>(d, ca, l);
           h->launches++;
         }
         k_cam_candidates<<<(d.K + 255) / 256, 256, 0, st>>>(d);

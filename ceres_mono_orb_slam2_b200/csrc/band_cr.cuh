@@ -97,13 +97,35 @@ __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, 
   double* T = P + (size_t)kPB * ps;                      // [n*n/4] scratch of the inverse
   __shared__ int s_fail;
   if (tid == 0) s_fail = 0;
-  const double* D0 = cr_arr(a, CR_D0, node);
-  const double* AccL = cr_arr(a, CR_ACCL, node);
-  const double* AccR = cr_arr(a, CR_ACCR, node);
-  for (int r = warp; r < n; r += nw) {
-    const size_t ro = (size_t)r * n;
-    double* Lr = L + r * (r + 1) / 2;
-    for (int c = lane; c <= r; c += 32) Lr[c] = (D0[ro + c] - AccL[ro + c]) - AccR[ro + c];
+  const double* __restrict__ D0 = cr_arr(a, CR_D0, node);
+  const double* __restrict__ AccL = cr_arr(a, CR_ACCL, node);
+  const double* __restrict__ AccR = cr_arr(a, CR_ACCR, node);
+#ifdef CMOS_CR_TIMING
+  long long tk[6]; tk[0] = clock64();
+#endif
+  // gather the lower triangle, flattened over its packed index so that every thread has 4 x 3 independent loads in flight
+  // (at level 1 nothing has been accumulated yet: the Acc arrays are all zero and are not read)
+  {
+    const int ne = n * (n + 1) / 2;
+    for (int e0 = tid; e0 < ne; e0 += 4 * kSolveThreads) {
+      double v[4]; int idx[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * kSolveThreads;
+        idx[u] = -1; v[u] = 0.0;
+        if (e < ne) {
+          int r = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+          while ((r + 1) * (r + 2) / 2 <= e) r++;
+          while (r * (r + 1) / 2 > e) r--;
+          const int c = e - r * (r + 1) / 2;
+          const size_t g = (size_t)r * n + c;
+          idx[u] = e;
+          v[u] = level == 1 ? D0[g] : (D0[g] - AccL[g]) - AccR[g];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (idx[u] >= 0) L[idx[u]] = v[u];
+    }
   }
   {
     const int b0 = (node - 1) * a.Wb;
@@ -116,8 +138,14 @@ __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, 
     }
   }
   __syncthreads();
+#ifdef CMOS_CR_TIMING
+  tk[1] = clock64();
+#endif
   packed_cholesky(L, P, n, ps, &s_fail);
   __syncthreads();
+#ifdef CMOS_CR_TIMING
+  tk[2] = clock64();
+#endif
   if (s_fail) {                                          // not positive definite: the LM step is invalid
     if (tid == 0) st.solve_failed = 1;
     return;
@@ -150,6 +178,9 @@ __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, 
     }
     __syncthreads();
   }
+#ifdef CMOS_CR_TIMING
+  tk[3] = clock64();
+#endif
   double* Linv = cr_arr(a, CR_LINV, node);
   for (int r = warp; r < n; r += nw) {
     const double* Lr = L + r * (r + 1) / 2;
@@ -157,6 +188,12 @@ __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, 
   }
   double* y = cr_vec(a, CR_Y, node);
   for (int k = tid; k < n; k += kSolveThreads) y[k] = L[n * (n + 1) / 2 + k];
+#ifdef CMOS_CR_TIMING
+  tk[4] = clock64();
+  if (tid == 0 && blockIdx.x == 0 && st.iteration == 1)
+    printf("k_cr_factor level %d n %d: gather %lld potrf %lld inverse %lld store %lld cycles\n", level, n, tk[1] - tk[0],
+           tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -283,15 +320,19 @@ __global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur(BaDev d, CrArgs 
     }
 }
 
-// Back substitution of one level: x_i = L^-T (y_i - V_l x_l - V_r x_r), one CTA per node.
-__global__ void __launch_bounds__(256) k_cr_back(BaDev d, CrArgs a, int level) {
+// Back substitution of one level: x_i = L^-T (y_i - V_l x_l - V_r x_r), one CTA per node.  Both products are matrix-vector
+// products over rows that are independent of each other: a warp takes four rows per step so that 16-40 loads per lane are in
+// flight (the first version walked row by row and was latency bound at 90 us per level).
+constexpr int kCrBackWarps = 16;
+__global__ void __launch_bounds__(32 * kCrBackWarps) k_cr_back(BaDev d, CrArgs a, int level) {
   __shared__ double s_z[kCrMaxN], s_xl[kCrMaxN], s_xr[kCrMaxN];
+  __shared__ double s_part[kCrBackWarps][kCrMaxN];
   const LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
   const int node = cr_node_at(level, blockIdx.x), n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, h = 1 << (level - 1);
   const int l = node - h, r = node + h;
   const bool has_l = l >= 1, has_r = r <= a.N;
-  for (int k = tid; k < n; k += 256) {
+  for (int k = tid; k < n; k += 32 * kCrBackWarps) {
     s_xl[k] = has_l ? cr_vec(a, CR_X, l)[k] : 0.0;
     s_xr[k] = has_r ? cr_vec(a, CR_X, r)[k] : 0.0;
   }
@@ -299,26 +340,58 @@ __global__ void __launch_bounds__(256) k_cr_back(BaDev d, CrArgs a, int level) {
   const double* __restrict__ Vl = cr_arr(a, CR_VL, node);
   const double* __restrict__ Vr = cr_arr(a, CR_VR, node);
   const double* __restrict__ y = cr_vec(a, CR_Y, node);
-  for (int k = warp; k < n; k += 8) {
-    double v = 0.0;
-    if (has_l) for (int j = lane; j < n; j += 32) v += Vl[(size_t)k * n + j] * s_xl[j];
-    double w = 0.0;
-    if (has_r) for (int j = lane; j < n; j += 32) w += Vr[(size_t)k * n + j] * s_xr[j];
-    v += w;
+  constexpr int kCols = (kCrMaxN + 31) / 32;               // column groups per lane
+  for (int k0 = 4 * warp; k0 < n; k0 += 4 * kCrBackWarps) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) s_z[k] = y[k] - v;
+    for (int u = 0; u < kCols; u++) {
+      const int j = lane + 32 * u;
+      if (j < n) {
+        const double xl = s_xl[j], xr = s_xr[j];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int k = min(k0 + q, n - 1);
+          const double vl = has_l ? Vl[(size_t)k * n + j] : 0.0;
+          const double vr = has_r ? Vr[(size_t)k * n + j] : 0.0;
+          acc[q] += vl * xl + vr * xr;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    }
+    if (lane < 4 && k0 + lane < n) {
+      const double v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+      s_z[k0 + lane] = y[k0 + lane] - v;
+    }
   }
   __syncthreads();
+  // x[j] = sum_{k >= j} Linv[k][j] z[k]: warp w takes rows k = w, w + 16, ..., lanes the columns; partial sums per warp
   const double* __restrict__ Linv = cr_arr(a, CR_LINV, node);
+  {
+    double part[kCols];
+#pragma unroll
+    for (int u = 0; u < kCols; u++) part[u] = 0.0;
+    for (int k = warp; k < n; k += kCrBackWarps) {
+      const double zk = s_z[k];
+#pragma unroll
+      for (int u = 0; u < kCols; u++) {
+        const int j = lane + 32 * u;
+        if (j <= k) part[u] += Linv[(size_t)k * n + j] * zk;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kCols; u++) { const int j = lane + 32 * u; if (j < n) s_part[warp][j] = part[u]; }
+  }
+  __syncthreads();
   double* x = cr_vec(a, CR_X, node);
   const int b0 = (node - 1) * a.Wb;
-  for (int j = tid; j < n; j += 256) {
-    double v0 = 0.0, v1 = 0.0;
-    int k = j;
-    for (; k + 1 < n; k += 2) { v0 += Linv[(size_t)k * n + j] * s_z[k]; v1 += Linv[(size_t)(k + 1) * n + j] * s_z[k + 1]; }
-    if (k < n) v0 += Linv[(size_t)k * n + j] * s_z[k];
-    const double v = v0 + v1;
+  for (int j = tid; j < n; j += 32 * kCrBackWarps) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kCrBackWarps; w++) v += s_part[w][j];
     x[j] = v;
     if (b0 + j / 6 < d.Kv) d.yc[6 * b0 + j] = v;
   }

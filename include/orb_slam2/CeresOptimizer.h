@@ -51,6 +51,102 @@ class CeresOptimizer {
                   "CeresOptimizer::LocalBundleAdjustment");
   }
 
+  // ---- graph collection (host only, no device call: testable without a GPU) --------------------------------------------
+  // LocalBundleAdjustment(keyframe, stop_flag, map), CeresOptimizer.cc:349-406 and :421-502:
+  //   local keyframes  = the keyframe, then GetVectorCovisibleKeyFrames() that are not bad (a bad neighbour is still MARKED
+  //                      local, :358-359, so it can never become a fixed keyframe);
+  //   local map points = non-null, non-bad GetMapPointMatches() of the local keyframes, first occurrence wins (:374-378);
+  //   fixed keyframes  = observers of local points that are neither marked local nor already marked fixed, if not bad (:394-401);
+  //   residual blocks  = per local point every observation whose keyframe is not bad and is local or fixed (:433, :460, :483);
+  //   constant         = fixed keyframes, and keyframe id 0 (:476-481).
+  // Where the reference iterates an unordered_map / map keyed by pointer, this uses first-insertion order.
+  static void CollectLocalGraph(const MapView& m, int keyframe, CollectedGraph& out) {
+    out = CollectedGraph();
+    std::vector<int> kf_row(m.n_keyframes, -1), pt_row(m.n_points, -1);
+    std::vector<uint8_t> marked_local(m.n_keyframes, 0), marked_fixed(m.n_keyframes, 0);
+    auto add_keyframe = [&](int k, bool local) {
+      kf_row[k] = (int)out.keyframe_index.size();
+      out.keyframe_index.push_back(k);
+      out.pose7.insert(out.pose7.end(), m.keyframe_pose7 + 7 * (size_t)k, m.keyframe_pose7 + 7 * (size_t)k + 7);
+      out.flags.push_back((uint8_t)((local ? 0 : 2) | ((!local || m.keyframe_id[k] == 0) ? 1 : 0)));
+    };
+    add_keyframe(keyframe, true);
+    marked_local[keyframe] = 1;
+    for (size_t i = 0; i < m.covisible[keyframe].size(); i++) {
+      const int nb = m.covisible[keyframe][i];
+      const bool first = !marked_local[nb];
+      marked_local[nb] = 1;
+      if (!m.keyframe_bad[nb] && first) add_keyframe(nb, true);
+    }
+    const int n_local = (int)out.keyframe_index.size();
+    for (int r = 0; r < n_local; r++) {
+      const std::vector<int>& pts = m.keyframe_points[out.keyframe_index[r]];
+      for (size_t i = 0; i < pts.size(); i++) {
+        const int p = pts[i];
+        if (p < 0 || m.point_bad[p] || pt_row[p] >= 0) continue;
+        pt_row[p] = (int)out.point_index.size();
+        out.point_index.push_back(p);
+        out.point_pos.insert(out.point_pos.end(), m.point_pos + 3 * (size_t)p, m.point_pos + 3 * (size_t)p + 3);
+      }
+    }
+    for (size_t r = 0; r < out.point_index.size(); r++) {
+      const std::vector<std::pair<int, int> >& obs = m.observations[out.point_index[r]];
+      for (size_t o = 0; o < obs.size(); o++) {
+        const int k = obs[o].first;
+        if (marked_local[k] || marked_fixed[k]) continue;
+        marked_fixed[k] = 1;
+        if (!m.keyframe_bad[k]) add_keyframe(k, false);
+      }
+    }
+    add_observations(m, kf_row, 0, false, out);
+  }
+
+  // BundleAdjustment(map->GetAllKeyFrames(), map->GetAllMapPoints(), ...), CeresOptimizer.cc:53-57, 88-175: every keyframe
+  // that is not bad (id 0 constant, :115-120), every map point that is not bad and keeps at least one observation by a
+  // non-bad keyframe with id <= the largest id among them (:141, :168-173 removes points without edges).
+  static void CollectGlobalGraph(const MapView& m, CollectedGraph& out) {
+    out = CollectedGraph();
+    std::vector<int> kf_row(m.n_keyframes, -1);
+    unsigned long max_id = 0;
+    for (int k = 0; k < m.n_keyframes; k++) {
+      if (m.keyframe_bad[k]) continue;
+      kf_row[k] = (int)out.keyframe_index.size();
+      out.keyframe_index.push_back(k);
+      out.pose7.insert(out.pose7.end(), m.keyframe_pose7 + 7 * (size_t)k, m.keyframe_pose7 + 7 * (size_t)k + 7);
+      out.flags.push_back(m.keyframe_id[k] == 0 ? 1 : 0);
+      max_id = std::max(max_id, m.keyframe_id[k]);
+    }
+    for (int p = 0; p < m.n_points; p++) {
+      if (m.point_bad[p]) continue;
+      out.point_index.push_back(p);
+      out.point_pos.insert(out.point_pos.end(), m.point_pos + 3 * (size_t)p, m.point_pos + 3 * (size_t)p + 3);
+    }
+    add_observations(m, kf_row, max_id, true, out);
+  }
+
+  // Write-back of LocalBundleAdjustment (CeresOptimizer.cc:567-598): the (keyframe, map point) pairs to erase on both
+  // sides (EraseMapPointMatch / EraseObservation), the local keyframes' poses (SetPose) and the local points' positions
+  // (SetWorldPos + UpdateNormalAndDepth), all as map indices.  Fixed keyframes are not written.
+  struct LocalResult {
+    std::vector<std::pair<int, int> > erase;               // (map keyframe index, map point index)
+    std::vector<int> keyframes, points;                    // map indices, rows of pose7 / pos below
+    std::vector<double> pose7, pos;
+  };
+  static LocalResult CollectLocalResult(const CollectedGraph& c, const GraphView& g) {
+    LocalResult r;
+    for (int o = 0; o < g.n_obs; o++)
+      if (!g.erase.empty() && g.erase[o])
+        r.erase.push_back(std::make_pair(c.keyframe_index[c.obs_keyframe[o]], c.point_index[c.obs_point[o]]));
+    for (size_t k = 0; k < c.keyframe_index.size(); k++) {
+      if (c.flags[k] & 2) continue;
+      r.keyframes.push_back(c.keyframe_index[k]);
+      r.pose7.insert(r.pose7.end(), c.pose7.begin() + 7 * k, c.pose7.begin() + 7 * k + 7);
+    }
+    r.points = c.point_index;
+    r.pos = c.point_pos;
+    return r;
+  }
+
   // returns n_initial_correspondences - n_bad (CeresOptimizer.cc:341); fills frame.is_outlier, updates frame.pose7
   static int PoseOptimization(FramePoseView* frame) {
     frame->is_outlier.assign(frame->n, 0);
@@ -156,6 +252,36 @@ class CeresOptimizer {
   static void release() { slot().reset(); }
 
  private:
+  // residual blocks in the reference's order: per collected point, its GetObservations() in map order.  Points that end
+  // up without any block are dropped (global: RemoveParameterBlock, :168-170; local: such a point has no residual either).
+  static void add_observations(const MapView& m, const std::vector<int>& kf_row, unsigned long max_id, bool use_max_id,
+                               CollectedGraph& out) {
+    std::vector<int> keep_index;
+    std::vector<double> keep_pos;
+    for (size_t r = 0; r < out.point_index.size(); r++) {
+      const int p = out.point_index[r];
+      const std::vector<std::pair<int, int> >& obs = m.observations[p];
+      int n_edges = 0;
+      for (size_t o = 0; o < obs.size(); o++) {
+        const int k = obs[o].first, kp = obs[o].second;
+        if (m.keyframe_bad[k] || kf_row[k] < 0) continue;
+        if (use_max_id && m.keyframe_id[k] > max_id) continue;
+        const KeyPoint& u = m.undistort_keypoints[k][kp];
+        out.obs_keyframe.push_back(kf_row[k]);
+        out.obs_point.push_back((int32_t)keep_index.size());
+        out.obs_keypoint.push_back(kp);
+        out.obs_uv.push_back(u.x); out.obs_uv.push_back(u.y);
+        out.obs_inv_sigma2.push_back(m.inv_level_sigma2[k][u.octave]);
+        n_edges++;
+      }
+      if (n_edges == 0) continue;
+      keep_index.push_back(p);
+      keep_pos.insert(keep_pos.end(), out.point_pos.begin() + 3 * r, out.point_pos.begin() + 3 * r + 3);
+    }
+    out.point_index.swap(keep_index);
+    out.point_pos.swap(keep_pos);
+  }
+
   static cmos_ba_params& params() {
     static cmos_ba_params p = {128, 16384, 131072, 0, 1, 4096, 0};
     return p;

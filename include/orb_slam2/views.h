@@ -127,6 +127,43 @@ struct GraphView {
   std::vector<uint8_t> erase;               // out (LocalBA): observations to erase from the map
 };
 
+// The map as LocalBundleAdjustment(keyframe, stop_flag, map) and GlobalBundleAdjustemnt(map, ...) walk it
+// (CeresOptimizer.cc:53-57, 349-406): keyframes and map points by index with the accessors those functions call.
+struct MapView {
+  int n_keyframes = 0, n_points = 0;
+  std::vector<unsigned long> keyframe_id;                  // id_
+  std::vector<uint8_t> keyframe_bad;                       // isBad()
+  const double* keyframe_pose7 = nullptr;                  // n_keyframes x 7: Matrix4dToMatrix_7_1(GetPose())
+  std::vector<std::vector<int> > covisible;                // GetVectorCovisibleKeyFrames(), indices, in its order
+  std::vector<std::vector<int> > keyframe_points;          // GetMapPointMatches(): per keypoint a point index or -1
+  std::vector<const KeyPoint*> undistort_keypoints;        // undistort_keypoints_ of every keyframe
+  std::vector<const float*> inv_level_sigma2;              // inv_level_sigma2s_ of every keyframe
+  std::vector<uint8_t> point_bad;                          // isBad()
+  const double* point_pos = nullptr;                       // n_points x 3: GetWorldPos()
+  std::vector<std::vector<std::pair<int, int> > > observations;   // GetObservations(): (keyframe index, keypoint index)
+  float K4[4];                                             // fx_, fy_, cx_, cy_ (one camera)
+};
+
+// A bundle-adjustment problem collected from a MapView: owns the arrays a GraphView points at, and remembers which map
+// keyframe / point every graph row is, so the result can be written back (SetPose / SetWorldPos / erase lists).
+struct CollectedGraph {
+  std::vector<int> keyframe_index, point_index;            // graph row -> map index
+  std::vector<double> pose7, point_pos;
+  std::vector<uint8_t> flags;                              // bit0 constant, bit1 not a local keyframe
+  std::vector<int32_t> obs_keyframe, obs_point;            // graph rows
+  std::vector<int> obs_keypoint;                           // keypoint index of the observation in its keyframe
+  std::vector<float> obs_uv, obs_inv_sigma2;
+  GraphView view(const float K4[4]) {
+    GraphView g;
+    g.n_keyframes = (int)keyframe_index.size(); g.n_points = (int)point_index.size(); g.n_obs = (int)obs_keyframe.size();
+    g.keyframe_pose7 = pose7.data(); g.keyframe_flags = flags.data(); g.point_pos = point_pos.data();
+    g.obs_keyframe = obs_keyframe.data(); g.obs_point = obs_point.data(); g.obs_uv = obs_uv.data();
+    g.obs_inv_sigma2 = obs_inv_sigma2.data();
+    for (int k = 0; k < 4; k++) g.K4[k] = K4[k];
+    return g;
+  }
+};
+
 // Sophus::Sim3d as scale(), rotationMatrix() (row-major), translation() — 13 doubles, the layout the C ABI reads.
 struct Sim3POD {
   double s = 1.0;

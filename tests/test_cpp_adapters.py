@@ -60,3 +60,32 @@ def test_essential_graph_edge_collection_follows_the_reference_order(tmp_path):
         (6, 7, 1), (5, 7, 1),                        # keyframe 7: parent 6; (0,7) already inserted; co-visible 5
     ]
     assert got == expected, got
+
+
+def test_ba_graph_collection_follows_the_reference(tmp_path):
+    """CeresOptimizer::CollectLocalGraph / CollectGlobalGraph / CollectLocalResult (host logic of the adapter) on a map worked
+    out by hand against CeresOptimizer.cc:349-406, 421-502, 567-598 (local) and :88-175 (global): the current keyframe and
+    its non-bad co-visible keyframes are local (a bad neighbour is marked local and can never become fixed); keyframe id 0
+    is local but constant; observers of local points that are not local become fixed; bad points / bad keyframes are
+    skipped; a point whose observers are all skipped is dropped."""
+    exe = os.path.join(str(tmp_path), "ba_graph_collect")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", os.path.join(ROOT, "tests", "cpp", "ba_graph_collect.cpp"),
+                    "-o", exe, "-L" + LIBDIR, "-lcmos_b200", "-Wl,-rpath," + LIBDIR], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    got = {" ".join(l.split()[:2]): l.split()[2:] for l in out}
+    # local: keyframe 2 (current), 1, 0 (id 0 -> constant, flag 1); bad 3 skipped; fixed (flag 3): 4 (reached through local
+    # point 2) then 5 (through point 1), the order in which the local points' observations reach them
+    assert got["local keyframes"] == ["2:0", "1:0", "0:1", "4:3", "5:3"]
+    # local points in first-seen order over the local keyframes' GetMapPointMatches(): kf2 -> 2, 0, (4 bad), 3; kf1 -> 1; kf0 -> -
+    assert got["local points"] == ["2", "0", "3", "1"]
+    assert got["local obs"] == [
+        "(1,2,101,10,0.5)", "(2,2,200,0,1)", "(4,2,400,0,1)",         # point 2: keyframes 1, 2, 4
+        "(0,0,0,0,1)", "(2,0,201,10,0.5)",                            # point 0: keyframes 0, 2
+        "(2,3,203,30,0.5)", "(4,3,401,10,0.5)",                       # point 3: keyframe 3 is bad
+        "(0,1,1,10,0.5)", "(1,1,100,0,1)", "(5,1,500,0,1)"]           # point 1: keyframes 0, 1, 5
+    assert got["result erase"] == ["(2,2)", "(5,1)"]
+    assert got["result keyframes"] == ["2", "1", "0"] and got["result points"] == ["2", "0", "3", "1"]
+    # global: all non-bad keyframes in map order, id 0 constant; point 4 bad; point 5 keeps its observation by keyframe 6
+    assert got["global keyframes"] == ["0:1", "1:0", "2:0", "4:0", "5:0", "6:0"]
+    assert got["global points"] == ["0", "1", "2", "3", "5", "6"]
+    assert len(got["global obs"]) == 2 + 3 + 3 + 2 + 1 + 1 and got["global obs"][-2:] == ["(6,5,600,0,1)", "(5,6,501,10,0.5)"]
