@@ -757,25 +757,9 @@ __device__ __forceinline__ void load_jp_scaled(const BaDev& d, int p, int j, dou
   Jp[0] = v0.x * s0; Jp[1] = v0.y * s1; Jp[2] = v1.x * s2; Jp[3] = v1.y * s0; Jp[4] = v2.x * s1; Jp[5] = v2.y * s2;
 }
 
-// CTA (4 warps) per non-zero block (a,b), a <= b (variable-keyframe indices): threads stride over the block's
-// observation pairs, warp shuffles + a fixed-order cross-warp sum reduce the 6x6 (+ rhs); writes the
-// lower-triangle copy S[b][a].
-constexpr int kSchurThreads = 128;
-__global__ void __launch_bounds__(kSchurThreads) k_schur(BaDev d) {
-  __shared__ double s_part[kSchurThreads / 32][42];
-  const LmState& st = *d.st;
-  if (st.done) return;
-  const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int a = d.blk_a[blk], b = d.blk_b[blk];
-  double sca[6], scb[6];
-#pragma unroll
-  for (int k = 0; k < 6; k++) { sca[k] = d.scale_c[6 * (size_t)a + k]; scb[k] = d.scale_c[6 * (size_t)b + k]; }
-  double acc[36], racc[6];
-#pragma unroll
-  for (int k = 0; k < 36; k++) acc[k] = 0.0;
-#pragma unroll
-  for (int k = 0; k < 6; k++) racc[k] = 0.0;
-  for (int e = d.blk_start[blk] + tid; e < d.blk_start[blk + 1]; e += kSchurThreads) {
+// One co-observation pair (pa, pb) of block (a, b): acc += Jc_a' (Jp_a Hpp^-1 Jp_b') Jc_b; the diagonal pair also feeds the rhs.
+__device__ __forceinline__ void schur_pair(const BaDev& d, const int e, const double* sca, const double* scb, double* acc,
+                                           double* racc) {
     const int pa = d.pair_a[e], pb = d.pair_b[e];
     const int j = d.o_pt[pa];
     double Jca[12], Jpa[6], Jpb[6], U[12];
@@ -813,7 +797,27 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(BaDev d) {
     for (int r = 0; r < 6; r++)
 #pragma unroll
       for (int c = 0; c < 6; c++) acc[r * 6 + c] += Jca[r] * U0[c] + Jca[6 + r] * U1[c];
-  }
+}
+
+// CTA (4 warps) per non-zero block (a,b), a <= b (variable-keyframe indices): threads stride over the block's
+// observation pairs, warp shuffles + a fixed-order cross-warp sum reduce the 6x6 (+ rhs); writes the
+// lower-triangle copy S[b][a].
+constexpr int kSchurThreads = 128;
+__global__ void __launch_bounds__(kSchurThreads) k_schur(BaDev d) {
+  __shared__ double s_part[kSchurThreads / 32][42];
+  const LmState& st = *d.st;
+  if (st.done) return;
+  const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int a = d.blk_a[blk], b = d.blk_b[blk];
+  double sca[6], scb[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) { sca[k] = d.scale_c[6 * (size_t)a + k]; scb[k] = d.scale_c[6 * (size_t)b + k]; }
+  double acc[36], racc[6];
+#pragma unroll
+  for (int k = 0; k < 36; k++) acc[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; k++) racc[k] = 0.0;
+  for (int e = d.blk_start[blk] + tid; e < d.blk_start[blk + 1]; e += kSchurThreads) schur_pair(d, e, sca, scb, acc, racc);
 #pragma unroll
   for (int k = 0; k < 36; k++) {
     const double v = warp_sum(acc[k]);
@@ -848,6 +852,72 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(BaDev d) {
     for (int w = 0; w < kSchurThreads / 32; w++) v += s_part[w][36 + k];
     d.rhs[6 * a + k] = (d.is_root ? sca[k] * d.gc[6 * (size_t)a + k] : 0.0) - v;
   }
+}
+
+// WARP per non-zero block, for graphs with many blocks and few pairs per block (configs[4]: 21 k blocks x 71 pairs — with a
+// CTA per block half the threads had no pair and every warp still paid 42 five-step shuffle reductions).  Lanes stride over
+// the pairs; the 36 + 6 partial sums are combined by a REDUCE-SCATTER over the lanes (each step a lane keeps one half of
+// its values and receives the partner's partials of that half: 16 + 8 + 4 + 2 + 1 shuffles for 32 values instead of
+// 32 x 5), the remaining 4 + 6 values by butterflies.  Fixed order: repeated runs are bit-identical.
+constexpr int kSchurWarps = 4;
+__global__ void __launch_bounds__(32 * kSchurWarps) k_schur_warp(BaDev d) {
+  const LmState& st = *d.st;
+  if (st.done) return;
+  const int lane = threadIdx.x & 31, blk = blockIdx.x * kSchurWarps + (threadIdx.x >> 5);
+  if (blk >= d.n_blocks) return;
+  const int a = d.blk_a[blk], b = d.blk_b[blk];
+  double sca[6], scb[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) { sca[k] = d.scale_c[6 * (size_t)a + k]; scb[k] = d.scale_c[6 * (size_t)b + k]; }
+  double acc[36], racc[6];
+#pragma unroll
+  for (int k = 0; k < 36; k++) acc[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; k++) racc[k] = 0.0;
+  for (int e = d.blk_start[blk] + lane; e < d.blk_start[blk + 1]; e += 32) schur_pair(d, e, sca, scb, acc, racc);
+  // reduce-scatter of acc[0..31]: after the step with offset o a lane holds o values; lane L ends with the total of value
+  // index rev(L) where the bits of L select the halves: bit 4 -> +16, bit 3 -> +8, ...
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; i++) {
+      const double keep = up ? acc[o + i] : acc[i];
+      const double send = up ? acc[i] : acc[o + i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  const int mine = lane;                                 // value index held in acc[0]: bits of the lane, as selected above
+  double tail = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const double v = warp_sum(acc[32 + k]);
+    if (lane == k) tail = v;
+  }
+  double rs = 0.0;
+  if (a == b) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const double v = warp_sum(racc[k]);
+      if (lane == k) rs = v;
+    }
+  }
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    const int idx = pass == 0 ? mine : 32 + lane;
+    if (pass == 1 && lane >= 4) break;
+    const int r = idx / 6, c = idx - 6 * r;
+    double v = -(pass == 0 ? acc[0] : tail);
+    if (a == b && d.is_root) {
+      const double* Hc = d.Hcc + 21 * (size_t)a;
+      const int lo = r < c ? r : c, hi = r < c ? c : r;
+      const double h = sca[r] * sca[c] * Hc[SYM6(lo, hi)];
+      v += h;
+      if (r == c) v += fmin(fmax(h, kMinLmDiag), kMaxLmDiag) / st.radius;
+    }
+    d.Sblk[(size_t)blk * 36 + idx] = v;
+  }
+  if (a == b && lane < 6) d.rhs[6 * a + lane] = (d.is_root ? sca[lane] * d.gc[6 * (size_t)a + lane] : 0.0) - rs;
 }
 
 // candidate keyframe poses from the solved reduced system + the keyframes' share of the step statistics
@@ -2045,6 +2115,7 @@ struct cmos_ba {
   std::vector<int> pan_start, pan_first_col; // [n_panels + 1], [n_panels]
   size_t cap_pan_tiles = 0;
   int band_W = 0;                            // > 0: banded reduced system, solved by k_solve_band
+  bool schur_warp = false;                   // k_schur_warp instead of k_schur (average pairs per block <= 96)
   int cr_N = 0, cr_n = 0, cr_Wb = 0, cr_levels = 0;   // cr_N > 0: banded system solved by block cyclic reduction (band_cr.cuh)
   int* d_band_blk = nullptr;                 // [Kv][band_W + 1]
   double* d_trace = nullptr;       // [2][trace_rows][8]
@@ -2138,7 +2209,9 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
     k_point_prep<<<(d.M + kLinThreads - 1) / kLinThreads, kLinThreads, 0, st>>>(d);
     h->launches++;
     if (d.Kv > 0) {
-      k_schur<<<d.n_blocks, kSchurThreads, 0, st>>>(d);
+      // many small blocks (global BA): a warp per block; few large ones (local BA): a CTA per block
+      if (h->schur_warp) k_schur_warp<<<(d.n_blocks + kSchurWarps - 1) / kSchurWarps, 32 * kSchurWarps, 0, st>>>(d);
+      else k_schur<<<d.n_blocks, kSchurThreads, 0, st>>>(d);
       h->launches++;
       // the one exchange step of the sharded solve: partial reduced camera system + rhs summed over ranks
       if (multi && (rc = allreduce(d.Sblk, (size_t)d.n_blocks * 36 + d.nc, kNcclSum))) return rc;
@@ -2157,14 +2230,14 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
           k_cr_factor<<<cnt, kSolveThreads, cr_factor_smem(ca.n), st>>>(d, ca, l);
           h->launches++;
           if (l < ca.levels) {
-            k_cr_spike<<<dim3(tile_ctas, 2, cnt), 32 * kCrGemmWarps, 0, st>>>(d, ca, l);
+            k_cr_spike<<<dim3(ca.n / kCrSlab, 2, cnt), kCrSpikeThreads, cr_spike_smem(ca.n), st>>>(d, ca, l);
             k_cr_schur<<<dim3(tile_ctas, 4, cnt), 32 * kCrGemmWarps, 0, st>>>(d, ca, l);
             h->launches += 2;
           }
         }
         for (int l = ca.levels; l >= 1; l--) {
           const int cnt = ((ca.N >> (l - 1)) + 1) / 2;
-          k_cr_back<<<cnt, 32 * kCrBackWarps, 0, st>>>(d, ca, l);
+          k_cr_back<<<cnt, 32 * kCrBackWarps, cr_back_smem(ca.n), st>>>(d, ca, l);
           h->launches++;
         }
         k_cam_candidates<<<(d.K + 255) / 256, 256, 0, st>>>(d);
@@ -2281,6 +2354,8 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
   cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
   cudaFuncSetAttribute(k_solve_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
   cudaFuncSetAttribute(k_cr_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cr_factor_smem(kCrMaxN));
+  cudaFuncSetAttribute(k_cr_spike, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cr_spike_smem(kCrMaxN));
+  cudaFuncSetAttribute(k_cr_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cr_back_smem(kCrMaxN));
   cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
   cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
   cudaFuncSetAttribute(k_syrk_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
@@ -2581,6 +2656,12 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
   d.ticket = (unsigned int*)(h->d_red + 8);
   d.Hcc = h->d_HG; d.gc = h->d_HG + 21 * (size_t)Kv;
   d.Sblk = h->d_Sblk; d.rhs = h->d_Sblk + (size_t)nb * 36;
+  {
+    const char* force = std::getenv("CMOS_BA_SCHUR");   // "warp" / "cta": A/B runs
+    h->schur_warp = nb > 0 && n_pairs <= (size_t)96 * nb;
+    if (force && force[0] == 'w') h->schur_warp = true;
+    if (force && force[0] == 'c') h->schur_warp = false;
+  }
   d.multi = h->n_ranks > 1; d.is_root = h->rank == 0;
   const int nlb = (int)(((size_t)M * kPointLanes + kLinThreads - 1) / kLinThreads);
   d.n_lin_blocks = nlb;

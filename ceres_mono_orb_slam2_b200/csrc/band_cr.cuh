@@ -8,6 +8,8 @@
 //     D_i = L L',  y_i = L^-1 b_i,  V_l = L^-1 S_il,  V_r = L^-1 S_ir                       (k_cr_factor, k_cr_spike)
 //     S_ll -= V_l' V_l,  S_rr -= V_r' V_r,  S_lr = -V_l' V_r,  b_l -= V_l' y_i,  b_r -= V_r' y_i   (k_cr_schur)
 // and, from the last level back to the first,  x_i = L^-T (y_i - V_l x_l - V_r x_r)            (k_cr_back).
+// L^-1 is never formed: V = L^-1 S and x = L^-T z are blocked substitutions against the packed factor (a first version
+// inverted L explicitly by pairwise merging; that cost 88 k cycles per node, more than the factorisation itself).
 // This is a Cholesky factorisation in nested-dissection order: the pivot chain is log2(N) dense n x n factorisations
 // (6 x 120 pivots at configs[4]) instead of 6 Kv = 6000.  Every accumulation has one writer and a fixed order, so repeated
 // solves are bit-identical.  The dense products run on the fp64 tensor cores (mma.sync m8n8k4, SASS DMMA).
@@ -17,7 +19,8 @@
 //   AccL  sum of V_r' V_r of the nodes eliminated on i's LEFT  (i was their right neighbour)
 //   AccR  sum of V_l' V_l of the nodes eliminated on i's RIGHT (i was their left neighbour)
 //   Ep    S_{i,i-1} from Sblk (rows of i, columns of i-1)
-//   Linv  L_i^-1 (dense lower triangular, zeros above)
+//   Lp    the packed factor of D_i as packed_cholesky leaves it: rows 0..n-1 at r (r + 1) / 2, off-diagonal 6 x 6 blocks =
+//         L, diagonal blocks = the INVERSE of their Cholesky block (so substitutions are dot products, not divisions)
 //   Vl, Vr, Clr = V_l' V_r (rows of l, columns of r)
 // and vectors of N x n: bL, bR (like AccL / AccR), y, x.
 #pragma once
@@ -29,7 +32,7 @@ struct CrArgs {
   const int* band_blk;      // [Kv][W+1]: id of block (b - off, b), or -1
   double* base;
 };
-enum { CR_D0 = 0, CR_ACCL, CR_ACCR, CR_EP, CR_LINV, CR_VL, CR_VR, CR_CLR, CR_NARR };
+enum { CR_D0 = 0, CR_ACCL, CR_ACCR, CR_EP, CR_LP, CR_VL, CR_VR, CR_CLR, CR_NARR };
 enum { CR_BL = 0, CR_BR, CR_Y, CR_X, CR_NVEC };
 
 __host__ __device__ inline size_t cr_doubles(int N, int n) { return (size_t)N * n * ((size_t)CR_NARR * n + CR_NVEC); }
@@ -41,9 +44,14 @@ __device__ __forceinline__ double* cr_vec(const CrArgs& a, int k, int node) {
 }
 __device__ __forceinline__ int cr_node_at(int level, int t) { return (1 << (level - 1)) * (2 * t + 1); }
 
+// Node i, eliminated at `level`, has received contributions from its left side at every level below (the node i - 2^(k-1)
+// always exists) and from its right side iff node i + 1 exists; the first contribution of either side comes at level 1.
+__device__ __forceinline__ bool cr_has_acc_left(int level) { return level >= 2; }
+__device__ __forceinline__ bool cr_has_acc_right(const CrArgs& a, int node, int level) { return level >= 2 && node < a.N; }
+
 constexpr int kCrMaxN = 144;            // 6 * kBandMaxW
 inline size_t cr_factor_smem(int n) {
-  return ((size_t)(n + 1) * (n + 2) / 2 + (size_t)kPB * (n + 2) + (size_t)n * n / 4 + 8) * sizeof(double);
+  return ((size_t)(n + 1) * (n + 2) / 2 + (size_t)kPB * (n + 2) + 8) * sizeof(double);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -53,14 +61,10 @@ __global__ void __launch_bounds__(256) k_cr_assemble(BaDev d, CrArgs a) {
   if (st.done || st.solve_failed) return;
   const int node = blockIdx.x + 1, tid = threadIdx.x, n = a.n, n2 = n * n;
   double* D0 = cr_arr(a, CR_D0, node);
-  double* AccL = cr_arr(a, CR_ACCL, node);
-  double* AccR = cr_arr(a, CR_ACCR, node);
   double* Ep = cr_arr(a, CR_EP, node);
+  // (AccL / AccR / bL / bR need no clearing: their first contribution, at level 1, is a plain store — cr_has_acc)
   const double2 z2 = make_double2(0.0, 0.0);
-  for (int e = tid; e < n2 / 2; e += 256) {
-    ((double2*)D0)[e] = z2; ((double2*)AccL)[e] = z2; ((double2*)AccR)[e] = z2; ((double2*)Ep)[e] = z2;
-  }
-  for (int e = tid; e < n; e += 256) { cr_vec(a, CR_BL, node)[e] = 0.0; cr_vec(a, CR_BR, node)[e] = 0.0; }
+  for (int e = tid; e < n2 / 2; e += 256) { ((double2*)D0)[e] = z2; ((double2*)Ep)[e] = z2; }
   __syncthreads();
   const int b0 = (node - 1) * a.Wb, NB = a.W + 1;
   for (int e = tid; e < a.Wb * NB * 36; e += 256) {
@@ -84,27 +88,26 @@ __global__ void __launch_bounds__(256) k_cr_assemble(BaDev d, CrArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Factor one node per CTA: gather D and b, packed Cholesky in shared memory (the rhs rides as row n), explicit inverse of
-// the factor by pairwise merging of diagonal segments ([[A,0],[B,C]]^-1 = [[A^-1,0],[-C^-1 B A^-1, C^-1]]), results to HBM.
+// Factor one node per CTA: gather D and b, packed Cholesky in shared memory (the rhs rides as row n and leaves as y), the
+// packed factor and y to HBM.
 __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, int level) {
   extern __shared__ __align__(16) double smem_d[];
   LmState& st = *d.st;
   if (st.done || st.solve_failed) return;                // (k_point_prep raises solve_failed for a singular point block)
-  const int node = cr_node_at(level, blockIdx.x), n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nw = kSolveThreads / 32, ps = n + 2, nb = n / 6;
+  const int node = cr_node_at(level, blockIdx.x), n = a.n, tid = threadIdx.x;
+  const int ps = n + 2;
   double* L = smem_d;
   double* P = L + (size_t)(n + 1) * (n + 2) / 2;
-  double* T = P + (size_t)kPB * ps;                      // [n*n/4] scratch of the inverse
   __shared__ int s_fail;
   if (tid == 0) s_fail = 0;
   const double* __restrict__ D0 = cr_arr(a, CR_D0, node);
   const double* __restrict__ AccL = cr_arr(a, CR_ACCL, node);
   const double* __restrict__ AccR = cr_arr(a, CR_ACCR, node);
+  const bool hl = cr_has_acc_left(level), hr = cr_has_acc_right(a, node, level);
 #ifdef CMOS_CR_TIMING
   long long tk[6]; tk[0] = clock64();
 #endif
   // gather the lower triangle, flattened over its packed index so that every thread has 4 x 3 independent loads in flight
-  // (at level 1 nothing has been accumulated yet: the Acc arrays are all zero and are not read)
   {
     const int ne = n * (n + 1) / 2;
     for (int e0 = tid; e0 < ne; e0 += 4 * kSolveThreads) {
@@ -120,7 +123,8 @@ __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, 
           const int c = e - r * (r + 1) / 2;
           const size_t g = (size_t)r * n + c;
           idx[u] = e;
-          v[u] = level == 1 ? D0[g] : (D0[g] - AccL[g]) - AccR[g];
+          const double al = hl ? AccL[g] : 0.0, ar = hr ? AccR[g] : 0.0;
+          v[u] = (D0[g] - al) - ar;
         }
       }
 #pragma unroll
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, 
     for (int k = tid; k < n; k += kSolveThreads) {
       const int cam = b0 + k / 6;
       const double r0 = cam < d.Kv ? d.rhs[6 * b0 + k] : 0.0;
-      L[n * (n + 1) / 2 + k] = (r0 - bL[k]) - bR[k];
+      L[n * (n + 1) / 2 + k] = (r0 - (hl ? bL[k] : 0.0)) - (hr ? bR[k] : 0.0);
     }
   }
   __syncthreads();
@@ -150,49 +154,16 @@ __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, 
     if (tid == 0) st.solve_failed = 1;
     return;
   }
-  // explicit inverse M = L^-1.  Segments of s = 1, 2, 4, ... blocks; A = [2ks, (2k+1)s), C = [(2k+1)s, min((2k+2)s, nb)).
-  for (int s = 1; s < nb; s *= 2) {
-    const int np = (nb + s - 1) / (2 * s);               // pairs whose C part is not empty: (2k + 1) s < nb
-    const int pe = 36 * s * s, sa = 6 * s;
-    // T = L_CA * M_AA   (rows of C, columns of A; M_AA lower triangular)
-    for (int e = tid; e < np * pe; e += kSolveThreads) {
-      const int pr = e / pe, rem = e - pr * pe, r = rem / sa, j = rem - r * sa;
-      const int a0 = 6 * (2 * pr * s), c0 = a0 + sa, c1 = min(c0 + sa, n);
-      if (c0 + r >= c1) continue;
-      const double* Lrow = L + (c0 + r) * (c0 + r + 1) / 2 + a0;
-      double v = 0.0;
-      for (int k = j; k < sa; k++) v += Lrow[k] * L[(a0 + k) * (a0 + k + 1) / 2 + a0 + j];
-      T[(size_t)pr * pe + rem] = v;
-    }
-    __syncthreads();
-    // M_CA = -M_CC * T, written over L_CA (phase 1 is done reading it; M_CC and T are not written in this phase)
-    for (int e = tid; e < np * pe; e += kSolveThreads) {
-      const int pr = e / pe, rem = e - pr * pe, r = rem / sa, j = rem - r * sa;
-      const int a0 = 6 * (2 * pr * s), c0 = a0 + sa, c1 = min(c0 + sa, n);
-      if (c0 + r >= c1) continue;
-      const double* Mrow = L + (c0 + r) * (c0 + r + 1) / 2 + c0;
-      const double* Tc = T + (size_t)pr * pe + j;
-      double v = 0.0;
-      for (int k = 0; k <= r; k++) v += Mrow[k] * Tc[k * sa];
-      L[(c0 + r) * (c0 + r + 1) / 2 + a0 + j] = -v;
-    }
-    __syncthreads();
-  }
-#ifdef CMOS_CR_TIMING
-  tk[3] = clock64();
-#endif
-  double* Linv = cr_arr(a, CR_LINV, node);
-  for (int r = warp; r < n; r += nw) {
-    const double* Lr = L + r * (r + 1) / 2;
-    for (int c = lane; c < n; c += 32) Linv[(size_t)r * n + c] = c <= r ? Lr[c] : 0.0;
-  }
+  double2* Lp = (double2*)cr_arr(a, CR_LP, node);
+  const int ne2 = (n * (n + 1) / 2 + 1) / 2;             // packed triangle, in double2 (n (n + 1) / 2 is even for n % 4 == 0)
+  for (int e = tid; e < ne2; e += kSolveThreads) Lp[e] = ((const double2*)L)[e];
   double* y = cr_vec(a, CR_Y, node);
   for (int k = tid; k < n; k += kSolveThreads) y[k] = L[n * (n + 1) / 2 + k];
 #ifdef CMOS_CR_TIMING
-  tk[4] = clock64();
+  tk[3] = clock64();
   if (tid == 0 && blockIdx.x == 0 && st.iteration == 1)
-    printf("k_cr_factor level %d n %d: gather %lld potrf %lld inverse %lld store %lld cycles\n", level, n, tk[1] - tk[0],
-           tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3]);
+    printf("k_cr_factor level %d n %d: gather %lld potrf %lld store %lld cycles\n", level, n, tk[1] - tk[0], tk[2] - tk[1],
+           tk[3] - tk[2]);
 #endif
 }
 
@@ -239,37 +210,65 @@ __device__ __forceinline__ CrCoupling cr_coupling(const CrArgs& a, int node, int
   return c;
 }
 
-// V_side = L^-1 S_{i,side}: grid (tile groups, side, node), one warp per 24 x 24 tile of V.
+// V_side = L^-1 S_{i,side} by blocked forward substitution: grid (column slabs of 24, side, node).  The CTA holds the packed
+// factor and its 24-column slab of S in shared memory; block row p = 0 .. n/6 - 1:
+//   W = S_p - sum_{q < p} L_pq X_q   (thread = (row in block, column), dot products of length 6 p)
+//   X_p = inv(L_pp) W                (the diagonal block is stored inverted)
 constexpr int kCrGemmWarps = 4;
-__global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_spike(BaDev d, CrArgs a, int level) {
+constexpr int kCrSlab = 24;
+constexpr int kCrSpikeThreads = 6 * kCrSlab;              // 144
+inline size_t cr_spike_smem(int n) { return ((size_t)n * (n + 1) / 2 + (size_t)n * kCrSlab + 6 * kCrSlab) * sizeof(double); }
+__global__ void __launch_bounds__(kCrSpikeThreads) k_cr_spike(BaDev d, CrArgs a, int level) {
+  extern __shared__ __align__(16) double smem_d[];
   const LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
-  const int node = cr_node_at(level, blockIdx.z), side = blockIdx.y, n = a.n, nt = n / 24;
+  const int node = cr_node_at(level, blockIdx.z), side = blockIdx.y, n = a.n, nb = n / 6, tid = threadIdx.x;
   const int nbr = side ? node + (1 << (level - 1)) : node - (1 << (level - 1));
   if (nbr < 1 || nbr > a.N) return;
-  const int tile = blockIdx.x * kCrGemmWarps + (threadIdx.x >> 5);
-  if (tile >= nt * nt) return;
-  const int r0 = 24 * (tile / nt), j0 = 24 * (tile % nt);
+  const int j0 = kCrSlab * blockIdx.x;
+  double* L = smem_d;                                    // packed factor
+  double* X = L + (size_t)n * (n + 1) / 2;               // [n][24] the slab, solved in place
+  double* Wb = X + (size_t)n * kCrSlab;                  // [6][24]
   const CrCoupling cp = cr_coupling(a, node, level, side);
-  const double* __restrict__ Linv = cr_arr(a, CR_LINV, node);
-  const double* __restrict__ src = cp.src;
-  CrTile t;
-  if (cp.trans)
-    cr_tile_mma(t, 0, r0 + 24,
-                [&](int r, int k) { return __ldg(Linv + (size_t)(r0 + r) * n + k); },
-                [&](int k, int c) { return __ldg(src + (size_t)(j0 + c) * n + k); });
-  else
-    cr_tile_mma(t, 0, r0 + 24,
-                [&](int r, int k) { return __ldg(Linv + (size_t)(r0 + r) * n + k); },
-                [&](int k, int c) { return __ldg(src + (size_t)k * n + j0 + c); });
+  {
+    const double2* __restrict__ Lp = (const double2*)cr_arr(a, CR_LP, node);
+    const int ne2 = (n * (n + 1) / 2 + 1) / 2;
+    for (int e = tid; e < ne2; e += kCrSpikeThreads) ((double2*)L)[e] = Lp[e];
+    const double* __restrict__ src = cp.src;
+    if (cp.trans) {        // S[k][j0 + c] = sign * src[j0 + c][k]: consecutive threads walk k
+      for (int e = tid; e < n * kCrSlab; e += kCrSpikeThreads) {
+        const int c = e / n, k = e - c * n;
+        X[k * kCrSlab + c] = cp.sign * src[(size_t)(j0 + c) * n + k];
+      }
+    } else {
+      for (int e = tid; e < n * kCrSlab; e += kCrSpikeThreads) {
+        const int k = e / kCrSlab, c = e - k * kCrSlab;
+        X[e] = cp.sign * src[(size_t)k * n + j0 + c];
+      }
+    }
+  }
+  __syncthreads();
+  const int i = tid / kCrSlab, c = tid - i * kCrSlab;     // row inside the block, column of the slab
+  for (int p = 0; p < nb; p++) {
+    const int row = 6 * p + i;
+    const double* Lrow = L + row * (row + 1) / 2;
+    double v0 = X[row * kCrSlab + c], v1 = 0.0;
+    int k = 0;
+    for (; k + 1 < 6 * p; k += 2) { v0 -= Lrow[k] * X[k * kCrSlab + c]; v1 -= Lrow[k + 1] * X[(k + 1) * kCrSlab + c]; }
+    Wb[i * kCrSlab + c] = v0 + v1;
+    __syncthreads();
+    double x = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; q++)
+      if (q <= i) x += Lrow[6 * p + q] * Wb[q * kCrSlab + c];     // inverse of the diagonal Cholesky block
+    X[row * kCrSlab + c] = x;
+    __syncthreads();
+  }
   double* V = cr_arr(a, side ? CR_VR : CR_VL, node);
-  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-#pragma unroll
-  for (int mi = 0; mi < 3; mi++)
-#pragma unroll
-    for (int ni = 0; ni < 3; ni++)
-      *(double2*)(V + (size_t)(r0 + 8 * mi + g) * n + j0 + 8 * ni + 2 * q) =
-          make_double2(cp.sign * t.c[mi][ni][0], cp.sign * t.c[mi][ni][1]);
+  for (int e = tid; e < n * kCrSlab; e += kCrSpikeThreads) {
+    const int k = e / kCrSlab, cc = e - k * kCrSlab;
+    V[(size_t)k * n + j0 + cc] = X[e];
+  }
 }
 
 // Schur products of an eliminated node: grid (tile groups, product, node).
@@ -293,7 +292,7 @@ __global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur(BaDev d, CrArgs 
       double v = 0.0;
       for (int k = 0; k < n; k++) v += V[(size_t)k * n + c] * y[k];
       double* dst = sd ? cr_vec(a, CR_BL, r) : cr_vec(a, CR_BR, l);
-      dst[c] += v;
+      dst[c] = level == 1 ? v : dst[c] + v;               // the first contribution of a side is a store (no clearing pass)
     }
     return;
   }
@@ -315,23 +314,30 @@ __global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur(BaDev d, CrArgs 
 #pragma unroll
     for (int ni = 0; ni < 3; ni++) {
       double2* o = (double2*)(dst + (size_t)(p0 + 8 * mi + g) * n + q0 + 8 * ni + 2 * q);
-      if (prod == 2) *o = make_double2(t.c[mi][ni][0], t.c[mi][ni][1]);
+      if (prod == 2 || level == 1) *o = make_double2(t.c[mi][ni][0], t.c[mi][ni][1]);
       else { const double2 old = *o; *o = make_double2(old.x + t.c[mi][ni][0], old.y + t.c[mi][ni][1]); }
     }
 }
 
-// Back substitution of one level: x_i = L^-T (y_i - V_l x_l - V_r x_r), one CTA per node.  Both products are matrix-vector
-// products over rows that are independent of each other: a warp takes four rows per step so that 16-40 loads per lane are in
-// flight (the first version walked row by row and was latency bound at 90 us per level).
+// Back substitution of one level, one CTA per node: z = y_i - V_l x_l - V_r x_r (rows are independent: a warp takes four
+// rows per step so that 16-40 loads per lane are in flight), then L' x = z by blocked substitution against the packed
+// factor in shared memory, from the last block up (right-looking: x_p = inv(L_pp)' z_p, then z_q -= L_pq' x_p for q < p).
 constexpr int kCrBackWarps = 16;
+inline size_t cr_back_smem(int n) { return ((size_t)n * (n + 1) / 2 + 2) * sizeof(double); }
 __global__ void __launch_bounds__(32 * kCrBackWarps) k_cr_back(BaDev d, CrArgs a, int level) {
-  __shared__ double s_z[kCrMaxN], s_xl[kCrMaxN], s_xr[kCrMaxN];
-  __shared__ double s_part[kCrBackWarps][kCrMaxN];
+  extern __shared__ __align__(16) double smem_d[];
+  __shared__ double s_z[kCrMaxN], s_xl[kCrMaxN], s_xr[kCrMaxN], s_x[kCrMaxN];
   const LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
-  const int node = cr_node_at(level, blockIdx.x), n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, h = 1 << (level - 1);
-  const int l = node - h, r = node + h;
+  const int node = cr_node_at(level, blockIdx.x), n = a.n, nb = n / 6, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = 1 << (level - 1), l = node - h, r = node + h;
   const bool has_l = l >= 1, has_r = r <= a.N;
+  double* L = smem_d;
+  {
+    const double2* __restrict__ Lp = (const double2*)cr_arr(a, CR_LP, node);
+    const int ne2 = (n * (n + 1) / 2 + 1) / 2;
+    for (int e = tid; e < ne2; e += 32 * kCrBackWarps) ((double2*)L)[e] = Lp[e];
+  }
   for (int k = tid; k < n; k += 32 * kCrBackWarps) {
     s_xl[k] = has_l ? cr_vec(a, CR_X, l)[k] : 0.0;
     s_xr[k] = has_r ? cr_vec(a, CR_X, r)[k] : 0.0;
@@ -368,30 +374,27 @@ __global__ void __launch_bounds__(32 * kCrBackWarps) k_cr_back(BaDev d, CrArgs a
     }
   }
   __syncthreads();
-  // x[j] = sum_{k >= j} Linv[k][j] z[k]: warp w takes rows k = w, w + 16, ..., lanes the columns; partial sums per warp
-  const double* __restrict__ Linv = cr_arr(a, CR_LINV, node);
-  {
-    double part[kCols];
+  for (int p = nb - 1; p >= 0; p--) {
+    if (tid < 6) {                                         // x_p = inv(L_pp)' z_p: column tid of the inverted block
+      double x = 0.0;
 #pragma unroll
-    for (int u = 0; u < kCols; u++) part[u] = 0.0;
-    for (int k = warp; k < n; k += kCrBackWarps) {
-      const double zk = s_z[k];
-#pragma unroll
-      for (int u = 0; u < kCols; u++) {
-        const int j = lane + 32 * u;
-        if (j <= k) part[u] += Linv[(size_t)k * n + j] * zk;
-      }
+      for (int q = 0; q < 6; q++)
+        if (q >= tid) x += L[(6 * p + q) * (6 * p + q + 1) / 2 + 6 * p + tid] * s_z[6 * p + q];
+      s_x[6 * p + tid] = x;
     }
+    __syncthreads();
+    if (tid < 6 * p) {                                     // z_k -= sum_q L[6p + q][k] x[6p + q]
+      double v = 0.0;
 #pragma unroll
-    for (int u = 0; u < kCols; u++) { const int j = lane + 32 * u; if (j < n) s_part[warp][j] = part[u]; }
+      for (int q = 0; q < 6; q++) v += L[(6 * p + q) * (6 * p + q + 1) / 2 + tid] * s_x[6 * p + q];
+      s_z[tid] -= v;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   double* x = cr_vec(a, CR_X, node);
   const int b0 = (node - 1) * a.Wb;
   for (int j = tid; j < n; j += 32 * kCrBackWarps) {
-    double v = 0.0;
-#pragma unroll
-    for (int w = 0; w < kCrBackWarps; w++) v += s_part[w][j];
+    const double v = s_x[j];
     x[j] = v;
     if (b0 + j / 6 < d.Kv) d.yc[6 * b0 + j] = v;
   }

@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <list>
 #include <utility>
@@ -152,7 +153,19 @@ void fast_detect(const uint8_t* img, int w, int h, int pitch, int threshold, std
   std::vector<int> score((size_t)w * h, 0);
   for (int y = 3; y < h - 3; y++)
     for (int x = 3; x < w - 3; x++) {
-      int m = fast_arc_max(img + y * pitch + x, pitch);
+      // Early reject, exact: an arc of 9 of the 16 ring pixels contains at least one pixel of every opposite pair
+      // (k, k + 8), so a pair with both |ring - c| <= t rules the corner out.  OpenCV's FAST does the same kind of test
+      // before scoring; without it this CPU path (also the bench's CPU baseline) would score every pixel.
+      const uint8_t* p = img + y * pitch + x;
+      const int c = p[0];
+      bool reject = false;
+      for (int k = 0; k < 8 && !reject; k += 2) {          // pairs (0,8), (2,10), (4,12), (6,14) — the rest is left to the score
+        const int d0 = std::abs((int)p[kRingDy[k] * pitch + kRingDx[k]] - c);
+        const int d1 = std::abs((int)p[kRingDy[k + 8] * pitch + kRingDx[k + 8]] - c);
+        reject = d0 <= threshold && d1 <= threshold;
+      }
+      if (reject) continue;
+      int m = fast_arc_max(p, pitch);
       if (m > threshold) score[y * w + x] = m - 1;
     }
   for (int y = 3; y < h - 3; y++)
