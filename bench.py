@@ -86,6 +86,75 @@ def make_last_views(kps, desc, counts, offs, cap, seed):
     return lk, lcounts, flags, xw, mdesc, T
 
 
+def orb_source_hash():
+    """sha256 over the sources of the ORB / matcher kernels.  profiles/traffic.json records the hash of the tree it was
+    captured on; `roofline.traffic` is only reported when it matches the tree being benchmarked."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "ceres_mono_orb_slam2_b200", "csrc")
+    for f in ("orb.cu", "orb_device.cuh", "match.cu", "match_device.cuh", "cmos_common.h", "Makefile"):
+        with open(os.path.join(csrc, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def load_traffic():
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None, "profiles/traffic.json missing"
+    if t.get("_src_sha256") != orb_source_hash():
+        return None, ("profiles/traffic.json was captured on a different tree (kernel sources changed since): traffic "
+                      "withheld, regenerate with tools/gpu_round.sh + tools/make_traffic.py")
+    return t, t.get("_source")
+
+
+def configs0_line(device: int):
+    """BASELINE.json configs[0]: ORBextractor on one 640x480 frame, TUM2.yaml (1000 features) — the reference's own
+    CPU-runnable case.  One frame, one host thread for the CPU legs; the GPU leg is the same call through the C ABI with a
+    host image (upload + kernels + download)."""
+    from ceres_mono_orb_slam2_b200 import ORBextractor, synth
+    img = synth.make_image(640, 480, 11)
+    out = {"workload": "configs[0]: ORBextractor::operator() on one synthetic 640x480 frame, TUM2.yaml (1000 features, 8 levels, 1.2)"}
+
+    def best_of(fn, n):
+        best = None
+        for _ in range(n):
+            t0 = time.perf_counter(); r = fn(); dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return best, r
+
+    ext = ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=1, device=device)
+    ext(img)
+    dt, (k, _) = best_of(lambda: ext(img), 20)
+    out["b200"] = {"ms_per_frame": dt * 1e3, "features": int(len(k)), "value": len(k) / dt / 1e6, "unit": UNIT,
+                   "timing": "wall clock around the synchronous host-buffer call, best of 20"}
+    kind = cpu_kind()
+    if kind == "reference":
+        from oracle import pyref
+        cpu = pyref.RefOrbExtractor(1000, 1.2, 8, 20, 7)
+    else:
+        from oracle import pyoracle as po
+        cpu = po.OrbOracle(1000, 1.2, 8, 20, 7)
+    cpu.extract(img)
+    dt, (ck, cd) = best_of(lambda: cpu.extract(img), 5)
+    out["cpu"] = {"ms_per_frame": dt * 1e3, "features": int(len(ck)), "value": len(ck) / dt / 1e6, "unit": UNIT, "cores": 1,
+                  "kind": kind, "equal_to_b200": bool(len(ck) == len(k) and np.array_equal(ck, k))}
+    try:    # cross-check number: OpenCV's own cv::ORB (SIMD FAST, Harris ranking — a different selection rule, so only the
+        import cv2    # time is comparable, not the keypoints)
+        cv2.setNumThreads(1)
+        orb = cv2.ORB_create(nfeatures=1000, scaleFactor=1.2, nlevels=8, edgeThreshold=19, fastThreshold=20)
+        orb.detectAndCompute(img, None)
+        dt, (kk, _) = best_of(lambda: orb.detectAndCompute(img, None), 5)
+        out["cv2_orb_cross_check"] = {"ms_per_frame": dt * 1e3, "features": len(kk), "cores": 1,
+                                      "note": "cv2.ORB_create(1000, 1.2, 8).detectAndCompute, OpenCV %s, one thread: OpenCV's "
+                                              "SIMD implementation of the same family of steps (different keypoint "
+                                              "selection), for scale only" % cv2.__version__}
+    except Exception as e:   # cv2 is test-time tooling; the bench does not depend on it
+        out["cv2_orb_cross_check"] = {"unavailable": str(e)[:100]}
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------
 # Clock sampling during the timed region
 
@@ -166,14 +235,32 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # CPU arm: the restated reference path (oracle/) on the host cores
 
+def cpu_kind():
+    """"reference": ORBextractor::operator() is the reference's OWN source (src/ORBextractor.cc, unmodified, compiled into
+    oracle/_ref/libref.so against the OpenCV stand-in whose five image primitives are the cv2-pinned restatements);
+    "port": the restatement in oracle/orb_oracle.cpp.  SearchByProjection is the oracle port in both cases (a few ms per frame
+    next to ~65 ms of extraction)."""
+    try:
+        from oracle import pyref
+        pyref.lib()
+        return "reference"
+    except Exception:
+        return "port"
+
+
 def cpu_orb_throughput(n_frames: int, threads: int, seed: int, repeats: int = 1):
-    """Extract + SearchByProjection(cur,last) of `n_frames` frames with the CPU oracle, `threads` frames in
-    flight.  Returns (Mfeat/s, seconds per pass, features per pass)."""
+    """Extract + SearchByProjection(cur,last) of `n_frames` frames on the host cores, `threads` frames in flight: the
+    reference's own ORBextractor (oracle/_ref) when it is built, else the oracle port.
+    Returns (Mfeat/s, seconds per pass, features per pass)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import pyoracle as po
     from ceres_mono_orb_slam2_b200 import synth
     frames, offs = make_batch(n_frames, seed)
-    oracles = [po.OrbOracle(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH) for _ in range(threads)]
+    if cpu_kind() == "reference":
+        from oracle import pyref
+        oracles = [pyref.RefOrbExtractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH) for _ in range(threads)]
+    else:
+        oracles = [po.OrbOracle(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH) for _ in range(threads)]
     sfs = oracles[0].scale_factors
     bounds6 = np.array([0.0, W, 0.0, H, np.float32(64) / np.float32(W), np.float32(48) / np.float32(H)], np.float32)
     K4 = np.array(synth.KITTI_K, np.float32)
@@ -227,15 +314,20 @@ def cpu_ba_baseline():
     out["pose_optimization"] = {"value": 1500 * (s["iterations"] + 1) / best / 1e6, "ms_per_solve": best * 1e3,
                                 "sample": "configs[2], best of 5"}
     G = synth.make_ba_problem(20, 3000, 4, seed=4)
-    best = None
-    for _ in range(3):
-        t0 = time.perf_counter()
-        _, _, _, ss = po.ba_local(G["poses"], G["fixed"], G["points"], G["obs_cam"], G["obs_pt"], G["uv"], G["inv_sigma2"],
-                                  G["K"])
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    ev = 12000 * sum(x["iterations"] + 1 for x in ss)
-    out["local_ba"] = {"value": ev / best / 1e6, "ms_per_solve": best * 1e3, "sample": "configs[3], best of 3"}
+    for threads, key in ((1, "local_ba"), (4, "local_ba_4_threads")):     # the reference sets num_threads = 4 (CeresOptimizer.cc:516)
+        po.lib().ba_oracle_set_threads(threads)
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            _, _, _, ss = po.ba_local(G["poses"], G["fixed"], G["points"], G["obs_cam"], G["obs_pt"], G["uv"], G["inv_sigma2"],
+                                      G["K"])
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        ev = 12000 * sum(x["iterations"] + 1 for x in ss)
+        out[key] = {"value": ev / best / 1e6, "ms_per_solve": best * 1e3, "cores": threads,
+                    "sample": "configs[3], best of 3" + ("" if threads == 1 else
+                                                         "; residual / Jacobian evaluation on 4 threads, Schur + solve on one")}
+    po.lib().ba_oracle_set_threads(1)
     G = synth.make_essential_graph_problem(1000, seed=8, n_group=10, covis=(2, 3, 5), n_points=100000)
     best = None
     for _ in range(2):
@@ -273,12 +365,13 @@ def run_reference(args):
         "config": {"workload": "configs[1]: ORB extract + SearchByProjection(cur,last,th=15), KITTI00-02 "
                                "(1241x376, 2000 feat, 8 levels)",
                    "step": f"bounded sample: {sample} frames of the 64-frame batch per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
                          "sample": f"{sample} frames x {args.steps} steps, {cores} threads (one frame per thread)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the reference's own C++ (OpenCV + Ceres) cannot be built in this image; this arm times the CPU "
-                "restatement in oracle/ (bit-identical to OpenCV 4.13 semantics)",
+        "note": "ORBextractor::operator() is the reference's own src/ORBextractor.cc compiled unmodified into oracle/_ref "
+                "(OpenCV's five image primitives behind it are scalar restatements pinned bit-exact to cv2 4.13, FAST with the "
+                "usual early reject); SearchByProjection is the oracle port; one frame per host thread",
     }
     emit(json.dumps(line))
 
@@ -421,18 +514,22 @@ def run_b200(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         alg = algorithmic_bytes_per_frame(feats_per_step / B)
         stage_avg = {k: v / max(orb_calls, 1) for k, v in orb_ms.items()}
+        orb_ms_extra = {}
         for k, (v, c) in match_ms.items():
             if c:
                 stage_avg[k] = v / c
         dom = max(stage_avg, key=stage_avg.get)
         dom_ms = stage_avg[dom]
         achieved = alg[dom] * B / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
-        except Exception:
-            pass
+        traffic_all, traffic_src = load_traffic()
+        traffic = traffic_all.get(dom) if traffic_all else None
         step_ms = ms_max / args.steps
+        # largest SINGLE kernel (the stage roofline above can span several launches: pyramid = 8, search_frame = 2)
+        single = {"fast": "k_fast", "blur": "k_blur", "describe": "k_describe", "quadtree": "k_octree", "grid": "k_build_grid"}
+        if "pyramid_launches" in orb_ms_extra:
+            single["pyramid"] = "k_pyramid"
+        big = max((k for k in stage_avg if k in single), key=lambda k: stage_avg[k])
+        big_ach = alg[big] * B / (stage_avg[big] * 1e-3) / 1e9 if stage_avg[big] > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -445,7 +542,11 @@ def run_b200(args):
                              % ((B * (H * W) + 2 * B * 1738559) // 1000000),
                        "parallelism": f"frames sharded, {world} rank(s), no collective on the data path"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "largest_single_kernel": {"kernel": single[big], "stage": big, "kernel_ms": stage_avg[big],
+                                                   "algorithmic_bytes_per_launch": alg[big] * B, "achieved": big_ach,
+                                                   "frac": big_ach / peak,
+                                                   "traffic": traffic_all.get(big) if traffic_all else None},
                          "algorithmic_bytes_per_launch": alg[dom] * B, "kernel_ms": dom_ms,
                          "stage_ms": stage_avg, "stage_share": {k: v / step_ms for k, v in stage_avg.items()},
                          "whole_step": {"algorithmic_bytes": alg["frame_total"] * B,
@@ -468,14 +569,33 @@ def run_b200(args):
             cores = os.cpu_count() or 1
             n_s = B                       # the whole 64-frame batch of one GPU step: ~10-20 s of CPU work in two passes
             v, dt, _ = cpu_orb_throughput(n_s, cores, seed=1000, repeats=2)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
                                     "sample": f"{n_s} frames (one full step of the same workload), {cores} threads, best of 2 "
                                               f"({dt:.2f} s per pass, {2 * dt * cores:.0f} core-seconds)"}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"]["kind"] = cpu_kind()
+            line["configs0"] = configs0_line(local_rank)
         if not args.no_ba:
             from ceres_mono_orb_slam2_b200 import ba_bench
             line["ba"] = ba_bench.run(local_rank, world, args)
             if world == 1 and not args.no_cpu:
                 line["ba"]["cpu_baseline"] = cpu_ba_baseline()
+            # BASELINE.json's metric has two halves: the LocalBA half gets the same keys as the ORB half, at top level
+            lb = line["ba"].get("local_ba")
+            if lb:
+                sec = {"metric": "local_ba_mresid_per_s", "unit": "Mresid/s", "value": lb["value"], "ms_per_solve": lb["ms_per_solve"],
+                       "config": {"workload": lb["config"]}, "dtype": "f64", "e2e": lb["e2e"],
+                       "gpu_launches_per_solve": lb["gpu_launches_per_solve"],
+                       "roofline": {"bound": "hbm", "achieved": lb["roofline"]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                                    "frac": lb["roofline"]["achieved_gbs"] / peak, "traffic": None,
+                                    "algorithmic_bytes_per_eval": lb["roofline"]["algorithmic_bytes_per_eval"],
+                                    "note": "whole solve (98 launches), latency-bound: 120 unknowns, one SM factorises"}}
+                cb = line["ba"].get("cpu_baseline")
+                if cb:
+                    sec["cpu_baseline"] = {"value": cb["local_ba"]["value"], "unit": "Mresid/s", "cores": 1, "kind": "port",
+                                           "sample": cb["local_ba"]["sample"],
+                                           "four_threads": cb.get("local_ba_4_threads")}
+                line["secondary"] = {"local_ba": sec}
         emit(json.dumps(line))
     elif not args.no_ba:
         from ceres_mono_orb_slam2_b200 import ba_bench

@@ -494,6 +494,9 @@ struct BaDev {
   const int* pt_start;                      // [M+1]
   const int *cam_start, *cam_obs;           // [Kv+1], [#obs of variable keyframes]
   const int *blk_a, *blk_b, *blk_start;     // [n_blocks], [n_blocks], [n_blocks+1]
+  const int *chunk_start, *chunk_blk, *blk_chunk0;   // [n_chunks+1] pair ranges, [n_chunks] block of a chunk, [n_blocks+1]
+  double* schur_part;                       // [n_chunks][42] per-chunk partial sums of k_schur_chunks
+  int n_chunks;
   const int *pair_a, *pair_b;               // observation pairs of every block
   double *Jc, *Jp, *res;                    // [N][12], [N][6], [N][2]  (rows already weighted by sqrt(rho'))
   double *Hpp, *gp, *Hinv, *tp, *scale_p;   // [M][6], [M][3], [M][6], [M][3], [M][3]
@@ -504,6 +507,8 @@ struct BaDev {
   double* red;                              // [8] locally reduced scalars (all-reduced across ranks when multi)
   unsigned int* ticket;                     // [2] arrival counters of the fused reduce-and-decide tails (single GPU)
   int multi, is_root;                       // multi: points are sharded over ranks; is_root: adds the keyframe-only terms
+  int rank, n_ranks;
+  double* lin_tail;                         // multi: [cost, |x|^2, gmax slot per rank] behind H_cc / g_c in the same message
   double *part;                             // partial sums, see offsets
   int n_lin_blocks;
   // offsets into part
@@ -695,13 +700,25 @@ __device__ void post_lin_body(const BaDev& d, LmState& st, int phase, double* sc
     const double cost = part_sum(d.part + d.o_lin_cost, d.n_lin_blocks, scratch);
     const double x1 = part_sum(d.part + d.o_lin_xn2, d.n_lin_blocks, scratch);
     const double g1 = part_max(d.part + d.o_lin_gmax, d.n_lin_blocks, scratch);
-    if (threadIdx.x == 0) { d.red[0] = cost; d.red[1] = x1; d.red[2] = g1; }
+    if (threadIdx.x == 0) {
+      if (d.multi) {   // rides behind H_cc / g_c in ONE sum all-reduce: the max becomes a slot per rank
+        d.lin_tail[0] = cost; d.lin_tail[1] = x1;
+        for (int r = 0; r < d.n_ranks; r++) d.lin_tail[2 + r] = r == d.rank ? g1 : 0.0;
+      } else {
+        d.red[0] = cost; d.red[1] = x1; d.red[2] = g1;
+      }
+    }
     __syncthreads();
   }
   if (phase != 1) {
     const double g2 = part_max(d.part + d.o_cam_gmax, d.Kv, scratch);
     const double x2 = part_sum(d.part + d.o_cam_xn2, d.Kv, scratch);
     if (threadIdx.x == 0) {
+      if (d.multi) {
+        double g = 0.0;
+        for (int r = 0; r < d.n_ranks; r++) g = fmax(g, d.lin_tail[2 + r]);
+        d.red[0] = d.lin_tail[0]; d.red[1] = d.lin_tail[1]; d.red[2] = g;
+      }
       lm_after_linearize(st, d.red[0], fmax(d.red[2], g2), sqrt(d.red[1] + x2), d.trace);
       if (!st.done && d.stop_flag && *d.stop_flag) { st.done = 1; st.termination = TERM_USER; }   // StopFlagCallback
     }
@@ -710,7 +727,15 @@ __device__ void post_lin_body(const BaDev& d, LmState& st, int phase, double* sc
 __global__ void __launch_bounds__(256) k_post_lin(BaDev d, int phase) {
   __shared__ double scratch[33];
   LmState& st = *d.st;
-  if (st.done || !st.need_lin) return;
+  if (st.done) return;
+  if (!st.need_lin) {
+    // Rejected step: nothing was re-linearised, but the collective still runs.  The root's message buffer holds the
+    // totals of the last linearisation; every other rank contributes zeros so that the sum reproduces them (summing the
+    // already reduced buffers would multiply H_cc / g_c by the number of ranks).
+    if (phase == 1 && d.multi && !d.is_root)
+      for (int i = threadIdx.x; i < 27 * d.Kv + 2 + d.n_ranks; i += blockDim.x) d.Hcc[i] = 0.0;
+    return;
+  }
   post_lin_body(d, st, phase, scratch);
 }
 
@@ -854,17 +879,24 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(BaDev d) {
   }
 }
 
-// WARP per non-zero block, for graphs with many blocks and few pairs per block (configs[4]: 21 k blocks x 71 pairs — with a
-// CTA per block half the threads had no pair and every warp still paid 42 five-step shuffle reductions).  Lanes stride over
-// the pairs; the 36 + 6 partial sums are combined by a REDUCE-SCATTER over the lanes (each step a lane keeps one half of
-// its values and receives the partner's partials of that half: 16 + 8 + 4 + 2 + 1 shuffles for 32 values instead of
-// 32 x 5), the remaining 4 + 6 values by butterflies.  Fixed order: repeated runs are bit-identical.
+// Chunked Schur complement.  The pair lists of the blocks are very uneven (configs[4]: 500 pairs on a diagonal block, a
+// handful on the band's edge; with a warp or a CTA per block the diagonal blocks were a 16-round dependent-load chain that
+// set the kernel's duration while most warps had nothing to do).  A WARP takes one CHUNK of <= kSchurChunk pairs of one
+// block — one pair per lane per round — and the 36 + 6 partial sums are combined by a REDUCE-SCATTER over the lanes (each
+// step a lane keeps one half of its values and receives the partner's partials of that half: 16 + 8 + 4 + 2 + 1 shuffles
+// for 32 values instead of 32 x 5), the remaining 4 + 6 values by butterflies.  k_schur_combine then sums the chunks of a
+// block in chunk order and adds the keyframe-only terms.  Fixed order everywhere: repeated runs are bit-identical.
 constexpr int kSchurWarps = 4;
-__global__ void __launch_bounds__(32 * kSchurWarps) k_schur_warp(BaDev d) {
+constexpr int kSchurPart = 42;             // 36 block entries + 6 rhs entries per chunk
+#ifndef CMOS_SCHUR_MINB
+#define CMOS_SCHUR_MINB 1   // resident CTAs per SM the register allocation must allow (A/B: tools/build_variant.sh)
+#endif
+__global__ void __launch_bounds__(32 * kSchurWarps, CMOS_SCHUR_MINB) k_schur_chunks(BaDev d) {
   const LmState& st = *d.st;
   if (st.done) return;
-  const int lane = threadIdx.x & 31, blk = blockIdx.x * kSchurWarps + (threadIdx.x >> 5);
-  if (blk >= d.n_blocks) return;
+  const int lane = threadIdx.x & 31, chunk = blockIdx.x * kSchurWarps + (threadIdx.x >> 5);
+  if (chunk >= d.n_chunks) return;
+  const int blk = d.chunk_blk[chunk];
   const int a = d.blk_a[blk], b = d.blk_b[blk];
   double sca[6], scb[6];
 #pragma unroll
@@ -874,9 +906,9 @@ __global__ void __launch_bounds__(32 * kSchurWarps) k_schur_warp(BaDev d) {
   for (int k = 0; k < 36; k++) acc[k] = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; k++) racc[k] = 0.0;
-  for (int e = d.blk_start[blk] + lane; e < d.blk_start[blk + 1]; e += 32) schur_pair(d, e, sca, scb, acc, racc);
+  for (int e = d.chunk_start[chunk] + lane; e < d.chunk_start[chunk + 1]; e += 32) schur_pair(d, e, sca, scb, acc, racc);
   // reduce-scatter of acc[0..31]: after the step with offset o a lane holds o values; lane L ends with the total of value
-  // index rev(L) where the bits of L select the halves: bit 4 -> +16, bit 3 -> +8, ...
+  // index L (bit 4 of the lane selects +16, bit 3 +8, ...)
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) {
     const bool up = (lane & o) != 0;
@@ -887,37 +919,50 @@ __global__ void __launch_bounds__(32 * kSchurWarps) k_schur_warp(BaDev d) {
       acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
     }
   }
-  const int mine = lane;                                 // value index held in acc[0]: bits of the lane, as selected above
   double tail = 0.0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const double v = warp_sum(acc[32 + k]);
     if (lane == k) tail = v;
   }
-  double rs = 0.0;
   if (a == b) {
 #pragma unroll
     for (int k = 0; k < 6; k++) {
       const double v = warp_sum(racc[k]);
-      if (lane == k) rs = v;
+      if (lane == 4 + k) tail = v;
     }
   }
-#pragma unroll
-  for (int pass = 0; pass < 2; pass++) {
-    const int idx = pass == 0 ? mine : 32 + lane;
-    if (pass == 1 && lane >= 4) break;
+  double* out = d.schur_part + (size_t)chunk * kSchurPart;
+  out[lane] = acc[0];
+  if (lane < 10) out[32 + lane] = tail;
+}
+
+// thread per (block, entry): sums the block's chunk partials in chunk order, adds H_cc + D_c^2 / g_c on the diagonal
+__global__ void __launch_bounds__(256) k_schur_combine(BaDev d) {
+  const LmState& st = *d.st;
+  if (st.done) return;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int blk = t / 48, idx = t - 48 * blk;
+  if (blk >= d.n_blocks || idx >= kSchurPart) return;
+  const int a = d.blk_a[blk], b = d.blk_b[blk];
+  if (idx >= 36 && a != b) return;
+  double sum = 0.0;
+  for (int c = d.blk_chunk0[blk]; c < d.blk_chunk0[blk + 1]; c++) sum += d.schur_part[(size_t)c * kSchurPart + idx];
+  if (idx < 36) {
     const int r = idx / 6, c = idx - 6 * r;
-    double v = -(pass == 0 ? acc[0] : tail);
-    if (a == b && d.is_root) {
+    double v = -sum;
+    if (a == b && d.is_root) {   // keyframe-only terms are added once (by the root rank when points are sharded)
       const double* Hc = d.Hcc + 21 * (size_t)a;
       const int lo = r < c ? r : c, hi = r < c ? c : r;
-      const double h = sca[r] * sca[c] * Hc[SYM6(lo, hi)];
+      const double h = d.scale_c[6 * (size_t)a + r] * d.scale_c[6 * (size_t)a + c] * Hc[SYM6(lo, hi)];
       v += h;
       if (r == c) v += fmin(fmax(h, kMinLmDiag), kMaxLmDiag) / st.radius;
     }
     d.Sblk[(size_t)blk * 36 + idx] = v;
+  } else {
+    const int k = idx - 36;
+    d.rhs[6 * a + k] = (d.is_root ? d.scale_c[6 * (size_t)a + k] * d.gc[6 * (size_t)a + k] : 0.0) - sum;
   }
-  if (a == b && lane < 6) d.rhs[6 * a + lane] = (d.is_root ? sca[lane] * d.gc[6 * (size_t)a + lane] : 0.0) - rs;
 }
 
 // candidate keyframe poses from the solved reduced system + the keyframes' share of the step statistics
@@ -2115,7 +2160,10 @@ struct cmos_ba {
   std::vector<int> pan_start, pan_first_col; // [n_panels + 1], [n_panels]
   size_t cap_pan_tiles = 0;
   int band_W = 0;                            // > 0: banded reduced system, solved by k_solve_band
-  bool schur_warp = false;                   // k_schur_warp instead of k_schur (average pairs per block <= 96)
+  bool schur_chunked = true;                 // k_schur_chunks + k_schur_combine (default) or the CTA-per-block k_schur
+  int *d_chunk_start = nullptr, *d_chunk_blk = nullptr, *d_blk_chunk0 = nullptr;
+  double* d_schur_part = nullptr;
+  size_t cap_chunks = 0, cap_chunk_blocks = 0;
   int cr_N = 0, cr_n = 0, cr_Wb = 0, cr_levels = 0;   // cr_N > 0: banded system solved by block cyclic reduction (band_cr.cuh)
   int* d_band_blk = nullptr;                 // [Kv][band_W + 1]
   double* d_trace = nullptr;       // [2][trace_rows][8]
@@ -2190,13 +2238,10 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
       return CMOS_OK;
     }
     int rc;
-    if (d.Kv > 0) {
-      if ((rc = allreduce(h->d_HG, (size_t)27 * d.Kv, kNcclSum))) return rc;      // H_cc and g_c of every keyframe
-      k_cam_finish<<<(d.Kv + 127) / 128, 128, 0, st>>>(d);
-    }
     k_post_lin<<<1, 256, 0, st>>>(d, 1);
-    if ((rc = allreduce(d.red, 2, kNcclSum))) return rc;                          // cost, |x|^2
-    if ((rc = allreduce(d.red + 2, 1, kNcclMax))) return rc;                      // gradient max norm
+    // ONE message: H_cc and g_c of every keyframe, then cost, |x|^2 and the per-rank gradient-max slots
+    if ((rc = allreduce(h->d_HG, (size_t)27 * d.Kv + 2 + d.n_ranks, kNcclSum))) return rc;
+    if (d.Kv > 0) k_cam_finish<<<(d.Kv + 127) / 128, 128, 0, st>>>(d);
     k_post_lin<<<1, 256, 0, st>>>(d, 2);
     h->launches += 3;
     return CMOS_OK;
@@ -2209,10 +2254,14 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
     k_point_prep<<<(d.M + kLinThreads - 1) / kLinThreads, kLinThreads, 0, st>>>(d);
     h->launches++;
     if (d.Kv > 0) {
-      // many small blocks (global BA): a warp per block; few large ones (local BA): a CTA per block
-      if (h->schur_warp) k_schur_warp<<<(d.n_blocks + kSchurWarps - 1) / kSchurWarps, 32 * kSchurWarps, 0, st>>>(d);
-      else k_schur<<<d.n_blocks, kSchurThreads, 0, st>>>(d);
-      h->launches++;
+      if (h->schur_chunked) {
+        k_schur_chunks<<<(d.n_chunks + kSchurWarps - 1) / kSchurWarps, 32 * kSchurWarps, 0, st>>>(d);
+        k_schur_combine<<<(d.n_blocks * 48 + 255) / 256, 256, 0, st>>>(d);
+        h->launches += 2;
+      } else {
+        k_schur<<<d.n_blocks, kSchurThreads, 0, st>>>(d);
+        h->launches++;
+      }
       // the one exchange step of the sharded solve: partial reduced camera system + rhs summed over ranks
       if (multi && (rc = allreduce(d.Sblk, (size_t)d.n_blocks * 36 + d.nc, kNcclSum))) return rc;
       if (small) {
@@ -2230,7 +2279,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
           k_cr_factor<<<cnt, kSolveThreads, cr_factor_smem(ca.n), st>>>(d, ca, l);
           h->launches++;
           if (l < ca.levels) {
-            k_cr_spike<<<dim3(ca.n / kCrSlab, 2, cnt), kCrSpikeThreads, cr_spike_smem(ca.n), st>>>(d, ca, l);
+            k_cr_spike<<<dim3(ca.n / kCrSlab / cr_spike_warps(ca.n), 2, cnt), 32 * cr_spike_warps(ca.n), cr_spike_smem(ca.n), st>>>(d, ca, l);
             k_cr_schur<<<dim3(tile_ctas, 4, cnt), 32 * kCrGemmWarps, 0, st>>>(d, ca, l);
             h->launches += 2;
           }
@@ -2335,7 +2384,7 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
        alloc(&h->d_o_uv, N) && alloc(&h->d_o_w, N) && alloc(&h->d_o_mode, N) && alloc(&h->d_cam_flags, K) &&
        alloc(&h->d_erase, N);
   ok = ok && alloc(&d.Jc, 12 * N) && alloc(&d.Jp, 6 * N) && alloc(&d.res, 2 * N) && alloc(&d.Hpp, 6 * M) && alloc(&d.gp, 3 * M) &&
-       alloc(&d.Hinv, 6 * M) && alloc(&d.tp, 3 * M) && alloc(&d.scale_p, 3 * M) && alloc(&h->d_HG, 27 * K) &&
+       alloc(&d.Hinv, 6 * M) && alloc(&d.tp, 3 * M) && alloc(&d.scale_p, 3 * M) && alloc(&h->d_HG, 27 * K + 2 + 64) &&
        alloc(&h->d_var_cam, K) && alloc(&h->d_red, 16) && alloc(&h->d_Sblk, h->cap_blocks * 36 + 6 * K + 8) &&
        alloc(&d.scale_c, 6 * K) && alloc(&d.S, h->cap_S) &&
        alloc(&d.yc, 6 * K + 8) && alloc(&d.part, 6 * nlb + 4 * K + 16) && alloc(&d.st, 1) &&
@@ -2354,7 +2403,7 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
   cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
   cudaFuncSetAttribute(k_solve_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
   cudaFuncSetAttribute(k_cr_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cr_factor_smem(kCrMaxN));
-  cudaFuncSetAttribute(k_cr_spike, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cr_spike_smem(kCrMaxN));
+  cudaFuncSetAttribute(k_cr_spike, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_cr_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cr_back_smem(kCrMaxN));
   cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
   cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
@@ -2375,7 +2424,8 @@ int cmos_ba_destroy(cmos_ba_t h) {
                   h->d_blk_start, h->d_pair_a, h->d_pair_b, h->d_perm, h->d_o_uv, h->d_o_w, h->d_o_mode, h->d_cam_flags,
                   h->d_erase, d.Jc, d.Jp, d.res, d.Hpp, d.gp, d.Hinv, d.tp, d.scale_p, h->d_HG, h->d_var_cam, h->d_red, h->d_Sblk, d.scale_c, d.S,
                   d.yc, d.part, d.st, h->d_Linv, h->d_pan_tiles, h->d_pan_first, h->d_band_blk, h->d_trace, h->d_summaries, h->dp_pose, h->dp_xw, h->dp_uv, h->dp_w,
-                  h->dp_n, h->dp_inl, h->dp_out, h->dp_sum, h->dp_trace};
+                  h->dp_n, h->dp_inl, h->dp_out, h->dp_sum, h->dp_trace, h->d_chunk_start, h->d_chunk_blk, h->d_blk_chunk0,
+                  h->d_schur_part};
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (void* b : {(void*)h->ds_obs, (void*)h->ds_sig, (void*)h->ds_pts, (void*)h->ds_out, (void*)h->ds_bad})
@@ -2657,12 +2707,39 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
   d.Hcc = h->d_HG; d.gc = h->d_HG + 21 * (size_t)Kv;
   d.Sblk = h->d_Sblk; d.rhs = h->d_Sblk + (size_t)nb * 36;
   {
-    const char* force = std::getenv("CMOS_BA_SCHUR");   // "warp" / "cta": A/B runs
-    h->schur_warp = nb > 0 && n_pairs <= (size_t)96 * nb;
-    if (force && force[0] == 'w') h->schur_warp = true;
-    if (force && force[0] == 'c') h->schur_warp = false;
+    // chunks of <= chunk_pairs pairs, never across blocks.  One round (32 pairs) per warp unless that makes more than
+    // ~64 k warps; CMOS_BA_SCHUR=cta selects the CTA-per-block kernel (A/B runs).
+    const char* force = std::getenv("CMOS_BA_SCHUR");
+    h->schur_chunked = !(force && force[0] == 'c');
+    int chunk_pairs = 32;
+    while (n_pairs / chunk_pairs > 65536) chunk_pairs *= 2;
+    std::vector<int> chunk_start, chunk_blk, blk_chunk0(nb + 1, 0);
+    for (int i = 0; i < nb; i++) {
+      blk_chunk0[i] = (int)chunk_blk.size();
+      for (int e = blk_start[i]; e < blk_start[i + 1]; e += chunk_pairs) { chunk_start.push_back(e); chunk_blk.push_back(i); }
+    }
+    blk_chunk0[nb] = (int)chunk_blk.size();
+    chunk_start.push_back(nb > 0 ? blk_start[nb] : 0);
+    const size_t nch = chunk_blk.size();
+    if (nch > h->cap_chunks || (size_t)nb > h->cap_chunk_blocks) {
+      CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));
+      cudaFree(h->d_chunk_start); cudaFree(h->d_chunk_blk); cudaFree(h->d_blk_chunk0); cudaFree(h->d_schur_part);
+      h->d_chunk_start = h->d_chunk_blk = h->d_blk_chunk0 = nullptr; h->d_schur_part = nullptr;
+      h->cap_chunks = h->cap_chunk_blocks = 0;
+      const size_t wc = nch + nch / 4 + 16, wb = (size_t)nb + nb / 4 + 16;
+      CMOS_REQUIRE(alloc(&h->d_chunk_start, wc + 1) && alloc(&h->d_chunk_blk, wc) && alloc(&h->d_blk_chunk0, wb + 1) &&
+                   alloc(&h->d_schur_part, wc * kSchurPart), "cannot allocate the Schur chunk lists (%zu chunks)", nch);
+      h->cap_chunks = wc; h->cap_chunk_blocks = wb;
+    }
+    CMOS_CUDA_OK(up(h->d_chunk_start, chunk_start.data(), chunk_start.size() * sizeof(int)));
+    if (nch) CMOS_CUDA_OK(up(h->d_chunk_blk, chunk_blk.data(), nch * sizeof(int)));
+    CMOS_CUDA_OK(up(h->d_blk_chunk0, blk_chunk0.data(), blk_chunk0.size() * sizeof(int)));
+    CMOS_CUDA_OK(cudaStreamSynchronize(st));          // the host vectors above go out of scope
+    d.chunk_start = h->d_chunk_start; d.chunk_blk = h->d_chunk_blk; d.blk_chunk0 = h->d_blk_chunk0;
+    d.schur_part = h->d_schur_part; d.n_chunks = (int)nch;
   }
   d.multi = h->n_ranks > 1; d.is_root = h->rank == 0;
+  d.rank = h->rank; d.n_ranks = h->n_ranks; d.lin_tail = h->d_HG + 27 * (size_t)Kv;
   const int nlb = (int)(((size_t)M * kPointLanes + kLinThreads - 1) / kLinThreads);
   d.n_lin_blocks = nlb;
   int o = 0;
@@ -2798,7 +2875,7 @@ int cmos_ba_comm_unique_id(uint8_t* id128) {
 }
 
 int cmos_ba_comm_init(cmos_ba_t h, const uint8_t* id128, int32_t n_ranks, int32_t rank) {
-  CMOS_REQUIRE(h && id128 && n_ranks >= 1 && rank >= 0 && rank < n_ranks, "bad argument");
+  CMOS_REQUIRE(h && id128 && n_ranks >= 1 && n_ranks <= 64 && rank >= 0 && rank < n_ranks, "bad argument (1 <= n_ranks <= 64)");
   if (!g_nccl.load()) { set_error("NCCL (libnccl.so.2) is not available: %s", dlerror()); return CMOS_ERR_STATE; }
   CMOS_CUDA_OK(cudaSetDevice(h->p.device));
   if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }

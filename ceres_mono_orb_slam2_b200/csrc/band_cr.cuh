@@ -19,8 +19,8 @@
 //   AccL  sum of V_r' V_r of the nodes eliminated on i's LEFT  (i was their right neighbour)
 //   AccR  sum of V_l' V_l of the nodes eliminated on i's RIGHT (i was their left neighbour)
 //   Ep    S_{i,i-1} from Sblk (rows of i, columns of i-1)
-//   Lp    the packed factor of D_i as packed_cholesky leaves it: rows 0..n-1 at r (r + 1) / 2, off-diagonal 6 x 6 blocks =
-//         L, diagonal blocks = the INVERSE of their Cholesky block (so substitutions are dot products, not divisions)
+//   Lp    the packed factor of D_i: rows 0..n-1 at r (r + 1) / 2; blocks below the 24 x 24 diagonal blocks = L, the
+//         24 x 24 diagonal blocks = the INVERSE of their Cholesky block (substitutions are tile products, not divisions)
 //   Vl, Vr, Clr = V_l' V_r (rows of l, columns of r)
 // and vectors of N x n: bL, bR (like AccL / AccR), y, x.
 #pragma once
@@ -154,6 +154,35 @@ __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, 
     if (tid == 0) st.solve_failed = 1;
     return;
   }
+  // Invert the 24 x 24 diagonal Cholesky blocks in place ([[A,0],[B,C]]^-1 = [[A^-1,0],[-C^-1 B A^-1, C^-1]], 6 -> 12 -> 24;
+  // the 6 x 6 diagonal blocks are already stored inverted): the spike and back substitutions then run in 24-row block
+  // steps of tensor-core tile products instead of 6-row steps.  Scratch = the panel buffer (n / 24 pairs x 144 values).
+  {
+    const int nb = n / 6;
+    double* T = P;
+    for (int sb = 1; sb <= 2; sb *= 2) {
+      const int np = nb / (2 * sb), pe = 36 * sb * sb, sa = 6 * sb;
+      for (int e = tid; e < np * pe; e += kSolveThreads) {         // T = L_CA * M_AA
+        const int pr = e / pe, rem = e - pr * pe, r = rem / sa, j = rem - r * sa;
+        const int a0 = 6 * (2 * pr * sb), c0 = a0 + sa;
+        const double* Lrow = L + (c0 + r) * (c0 + r + 1) / 2 + a0;
+        double v = 0.0;
+        for (int k = j; k < sa; k++) v += Lrow[k] * L[(a0 + k) * (a0 + k + 1) / 2 + a0 + j];
+        T[e] = v;
+      }
+      __syncthreads();
+      for (int e = tid; e < np * pe; e += kSolveThreads) {         // M_CA = -M_CC * T, over L_CA
+        const int pr = e / pe, rem = e - pr * pe, r = rem / sa, j = rem - r * sa;
+        const int a0 = 6 * (2 * pr * sb), c0 = a0 + sa;
+        const double* Mrow = L + (c0 + r) * (c0 + r + 1) / 2 + c0;
+        const double* Tc = T + (size_t)pr * pe + j;
+        double v = 0.0;
+        for (int k = 0; k <= r; k++) v += Mrow[k] * Tc[k * sa];
+        L[(c0 + r) * (c0 + r + 1) / 2 + a0 + j] = -v;
+      }
+      __syncthreads();
+    }
+  }
   double2* Lp = (double2*)cr_arr(a, CR_LP, node);
   const int ne2 = (n * (n + 1) / 2 + 1) / 2;             // packed triangle, in double2 (n (n + 1) / 2 is even for n % 4 == 0)
   for (int e = tid; e < ne2; e += kSolveThreads) Lp[e] = ((const double2*)L)[e];
@@ -176,24 +205,32 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, const double a,
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 struct CrTile { double c[3][3][2]; };
-template <typename FA, typename FB>
-__device__ __forceinline__ void cr_tile_mma(CrTile& t, const int k_begin, const int k_end, FA load_a, FB load_b) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+__device__ __forceinline__ void cr_tile_zero(CrTile& t) {
 #pragma unroll
   for (int mi = 0; mi < 3; mi++)
 #pragma unroll
     for (int ni = 0; ni < 3; ni++) t.c[mi][ni][0] = t.c[mi][ni][1] = 0.0;
+}
+// t += A B over k in [k_begin, k_end) (multiples of 4): load_a(row in tile, k), load_b(k, column in tile)
+template <typename FA, typename FB>
+__device__ __forceinline__ void cr_tile_acc(CrTile& t, const int k_begin, const int k_end, FA load_a, FB load_b) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   for (int k0 = k_begin; k0 < k_end; k0 += 4) {
     double fa[3], fb[3];
 #pragma unroll
-    for (int mi = 0; mi < 3; mi++) fa[mi] = load_a(8 * mi + g, k0 + q);     // (row in tile, k)
+    for (int mi = 0; mi < 3; mi++) fa[mi] = load_a(8 * mi + g, k0 + q);
 #pragma unroll
-    for (int ni = 0; ni < 3; ni++) fb[ni] = load_b(k0 + q, 8 * ni + g);     // (k, column in tile)
+    for (int ni = 0; ni < 3; ni++) fb[ni] = load_b(k0 + q, 8 * ni + g);
 #pragma unroll
     for (int mi = 0; mi < 3; mi++)
 #pragma unroll
       for (int ni = 0; ni < 3; ni++) dmma_884(t.c[mi][ni][0], t.c[mi][ni][1], fa[mi], fb[ni]);
   }
+}
+template <typename FA, typename FB>
+__device__ __forceinline__ void cr_tile_mma(CrTile& t, const int k_begin, const int k_end, FA load_a, FB load_b) {
+  cr_tile_zero(t);
+  cr_tile_acc(t, k_begin, k_end, load_a, load_b);
 }
 
 // The node that connected i with its level-`level` neighbour on side `right` (0 = left), and how to read S_{i,nb} from it:
@@ -210,64 +247,80 @@ __device__ __forceinline__ CrCoupling cr_coupling(const CrArgs& a, int node, int
   return c;
 }
 
-// V_side = L^-1 S_{i,side} by blocked forward substitution: grid (column slabs of 24, side, node).  The CTA holds the packed
-// factor and its 24-column slab of S in shared memory; block row p = 0 .. n/6 - 1:
-//   W = S_p - sum_{q < p} L_pq X_q   (thread = (row in block, column), dot products of length 6 p)
-//   X_p = inv(L_pp) W                (the diagonal block is stored inverted)
+// V_side = L^-1 S_{i,side} by blocked forward substitution in 24-row steps on the fp64 tensor cores.  Grid (slab groups, side,
+// node); the CTA holds the packed factor in shared memory, each of its warps one 24-column slab of S:
+//   p = 0 .. n/24 - 1:   W = S_p - sum_{q < p} L_pq X_q,   X_p = inv(L_pp) W        (24 x 24 x 24 tile products)
 constexpr int kCrGemmWarps = 4;
 constexpr int kCrSlab = 24;
-constexpr int kCrSpikeThreads = 6 * kCrSlab;              // 144
-inline size_t cr_spike_smem(int n) { return ((size_t)n * (n + 1) / 2 + (size_t)n * kCrSlab + 6 * kCrSlab) * sizeof(double); }
-__global__ void __launch_bounds__(kCrSpikeThreads) k_cr_spike(BaDev d, CrArgs a, int level) {
+inline int cr_spike_warps(int n) {                         // slabs per CTA: a divisor of n / 24 whose staging fits 200 KB
+  const int nt = n / kCrSlab;
+  for (int w = nt; w >= 1; w--)
+    if (nt % w == 0 && ((size_t)n * (n + 1) / 2 + (size_t)n * (kCrSlab * w + 4)) * sizeof(double) <= 200 * 1024) return w;
+  return 1;
+}
+inline size_t cr_spike_smem(int n) {
+  return ((size_t)n * (n + 1) / 2 + (size_t)n * (kCrSlab * cr_spike_warps(n) + 4)) * sizeof(double);
+}
+__global__ void __launch_bounds__(192) k_cr_spike(BaDev d, CrArgs a, int level) {
   extern __shared__ __align__(16) double smem_d[];
   const LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
-  const int node = cr_node_at(level, blockIdx.z), side = blockIdx.y, n = a.n, nb = n / 6, tid = threadIdx.x;
+  const int node = cr_node_at(level, blockIdx.z), side = blockIdx.y, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nbr = side ? node + (1 << (level - 1)) : node - (1 << (level - 1));
   if (nbr < 1 || nbr > a.N) return;
-  const int j0 = kCrSlab * blockIdx.x;
+  const int kw = blockDim.x >> 5, ld = kCrSlab * kw + 4;   // + 4: the four k rows of a B fragment fall into different banks
   double* L = smem_d;                                    // packed factor
-  double* X = L + (size_t)n * (n + 1) / 2;               // [n][24] the slab, solved in place
-  double* Wb = X + (size_t)n * kCrSlab;                  // [6][24]
-  const CrCoupling cp = cr_coupling(a, node, level, side);
+  double* Xs = L + (size_t)n * (n + 1) / 2;              // [n][ld]: solved block rows, warp w owns columns 24 w .. 24 w + 23
   {
     const double2* __restrict__ Lp = (const double2*)cr_arr(a, CR_LP, node);
     const int ne2 = (n * (n + 1) / 2 + 1) / 2;
-    for (int e = tid; e < ne2; e += kCrSpikeThreads) ((double2*)L)[e] = Lp[e];
-    const double* __restrict__ src = cp.src;
-    if (cp.trans) {        // S[k][j0 + c] = sign * src[j0 + c][k]: consecutive threads walk k
-      for (int e = tid; e < n * kCrSlab; e += kCrSpikeThreads) {
-        const int c = e / n, k = e - c * n;
-        X[k * kCrSlab + c] = cp.sign * src[(size_t)(j0 + c) * n + k];
-      }
-    } else {
-      for (int e = tid; e < n * kCrSlab; e += kCrSpikeThreads) {
-        const int k = e / kCrSlab, c = e - k * kCrSlab;
-        X[e] = cp.sign * src[(size_t)k * n + j0 + c];
-      }
-    }
+    for (int e = tid; e < ne2; e += blockDim.x) ((double2*)L)[e] = Lp[e];
   }
   __syncthreads();
-  const int i = tid / kCrSlab, c = tid - i * kCrSlab;     // row inside the block, column of the slab
-  for (int p = 0; p < nb; p++) {
-    const int row = 6 * p + i;
-    const double* Lrow = L + row * (row + 1) / 2;
-    double v0 = X[row * kCrSlab + c], v1 = 0.0;
-    int k = 0;
-    for (; k + 1 < 6 * p; k += 2) { v0 -= Lrow[k] * X[k * kCrSlab + c]; v1 -= Lrow[k + 1] * X[(k + 1) * kCrSlab + c]; }
-    Wb[i * kCrSlab + c] = v0 + v1;
-    __syncthreads();
-    double x = 0.0;
-#pragma unroll
-    for (int q = 0; q < 6; q++)
-      if (q <= i) x += Lrow[6 * p + q] * Wb[q * kCrSlab + c];     // inverse of the diagonal Cholesky block
-    X[row * kCrSlab + c] = x;
-    __syncthreads();
-  }
+  const CrCoupling cp = cr_coupling(a, node, level, side);
+  const double* __restrict__ src = cp.src;
+  const int j0 = kCrSlab * (blockIdx.x * kw + warp), wc = kCrSlab * warp;
+  const int g = lane >> 2, q = lane & 3;
   double* V = cr_arr(a, side ? CR_VR : CR_VL, node);
-  for (int e = tid; e < n * kCrSlab; e += kCrSpikeThreads) {
-    const int k = e / kCrSlab, cc = e - k * kCrSlab;
-    V[(size_t)k * n + j0 + cc] = X[e];
+  for (int p = 0; p < n / kCrSlab; p++) {
+    const int r0 = kCrSlab * p;
+    CrTile t;
+#pragma unroll
+    for (int mi = 0; mi < 3; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 3; ni++) {
+        const int row = r0 + 8 * mi + g, col = j0 + 8 * ni + 2 * q;
+        if (cp.trans) {
+          t.c[mi][ni][0] = cp.sign * __ldg(src + (size_t)col * n + row);
+          t.c[mi][ni][1] = cp.sign * __ldg(src + (size_t)(col + 1) * n + row);
+        } else {
+          const double2 v = __ldg((const double2*)(src + (size_t)row * n + col));
+          t.c[mi][ni][0] = cp.sign * v.x; t.c[mi][ni][1] = cp.sign * v.y;
+        }
+      }
+    cr_tile_acc(t, 0, r0,                                 // W -= L_p,0..p-1 X_0..p-1
+                [&](int r, int k) { const int R = r0 + r; return -L[R * (R + 1) / 2 + k]; },
+                [&](int k, int c) { return Xs[k * ld + wc + c]; });
+#pragma unroll
+    for (int mi = 0; mi < 3; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 3; ni++)
+        *(double2*)(Xs + (r0 + 8 * mi + g) * ld + wc + 8 * ni + 2 * q) = make_double2(t.c[mi][ni][0], t.c[mi][ni][1]);
+    __syncwarp();
+    CrTile x;
+    cr_tile_mma(x, 0, kCrSlab,                            // X_p = inv(L_pp) W, the inverse is lower triangular
+                [&](int r, int k) { const int R = r0 + r; return k <= r ? L[R * (R + 1) / 2 + r0 + k] : 0.0; },
+                [&](int k, int c) { return Xs[(r0 + k) * ld + wc + c]; });
+    __syncwarp();
+#pragma unroll
+    for (int mi = 0; mi < 3; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 3; ni++) {
+        const double2 v = make_double2(x.c[mi][ni][0], x.c[mi][ni][1]);
+        *(double2*)(Xs + (r0 + 8 * mi + g) * ld + wc + 8 * ni + 2 * q) = v;
+        *(double2*)(V + (size_t)(r0 + 8 * mi + g) * n + j0 + 8 * ni + 2 * q) = v;
+      }
+    __syncwarp();
   }
 }
 
@@ -321,7 +374,7 @@ __global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur(BaDev d, CrArgs 
 
 // Back substitution of one level, one CTA per node: z = y_i - V_l x_l - V_r x_r (rows are independent: a warp takes four
 // rows per step so that 16-40 loads per lane are in flight), then L' x = z by blocked substitution against the packed
-// factor in shared memory, from the last block up (right-looking: x_p = inv(L_pp)' z_p, then z_q -= L_pq' x_p for q < p).
+// factor in shared memory, from the last 24-row block up (right-looking: x_p = inv(L_pp)' z_p, then z_q -= L_pq' x_p, q < p).
 constexpr int kCrBackWarps = 16;
 inline size_t cr_back_smem(int n) { return ((size_t)n * (n + 1) / 2 + 2) * sizeof(double); }
 __global__ void __launch_bounds__(32 * kCrBackWarps) k_cr_back(BaDev d, CrArgs a, int level) {
@@ -329,7 +382,7 @@ __global__ void __launch_bounds__(32 * kCrBackWarps) k_cr_back(BaDev d, CrArgs a
   __shared__ double s_z[kCrMaxN], s_xl[kCrMaxN], s_xr[kCrMaxN], s_x[kCrMaxN];
   const LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
-  const int node = cr_node_at(level, blockIdx.x), n = a.n, nb = n / 6, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int node = cr_node_at(level, blockIdx.x), n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = 1 << (level - 1), l = node - h, r = node + h;
   const bool has_l = l >= 1, has_r = r <= a.N;
   double* L = smem_d;
@@ -374,20 +427,25 @@ __global__ void __launch_bounds__(32 * kCrBackWarps) k_cr_back(BaDev d, CrArgs a
     }
   }
   __syncthreads();
-  for (int p = nb - 1; p >= 0; p--) {
-    if (tid < 6) {                                         // x_p = inv(L_pp)' z_p: column tid of the inverted block
-      double x = 0.0;
-#pragma unroll
-      for (int q = 0; q < 6; q++)
-        if (q >= tid) x += L[(6 * p + q) * (6 * p + q + 1) / 2 + 6 * p + tid] * s_z[6 * p + q];
-      s_x[6 * p + tid] = x;
+  for (int p = n / 24 - 1; p >= 0; p--) {
+    const int r0 = 24 * p;
+    if (tid < 24) {                                        // x_p = inv(L_pp)' z_p: column tid of the inverted block
+      double x0 = 0.0, x1 = 0.0;
+      for (int qq = tid; qq < 24; qq += 2) {
+        x0 += L[(r0 + qq) * (r0 + qq + 1) / 2 + r0 + tid] * s_z[r0 + qq];
+        if (qq + 1 < 24) x1 += L[(r0 + qq + 1) * (r0 + qq + 2) / 2 + r0 + tid] * s_z[r0 + qq + 1];
+      }
+      s_x[r0 + tid] = x0 + x1;
     }
     __syncthreads();
-    if (tid < 6 * p) {                                     // z_k -= sum_q L[6p + q][k] x[6p + q]
-      double v = 0.0;
-#pragma unroll
-      for (int q = 0; q < 6; q++) v += L[(6 * p + q) * (6 * p + q + 1) / 2 + tid] * s_x[6 * p + q];
-      s_z[tid] -= v;
+    if (tid < r0) {                                        // z_k -= sum_q L[r0 + q][k] x[r0 + q]
+      double v0 = 0.0, v1 = 0.0;
+#pragma unroll 4
+      for (int qq = 0; qq < 24; qq += 2) {
+        v0 += L[(r0 + qq) * (r0 + qq + 1) / 2 + tid] * s_x[r0 + qq];
+        v1 += L[(r0 + qq + 1) * (r0 + qq + 2) / 2 + tid] * s_x[r0 + qq + 1];
+      }
+      s_z[tid] -= v0 + v1;
     }
     __syncthreads();
   }

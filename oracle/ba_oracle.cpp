@@ -26,6 +26,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -112,6 +113,20 @@ struct Lin {     // one linearised residual block (already corrected by the loss
   double Jp[6];    // 2x3
 };
 
+// Ceres evaluates residuals and Jacobians with options.num_threads threads (LocalBundleAdjustment sets 4,
+// CeresOptimizer.cc:516).  g_eval_threads > 1 splits the residual blocks into contiguous chunks; the per-block costs are
+// then summed in block order, so the result is bit-identical to the one-thread evaluation.  Only the evaluation is threaded
+// (Schur elimination and the reduced solve stay on one thread).
+int g_eval_threads = 1;
+template <typename F>
+void parallel_blocks(size_t n, F f) {
+  const int T = (int)std::min<size_t>((size_t)std::max(1, g_eval_threads), std::max<size_t>(n / 256, 1));
+  if (T <= 1) { f(0, n); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; t++) th.emplace_back([=] { f(n * t / T, n * (t + 1) / T); });
+  for (auto& x : th) x.join();
+}
+
 struct Solver {
   int K = 0, M = 0;
   std::vector<double> cams, pts;   // current x
@@ -124,22 +139,28 @@ struct Solver {
 
   // ---- evaluation -------------------------------------------------------------------------------
   double cost_only(const std::vector<double>& c, const std::vector<double>& p) const {
+    std::vector<double> bc(blocks.size());
+    parallel_blocks(blocks.size(), [&](size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; i++) {
+        const Block& b = blocks[i];
+        double r[2];
+        reprojection_residual<double>(&c[7 * b.cam], &c[7 * b.cam + 3], &p[3 * b.pt], K4, b.u, b.v, b.w, r);
+        const double s = r[0] * r[0] + r[1] * r[1];
+        double rho0 = s;
+        if (b.huber && s > kHuberA * kHuberA) rho0 = 2.0 * kHuberA * std::sqrt(s) - kHuberA * kHuberA;
+        bc[i] = 0.5 * rho0;
+      }
+    });
     double cost = 0.0;
-    for (const Block& b : blocks) {
-      double r[2];
-      reprojection_residual<double>(&c[7 * b.cam], &c[7 * b.cam + 3], &p[3 * b.pt], K4, b.u, b.v, b.w, r);
-      const double s = r[0] * r[0] + r[1] * r[1];
-      double rho0 = s;
-      if (b.huber && s > kHuberA * kHuberA) rho0 = 2.0 * kHuberA * std::sqrt(s) - kHuberA * kHuberA;
-      cost += 0.5 * rho0;
-    }
+    for (double v : bc) cost += v;
     return cost;
   }
 
   double linearize(std::vector<Lin>& lin) const {
     lin.resize(blocks.size());
-    double cost = 0.0;
-    for (size_t i = 0; i < blocks.size(); i++) {
+    std::vector<double> bc(blocks.size());
+    parallel_blocks(blocks.size(), [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; i++) {
       const Block& b = blocks[i];
       typedef Jet<10> J10;
       J10 t[3], q[4], X[3], r[2];
@@ -157,7 +178,7 @@ struct Solver {
         rho0 = 2.0 * kHuberA * rr - kHuberA * kHuberA;
         rho1 = std::max(std::numeric_limits<double>::min(), kHuberA / rr);
       }
-      cost += 0.5 * rho0;
+      bc[i] = 0.5 * rho0;
       const double sc = b.huber ? std::sqrt(rho1) : 1.0;   // corrector with alpha = 0
       for (int row = 0; row < 2; row++) {
         L.r[row] = sc * r[row].a;
@@ -170,6 +191,9 @@ struct Solver {
         for (int k = 0; k < 3; k++) L.Jp[row * 3 + k] = sc * r[row].v[7 + k];
       }
     }
+    });
+    double cost = 0.0;
+    for (double v : bc) cost += v;
     return cost;
   }
 
@@ -295,6 +319,8 @@ struct ba_oracle_summary {
 };
 
 // trace: [iterations+1][8] = cost, cost_change, gradient_max_norm, step_norm, relative_decrease, radius, accepted, valid
+void ba_oracle_set_threads(int n) { g_eval_threads = n < 1 ? 1 : n; }
+
 int ba_oracle_solve(int K, double* cams, const uint8_t* cam_const, int M, double* pts, int pts_const, int N,
                     const int32_t* obs_cam, const int32_t* obs_pt, const float* uv, const float* inv_sigma2,
                     const uint8_t* mode, const double* K4, int max_iterations, ba_oracle_summary* out, double* trace,
