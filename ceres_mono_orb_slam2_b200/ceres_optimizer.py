@@ -147,6 +147,10 @@ class CeresOptimizer:
         check(self._L.cmos_ba_get_results(self._h, ptr(cams), ptr(pts), ptr(erase), ptr(summ), C.c_void_p(stream)))
         return cams, pts, erase, summ
 
+    def debug_stop_at(self, pass_: int, iteration: int):
+        """Test hook: the device raises the stop flag itself after `iteration` iterations of `pass_` (-1: off)."""
+        check(self._L.cmos_ba_debug_stop_at(self._h, int(pass_), int(iteration)))
+
     def trace(self, pass_: int, rows: int):
         t = np.zeros((rows, 8))
         check(self._L.cmos_ba_debug_trace(self._h, pass_, ptr(t), rows))

@@ -516,6 +516,8 @@ struct BaDev {
   LmState* st;
   double* trace;                            // [rows][8] of the running pass, or null
   const volatile uint8_t* stop_flag;        // mapped host byte or null
+  double *snap_cams, *snap_pts;             // parameters at the start of the running pass (restored when the solve is aborted)
+  int pass, dbg_stop_pass, dbg_stop_iter;   // test hook: the device raises the stop flag itself at (pass, iteration)
 };
 
 // `pad` of LmState doubles as the "aborted" flag: LocalBundleAdjustment returns without writing anything back
@@ -528,6 +530,11 @@ __global__ void k_lm_init(BaDev d, int max_iterations) {
 }
 
 __device__ bool last_cta_arrives(unsigned int* ticket, unsigned int n_ctas);
+// cmos_ba_debug_stop_at: emulates another thread raising the stop flag at a reproducible point of the solve
+__device__ __forceinline__ void dbg_raise_stop(const BaDev& d, const LmState& st) {
+  if (d.dbg_stop_iter >= 0 && d.stop_flag && d.pass == d.dbg_stop_pass && st.iteration >= d.dbg_stop_iter)
+    *const_cast<volatile uint8_t*>(d.stop_flag) = 1;
+}
 __device__ void post_lin_body(const BaDev& d, LmState& st, int phase, double* scratch);
 __device__ void decide_body(const BaDev& d, LmState& st, int phase, double* scratch);
 
@@ -720,6 +727,7 @@ __device__ void post_lin_body(const BaDev& d, LmState& st, int phase, double* sc
         d.red[0] = d.lin_tail[0]; d.red[1] = d.lin_tail[1]; d.red[2] = g;
       }
       lm_after_linearize(st, d.red[0], fmax(d.red[2], g2), sqrt(d.red[1] + x2), d.trace);
+      dbg_raise_stop(d, st);
       if (!st.done && d.stop_flag && *d.stop_flag) { st.done = 1; st.termination = TERM_USER; }   // StopFlagCallback
     }
   }
@@ -1384,6 +1392,7 @@ __device__ void decide_body(const BaDev& d, LmState& st, int phase, double* scra
     if (threadIdx.x == 0) {
       lm_decide(st, ok, mcc, d.red[3], sqrt(sn2), d.trace);
       st.solve_failed = 0;
+      dbg_raise_stop(d, st);
       if (!st.done && d.stop_flag && *d.stop_flag) { st.done = 1; st.termination = TERM_USER; }
     }
   }
@@ -1419,6 +1428,21 @@ __global__ void __launch_bounds__(256) k_outlier_scan(BaDev d, const uint8_t* __
 __global__ void k_set_mode(BaDev d, int mode) {
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p < d.N) d.o_mode[p] = (uint8_t)mode;
+}
+
+// ceres::Solve leaves the parameter blocks at their ORIGINAL values when a callback aborts it (USER_FAILURE is not a usable
+// solution): an abort in the middle of a pass discards that pass.  Snapshot at the start of the pass, restore at its end.
+__global__ void k_snapshot(BaDev d) {
+  const int i = blockIdx.x * 256 + threadIdx.x, cur = d.st->cur;
+  if (i < 7 * d.K) d.snap_cams[i] = d.cams[cur][i];
+  if (i < 3 * d.M) d.snap_pts[i] = d.pts[cur][i];
+}
+__global__ void k_restore_on_abort(BaDev d) {
+  const LmState& st = *d.st;
+  if (st.termination != TERM_USER || st.pad) return;     // pad: the flag was already up at the start (nothing is written back)
+  const int i = blockIdx.x * 256 + threadIdx.x, cur = st.cur;
+  if (i < 7 * d.K) d.cams[cur][i] = d.snap_cams[i];
+  if (i < 3 * d.M) d.pts[cur][i] = d.snap_pts[i];
 }
 
 __global__ void k_summary(BaDev d, cmos_ba_summary* out) {
@@ -2170,6 +2194,7 @@ struct cmos_ba {
   int trace_rows = 0;
   cmos_ba_summary* d_summaries = nullptr;   // [2]
   bool has_problem = false, ran = false;
+  int dbg_stop_pass = -1, dbg_stop_iter = -1;
   int launches = 0;
   // pose optimisation staging
   double *dp_pose = nullptr, *dp_xw = nullptr, *dp_trace = nullptr;
@@ -2220,7 +2245,9 @@ int map_stop_flag(cmos_ba* h, const uint8_t* flag, const volatile uint8_t** dev)
 int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
   BaDev d = h->d;
   d.trace = h->d_trace + (size_t)pass * h->trace_rows * kTraceCols;
+  d.pass = pass; d.dbg_stop_pass = h->dbg_stop_pass; d.dbg_stop_iter = h->dbg_stop_iter;
   const int nlb = d.n_lin_blocks;
+  const int g_par = (std::max(7 * d.K, 3 * d.M) + 255) / 256;
   const bool small = d.nc <= kSmallMaxN;
   const size_t small_smem = ((size_t)(d.nc + 1) * (d.nc + 2) / 2 + (size_t)kPB * (d.nc + 2) + d.nc) * sizeof(double);
   const bool multi = d.multi != 0;
@@ -2246,6 +2273,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
     h->launches += 3;
     return CMOS_OK;
   };
+  if (d.stop_flag) { k_snapshot<<<g_par, 256, 0, st>>>(d); h->launches++; }
   k_lm_init<<<1, 1, 0, st>>>(d, max_iterations);
   h->launches++;
   for (int it = 0; it < max_iterations; it++) {
@@ -2342,6 +2370,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
     int rc;
     if ((rc = linearize())) return rc;
   }
+  if (d.stop_flag) { k_restore_on_abort<<<g_par, 256, 0, st>>>(d); h->launches++; }
   k_summary<<<1, 1, 0, st>>>(d, h->d_summaries + pass);
   h->launches++;
   CMOS_CUDA_OK(cudaGetLastError());
@@ -2376,7 +2405,8 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
   BaDev& d = h->d;
   const size_t nlb = ((size_t)M * kPointLanes + kLinThreads - 1) / kLinThreads;
   ok = ok && alloc(&d.cams[0], 7 * K) && alloc(&d.cams[1], 7 * K) && alloc(&d.pts[0], 3 * M) && alloc(&d.pts[1], 3 * M);
-  ok = ok && alloc(&h->d_cams0, 7 * K) && alloc(&h->d_pts0, 3 * M) && alloc(&h->d_cams_out, 7 * K) && alloc(&h->d_pts_out, 3 * M);
+  ok = ok && alloc(&h->d_cams0, 7 * K) && alloc(&h->d_pts0, 3 * M) && alloc(&h->d_cams_out, 7 * K) && alloc(&h->d_pts_out, 3 * M) &&
+       alloc(&d.snap_cams, 7 * K) && alloc(&d.snap_pts, 3 * M);
   ok = ok && alloc(&h->d_cam_var, K) && alloc(&h->d_o_cam, N) && alloc(&h->d_o_cv, N) && alloc(&h->d_o_pt, N) &&
        alloc(&h->d_pt_start, M + 1) && alloc(&h->d_cam_start, K + 1) && alloc(&h->d_cam_obs, N) &&
        alloc(&h->d_blk_a, h->cap_blocks) && alloc(&h->d_blk_b, h->cap_blocks) && alloc(&h->d_blk_start, h->cap_blocks + 1) &&
@@ -2424,7 +2454,7 @@ int cmos_ba_destroy(cmos_ba_t h) {
                   h->d_blk_start, h->d_pair_a, h->d_pair_b, h->d_perm, h->d_o_uv, h->d_o_w, h->d_o_mode, h->d_cam_flags,
                   h->d_erase, d.Jc, d.Jp, d.res, d.Hpp, d.gp, d.Hinv, d.tp, d.scale_p, h->d_HG, h->d_var_cam, h->d_red, h->d_Sblk, d.scale_c, d.S,
                   d.yc, d.part, d.st, h->d_Linv, h->d_pan_tiles, h->d_pan_first, h->d_band_blk, h->d_trace, h->d_summaries, h->dp_pose, h->dp_xw, h->dp_uv, h->dp_w,
-                  h->dp_n, h->dp_inl, h->dp_out, h->dp_sum, h->dp_trace, h->d_chunk_start, h->d_chunk_blk, h->d_blk_chunk0,
+                  h->dp_n, h->dp_inl, h->dp_out, h->dp_sum, h->dp_trace, d.snap_cams, d.snap_pts, h->d_chunk_start, h->d_chunk_blk, h->d_blk_chunk0,
                   h->d_schur_part};
   for (void* b : bufs)
     if (b) cudaFree(b);
@@ -2895,6 +2925,12 @@ int cmos_ba_debug_trace(cmos_ba_t h, int32_t pass, double* trace, int32_t rows) 
   CMOS_CUDA_OK(cudaDeviceSynchronize());
   CMOS_CUDA_OK(cudaMemcpy(trace, h->d_trace + (size_t)pass * h->trace_rows * kTraceCols,
                           (size_t)rows * kTraceCols * sizeof(double), cudaMemcpyDeviceToHost));
+  return CMOS_OK;
+}
+
+int cmos_ba_debug_stop_at(cmos_ba_t h, int32_t pass, int32_t iteration) {
+  CMOS_REQUIRE(h, "null handle");
+  h->dbg_stop_pass = pass; h->dbg_stop_iter = iteration;
   return CMOS_OK;
 }
 

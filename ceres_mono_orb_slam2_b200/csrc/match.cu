@@ -459,7 +459,9 @@ __global__ void __launch_bounds__(kReplayThreads) k_sf_replay(cmos_camera cam, c
     int removed = 0;
     for (int e = tid; e < nev; e += kReplayThreads) {
       const int b = ev_bin[e];
-      if (b != s_keep[0] && b != s_keep[1] && b != s_keep[2]) { s_match[ev_idx[e]] = -1; removed++; }
+      // ORBmatcher.cc:1262 nulls map_points_[idx]: the keypoint is no longer claimed either (a 2 x th retry, Tracking.cc:636-639,
+      // or a later SearchLocalPoints on the same frame may match it again)
+      if (b != s_keep[0] && b != s_keep[1] && b != s_keep[2]) { s_match[ev_idx[e]] = -1; s_claimed[ev_idx[e]] = 0; removed++; }
     }
     if (removed) atomicSub(&s_nmatch, removed);
     __syncthreads();
@@ -488,6 +490,8 @@ struct SearchPointsArgs {
   uint8_t* claimed;
   int* assign;
   int* nmatches;
+  uint32_t* g_lists;   // non-null: candidate lists and counts live in HBM ([B][point_stride][kListCapPts], [B][point_stride])
+  uint16_t* g_cnt;     // — used when a large local map (> ~6000 points) does not fit the CTA's shared memory
 };
 
 __global__ void __launch_bounds__(kSearchThreads) k_search_points(cmos_camera cam, const cmos_keypoint* __restrict__ kps,
@@ -501,10 +505,11 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_points(cmos_camera ca
   const int n = min(counts[f], stride);
   const int np = min(a.n_points[f], a.point_stride);
   // carve: lists[np][kListCapPts] u32 | assign[n] i32 | cnt[np] u16 | claimed[n] u8
-  uint32_t* lists = (uint32_t*)smem_raw;
-  int* s_assign = (int*)(lists + (size_t)a.point_stride * kListCapPts);
-  uint16_t* cnt = (uint16_t*)(s_assign + stride);
-  uint8_t* s_claimed = (uint8_t*)(cnt + a.point_stride);
+  const bool in_hbm = a.g_lists != nullptr;
+  uint32_t* lists = in_hbm ? a.g_lists + (size_t)f * a.point_stride * kListCapPts : (uint32_t*)smem_raw;
+  int* s_assign = in_hbm ? (int*)smem_raw : (int*)(lists + (size_t)a.point_stride * kListCapPts);
+  uint16_t* cnt = in_hbm ? a.g_cnt + (size_t)f * a.point_stride : (uint16_t*)(s_assign + stride);
+  uint8_t* s_claimed = in_hbm ? (uint8_t*)(s_assign + stride) : (uint8_t*)(cnt + a.point_stride);
   __shared__ int s_nmatch;
 
   FrameDev F{kps + (long long)f * stride, desc + (long long)f * stride * 32,
@@ -731,6 +736,8 @@ struct cmos_match {
   int launches = 0;
   // own device buffers
   int *d_grid_start = nullptr, *d_grid_idx = nullptr;
+  uint32_t* g_lists = nullptr;     // HBM candidate lists of k_search_points (allocated on first use by a large local map)
+  uint16_t* g_cnt = nullptr;
   uint32_t *d_lists = nullptr, *d_best = nullptr;   // SearchByProjection(frame,last) phase-1 results
   uint16_t* d_cnt = nullptr;
   // staging for host callers
@@ -853,7 +860,7 @@ int cmos_match_destroy(cmos_match_t h) {
   void* bufs[] = {h->d_grid_start, h->d_grid_idx, h->d_lists, h->d_best, h->d_cnt, h->s_kps, h->s_last_kps, h->s_desc, h->s_last_desc, h->s_last_flags,
                   h->s_claimed, h->s_counts, h->s_last_counts, h->s_match, h->s_nmatches, h->s_last_xw, h->s_T,
                   h->s_np, h->s_level, h->s_in_view, h->s_pdesc, h->s_has_obs, h->s_view_cos, h->s_proj, h->s_mind,
-                  h->s_maxd, h->s_pxw, h->s_pnormal, h->s_pose};
+                  h->s_maxd, h->s_pxw, h->s_pnormal, h->s_pose, h->g_lists, h->g_cnt};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -973,8 +980,10 @@ int cmos_match_search_by_projection_points(cmos_match_t h, const int32_t* n_poin
   CMOS_REQUIRE(point_stride >= 1 && point_stride <= h->p.max_points, "point_stride %d outside 1..%d", point_stride,
                h->p.max_points);
   CMOS_REQUIRE(nn_ratio > 0.f, "nn_ratio must be positive");
-  CMOS_REQUIRE(search_points_smem(point_stride, h->stride) <= 220 * 1024,
-               "point_stride %d x stride %d exceeds the search kernel's shared memory", point_stride, h->stride);
+  // lists in shared memory when they fit (about 6000 points next to 2000 keypoints), otherwise in HBM scratch: a large
+  // local map must not make the drop-in throw (ORBmatcher::SearchByProjection(F, points) passes the whole list)
+  const bool lists_in_hbm = search_points_smem(point_stride, h->stride) > 220 * 1024;
+  CMOS_REQUIRE(!lists_in_hbm || (size_t)h->stride * 5 + 16 <= 220 * 1024, "stride %d exceeds the search kernel's shared memory", h->stride);
   CMOS_CUDA_OK(cudaSetDevice(h->p.device));
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   const int B = h->n_frames;
@@ -1001,8 +1010,18 @@ int cmos_match_search_by_projection_points(cmos_match_t h, const int32_t* n_poin
     a.proj_xy = h->s_proj; a.desc = h->s_pdesc; a.has_obs = h->s_has_obs;
     a.claimed = claimed ? h->s_claimed : nullptr; a.assign = h->s_match; a.nmatches = h->s_nmatches;
   }
+  if (lists_in_hbm) {
+    const size_t need = (size_t)h->p.max_batch * std::max(h->p.max_points, 1);
+    if (!h->g_lists) {
+      cudaError_t err = cudaSuccess;
+      h->g_lists = dev_alloc<uint32_t>(need * kListCapPts, &err);
+      h->g_cnt = dev_alloc<uint16_t>(need, &err);
+      CMOS_CUDA_OK(err);
+    }
+    a.g_lists = h->g_lists; a.g_cnt = h->g_cnt;
+  }
   h->timer[2].begin(st);
-  k_search_points<<<B, kSearchThreads, search_points_smem(point_stride, h->stride), st>>>(
+  k_search_points<<<B, kSearchThreads, lists_in_hbm ? (size_t)h->stride * 5 + 16 : search_points_smem(point_stride, h->stride), st>>>(
       h->cam, h->kps, h->desc, h->counts, h->stride, h->d_grid_start, h->d_grid_idx, h->p.max_keypoints, a);
   h->timer[2].mark(st);
   CMOS_CUDA_OK(cudaGetLastError());

@@ -106,16 +106,26 @@ int cmos_track_frames(cmos_track_t h, const uint8_t* images, int64_t frame_strid
   CMOS_CUDA_OK(cudaSetDevice(h->p.orb.device));
   const int cf = h->p.chunk_frames, nl = (int)h->lanes.size();
   int launches = 0, rc = CMOS_OK;
+  // inside the loop a CUDA error must not return: copies into caller memory may be in flight on other lanes (drained below)
+#define TRACK_CUDA(call)                                                                      \
+  {                                                                                           \
+    const cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                                  \
+      cmos::set_error("%s failed: %s", #call, cudaGetErrorString(e_));                        \
+      rc = CMOS_ERR_CUDA;                                                                     \
+      break;                                                                                  \
+    }                                                                                         \
+  }
   for (int f0 = 0, c = 0; f0 < n_frames && !rc; f0 += cf, c++) {
     Lane& L = h->lanes[c % nl];
     const int n = std::min(cf, n_frames - f0);
     const size_t nq = (size_t)n * last_stride, o = (size_t)f0 * last_stride;
-    CMOS_CUDA_OK(cudaMemcpyAsync(L.d_T, Tcw + (size_t)f0 * 16, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, L.st));
-    CMOS_CUDA_OK(cudaMemcpyAsync(L.d_last_kps, last_keypoints + o, nq * sizeof(cmos_keypoint), cudaMemcpyHostToDevice, L.st));
-    CMOS_CUDA_OK(cudaMemcpyAsync(L.d_last_counts, last_counts + f0, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, L.st));
-    CMOS_CUDA_OK(cudaMemcpyAsync(L.d_flags, last_flags + o, nq, cudaMemcpyHostToDevice, L.st));
-    CMOS_CUDA_OK(cudaMemcpyAsync(L.d_xw, last_xw + o * 3, nq * 3 * sizeof(double), cudaMemcpyHostToDevice, L.st));
-    CMOS_CUDA_OK(cudaMemcpyAsync(L.d_last_desc, last_descriptors + o * 32, nq * 32, cudaMemcpyHostToDevice, L.st));
+    TRACK_CUDA(cudaMemcpyAsync(L.d_T, Tcw + (size_t)f0 * 16, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, L.st));
+    TRACK_CUDA(cudaMemcpyAsync(L.d_last_kps, last_keypoints + o, nq * sizeof(cmos_keypoint), cudaMemcpyHostToDevice, L.st));
+    TRACK_CUDA(cudaMemcpyAsync(L.d_last_counts, last_counts + f0, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, L.st));
+    TRACK_CUDA(cudaMemcpyAsync(L.d_flags, last_flags + o, nq, cudaMemcpyHostToDevice, L.st));
+    TRACK_CUDA(cudaMemcpyAsync(L.d_xw, last_xw + o * 3, nq * 3 * sizeof(double), cudaMemcpyHostToDevice, L.st));
+    TRACK_CUDA(cudaMemcpyAsync(L.d_last_desc, last_descriptors + o * 32, nq * 32, cudaMemcpyHostToDevice, L.st));
     if ((rc = cmos_orb_extract_async(L.orb, images + (size_t)f0 * frame_stride, frame_stride, pitch, width, height, n,
                                      keypoints + (size_t)f0 * capacity, descriptors + (size_t)f0 * capacity * 32,
                                      counts + f0, capacity, L.st))) break;
@@ -126,17 +136,19 @@ int cmos_track_frames(cmos_track_t h, const uint8_t* images, int64_t frame_strid
                                                     L.d_last_desc, last_stride, th, check_orientation, nullptr, L.d_match,
                                                     L.d_nm, 1, L.st))) break;
     const size_t row = (size_t)h->kp_cap * sizeof(int);
-    if (capacity == h->kp_cap)
-      CMOS_CUDA_OK(cudaMemcpyAsync(match + (size_t)f0 * capacity, L.d_match, row * n, cudaMemcpyDeviceToHost, L.st));
-    else
-      CMOS_CUDA_OK(cudaMemcpy2DAsync(match + (size_t)f0 * capacity, (size_t)capacity * sizeof(int), L.d_match, row, row, n,
-                                     cudaMemcpyDeviceToHost, L.st));
-    CMOS_CUDA_OK(cudaMemcpyAsync(nmatches + f0, L.d_nm, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, L.st));
+    if (capacity == h->kp_cap) {
+      TRACK_CUDA(cudaMemcpyAsync(match + (size_t)f0 * capacity, L.d_match, row * n, cudaMemcpyDeviceToHost, L.st));
+    } else {
+      TRACK_CUDA(cudaMemcpy2DAsync(match + (size_t)f0 * capacity, (size_t)capacity * sizeof(int), L.d_match, row, row, n,
+                                   cudaMemcpyDeviceToHost, L.st));
+    }
+    TRACK_CUDA(cudaMemcpyAsync(nmatches + f0, L.d_nm, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, L.st));
     int a = 0, b = 0;
     cmos_orb_last_launch_count(L.orb, &a);
     cmos_match_last_launch_count(L.match, &b);
     launches += a + 1 + b;   // + the grid kernel of set_frames
   }
+#undef TRACK_CUDA
   // drain every lane even after an error, so no copy into caller memory is still in flight on return
   for (Lane& L : h->lanes) {
     int r2 = cmos_orb_finish(L.orb, L.st);

@@ -4,6 +4,8 @@
 #ifndef ORB_SLAM2_CMOS_ORBMATCHER_H
 #define ORB_SLAM2_CMOS_ORBMATCHER_H
 
+#include <map>
+#include <tuple>
 #include <utility>
 
 #include "views.h"
@@ -16,15 +18,25 @@ class ORBmatcher {
   static const int TH_HIGH = CMOS_TH_HIGH;
   static const int HISTO_LENGTH = CMOS_HISTO_LENGTH;
 
+  // The reference constructs an ORBmatcher as a stack temporary at every call site, several times per frame
+  // (Tracking.cc:617, 766, 840, ...).  The device engines (about 30 device allocations and a stream each) are therefore
+  // NOT owned by the object: they are borrowed from a per-thread cache keyed by (max_keypoints, max_points, device) and
+  // live until the thread exits or ORBmatcher::release() is called — constructing a matcher costs nothing after the first.
   ORBmatcher(float nnratio = 0.6f, bool checkOri = true, int max_keypoints = 4096, int max_points = 8192, int device = 0)
       : max_keypoints_(max_keypoints), max_points_(max_points), device_(device), mfNNratio(nnratio),
         mbCheckOrientation(checkOri) {
-    cmos_match_params p = {1, max_keypoints, max_points, device};
-    cmos_throw_if(cmos_match_create(&p, &h_), "ORBmatcher");
+    Engines& e = cache().get(max_keypoints, max_points, device);
+    if (!e.match) {
+      cmos_match_params p = {1, max_keypoints, max_points, device};
+      cmos_throw_if(cmos_match_create(&p, &e.match), "ORBmatcher");
+    }
+    h_ = e.match; kf_ = e.kf; eng_ = &e;
   }
-  ~ORBmatcher() { cmos_match_destroy(h_); cmos_kfmatch_destroy(kf_); }
+  ~ORBmatcher() {}
   ORBmatcher(const ORBmatcher&) = delete;
   ORBmatcher& operator=(const ORBmatcher&) = delete;
+  // destroys the calling thread's cached engines (no ORBmatcher of this thread may be alive)
+  static void release() { cache().clear(); }
 
   // Hamming distance of two 256-bit descriptors (ORBmatcher.cc:1422-1437)
   static int DescriptorDistance(const uint8_t* a, const uint8_t* b) {
@@ -223,9 +235,25 @@ class ORBmatcher {
     if (!kf_) {
       cmos_kfmatch_params p = {max_keypoints_, max_points_, 16384, device_};
       cmos_throw_if(cmos_kfmatch_create(&p, &kf_), "ORBmatcher (keyframe searches)");
+      eng_->kf = kf_;
     }
     return kf_;
   }
+  struct Engines { cmos_match_t match = nullptr; cmos_kfmatch_t kf = nullptr; };
+  struct Cache {                                   // thread_local: destroyed at thread exit
+    std::map<std::tuple<int, int, int>, Engines> m;
+    Engines& get(int kp, int pts, int dev) { return m[std::make_tuple(kp, pts, dev)]; }
+    void clear() {
+      for (auto& kv : m) { cmos_match_destroy(kv.second.match); cmos_kfmatch_destroy(kv.second.kf); }
+      m.clear();
+    }
+    ~Cache() { clear(); }
+  };
+  static Cache& cache() {
+    static thread_local Cache c;
+    return c;
+  }
+  Engines* eng_ = nullptr;
   void kf_view(int slot, const cmos_camera& cam, bool is_keyframe, const KeyPoint* kps, const uint8_t* desc, int n) {
     cmos_throw_if(cmos_kfmatch_set_view(kf(), slot, &cam, is_keyframe ? 1 : 0, kps, desc, n), "ORBmatcher: view grid");
   }

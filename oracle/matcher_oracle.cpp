@@ -194,7 +194,7 @@ int match_oracle_search_by_projection_frame(
     three_maxima(rot_hist, kHistoLength, i1, i2, i3);
     for (int b = 0; b < kHistoLength; b++)
       if (b != i1 && b != i2 && b != i3)
-        for (int idx : rot_hist[b]) { cur_match[idx] = -1; nmatches--; }
+        for (int idx : rot_hist[b]) { cur_match[idx] = -1; cur_claimed[idx] = 0; nmatches--; }   // :1262 map_points_[idx] = nullptr
   }
   return nmatches;
 }

@@ -214,6 +214,34 @@ def test_search_points_overflow_ties():
     assert nm[0] == onm and np.array_equal(assign[0], oa)
 
 
+def test_search_points_large_local_map():
+    """A local map of 9000 points next to 2000 keypoints: the candidate lists no longer fit the CTA's shared memory and live
+    in HBM scratch (the drop-in used to throw above ~6000 points).  Same result as the oracle."""
+    rng = np.random.default_rng(99)
+    n, npnt = 2000, 9000
+    kps = np.zeros(n, KP_DTYPE)
+    kps["x"] = rng.uniform(20, W - 20, n).astype(np.float32); kps["y"] = rng.uniform(20, H - 20, n).astype(np.float32)
+    kps["octave"] = rng.integers(0, 4, n)
+    desc = rng.integers(0, 256, (n, 32)).astype(np.uint8)
+    o = po.OrbOracle(2000, 1.2, 8, 20, 7)
+    cam = Camera.create(W, H, K, o.scale_factors)
+    src = rng.integers(0, n, npnt)                                   # every point is a noisy copy of some keypoint
+    in_view = (rng.random(npnt) < 0.9).astype(np.uint8); level = kps["octave"][src].astype(np.int32)
+    vcos = rng.uniform(0.99, 1, npnt).astype(np.float32)
+    proj = np.stack([kps["x"][src] + rng.normal(0, 1.5, npnt), kps["y"][src] + rng.normal(0, 1.5, npnt)], 1).astype(np.float32)
+    mdesc = desc[src].copy()
+    mdesc[np.arange(npnt), rng.integers(0, 32, npnt)] ^= (1 << rng.integers(0, 8, npnt)).astype(np.uint8)
+    has_obs = (rng.random(npnt) < 0.7).astype(np.uint8)
+    m = ORBmatcher(0.8, True, max_batch=1, max_keypoints=n, max_points=npnt)
+    m.set_frames(cam, kps[None], desc[None], np.array([n], np.int32), 1, n)
+    assign, nm = m.SearchByProjectionPoints(np.array([npnt], np.int32), in_view[None], level[None], vcos[None], proj[None],
+                                            mdesc[None], has_obs[None], npnt, 3.0)
+    gs, gi = po.build_grid(kps, cam.bounds6())
+    oa, onm, _ = po.search_by_projection_points(kps, desc, gs, gi, cam.bounds6(), o.scale_factors, in_view, level, vcos,
+                                                proj, mdesc, has_obs, 3.0, 0.8)
+    assert nm[0] == onm and np.array_equal(assign[0], oa) and onm > 1000
+
+
 def test_empty_inputs():
     o = po.OrbOracle(2000, 1.2, 8, 20, 7)
     cam = Camera.create(W, H, K, o.scale_factors)

@@ -115,7 +115,7 @@ def py_search_frame(cur_kps, cur_desc, b, K4, sf, T, last_kps, flags, xw, ldesc,
         for i in range(30):
             if i not in (i1, i2_, i3):
                 for idx in hist[i]:
-                    match[idx] = -1; nm -= 1
+                    match[idx] = -1; claimed[idx] = 0; nm -= 1      # ORBmatcher.cc:1262: map_points_[idx] = nullptr
     return match, nm
 
 
