@@ -1109,6 +1109,12 @@ __device__ __forceinline__ void solve_row_update(const double* li, const double*
 __device__ __forceinline__ void packed_cholesky(double* __restrict__ L, double* __restrict__ P, const int n, const int ps,
                                                 int* s_fail) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = kSolveThreads / 32;
+#ifdef CMOS_CR_TIMING
+  long long pk[6] = {0, 0, 0, 0, 0, 0}, tp = clock64();
+#define PK(i) { const long long tn = clock64(); pk[i] += tn - tp; tp = tn; }
+#else
+#define PK(i)
+#endif
   if (tid == 0 && n > 0) factor_diag6(L, 0, s_fail);
   __syncthreads();
   for (int k0 = 0; k0 < n; k0 += kPB) {
@@ -1131,7 +1137,9 @@ __device__ __forceinline__ void packed_cholesky(double* __restrict__ L, double* 
 #pragma unroll
       for (int c = 0; c < kPB; c++) { rowp[c] = x[c]; P[c * ps + i] = x[c]; }
     }
+    PK(0)
     __syncthreads();
+    PK(1)
     // trailing update.  Look-ahead: warp 0 updates the NEXT diagonal block (rows t0..t0+5 lie entirely inside it) and its
     // lane 0 factors it at once, while the other warps update the rows below — the next round starts with its panel solve.
     if (warp == 0) {
@@ -1146,7 +1154,9 @@ __device__ __forceinline__ void packed_cholesky(double* __restrict__ L, double* 
           L[i * (i + 1) / 2 + cc] -= v;
         }
         __syncwarp();
+        PK(2)
         if (lane == 0) factor_diag6(L, t0, s_fail);
+        PK(3)
       }
     } else {
 #if CMOS_SOLVE_TILE
@@ -1208,8 +1218,15 @@ __device__ __forceinline__ void packed_cholesky(double* __restrict__ L, double* 
       }
     }
 #endif
+    PK(4)
     __syncthreads();
+    PK(5)
   }
+#ifdef CMOS_CR_TIMING
+  if ((tid == 0 || tid == 32) && blockIdx.x == 0)
+    printf("packed_cholesky tid %d n %d: solve %lld sync %lld | w0 diag-update %lld factor_diag6 %lld | trailing %lld sync %lld\n", tid, n, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5]);
+#endif
+#undef PK
 }
 
 __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {

@@ -152,3 +152,84 @@ class RefVocabulary:
         w1 = np.ascontiguousarray(a["words"], np.int32); v1 = np.ascontiguousarray(a["values"], np.float64)
         w2 = np.ascontiguousarray(b["words"], np.int32); v2 = np.ascontiguousarray(b["values"], np.float64)
         return float(self.L.ref_bow_score(self.h, _p(w1), _p(v1), len(w1), _p(w2), _p(v2), len(w2)))
+
+
+# ---------------------------------------------------------------------------------------------------
+# The reference's own Frame / KeyFrame / MapPoint / ORBmatcher (oracle/ref_shim/ref_matcher.cpp).  Same argument meaning as
+# the matching functions of oracle.pyoracle, so tests can run the two side by side.
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def frame_construct(img, nfeatures, K4, dist, scale=1.2, nlevels=8, ini_th=20, min_th=7):
+    """Frame::Frame(imgGray, ...) of the reference: returns (keypoints, undistorted keypoints, descriptors, bounds6,
+    grid_start, grid_idx)."""
+    img = np.ascontiguousarray(img, np.uint8); h, w = img.shape
+    cap = 4 * nfeatures + 64
+    kps = np.zeros(cap, KP_DTYPE); un = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+    b6 = np.zeros(6, np.float32); gs = np.zeros(64 * 48 + 1, np.int32); gi = np.zeros(cap, np.int32)
+    k = _f32(K4); d = _f32(dist)
+    n = lib().ref_frame_construct(_p(img), w, h, w, int(nfeatures), C.c_float(scale), int(nlevels), int(ini_th), int(min_th),
+                                  _p(k), _p(d), len(d), cap, _p(kps), _p(un), _p(desc), _p(b6), _p(gs), _p(gi))
+    assert n <= cap
+    return kps[:n], un[:n], desc[:n], b6, gs, gi[:gs[-1]]
+
+
+def build_grid(kps, bounds6, scale_factors):
+    kps = np.ascontiguousarray(kps); sf = _f32(scale_factors); b = _f32(bounds6)
+    gs = np.zeros(64 * 48 + 1, np.int32); gi = np.zeros(max(len(kps), 1), np.int32)
+    n = lib().ref_build_grid(_p(kps), len(kps), _p(b), _p(sf), len(sf), _p(gs), _p(gi))
+    return gs, gi[:n]
+
+
+def features_in_area(kps, bounds6, scale_factors, x, y, r, min_level, max_level):
+    kps = np.ascontiguousarray(kps); sf = _f32(scale_factors); b = _f32(bounds6)
+    out = np.zeros(max(len(kps), 1), np.int32)
+    n = lib().ref_features_in_area(_p(kps), len(kps), _p(b), _p(sf), len(sf), C.c_float(x), C.c_float(y), C.c_float(r),
+                                   int(min_level), int(max_level), _p(out))
+    return out[:n]
+
+
+def search_by_projection_frame(cur_kps, cur_desc, bounds6, K4, scale_factors, Tcw, last_kps, last_flags, last_xw, last_desc,
+                               th, check_ori, claimed=None, nn_ratio=0.9):
+    cur_kps = np.ascontiguousarray(cur_kps); cur_desc = np.ascontiguousarray(cur_desc, np.uint8)
+    last_kps = np.ascontiguousarray(last_kps); n = len(cur_kps)
+    claimed = np.zeros(max(n, 1), np.uint8) if claimed is None else claimed
+    match = np.full(max(n, 1), -1, np.int32)
+    b = _f32(bounds6); k = _f32(K4); sf = _f32(scale_factors); T = np.ascontiguousarray(Tcw, np.float64)
+    lf = np.ascontiguousarray(last_flags, np.uint8); lx = np.ascontiguousarray(last_xw, np.float64)
+    ld = np.ascontiguousarray(last_desc, np.uint8)
+    nm = lib().ref_search_by_projection_frame(_p(cur_kps), _p(cur_desc), n, _p(b), _p(k), _p(sf), len(sf), _p(T), _p(last_kps),
+                                              len(last_kps), _p(lf), _p(lx), _p(ld), C.c_float(th), int(check_ori),
+                                              C.c_float(nn_ratio), _p(claimed), _p(match))
+    return match[:n], nm, claimed[:n]
+
+
+def search_by_projection_points(kps, desc, bounds6, scale_factors, in_view, level, view_cos, proj_xy, mp_desc, has_obs, th,
+                                nn_ratio, claimed=None):
+    kps = np.ascontiguousarray(kps); desc = np.ascontiguousarray(desc, np.uint8); n = len(kps)
+    claimed = np.zeros(max(n, 1), np.uint8) if claimed is None else claimed
+    assign = np.full(max(n, 1), -1, np.int32)
+    b = _f32(bounds6); sf = _f32(scale_factors)
+    iv = np.ascontiguousarray(in_view, np.uint8); lv = np.ascontiguousarray(level, np.int32)
+    vc = _f32(view_cos); pj = _f32(proj_xy); md = np.ascontiguousarray(mp_desc, np.uint8)
+    ho = np.ascontiguousarray(has_obs, np.uint8)
+    nm = lib().ref_search_by_projection_points(_p(kps), _p(desc), n, _p(b), _p(sf), len(sf), len(iv), _p(iv), _p(lv), _p(vc),
+                                               _p(pj), _p(md), _p(ho), C.c_float(th), C.c_float(nn_ratio), _p(claimed), _p(assign))
+    return assign[:n], nm, claimed[:n]
+
+
+def is_in_frustum(pose15, K4, bounds4, scale_factors, cos_limit, xw, normal, min_dist, max_dist):
+    n = len(xw)
+    pose15 = np.ascontiguousarray(pose15, np.float64); k = _f32(K4); b = _f32(bounds4); sf = _f32(scale_factors)
+    xw = np.ascontiguousarray(xw, np.float64); normal = np.ascontiguousarray(normal, np.float64)
+    mn = _f32(min_dist); mx = _f32(max_dist)
+    in_view = np.zeros(n, np.uint8); proj = np.zeros((n, 2), np.float32); level = np.zeros(n, np.int32); vcos = np.zeros(n, np.float32)
+    lib().ref_is_in_frustum(_p(pose15), _p(k), _p(b), _p(sf), len(sf), C.c_float(cos_limit), n, _p(xw), _p(normal), _p(mn),
+                            _p(mx), _p(in_view), _p(proj), _p(level), _p(vcos))
+    return in_view, proj, level, vcos
+
+
+def descriptor_distance(a, b):
+    return lib().ref_descriptor_distance(_p(np.ascontiguousarray(a, np.uint8)), _p(np.ascontiguousarray(b, np.uint8)))

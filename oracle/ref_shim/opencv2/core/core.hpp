@@ -42,6 +42,8 @@ void orb_oracle_resize(const uint8_t* src, int sw, int sh, int spitch, uint8_t* 
 void orb_oracle_blur7(const uint8_t* src, int w, int h, int spitch, uint8_t* dst, int dpitch);
 int orb_oracle_fast(const uint8_t* img, int w, int h, int pitch, int threshold, int* out, int cap);
 void orb_oracle_fast_atan2(const float* y, const float* x, float* out, int n);
+// oracle/matcher_oracle.cpp: cv::undistortPoints restated, pinned bit-exact to cv2 4.13 (tests/test_oracle_matcher.py)
+void frame_oracle_undistort_points(const float* K4, const float* dist, int n_dist, const float* xy_in, int n, float* xy_out);
 }
 
 typedef unsigned char uchar;
@@ -132,7 +134,7 @@ class Mat {
   void create(int r, int c, int type) {
     if (data && rows == r && cols == c && type_ == type) return;
     release();
-    rows = r; cols = c; type_ = type;
+    rows = r; cols = c; type_ = type; channels_ = 1;
     step = c * shim_elem_size(type);
     whole_rows_ = r; whole_cols_ = c; ofs_x_ = ofs_y_ = 0;
     size_t bytes = step * (size_t)r;
@@ -179,6 +181,31 @@ class Mat {
     for (int y = 0; y < rows; y++) std::memmove(dst.data + (size_t)y * dst.step, data + (size_t)y * step, cols * elemSize());
   }
 
+  // element i of a single-row or single-column matrix (Frame.cc:330 reads dist_coef_.at<float>(0))
+  template <typename T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
+  template <typename T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
+  // reshape(cn): only the channel count changes, N x 2 one-channel <-> N x 1 two-channel over the same bytes (Frame.cc:343-345)
+  Mat reshape(int cn) const {
+    Mat m(*this);
+    const int total = cols * channels_;
+    assert(total % cn == 0 && step == (size_t)cols * channels_ * elemSize());
+    m.channels_ = cn; m.cols = total / cn; m.whole_cols_ = m.cols;
+    return m;
+  }
+  int channels() const { return channels_; }
+  static Mat ones(int r, int c, int type) {
+    Mat m(r, c, type);
+    for (int y = 0; y < r; y++) for (int x = 0; x < c; x++) { if (type == CV_32F) m.at<float>(y, x) = 1.f; else m.at<uchar>(y, x) = 1; }
+    return m;
+  }
+  void convertTo(Mat& dst, int type) const {      // CV_8U / CV_32F -> CV_32F, in place allowed (Frame.cc:485)
+    Mat src = (dst.data == data) ? clone() : *this;
+    if (type != CV_32F) throw std::runtime_error("cv shim: convertTo supports CV_32F targets only");
+    Mat out(src.rows, src.cols, CV_32F);
+    for (int y = 0; y < src.rows; y++)
+      for (int x = 0; x < src.cols; x++) out.at<float>(y, x) = src.type() == CV_32F ? src.at<float>(y, x) : (float)src.at<uchar>(y, x);
+    dst = out;
+  }
   template <typename T> T& at(int y, int x) { return *(T*)(data + (size_t)y * step + (size_t)x * sizeof(T)); }
   template <typename T> const T& at(int y, int x) const { return *(const T*)(data + (size_t)y * step + (size_t)x * sizeof(T)); }
   uchar* ptr(int y = 0) { return data + (size_t)y * step; }
@@ -188,12 +215,13 @@ class Mat {
 
  private:
   void share(const Mat& o) {
-    rows = o.rows; cols = o.cols; step = o.step; data = o.data; type_ = o.type_;
+    rows = o.rows; cols = o.cols; step = o.step; data = o.data; type_ = o.type_; channels_ = o.channels_;
     buf_ = o.buf_; ref_ = o.ref_;
     whole_rows_ = o.whole_rows_; whole_cols_ = o.whole_cols_; ofs_x_ = o.ofs_x_; ofs_y_ = o.ofs_y_;
     if (ref_) ++*ref_;
   }
   int type_ = CV_8U;
+  int channels_ = 1;
   uchar* buf_ = nullptr;
   long* ref_ = nullptr;
   int whole_rows_ = 0, whole_cols_ = 0, ofs_x_ = 0, ofs_y_ = 0;
@@ -308,6 +336,45 @@ inline void FAST(InputArray image_, std::vector<KeyPoint>& keypoints, int thresh
   keypoints.reserve(n);
   for (int i = 0; i < n; i++)
     keypoints.push_back(KeyPoint((float)out[3 * i], (float)out[3 * i + 1], 7.f, -1, (float)out[3 * i + 2]));
+}
+
+// The little float-matrix arithmetic Frame::ComputeStereoMatches needs (dead code in this monocular fork, but Frame.cc must
+// compile unmodified): Mat - Mat, scalar * Mat, L1 norm of a difference.
+enum { NORM_L1 = 2 };
+inline Mat operator*(double s, const Mat& a) {
+  Mat o(a.rows, a.cols, CV_32F);
+  for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) o.at<float>(y, x) = (float)(s * a.at<float>(y, x));
+  return o;
+}
+inline Mat operator-(const Mat& a, const Mat& b) {
+  Mat o(a.rows, a.cols, CV_32F);
+  for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) o.at<float>(y, x) = a.at<float>(y, x) - b.at<float>(y, x);
+  return o;
+}
+inline double norm(const Mat& a, const Mat& b, int type) {
+  if (type != NORM_L1) throw std::runtime_error("cv shim: only NORM_L1");
+  double s = 0;
+  for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) s += std::fabs((double)a.at<float>(y, x) - b.at<float>(y, x));
+  return s;
+}
+
+// cv::undistortPoints(src, dst, K, dist, R = empty, P = K) on an N x 1 two-channel CV_32F matrix (Frame.cc:344,371).
+inline void undistortPoints(InputArray src_, Mat& dst, InputArray K_, InputArray dist_, InputArray R_, InputArray P_) {
+  Mat src = src_.getMat(), K = K_.getMat(), dist = dist_.getMat(), P = P_.getMat();
+  if (!R_.empty() || src.type() != CV_32F || src.channels() != 2 || K.type() != CV_32F || dist.type() != CV_32F)
+    throw std::runtime_error("cv shim: undistortPoints supports N x 1 CV_32FC2 points, float K / dist, no rectification");
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)
+    if (K.at<float>(i, j) != P.at<float>(i, j)) throw std::runtime_error("cv shim: undistortPoints needs P == K");
+  const float K4[4] = {K.at<float>(0, 0), K.at<float>(1, 1), K.at<float>(0, 2), K.at<float>(1, 2)};
+  const int nd = dist.rows * dist.cols;
+  std::vector<float> d(nd);
+  for (int i = 0; i < nd; i++) d[i] = dist.at<float>(i);
+  const int n = src.rows * src.cols;
+  std::vector<float> in((size_t)2 * n), out((size_t)2 * n);
+  std::memcpy(in.data(), src.data, in.size() * sizeof(float));
+  frame_oracle_undistort_points(K4, d.data(), nd, in.data(), n, out.data());
+  if (dst.data != src.data) { dst.create(src.rows, src.cols * 2, CV_32F); dst = dst.reshape(2); }
+  std::memcpy(dst.data, out.data(), out.size() * sizeof(float));
 }
 
 inline float fastAtan2(float y, float x) {
