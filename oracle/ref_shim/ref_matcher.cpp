@@ -303,6 +303,276 @@ void ref_is_in_frustum(const double* pose15, const float* K4, const float* bound
   }
 }
 
+// -------------------------------------------------------------------------------------------------------------------
+// The keyframe searches (ORBmatcher.cc:128-1159, 1273-1384).  Views: kps / desc / n, bounds6 as the Frame holds them
+// (KeyFrame::KeyFrame truncates them to int itself, KeyFrame.cc:80-83), K4, scale factors.
+
+}  // extern "C"
+
+namespace {
+
+struct ViewArgs { const void* kps; const uint8_t* desc; int n; const float* bounds6; const float* K4; const float* sf; int nl; };
+
+void view_frame(Frame& F, const ViewArgs& v, const double* Tcw16) {
+  set_frame_statics(v.bounds6, v.K4);
+  fill_frame(F, v.kps, v.desc, v.n, v.sf, v.nl);
+  if (Tcw16) set_pose_rowmajor(F, Tcw16); else F.SetPose(Eigen::Matrix4d::Identity());
+}
+// pose12 = R (row-major 9) + t (3)
+void pose12_to_T(const double* p, double* T16) {
+  for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) T16[4 * r + c] = p[3 * r + c]; T16[4 * r + 3] = p[9 + r]; }
+  T16[12] = T16[13] = T16[14] = 0; T16[15] = 1;
+}
+void set_feature_vector(DBoW2::FeatureVector& fv, int nn, const int32_t* node, const int32_t* start, const int32_t* idx) {
+  fv.clear();
+  for (int k = 0; k < nn; k++)
+    for (int e = start[k]; e < start[k + 1]; e++) fv.addFeature((DBoW2::NodeId)node[k], (unsigned)idx[e]);
+}
+Eigen::Matrix4d mat4_rowmajor(const double* T16) {
+  Eigen::Matrix4d T;
+  for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) T(r, c) = T16[4 * r + c];
+  return T;
+}
+MapPoint* add_point_full(PointPool& pool, const double* xw, const double* normal, float min_d, float max_d, const uint8_t* desc) {
+  MapPoint* p = pool.add(xw, desc, 0);
+  if (normal) p->normal_vector_ = Eigen::Vector3d(normal[0], normal[1], normal[2]);
+  p->min_distance_ = min_d; p->max_distance_ = max_d;
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+// SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist) — :1273-1384
+int ref_search_by_projection_reloc(const void* kps28, const uint8_t* desc, int n, const float* bounds6, const float* K4,
+                                   const float* sf, int nl, const double* Tcw, int n_kf, const uint8_t* kf_valid,
+                                   const double* kf_xw, const float* kf_min_d, const float* kf_max_d, const uint8_t* kf_desc,
+                                   const float* kf_angle, float th, int orb_dist, int check_ori, uint8_t* cur_has_point,
+                                   int32_t* cur_match) {
+  const ViewArgs v = {kps28, desc, n, bounds6, K4, sf, nl};
+  Frame cur;
+  view_frame(cur, v, Tcw);
+  PointPool pool(sf, nl);
+  const double z3[3] = {0, 0, 1};
+  for (int i = 0; i < n; i++) if (cur_has_point[i]) cur.map_points_[i] = pool.add(z3, nullptr, 1);
+  // the keyframe: only its keypoint angles and map points are read
+  std::vector<KP28> kk(n_kf);
+  for (int i = 0; i < n_kf; i++) { KP28 k = {0, 0, 31, kf_angle[i], 0, 0, -1}; kk[i] = k; }
+  std::vector<uint8_t> kd((size_t)std::max(n_kf, 1) * 32, 0);
+  Frame kf_frame;
+  const ViewArgs kv = {kk.data(), kd.data(), n_kf, bounds6, K4, sf, nl};
+  view_frame(kf_frame, kv, nullptr);
+  KeyFrame kf(kf_frame, &pool.map, static_cast<KeyFrameDatabase*>(nullptr));
+  std::map<MapPoint*, int> kidx;
+  for (int i = 0; i < n_kf; i++)
+    if (kf_valid[i]) {
+      MapPoint* p = add_point_full(pool, kf_xw + 3 * i, nullptr, kf_min_d[i], kf_max_d[i], kf_desc + 32 * (size_t)i);
+      kf.AddMapPoint(p, i); kidx[p] = i;
+    }
+  std::set<MapPoint*> found;
+  ORBmatcher matcher(0.9f, check_ori != 0);
+  const int nm = matcher.SearchByProjection(cur, &kf, found, th, orb_dist);
+  for (int i = 0; i < n; i++) {
+    MapPoint* p = cur.map_points_[i];
+    std::map<MapPoint*, int>::const_iterator it = p ? kidx.find(p) : kidx.end();
+    cur_match[i] = it == kidx.end() ? -1 : it->second;
+    cur_has_point[i] = p != nullptr;
+  }
+  return nm;
+}
+
+// SearchByProjection(KeyFrame* pKF, Scw, vpPoints, vpMatched, th) — :258-361
+int ref_search_by_projection_sim3(const void* kps28, const uint8_t* desc, int n, const float* bounds6, const float* K4,
+                                  const float* sf, int nl, const double* Scw, int n_points, const uint8_t* pt_skip,
+                                  const double* xw, const double* normal, const float* min_d, const float* max_d,
+                                  const uint8_t* pt_desc, int th, uint8_t* matched, int32_t* assign) {
+  const ViewArgs v = {kps28, desc, n, bounds6, K4, sf, nl};
+  Frame f;
+  view_frame(f, v, nullptr);
+  PointPool pool(sf, nl);
+  KeyFrame kf(f, &pool.map, static_cast<KeyFrameDatabase*>(nullptr));
+  const double z3[3] = {0, 0, 1};
+  std::vector<MapPoint*> vpMatched(n, static_cast<MapPoint*>(nullptr));
+  for (int i = 0; i < n; i++) if (matched[i]) vpMatched[i] = pool.add(z3, nullptr, 1);
+  std::vector<MapPoint*> pts(n_points);
+  std::map<MapPoint*, int> pidx;
+  for (int p = 0; p < n_points; p++) {
+    pts[p] = add_point_full(pool, xw + 3 * p, normal + 3 * p, min_d[p], max_d[p], pt_desc + 32 * (size_t)p);
+    if (pt_skip[p]) pts[p]->is_bad_ = true;
+    pidx[pts[p]] = p;
+  }
+  ORBmatcher matcher(0.75f, true);
+  const int nm = matcher.SearchByProjection(&kf, mat4_rowmajor(Scw), pts, vpMatched, th);
+  for (int i = 0; i < n; i++) {
+    std::map<MapPoint*, int>::const_iterator it = vpMatched[i] ? pidx.find(vpMatched[i]) : pidx.end();
+    assign[i] = it == pidx.end() ? -1 : it->second;
+    matched[i] = vpMatched[i] != nullptr;
+  }
+  return nm;
+}
+
+// Fuse(KeyFrame*, vpMapPoints, th) :724-842 (sim3 == 0, pose15 = Rcw, tcw, Ow) and Fuse(KeyFrame*, Scw, vpPoints, th,
+// vpReplacePoint) :844-954 (sim3 == 1).  The keyframe starts without map points and every candidate is a distinct point, so
+// the FIRST point that decides for a keypoint is added to the keyframe there (AddMapPoint) — that index is reported in
+// added_idx[p]; later points deciding for the same keypoint go through Replace.  Returns nFused.
+int ref_fuse(const void* kps28, const uint8_t* desc, int n, const float* bounds6, const float* K4, const float* sf, int nl,
+             int sim3, const double* pose, int n_points, const uint8_t* pt_skip, const double* xw, const double* normal,
+             const float* min_d, const float* max_d, const uint8_t* pt_desc, float th, int32_t* added_idx,
+             int32_t* replace_idx) {
+  const ViewArgs v = {kps28, desc, n, bounds6, K4, sf, nl};
+  Frame f;
+  double T16[16];
+  if (!sim3) { pose12_to_T(pose, T16); view_frame(f, v, T16); } else view_frame(f, v, nullptr);
+  PointPool pool(sf, nl);
+  KeyFrame kf(f, &pool.map, static_cast<KeyFrameDatabase*>(nullptr));
+  std::vector<MapPoint*> pts(n_points);
+  for (int p = 0; p < n_points; p++) {
+    pts[p] = add_point_full(pool, xw + 3 * p, normal + 3 * p, min_d[p], max_d[p], pt_desc + 32 * (size_t)p);
+    if (pt_skip[p]) pts[p]->is_bad_ = true;
+    pool.map.AddMapPoint(pts[p]);
+  }
+  ORBmatcher matcher(0.6f, true);
+  int nf;
+  std::vector<MapPoint*> replace(n_points, static_cast<MapPoint*>(nullptr));
+  if (sim3) nf = matcher.Fuse(&kf, mat4_rowmajor(pose), pts, th, replace);
+  else nf = matcher.Fuse(&kf, pts, th);
+  std::map<MapPoint*, int> pidx;
+  for (int p = 0; p < n_points; p++) pidx[pts[p]] = p;
+  for (int p = 0; p < n_points; p++) {
+    added_idx[p] = (!pt_skip[p] && pts[p]->IsInKeyFrame(&kf)) ? pts[p]->GetIndexInKeyFrame(&kf) : -1;
+    replace_idx[p] = replace[p] ? pidx[replace[p]] : -1;
+  }
+  return nf;
+}
+
+// SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) — :956-1159.  already2 is what the reference derives from
+// vpMatches12 (the keyframe-2 index of every pre-matched point): already1_idx2[i1] = that index, -1 = none, -2 = not matched.
+int ref_search_by_sim3(const void* kps1, const uint8_t* desc1, int n1, const void* kps2, const uint8_t* desc2, int n2,
+                       const float* bounds6, const float* K4, const float* sf, int nl, const double* pose1, const double* pose2,
+                       float s12, const double* R12, const double* t12, const uint8_t* valid1, const int32_t* already1_idx2,
+                       const double* xw1, const float* min_d1, const float* max_d1, const uint8_t* mpdesc1, const uint8_t* valid2,
+                       const double* xw2, const float* min_d2, const float* max_d2, const uint8_t* mpdesc2, float th,
+                       int32_t* match12) {
+  const ViewArgs v1 = {kps1, desc1, n1, bounds6, K4, sf, nl}, v2 = {kps2, desc2, n2, bounds6, K4, sf, nl};
+  double T1[16], T2[16];
+  pose12_to_T(pose1, T1); pose12_to_T(pose2, T2);
+  Frame f1, f2;
+  view_frame(f1, v1, T1); view_frame(f2, v2, T2);
+  PointPool pool(sf, nl);
+  KeyFrame kf1(f1, &pool.map, static_cast<KeyFrameDatabase*>(nullptr)), kf2(f2, &pool.map, static_cast<KeyFrameDatabase*>(nullptr));
+  std::map<MapPoint*, int> idx2;
+  for (int i = 0; i < n1; i++)
+    if (valid1[i]) kf1.AddMapPoint(add_point_full(pool, xw1 + 3 * i, nullptr, min_d1[i], max_d1[i], mpdesc1 + 32 * (size_t)i), i);
+  for (int i = 0; i < n2; i++)
+    if (valid2[i]) {
+      MapPoint* p = add_point_full(pool, xw2 + 3 * i, nullptr, min_d2[i], max_d2[i], mpdesc2 + 32 * (size_t)i);
+      kf2.AddMapPoint(p, i); idx2[p] = i;
+    }
+  const double z3[3] = {0, 0, 1};
+  std::vector<MapPoint*> vpMatches12(n1, static_cast<MapPoint*>(nullptr));
+  for (int i = 0; i < n1; i++)
+    if (already1_idx2[i] > -2) {
+      MapPoint* dmy = pool.add(z3, nullptr, 1);
+      if (already1_idx2[i] >= 0) dmy->observations_[&kf2] = (size_t)already1_idx2[i];
+      vpMatches12[i] = dmy;
+    }
+  Eigen::Matrix3d R;
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R(r, c) = R12[3 * r + c];
+  ORBmatcher matcher(0.75f, true);
+  const int nf = matcher.SearchBySim3(&kf1, &kf2, vpMatches12, s12, R, Eigen::Vector3d(t12[0], t12[1], t12[2]), th);
+  for (int i = 0; i < n1; i++) {
+    std::map<MapPoint*, int>::const_iterator it = vpMatches12[i] ? idx2.find(vpMatches12[i]) : idx2.end();
+    match12[i] = it == idx2.end() ? -1 : it->second;
+  }
+  return nf;
+}
+
+// SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) :148-256 (mode 0: match[idx of F] = idx of KF) and
+// SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) :462-580 (mode 1: match[idx1] = idx2).
+int ref_search_by_bow(int mode, const void* kps1, const uint8_t* desc1, int n1, const uint8_t* valid1, int nn1,
+                      const int32_t* node1, const int32_t* start1, const int32_t* feat1, const void* kps2, const uint8_t* desc2,
+                      int n2, const uint8_t* valid2, int nn2, const int32_t* node2, const int32_t* start2, const int32_t* feat2,
+                      const float* bounds6, const float* K4, const float* sf, int nl, float nn_ratio, int check_ori,
+                      int32_t* match) {
+  const ViewArgs v1 = {kps1, desc1, n1, bounds6, K4, sf, nl}, v2 = {kps2, desc2, n2, bounds6, K4, sf, nl};
+  Frame f1, f2;
+  view_frame(f1, v1, nullptr); view_frame(f2, v2, nullptr);
+  set_feature_vector(f1.feature_vector_, nn1, node1, start1, feat1);
+  set_feature_vector(f2.feature_vector_, nn2, node2, start2, feat2);
+  PointPool pool(sf, nl);
+  KeyFrame kf1(f1, &pool.map, static_cast<KeyFrameDatabase*>(nullptr));
+  const double z3[3] = {0, 0, 1};
+  std::map<MapPoint*, int> i1;
+  for (int i = 0; i < n1; i++)
+    if (valid1[i]) { MapPoint* p = pool.add(z3, nullptr, 1); kf1.AddMapPoint(p, i); i1[p] = i; }
+  ORBmatcher matcher(nn_ratio, check_ori != 0);
+  if (mode == 0) {
+    std::vector<MapPoint*> out;
+    const int nm = matcher.SearchByBoW(&kf1, f2, out);
+    for (int i = 0; i < n2; i++) {
+      std::map<MapPoint*, int>::const_iterator it = out[i] ? i1.find(out[i]) : i1.end();
+      match[i] = it == i1.end() ? -1 : it->second;
+    }
+    return nm;
+  }
+  KeyFrame kf2(f2, &pool.map, static_cast<KeyFrameDatabase*>(nullptr));
+  std::map<MapPoint*, int> i2;
+  for (int i = 0; i < n2; i++)
+    if (valid2[i]) { MapPoint* p = pool.add(z3, nullptr, 1); kf2.AddMapPoint(p, i); i2[p] = i; }
+  std::vector<MapPoint*> out;
+  const int nm = matcher.SearchByBoW(&kf1, &kf2, out);
+  for (int i = 0; i < n1; i++) {
+    std::map<MapPoint*, int>::const_iterator it = out[i] ? i2.find(out[i]) : i2.end();
+    match[i] = it == i2.end() ? -1 : it->second;
+  }
+  return nm;
+}
+
+// SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo = false) — :582-722 with CheckDistEpipolarLine :128-146
+int ref_search_for_triangulation(const void* kps1, const uint8_t* desc1, int n1, const uint8_t* has1, int nn1, const int32_t* node1,
+                                 const int32_t* start1, const int32_t* feat1, const void* kps2, const uint8_t* desc2, int n2,
+                                 const uint8_t* has2, int nn2, const int32_t* node2, const int32_t* start2, const int32_t* feat2,
+                                 const double* F12, const double* pose1, const double* pose2, const float* bounds6,
+                                 const float* K4, const float* sf, int nl, int check_ori, int32_t* match12) {
+  const ViewArgs v1 = {kps1, desc1, n1, bounds6, K4, sf, nl}, v2 = {kps2, desc2, n2, bounds6, K4, sf, nl};
+  double T1[16], T2[16];
+  pose12_to_T(pose1, T1); pose12_to_T(pose2, T2);
+  Frame f1, f2;
+  view_frame(f1, v1, T1); view_frame(f2, v2, T2);
+  set_feature_vector(f1.feature_vector_, nn1, node1, start1, feat1);
+  set_feature_vector(f2.feature_vector_, nn2, node2, start2, feat2);
+  PointPool pool(sf, nl);
+  KeyFrame kf1(f1, &pool.map, static_cast<KeyFrameDatabase*>(nullptr)), kf2(f2, &pool.map, static_cast<KeyFrameDatabase*>(nullptr));
+  const double z3[3] = {0, 0, 1};
+  for (int i = 0; i < n1; i++) if (has1[i]) kf1.AddMapPoint(pool.add(z3, nullptr, 1), i);
+  for (int i = 0; i < n2; i++) if (has2[i]) kf2.AddMapPoint(pool.add(z3, nullptr, 1), i);
+  Eigen::Matrix3d F;
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) F(r, c) = F12[3 * r + c];
+  std::vector<std::pair<size_t, size_t> > pairs;
+  ORBmatcher matcher(0.6f, check_ori != 0);
+  const int nm = matcher.SearchForTriangulation(&kf1, &kf2, F, pairs, false);
+  for (int i = 0; i < n1; i++) match12[i] = -1;
+  for (size_t k = 0; k < pairs.size(); k++) match12[pairs[k].first] = (int32_t)pairs[k].second;
+  return nm;
+}
+
+// SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) — :364-460
+int ref_search_for_initialization(const void* kps1, const uint8_t* desc1, int n1, const void* kps2, const uint8_t* desc2, int n2,
+                                  const float* bounds6, const float* K4, const float* sf, int nl, float* prev_matched,
+                                  int window_size, float nn_ratio, int check_ori, int32_t* match12) {
+  const ViewArgs v1 = {kps1, desc1, n1, bounds6, K4, sf, nl}, v2 = {kps2, desc2, n2, bounds6, K4, sf, nl};
+  Frame f1, f2;
+  view_frame(f1, v1, nullptr); view_frame(f2, v2, nullptr);
+  std::vector<cv::Point2f> prev(n1);
+  for (int i = 0; i < n1; i++) prev[i] = cv::Point2f(prev_matched[2 * i], prev_matched[2 * i + 1]);
+  std::vector<int> m12;
+  ORBmatcher matcher(nn_ratio, check_ori != 0);
+  const int nm = matcher.SearchForInitialization(f1, f2, prev, m12, window_size);
+  for (int i = 0; i < n1; i++) { match12[i] = m12[i]; prev_matched[2 * i] = prev[i].x; prev_matched[2 * i + 1] = prev[i].y; }
+  return nm;
+}
+
 // ORBmatcher::DescriptorDistance (ORBmatcher.cc:1422-1437)
 int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
   cv::Mat ma(1, 32, CV_8U), mb(1, 32, CV_8U);

@@ -173,3 +173,133 @@ def oracle_init(S, c, window=100, nn_ratio=0.9, check_ori=True):
 def gpu_init(m, S, c, window=100):
     gpu_bind(m, S, 0, 1, False); gpu_bind(m, S, 1, 2, False)
     return m.SearchForInitialization(c["prev"], window)
+
+
+# ---- the REFERENCE's own ORBmatcher over real KeyFrame / MapPoint objects (oracle/_ref, oracle/ref_shim/ref_matcher.cpp) ----
+def _ref_view(S, which):
+    from oracle.pyoracle import _p
+    k, d = (S["k1"], S["desc1"]) if which == 1 else (S["k2"], S["desc2"])
+    k = np.ascontiguousarray(k); d = np.ascontiguousarray(d, np.uint8)
+    return k, d, (_p(k), _p(d), len(k))
+
+
+def _ref_cam(S):
+    from oracle.pyoracle import _p
+    b = bounds6(S); K = np.array(S["K"], np.float32); sf = np.ascontiguousarray(S["sf"], np.float32)
+    return (b, K, sf), (_p(b), _p(K), _p(sf), len(sf))
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dt)
+
+
+def ref_reloc(S, c, check_ori=True):
+    import ctypes as C
+    from oracle import pyref as pr
+    from oracle.pyoracle import _p
+    k, d, v = _ref_view(S, 2); keep, cam = _ref_cam(S)
+    hp = _c(c["cur_has_point"], np.uint8).copy(); match = np.full(max(len(k), 1), -1, np.int32)
+    T = _c(c["Tcw"], np.float64); va = _c(c["kf_valid"], np.uint8); xw = _c(c["kf_xw"], np.float64)
+    mn = _c(c["kf_min_d"], np.float32); mx = _c(c["kf_max_d"], np.float32); kd = _c(c["kf_desc"], np.uint8); an = _c(c["kf_angle"], np.float32)
+    nm = pr.lib().ref_search_by_projection_reloc(*v, *cam, _p(T), len(va), _p(va), _p(xw), _p(mn), _p(mx), _p(kd), _p(an),
+                                                 C.c_float(c["th"]), int(c["orb_dist"]), int(check_ori), _p(hp), _p(match))
+    return match[:len(k)], nm, hp
+
+
+def ref_proj_sim3(S, c, th=10):
+    from oracle import pyref as pr
+    from oracle.pyoracle import _p
+    k, d, v = _ref_view(S, 2); keep, cam = _ref_cam(S)
+    m = _c(c["matched"], np.uint8).copy(); assign = np.full(max(len(k), 1), -1, np.int32)
+    Scw = _c(c["Scw"], np.float64); sk = _c(c["pt_skip"], np.uint8); x = _c(c["xw"], np.float64); nr = _c(c["normal"], np.float64)
+    mn = _c(c["min_d"], np.float32); mx = _c(c["max_d"], np.float32); pd = _c(c["pt_desc"], np.uint8)
+    nm = pr.lib().ref_search_by_projection_sim3(*v, *cam, _p(Scw), len(sk), _p(sk), _p(x), _p(nr), _p(mn), _p(mx), _p(pd), int(th),
+                                                _p(m), _p(assign))
+    return assign[:len(k)], nm, m
+
+
+def ref_fuse(S, c, sim3, th=3.0):
+    """Returns (added_idx, replace_idx, nFused): keypoint index where point p was ADDED to the keyframe (-1: not added), for the
+    Sim3 variant the point p that vpReplacePoint[p] names, and the reference's return value."""
+    import ctypes as C
+    from oracle import pyref as pr
+    from oracle.pyoracle import _p
+    k, d, v = _ref_view(S, 2); keep, cam = _ref_cam(S)
+    n = len(c["pt_skip"])
+    added = np.full(max(n, 1), -1, np.int32); repl = np.full(max(n, 1), -1, np.int32)
+    R2 = np.asarray(c["pose15"][:9]).reshape(3, 3); t2 = np.asarray(c["pose15"][9:12])
+    pose = _c(c["Scw"], np.float64) if sim3 else _c(np.concatenate([R2.reshape(-1), t2]), np.float64)
+    sk = _c(c["pt_skip"], np.uint8); x = _c(c["xw"], np.float64); nr = _c(c["normal"], np.float64)
+    mn = _c(c["min_d"], np.float32); mx = _c(c["max_d"], np.float32); pd = _c(c["pt_desc"], np.uint8)
+    nf = pr.lib().ref_fuse(*v, *cam, int(sim3), _p(pose), n, _p(sk), _p(x), _p(nr), _p(mn), _p(mx), _p(pd), C.c_float(th),
+                           _p(added), _p(repl))
+    return added[:n], repl[:n], nf
+
+
+def sim3_consistent_case(c, n2, seed=0):
+    """SearchBySim3 derives vbAlreadyMatched2 from vpMatches12 (the keyframe-2 index of every pre-matched point, :990-1000):
+    pair the case's two independent `already` sets up so that the oracle and the reference see the same input."""
+    rng = np.random.default_rng(seed)
+    a1 = np.nonzero(c["side1"][1])[0]; a2 = np.nonzero(c["side2"][1])[0]
+    idx2 = np.full(len(c["side1"][1]), -2, np.int32)
+    take = a2[: len(a1)]
+    idx2[a1] = -1
+    idx2[a1[: len(take)]] = take
+    already2 = np.zeros(n2, np.uint8); already2[take] = 1
+    c2 = dict(c)
+    c2["side2"] = (c["side2"][0], already2) + tuple(c["side2"][2:])
+    c2["already1_idx2"] = idx2
+    return c2
+
+
+def ref_sim3(S, c, th=7.5):
+    import ctypes as C
+    from oracle import pyref as pr
+    from oracle.pyoracle import _p
+    k1, d1, v1 = _ref_view(S, 1); k2, d2, v2 = _ref_view(S, 2); keep, cam = _ref_cam(S)
+    s1, s2 = c["side1"], c["side2"]
+    a = [_c(c["pose1"], np.float64), _c(c["pose2"], np.float64), _c(c["R12"], np.float64), _c(c["t12"], np.float64),
+         _c(s1[0], np.uint8), _c(c["already1_idx2"], np.int32), _c(s1[2], np.float64), _c(s1[3], np.float32), _c(s1[4], np.float32),
+         _c(s1[5], np.uint8), _c(s2[0], np.uint8), _c(s2[2], np.float64), _c(s2[3], np.float32), _c(s2[4], np.float32), _c(s2[5], np.uint8)]
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    nf = pr.lib().ref_search_by_sim3(*v1, *v2, *cam, _p(a[0]), _p(a[1]), C.c_float(c["s12"]), _p(a[2]), _p(a[3]), *[_p(x) for x in a[4:]],
+                                     C.c_float(th), _p(m12))
+    return m12[:len(k1)], nf
+
+
+def ref_bow(S, c, mode, nn_ratio=0.75, check_ori=True):
+    import ctypes as C
+    from oracle import pyref as pr
+    from oracle.pyoracle import _p, _fv
+    k1, d1, v1 = _ref_view(S, 1); k2, d2, v2 = _ref_view(S, 2); keep, cam = _ref_cam(S)
+    va1 = _c(c["valid1"], np.uint8); va2 = _c(c["valid2"] if mode == 1 else np.ones(len(k2)), np.uint8)
+    n1, s1, f1 = _fv(c["fv1"]); n2, s2, f2 = _fv(c["fv2"])
+    n_out = len(k2) if mode == 0 else len(k1)
+    match = np.full(max(n_out, 1), -1, np.int32)
+    nm = pr.lib().ref_search_by_bow(int(mode), *v1, _p(va1), len(n1), _p(n1), _p(s1), _p(f1), *v2, _p(va2), len(n2), _p(n2), _p(s2),
+                                    _p(f2), *cam, C.c_float(nn_ratio), int(check_ori), _p(match))
+    return match[:n_out], nm
+
+
+def ref_triangulation(S, c, check_ori=True):
+    from oracle import pyref as pr
+    from oracle.pyoracle import _p, _fv
+    k1, d1, v1 = _ref_view(S, 1); k2, d2, v2 = _ref_view(S, 2); keep, cam = _ref_cam(S)
+    h1 = _c(c["has1"], np.uint8); h2 = _c(c["has2"], np.uint8)
+    n1, s1, f1 = _fv(c["fv1"]); n2, s2, f2 = _fv(c["fv2"])
+    F = _c(c["F12"], np.float64)
+    p1 = _c(np.concatenate([S["R1"].reshape(-1), S["t1"]]), np.float64); p2 = _c(np.concatenate([S["R2"].reshape(-1), S["t2"]]), np.float64)
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    nm = pr.lib().ref_search_for_triangulation(*v1, _p(h1), len(n1), _p(n1), _p(s1), _p(f1), *v2, _p(h2), len(n2), _p(n2), _p(s2),
+                                               _p(f2), _p(F), _p(p1), _p(p2), *cam, int(check_ori), _p(m12))
+    return m12[:len(k1)], nm
+
+
+def ref_init(S, c, window=100, nn_ratio=0.9, check_ori=True):
+    import ctypes as C
+    from oracle import pyref as pr
+    from oracle.pyoracle import _p
+    k1, d1, v1 = _ref_view(S, 1); k2, d2, v2 = _ref_view(S, 2); keep, cam = _ref_cam(S)
+    prev = _c(c["prev"], np.float32).copy(); m12 = np.full(max(len(k1), 1), -1, np.int32)
+    nm = pr.lib().ref_search_for_initialization(*v1, *v2, *cam, _p(prev), int(window), C.c_float(nn_ratio), int(check_ori), _p(m12))
+    return m12[:len(k1)], nm, prev

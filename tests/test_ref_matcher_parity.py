@@ -193,3 +193,104 @@ def test_cuda_search_by_projection_points_equals_reference(scene):
                                             v[5][None], npnt, 3.0)
     ra, rnm, _ = pr.search_by_projection_points(ck, cd, b, sf, *v, 3.0, 0.8)
     assert nm[0] == rnm and np.array_equal(assign[0, :n], ra)
+
+
+# ------------------------------------------------------------------------------------------------ keyframe searches (a11-a15)
+
+from tests import kf_cases as kc                      # noqa: E402
+from tests.matcher_scenarios import make_two_views    # noqa: E402
+
+
+@pytest.fixture(scope="module", params=["sparse", "crowded"])
+def two_views(request):
+    if request.param == "sparse":
+        return make_two_views(n=1200, seed=0)
+    # crowded: few distinct descriptors, many ties and long claim chains (the GPU tests' second scenario)
+    S = make_two_views(n=500, seed=5, width=400, height=300, n_extra=100, flip_bits=2)
+    rng = np.random.default_rng(7)
+    base = rng.integers(0, 256, (6, 32)).astype(np.uint8)
+    for key in ("desc1", "desc2", "mp_desc"):
+        S[key] = base[rng.integers(0, 6, len(S[key]))]
+    return S
+
+
+def test_reference_reloc_projection(two_views):
+    S = two_views
+    c = kc.case_reloc(S)
+    om, onm, ohp = kc.oracle_reloc(S, c)
+    rm, rnm, rhp = kc.ref_reloc(S, c)
+    assert rnm == onm and np.array_equal(rm, om) and np.array_equal(rhp, ohp)
+
+
+def test_reference_sim3_projection(two_views):
+    S = two_views
+    c = kc.case_points(S)
+    oa, onm, om = kc.oracle_proj_sim3(S, c)
+    ra, rnm, rm = kc.ref_proj_sim3(S, c)
+    assert rnm == onm and np.array_equal(ra, oa) and np.array_equal(rm, om)
+
+
+@pytest.mark.parametrize("sim3", [0, 1])
+def test_reference_fuse(two_views, sim3):
+    """The reference mutates the map inside Fuse; the oracle / CUDA path return per-point decisions that the adapter applies.
+    Comparable without re-implementing Replace: the return value, and for every point the reference ADDED to the keyframe
+    (first to decide for a free keypoint) the keypoint index equals the oracle's decision for it."""
+    S = two_views
+    c = kc.case_points(S)
+    order = c["order"]
+    first = np.zeros(len(order), bool)
+    seen = set()
+    for i, p in enumerate(order):           # the case repeats points; the reference would see the SAME MapPoint* twice
+        if p not in seen:
+            first[i] = True; seen.add(p)
+    c = {k: (v[first] if isinstance(v, np.ndarray) and len(v) == len(order) else v) for k, v in c.items()}
+    obi, obd, onf = kc.oracle_fuse(S, c, sim3)
+    added, repl, rnf = kc.ref_fuse(S, c, sim3)
+    assert rnf == onf
+    if sim3 == 0:
+        got = added >= 0
+        assert got.sum() > 0 and np.array_equal(added[got], obi[got])
+        # every oracle decision is either an addition or a replacement of the point that sits there
+        dec = np.nonzero(obi >= 0)[0]
+        owner = {int(added[p]): p for p in np.nonzero(got)[0]}
+        assert all(int(obi[p]) in owner for p in dec)
+    else:
+        # Fuse(KF, Scw, ...) adds the first decider of a free keypoint and records later ones in vpReplacePoint (:938-947)
+        got = added >= 0
+        assert got.sum() > 0 and np.array_equal(added[got], obi[got])
+        owner = {int(added[p]): p for p in np.nonzero(got)[0]}
+        for p in np.nonzero((obi >= 0) & ~got)[0]:
+            assert repl[p] == owner[int(obi[p])], "vpReplacePoint names the point that already sits at the decided keypoint"
+
+
+def test_reference_search_by_sim3(two_views):
+    S = two_views
+    c = kc.sim3_consistent_case(kc.case_sim3(S), len(S["k2"]))
+    om, onf = kc.oracle_sim3(S, c)
+    rm, rnf = kc.ref_sim3(S, c)
+    assert rnf == onf and np.array_equal(rm, om) and onf > 5
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_reference_search_by_bow(two_views, mode):
+    S = two_views
+    c = kc.case_bow(S)
+    om, onm = kc.oracle_bow(S, c, mode)
+    rm, rnm = kc.ref_bow(S, c, mode)
+    assert rnm == onm and np.array_equal(rm, om) and onm > 5
+
+
+def test_reference_search_for_triangulation(two_views):
+    S = two_views
+    c = kc.case_triangulation(S)
+    om, onm = kc.oracle_triangulation(S, c)
+    rm, rnm = kc.ref_triangulation(S, c)
+    assert rnm == onm and np.array_equal(rm, om) and onm > 5
+
+
+def test_reference_search_for_initialization(two_views):
+    S = two_views
+    c = kc.case_init(S)
+    om, onm, oprev = kc.oracle_init(S, c)
+    rm, rnm, rprev = kc.ref_init(S, c)
+    assert rnm == onm and np.array_equal(rm, om) and np.array_equal(rprev, oprev)
