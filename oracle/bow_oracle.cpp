@@ -8,8 +8,9 @@
 //   BowVector::addWeight / normalize      /root/reference/lib/DBoW2/DBoW2/BowVector.cpp:34-84
 //   FeatureVector::addFeature             /root/reference/lib/DBoW2/DBoW2/FeatureVector.cpp:31-45
 // for the weighting / scoring of ORBvoc.txt (TF_IDF, L1_NORM: loadFromTextFile, TemplatedVocabulary.h:1330-1420).
-// DBoW2 needs OpenCV's C++ headers to compile, which this image lacks, and the reference has no tests for it:
-// PARITY UNPINNED; the restatement is checked against brute force in tests/test_oracle_matcher2.py.
+// PINNED TO THE REFERENCE ITSELF: tests/test_ref_parity.py loads the same vocabulary into the reference's own vendored
+// DBoW2 (compiled unmodified into oracle/_ref/libref.so, loadFromTextFile) and requires identical BowVector values (bit for
+// bit) and FeatureVector; tests/test_oracle_matcher2.py adds a brute-force descent.
 //
 // The vocabulary tree is passed flattened: node 0 is the root; children of node i are
 // children[child_start[i] .. child_start[i+1]) in stored order; a node without children is a leaf with a word id and

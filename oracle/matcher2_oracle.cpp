@@ -12,9 +12,11 @@
 //   KeyFrame::GetFeaturesInArea / IsInImage                               /root/reference/src/KeyFrame.cc:575-626
 //   MapPoint::PredictScale, Get{Min,Max}DistanceInvariance                /root/reference/src/MapPoint.cc:380-420
 //   MapPoint::ComputeDistinctiveDescriptors, UpdateNormalAndDepth         /root/reference/src/MapPoint.cc:256-315,335-378
-// Own code of the reference, integer Hamming + float32/float64 geometry.  The reference has no tests for any of it:
-// PARITY UNPINNED by the reference; this restatement follows the source statement by statement and is checked
-// against hand-built known answers and brute force in tests/test_oracle_matcher2.py.
+// Own code of the reference, integer Hamming + float32/float64 geometry.  The reference has no tests for any of it.
+// PINNED TO THE REFERENCE ITSELF: tests/test_ref_matcher_parity.py runs the reference's own, unmodified src/ORBmatcher.cc,
+// KeyFrame.cc and MapPoint.cc (oracle/_ref/libref.so, built by oracle/ref_shim/Makefile against stand-ins for the absent
+// OpenCV / Eigen / glog headers) over real KeyFrame / MapPoint objects and requires identical matches from this
+// restatement; tests/test_oracle_matcher2.py adds hand-built known answers and brute force.
 //
 // Flattening.  A MapPoint* is an index into the caller's arrays; predicates on the pointer graph
 // that do not change during a call are bytes prepared by the caller ("pMP && !pMP->isBad() && !found.count(pMP)").

@@ -10,8 +10,13 @@
 //   ORBmatcher::DescriptorDistance               /root/reference/src/ORBmatcher.cc:1422-1437
 //   Frame::isInFrustum, MapPoint::PredictScale   /root/reference/src/Frame.cc:191-241, MapPoint.cc:405-420
 // All of this is the reference's own code (no third-party arithmetic), integer Hamming distances plus
-// float32/float64 geometry.  The reference has no tests for it: parity is pinned by this restatement
-// and by the brute-force cross-checks in tests/test_oracle_matcher.py.  Float policy as orb_oracle.cpp.
+// float32/float64 geometry.  The reference has no tests for it.  PINNED TO THE REFERENCE ITSELF:
+// tests/test_ref_matcher_parity.py runs the reference's own, unmodified src/ORBmatcher.cc, Frame.cc and MapPoint.cc
+// (oracle/_ref/libref.so, recipe oracle/ref_shim/Makefile) over real Frame / MapPoint objects — Frame::Frame end to end,
+// the grid, GetFeaturesInArea, isInFrustum / PredictScale, both SearchByProjection variants — and requires identical
+// results from this restatement; tests/test_oracle_matcher.py adds brute-force cross-checks.  The one modelling choice is
+// the association of Eigen's 3-term product sums (Eigen is unvendored; see oracle/ref_shim/Eigen/Core).
+// Float policy as orb_oracle.cpp.
 //
 // Pointer graphs are flattened: a MapPoint* becomes an index; "F.map_points_[idx] &&
 // F.map_points_[idx]->Observations() > 0" becomes a per-keypoint `claimed` byte that the call updates as

@@ -14,9 +14,11 @@
 // cv::FAST TYPE_9_16 + NMS, cv::GaussianBlur 7x7 s=2, cv::fastAtan2, cvRound) are third-party and
 // NOT vendored in /root/reference (CMakeLists.txt:21, unpinned).  They are restated here from OpenCV's
 // published fixed-point algorithms and PINNED against cv2 4.13.0 (the only OpenCV in this image) by
-// tests/test_oracle_orb.py, bit for bit.  The reference itself ships no tests or golden vectors
-// (SURVEY.md §4): parity for this path is therefore "pinned to OpenCV 4.13 semantics + this restatement",
-// not to outputs of the reference binary (which cannot be built here: no OpenCV/Eigen/Ceres C++).
+// tests/test_oracle_orb.py, bit for bit.  The reference itself ships no tests or golden vectors.
+// The reference's OWN code of this path is PINNED TO THE REFERENCE ITSELF: tests/test_ref_parity.py compiles the unmodified
+// src/ORBextractor.cc against a minimal OpenCV stand-in (oracle/ref_shim/, whose five image primitives are the restatements
+// below) and requires keypoints, descriptors and bordered pyramid levels identical to this file's, on the BASELINE
+// configs[0] / configs[1] frames and on edge images.
 //
 // Float policy (SURVEY.md §7 hard part 2): compiled with -ffp-contract=off, no -march=native;
 // cosf/sinf are glibc's; cvRound is round-half-to-even.

@@ -573,6 +573,65 @@ int ref_search_for_initialization(const void* kps1, const uint8_t* desc1, int n1
   return nm;
 }
 
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:256-315) and MapPoint::UpdateNormalAndDepth (:335-378) on real
+// MapPoint / KeyFrame objects.  Observation lists are CSR by point (obs_start), obs_kf ascending and distinct inside a
+// point; the keyframes are constructed in one block in index order, so the reference's std::map<KeyFrame*, size_t>
+// iterates a point's observations in list order.  out_desc[p] = descriptor_ after the call (zeros for an empty list).
+void ref_map_point_maintenance(int n_points, const int32_t* obs_start, const int32_t* obs_kf, const uint8_t* obs_desc, int n_kf,
+                               const double* Ow, const double* pos, const int32_t* ref_kf, const int32_t* ref_level,
+                               const float* sf, int nl, const float* bounds6, const float* K4, uint8_t* out_desc,
+                               double* normal, float* min_d, float* max_d) {
+  set_frame_statics(bounds6, K4);
+  // rows of every keyframe: one keypoint per observation it hosts
+  std::vector<std::vector<int> > rows(n_kf);           // observation ids per keyframe
+  const int n_obs = obs_start[n_points];
+  std::vector<int> row_of(n_obs);
+  for (int o = 0; o < n_obs; o++) { row_of[o] = (int)rows[obs_kf[o]].size(); rows[obs_kf[o]].push_back(o); }
+  std::vector<int> obs_point(n_obs);
+  for (int p = 0; p < n_points; p++) for (int o = obs_start[p]; o < obs_start[p + 1]; o++) obs_point[o] = p;
+  PointPool pool(sf, nl);
+  // raw block: keyframe k lives at block + k * sizeof(KeyFrame)  (ascending addresses == ascending index)
+  void* block = ::operator new(sizeof(KeyFrame) * (size_t)std::max(n_kf, 1) + 64);
+  KeyFrame* kfs = (KeyFrame*)(((uintptr_t)block + 63) & ~(uintptr_t)63);
+  for (int k = 0; k < n_kf; k++) {
+    const int m = (int)rows[k].size();
+    std::vector<KP28> kk(std::max(m, 1));
+    std::vector<uint8_t> dd((size_t)std::max(m, 1) * 32, 0);
+    for (int r = 0; r < m; r++) {
+      const int o = rows[k][r], p = obs_point[o];
+      KP28 kp = {0, 0, 31, 0, 0, (ref_kf[p] == k) ? ref_level[p] : 0, -1};
+      kk[r] = kp;
+      std::memcpy(&dd[32 * (size_t)r], obs_desc + 32 * (size_t)o, 32);
+    }
+    Frame f;
+    fill_frame(f, kk.data(), dd.data(), m, sf, nl);
+    Eigen::Matrix4d T = Eigen::Matrix4d::Identity();
+    for (int a = 0; a < 3; a++) T(a, 3) = -Ow[3 * k + a];      // R = I: Ow = -R' t
+    f.SetPose(T);
+    new (&kfs[k]) KeyFrame(f, &pool.map, static_cast<KeyFrameDatabase*>(nullptr));
+  }
+  const double z3[3] = {0, 0, 1};
+  for (int p = 0; p < n_points; p++) {
+    MapPoint* mp = pool.add(pos + 3 * p, nullptr, 0);
+    mp->normal_vector_ = Eigen::Vector3d(normal[3 * p], normal[3 * p + 1], normal[3 * p + 2]);
+    mp->min_distance_ = min_d[p]; mp->max_distance_ = max_d[p];
+    mp->descriptor_.create(1, 32, CV_8U);
+    std::memset(mp->descriptor_.data, 0, 32);
+    for (int o = obs_start[p]; o < obs_start[p + 1]; o++) mp->observations_[&kfs[obs_kf[o]]] = (size_t)row_of[o];
+    mp->n_observations_ = obs_start[p + 1] - obs_start[p];
+    mp->reference_keyframe_ = n_kf > 0 ? &kfs[ref_kf[p]] : nullptr;
+    mp->ComputeDistinctiveDescriptors();
+    mp->UpdateNormalAndDepth();
+    std::memcpy(out_desc + 32 * (size_t)p, mp->descriptor_.data, 32);
+    const Eigen::Vector3d nv = mp->GetNormal();
+    normal[3 * p] = nv(0); normal[3 * p + 1] = nv(1); normal[3 * p + 2] = nv(2);
+    min_d[p] = mp->min_distance_; max_d[p] = mp->max_distance_;
+  }
+  (void)z3;
+  for (int k = 0; k < n_kf; k++) kfs[k].~KeyFrame();
+  ::operator delete(block);
+}
+
 // ORBmatcher::DescriptorDistance (ORBmatcher.cc:1422-1437)
 int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
   cv::Mat ma(1, 32, CV_8U), mb(1, 32, CV_8U);

@@ -294,3 +294,39 @@ def test_reference_search_for_initialization(two_views):
     om, onm, oprev = kc.oracle_init(S, c)
     rm, rnm, rprev = kc.ref_init(S, c)
     assert rnm == onm and np.array_equal(rm, om) and np.array_equal(rprev, oprev)
+
+
+def test_reference_map_point_maintenance():
+    """MapPoint::ComputeDistinctiveDescriptors and UpdateNormalAndDepth of the reference on real MapPoint / KeyFrame objects
+    against the oracle.  min / max distance as the reference stores them (GetMin/MaxDistanceInvariance
+    apply 0.8 / 1.2 on read)."""
+    import ctypes as C
+    from oracle.pyoracle import _p
+    from tests.matcher_scenarios import make_map_observations
+    M = make_map_observations(n_points=1500, n_keyframes=60, seed=7, max_obs=40)
+    rng = np.random.default_rng(3)
+    st = M["start"]; obs_kf = M["obs_kf"].copy(); ref_kf = M["ref_kf"].copy()
+    for p in range(len(st) - 1):                   # a std::map<KeyFrame*, size_t> holds each keyframe once, in address order
+        n = st[p + 1] - st[p]
+        if n:
+            obs_kf[st[p]:st[p + 1]] = np.sort(rng.choice(60, n, replace=False))
+            ref_kf[p] = obs_kf[st[p] + rng.integers(0, n)]
+    sf = np.empty(8, np.float32); sf[0] = 1
+    for i in range(1, 8):
+        sf[i] = np.float32(np.float64(sf[i - 1]) * np.float64(np.float32(1.2)))
+    obest = po.distinctive_descriptors(st, M["desc"])
+    on, omn, omx = po.update_normal_and_depth(st, obs_kf, M["Ow"], M["pos"], ref_kf, M["ref_level"], sf, M["normal0"], M["min0"], M["max0"])
+    npnt = len(st) - 1
+    out_desc = np.zeros((npnt, 32), np.uint8)
+    nr = np.ascontiguousarray(M["normal0"], np.float64).copy(); mn = M["min0"].copy(); mx = M["max0"].copy()
+    b6 = np.array([0, 1241, 0, 376, 64 / 1241, 48 / 376], np.float32); K4 = np.array(synth.KITTI_K, np.float32)
+    okf = np.ascontiguousarray(obs_kf, np.int32); od = np.ascontiguousarray(M["desc"], np.uint8)
+    Ow = np.ascontiguousarray(M["Ow"], np.float64); pos = np.ascontiguousarray(M["pos"], np.float64)
+    rk = np.ascontiguousarray(ref_kf, np.int32); rl = np.ascontiguousarray(M["ref_level"], np.int32)
+    pr.lib().ref_map_point_maintenance(npnt, _p(st), _p(okf), _p(od), 60, _p(Ow), _p(pos), _p(rk), _p(rl), _p(sf), 8, _p(b6), _p(K4),
+                                       _p(out_desc), _p(nr), _p(mn), _p(mx))
+    has = obest >= 0
+    assert has.sum() > 1000
+    assert np.array_equal(out_desc[has], M["desc"][st[:-1][has] + obest[has]])
+    assert not out_desc[~has].any()
+    assert np.array_equal(nr, on) and np.array_equal(mn, omn) and np.array_equal(mx, omx)
