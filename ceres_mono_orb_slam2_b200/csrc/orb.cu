@@ -1348,6 +1348,17 @@ int cmos_orb_finish(cmos_orb_t h, void* stream) {
   return CMOS_OK;
 }
 
+// The overflow word alone (pinned host memory, written behind the kernels): for callers that waited on an event of their own.
+int cmos_orb_check_overflow(cmos_orb_t h) {
+  CMOS_REQUIRE(h, "null handle");
+  if (h->h_overflow && *h->h_overflow) {
+    *h->h_overflow = 0;
+    set_error("FAST candidate buffer overflow");
+    return CMOS_ERR_CAPACITY;
+  }
+  return CMOS_OK;
+}
+
 int cmos_orb_download(cmos_orb_t h, int32_t n_frames, cmos_keypoint* keypoints, uint8_t* descriptors,
                       int32_t* counts, int32_t capacity, void* stream) {
   CMOS_REQUIRE(h && counts, "null argument");

@@ -26,6 +26,16 @@ struct Lane {
   int *d_last_counts = nullptr, *d_match = nullptr, *d_nm = nullptr;
   uint8_t *d_flags = nullptr, *d_last_desc = nullptr;
 };
+
+constexpr int kTrackSlots = 4;        // batches that may be in flight between cmos_track_submit and cmos_track_wait
+struct Slot {
+  bool busy = false;
+  int64_t ticket = -1;
+  std::vector<cudaEvent_t> done;      // one event per lane, recorded behind the batch's last copy on that lane
+  int rc = 0;
+  int32_t* match = nullptr;           // for the tail padding done at wait()
+  int n_frames = 0, capacity = 0;
+};
 }  // namespace
 
 struct cmos_track {
@@ -34,6 +44,8 @@ struct cmos_track {
   int kp_cap = 0;
   std::vector<Lane> lanes;
   int launches = 0;
+  Slot slots[kTrackSlots];
+  int64_t next_ticket = 0;
 };
 
 extern "C" {
@@ -41,6 +53,9 @@ extern "C" {
 int cmos_track_destroy(cmos_track_t h) {
   if (!h) return CMOS_OK;
   cudaSetDevice(h->p.orb.device);
+  for (Slot& sl : h->slots)
+    for (cudaEvent_t e : sl.done)
+      if (e) cudaEventDestroy(e);
   for (Lane& L : h->lanes) {
     if (L.orb) cmos_orb_destroy(L.orb);
     if (L.match) cmos_match_destroy(L.match);
@@ -81,6 +96,11 @@ int cmos_track_create(const cmos_track_params* params, const cmos_camera* cam, c
     L.d_last_desc = dev_alloc<uint8_t>(n * 32, &err);
     if (err != cudaSuccess) { set_error("device allocation failed: %s", cudaGetErrorString(err)); rc = CMOS_ERR_CUDA; break; }
   }
+  for (Slot& sl : h->slots) {
+    sl.done.assign(h->lanes.size(), nullptr);
+    for (cudaEvent_t& e : sl.done)
+      if (!rc && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = CMOS_ERR_CUDA;
+  }
   if (rc) { cmos_track_destroy(h); return rc; }
   *out = h;
   return CMOS_OK;
@@ -92,18 +112,22 @@ int cmos_track_keypoint_capacity(cmos_track_t h, int32_t* cap) {
   return CMOS_OK;
 }
 
-int cmos_track_frames(cmos_track_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
+int cmos_track_submit(cmos_track_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
                       int32_t height, int32_t n_frames, const double* Tcw, const cmos_keypoint* last_keypoints,
                       const int32_t* last_counts, const uint8_t* last_flags, const double* last_xw,
                       const uint8_t* last_descriptors, int32_t last_stride, float th, int32_t check_orientation,
                       cmos_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int32_t capacity, int32_t* match,
-                      int32_t* nmatches) {
+                      int32_t* nmatches, int64_t* ticket) {
   CMOS_REQUIRE(h && images && Tcw && last_keypoints && last_counts && last_flags && last_xw && last_descriptors &&
-               keypoints && descriptors && counts && match && nmatches, "null argument");
+               keypoints && descriptors && counts && match && nmatches && ticket, "null argument");
   CMOS_REQUIRE(n_frames >= 1, "n_frames must be positive");
   CMOS_REQUIRE(capacity >= h->kp_cap, "capacity %d < cmos_track_keypoint_capacity %d", capacity, h->kp_cap);
   CMOS_REQUIRE(last_stride >= 1 && last_stride <= h->kp_cap, "last_stride %d outside 1..%d", last_stride, h->kp_cap);
   CMOS_CUDA_OK(cudaSetDevice(h->p.orb.device));
+  Slot* slot = nullptr;
+  for (Slot& sl : h->slots)
+    if (!sl.busy) { slot = &sl; break; }
+  if (!slot) { set_error("%d batches are already in flight: call cmos_track_wait first", kTrackSlots); return CMOS_ERR_STATE; }
   const int cf = h->p.chunk_frames, nl = (int)h->lanes.size();
   int launches = 0, rc = CMOS_OK;
   // inside the loop a CUDA error must not return: copies into caller memory may be in flight on other lanes (drained below)
@@ -149,16 +173,57 @@ int cmos_track_frames(cmos_track_t h, const uint8_t* images, int64_t frame_strid
     launches += a + 1 + b;   // + the grid kernel of set_frames
   }
 #undef TRACK_CUDA
-  // drain every lane even after an error, so no copy into caller memory is still in flight on return
+  h->launches = launches;
+  if (rc) {   // drain every lane after an error, so no copy into caller memory is still in flight on return
+    for (Lane& L : h->lanes) cmos_orb_finish(L.orb, L.st);
+    return rc;
+  }
+  for (size_t l = 0; l < h->lanes.size(); l++) {
+    if (cudaEventRecord(slot->done[l], h->lanes[l].st) != cudaSuccess) {
+      for (Lane& L : h->lanes) cmos_orb_finish(L.orb, L.st);
+      set_error("cudaEventRecord failed");
+      return CMOS_ERR_CUDA;
+    }
+  }
+  slot->busy = true; slot->ticket = h->next_ticket++; slot->match = match; slot->n_frames = n_frames; slot->capacity = capacity;
+  *ticket = slot->ticket;
+  return CMOS_OK;
+}
+
+int cmos_track_wait(cmos_track_t h, int64_t ticket) {
+  CMOS_REQUIRE(h, "null handle");
+  Slot* slot = nullptr;
+  for (Slot& sl : h->slots)
+    if (sl.busy && sl.ticket == ticket) { slot = &sl; break; }
+  if (!slot) { set_error("ticket %lld is not in flight", (long long)ticket); return CMOS_ERR_STATE; }
+  CMOS_CUDA_OK(cudaSetDevice(h->p.orb.device));
+  int rc = CMOS_OK;
+  for (cudaEvent_t e : slot->done)
+    if (cudaEventSynchronize(e) != cudaSuccess && !rc) { set_error("cudaEventSynchronize failed"); rc = CMOS_ERR_CUDA; }
+  // the FAST candidate-overflow flag of a lane is a pinned host word the extractor writes behind its kernels
   for (Lane& L : h->lanes) {
-    int r2 = cmos_orb_finish(L.orb, L.st);
+    int r2 = cmos_orb_check_overflow(L.orb);
     if (!rc) rc = r2;
   }
-  if (capacity > h->kp_cap)   // rows are kp_cap wide on the device: pad the tail like the unfused call does
-    for (int f = 0; f < n_frames; f++)
-      for (int i = h->kp_cap; i < capacity; i++) match[(size_t)f * capacity + i] = -1;
-  h->launches = launches;
+  if (slot->capacity > h->kp_cap)   // rows are kp_cap wide on the device: pad the tail like the unfused call does
+    for (int f = 0; f < slot->n_frames; f++)
+      for (int i = h->kp_cap; i < slot->capacity; i++) slot->match[(size_t)f * slot->capacity + i] = -1;
+  slot->busy = false;
   return rc;
+}
+
+int cmos_track_frames(cmos_track_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
+                      int32_t height, int32_t n_frames, const double* Tcw, const cmos_keypoint* last_keypoints,
+                      const int32_t* last_counts, const uint8_t* last_flags, const double* last_xw,
+                      const uint8_t* last_descriptors, int32_t last_stride, float th, int32_t check_orientation,
+                      cmos_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int32_t capacity, int32_t* match,
+                      int32_t* nmatches) {
+  int64_t ticket = -1;
+  int rc = cmos_track_submit(h, images, frame_stride, pitch, width, height, n_frames, Tcw, last_keypoints, last_counts,
+                             last_flags, last_xw, last_descriptors, last_stride, th, check_orientation, keypoints, descriptors,
+                             counts, capacity, match, nmatches, &ticket);
+  if (rc) return rc;
+  return cmos_track_wait(h, ticket);
 }
 
 int cmos_track_last_launch_count(cmos_track_t h, int32_t* n) {

@@ -61,6 +61,23 @@ class TrackingFrontEnd:
                                         ptr(match), ptr(nm)))
         return out
 
+    def submit(self, images, Tcw, last_keypoints, last_counts, last_flags, last_xw, last_descriptors, th: float, out):
+        """Asynchronous half of track(): enqueues the batch and returns a ticket at once (cmos_track_submit).  Every buffer
+        (inputs and `out`) must stay valid and untouched until wait(ticket) returns; up to 4 batches may be in flight."""
+        B, H, W = images.shape
+        S = last_flags.shape[1]
+        kps, desc, counts, match, nm = out
+        cap = match.shape[1]
+        t = C.c_int64(-1)
+        check(self._L.cmos_track_submit(self._h, ptr(images), C.c_int64(H * W), W, W, H, B, ptr(Tcw), ptr(last_keypoints),
+                                        ptr(last_counts), ptr(last_flags), ptr(last_xw), ptr(last_descriptors), S,
+                                        C.c_float(th), int(self.check_ori), ptr(kps), ptr(desc), ptr(counts), cap,
+                                        ptr(match), ptr(nm), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int):
+        check(self._L.cmos_track_wait(self._h, C.c_int64(ticket)))
+
     def launch_count(self) -> int:
         n = C.c_int32()
         check(self._L.cmos_track_last_launch_count(self._h, C.byref(n)))

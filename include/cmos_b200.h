@@ -101,6 +101,8 @@ int cmos_orb_extract_async(cmos_orb_t h, const uint8_t* images, int64_t frame_st
                            int32_t width, int32_t height, int32_t n_frames, cmos_keypoint* keypoints,
                            uint8_t* descriptors, int32_t* counts, int32_t capacity, void* stream);
 int cmos_orb_finish(cmos_orb_t h, void* stream);
+/* Only the candidate-overflow check of cmos_orb_finish, for callers that synchronised through an event of their own. */
+int cmos_orb_check_overflow(cmos_orb_t h);
 
 /* Device views of the last extraction: keypoints [max_batch][cap], descriptors [max_batch][cap][32],
  * counts [max_batch], level_counts [max_batch][CMOS_MAX_LEVELS]. */
@@ -419,7 +421,21 @@ int cmos_track_frames(cmos_track_t h, const uint8_t* images, int64_t frame_strid
                       const uint8_t* last_descriptors, int32_t last_stride, float th, int32_t check_orientation,
                       cmos_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int32_t capacity,
                       int32_t* match, int32_t* nmatches);
-/* Kernels launched by the last cmos_track_frames call. */
+/* The same work split into an asynchronous pair, so that a caller can keep several batches in flight (upload of batch k + 1
+ * under the kernels of batch k and the download of batch k - 1) instead of paying the pipeline fill and drain on every call:
+ * cmos_track_submit enqueues everything and returns a ticket at once; cmos_track_wait blocks until that batch's outputs are
+ * in the caller's buffers.  All buffers of a submitted batch must stay valid and untouched until its wait returns; at most
+ * 4 batches may be in flight (CMOS_ERR_STATE beyond that).  cmos_track_frames == submit + wait.
+ * (Tracking.cc:617-646 consumes frame t while the camera thread already holds frame t + 1.) */
+int cmos_track_submit(cmos_track_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
+                      int32_t height, int32_t n_frames, const double* Tcw, const cmos_keypoint* last_keypoints,
+                      const int32_t* last_counts, const uint8_t* last_flags, const double* last_xw,
+                      const uint8_t* last_descriptors, int32_t last_stride, float th, int32_t check_orientation,
+                      cmos_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int32_t capacity, int32_t* match,
+                      int32_t* nmatches, int64_t* ticket);
+int cmos_track_wait(cmos_track_t h, int64_t ticket);
+
+/* Kernels launched by the last cmos_track_frames / cmos_track_submit call. */
 int cmos_track_last_launch_count(cmos_track_t h, int32_t* n);
 
 /* ------------------------------------------------------------------------------------------------

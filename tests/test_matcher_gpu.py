@@ -314,6 +314,26 @@ def test_tracking_front_end_equals_unfused_calls(lanes, chunk):
             assert np.array_equal(k2[f, :n], kps[f, :n]) and np.array_equal(d2[f, :n], desc[f, :n])
             assert np.array_equal(m2[f, :n], match[f, :n])
     assert nm.sum() > 100 * B and fe.launch_count() > 0
+    # asynchronous pair: three batches in flight (the same batch and two shifted copies), waited for out of order
+    from ceres_mono_orb_slam2_b200 import CmosError
+    outs, tickets, ins = [], [], []
+    for s_ in range(3):
+        idx = np.roll(np.arange(B), s_)
+        a = tuple(np.ascontiguousarray(x[idx]) for x in (frames, T, lk, lcounts, flags, xw, mdesc))
+        o = (np.zeros((B, cap), KP_DTYPE), np.zeros((B, cap, 32), np.uint8), np.zeros(B, np.int32),
+             np.full((B, cap), -1, np.int32), np.zeros(B, np.int32))
+        ins.append((a, idx)); outs.append(o)
+        tickets.append(fe.submit(*a, 15.0, out=o))
+    for s_ in (1, 0, 2):
+        fe.wait(tickets[s_])
+        idx = ins[s_][1]
+        k2, d2, c2, m2, n2 = outs[s_]
+        assert np.array_equal(c2, counts[idx]) and np.array_equal(n2, nm[idx])
+        for j, f in enumerate(idx):
+            n = int(counts[f])
+            assert np.array_equal(k2[j, :n], kps[f, :n]) and np.array_equal(m2[j, :n], match[f, :n])
+    with pytest.raises(CmosError):
+        fe.wait(tickets[0])            # already waited for
 
 
 def test_undistort_keypoints_and_distorted_bounds():
