@@ -1103,10 +1103,118 @@ __device__ __forceinline__ void solve_row_update(const double* li, const double*
   for (int u = 0; u < kGroups; u++) { const int c = cb + 32 * u; if (c <= cmax) rowp[c] -= v[u]; }
 }
 
+constexpr int kPBuf = 8;      // rows of the panel buffer: 6 panel columns + 2 rows of zeros (the k = 8 of two m8n8k4 steps)
+
+// fp64 tensor-core tile product: D (8 x 8) += A (8 x 4) B (4 x 8).  Fragment layout (PTX ISA, mma.m8n8k4 .f64):
+// A[row = lane / 4][col = lane % 4], B[row = lane % 4][col = lane / 4], C[row = lane / 4][col = 2 (lane % 4) + {0, 1}].
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+#ifndef CMOS_CHOL_V1
 // Right-looking Cholesky of a packed lower triangle in shared memory, panels of 6 columns, rows 0..n (row n = the rhs,
 // which leaves as the forward-substituted y).  On return every 6x6 diagonal block holds the INVERSE of its Cholesky
-// block (factor_diag6).  All kSolveThreads threads of the CTA call it; P is the [kPB][ps] panel buffer.
+// block (factor_diag6).  All kSolveThreads threads of the CTA call it; P is the [kPBuf][ps] panel buffer.
+//
+// The pivot chain — factor the 6 x 6 diagonal block, solve the six rows of the next block against it, update the next
+// diagonal block, factor again — is the critical path of every BA solve (LocalBA: 15 factorisations of 120 unknowns;
+// GlobalBA: 6 per LM iteration).  Warp 0 does nothing else: it runs one block ahead of the other 15 warps, which solve the
+// remaining rows and apply the rank-6 trailing update on the fp64 tensor cores (8 x 8 tiles, the panel's six columns padded
+// to k = 8 with zero rows of P).  One named barrier hands the solved panel from all warps to the updaters without stopping
+// warp 0; one __syncthreads per panel.  (Round 1's version: every warp took part in every phase, two __syncthreads per
+// panel, scalar trailing update bound by shared-memory wavefronts: 3760 cycles per panel at n = 114, now measured in
+// profiles/.)
 __device__ __forceinline__ void packed_cholesky(double* __restrict__ L, double* __restrict__ P, const int n, const int ps,
+                                                int* s_fail) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kUpd = kSolveThreads - 32, kUpdWarps = kUpd / 32;
+  for (int i = tid; i < 2 * ps; i += kSolveThreads) P[6 * ps + i] = 0.0;       // k = 6, 7 of the padded panel
+  // (r, c) of the next diagonal block's element a lane of warp 0 updates
+  int dr = 0, dc = lane;
+  while (dc > dr) { dc -= dr + 1; dr++; }
+  if (tid == 0 && n > 0) factor_diag6(L, 0, s_fail);
+  __syncthreads();
+  const int g = lane >> 2, q = lane & 3;
+  for (int k0 = 0; k0 < n; k0 += kPB) {
+    if (*s_fail) break;
+    const int t0 = k0 + kPB;
+    const int nc = t0 < n ? kPB : 0;                       // rows of the next diagonal block (warp 0's)
+    const int R0 = t0 + nc;                                // first row of the other warps
+    // ---- panel solve: row i times inv(L11)'
+    auto solve_row = [&](const int i) {
+      double* rowp = L + i * (i + 1) / 2 + k0;
+      double a[kPB], x[kPB];
+#pragma unroll
+      for (int c = 0; c < kPB; c++) a[c] = rowp[c];
+#pragma unroll
+      for (int c = 0; c < kPB; c++) {
+        const double* di = L + (k0 + c) * (k0 + c + 1) / 2 + k0;
+        double v = 0.0;
+#pragma unroll
+        for (int qq = 0; qq <= c; qq++) v += a[qq] * di[qq];
+        x[c] = v;
+      }
+#pragma unroll
+      for (int c = 0; c < kPB; c++) { rowp[c] = x[c]; P[c * ps + i] = x[c]; }
+    };
+    if (warp == 0) {
+      if (lane < nc) solve_row(t0 + lane);
+      __syncwarp();
+      asm volatile("bar.arrive 1, %0;" ::"n"(kSolveThreads) : "memory");   // hands the chain rows' X to the updaters
+      if (nc) {
+        if (lane < kPB * (kPB + 1) / 2) {
+          const int i = t0 + dr, cc = t0 + dc;
+          double v = 0.0;
+#pragma unroll
+          for (int qq = 0; qq < kPB; qq++) v += P[qq * ps + i] * P[qq * ps + cc];
+          L[i * (i + 1) / 2 + cc] -= v;
+        }
+        __syncwarp();
+        if (lane == 0) factor_diag6(L, t0, s_fail);
+      }
+    } else {
+      for (int i = R0 + tid - 32; i <= n; i += kUpd) solve_row(i);
+      asm volatile("bar.sync 1, %0;" ::"n"(kSolveThreads) : "memory");     // every X of this panel is in P
+      // ---- trailing update of rows R0..n, columns t0..min(row, n - 1): 8 x 8 tiles, row tile ti has min(ti + 2, max_ct)
+      // column tiles (the triangle), flattened over the 15 updater warps
+      const int n_rt = (n - R0 + 8) >> 3;                  // ceil((n - R0 + 1) / 8)
+      const int max_ct = ((n - 1 - t0) >> 3) + 1;
+      const int lin = max(0, min(n_rt, max_ct - 1));       // row tiles that still have ti + 2 column tiles
+      const int total = lin * (lin + 3) / 2 + (n_rt - lin) * max_ct;
+      for (int e = warp - 1; e < total; e += kUpdWarps) {
+        int ti, tj;
+        if (e < lin * (lin + 3) / 2) {
+          ti = (int)((sqrtf(8.0f * (float)e + 9.0f) - 3.0f) * 0.5f);
+          while ((ti + 1) * (ti + 4) / 2 <= e) ti++;
+          while (ti * (ti + 3) / 2 > e) ti--;
+          tj = e - ti * (ti + 3) / 2;
+        } else {
+          const int r = e - lin * (lin + 3) / 2;
+          ti = lin + r / max_ct; tj = r - (r / max_ct) * max_ct;
+        }
+        const int row = R0 + 8 * ti + g, col = t0 + 8 * tj + 2 * q;          // C fragment: (row, col), (row, col + 1)
+        const int arow = min(row, n), bcol = min(t0 + 8 * tj + g, n);         // clamped operand rows (masked at the store)
+        const double a0 = -P[q * ps + arow], a1 = -P[(4 + q) * ps + arow];
+        const double b0 = P[q * ps + bcol], b1 = P[(4 + q) * ps + bcol];
+        const int cmax = min(row, n - 1);
+        const bool v0 = row <= n && col <= cmax, v1 = row <= n && col + 1 <= cmax;
+        double* cp = L + row * (row + 1) / 2 + col;
+        double c0 = v0 ? cp[0] : 0.0, c1 = v1 ? cp[1] : 0.0;
+        dmma_884(c0, c1, a0, b0);
+        dmma_884(c0, c1, a1, b1);
+        if (v0) cp[0] = c0;
+        if (v1) cp[1] = c1;
+      }
+    }
+    __syncthreads();
+  }
+}
+#else
+// Right-looking Cholesky of a packed lower triangle in shared memory, panels of 6 columns, rows 0..n (row n = the rhs,
+// which leaves as the forward-substituted y).  On return every 6x6 diagonal block holds the INVERSE of its Cholesky
+// block (factor_diag6).  All kSolveThreads threads of the CTA call it; P is the [kPBuf][ps] panel buffer.
+__device__ __forceinline__ void packed_cholesky_v1(double* __restrict__ L, double* __restrict__ P, const int n, const int ps,
                                                 int* s_fail) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = kSolveThreads / 32;
 #ifdef CMOS_CR_TIMING
@@ -1228,6 +1336,9 @@ __device__ __forceinline__ void packed_cholesky(double* __restrict__ L, double* 
 #endif
 #undef PK
 }
+
+#define packed_cholesky packed_cholesky_v1
+#endif
 
 __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
   extern __shared__ __align__(16) double smem_d[];
@@ -2266,7 +2377,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
   const int nlb = d.n_lin_blocks;
   const int g_par = (std::max(7 * d.K, 3 * d.M) + 255) / 256;
   const bool small = d.nc <= kSmallMaxN;
-  const size_t small_smem = ((size_t)(d.nc + 1) * (d.nc + 2) / 2 + (size_t)kPB * (d.nc + 2) + d.nc) * sizeof(double);
+  const size_t small_smem = ((size_t)(d.nc + 1) * (d.nc + 2) / 2 + (size_t)kPBuf * (d.nc + 2) + d.nc) * sizeof(double);
   const bool multi = d.multi != 0;
   auto allreduce = [&](double* buf, size_t count, int op) -> int {
     const int rc = g_nccl.AllReduce(buf, buf, count, kNcclDouble, op, h->comm, st);

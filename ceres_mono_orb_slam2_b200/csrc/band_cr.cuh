@@ -51,7 +51,7 @@ __device__ __forceinline__ bool cr_has_acc_right(const CrArgs& a, int node, int 
 
 constexpr int kCrMaxN = 144;            // 6 * kBandMaxW
 inline size_t cr_factor_smem(int n) {
-  return ((size_t)(n + 1) * (n + 2) / 2 + (size_t)kPB * (n + 2) + 8) * sizeof(double);
+  return ((size_t)(n + 1) * (n + 2) / 2 + (size_t)kPBuf * (n + 2) + 8) * sizeof(double);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -200,10 +200,6 @@ __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, 
 // fp64 tensor-core tile: one warp accumulates a 24 x 24 output tile as 3 x 3 mma.m8n8k4 tiles.
 // Fragment layout (PTX ISA, mma.m8n8k4 .f64): A[row = lane / 4][col = lane % 4], B[row = lane % 4][col = lane / 4],
 // C[row = lane / 4][col = 2 (lane % 4) + {0, 1}].
-__device__ __forceinline__ void dmma_884(double& c0, double& c1, const double a, const double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
 struct CrTile { double c[3][3][2]; };
 __device__ __forceinline__ void cr_tile_zero(CrTile& t) {
 #pragma unroll
