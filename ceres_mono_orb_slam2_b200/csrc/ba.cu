@@ -1136,6 +1136,12 @@ __device__ __forceinline__ void packed_cholesky(double* __restrict__ L, double* 
   if (tid == 0 && n > 0) factor_diag6(L, 0, s_fail);
   __syncthreads();
   const int g = lane >> 2, q = lane & 3;
+#ifdef CMOS_CR_TIMING
+  long long pk[6] = {0, 0, 0, 0, 0, 0}, tp = clock64();
+#define PK(i) { const long long tn = clock64(); pk[i] += tn - tp; tp = tn; }
+#else
+#define PK(i)
+#endif
   for (int k0 = 0; k0 < n; k0 += kPB) {
     if (*s_fail) break;
     const int t0 = k0 + kPB;
@@ -1161,6 +1167,7 @@ __device__ __forceinline__ void packed_cholesky(double* __restrict__ L, double* 
     if (warp == 0) {
       if (lane < nc) solve_row(t0 + lane);
       __syncwarp();
+      PK(0)
       asm volatile("bar.arrive 1, %0;" ::"n"(kSolveThreads) : "memory");   // hands the chain rows' X to the updaters
       if (nc) {
         if (lane < kPB * (kPB + 1) / 2) {
@@ -1171,11 +1178,15 @@ __device__ __forceinline__ void packed_cholesky(double* __restrict__ L, double* 
           L[i * (i + 1) / 2 + cc] -= v;
         }
         __syncwarp();
+        PK(1)
         if (lane == 0) factor_diag6(L, t0, s_fail);
+        PK(2)
       }
     } else {
       for (int i = R0 + tid - 32; i <= n; i += kUpd) solve_row(i);
-      asm volatile("bar.sync 1, %0;" ::"n"(kSolveThreads) : "memory");     // every X of this panel is in P
+      PK(0)
+      asm volatile("bar.sync 1, %0;" ::"n"(kSolveThreads) : "memory");
+      PK(1)     // every X of this panel is in P
       // ---- trailing update of rows R0..n, columns t0..min(row, n - 1): 8 x 8 tiles, row tile ti has min(ti + 2, max_ct)
       // column tiles (the triangle), flattened over the 15 updater warps
       const int n_rt = (n - R0 + 8) >> 3;                  // ceil((n - R0 + 1) / 8)
@@ -1206,9 +1217,16 @@ __device__ __forceinline__ void packed_cholesky(double* __restrict__ L, double* 
         if (v0) cp[0] = c0;
         if (v1) cp[1] = c1;
       }
+      PK(2)
     }
     __syncthreads();
+    PK(3)
   }
+#ifdef CMOS_CR_TIMING
+  if ((tid == 0 || tid == 32 || tid == 480) && blockIdx.x == 0)
+    printf("packed_cholesky v2 tid %d n %d: [w0: solve6 / diag-update / factor_diag6 | updaters: solve / barrier / dmma update] %lld %lld %lld | end sync %lld\n", tid, n, pk[0], pk[1], pk[2], pk[3]);
+#endif
+#undef PK
 }
 #else
 // Right-looking Cholesky of a packed lower triangle in shared memory, panels of 6 columns, rows 0..n (row n = the rhs,
@@ -1340,6 +1358,69 @@ __device__ __forceinline__ void packed_cholesky_v1(double* __restrict__ L, doubl
 #define packed_cholesky packed_cholesky_v1
 #endif
 
+// After packed_cholesky: invert the 24 x 24 diagonal Cholesky blocks in place ([[A,0],[B,C]]^-1 = [[A^-1,0],[-C^-1 B A^-1, C^-1]],
+// 6 -> 12 -> 24; the 6 x 6 diagonal blocks are already stored inverted; the last block may be 6, 12 or 18 wide).
+// Substitutions then run in 24-row steps of independent dot products instead of 6-row steps.  T: scratch of 6 n + 36 doubles
+// (the panel buffer).  All kSolveThreads threads.
+__device__ __forceinline__ void invert_diag24(double* __restrict__ L, double* __restrict__ T, const int n) {
+  const int tid = threadIdx.x, nb = n / 6;
+  for (int sb = 1; sb <= 2; sb *= 2) {
+    const int np = (nb + sb - 1) / (2 * sb), pe = 36 * sb * sb, sa = 6 * sb;
+    for (int e = tid; e < np * pe; e += kSolveThreads) {         // T = L_CA * M_AA
+      const int pr = e / pe, rem = e - pr * pe, r = rem / sa, j = rem - r * sa;
+      const int a0 = 6 * (2 * pr * sb), c0 = a0 + sa;
+      if (c0 + r >= min(c0 + sa, n)) continue;
+      const double* Lrow = L + (c0 + r) * (c0 + r + 1) / 2 + a0;
+      double v = 0.0;
+      for (int k = j; k < sa; k++) v += Lrow[k] * L[(a0 + k) * (a0 + k + 1) / 2 + a0 + j];
+      T[e] = v;
+    }
+    __syncthreads();
+    for (int e = tid; e < np * pe; e += kSolveThreads) {         // M_CA = -M_CC * T, over L_CA
+      const int pr = e / pe, rem = e - pr * pe, r = rem / sa, j = rem - r * sa;
+      const int a0 = 6 * (2 * pr * sb), c0 = a0 + sa;
+      if (c0 + r >= min(c0 + sa, n)) continue;
+      const double* Mrow = L + (c0 + r) * (c0 + r + 1) / 2 + c0;
+      const double* Tc = T + (size_t)pr * pe + j;
+      double v = 0.0;
+      for (int k = 0; k <= r; k++) v += Mrow[k] * Tc[k * sa];
+      L[(c0 + r) * (c0 + r + 1) / 2 + a0 + j] = -v;
+    }
+    __syncthreads();
+  }
+}
+
+// L' x = y in 24-row block steps against a factor whose 24 x 24 diagonal blocks are inverted (invert_diag24), from the last
+// block up: x_p = inv(L_pp)' y_p, then y_q -= L_pq' x_p for the rows above.  y (n entries, shared memory) becomes x.
+// s_x: 24 doubles of shared scratch.  All threads of the CTA (blockDim.x >= n).
+__device__ __forceinline__ void back_substitute24(const double* __restrict__ L, double* __restrict__ y, double* __restrict__ s_x,
+                                                  const int n) {
+  const int tid = threadIdx.x;
+  for (int r0 = ((n - 1) / 24) * 24; r0 >= 0; r0 -= 24) {
+    const int bs = min(24, n - r0);
+    if (tid < bs) {
+      double x0 = 0.0, x1 = 0.0;
+      for (int qq = tid; qq < bs; qq += 2) {
+        x0 += L[(r0 + qq) * (r0 + qq + 1) / 2 + r0 + tid] * y[r0 + qq];
+        if (qq + 1 < bs) x1 += L[(r0 + qq + 1) * (r0 + qq + 2) / 2 + r0 + tid] * y[r0 + qq + 1];
+      }
+      s_x[tid] = x0 + x1;
+    }
+    __syncthreads();
+    if (tid < r0) {
+      double v0 = 0.0, v1 = 0.0;
+      for (int qq = 0; qq < bs; qq += 2) {
+        v0 += L[(r0 + qq) * (r0 + qq + 1) / 2 + tid] * s_x[qq];
+        if (qq + 1 < bs) v1 += L[(r0 + qq + 1) * (r0 + qq + 2) / 2 + tid] * s_x[qq + 1];
+      }
+      y[tid] -= v0 + v1;
+    } else if (tid < r0 + bs) {
+      y[tid] = s_x[tid - r0];
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
   extern __shared__ __align__(16) double smem_d[];
   LmState& st = *d.st;
@@ -1373,45 +1454,25 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
   packed_cholesky(L, P, n, ps, &s_fail);
   TK(4)
   __syncthreads();
-  if (warp == 0) {
+  // back substitution L' x = y in 24-row block steps by the whole CTA (it was one warp walking 6-row blocks: 19 k of the
+  // 88 k cycles of this kernel)
+  {
+    __shared__ double s_x24[24];
     double* y = L + n * (n + 1) / 2;      // forward-substituted rhs
     if (!s_fail) {
-      // blocked back substitution L' x = y: x_block = inv(L11)' y_block (lanes 0..5, one dot product each), then the warp
-      // updates the rows above
-      for (int k0 = n - kPB; k0 >= 0; k0 -= kPB) {
-        double xr = 0.0;
-        if (lane < kPB) {
-#pragma unroll
-          for (int q = 0; q < kPB; q++)
-            if (q >= lane) xr += L[(k0 + q) * (k0 + q + 1) / 2 + k0 + lane] * y[k0 + q];
-        }
-        __syncwarp();
-        if (lane < kPB) y[k0 + lane] = xr;
-        double x[kPB];
-#pragma unroll
-        for (int r = 0; r < kPB; r++) x[r] = __shfl_sync(0xffffffffu, xr, r);
-        for (int kb = lane; kb < k0; kb += 128) {
-          double v[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-          for (int r = 0; r < kPB; r++) {
-            const double* lr = L + (k0 + r) * (k0 + r + 1) / 2;
-#pragma unroll
-            for (int u = 0; u < 4; u++) { const int k = kb + 32 * u; if (k < k0) v[u] += lr[k] * x[r]; }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; u++) { const int k = kb + 32 * u; if (k < k0) y[k] -= v[u]; }
-        }
-        __syncwarp();
+      invert_diag24(L, P, n);
+      back_substitute24(L, y, s_x24, n);
+    }
+    if (warp == 0) {
+      int bad = 0;
+      for (int k = lane; k < n; k += 32) {
+        const double v = s_fail ? 0.0 : y[k];
+        d.yc[k] = v;
+        bad |= !isfinite(v);
       }
+      bad = __any_sync(0xffffffffu, bad);
+      if (lane == 0 && bad) s_fail = 1;
     }
-    int bad = 0;
-    for (int k = lane; k < n; k += 32) {
-      const double v = s_fail ? 0.0 : y[k];
-      d.yc[k] = v;
-      bad |= !isfinite(v);
-    }
-    bad = __any_sync(0xffffffffu, bad);
-    if (lane == 0 && bad) s_fail = 1;
   }
   __syncthreads();
   TK(5)

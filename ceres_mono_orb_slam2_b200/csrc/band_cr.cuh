@@ -154,35 +154,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, 
     if (tid == 0) st.solve_failed = 1;
     return;
   }
-  // Invert the 24 x 24 diagonal Cholesky blocks in place ([[A,0],[B,C]]^-1 = [[A^-1,0],[-C^-1 B A^-1, C^-1]], 6 -> 12 -> 24;
-  // the 6 x 6 diagonal blocks are already stored inverted): the spike and back substitutions then run in 24-row block
-  // steps of tensor-core tile products instead of 6-row steps.  Scratch = the panel buffer (n / 24 pairs x 144 values).
-  {
-    const int nb = n / 6;
-    double* T = P;
-    for (int sb = 1; sb <= 2; sb *= 2) {
-      const int np = nb / (2 * sb), pe = 36 * sb * sb, sa = 6 * sb;
-      for (int e = tid; e < np * pe; e += kSolveThreads) {         // T = L_CA * M_AA
-        const int pr = e / pe, rem = e - pr * pe, r = rem / sa, j = rem - r * sa;
-        const int a0 = 6 * (2 * pr * sb), c0 = a0 + sa;
-        const double* Lrow = L + (c0 + r) * (c0 + r + 1) / 2 + a0;
-        double v = 0.0;
-        for (int k = j; k < sa; k++) v += Lrow[k] * L[(a0 + k) * (a0 + k + 1) / 2 + a0 + j];
-        T[e] = v;
-      }
-      __syncthreads();
-      for (int e = tid; e < np * pe; e += kSolveThreads) {         // M_CA = -M_CC * T, over L_CA
-        const int pr = e / pe, rem = e - pr * pe, r = rem / sa, j = rem - r * sa;
-        const int a0 = 6 * (2 * pr * sb), c0 = a0 + sa;
-        const double* Mrow = L + (c0 + r) * (c0 + r + 1) / 2 + c0;
-        const double* Tc = T + (size_t)pr * pe + j;
-        double v = 0.0;
-        for (int k = 0; k <= r; k++) v += Mrow[k] * Tc[k * sa];
-        L[(c0 + r) * (c0 + r + 1) / 2 + a0 + j] = -v;
-      }
-      __syncthreads();
-    }
-  }
+  invert_diag24(L, P, n);      // the spike and back substitutions run in 24-row block steps of tensor-core tile products
   double2* Lp = (double2*)cr_arr(a, CR_LP, node);
   const int ne2 = (n * (n + 1) / 2 + 1) / 2;             // packed triangle, in double2 (n (n + 1) / 2 is even for n % 4 == 0)
   for (int e = tid; e < ne2; e += kSolveThreads) Lp[e] = ((const double2*)L)[e];
@@ -423,32 +395,11 @@ __global__ void __launch_bounds__(32 * kCrBackWarps) k_cr_back(BaDev d, CrArgs a
     }
   }
   __syncthreads();
-  for (int p = n / 24 - 1; p >= 0; p--) {
-    const int r0 = 24 * p;
-    if (tid < 24) {                                        // x_p = inv(L_pp)' z_p: column tid of the inverted block
-      double x0 = 0.0, x1 = 0.0;
-      for (int qq = tid; qq < 24; qq += 2) {
-        x0 += L[(r0 + qq) * (r0 + qq + 1) / 2 + r0 + tid] * s_z[r0 + qq];
-        if (qq + 1 < 24) x1 += L[(r0 + qq + 1) * (r0 + qq + 2) / 2 + r0 + tid] * s_z[r0 + qq + 1];
-      }
-      s_x[r0 + tid] = x0 + x1;
-    }
-    __syncthreads();
-    if (tid < r0) {                                        // z_k -= sum_q L[r0 + q][k] x[r0 + q]
-      double v0 = 0.0, v1 = 0.0;
-#pragma unroll 4
-      for (int qq = 0; qq < 24; qq += 2) {
-        v0 += L[(r0 + qq) * (r0 + qq + 1) / 2 + tid] * s_x[r0 + qq];
-        v1 += L[(r0 + qq + 1) * (r0 + qq + 2) / 2 + tid] * s_x[r0 + qq + 1];
-      }
-      s_z[tid] -= v0 + v1;
-    }
-    __syncthreads();
-  }
+  back_substitute24(L, s_z, s_x, n);       // s_z becomes x
   double* x = cr_vec(a, CR_X, node);
   const int b0 = (node - 1) * a.Wb;
   for (int j = tid; j < n; j += 32 * kCrBackWarps) {
-    const double v = s_x[j];
+    const double v = s_z[j];
     x[j] = v;
     if (b0 + j / 6 < d.Kv) d.yc[6 * b0 + j] = v;
   }

@@ -140,6 +140,122 @@ __global__ void __launch_bounds__(256) k_resize(OrbGeom g, int level, const shor
   }
 }
 
+// Second-generation resize: the INTERIOR of level l from the interior of level l-1, one CTA per 128 x 16 output tile.
+// Round 1's k_resize spent ~65 thread-instructions per output pixel: every output row redid the horizontal pass of both of
+// its source rows and the vertical pass was two 32-bit multiplies, shifts and clamps per pixel.  Here
+//   * the horizontal pass runs ONCE per source row of the tile (about 1.2 source rows per output row) into shared memory as
+//     u16 (t >> 4 <= 32640 fits), four columns per thread: three aligned word loads, funnel shifts, one DP2A per pixel;
+//   * the vertical pass is two IMAD.HI per pixel: ((b * tt) >> 16) == umulhi(b << 16, tt), the "+ 2" rides as the addend;
+//     the result cannot exceed 255 (the weights sum to 2048), so OpenCV's saturation is a no-op and is dropped;
+//   * the reflect-101 borders of all levels are filled afterwards by ONE launch of k_borders (the resize itself clamps source
+//     coordinates, ORBextractor.cc:1120 / OpenCV's xofs clamp, and never reads a border).
+// Bit-exact with cv::resize INTER_LINEAR (tests compare every plane byte with the oracle and with the reference build).
+constexpr int kRzTW = 128, kRzTH = 16, kRzMaxSrcRows = 24;
+__global__ void __launch_bounds__(256) k_resize2(OrbGeom g, int level, const short4* __restrict__ xtab,
+                                                 const short4* __restrict__ ytab, uint8_t* __restrict__ pyr) {
+  __shared__ __align__(8) uint16_t s_h[kRzMaxSrcRows][kRzTW];
+  const LevelGeom& L = g.lv[level];
+  const LevelGeom& S = g.lv[level - 1];
+  const int tid = threadIdx.x, cg = tid & 31, rsub = tid >> 5;      // column group (4 output columns), row phase 0..7
+  const int x_first = blockIdx.x * kRzTW + 4 * cg;
+  const int r_first = blockIdx.y * kRzTH, r_last = min(r_first + kRzTH, L.h) - 1;
+  uint8_t* frame = pyr + (long long)blockIdx.z * g.frame_bytes;
+  const uint8_t* src = frame + S.plane_off + (long long)kBorder * S.pitch + kXOff;
+  const int y_lo = min(max((int)__ldg(ytab + r_first).x, 0), S.h - 1);
+  const int y_hi = min(max((int)__ldg(ytab + r_last).x + 1, 0), S.h - 1);
+  if (x_first < L.w) {
+    // column set-up: coefficient pairs and the byte offsets of the four source pairs inside three aligned words
+    unsigned coef[4], sh[4];
+    bool hi[4];
+    int wb;
+    {
+      int sx[4];
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const short4 t = __ldg(xtab + min(x_first + b, L.w - 1));
+        coef[b] = ((unsigned)(unsigned short)t.x) | ((unsigned)(unsigned short)t.y << 16);
+        sx[b] = t.z;
+      }
+      wb = sx[0] >> 2;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int o = min(sx[b] - 4 * wb, 8);      // 0..8 (a clamped column of a partial group never exceeds it)
+        hi[b] = o >= 4;
+        sh[b] = 8u * (unsigned)(o & 3);
+      }
+    }
+    for (int sr = y_lo + rsub; sr <= y_hi; sr += 8) {
+      const uint32_t* p = (const uint32_t*)(src + (long long)sr * S.pitch) + wb;
+      const uint32_t u0 = p[0], u1 = p[1], u2 = p[2];
+      unsigned tt[4];
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const uint32_t w = __funnelshift_r(hi[b] ? u1 : u0, hi[b] ? u2 : u1, sh[b]);
+        tt[b] = __dp2a_lo(coef[b], w, 0u) >> 4;
+      }
+      *(uint2*)&s_h[sr - y_lo][4 * cg] = make_uint2(tt[0] | (tt[1] << 16), tt[2] | (tt[3] << 16));
+    }
+  }
+  __syncthreads();
+  if (x_first >= L.w) return;
+  for (int r = r_first + rsub; r <= r_last; r += 8) {
+    const short4 ty = __ldg(ytab + r);
+    const int l0 = min(max((int)ty.x, 0), S.h - 1) - y_lo, l1 = min(max((int)ty.x + 1, 0), S.h - 1) - y_lo;
+    const unsigned B0 = (unsigned)ty.y << 16, B1 = (unsigned)ty.z << 16;
+    const uint2 h0 = *(const uint2*)&s_h[l0][4 * cg], h1 = *(const uint2*)&s_h[l1][4 * cg];
+    const unsigned v0 = (__umulhi(B0, h0.x & 0xffffu) + 2u + __umulhi(B1, h1.x & 0xffffu)) >> 2;
+    const unsigned v1 = (__umulhi(B0, h0.x >> 16) + 2u + __umulhi(B1, h1.x >> 16)) >> 2;
+    const unsigned v2 = (__umulhi(B0, h0.y & 0xffffu) + 2u + __umulhi(B1, h1.y & 0xffffu)) >> 2;
+    const unsigned v3 = (__umulhi(B0, h0.y >> 16) + 2u + __umulhi(B1, h1.y >> 16)) >> 2;
+    *(uint32_t*)(frame + L.plane_off + (long long)(r + kBorder) * L.pitch + kXOff + x_first) = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+  }
+}
+
+// cv::copyMakeBorder(..., BORDER_REFLECT_101 + BORDER_ISOLATED) of levels first_level.. in ONE launch (ORBextractor.cc:1122):
+// grid (work blocks, level - first_level, frame).  Work block b < n_side: the side borders of 21 interior rows (threads =
+// rows x 12 words: words that hold bx in [-19, -1] or [w, w + 18]; words shared with the interior are read-modified-written);
+// the remaining blocks: one of the 38 border rows each, word per thread.
+constexpr int kSideRows = 21;     // 21 rows x 12 words = 252 threads of a 256-thread CTA
+__global__ void __launch_bounds__(256) k_borders(OrbGeom g, int first_level, int n_side_max, uint8_t* __restrict__ pyr) {
+  const LevelGeom& L = g.lv[first_level + blockIdx.y];
+  uint8_t* plane = pyr + (long long)blockIdx.z * g.frame_bytes + L.plane_off;
+  const uint8_t* in = plane + (long long)kBorder * L.pitch + kXOff;      // interior origin
+  int b = blockIdx.x;
+  if (b < n_side_max) {
+    const int row = b * kSideRows + threadIdx.x / 12, k = threadIdx.x % 12;
+    if (threadIdx.x >= kSideRows * 12 || row >= L.h) return;
+    // left words cover bx in [-20, -1] (5 words), right words start at the word holding bx = w
+    const int w_first_right = (kXOff + L.w) >> 2;
+    const int word = k < 5 ? (kXOff - 20) / 4 + k : w_first_right + (k - 5);
+    if (4 * word >= L.pitch) return;
+    uint32_t* dst = (uint32_t*)(plane + (long long)(row + kBorder) * L.pitch) + word;
+    uint32_t v = *dst;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int bx = 4 * word + q - kXOff;
+      if ((bx < 0 && bx >= -kBorder) || (bx >= L.w && bx < L.w + kBorder)) {
+        const uint32_t px = in[(long long)row * L.pitch + reflect101(bx, L.w)];
+        v = (v & ~(0xffu << (8 * q))) | (px << (8 * q));
+      }
+    }
+    *dst = v;
+    return;
+  }
+  b -= n_side_max;
+  if (b >= 2 * kBorder) return;
+  const int prow = b < kBorder ? b : L.h + b;                       // plane row: 0..18 and h + 19 .. h + 37
+  const int sy = reflect101(prow - kBorder, L.h);
+  for (int word = threadIdx.x; 4 * word < L.pitch; word += 256) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int bx = 4 * word + q - kXOff;
+      if (bx >= -kBorder && bx < L.w + kBorder) v |= (uint32_t)in[(long long)sy * L.pitch + reflect101(bx, L.w)] << (8 * q);
+    }
+    *((uint32_t*)(plane + (long long)prow * L.pitch) + word) = v;
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // FAST-9/16 (cv::FAST's cornerScore, Appendix A.3): m = max over the 16 arcs of 9 contiguous ring pixels of
 // min(ring - c) and of min(c - ring); corner iff m > t, score m - 1.
@@ -906,6 +1022,7 @@ struct cmos_orb {
   int fast_threads = 128;   // CMOS_FAST_THREADS=256 selects the wider CTA (tuning knob)
   bool fast_small_cells = false;   // every cell of the current geometry fits the 48 x 48 tile (CMOS_FAST_LARGE_TILE=1 disables)
   int resize_rows = 2;      // CMOS_RESIZE_ROWS=1|2|4 output rows per thread of k_resize (tuning knob)
+  bool resize_v2 = true;    // k_resize2 + k_borders (CMOS_RESIZE_V1=1 selects round 1's k_resize, A/B runs)
   bool has_result = false;
   StageTimer timer;
 };
@@ -1075,6 +1192,19 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
     k_level0<<<grid, blk, 0, st>>>(g, d_images, frame_stride, pitch, h->d_pyr);
     launches++;
   }
+  if (h->resize_v2) {
+    for (int l = 1; l < g.nlevels; l++) {
+      const LevelGeom& L = g.lv[l];
+      dim3 grid((L.w + kRzTW - 1) / kRzTW, (L.h + kRzTH - 1) / kRzTH, n_frames);
+      k_resize2<<<grid, 256, 0, st>>>(g, l, h->d_tab + h->xtab_off[l], h->d_tab + h->ytab_off[l], h->d_pyr);
+      launches++;
+    }
+    if (g.nlevels > 1) {
+      const int n_side = (g.lv[1].h + kSideRows - 1) / kSideRows;            // level 1 is the tallest of levels 1..
+      k_borders<<<dim3(n_side + 2 * kBorder, g.nlevels - 1, n_frames), 256, 0, st>>>(g, 1, n_side, h->d_pyr);
+      launches++;
+    }
+  } else
   for (int l = 1; l < g.nlevels; l++) {
     const LevelGeom& L = g.lv[l];
     const int rr = h->resize_rows;
@@ -1149,6 +1279,7 @@ int cmos_orb_create(const cmos_orb_params* params, cmos_orb_t* out) {
   h->p = *params;
   h->device = params->device;
   if (const char* e = std::getenv("CMOS_FAST_THREADS")) h->fast_threads = std::atoi(e) == 256 ? 256 : 128;
+  if (const char* e = std::getenv("CMOS_RESIZE_V1")) h->resize_v2 = !(e[0] == '1');
   if (const char* e = std::getenv("CMOS_RESIZE_ROWS")) { int r = std::atoi(e); h->resize_rows = r == 2 ? 2 : r == 4 ? 4 : 1; }
   // tables of the constructor, ORBextractor.cc:410-470 (scaleFactor member is double, ORBextractor.h:95)
   const int nl = params->nlevels;
