@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(256) k_resize2(OrbGeom g, int level, const sho
 // rows x 12 words: words that hold bx in [-19, -1] or [w, w + 18]; words shared with the interior are read-modified-written);
 // the remaining blocks: one of the 38 border rows each, word per thread.
 constexpr int kSideRows = 21;     // 21 rows x 12 words = 252 threads of a 256-thread CTA
+constexpr int kBorderRowsPerCta = 4;
 __global__ void __launch_bounds__(256) k_borders(OrbGeom g, int first_level, int n_side_max, uint8_t* __restrict__ pyr) {
   const LevelGeom& L = g.lv[first_level + blockIdx.y];
   uint8_t* plane = pyr + (long long)blockIdx.z * g.frame_bytes + L.plane_off;
@@ -242,15 +243,22 @@ __global__ void __launch_bounds__(256) k_borders(OrbGeom g, int first_level, int
     return;
   }
   b -= n_side_max;
-  if (b >= 2 * kBorder) return;
-  const int prow = b < kBorder ? b : L.h + b;                       // plane row: 0..18 and h + 19 .. h + 37
+  // kBorderRowsPerCta border rows per CTA (one row per group of 64 threads): 17 k one-row CTAs were launch-bound
+  const int br = b * kBorderRowsPerCta + (threadIdx.x >> 6);
+  if (br >= 2 * kBorder) return;
+  const int prow = br < kBorder ? br : L.h + br;                    // plane row: 0..18 and h + 19 .. h + 37
   const int sy = reflect101(prow - kBorder, L.h);
-  for (int word = threadIdx.x; 4 * word < L.pitch; word += 256) {
+  for (int word = threadIdx.x & 63; 4 * word < L.pitch; word += 64) {
+    const int bx0 = 4 * word - kXOff;
     uint32_t v = 0;
+    if (bx0 >= 0 && bx0 + 3 < L.w) {        // above / below the interior: a word-aligned copy of interior row sy
+      v = *(const uint32_t*)(in + (long long)sy * L.pitch + bx0);
+    } else {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int bx = 4 * word + q - kXOff;
-      if (bx >= -kBorder && bx < L.w + kBorder) v |= (uint32_t)in[(long long)sy * L.pitch + reflect101(bx, L.w)] << (8 * q);
+      for (int q = 0; q < 4; q++) {
+        const int bx = bx0 + q;
+        if (bx >= -kBorder && bx < L.w + kBorder) v |= (uint32_t)in[(long long)sy * L.pitch + reflect101(bx, L.w)] << (8 * q);
+      }
     }
     *((uint32_t*)(plane + (long long)prow * L.pitch) + word) = v;
   }
@@ -1201,7 +1209,7 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
     }
     if (g.nlevels > 1) {
       const int n_side = (g.lv[1].h + kSideRows - 1) / kSideRows;            // level 1 is the tallest of levels 1..
-      k_borders<<<dim3(n_side + 2 * kBorder, g.nlevels - 1, n_frames), 256, 0, st>>>(g, 1, n_side, h->d_pyr);
+      k_borders<<<dim3(n_side + (2 * kBorder + kBorderRowsPerCta - 1) / kBorderRowsPerCta, g.nlevels - 1, n_frames), 256, 0, st>>>(g, 1, n_side, h->d_pyr);
       launches++;
     }
   } else
