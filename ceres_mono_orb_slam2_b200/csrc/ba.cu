@@ -2465,7 +2465,9 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
   if (d.stop_flag) { k_snapshot<<<g_par, 256, 0, st>>>(d); h->launches++; }
   k_lm_init<<<1, 1, 0, st>>>(d, max_iterations);
   h->launches++;
+  NvtxRange nvtx_solve(pass == 0 ? "cmos.ba.solve.pass0" : "cmos.ba.solve.pass1");
   for (int it = 0; it < max_iterations; it++) {
+    NvtxRange nvtx_it("cmos.ba.lm_iteration");
     int rc;
     if ((rc = linearize())) return rc;
     k_point_prep<<<(d.M + kLinThreads - 1) / kLinThreads, kLinThreads, 0, st>>>(d);

@@ -1,5 +1,6 @@
 // Shared host-side helpers for the C-ABI translation units (error text, CUDA checks).
 #pragma once
+#include <nvtx3/nvToolsExt.h>
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdio>
@@ -35,6 +36,15 @@ static inline T* dev_alloc(size_t n, cudaError_t* err) {
   if (e != cudaSuccess && err) *err = e;
   return (T*)p;
 }
+
+// NVTX range over a host-side enqueue section (header-only NVTX v3: the injection library is looked up at run time, nothing is
+// linked).  Ranges name the stages in an nsys / ncu timeline: cmos.orb.pyramid, cmos.ba.lm_iteration, ...
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // Per-stage device timing with CUDA events recorded on the launching stream (bench.py's roofline reads this).
 // When disabled nothing is recorded.  Events of up to kRing calls are kept and folded into the totals when the

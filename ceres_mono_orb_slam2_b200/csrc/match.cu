@@ -892,6 +892,7 @@ int cmos_match_set_frames(cmos_match_t h, const cmos_camera* cam, const cmos_key
   h->n_frames = n_frames;
   h->stride = stride;
   const size_t smem = (kCells + 1) * sizeof(int) + (size_t)stride * sizeof(short) + 16;
+  NvtxRange nvtx_grid("cmos.match.build_grid");
   h->timer[0].begin(st);
   k_build_grid<<<n_frames, 256, smem, st>>>(h->cam, h->kps, h->counts, stride, h->p.max_keypoints, h->d_grid_start,
                                             h->d_grid_idx);
@@ -948,6 +949,7 @@ int cmos_match_search_by_projection_frame(cmos_match_t h, const double* Tcw, con
     a.last_xw = h->s_last_xw; a.last_desc = h->s_last_desc; a.claimed = claimed ? h->s_claimed : nullptr;
     a.match = h->s_match; a.nmatches = h->s_nmatches;
   }
+  NvtxRange nvtx_frame("cmos.match.search_by_projection_frame");
   h->timer[1].begin(st);
   k_sf_lists<<<dim3((last_stride + kSfWarps - 1) / kSfWarps, B), kSfWarps * 32, 0, st>>>(
       h->cam, h->kps, h->desc, h->counts, h->stride, h->d_grid_start, h->d_grid_idx, h->p.max_keypoints, a, h->d_lists,
@@ -1020,6 +1022,7 @@ int cmos_match_search_by_projection_points(cmos_match_t h, const int32_t* n_poin
     }
     a.g_lists = h->g_lists; a.g_cnt = h->g_cnt;
   }
+  NvtxRange nvtx_pts("cmos.match.search_by_projection_points");
   h->timer[2].begin(st);
   k_search_points<<<B, kSearchThreads, lists_in_hbm ? (size_t)h->stride * 5 + 16 : search_points_smem(point_stride, h->stride), st>>>(
       h->cam, h->kps, h->desc, h->counts, h->stride, h->d_grid_start, h->d_grid_idx, h->p.max_keypoints, a);

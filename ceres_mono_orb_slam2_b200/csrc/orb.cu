@@ -1193,8 +1193,10 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
   CMOS_CUDA_OK(cudaMemsetAsync(h->d_cand_count, 0, (size_t)h->p.max_batch * kMaxLevels * sizeof(int), st));
   CMOS_CUDA_OK(cudaMemsetAsync(h->d_overflow, 0, sizeof(int), st));
   dim3 blk(64, 4);
+  NvtxRange nvtx_extract("cmos.orb.extract");
   h->timer.begin(st);
   {
+    NvtxRange nvtx_pyr("cmos.orb.pyramid");
     const LevelGeom& L = g.lv[0];
     dim3 grid((L.pitch / 4 + 63) / 64, (L.rows + 3) / 4, n_frames);
     k_level0<<<grid, blk, 0, st>>>(g, d_images, frame_stride, pitch, h->d_pyr);
@@ -1224,6 +1226,7 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
   }
   h->timer.mark(st);   // stage 0: pyramid
   if (h->n_cells > 0) {
+    NvtxRange nvtx_fast("cmos.orb.fast");
     const dim3 fg(h->n_cells, n_frames);
 #define CMOS_FAST_LAUNCH(T, TW, TH, CAP) \
   k_fast<T, TW, TH, CAP><<<fg, T, 0, st>>>(g, h->d_cells, h->d_pyr, h->d_cand, h->d_cand_count, h->d_overflow, h->d_dbg, h->dbg_cell)

@@ -128,6 +128,7 @@ int cmos_track_submit(cmos_track_t h, const uint8_t* images, int64_t frame_strid
   for (Slot& sl : h->slots)
     if (!sl.busy) { slot = &sl; break; }
   if (!slot) { set_error("%d batches are already in flight: call cmos_track_wait first", kTrackSlots); return CMOS_ERR_STATE; }
+  NvtxRange nvtx_submit("cmos.track.submit");
   const int cf = h->p.chunk_frames, nl = (int)h->lanes.size();
   int launches = 0, rc = CMOS_OK;
   // inside the loop a CUDA error must not return: copies into caller memory may be in flight on other lanes (drained below)
@@ -196,6 +197,7 @@ int cmos_track_wait(cmos_track_t h, int64_t ticket) {
   for (Slot& sl : h->slots)
     if (sl.busy && sl.ticket == ticket) { slot = &sl; break; }
   if (!slot) { set_error("ticket %lld is not in flight", (long long)ticket); return CMOS_ERR_STATE; }
+  NvtxRange nvtx_wait("cmos.track.wait");
   CMOS_CUDA_OK(cudaSetDevice(h->p.orb.device));
   int rc = CMOS_OK;
   for (cudaEvent_t e : slot->done)

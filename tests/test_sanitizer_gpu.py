@@ -1,0 +1,57 @@
+"""compute-sanitizer over one small invocation of every hot path (SURVEY.md §5 build notes): memcheck (out-of-bounds / misaligned
+accesses, API errors) and racecheck (shared-memory hazards — the engine relies on named barriers, warp-specialised phases and
+"last CTA" tails).  The workload is tiny because the tools slow kernels down by one to two orders of magnitude."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SNIPPET = r'''
+import sys
+sys.path.insert(0, %r)
+import numpy as np
+from ceres_mono_orb_slam2_b200 import Camera, CeresOptimizer, ORBextractor, ORBmatcher, synth
+W, H = 320, 240
+frames, offs = synth.make_sequence(W, H, 2, 5, return_offsets=True)
+ext = ORBextractor(300, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=2)
+kps, desc, counts = ext.extract_batch(frames)
+cap = ext.capacity
+cam = Camera.create(W, H, synth.TUM2_K, ext.GetScaleFactors(), 1.2)
+n0 = int(counts[0])
+fl, xw, md = synth.make_last_frame_view(kps[0, :n0], desc[0, :n0], (offs[0] - offs[1]).astype(float), 9, K=synth.TUM2_K)
+flags = np.zeros((1, cap), np.uint8); X = np.zeros((1, cap, 3)); D = np.zeros((1, cap, 32), np.uint8)
+flags[0, :n0] = fl; X[0, :n0] = xw; D[0, :n0] = md
+m = ORBmatcher(0.9, True, max_batch=1, max_keypoints=cap)
+m.set_frames(cam, kps[1:2], desc[1:2], counts[1:2], 1, cap)
+match, nm = m.SearchByProjectionFrame(np.eye(4).reshape(1, 16), kps[0:1], counts[0:1], flags, X, D, cap, 15.0)
+K4 = np.array(synth.KITTI_K, np.float32)
+G = synth.make_ba_problem(6, 120, 4, seed=11, n_fixed_extra=2)
+fl2 = G["fixed"].copy(); fl2[6:] |= 2
+opt = CeresOptimizer(max_cams=64, max_points=4000, max_obs=20000, max_pose_batch=1, max_pose_corr=200)
+opt.LocalBundleAdjustment(G["poses"], fl2, G["points"], G["obs_cam"], G["obs_pt"], G["uv"], G["inv_sigma2"], K4)
+P = synth.make_pose_problem(150, seed=8)
+opt.PoseOptimization(P["pose"][None], P["Xw"][None], P["uv"][None], P["inv_sigma2"][None], K4)
+G2 = synth.make_ba_problem_fast(64, 64 * 40, 5, seed=3, window=4)     # banded: the nested-dissection solver
+opt.BundleAdjustment(G2["poses"], G2["fixed"], G2["points"], G2["obs_cam"], G2["obs_pt"], G2["uv"], G2["inv_sigma2"], K4, n_iterations=2)
+print("SANITIZER_WORKLOAD_DONE", int(counts.sum()), int(nm[0]))
+''' % ROOT
+
+
+@pytest.mark.parametrize("tool", ["memcheck", "racecheck"])
+def test_compute_sanitizer_is_clean(tool, tmp_path):
+    exe = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not os.path.exists(exe):
+        pytest.skip("compute-sanitizer not installed")
+    script = tmp_path / "workload.py"
+    script.write_text(SNIPPET)
+    r = subprocess.run([exe, "--tool", tool, "--error-exitcode", "7", "--launch-timeout", "120", sys.executable, str(script)],
+                       capture_output=True, text=True, timeout=1500)
+    tail = (r.stdout + r.stderr)[-4000:]
+    assert "SANITIZER_WORKLOAD_DONE" in r.stdout, tail
+    assert r.returncode == 0, tail
+    assert "ERROR SUMMARY: 0 errors" in (r.stdout + r.stderr), tail
