@@ -1,6 +1,11 @@
 """compute-sanitizer over one small invocation of every hot path (SURVEY.md §5 build notes): memcheck (out-of-bounds / misaligned
 accesses, API errors) and racecheck (shared-memory hazards — the engine relies on named barriers, warp-specialised phases and
-"last CTA" tails).  The workload is tiny because the tools slow kernels down by one to two orders of magnitude."""
+"last CTA" tails).  The workload is tiny because the tools slow kernels down by one to two orders of magnitude.
+
+Not in the workload: round 1's serial band solver (k_band_backsub, used only for bands of fewer than 8 nodes).  racecheck reports
+its TMA ring as a WARNING (0 errors): a write-after-read between the lanes' generic-proxy reads of a ring slot and lane 0's
+cp.async.bulk refill of that slot, which the kernel orders with __syncwarp() + fence.proxy.async — the tool does not model the
+proxy fence."""
 import os
 import shutil
 import subprocess
@@ -32,7 +37,7 @@ match, nm = m.SearchByProjectionFrame(np.eye(4).reshape(1, 16), kps[0:1], counts
 K4 = np.array(synth.KITTI_K, np.float32)
 G = synth.make_ba_problem(6, 120, 4, seed=11, n_fixed_extra=2)
 fl2 = G["fixed"].copy(); fl2[6:] |= 2
-opt = CeresOptimizer(max_cams=64, max_points=4000, max_obs=20000, max_pose_batch=1, max_pose_corr=200)
+opt = CeresOptimizer(max_cams=128, max_points=4000, max_obs=20000, max_pose_batch=1, max_pose_corr=200)
 opt.LocalBundleAdjustment(G["poses"], fl2, G["points"], G["obs_cam"], G["obs_pt"], G["uv"], G["inv_sigma2"], K4)
 P = synth.make_pose_problem(150, seed=8)
 opt.PoseOptimization(P["pose"][None], P["Xw"][None], P["uv"][None], P["inv_sigma2"][None], K4)
