@@ -47,7 +47,10 @@ namespace cmos {
 constexpr int kPoseThreads = 256;
 constexpr int kLinThreads = 128;
 constexpr int kPointLanes = 4;       // lanes per map point in k_linearize / k_backsub (a power of two <= 32)
-constexpr int kCamThreads = 128;
+#ifndef CMOS_CAM_THREADS
+#define CMOS_CAM_THREADS 128
+#endif
+constexpr int kCamThreads = CMOS_CAM_THREADS;
 #ifndef CMOS_SOLVE_THREADS
 #define CMOS_SOLVE_THREADS 512
 #endif
