@@ -1,9 +1,17 @@
 """profiles/traffic.json from an ncu --set full summary (tools/ncu_summary.py output) of ONE 64-frame step:
-per bench stage, DRAM bytes read + written per launch (summed over the stage's kernels)."""
+per bench stage, DRAM bytes read + written per launch (summed over the stage's kernels).
+
+  python tools/make_traffic.py <summary.json> profiles/traffic.json [<sha256 file written on the box at capture time>]
+
+`_src_sha256` is bench.orb_source_hash() of the tree the capture ran on; bench.py reports `roofline.traffic` only when it
+matches the tree being benchmarked."""
 import json
+import os
 import sys
 
-STAGE = {"k_level0": "pyramid", "k_resize": "pyramid", "k_fast": "fast", "k_octree": "quadtree", "k_blur": "blur",
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+STAGE = {"k_level0": "pyramid", "k_resize": "pyramid", "k_resize2": "pyramid", "k_borders": "pyramid", "k_fast": "fast", "k_octree": "quadtree", "k_blur": "blur",
          "k_describe": "describe", "k_build_grid": "grid", "k_sf_lists": "search_frame", "k_sf_replay": "search_frame"}
 d = json.load(open(sys.argv[1]))
 out, dur = {}, {}
@@ -14,6 +22,11 @@ for r in d["launches"]:
         continue
     out[st] = out.get(st, 0) + int(r["dram_traffic"])
     dur[st] = dur.get(st, 0.0) + r.get("duration_us", 0.0)
+if len(sys.argv) > 3:
+    out["_src_sha256"] = open(sys.argv[3]).read().strip()
+else:
+    import bench
+    out["_src_sha256"] = bench.orb_source_hash()
 out["_source"] = f"{d['report']}: dram__bytes_read.sum + dram__bytes_write.sum per launch, one 64-frame step"
 out["_ncu_duration_us"] = {k: round(v, 1) for k, v in dur.items()}
 json.dump(out, open(sys.argv[2], "w"), indent=1)
