@@ -519,7 +519,6 @@ struct BaDev {
   LmState* st;
   double* trace;                            // [rows][8] of the running pass, or null
   const volatile uint8_t* stop_flag;        // mapped host byte or null
-  double *snap_cams, *snap_pts;             // parameters at the start of the running pass (restored when the solve is aborted)
   int pass, dbg_stop_pass, dbg_stop_iter;   // test hook: the device raises the stop flag itself at (pass, iteration)
 };
 
@@ -1622,21 +1621,9 @@ __global__ void k_set_mode(BaDev d, int mode) {
   if (p < d.N) d.o_mode[p] = (uint8_t)mode;
 }
 
-// ceres::Solve leaves the parameter blocks at their ORIGINAL values when a callback aborts it (USER_FAILURE is not a usable
-// solution): an abort in the middle of a pass discards that pass.  Snapshot at the start of the pass, restore at its end.
-__global__ void k_snapshot(BaDev d) {
-  const int i = blockIdx.x * 256 + threadIdx.x, cur = d.st->cur;
-  if (i < 7 * d.K) d.snap_cams[i] = d.cams[cur][i];
-  if (i < 3 * d.M) d.snap_pts[i] = d.pts[cur][i];
-}
-__global__ void k_restore_on_abort(BaDev d) {
-  const LmState& st = *d.st;
-  if (st.termination != TERM_USER || st.pad) return;     // pad: the flag was already up at the start (nothing is written back)
-  const int i = blockIdx.x * 256 + threadIdx.x, cur = st.cur;
-  if (i < 7 * d.K) d.cams[cur][i] = d.snap_cams[i];
-  if (i < 3 * d.M) d.pts[cur][i] = d.snap_pts[i];
-}
-
+// StopFlagCallback returns SOLVER_TERMINATE_SUCCESSFULLY (CeresOptimizer.h:340): ceres::Solve ends with USER_SUCCESS, a usable
+// solution, so the parameter blocks keep the iterate reached when the flag was seen — nothing is rolled back.  What discards
+// work is the reference's own `if (*stop_flag) return;` at the start of a LocalBundleAdjustment pass (`pad` above).
 __global__ void k_summary(BaDev d, cmos_ba_summary* out) {
   const LmState& st = *d.st;
   cmos_ba_summary s;
@@ -2465,7 +2452,6 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
     h->launches += 3;
     return CMOS_OK;
   };
-  if (d.stop_flag) { k_snapshot<<<g_par, 256, 0, st>>>(d); h->launches++; }
   k_lm_init<<<1, 1, 0, st>>>(d, max_iterations);
   h->launches++;
   NvtxRange nvtx_solve(pass == 0 ? "cmos.ba.solve.pass0" : "cmos.ba.solve.pass1");
@@ -2564,7 +2550,6 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
     int rc;
     if ((rc = linearize())) return rc;
   }
-  if (d.stop_flag) { k_restore_on_abort<<<g_par, 256, 0, st>>>(d); h->launches++; }
   k_summary<<<1, 1, 0, st>>>(d, h->d_summaries + pass);
   h->launches++;
   CMOS_CUDA_OK(cudaGetLastError());
@@ -2599,8 +2584,7 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
   BaDev& d = h->d;
   const size_t nlb = ((size_t)M * kPointLanes + kLinThreads - 1) / kLinThreads;
   ok = ok && alloc(&d.cams[0], 7 * K) && alloc(&d.cams[1], 7 * K) && alloc(&d.pts[0], 3 * M) && alloc(&d.pts[1], 3 * M);
-  ok = ok && alloc(&h->d_cams0, 7 * K) && alloc(&h->d_pts0, 3 * M) && alloc(&h->d_cams_out, 7 * K) && alloc(&h->d_pts_out, 3 * M) &&
-       alloc(&d.snap_cams, 7 * K) && alloc(&d.snap_pts, 3 * M);
+  ok = ok && alloc(&h->d_cams0, 7 * K) && alloc(&h->d_pts0, 3 * M) && alloc(&h->d_cams_out, 7 * K) && alloc(&h->d_pts_out, 3 * M);
   ok = ok && alloc(&h->d_cam_var, K) && alloc(&h->d_o_cam, N) && alloc(&h->d_o_cv, N) && alloc(&h->d_o_pt, N) &&
        alloc(&h->d_pt_start, M + 1) && alloc(&h->d_cam_start, K + 1) && alloc(&h->d_cam_obs, N) &&
        alloc(&h->d_blk_a, h->cap_blocks) && alloc(&h->d_blk_b, h->cap_blocks) && alloc(&h->d_blk_start, h->cap_blocks + 1) &&
@@ -2648,7 +2632,7 @@ int cmos_ba_destroy(cmos_ba_t h) {
                   h->d_blk_start, h->d_pair_a, h->d_pair_b, h->d_perm, h->d_o_uv, h->d_o_w, h->d_o_mode, h->d_cam_flags,
                   h->d_erase, d.Jc, d.Jp, d.res, d.Hpp, d.gp, d.Hinv, d.tp, d.scale_p, h->d_HG, h->d_var_cam, h->d_red, h->d_Sblk, d.scale_c, d.S,
                   d.yc, d.part, d.st, h->d_Linv, h->d_pan_tiles, h->d_pan_first, h->d_band_blk, h->d_trace, h->d_summaries, h->dp_pose, h->dp_xw, h->dp_uv, h->dp_w,
-                  h->dp_n, h->dp_inl, h->dp_out, h->dp_sum, h->dp_trace, d.snap_cams, d.snap_pts, h->d_chunk_start, h->d_chunk_blk, h->d_blk_chunk0,
+                  h->dp_n, h->dp_inl, h->dp_out, h->dp_sum, h->dp_trace, h->d_chunk_start, h->d_chunk_blk, h->d_blk_chunk0,
                   h->d_schur_part};
   for (void* b : bufs)
     if (b) cudaFree(b);

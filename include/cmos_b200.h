@@ -579,9 +579,10 @@ int cmos_ba_debug_trace(cmos_ba_t h, int32_t pass, double* trace, int32_t rows);
 /* Test hook for StopFlagCallback (include/CeresOptimizer.h:332-349, src/CeresOptimizer.cc:509-514): in the following solves
  * the DEVICE raises the caller's stop flag itself once `pass` (0 / 1 of LocalBundleAdjustment, 0 of the others) has finished
  * `iteration` iterations — what another thread setting the flag at that moment would do, but reproducible.  -1 disables.
- * Semantics under test: a flag that is up when a pass starts returns without writing anything back (:509-512); an abort in
- * the middle of a pass discards that pass (ceres::Solve restores the parameter blocks on USER_FAILURE) and the function
- * carries on with the parameters the pass started from. */
+ * Semantics under test: a flag that is up when a LocalBundleAdjustment pass starts returns without writing anything back
+ * (:509-512); a flag seen by the callback in the middle of a solve ends it with USER_SUCCESS (the callback returns
+ * SOLVER_TERMINATE_SUCCESSFULLY, CeresOptimizer.h:340), so the function carries on with the iterate reached at that moment —
+ * the same result as a solve whose max_num_iterations was that iteration. */
 int cmos_ba_debug_stop_at(cmos_ba_t h, int32_t pass, int32_t iteration);
 int cmos_ba_debug_pose_trace(cmos_ba_t h, int32_t frame, double* trace, int32_t rows);
 /* Kernels launched by the last cmos_ba_run_* / cmos_ba_pose_optimization call. */

@@ -116,11 +116,12 @@ def test_stop_flag_semantics():
 def test_stop_flag_raised_mid_solve():
     """StopFlagCallback semantics when the flag goes up DURING a solve (CeresOptimizer.cc:509-514, CeresOptimizer.h:332-349).
     The device raises the flag itself at a fixed (pass, iteration) — cmos_ba_debug_stop_at — so the test is reproducible.
-    ceres::Solve restores the parameter blocks when a callback aborts it, so an aborted pass is discarded:
+    The callback returns SOLVER_TERMINATE_SUCCESSFULLY, so ceres::Solve ends with USER_SUCCESS — a usable solution: the
+    parameter blocks keep the iterate reached when the flag was seen, as if max_num_iterations had been that iteration:
       * abort in pass 0 -> pass 1 finds the flag up and LocalBundleAdjustment returns without writing anything (:509-512);
-      * abort in pass 1 -> the function carries on with the result of pass 0: outlier scan, erase list, write-back — what the
-        oracle computes with (5, 0) iterations;
-      * abort of BundleAdjustment -> the poses and points it writes back are the ones it was given."""
+      * abort in pass 1 after 3 iterations -> outlier scan, erase list and write-back on that iterate — what the oracle
+        computes with (5, 3) iterations;
+      * abort of BundleAdjustment after 2 iterations -> what the oracle computes with n_iterations = 2."""
     G = synth.make_ba_problem(6, 200, 4, seed=11, n_fixed_extra=2)
     K4 = np.array(synth.KITTI_K, np.float32)
     flags = G["fixed"].copy(); flags[6:] |= 2
@@ -135,8 +136,8 @@ def test_stop_flag_raised_mid_solve():
     opt.debug_stop_at(1, 3)
     cams, pts, erase, summ = opt.LocalBundleAdjustment(*a, stop_flag=flag)
     oc, op_, oer, os_ = po.ba_local(G["poses"], flags, G["points"], G["obs_cam"], G["obs_pt"], G["uv"], G["inv_sigma2"], G["K"],
-                                    iters=(5, 0))
-    assert flag[0] == 1 and summ[0]["iterations"] == os_[0]["iterations"] == 5 and summ[1]["iterations"] == 3
+                                    iters=(5, 3))
+    assert flag[0] == 1 and summ[0]["iterations"] == os_[0]["iterations"] == 5 and summ[1]["iterations"] == os_[1]["iterations"] == 3
     assert summ[1]["termination"] == 4
     assert rel_err(cams, oc) < 1e-7 and rel_err(pts, op_) < 1e-7 and np.array_equal(erase, oer)
     assert not np.array_equal(cams, G["poses"])
@@ -144,8 +145,10 @@ def test_stop_flag_raised_mid_solve():
     opt.debug_stop_at(0, 2)
     cams, pts, s = opt.BundleAdjustment(G["poses"], G["fixed"], G["points"], G["obs_cam"], G["obs_pt"], G["uv"], G["inv_sigma2"],
                                         K4, n_iterations=8, stop_flag=flag)
-    assert flag[0] == 1 and s["iterations"] == 2 and s["termination"] == 4
-    assert np.array_equal(cams, G["poses"]) and np.array_equal(pts, G["points"])
+    oc, op_, os_, _tr = po.ba_global(G["poses"], G["fixed"], G["points"], G["obs_cam"], G["obs_pt"], G["uv"], G["inv_sigma2"], G["K"],
+                                n_iterations=2)
+    assert flag[0] == 1 and s["iterations"] == os_["iterations"] == 2 and s["termination"] == 4
+    assert rel_err(cams, oc) < 1e-7 and rel_err(pts, op_) < 1e-7 and not np.array_equal(cams, G["poses"])
     flag[0] = 0
     opt.debug_stop_at(-1, -1)
     cams, pts, s = opt.BundleAdjustment(G["poses"], G["fixed"], G["points"], G["obs_cam"], G["obs_pt"], G["uv"], G["inv_sigma2"],
