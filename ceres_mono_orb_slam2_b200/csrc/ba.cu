@@ -1394,33 +1394,76 @@ __device__ __forceinline__ void invert_diag24(double* __restrict__ L, double* __
 
 // L' x = y in 24-row block steps against a factor whose 24 x 24 diagonal blocks are inverted (invert_diag24), from the last
 // block up: x_p = inv(L_pp)' y_p, then y_q -= L_pq' x_p for the rows above.  y (n entries, shared memory) becomes x.
-// s_x: 24 doubles of shared scratch.  All threads of the CTA (blockDim.x >= n).
+// s_x: 24 doubles of shared scratch.  All threads of the CTA (blockDim.x >= n, a multiple of 32).  Every dot product is
+// split over 4 (or 2) adjacent lanes when the CTA has the threads for it — the 24 dependent load + FMA pairs of one thread
+// were the whole cost of a step (8.4 k cycles at n = 120) — and added by shuffles in a fixed order.
 __device__ __forceinline__ void back_substitute24(const double* __restrict__ L, double* __restrict__ y, double* __restrict__ s_x,
                                                   const int n) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lpu = 4 * n <= nt ? 4 : (2 * n <= nt ? 2 : 1);      // lanes per unknown
+  const int u = tid / lpu, sub = tid - u * lpu;
   for (int r0 = ((n - 1) / 24) * 24; r0 >= 0; r0 -= 24) {
     const int bs = min(24, n - r0);
-    if (tid < bs) {
-      double x0 = 0.0, x1 = 0.0;
-      for (int qq = tid; qq < bs; qq += 2) {
-        x0 += L[(r0 + qq) * (r0 + qq + 1) / 2 + r0 + tid] * y[r0 + qq];
-        if (qq + 1 < bs) x1 += L[(r0 + qq + 1) * (r0 + qq + 2) / 2 + r0 + tid] * y[r0 + qq + 1];
-      }
-      s_x[tid] = x0 + x1;
+    {
+      double v = 0.0;
+      if (u < bs)
+        for (int qq = u + sub; qq < bs; qq += lpu) v += L[(r0 + qq) * (r0 + qq + 1) / 2 + r0 + u] * y[r0 + qq];
+      if (lpu == 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (lpu >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
+      if (u < bs && sub == 0) s_x[u] = v;
     }
     __syncthreads();
-    if (tid < r0) {
-      double v0 = 0.0, v1 = 0.0;
-      for (int qq = 0; qq < bs; qq += 2) {
-        v0 += L[(r0 + qq) * (r0 + qq + 1) / 2 + tid] * s_x[qq];
-        if (qq + 1 < bs) v1 += L[(r0 + qq + 1) * (r0 + qq + 2) / 2 + tid] * s_x[qq + 1];
+    {
+      double v = 0.0;
+      if (u < r0)
+        for (int qq = sub; qq < bs; qq += lpu) v += L[(r0 + qq) * (r0 + qq + 1) / 2 + u] * s_x[qq];
+      if (lpu == 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (lpu >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
+      if (sub == 0) {
+        if (u < r0) y[u] -= v;
+        else if (u < r0 + bs) y[u] = s_x[u - r0];
       }
-      y[tid] -= v0 + v1;
-    } else if (tid < r0 + bs) {
-      y[tid] = s_x[tid - r0];
     }
     __syncthreads();
   }
+}
+
+}  // namespace cmos
+#include "chol_reg.cuh"
+namespace cmos {
+
+// Doubles of scratch behind the packed triangle that factor_and_invert24 needs for an n-column system.
+__host__ __device__ inline size_t chol_scratch_doubles(int n) {
+  const size_t v2 = (size_t)kPBuf * (n + 2) + 40;
+#ifndef CMOS_CHOL_SMEM
+  if (chol_reg_supported(n)) { const size_t r = chol_reg_scratch(n); return r > v2 ? r : v2; }
+#endif
+  return v2;
+}
+
+// Cholesky of the packed triangle L (rows 0..n, row n = rhs -> y) followed by the inversion of the 24 x 24 diagonal blocks
+// (the format invert_diag24 documents).  Systems of up to 120 unknowns take the register-resident tile factorisation
+// (chol_reg.cuh), larger ones the shared-memory panels of packed_cholesky; CMOS_CHOL_SMEM at build time forces the latter
+// (A/B).  P: chol_scratch_doubles(n) doubles.  All kSolveThreads threads; L complete (synchronised) on entry; on return
+// *s_fail tells whether a pivot failed (then the diagonal blocks are not inverted).
+__device__ __forceinline__ void factor_and_invert24(double* __restrict__ L, double* __restrict__ P, const int n, int* s_fail) {
+#ifndef CMOS_CHOL_SMEM
+  if (chol_reg_supported(n)) {
+    packed_cholesky_reg(L, P, n, s_fail);
+    __syncthreads();
+#ifdef CMOS_CHOL_TIMING
+    const long long ti0 = clock64();
+#endif
+    if (!*s_fail) invert_diag24_r8(L, P, n);
+#ifdef CMOS_CHOL_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0) printf("invert_diag24_r8 n %d: %lld cycles\n", n, clock64() - ti0);
+#endif
+    return;
+  }
+#endif
+  packed_cholesky(L, P, n, n + 2, s_fail);
+  __syncthreads();
+  if (!*s_fail) invert_diag24(L, P, n);
 }
 
 __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
@@ -1429,8 +1472,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
   if (st.done) return;
   const int n = d.nc, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* L = smem_d;                                   // rows 0..n, row i at i*(i+1)/2
-  const int ps = n + 2;
-  double* P = L + (size_t)(n + 1) * (n + 2) / 2;        // [kPB][ps]: the current panel's columns, by row
+  double* P = L + (size_t)(n + 1) * (n + 2) / 2;        // scratch of the factorisation (chol_scratch_doubles)
   __shared__ int s_fail;
   if (tid == 0) s_fail = st.solve_failed;
   for (int i = tid; i < n * (n + 1) / 2; i += kSolveThreads) L[i] = 0.0;
@@ -1453,7 +1495,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
 #else
 #define TK(i)
 #endif
-  packed_cholesky(L, P, n, ps, &s_fail);
+  factor_and_invert24(L, P, n, &s_fail);
   TK(4)
   __syncthreads();
   // back substitution L' x = y in 24-row block steps by the whole CTA (it was one warp walking 6-row blocks: 19 k of the
@@ -1461,10 +1503,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
   {
     __shared__ double s_x24[24];
     double* y = L + n * (n + 1) / 2;      // forward-substituted rhs
-    if (!s_fail) {
-      invert_diag24(L, P, n);
-      back_substitute24(L, y, s_x24, n);
-    }
+    if (!s_fail) back_substitute24(L, y, s_x24, n);
     if (warp == 0) {
       int bad = 0;
       for (int k = lane; k < n; k += 32) {
@@ -1486,6 +1525,35 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
   if ((tid == 0 || tid == 32 || tid == 1023) && st.iteration == 1)
     printf("solve_small tid %d n %d: setup+diag0 %lld | P2 %lld bar %lld P3 %lld bar %lld | backsub %lld cand %lld | total %lld\n", tid, n, tk[0], tk[1], tk[2], tk[3], tk[4], tk[5], tk[6], clock64() - tstart);
 #endif
+}
+
+// Test tap of the small dense solver (cmos_debug_solve_spd): A x = b through exactly the device code k_solve_small and
+// k_cr_factor run — factor_and_invert24 + back_substitute24 — on a caller-supplied SPD matrix.
+__global__ void __launch_bounds__(kSolveThreads) k_debug_solve_spd(const double* __restrict__ A, const double* __restrict__ b, int n,
+                                                                   double* __restrict__ x, int* fail, long long* cycles) {
+  extern __shared__ __align__(16) double smem_d[];
+  const int tid = threadIdx.x;
+  double* L = smem_d;
+  double* P = L + (size_t)(n + 1) * (n + 2) / 2;
+  __shared__ int s_fail;
+  __shared__ double s_x24[24];
+  if (tid == 0) s_fail = 0;
+  for (int e = tid; e < n * n; e += kSolveThreads) {
+    const int r = e / n, c = e - r * n;
+    if (c <= r) L[r * (r + 1) / 2 + c] = A[e];
+  }
+  for (int k = tid; k < n; k += kSolveThreads) L[n * (n + 1) / 2 + k] = b[k];
+  __syncthreads();
+  const long long t0 = clock64();
+  factor_and_invert24(L, P, n, &s_fail);
+  __syncthreads();
+  const long long t1 = clock64();
+  double* y = L + n * (n + 1) / 2;
+  if (!s_fail) back_substitute24(L, y, s_x24, n);
+  __syncthreads();
+  const long long t2 = clock64();
+  for (int k = tid; k < n; k += kSolveThreads) x[k] = s_fail ? 0.0 : y[k];
+  if (tid == 0) { *fail = s_fail; cycles[0] = t1 - t0; cycles[1] = t2 - t1; }
 }
 
 __global__ void __launch_bounds__(kLinThreads) k_backsub(BaDev d) {
@@ -2428,7 +2496,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
   const int nlb = d.n_lin_blocks;
   const int g_par = (std::max(7 * d.K, 3 * d.M) + 255) / 256;
   const bool small = d.nc <= kSmallMaxN;
-  const size_t small_smem = ((size_t)(d.nc + 1) * (d.nc + 2) / 2 + (size_t)kPBuf * (d.nc + 2) + d.nc) * sizeof(double);
+  const size_t small_smem = ((size_t)(d.nc + 1) * (d.nc + 2) / 2 + chol_scratch_doubles(d.nc)) * sizeof(double);
   const bool multi = d.multi != 0;
   auto allreduce = [&](double* buf, size_t count, int op) -> int {
     const int rc = g_nccl.AllReduce(buf, buf, count, kNcclDouble, op, h->comm, st);
@@ -2699,6 +2767,27 @@ int cmos_ba_debug_pose_trace(cmos_ba_t h, int32_t frame, double* trace, int32_t 
   CMOS_CUDA_OK(cudaDeviceSynchronize());
   CMOS_CUDA_OK(cudaMemcpy(trace, h->dp_trace + (size_t)frame * h->trace_rows * kTraceCols, (size_t)rows * kTraceCols * sizeof(double),
                           cudaMemcpyDeviceToHost));
+  return CMOS_OK;
+}
+
+int cmos_debug_solve_spd(const double* A, const double* b, int32_t n, double* x, int32_t* failed, int64_t* cycles2) {
+  CMOS_REQUIRE(A && b && x && failed && n >= 6 && n % 6 == 0 && n <= kSmallMaxN, "bad argument (n a multiple of 6, <= %d)", kSmallMaxN);
+  double *dA = nullptr, *db = nullptr, *dx = nullptr; int* df = nullptr; long long* dc = nullptr;
+  CMOS_CUDA_OK(cudaMalloc(&dA, (size_t)n * n * 8)); CMOS_CUDA_OK(cudaMalloc(&db, n * 8)); CMOS_CUDA_OK(cudaMalloc(&dx, n * 8));
+  CMOS_CUDA_OK(cudaMalloc(&df, 4)); CMOS_CUDA_OK(cudaMalloc(&dc, 16));
+  CMOS_CUDA_OK(cudaMemcpy(dA, A, (size_t)n * n * 8, cudaMemcpyHostToDevice));
+  CMOS_CUDA_OK(cudaMemcpy(db, b, n * 8, cudaMemcpyHostToDevice));
+  const size_t smem = ((size_t)(n + 1) * (n + 2) / 2 + chol_scratch_doubles(n)) * sizeof(double);
+  CMOS_CUDA_OK(cudaFuncSetAttribute(k_debug_solve_spd, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+  for (int rep = 0; rep < 2; rep++)       // the second run reports warm instruction-cache cycles
+    k_debug_solve_spd<<<1, kSolveThreads, smem>>>(dA, db, n, dx, df, dc);
+  CMOS_CUDA_OK(cudaDeviceSynchronize());
+  long long hc[2];
+  CMOS_CUDA_OK(cudaMemcpy(x, dx, n * 8, cudaMemcpyDeviceToHost));
+  CMOS_CUDA_OK(cudaMemcpy(failed, df, 4, cudaMemcpyDeviceToHost));
+  CMOS_CUDA_OK(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost));
+  if (cycles2) { cycles2[0] = hc[0]; cycles2[1] = hc[1]; }
+  cudaFree(dA); cudaFree(db); cudaFree(dx); cudaFree(df); cudaFree(dc);
   return CMOS_OK;
 }
 

@@ -51,7 +51,7 @@ __device__ __forceinline__ bool cr_has_acc_right(const CrArgs& a, int node, int 
 
 constexpr int kCrMaxN = 144;            // 6 * kBandMaxW
 inline size_t cr_factor_smem(int n) {
-  return ((size_t)(n + 1) * (n + 2) / 2 + (size_t)kPBuf * (n + 2) + 8) * sizeof(double);
+  return ((size_t)(n + 1) * (n + 2) / 2 + chol_scratch_doubles(n)) * sizeof(double);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -95,7 +95,6 @@ __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, 
   LmState& st = *d.st;
   if (st.done || st.solve_failed) return;                // (k_point_prep raises solve_failed for a singular point block)
   const int node = cr_node_at(level, blockIdx.x), n = a.n, tid = threadIdx.x;
-  const int ps = n + 2;
   double* L = smem_d;
   double* P = L + (size_t)(n + 1) * (n + 2) / 2;
   __shared__ int s_fail;
@@ -145,7 +144,9 @@ __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, 
 #ifdef CMOS_CR_TIMING
   tk[1] = clock64();
 #endif
-  packed_cholesky(L, P, n, ps, &s_fail);
+  // (the 24 x 24 diagonal blocks leave inverted: the spike and back substitutions run in 24-row block steps of tensor-core
+  // tile products)
+  factor_and_invert24(L, P, n, &s_fail);
   __syncthreads();
 #ifdef CMOS_CR_TIMING
   tk[2] = clock64();
@@ -154,7 +155,6 @@ __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, 
     if (tid == 0) st.solve_failed = 1;
     return;
   }
-  invert_diag24(L, P, n);      // the spike and back substitutions run in 24-row block steps of tensor-core tile products
   double2* Lp = (double2*)cr_arr(a, CR_LP, node);
   const int ne2 = (n * (n + 1) / 2 + 1) / 2;             // packed triangle, in double2 (n (n + 1) / 2 is even for n % 4 == 0)
   for (int e = tid; e < ne2; e += kSolveThreads) Lp[e] = ((const double2*)L)[e];

@@ -585,6 +585,11 @@ int cmos_ba_debug_trace(cmos_ba_t h, int32_t pass, double* trace, int32_t rows);
  * the same result as a solve whose max_num_iterations was that iteration. */
 int cmos_ba_debug_stop_at(cmos_ba_t h, int32_t pass, int32_t iteration);
 int cmos_ba_debug_pose_trace(cmos_ba_t h, int32_t frame, double* trace, int32_t rows);
+/* Test tap of the small dense reduced-camera-system solver (what Ceres' DENSE_SCHUR / SPARSE_SCHUR hand to LAPACK / CHOLMOD,
+ * src/CeresOptimizer.cc:178-187, 516-519): solves A x = b for a symmetric positive definite A (n x n row-major, n a multiple
+ * of 6, <= 228) with exactly the device routines the BA kernels use.  failed = 1 if a pivot was not positive.  cycles2
+ * (optional, 2 entries): SM cycles of the factorisation and of the back substitution. */
+int cmos_debug_solve_spd(const double* A, const double* b, int32_t n, double* x, int32_t* failed, int64_t* cycles2);
 /* Kernels launched by the last cmos_ba_run_* / cmos_ba_pose_optimization call. */
 int cmos_ba_last_launch_count(cmos_ba_t h, int32_t* n);
 /* Device time of the solves (CUDA events on the launching stream), as cmos_orb_set_profiling. */

@@ -19,9 +19,15 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_ba_global.csv \
   python tools/ba_profile.py global 2 > $O/ncu_ba_global.log 2>&1
 # full captures: one step of the ORB+match path, every kernel once
-# (pre-pass extraction 12 launches + 3 warm-up steps x 15 = 57 launches before the first timed 64-frame step)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ -s 57 -c 15 -o $O/full_orb \
+# (a window of 50 launches past the pre-pass; tools/make_traffic.py keeps one whole step, k_level0 to k_level0)
+timeout 900 ncu --set full --clock-control none -k regex:k_ -s 45 -c 36 -o $O/full_orb \
   python bench.py --steps 2 --warmup 3 --no-ba --no-cpu > $O/ncu_full_orb.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ -s 30 -c 12 -o $O/full_ba_local \
   python tools/ba_profile.py local > $O/ncu_full_ba_local.log 2>&1
+python -c 'import bench; print(bench.orb_source_hash())' > $O/src_sha256.txt
+# summarise on the box: gpurun copies back at most 64 MiB, the reports themselves stay behind when they are large
+python tools/ncu_summary.py $O/full_orb.ncu-rep $O/ncu_full_orb.json > /dev/null 2>&1
+python tools/ncu_summary.py $O/full_ba_local.ncu-rep $O/ncu_full_ba_local.json > /dev/null 2>&1
+for f in launches_orb launches_ba_local launches_ba_global; do python tools/summarize_launches.py $O/$f.csv > $O/${f}_summary.txt 2>&1; done
+find $O -name '*.ncu-rep' -size +12M -delete
 ls -la $O

@@ -15,7 +15,12 @@ STAGE = {"k_level0": "pyramid", "k_resize": "pyramid", "k_resize2": "pyramid", "
          "k_describe": "describe", "k_build_grid": "grid", "k_sf_lists": "search_frame", "k_sf_replay": "search_frame"}
 d = json.load(open(sys.argv[1]))
 out, dur = {}, {}
-for r in d["launches"]:
+# the capture may span several steps: keep ONE whole step = the launches from one k_level0 up to the next
+kn = lambda r: r["kernel"].split("::")[-1].split("<")[0].replace("void ", "").strip()
+starts = [i for i, r in enumerate(d["launches"]) if kn(r) == "k_level0"]
+launches = d["launches"][starts[-2]:starts[-1]] if len(starts) >= 2 else d["launches"]
+out["_launches_in_step"] = len(launches)
+for r in launches:
     name = r["kernel"].split("::")[-1].split("<")[0].replace("void ", "").strip()
     st = STAGE.get(name)
     if st is None or "dram_traffic" not in r:
