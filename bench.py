@@ -734,9 +734,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--lanes", type=int, default=4, help="stream lanes of the end-to-end front-end call")
+    ap.add_argument("--lanes", type=int, default=8, help="stream lanes of the end-to-end front-end call")
     ap.add_argument("--chunk", type=int, default=16, help="frames per pipelined chunk of the end-to-end call")
-    ap.add_argument("--split", type=int, default=2, help="sub-batches (own CUDA stream each) of the device-resident pass; 1 = off")
+    ap.add_argument("--split", type=int, default=4, help="sub-batches (own CUDA stream each) of the device-resident pass; 1 = off")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ba", action="store_true", help="skip the bundle-adjustment section")

@@ -46,6 +46,7 @@ struct cmos_track {
   int launches = 0;
   Slot slots[kTrackSlots];
   int64_t next_ticket = 0;
+  uint64_t next_chunk = 0;            // chunks are dealt to the lanes round-robin ACROSS batches
 };
 
 extern "C" {
@@ -141,8 +142,11 @@ int cmos_track_submit(cmos_track_t h, const uint8_t* images, int64_t frame_strid
       break;                                                                                  \
     }                                                                                         \
   }
-  for (int f0 = 0, c = 0; f0 < n_frames && !rc; f0 += cf, c++) {
-    Lane& L = h->lanes[c % nl];
+  // The lane of a chunk continues round-robin from the previous batch: with more lanes than chunks per batch the chunks
+  // of batch k + 1 upload on lanes that are idle while the lanes of batch k compute (inside a lane upload, kernels and
+  // download are stream-ordered, so a lane is busy for upload + compute + download of its chunk).
+  for (int f0 = 0; f0 < n_frames && !rc; f0 += cf) {
+    Lane& L = h->lanes[(size_t)(h->next_chunk++ % (uint64_t)nl)];
     const int n = std::min(cf, n_frames - f0);
     const size_t nq = (size_t)n * last_stride, o = (size_t)f0 * last_stride;
     TRACK_CUDA(cudaMemcpyAsync(L.d_T, Tcw + (size_t)f0 * 16, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, L.st));
