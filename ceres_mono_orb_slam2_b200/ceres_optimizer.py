@@ -125,6 +125,13 @@ class CeresOptimizer:
                                                        C.byref(summ)))
         return dict(lie=lie, Tiw=T.reshape(n, 4, 4), Xw=Xo[:m], summary=summ.as_dict())
 
+    def essential_graph_plan(self) -> dict:
+        """How the last OptimizeEssentialGraph call solved its normal equations (cmos_ba_debug_essential_graph_plan)."""
+        info = np.zeros(6, np.int32)
+        check(self._L.cmos_ba_debug_essential_graph_plan(self._h, ptr(info)))
+        return dict(zip(("nested_dissection", "keyframes_per_node", "node_unknowns", "nodes", "border_keyframes", "border_unknowns"),
+                        (int(v) for v in info)))
+
     def set_problem(self, cams, cam_flags, points, obs_cam, obs_pt, uv, inv_sigma2, K4):
         cams = np.ascontiguousarray(cams, np.float64); points = np.ascontiguousarray(points, np.float64)
         cf = np.ascontiguousarray(cam_flags, np.uint8)

@@ -2405,11 +2405,12 @@ struct cmos_ba {
   uint8_t* ds_bad = nullptr;
   // OptimizeEssentialGraph storage (allocated on first use, grown on demand)
   struct EgStore {
-    size_t cap_kf = 0, cap_e = 0, cap_n = 0, cap_pts = 0, cap_tiles = 0;
+    size_t cap_kf = 0, cap_e = 0, cap_n = 0, cap_pts = 0, cap_tiles = 0, cap_S = 0;
+    int plan_info[6] = {0, 0, 0, 0, 0, 0};   // last call: nested dissection used, Wb, node size, nodes, border keyframes, border size
     double *x0 = nullptr, *x1 = nullptr, *x_init = nullptr, *Scw = nullptr, *Snc = nullptr, *lie_out = nullptr, *Tiw = nullptr;
     uint8_t *flags = nullptr, *kind = nullptr;
     int *var = nullptr, *var_kf = nullptr, *ej = nullptr, *ei = nullptr, *inc_start = nullptr, *inc_edge = nullptr, *inc_other = nullptr,
-        *inc_sign = nullptr, *tiles = nullptr, *ref = nullptr, *first_col = nullptr;
+        *inc_sign = nullptr, *tiles = nullptr, *ref = nullptr, *first_col = nullptr, *pos = nullptr;
     Sim3D *meas = nullptr, *Swc = nullptr;
     double *r = nullptr, *J = nullptr, *A = nullptr, *v = nullptr, *Hd = nullptr, *g = nullptr, *scale = nullptr, *delta = nullptr,
            *S = nullptr, *rhs = nullptr, *yc = nullptr, *Linv = nullptr, *pe = nullptr, *pk = nullptr, *Xw = nullptr, *Xo = nullptr;
@@ -2418,7 +2419,7 @@ struct cmos_ba {
     void release() {
       for (void* b : {(void*)x0, (void*)x1, (void*)x_init, (void*)Scw, (void*)Snc, (void*)lie_out, (void*)Tiw, (void*)flags, (void*)kind,
                       (void*)var, (void*)var_kf, (void*)ej, (void*)ei, (void*)inc_start, (void*)inc_edge, (void*)inc_other, (void*)inc_sign,
-                      (void*)tiles, (void*)first_col, (void*)ref, (void*)meas, (void*)Swc, (void*)r, (void*)J, (void*)A, (void*)v, (void*)Hd, (void*)g,
+                      (void*)tiles, (void*)first_col, (void*)pos, (void*)ref, (void*)meas, (void*)Swc, (void*)r, (void*)J, (void*)A, (void*)v, (void*)Hd, (void*)g,
                       (void*)scale, (void*)delta, (void*)S, (void*)rhs, (void*)yc, (void*)Linv, (void*)pe, (void*)pk, (void*)Xw, (void*)Xo,
                       (void*)st})
         if (b) cudaFree(b);
@@ -2555,7 +2556,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
           k_cr_factor<<<cnt, kSolveThreads, cr_factor_smem(ca.n), st>>>(d, ca, l);
           h->launches++;
           if (l < ca.levels) {
-            k_cr_spike<<<dim3(ca.n / kCrSlab / cr_spike_warps(ca.n), 2, cnt), 32 * cr_spike_warps(ca.n), cr_spike_smem(ca.n), st>>>(d, ca, l);
+            k_cr_spike<<<dim3(ca.n / kCrSlab / cr_spike_warps(ca.n), 2, cnt), 32 * cr_spike_warps(ca.n), cr_spike_smem(ca.n), st>>>(d, ca, l, 0);
             k_cr_schur<<<dim3(tile_ctas, 4, cnt), 32 * kCrGemmWarps, 0, st>>>(d, ca, l);
             h->launches += 2;
           }
@@ -2680,6 +2681,7 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
   cudaFuncSetAttribute(k_solve_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
   cudaFuncSetAttribute(k_cr_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cr_factor_smem(kCrMaxN));
   cudaFuncSetAttribute(k_cr_spike, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_crb_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)crb_solve_smem(kCrMaxN));
   cudaFuncSetAttribute(k_cr_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cr_back_smem(kCrMaxN));
   cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
   cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
@@ -3279,6 +3281,60 @@ int cmos_ba_optimize_sim3(cmos_ba_t h, int32_t n, double* s12, double* R12, doub
   return CMOS_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// Band + border plan of a pose graph over Kv variable keyframes (edges between variable keyframes vi != vj).  A keyframe
+// whose edges reach further than Wc keyframes away goes to the border (greedy cover of the long edges: loop-closure edges
+// tie a handful of keyframes to far-away ones); the rest, in keyframe order, is banded with half-width <= Wc and is cut into
+// nodes of Wc keyframes (7 Wc unknowns padded to a multiple of 24).  ok = false: no such structure within the solver's
+// limits (node <= 144 unknowns, border <= 144 unknowns) -> the blocked Cholesky takes the system.
+struct EgPlan { bool ok = false; int Wb = 0, n = 0, N = 0, levels = 0, nb = 0, nbp = 0, Ki = 0; std::vector<int> pos; };
+EgPlan plan_eg_bcr(int Kv, const std::vector<std::pair<int, int>>& edges) {
+  EgPlan best;
+  if (Kv < 1) return best;
+  static const int kWc[] = {3, 6, 10, 13, 17, 20};
+  for (int pass = 0; pass < 2 && !best.ok; pass++) {          // pass 0: a border of <= 10 keyframes; pass 1: <= 20
+    const int nb_max = pass == 0 ? 10 : 20;
+    for (int Wc : kWc) {
+      std::vector<char> border(Kv, 0);
+      int nb = 0;
+      bool fits = true;
+      for (;;) {
+        std::vector<int> cnt(Kv, 0);
+        int any = 0;
+        for (const auto& e : edges)
+          if (!border[e.first] && !border[e.second] && std::abs(e.first - e.second) > Wc) { cnt[e.first]++; cnt[e.second]++; any++; }
+        if (!any) break;
+        int pick = 0;
+        for (int k = 1; k < Kv; k++) if (cnt[k] >= cnt[pick]) pick = k;     // most long edges, ties -> the newer keyframe
+        border[pick] = 1;
+        if (++nb > nb_max) { fits = false; break; }
+      }
+      if (!fits || nb >= Kv) continue;
+      EgPlan p;
+      p.ok = true; p.Wb = Wc; p.n = (7 * Wc + 23) / 24 * 24; p.nb = nb; p.nbp = (7 * nb + 23) / 24 * 24; p.Ki = Kv - nb;
+      p.N = (p.Ki + Wc - 1) / Wc;
+      p.levels = 1;
+      while ((1 << p.levels) <= p.N) p.levels++;
+      p.pos.resize(Kv);
+      for (int k = 0, pi = 0, bi = 0; k < Kv; k++) p.pos[k] = border[k] ? -1 - bi++ : pi++;
+      best = p;
+      break;
+    }
+  }
+  return best;
+}
+}  // namespace
+
+extern "C" {
+
+int cmos_ba_debug_essential_graph_plan(cmos_ba_t h, int32_t* info6) {
+  CMOS_REQUIRE(h && info6, "null argument");
+  for (int i = 0; i < 6; i++) info6[i] = h->eg.plan_info[i];
+  return CMOS_OK;
+}
+
 int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Scw, const uint8_t* kf_flags, const double* Snc,
                                      int32_t n_edges, const int32_t* edge_j, const int32_t* edge_i, const uint8_t* edge_kind,
                                      int32_t max_iterations, int32_t n_points, const double* Xw, const int32_t* ref_kf,
@@ -3313,8 +3369,19 @@ int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Sc
     if (vj >= 0) { const int q = fill[vj]++; inc_edge[q] = e; inc_other[q] = vi; inc_sign[q] = -1; }
     if (vi >= 0 && vj >= 0) { first_blk[std::max(vi, vj)] = std::min(first_blk[std::max(vi, vj)], std::min(vi, vj)); }
   }
+  // nested dissection (band + border) when the graph has that structure; CMOS_EG_BLOCKED=1 forces the blocked Cholesky
+  EgPlan plan;
+  {
+    std::vector<std::pair<int, int>> vv;
+    for (int e = 0; e < n_edges; e++) {
+      const int vi = var[edge_i[e]], vj = var[edge_j[e]];
+      if (vi >= 0 && vj >= 0 && vi != vj) vv.emplace_back(vi, vj);
+    }
+    const char* blocked = std::getenv("CMOS_EG_BLOCKED");
+    if (!(blocked && blocked[0] == '1')) plan = plan_eg_bcr(Kv, vv);
+  }
   std::vector<int> tiles, pan_start(1, 0), pan_first_col;
-  for (int k0 = 0; k0 < n; k0 += kNB) {
+  for (int k0 = 0; k0 < n && !plan.ok; k0 += kNB) {
     const int kb = std::min(kNB, n - k0), t0 = k0 + kb;
     int fc = k0;
     for (int r = k0; r < k0 + kb; r++) fc = std::min(fc, 7 * first_blk[r / 7]);
@@ -3329,17 +3396,21 @@ int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Sc
   }
   // ---- storage --------------------------------------------------------------------------------------------------------
   const size_t n_panels = (n + kNB - 1) / kNB;
-  if ((size_t)n_kf > g.cap_kf || (size_t)n_edges > g.cap_e || (size_t)n > g.cap_n || (size_t)n_points > g.cap_pts || tiles.size() > g.cap_tiles) {
+  // node arrays of the nested-dissection solve live in the allocation of the dense S (+ rhs and solution by node)
+  const size_t bcr_doubles = plan.ok ? cr_doubles(plan.N, plan.n) + crb_doubles(plan.N, plan.n, plan.nbp) + 2 * (size_t)plan.N * plan.n : 0;
+  if ((size_t)n_kf > g.cap_kf || (size_t)n_edges > g.cap_e || (size_t)n > g.cap_n || (size_t)n_points > g.cap_pts || tiles.size() > g.cap_tiles ||
+      bcr_doubles > g.cap_S) {
     const size_t ck = std::max<size_t>(n_kf, g.cap_kf), ce = std::max<size_t>(std::max(n_edges, 1), g.cap_e), cn = std::max<size_t>(std::max(n, 7), g.cap_n),
                  cp = std::max<size_t>(std::max(n_points, 1), g.cap_pts), ct = std::max<size_t>(std::max<size_t>(tiles.size(), 1), g.cap_tiles);
+    const size_t cS = std::max(std::max(cn * cn, bcr_doubles), g.cap_S);
     g.release();
     const size_t cpan = (cn + kNB - 1) / kNB;
     bool ok = alloc(&g.x0, 7 * ck) && alloc(&g.x1, 7 * ck) && alloc(&g.x_init, 7 * ck) && alloc(&g.Scw, 13 * ck) && alloc(&g.Snc, 13 * ck) &&
               alloc(&g.lie_out, 7 * ck) && alloc(&g.Tiw, 16 * ck) && alloc(&g.flags, ck) && alloc(&g.kind, ce) && alloc(&g.var, ck) &&
               alloc(&g.var_kf, ck) && alloc(&g.ej, ce) && alloc(&g.ei, ce) && alloc(&g.inc_start, ck + 1) && alloc(&g.inc_edge, 2 * ce) &&
-              alloc(&g.inc_other, 2 * ce) && alloc(&g.inc_sign, 2 * ce) && alloc(&g.tiles, ct) && alloc(&g.first_col, cpan + 1) && alloc(&g.ref, cp) && alloc(&g.meas, ce) &&
+              alloc(&g.inc_other, 2 * ce) && alloc(&g.inc_sign, 2 * ce) && alloc(&g.tiles, ct) && alloc(&g.first_col, cpan + 1) && alloc(&g.pos, ck) && alloc(&g.ref, cp) && alloc(&g.meas, ce) &&
               alloc(&g.Swc, ck) && alloc(&g.r, 7 * ce) && alloc(&g.J, 49 * ce) && alloc(&g.A, 49 * ce) && alloc(&g.v, 7 * ce) &&
-              alloc(&g.Hd, 49 * ck) && alloc(&g.g, cn) && alloc(&g.scale, cn) && alloc(&g.delta, cn) && alloc(&g.S, cn * cn) &&
+              alloc(&g.Hd, 49 * ck) && alloc(&g.g, cn) && alloc(&g.scale, cn) && alloc(&g.delta, cn) && alloc(&g.S, cS) &&
               alloc(&g.rhs, cn) && alloc(&g.yc, cn) && alloc(&g.Linv, cpan * kNB * kNB) && alloc(&g.pe, 3 * ce) && alloc(&g.pk, 3 * ck) &&
               alloc(&g.Xw, 3 * cp) && alloc(&g.Xo, 3 * cp) && alloc(&g.st, 1) &&
               cudaMallocHost((void**)&g.done_host, sizeof(int)) == cudaSuccess;
@@ -3348,7 +3419,7 @@ int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Sc
       g.release();
       return CMOS_ERR_CUDA;
     }
-    g.cap_kf = ck; g.cap_e = ce; g.cap_n = cn; g.cap_pts = cp; g.cap_tiles = ct;
+    g.cap_kf = ck; g.cap_e = ce; g.cap_n = cn; g.cap_pts = cp; g.cap_tiles = ct; g.cap_S = cS;
   }
   auto up = [&](void* dst, const void* src, size_t bytes) { return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
   CMOS_CUDA_OK(up(g.Scw, Scw, (size_t)n_kf * 13 * sizeof(double)));
@@ -3365,6 +3436,7 @@ int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Sc
   CMOS_CUDA_OK(up(g.inc_sign, inc_sign.data(), (size_t)n_inc * sizeof(int)));
   CMOS_CUDA_OK(up(g.tiles, tiles.data(), tiles.size() * sizeof(int)));
   CMOS_CUDA_OK(up(g.first_col, pan_first_col.data(), pan_first_col.size() * sizeof(int)));
+  if (plan.ok) CMOS_CUDA_OK(up(g.pos, plan.pos.data(), (size_t)Kv * sizeof(int)));
   CMOS_CUDA_OK(up(g.Xw, Xw, (size_t)n_points * 3 * sizeof(double)));
   CMOS_CUDA_OK(up(g.ref, ref_kf, (size_t)n_points * sizeof(int)));
   EgDev d{};
@@ -3378,6 +3450,16 @@ int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Sc
   d.st = g.st; d.trace = h->dp_trace;
   BaDev dv{};                       // the view the blocked Cholesky kernels read: S, rhs, yc, nc, st
   dv.S = g.S; dv.rhs = g.rhs; dv.yc = g.yc; dv.nc = n; dv.st = g.st;
+  CrArgs ca{};
+  g.plan_info[0] = plan.ok; g.plan_info[1] = plan.Wb; g.plan_info[2] = plan.n; g.plan_info[3] = plan.N; g.plan_info[4] = plan.nb; g.plan_info[5] = plan.nbp;
+  if (plan.ok) {
+    ca.n = plan.n; ca.Wb = plan.Wb; ca.N = plan.N; ca.W = plan.Wb; ca.levels = plan.levels; ca.band_blk = nullptr; ca.base = g.S;
+    ca.nbp = plan.nbp;
+    ca.bbase = g.S + cr_doubles(plan.N, plan.n);
+    double* rn = ca.bbase + crb_doubles(plan.N, plan.n, plan.nbp);
+    ca.rhs_nodes = rn; ca.x_nodes = rn + (size_t)plan.N * plan.n;
+    d.bcr = 1; d.n_interior = plan.Ki; d.n_border = plan.nb; d.pos = g.pos; d.ca = ca;
+  }
   const int eff_iterations = Kv > 0 ? max_iterations : 0;
   h->launches = 0;
   const int gk = (n_kf + 127) / 128, ge = std::max(1, (n_edges + 63) / 64), gw = std::max(1, (Kv + 3) / 4);
@@ -3392,6 +3474,32 @@ int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Sc
   };
   for (int it = 0; it < eff_iterations; it++) {
     linearize();
+    if (plan.ok) {
+      // nested dissection: log2(N) levels of node factorisations (all nodes of a level in parallel), the border last
+      k_eg_cr_clear<<<ca.N + 1, 256, 0, st>>>(d);
+      k_eg_build<<<gw, 128, 0, st>>>(d);
+      h->launches += 2;
+      const int nt = ca.n / 24, ntb = ca.nbp / 24, kw = cr_spike_warps(ca.n);
+      const int tile_ctas = (nt * nt + kCrGemmWarps - 1) / kCrGemmWarps;
+      const int tile_ctas_b = (std::max(nt * ntb, ntb * ntb) + kCrGemmWarps - 1) / kCrGemmWarps;
+      for (int l = 1; l <= ca.levels; l++) {
+        const int cnt = ((ca.N >> (l - 1)) + 1) / 2;
+        k_cr_factor<<<cnt, kSolveThreads, cr_factor_smem(ca.n), st>>>(dv, ca, l);
+        h->launches++;
+        if (l < ca.levels) { k_cr_spike<<<dim3(nt / kw, 2, cnt), 32 * kw, cr_spike_smem(ca.n), st>>>(dv, ca, l, 0); h->launches++; }
+        if (ntb) { k_cr_spike<<<dim3((ntb + kw - 1) / kw, 1, cnt), 32 * kw, cr_spike_smem(ca.n), st>>>(dv, ca, l, 2); h->launches++; }
+        if (l < ca.levels) { k_cr_schur<<<dim3(tile_ctas, 4, cnt), 32 * kCrGemmWarps, 0, st>>>(dv, ca, l); h->launches++; }
+        if (ntb) { k_crb_schur<<<dim3(tile_ctas_b, 4, cnt), 32 * kCrGemmWarps, 0, st>>>(dv, ca, l); h->launches++; }
+      }
+      if (ntb) { k_crb_solve<<<1, kSolveThreads, crb_solve_smem(ca.nbp), st>>>(dv, ca); h->launches++; }
+      for (int l = ca.levels; l >= 1; l--) {
+        const int cnt = ((ca.N >> (l - 1)) + 1) / 2;
+        k_cr_back<<<cnt, 32 * kCrBackWarps, cr_back_smem(ca.n), st>>>(dv, ca, l);
+        h->launches++;
+      }
+      k_eg_cr_scatter<<<(n + 255) / 256, 256, 0, st>>>(d);
+      h->launches++;
+    } else {
     CMOS_CUDA_OK(cudaMemsetAsync(g.S, 0, (size_t)n * n * sizeof(double), st));
     k_eg_build<<<gw, 128, 0, st>>>(d);
     h->launches++;
@@ -3417,6 +3525,7 @@ int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Sc
         k_backsolve_panel<<<std::max(1, (k0 - c0 + 255) / 256), 256, 0, st>>>(dv, k0, kb, g.Linv, c0);
         h->launches++;
       }
+    }
     k_eg_step<<<gk, 128, 0, st>>>(d);
     k_eg_eval<<<ge, 64, 0, st>>>(d);
     k_eg_decide<<<1, 256, 0, st>>>(d, g.done_host);

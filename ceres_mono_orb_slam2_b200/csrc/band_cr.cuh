@@ -31,6 +31,12 @@ struct CrArgs {
   int n, Wb, N, W, levels;
   const int* band_blk;      // [Kv][W+1]: id of block (b - off, b), or -1
   double* base;
+  // BORDERED systems (band + arrow: the pose graph of OptimizeEssentialGraph, whose loop edges tie a few keyframes to
+  // far-away ones — those keyframes are ordered last and form the border; posegraph.cuh).  nbp = 0: no border.
+  int nbp;                  // border unknowns, padded to a multiple of 24
+  double* bbase;            // border storage (crb_* below)
+  const double* rhs_nodes;  // [N][n] right-hand side by node (null: BaDev::rhs in 6-wide camera blocks)
+  double* x_nodes;          // [N][n] solution by node (null: BaDev::yc)
 };
 enum { CR_D0 = 0, CR_ACCL, CR_ACCR, CR_EP, CR_LP, CR_VL, CR_VR, CR_CLR, CR_NARR };
 enum { CR_BL = 0, CR_BR, CR_Y, CR_X, CR_NVEC };
@@ -48,6 +54,30 @@ __device__ __forceinline__ int cr_node_at(int level, int t) { return (1 << (leve
 // always exists) and from its right side iff node i + 1 exists; the first contribution of either side comes at level 1.
 __device__ __forceinline__ bool cr_has_acc_left(int level) { return level >= 2; }
 __device__ __forceinline__ bool cr_has_acc_right(const CrArgs& a, int node, int level) { return level >= 2 && node < a.N; }
+
+// Border: the system is [[B, F], [F', C]] with B block tridiagonal in nodes.  Eliminating node i also produces
+//   V_b = L^-1 F_i;  F_l -= V_l' V_b,  F_r -= V_r' V_b  (accumulated like AccR / AccL: one writer per level),
+//   C -= V_b' V_b,  g_C -= V_b' y_i  (one partial per node, summed in node order by k_crb_solve),
+// after the last level C x_C = g_C is one small dense solve, and the back substitution subtracts V_b x_C.
+//   F, FaccL, FaccR, Vb: N x n x nbp;  Cpart: N x nbp x nbp;  gpart: N x nbp;  C0: nbp x nbp;  gB, xB: nbp.
+enum { CRB_F = 0, CRB_FACCL, CRB_FACCR, CRB_VB, CRB_NARR };
+__host__ __device__ inline size_t crb_doubles(int N, int n, int nbp) {
+  return (size_t)CRB_NARR * N * n * nbp + (size_t)N * nbp * nbp + (size_t)N * nbp + (size_t)nbp * nbp + 2 * (size_t)nbp;
+}
+__device__ __forceinline__ double* crb_arr(const CrArgs& a, int k, int node) {
+  return a.bbase + ((size_t)k * a.N + (node - 1)) * a.n * a.nbp;
+}
+__device__ __forceinline__ double* crb_cpart(const CrArgs& a, int node) {
+  return a.bbase + (size_t)CRB_NARR * a.N * a.n * a.nbp + (size_t)(node - 1) * a.nbp * a.nbp;
+}
+__device__ __forceinline__ double* crb_gpart(const CrArgs& a, int node) {
+  return a.bbase + (size_t)CRB_NARR * a.N * a.n * a.nbp + (size_t)a.N * a.nbp * a.nbp + (size_t)(node - 1) * a.nbp;
+}
+__device__ __forceinline__ double* crb_c0(const CrArgs& a) {
+  return a.bbase + (size_t)CRB_NARR * a.N * a.n * a.nbp + (size_t)a.N * a.nbp * a.nbp + (size_t)a.N * a.nbp;
+}
+__device__ __forceinline__ double* crb_gb(const CrArgs& a) { return crb_c0(a) + (size_t)a.nbp * a.nbp; }
+__device__ __forceinline__ double* crb_xb(const CrArgs& a) { return crb_gb(a) + a.nbp; }
 
 constexpr int kCrMaxN = 144;            // 6 * kBandMaxW
 inline size_t cr_factor_smem(int n) {
@@ -136,7 +166,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, 
     const double* bR = cr_vec(a, CR_BR, node);
     for (int k = tid; k < n; k += kSolveThreads) {
       const int cam = b0 + k / 6;
-      const double r0 = cam < d.Kv ? d.rhs[6 * b0 + k] : 0.0;
+      const double r0 = a.rhs_nodes ? a.rhs_nodes[(size_t)(node - 1) * n + k] : (cam < d.Kv ? d.rhs[6 * b0 + k] : 0.0);
       L[n * (n + 1) / 2 + k] = (r0 - (hl ? bL[k] : 0.0)) - (hr ? bR[k] : 0.0);
     }
   }
@@ -229,13 +259,14 @@ inline int cr_spike_warps(int n) {                         // slabs per CTA: a d
 inline size_t cr_spike_smem(int n) {
   return ((size_t)n * (n + 1) / 2 + (size_t)n * (kCrSlab * cr_spike_warps(n) + 4)) * sizeof(double);
 }
-__global__ void __launch_bounds__(192) k_cr_spike(BaDev d, CrArgs a, int level) {
+// side 2 (launched on its own, side0 = 2): V_b = L^-1 (F_i - FaccL - FaccR), nbp columns.
+__global__ void __launch_bounds__(192) k_cr_spike(BaDev d, CrArgs a, int level, int side0) {
   extern __shared__ __align__(16) double smem_d[];
   const LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
-  const int node = cr_node_at(level, blockIdx.z), side = blockIdx.y, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nbr = side ? node + (1 << (level - 1)) : node - (1 << (level - 1));
-  if (nbr < 1 || nbr > a.N) return;
+  const int node = cr_node_at(level, blockIdx.z), side = side0 + blockIdx.y, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nbr = side == 1 ? node + (1 << (level - 1)) : node - (1 << (level - 1));
+  if (side < 2 && (nbr < 1 || nbr > a.N)) return;
   const int kw = blockDim.x >> 5, ld = kCrSlab * kw + 4;   // + 4: the four k rows of a B fragment fall into different banks
   double* L = smem_d;                                    // packed factor
   double* Xs = L + (size_t)n * (n + 1) / 2;              // [n][ld]: solved block rows, warp w owns columns 24 w .. 24 w + 23
@@ -245,11 +276,16 @@ __global__ void __launch_bounds__(192) k_cr_spike(BaDev d, CrArgs a, int level) 
     for (int e = tid; e < ne2; e += blockDim.x) ((double2*)L)[e] = Lp[e];
   }
   __syncthreads();
-  const CrCoupling cp = cr_coupling(a, node, level, side);
+  const bool border = side == 2;
+  const CrCoupling cp = border ? CrCoupling{crb_arr(a, CRB_F, node), false, 1.0} : cr_coupling(a, node, level, side);
   const double* __restrict__ src = cp.src;
   const int j0 = kCrSlab * (blockIdx.x * kw + warp), wc = kCrSlab * warp;
   const int g = lane >> 2, q = lane & 3;
-  double* V = cr_arr(a, side ? CR_VR : CR_VL, node);
+  const int ldv = border ? a.nbp : n;                    // columns of the coupling block and of V
+  if (j0 >= ldv) return;                                 // (only __syncwarp below)
+  double* V = border ? crb_arr(a, CRB_VB, node) : cr_arr(a, side ? CR_VR : CR_VL, node);
+  const double* __restrict__ fl = border && cr_has_acc_left(level) ? crb_arr(a, CRB_FACCL, node) : nullptr;
+  const double* __restrict__ fr = border && cr_has_acc_right(a, node, level) ? crb_arr(a, CRB_FACCR, node) : nullptr;
   for (int p = 0; p < n / kCrSlab; p++) {
     const int r0 = kCrSlab * p;
     CrTile t;
@@ -258,7 +294,13 @@ __global__ void __launch_bounds__(192) k_cr_spike(BaDev d, CrArgs a, int level) 
 #pragma unroll
       for (int ni = 0; ni < 3; ni++) {
         const int row = r0 + 8 * mi + g, col = j0 + 8 * ni + 2 * q;
-        if (cp.trans) {
+        if (border) {
+          const size_t o = (size_t)row * ldv + col;
+          double2 v = __ldg((const double2*)(src + o));
+          if (fl) { const double2 u = *(const double2*)(fl + o); v.x -= u.x; v.y -= u.y; }
+          if (fr) { const double2 u = *(const double2*)(fr + o); v.x -= u.x; v.y -= u.y; }
+          t.c[mi][ni][0] = v.x; t.c[mi][ni][1] = v.y;
+        } else if (cp.trans) {
           t.c[mi][ni][0] = cp.sign * __ldg(src + (size_t)col * n + row);
           t.c[mi][ni][1] = cp.sign * __ldg(src + (size_t)(col + 1) * n + row);
         } else {
@@ -286,7 +328,7 @@ __global__ void __launch_bounds__(192) k_cr_spike(BaDev d, CrArgs a, int level) 
       for (int ni = 0; ni < 3; ni++) {
         const double2 v = make_double2(x.c[mi][ni][0], x.c[mi][ni][1]);
         *(double2*)(Xs + (r0 + 8 * mi + g) * ld + wc + 8 * ni + 2 * q) = v;
-        *(double2*)(V + (size_t)(r0 + 8 * mi + g) * n + j0 + 8 * ni + 2 * q) = v;
+        *(double2*)(V + (size_t)(r0 + 8 * mi + g) * ldv + j0 + 8 * ni + 2 * q) = v;
       }
     __syncwarp();
   }
@@ -340,6 +382,101 @@ __global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur(BaDev d, CrArgs 
     }
 }
 
+// Border products of an eliminated node: grid (tile groups, product, node).
+//   product 0: FaccR[l] += V_l' V_b   1: FaccL[r] += V_r' V_b   2: Cpart[i] = V_b' V_b (lower tiles)   3: gpart[i] = V_b' y_i
+__global__ void __launch_bounds__(32 * kCrGemmWarps) k_crb_schur(BaDev d, CrArgs a, int level) {
+  const LmState& st = *d.st;
+  if (st.done || st.solve_failed) return;
+  const int node = cr_node_at(level, blockIdx.z), prod = blockIdx.y, n = a.n, nbp = a.nbp, h = 1 << (level - 1);
+  const int l = node - h, r = node + h;
+  const bool has_l = l >= 1, has_r = r <= a.N;
+  const double* __restrict__ Vb = crb_arr(a, CRB_VB, node);
+  if (prod == 3) {
+    if (blockIdx.x != 0) return;
+    const double* __restrict__ y = cr_vec(a, CR_Y, node);
+    double* gp = crb_gpart(a, node);
+    for (int c = threadIdx.x; c < nbp; c += 32 * kCrGemmWarps) {
+      double v = 0.0;
+      for (int k = 0; k < n; k++) v += Vb[(size_t)k * nbp + c] * y[k];
+      gp[c] = v;
+    }
+    return;
+  }
+  if ((prod == 0 && !has_l) || (prod == 1 && !has_r)) return;
+  const int ntr = (prod == 2 ? nbp : n) / 24, ntc = nbp / 24;
+  const int tile = blockIdx.x * kCrGemmWarps + (threadIdx.x >> 5);
+  if (tile >= ntr * ntc) return;
+  const int p0 = 24 * (tile / ntc), q0 = 24 * (tile % ntc);
+  if (prod == 2 && q0 > p0) return;
+  const double* __restrict__ Va = prod == 0 ? cr_arr(a, CR_VL, node) : prod == 1 ? cr_arr(a, CR_VR, node) : Vb;
+  const int lda = prod == 2 ? nbp : n;
+  CrTile t;
+  cr_tile_mma(t, 0, n,
+              [&](int rr, int k) { return __ldg(Va + (size_t)k * lda + p0 + rr); },
+              [&](int k, int c) { return __ldg(Vb + (size_t)k * nbp + q0 + c); });
+  double* dst = prod == 0 ? crb_arr(a, CRB_FACCR, l) : prod == 1 ? crb_arr(a, CRB_FACCL, r) : crb_cpart(a, node);
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < 3; mi++)
+#pragma unroll
+    for (int ni = 0; ni < 3; ni++) {
+      double2* o = (double2*)(dst + (size_t)(p0 + 8 * mi + g) * nbp + q0 + 8 * ni + 2 * q);
+      if (prod == 2 || level == 1) *o = make_double2(t.c[mi][ni][0], t.c[mi][ni][1]);
+      else { const double2 old = *o; *o = make_double2(old.x + t.c[mi][ni][0], old.y + t.c[mi][ni][1]); }
+    }
+}
+
+// The border system after every node is eliminated: (C0 - sum_i Cpart[i]) x_C = gB - sum_i gpart[i], sums in node order;
+// one CTA, the same small dense solver as LocalBundleAdjustment's reduced camera system.
+inline size_t crb_solve_smem(int nbp) { return ((size_t)(nbp + 1) * (nbp + 2) / 2 + chol_scratch_doubles(nbp)) * sizeof(double); }
+__global__ void __launch_bounds__(kSolveThreads) k_crb_solve(BaDev d, CrArgs a) {
+  extern __shared__ __align__(16) double smem_d[];
+  LmState& st = *d.st;
+  if (st.done || st.solve_failed) return;
+  const int nb = a.nbp, tid = threadIdx.x;
+  double* L = smem_d;
+  double* P = L + (size_t)(nb + 1) * (nb + 2) / 2;
+  __shared__ int s_fail;
+  __shared__ double s_x24[24];
+  if (tid == 0) s_fail = 0;
+  const double* __restrict__ C0 = crb_c0(a);
+  const double* __restrict__ gB = crb_gb(a);
+  const double* __restrict__ Cp = crb_cpart(a, 1);
+  const double* __restrict__ gp = crb_gpart(a, 1);
+  const int ne = nb * (nb + 1) / 2;
+  for (int e = tid; e < ne + nb; e += kSolveThreads) {
+    double v, s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;       // four interleaved partial sums, fixed order
+    size_t off, stride;
+    if (e < ne) {
+      int r = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      while ((r + 1) * (r + 2) / 2 <= e) r++;
+      while (r * (r + 1) / 2 > e) r--;
+      const int c = e - r * (r + 1) / 2;
+      off = (size_t)r * nb + c; stride = (size_t)nb * nb;
+      v = C0[off];
+    } else {
+      off = e - ne; stride = nb;
+      v = gB[off];
+    }
+    const double* __restrict__ src = e < ne ? Cp : gp;
+    int i = 0;
+    for (; i + 4 <= a.N; i += 4) {
+      s0 += src[off + (size_t)i * stride]; s1 += src[off + (size_t)(i + 1) * stride];
+      s2 += src[off + (size_t)(i + 2) * stride]; s3 += src[off + (size_t)(i + 3) * stride];
+    }
+    for (; i < a.N; i++) s0 += src[off + (size_t)i * stride];
+    L[e] = v - ((s0 + s1) + (s2 + s3));
+  }
+  __syncthreads();
+  factor_and_invert24(L, P, nb, &s_fail);
+  __syncthreads();
+  if (s_fail) { if (tid == 0) st.solve_failed = 1; return; }
+  double* y = L + ne;
+  back_substitute24(L, y, s_x24, nb);
+  double* xb = crb_xb(a);
+  for (int k = tid; k < nb; k += kSolveThreads) xb[k] = y[k];
+}
+
 // Back substitution of one level, one CTA per node: z = y_i - V_l x_l - V_r x_r (rows are independent: a warp takes four
 // rows per step so that 16-40 loads per lane are in flight), then L' x = z by blocked substitution against the packed
 // factor in shared memory, from the last 24-row block up (right-looking: x_p = inv(L_pp)' z_p, then z_q -= L_pq' x_p, q < p).
@@ -367,6 +504,8 @@ __global__ void __launch_bounds__(32 * kCrBackWarps) k_cr_back(BaDev d, CrArgs a
   const double* __restrict__ Vl = cr_arr(a, CR_VL, node);
   const double* __restrict__ Vr = cr_arr(a, CR_VR, node);
   const double* __restrict__ y = cr_vec(a, CR_Y, node);
+  const double* __restrict__ Vb = a.nbp ? crb_arr(a, CRB_VB, node) : nullptr;
+  const double* __restrict__ xb = a.nbp ? crb_xb(a) : nullptr;
   constexpr int kCols = (kCrMaxN + 31) / 32;               // column groups per lane
   for (int k0 = 4 * warp; k0 < n; k0 += 4 * kCrBackWarps) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -381,6 +520,17 @@ __global__ void __launch_bounds__(32 * kCrBackWarps) k_cr_back(BaDev d, CrArgs a
           const double vl = has_l ? Vl[(size_t)k * n + j] : 0.0;
           const double vr = has_r ? Vr[(size_t)k * n + j] : 0.0;
           acc[q] += vl * xl + vr * xr;
+        }
+      }
+    }
+    if (Vb) {                                                // bordered system: ... - V_b x_C
+#pragma unroll
+      for (int u = 0; u < kCols; u++) {
+        const int j = lane + 32 * u;
+        if (j < a.nbp) {
+          const double xj = xb[j];
+#pragma unroll
+          for (int q = 0; q < 4; q++) acc[q] += Vb[(size_t)min(k0 + q, n - 1) * a.nbp + j] * xj;
         }
       }
     }
@@ -401,7 +551,8 @@ __global__ void __launch_bounds__(32 * kCrBackWarps) k_cr_back(BaDev d, CrArgs a
   for (int j = tid; j < n; j += 32 * kCrBackWarps) {
     const double v = s_z[j];
     x[j] = v;
-    if (b0 + j / 6 < d.Kv) d.yc[6 * b0 + j] = v;
+    if (a.x_nodes) a.x_nodes[(size_t)(node - 1) * n + j] = v;
+    else if (b0 + j / 6 < d.Kv) d.yc[6 * b0 + j] = v;
   }
 }
 

@@ -15,7 +15,9 @@
 //   k_eg_post_lin            one CTA: fixed-order reductions, Jacobi scaling at iteration 0, LM bookkeeping
 //   k_eg_build               warp per variable keyframe: its block row of the scaled, damped normal equations into the dense
 //                            lower triangle (only this warp writes the row, duplicates of a keyframe pair accumulate in order)
-//   blocked Cholesky         k_potrf_diag / k_trsm_panel / k_syrk_tile / k_backsolve_panel inside the row envelope
+//   solve                    nested dissection of the band + border structure (band_cr.cuh: keyframes with long-range edges form
+//                            the border, the rest is block tridiagonal in nodes of Wb keyframes), or, when the graph has no
+//                            such structure, blocked Cholesky k_potrf_diag / k_trsm_panel / k_syrk_tile inside the row envelope
 //   k_eg_step                thread per keyframe: delta = -y * scale, candidate = Plus(x, delta)
 //   k_eg_eval                thread per edge: model cost change -(J d)'(r + J d / 2) and the candidate's cost term
 //   k_eg_decide              one CTA: reductions, accept / reject, radius, termination tests
@@ -43,7 +45,80 @@ struct EgDev {
   double *p_gmax, *p_xn2, *p_sn2;     // [Kv]
   LmState* st;
   double* trace;
+  // Nested-dissection solve of the normal equations (band_cr.cuh with a border): bcr != 0 -> k_eg_build writes the node
+  // blocks instead of the dense lower triangle.  pos[a] >= 0: position of variable keyframe a among the interior
+  // (banded) keyframes; pos[a] < 0: border keyframe -1 - pos[a] (a keyframe with an edge to a far-away one).
+  int bcr, n_interior, n_border;
+  const int* pos;
+  CrArgs ca;
 };
+
+// Where entry (scalar r of variable keyframe a, scalar c of variable keyframe b <= a) of the lower triangle lives.
+__device__ __forceinline__ double* eg_entry(const EgDev& d, int a, int r, int b, int c) {
+  if (!d.bcr) return d.S + (size_t)(7 * a + r) * d.n + 7 * b + c;
+  const CrArgs& ca = d.ca;
+  const int pa = d.pos[a], pb = d.pos[b];
+  if (pa >= 0 && pb >= 0) {                                  // interior x interior: same node, or node and its left neighbour
+    const int na = pa / ca.Wb, nb = pb / ca.Wb;
+    const int la = 7 * (pa - na * ca.Wb) + r, lb = 7 * (pb - nb * ca.Wb) + c;
+    return cr_arr(ca, na == nb ? CR_D0 : CR_EP, na + 1) + (size_t)la * ca.n + lb;
+  }
+  if (pa < 0 && pb < 0) return crb_c0(ca) + (size_t)(7 * (-1 - pa) + r) * ca.nbp + 7 * (-1 - pb) + c;
+  if (pa < 0) {                                              // border row, interior column: F_node(b)[b's scalar][a's scalar]
+    const int nb = pb / ca.Wb;
+    return crb_arr(ca, CRB_F, nb + 1) + (size_t)(7 * (pb - nb * ca.Wb) + c) * ca.nbp + 7 * (-1 - pa) + r;
+  }
+  const int na = pa / ca.Wb;                                 // interior row, border column (a border keyframe with a smaller index)
+  return crb_arr(ca, CRB_F, na + 1) + (size_t)(7 * (pa - na * ca.Wb) + r) * ca.nbp + 7 * (-1 - pb) + c;
+}
+__device__ __forceinline__ double* eg_rhs_entry(const EgDev& d, int a, int r) {
+  if (!d.bcr) return d.rhs + 7 * a + r;
+  const int pa = d.pos[a];
+  if (pa < 0) return crb_gb(d.ca) + 7 * (-1 - pa) + r;
+  const int na = pa / d.ca.Wb;
+  return const_cast<double*>(d.ca.rhs_nodes) + (size_t)na * d.ca.n + 7 * (pa - na * d.ca.Wb) + r;
+}
+
+// Zero the node blocks the assembly accumulates into and put ones on the diagonal of the padding rows (a node holds Wb
+// keyframes = 7 Wb unknowns, padded to a multiple of 24; the border likewise).  One CTA per node + one for the border.
+__global__ void __launch_bounds__(256) k_eg_cr_clear(EgDev d) {
+  const LmState& st = *d.st;
+  if (st.done) return;
+  const CrArgs& ca = d.ca;
+  const int tid = threadIdx.x, n = ca.n, nbp = ca.nbp;
+  if ((int)blockIdx.x < ca.N) {
+    const int node = blockIdx.x + 1;
+    double* D0 = cr_arr(ca, CR_D0, node);
+    double* Ep = cr_arr(ca, CR_EP, node);
+    for (int e = tid; e < n * n; e += 256) { D0[e] = 0.0; Ep[e] = 0.0; }
+    if (nbp) { double* F = crb_arr(ca, CRB_F, node); for (int e = tid; e < n * nbp; e += 256) F[e] = 0.0; }
+    double* rn = const_cast<double*>(ca.rhs_nodes) + (size_t)(node - 1) * n;
+    for (int e = tid; e < n; e += 256) rn[e] = 0.0;
+    __syncthreads();
+    const int real = 7 * max(0, min(ca.Wb, d.n_interior - (node - 1) * ca.Wb));
+    for (int e = real + tid; e < n; e += 256) D0[(size_t)e * n + e] = 1.0;
+  } else if (nbp) {
+    double* C0 = crb_c0(ca);
+    double* gB = crb_gb(ca);
+    for (int e = tid; e < nbp * nbp; e += 256) C0[e] = 0.0;
+    for (int e = tid; e < nbp; e += 256) gB[e] = 0.0;
+    __syncthreads();
+    for (int e = 7 * d.n_border + tid; e < nbp; e += 256) C0[(size_t)e * nbp + e] = 1.0;
+  }
+}
+
+// solution by node / border -> yc in variable-keyframe order
+__global__ void __launch_bounds__(256) k_eg_cr_scatter(EgDev d) {
+  const LmState& st = *d.st;
+  if (st.done || st.solve_failed) return;
+  const int q = blockIdx.x * 256 + threadIdx.x;
+  if (q >= d.n) return;
+  const int a = q / 7, r = q - 7 * a, pa = d.pos[a];
+  double v;
+  if (pa < 0) v = crb_xb(d.ca)[7 * (-1 - pa) + r];
+  else { const int na = pa / d.ca.Wb; v = d.ca.x_nodes[(size_t)na * d.ca.n + 7 * (pa - na * d.ca.Wb) + r]; }
+  d.yc[q] = v;
+}
 
 __device__ __forceinline__ void sim3_from_srt(const double* v13, Sim3D& S) {
   S.s = v13[0];
@@ -196,7 +271,6 @@ __global__ void __launch_bounds__(128) k_eg_build(EgDev d) {
   const int a = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0) st.solve_failed = 0;
   if (a >= d.Kv) return;
-  const int n = d.n;
   const double* sa = d.scale + 7 * (size_t)a;
   const double* Hd = d.Hd + 49 * (size_t)a;
   for (int q = lane; q < 49; q += 32) {
@@ -204,9 +278,9 @@ __global__ void __launch_bounds__(128) k_eg_build(EgDev d) {
     if (c > r) continue;
     double v = sa[r] * Hd[q] * sa[c];
     if (r == c) v += fmin(fmax(sa[r] * sa[r] * Hd[q], kMinLmDiag), kMaxLmDiag) / st.radius;
-    d.S[(size_t)(7 * a + r) * n + 7 * a + c] = v;
+    *eg_entry(d, a, r, a, c) = v;
   }
-  if (lane < 7) d.rhs[7 * a + lane] = sa[lane] * d.g[7 * (size_t)a + lane];
+  if (lane < 7) *eg_rhs_entry(d, a, lane) = sa[lane] * d.g[7 * (size_t)a + lane];
   for (int p = d.inc_start[a]; p < d.inc_start[a + 1]; p++) {
     const int b = d.inc_other[p];
     if (b < 0 || b >= a) continue;
@@ -214,7 +288,7 @@ __global__ void __launch_bounds__(128) k_eg_build(EgDev d) {
     const double* sb = d.scale + 7 * (size_t)b;
     for (int q = lane; q < 49; q += 32) {
       const int r = q / 7, c = q - 7 * r;
-      d.S[(size_t)(7 * a + r) * n + 7 * b + c] -= sa[r] * A[q] * sb[c];
+      *eg_entry(d, a, r, b, c) -= sa[r] * A[q] * sb[c];
     }
     __syncwarp();
   }

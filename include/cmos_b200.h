@@ -590,6 +590,11 @@ int cmos_ba_debug_pose_trace(cmos_ba_t h, int32_t frame, double* trace, int32_t 
  * of 6, <= 228) with exactly the device routines the BA kernels use.  failed = 1 if a pivot was not positive.  cycles2
  * (optional, 2 entries): SM cycles of the factorisation and of the back substitution. */
 int cmos_debug_solve_spd(const double* A, const double* b, int32_t n, double* x, int32_t* failed, int64_t* cycles2);
+/* How the last cmos_ba_optimize_essential_graph call solved its normal equations (what Ceres' SPARSE_NORMAL_CHOLESKY does
+ * with CHOLMOD, src/CeresOptimizer.cc:897-901): info6 = {1 if nested dissection over a band + border structure was used
+ * (0: blocked Cholesky inside the row envelope), keyframes per node, unknowns per node, nodes, border keyframes, border
+ * unknowns (padded)}. */
+int cmos_ba_debug_essential_graph_plan(cmos_ba_t h, int32_t* info6);
 /* Kernels launched by the last cmos_ba_run_* / cmos_ba_pose_optimization call. */
 int cmos_ba_last_launch_count(cmos_ba_t h, int32_t* n);
 /* Device time of the solves (CUDA events on the launching stream), as cmos_orb_set_profiling. */

@@ -281,7 +281,9 @@ def test_essential_graph_per_panel_back_substitution(monkeypatch):
     a = (G["Scw"], G["kf_flags"], G["Snc"], G["edge_j"], G["edge_i"], G["edge_kind"], G["Xw"], G["ref_kf"])
     ref = po.essential_graph(*a)
     opt = CeresOptimizer(max_cams=2, max_points=8, max_obs=8)
+    monkeypatch.setenv("CMOS_EG_BLOCKED", "1")           # (the nested-dissection solve has no panels)
     one = opt.OptimizeEssentialGraph(*a)
+    assert opt.essential_graph_plan()["nested_dissection"] == 0
     monkeypatch.setenv("CMOS_BA_PANEL_BACKSOLVE", "1")
     per = opt.OptimizeEssentialGraph(*a)
     monkeypatch.delenv("CMOS_BA_PANEL_BACKSOLVE")
@@ -289,6 +291,61 @@ def test_essential_graph_per_panel_back_substitution(monkeypatch):
         assert got["summary"]["iterations"] == ref["iterations"]
         assert np.abs(got["lie"] - ref["lie"]).max() <= 1e-7 * max(1.0, np.abs(ref["lie"]).max())       # relative, as above
     assert np.abs(one["lie"] - per["lie"]).max() <= 1e-7 * max(1.0, np.abs(ref["lie"]).max())          # different summation orders on a loop-closure graph (translations ~20)
+    opt.close()
+
+
+def _eg_args(G):
+    return (G["Scw"], G["kf_flags"], G["Snc"], G["edge_j"], G["edge_i"], G["edge_kind"], G["Xw"], G["ref_kf"])
+
+
+@pytest.mark.parametrize("case", ["loop", "wide_band", "no_loop", "two_nodes", "many_long_edges"])
+def test_essential_graph_nested_dissection_equals_blocked(monkeypatch, case):
+    """The band + border nested-dissection solve of the pose graph's normal equations (band_cr.cuh: keyframes with long-range
+    edges form the border) against the blocked Cholesky of the same system: same LM trajectory, logs within 1e-9 relative;
+    both against the oracle.  Graph shapes: a loop closure (border = the loop cluster), a wide co-visibility band (nodes of
+    120 unknowns), loop edges to the constant keyframe only (no border), a graph of two nodes, and one whose long edges do not fit a border
+    (the plan must decline and the blocked path must take it)."""
+    rng = np.random.default_rng(5)
+    if case == "loop":
+        G = synth.make_essential_graph_problem(150, seed=21, n_group=10, covis=(2, 3, 5), n_points=50)
+    elif case == "wide_band":
+        G = synth.make_essential_graph_problem(90, seed=22, n_group=4, covis=(2, 5, 9, 14), n_points=0)
+    elif case == "no_loop":
+        G = synth.make_essential_graph_problem(80, seed=23, n_group=3, covis=(2, 3), n_points=0)
+        L = G["loop_kf"]       # keep only the loop edges that end in the CONSTANT loop keyframe: constraints, but no off-diagonal block
+        keep = (G["edge_kind"] != 0) | (G["edge_j"] == L) | (G["edge_i"] == L)
+        for k in ("edge_j", "edge_i", "edge_kind"):
+            G[k] = G[k][keep]
+    elif case == "two_nodes":
+        G = synth.make_essential_graph_problem(9, seed=24, n_group=1, covis=(2,), n_points=0)
+    else:
+        G = synth.make_essential_graph_problem(120, seed=25, n_group=3, covis=(2, 3), n_points=0)
+        j = rng.integers(0, 50, 60).astype(np.int32); i = rng.integers(70, 120, 60).astype(np.int32)     # 60 random long edges
+        G["edge_j"] = np.concatenate([G["edge_j"], j]); G["edge_i"] = np.concatenate([G["edge_i"], i])
+        G["edge_kind"] = np.concatenate([G["edge_kind"], np.ones(60, np.uint8)])
+    a = _eg_args(G)
+    ref = po.essential_graph(*a)
+    opt = CeresOptimizer(max_cams=2, max_points=8, max_obs=8)
+    nd = opt.OptimizeEssentialGraph(*a)
+    plan = opt.essential_graph_plan()
+    monkeypatch.setenv("CMOS_EG_BLOCKED", "1")
+    bl = opt.OptimizeEssentialGraph(*a)
+    assert opt.essential_graph_plan()["nested_dissection"] == 0
+    monkeypatch.delenv("CMOS_EG_BLOCKED")
+    if case == "many_long_edges":
+        assert plan["nested_dissection"] == 0
+    else:
+        assert plan["nested_dissection"] == 1, plan
+        assert (plan["border_keyframes"] == 0) == (case == "no_loop"), plan
+        if case == "wide_band":
+            assert plan["node_unknowns"] == 120, plan
+    scale = max(1.0, np.abs(ref["lie"]).max())
+    for got in (nd, bl):
+        s = got["summary"]
+        assert (s["iterations"], s["successful_steps"], s["termination"]) == (ref["iterations"], ref["successful_steps"], ref["termination"])
+        assert np.abs(got["lie"] - ref["lie"]).max() <= 1e-7 * scale
+    assert np.abs(nd["lie"] - bl["lie"]).max() <= 1e-9 * scale
+    assert abs(nd["summary"]["final_cost"] - bl["summary"]["final_cost"]) <= 1e-9 * max(bl["summary"]["final_cost"], 1e-12) + 1e-15
     opt.close()
 
 
