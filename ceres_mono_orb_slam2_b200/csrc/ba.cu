@@ -2385,6 +2385,14 @@ struct cmos_ba {
   double* d_HG = nullptr;          // [Kv][21] H_cc then [Kv][6] g_c, contiguous (one all-reduce)
   double* d_Sblk = nullptr;        // [n_blocks][36] then rhs [nc], contiguous (one all-reduce)
   cudaStream_t stream = nullptr;
+  // set_problem staging: every array of a problem is packed into ONE page-locked buffer, uploaded with one copy and dealt
+  // to its device array by one kernel (it was ~25 pageable copies of ~15 us each: a third of a LocalBundleAdjustment call)
+  uint8_t *h_stage = nullptr, *d_stage = nullptr;
+  size_t cap_stage = 0;
+  // topology of the last problem (keyframe flags + observation index arrays): an identical one skips the structure build
+  std::vector<uint8_t> topo_flags;
+  std::vector<int> topo_obs_cam, topo_obs_pt, topo_perm;
+  bool topo_valid = false;
   // capacities
   size_t cap_pairs = 0, cap_blocks = 0, cap_S = 0;
   // device storage
@@ -2709,6 +2717,8 @@ int cmos_ba_destroy(cmos_ba_t h) {
   for (void* b : {(void*)h->ds_obs, (void*)h->ds_sig, (void*)h->ds_pts, (void*)h->ds_out, (void*)h->ds_bad})
     if (b) cudaFree(b);
   h->eg.release();
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->d_stage) cudaFree(h->d_stage);
   if (h->stop_registered_by_us && h->stop_host_page) cudaHostUnregister((void*)h->stop_host_page);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -2772,6 +2782,88 @@ int cmos_ba_debug_pose_trace(cmos_ba_t h, int32_t frame, double* trace, int32_t 
   return CMOS_OK;
 }
 
+}  // extern "C"
+
+namespace {
+constexpr int kStageMax = 28;
+struct StageTable { void* dst[kStageMax]; size_t off[kStageMax]; size_t bytes[kStageMax]; int n; };
+// one launch deals the packed upload to its destination arrays (offsets are 16-byte aligned, sizes multiples of 4 except
+// the keyframe flags)
+// (to_stage != 0: the other direction — results gathered into the packed buffer for one download)
+__global__ void __launch_bounds__(256) k_stage_scatter(StageTable t, uint8_t* __restrict__ stage, int to_stage) {
+  const size_t gt = (size_t)blockIdx.x * 256 + threadIdx.x, gs = (size_t)gridDim.x * 256;
+  for (int e = 0; e < t.n; e++) {
+    const uint8_t* s8 = to_stage ? (const uint8_t*)t.dst[e] : stage + t.off[e];
+    uint8_t* d8 = to_stage ? stage + t.off[e] : (uint8_t*)t.dst[e];
+    const size_t words = t.bytes[e] >> 2;
+    if ((((uintptr_t)d8 | (uintptr_t)s8) & 3) == 0) {
+      for (size_t i = gt; i < words; i += gs) ((uint32_t*)d8)[i] = ((const uint32_t*)s8)[i];
+      for (size_t i = 4 * words + gt; i < t.bytes[e]; i += gs) d8[i] = s8[i];
+    } else {
+      for (size_t i = gt; i < t.bytes[e]; i += gs) d8[i] = s8[i];
+    }
+  }
+}
+struct Stager {
+  cmos_ba* h;
+  StageTable t{};
+  size_t used = 0;
+  const void* srcs[kStageMax];
+  explicit Stager(cmos_ba* hh) : h(hh) { t.n = 0; }
+  void add(void* dst, const void* src, size_t bytes) {
+    if (!bytes) return;
+    t.dst[t.n] = dst; t.off[t.n] = used; t.bytes[t.n] = bytes; srcs[t.n] = src; t.n++;
+    used += (bytes + 15) & ~(size_t)15;
+  }
+  // copies the sources into the page-locked buffer, enqueues the upload and the scatter; host sources may die afterwards
+  int flush(cudaStream_t st) {
+    if (!t.n) return CMOS_OK;
+    if (used > h->cap_stage) {
+      CMOS_CUDA_OK(cudaStreamSynchronize(st));
+      if (h->h_stage) cudaFreeHost(h->h_stage);
+      if (h->d_stage) cudaFree(h->d_stage);
+      h->h_stage = h->d_stage = nullptr; h->cap_stage = 0;
+      const size_t want = used + used / 4 + 4096;
+      CMOS_CUDA_OK(cudaMallocHost((void**)&h->h_stage, want));
+      CMOS_CUDA_OK(cudaMalloc((void**)&h->d_stage, want));
+      h->cap_stage = want;
+    } else {
+      CMOS_CUDA_OK(cudaStreamSynchronize(st));      // the previous upload may still be reading the buffer
+    }
+    for (int e = 0; e < t.n; e++) std::memcpy(h->h_stage + t.off[e], srcs[e], t.bytes[e]);
+    CMOS_CUDA_OK(cudaMemcpyAsync(h->d_stage, h->h_stage, used, cudaMemcpyHostToDevice, st));
+    const int grid = (int)std::min<size_t>(296, (used / 4 + 255) / 256 + 1);
+    k_stage_scatter<<<grid, 256, 0, st>>>(t, h->d_stage, 0);
+    CMOS_CUDA_OK(cudaGetLastError());
+    return CMOS_OK;
+  }
+  // the other direction: add(device array, host destination, bytes) ..., then download() gathers, copies once, and
+  // hands every piece to its host destination (synchronises the stream)
+  int download(cudaStream_t st) {
+    if (!t.n) return CMOS_OK;
+    if (used > h->cap_stage) {
+      CMOS_CUDA_OK(cudaStreamSynchronize(st));
+      if (h->h_stage) cudaFreeHost(h->h_stage);
+      if (h->d_stage) cudaFree(h->d_stage);
+      h->h_stage = h->d_stage = nullptr; h->cap_stage = 0;
+      const size_t want = used + used / 4 + 4096;
+      CMOS_CUDA_OK(cudaMallocHost((void**)&h->h_stage, want));
+      CMOS_CUDA_OK(cudaMalloc((void**)&h->d_stage, want));
+      h->cap_stage = want;
+    }
+    const int grid = (int)std::min<size_t>(296, (used / 4 + 255) / 256 + 1);
+    k_stage_scatter<<<grid, 256, 0, st>>>(t, h->d_stage, 1);
+    CMOS_CUDA_OK(cudaGetLastError());
+    CMOS_CUDA_OK(cudaMemcpyAsync(h->h_stage, h->d_stage, used, cudaMemcpyDeviceToHost, st));
+    CMOS_CUDA_OK(cudaStreamSynchronize(st));
+    for (int e = 0; e < t.n; e++) std::memcpy(const_cast<void*>(srcs[e]), h->h_stage + t.off[e], t.bytes[e]);
+    return CMOS_OK;
+  }
+};
+}  // namespace
+
+extern "C" {
+
 int cmos_debug_solve_spd(const double* A, const double* b, int32_t n, double* x, int32_t* failed, int64_t* cycles2) {
   CMOS_REQUIRE(A && b && x && failed && n >= 6 && n % 6 == 0 && n <= kSmallMaxN, "bad argument (n a multiple of 6, <= %d)", kSmallMaxN);
   double *dA = nullptr, *db = nullptr, *dx = nullptr; int* df = nullptr; long long* dc = nullptr;
@@ -2802,7 +2894,30 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
                n_cams, n_points, n_obs, h->p.max_cams, h->p.max_points, h->p.max_obs);
   CMOS_CUDA_OK(cudaSetDevice(h->p.device));
   const int K = n_cams, M = n_points, N = n_obs;
+  // ---- same topology as the last problem (keyframe flags and observation index arrays): new values only ----
+  // (not for sharded solves: the structure build contains a collective, every rank must take the same path)
+  if (h->topo_valid && h->n_ranks == 1 && h->has_problem && h->d.K == K && h->d.M == M && h->d.N == N &&
+      std::memcmp(h->topo_flags.data(), cam_flags, K) == 0 &&
+      std::memcmp(h->topo_obs_cam.data(), obs_cam, (size_t)N * sizeof(int)) == 0 &&
+      std::memcmp(h->topo_obs_pt.data(), obs_pt, (size_t)N * sizeof(int)) == 0 && !std::getenv("CMOS_BA_NO_TOPO_CACHE")) {
+    std::vector<float2> o_uv(N);
+    std::vector<float> o_w(N);
+    for (int p = 0; p < N; p++) { const int i = h->topo_perm[p]; o_uv[p] = make_float2(uv[2 * i], uv[2 * i + 1]); o_w[p] = inv_sigma2[i]; }
+    Stager sg(h);
+    sg.add(h->d_cams0, cams, 7 * (size_t)K * sizeof(double));
+    sg.add(h->d_pts0, points, 3 * (size_t)M * sizeof(double));
+    sg.add(h->d_o_uv, o_uv.data(), (size_t)N * sizeof(float2));
+    sg.add(h->d_o_w, o_w.data(), (size_t)N * sizeof(float));
+    int rc = sg.flush(h->stream);
+    if (rc) return rc;
+    BaDev& d = h->d;
+    d.fx = (double)K4[0]; d.fy = (double)K4[1]; d.cx = (double)K4[2]; d.cy = (double)K4[3];
+    d.trace = nullptr; d.stop_flag = nullptr;
+    h->ran = false;
+    return CMOS_OK;
+  }
   // ---- structure (host, counting sorts only) ----
+  h->topo_valid = false;             // (stays false if this call fails half way)
   std::vector<int> cam_var(K, -1);
   int Kv = 0;
   for (int k = 0; k < K; k++)
@@ -2970,31 +3085,29 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
         }
       }
   }
-  // ---- upload ----
+  // ---- upload: one page-locked buffer, one copy, one scatter kernel ----
   cudaStream_t st = h->stream;
-  auto up = [&](void* dst, const void* src, size_t bytes) {
-    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
-  };
   BaDev& d = h->d;
-  CMOS_CUDA_OK(up(h->d_cams0, cams, 7 * (size_t)K * sizeof(double)));
-  CMOS_CUDA_OK(up(h->d_pts0, points, 3 * (size_t)M * sizeof(double)));
-  CMOS_CUDA_OK(up(h->d_cam_var, cam_var.data(), K * sizeof(int)));
-  CMOS_CUDA_OK(up(h->d_var_cam, var_cam.data(), var_cam.size() * sizeof(int)));
-  CMOS_CUDA_OK(up(h->d_cam_flags, cam_flags, K));
-  CMOS_CUDA_OK(up(h->d_o_cam, o_cam.data(), N * sizeof(int)));
-  CMOS_CUDA_OK(up(h->d_o_cv, o_cv.data(), N * sizeof(int)));
-  CMOS_CUDA_OK(up(h->d_o_pt, o_pt.data(), N * sizeof(int)));
-  CMOS_CUDA_OK(up(h->d_o_uv, o_uv.data(), N * sizeof(float2)));
-  CMOS_CUDA_OK(up(h->d_o_w, o_w.data(), N * sizeof(float)));
-  CMOS_CUDA_OK(up(h->d_perm, perm.data(), N * sizeof(int)));
-  CMOS_CUDA_OK(up(h->d_pt_start, pt_start.data(), (M + 1) * sizeof(int)));
-  CMOS_CUDA_OK(up(h->d_cam_start, cam_start.data(), (Kv + 1) * sizeof(int)));
-  CMOS_CUDA_OK(up(h->d_cam_obs, cam_obs.data(), cam_obs.size() * sizeof(int)));
-  CMOS_CUDA_OK(up(h->d_blk_a, blk_a.data(), nb * sizeof(int)));
-  CMOS_CUDA_OK(up(h->d_blk_b, blk_b.data(), nb * sizeof(int)));
-  CMOS_CUDA_OK(up(h->d_blk_start, blk_start.data(), (nb + 1) * sizeof(int)));
-  CMOS_CUDA_OK(up(h->d_pair_a, pair_a.data(), pair_a.size() * sizeof(int)));
-  CMOS_CUDA_OK(up(h->d_pair_b, pair_b.data(), pair_b.size() * sizeof(int)));
+  Stager sg(h);
+  sg.add(h->d_cams0, cams, 7 * (size_t)K * sizeof(double));
+  sg.add(h->d_pts0, points, 3 * (size_t)M * sizeof(double));
+  sg.add(h->d_cam_var, cam_var.data(), K * sizeof(int));
+  sg.add(h->d_var_cam, var_cam.data(), var_cam.size() * sizeof(int));
+  sg.add(h->d_cam_flags, cam_flags, K);
+  sg.add(h->d_o_cam, o_cam.data(), N * sizeof(int));
+  sg.add(h->d_o_cv, o_cv.data(), N * sizeof(int));
+  sg.add(h->d_o_pt, o_pt.data(), N * sizeof(int));
+  sg.add(h->d_o_uv, o_uv.data(), N * sizeof(float2));
+  sg.add(h->d_o_w, o_w.data(), N * sizeof(float));
+  sg.add(h->d_perm, perm.data(), N * sizeof(int));
+  sg.add(h->d_pt_start, pt_start.data(), (M + 1) * sizeof(int));
+  sg.add(h->d_cam_start, cam_start.data(), (Kv + 1) * sizeof(int));
+  sg.add(h->d_cam_obs, cam_obs.data(), cam_obs.size() * sizeof(int));
+  sg.add(h->d_blk_a, blk_a.data(), nb * sizeof(int));
+  sg.add(h->d_blk_b, blk_b.data(), nb * sizeof(int));
+  sg.add(h->d_blk_start, blk_start.data(), (nb + 1) * sizeof(int));
+  sg.add(h->d_pair_a, pair_a.data(), pair_a.size() * sizeof(int));
+  sg.add(h->d_pair_b, pair_b.data(), pair_b.size() * sizeof(int));
   d.K = K; d.Kv = Kv; d.M = M; d.N = N; d.n_blocks = nb; d.nc = 6 * Kv;
   d.fx = (double)K4[0]; d.fy = (double)K4[1]; d.cx = (double)K4[2]; d.cy = (double)K4[3];
   d.cam_var = h->d_cam_var; d.o_cam = h->d_o_cam; d.o_cv = h->d_o_cv; d.o_pt = h->d_o_pt; d.o_uv = h->d_o_uv;
@@ -3030,10 +3143,13 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
                    alloc(&h->d_schur_part, wc * kSchurPart), "cannot allocate the Schur chunk lists (%zu chunks)", nch);
       h->cap_chunks = wc; h->cap_chunk_blocks = wb;
     }
-    CMOS_CUDA_OK(up(h->d_chunk_start, chunk_start.data(), chunk_start.size() * sizeof(int)));
-    if (nch) CMOS_CUDA_OK(up(h->d_chunk_blk, chunk_blk.data(), nch * sizeof(int)));
-    CMOS_CUDA_OK(up(h->d_blk_chunk0, blk_chunk0.data(), blk_chunk0.size() * sizeof(int)));
-    CMOS_CUDA_OK(cudaStreamSynchronize(st));          // the host vectors above go out of scope
+    sg.add(h->d_chunk_start, chunk_start.data(), chunk_start.size() * sizeof(int));
+    if (nch) sg.add(h->d_chunk_blk, chunk_blk.data(), nch * sizeof(int));
+    sg.add(h->d_blk_chunk0, blk_chunk0.data(), blk_chunk0.size() * sizeof(int));
+    {
+      const int rc = sg.flush(st);                   // copies every source into the page-locked buffer: the host vectors may die
+      if (rc) return rc;
+    }
     d.chunk_start = h->d_chunk_start; d.chunk_blk = h->d_chunk_blk; d.blk_chunk0 = h->d_blk_chunk0;
     d.schur_part = h->d_schur_part; d.n_chunks = (int)nch;
   }
@@ -3048,7 +3164,11 @@ int cmos_ba_set_problem(cmos_ba_t h, int32_t n_cams, const double* cams, const u
   d.trace = nullptr; d.stop_flag = nullptr;
   CMOS_CUDA_OK(cudaMemsetAsync(d.part, 0, (size_t)o * sizeof(double), st));
   CMOS_CUDA_OK(cudaMemsetAsync(d.red, 0, 8 * sizeof(double), st));
-  CMOS_CUDA_OK(cudaStreamSynchronize(st));   // the host vectors die here
+  h->topo_flags.assign(cam_flags, cam_flags + K);
+  h->topo_obs_cam.assign(obs_cam, obs_cam + N);
+  h->topo_obs_pt.assign(obs_pt, obs_pt + N);
+  h->topo_perm = perm;
+  h->topo_valid = true;
   h->has_problem = true;
   h->ran = false;
   return CMOS_OK;
@@ -3124,11 +3244,19 @@ int cmos_ba_get_results(cmos_ba_t h, double* cams, double* points, uint8_t* eras
   CMOS_CUDA_OK(cudaSetDevice(h->p.device));
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   const BaDev& d = h->d;
-  if (cams) CMOS_CUDA_OK(cudaMemcpyAsync(cams, h->d_cams_out, 7 * (size_t)d.K * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (points) CMOS_CUDA_OK(cudaMemcpyAsync(points, h->d_pts_out, 3 * (size_t)d.M * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (erase) CMOS_CUDA_OK(cudaMemcpyAsync(erase, h->d_erase, d.N, cudaMemcpyDeviceToHost, st));
-  if (summaries) CMOS_CUDA_OK(cudaMemcpyAsync(summaries, h->d_summaries, 2 * sizeof(cmos_ba_summary), cudaMemcpyDeviceToHost, st));
-  CMOS_CUDA_OK(cudaStreamSynchronize(st));
+  {
+    // one gather kernel + one copy into the page-locked buffer instead of four pageable downloads.  The staging buffer is
+    // shared with set_problem's upload on the handle's own stream: wait for that stream first when another one is used.
+    if (st != h->stream) CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    Stager sg(h);
+    if (cams) sg.add(h->d_cams_out, cams, 7 * (size_t)d.K * sizeof(double));
+    if (points) sg.add(h->d_pts_out, points, 3 * (size_t)d.M * sizeof(double));
+    if (erase) sg.add(h->d_erase, erase, d.N);
+    if (summaries) sg.add(h->d_summaries, summaries, 2 * sizeof(cmos_ba_summary));
+    const int rc = sg.download(st);
+    if (rc) return rc;
+    CMOS_CUDA_OK(cudaStreamSynchronize(st));
+  }
   // The caller's stop-flag page is page-locked only while a solve can read it: a stale registration would make later
   // copies from unrelated heap memory that shares the page fail ("invalid argument": a partly pinned source range).
   if (h->stop_registered_by_us && h->stop_host_page) {

@@ -83,6 +83,32 @@ def test_local_bundle_adjustment_matches_oracle(cfg):
     assert np.array_equal(cams[flags & 1 == 1], G["poses"][flags & 1 == 1])
 
 
+def test_set_problem_topology_cache(monkeypatch):
+    """A second problem with the SAME keyframe flags and observation index arrays skips the structure build and uploads
+    values only (cmos_ba_set_problem): its result must be bit-identical to a handle that builds everything, and a changed
+    topology must rebuild."""
+    K4 = np.array(synth.KITTI_K, np.float32)
+    G1 = synth.make_ba_problem(12, 800, 4, seed=31)
+    rng = np.random.default_rng(1)
+    G2 = dict(G1)
+    G2["uv"] = (G1["uv"] + rng.normal(0, 0.3, G1["uv"].shape)).astype(np.float32)
+    G2["points"] = G1["points"] + rng.normal(0, 0.01, G1["points"].shape)
+    G2["poses"] = G1["poses"].copy(); G2["poses"][3:, :3] += rng.normal(0, 0.005, (len(G1["poses"]) - 3, 3))
+    G3 = synth.make_ba_problem(12, 800, 4, seed=32)          # other topology, same sizes
+    args = lambda G: (G["poses"], G["fixed"], G["points"], G["obs_cam"], G["obs_pt"], G["uv"], G["inv_sigma2"], K4)
+    n_obs = max(len(G1["obs_cam"]), len(G3["obs_cam"]))
+    a = CeresOptimizer(max_cams=12, max_points=800, max_obs=n_obs)
+    got = [a.LocalBundleAdjustment(*args(G)) for G in (G1, G2, G3, G3, G1)]
+    monkeypatch.setenv("CMOS_BA_NO_TOPO_CACHE", "1")
+    b = CeresOptimizer(max_cams=12, max_points=800, max_obs=n_obs)
+    ref = [b.LocalBundleAdjustment(*args(G)) for G in (G1, G2, G3, G3, G1)]
+    for (c1, p1, e1, s1), (c2, p2, e2, s2) in zip(got, ref):
+        assert np.array_equal(c1, c2) and np.array_equal(p1, p2) and np.array_equal(e1, e2)
+        assert [x["iterations"] for x in s1] == [x["iterations"] for x in s2]
+    assert not np.array_equal(got[0][0], got[1][0])           # the new values did arrive
+    a.close(); b.close()
+
+
 def test_global_bundle_adjustment_small_and_blocked_paths_match_oracle():
     K4 = np.array(synth.KITTI_K, np.float32)
     for n_cams, n_points, window in [(12, 400, None), (60, 2500, 6)]:      # 66 and 354 unknown pose dofs
