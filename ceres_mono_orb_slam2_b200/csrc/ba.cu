@@ -948,14 +948,10 @@ __global__ void __launch_bounds__(32 * kSchurWarps, CMOS_SCHUR_MINB) k_schur_chu
 }
 
 // thread per (block, entry): sums the block's chunk partials in chunk order, adds H_cc + D_c^2 / g_c on the diagonal
-__global__ void __launch_bounds__(256) k_schur_combine(BaDev d) {
-  const LmState& st = *d.st;
-  if (st.done) return;
-  const int t = blockIdx.x * 256 + threadIdx.x;
-  const int blk = t / 48, idx = t - 48 * blk;
-  if (blk >= d.n_blocks || idx >= kSchurPart) return;
-  const int a = d.blk_a[blk], b = d.blk_b[blk];
-  if (idx >= 36 && a != b) return;
+// entry idx of reduced-system block blk = (a, b): idx < 36 the block's entry (r, c) = (idx / 6, idx % 6), 36..41 the rhs of
+// keyframe a (diagonal blocks only): the block's chunks summed in chunk order, plus the keyframe-only terms
+__device__ __forceinline__ double schur_combined(const BaDev& d, const LmState& st, const int blk, const int idx, const int a,
+                                                 const int b) {
   double sum = 0.0;
   for (int c = d.blk_chunk0[blk]; c < d.blk_chunk0[blk + 1]; c++) sum += d.schur_part[(size_t)c * kSchurPart + idx];
   if (idx < 36) {
@@ -968,11 +964,23 @@ __global__ void __launch_bounds__(256) k_schur_combine(BaDev d) {
       v += h;
       if (r == c) v += fmin(fmax(h, kMinLmDiag), kMaxLmDiag) / st.radius;
     }
-    d.Sblk[(size_t)blk * 36 + idx] = v;
-  } else {
-    const int k = idx - 36;
-    d.rhs[6 * a + k] = (d.is_root ? d.scale_c[6 * (size_t)a + k] * d.gc[6 * (size_t)a + k] : 0.0) - sum;
+    return v;
   }
+  const int k = idx - 36;
+  return (d.is_root ? d.scale_c[6 * (size_t)a + k] * d.gc[6 * (size_t)a + k] : 0.0) - sum;
+}
+
+__global__ void __launch_bounds__(256) k_schur_combine(BaDev d) {
+  const LmState& st = *d.st;
+  if (st.done) return;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int blk = t / 48, idx = t - 48 * blk;
+  if (blk >= d.n_blocks || idx >= kSchurPart) return;
+  const int a = d.blk_a[blk], b = d.blk_b[blk];
+  if (idx >= 36 && a != b) return;
+  const double v = schur_combined(d, st, blk, idx, a, b);
+  if (idx < 36) d.Sblk[(size_t)blk * 36 + idx] = v;
+  else d.rhs[6 * a + idx - 36] = v;
 }
 
 // candidate keyframe poses from the solved reduced system + the keyframes' share of the step statistics
@@ -1397,13 +1405,15 @@ __device__ __forceinline__ void invert_diag24(double* __restrict__ L, double* __
 // s_x: 24 doubles of shared scratch.  All threads of the CTA (blockDim.x >= n, a multiple of 32).  Every dot product is
 // split over 4 (or 2) adjacent lanes when the CTA has the threads for it — the 24 dependent load + FMA pairs of one thread
 // were the whole cost of a step (8.4 k cycles at n = 120) — and added by shuffles in a fixed order.
-__device__ __forceinline__ void back_substitute24(const double* __restrict__ L, double* __restrict__ y, double* __restrict__ s_x,
-                                                  const int n) {
+// (kBlk = 8: the same against the 8 x 8 inverted diagonal tiles packed_cholesky_reg leaves — no 24-block inversion needed.)
+template <int kBlk>
+__device__ __forceinline__ void back_substitute_blocks(const double* __restrict__ L, double* __restrict__ y, double* __restrict__ s_x,
+                                                       const int n) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lpu = 4 * n <= nt ? 4 : (2 * n <= nt ? 2 : 1);      // lanes per unknown
   const int u = tid / lpu, sub = tid - u * lpu;
-  for (int r0 = ((n - 1) / 24) * 24; r0 >= 0; r0 -= 24) {
-    const int bs = min(24, n - r0);
+  for (int r0 = ((n - 1) / kBlk) * kBlk; r0 >= 0; r0 -= kBlk) {
+    const int bs = min(kBlk, n - r0);
     {
       double v = 0.0;
       if (u < bs)
@@ -1426,6 +1436,11 @@ __device__ __forceinline__ void back_substitute24(const double* __restrict__ L, 
     }
     __syncthreads();
   }
+}
+
+__device__ __forceinline__ void back_substitute24(const double* __restrict__ L, double* __restrict__ y, double* __restrict__ s_x,
+                                                  const int n) {
+  back_substitute_blocks<24>(L, y, s_x, n);
 }
 
 }  // namespace cmos
@@ -1466,6 +1481,17 @@ __device__ __forceinline__ void factor_and_invert24(double* __restrict__ L, doub
   if (!*s_fail) invert_diag24(L, P, n);
 }
 
+// The whole solve L L' x = rhs (k_solve_small, the border system of the bordered nested dissection).  y = row n of L becomes
+// x.  s_x: 24 doubles of shared scratch.  Substituting against the 8 x 8 inverted tiles directly (back_substitute_blocks<8>,
+// no 24-block inversion) was measured and is slower: 15 steps of two barrier-separated phases cost 16.7 k cycles at n = 120,
+// the 24-block inversion + 5 steps 12 k.
+__device__ __forceinline__ void factor_and_solve(double* __restrict__ L, double* __restrict__ P, const int n, int* s_fail,
+                                                 double* __restrict__ s_x) {
+  factor_and_invert24(L, P, n, s_fail);
+  __syncthreads();
+  if (!*s_fail) back_substitute24(L, L + n * (n + 1) / 2, s_x, n);
+}
+
 __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
   extern __shared__ __align__(16) double smem_d[];
   LmState& st = *d.st;
@@ -1495,15 +1521,12 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
 #else
 #define TK(i)
 #endif
-  factor_and_invert24(L, P, n, &s_fail);
+  __shared__ double s_x24[24];
+  factor_and_solve(L, P, n, &s_fail, s_x24);
   TK(4)
   __syncthreads();
-  // back substitution L' x = y in 24-row block steps by the whole CTA (it was one warp walking 6-row blocks: 19 k of the
-  // 88 k cycles of this kernel)
   {
-    __shared__ double s_x24[24];
-    double* y = L + n * (n + 1) / 2;      // forward-substituted rhs
-    if (!s_fail) back_substitute24(L, y, s_x24, n);
+    double* y = L + n * (n + 1) / 2;      // forward-substituted rhs, now the solution
     if (warp == 0) {
       int bad = 0;
       for (int k = lane; k < n; k += 32) {
@@ -1530,7 +1553,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
 // Test tap of the small dense solver (cmos_debug_solve_spd): A x = b through exactly the device code k_solve_small and
 // k_cr_factor run — factor_and_invert24 + back_substitute24 — on a caller-supplied SPD matrix.
 __global__ void __launch_bounds__(kSolveThreads) k_debug_solve_spd(const double* __restrict__ A, const double* __restrict__ b, int n,
-                                                                   double* __restrict__ x, int* fail, long long* cycles) {
+                                                                   double* __restrict__ x, int* fail, long long* cycles, int whole) {
   extern __shared__ __align__(16) double smem_d[];
   const int tid = threadIdx.x;
   double* L = smem_d;
@@ -1545,11 +1568,17 @@ __global__ void __launch_bounds__(kSolveThreads) k_debug_solve_spd(const double*
   for (int k = tid; k < n; k += kSolveThreads) L[n * (n + 1) / 2 + k] = b[k];
   __syncthreads();
   const long long t0 = clock64();
-  factor_and_invert24(L, P, n, &s_fail);
-  __syncthreads();
-  const long long t1 = clock64();
   double* y = L + n * (n + 1) / 2;
-  if (!s_fail) back_substitute24(L, y, s_x24, n);
+  long long t1;
+  if (whole) {                           // the path of k_solve_small / k_crb_solve
+    factor_and_solve(L, P, n, &s_fail, s_x24);
+    t1 = clock64();
+  } else {                               // the path of k_cr_factor + k_cr_back (24-block format)
+    factor_and_invert24(L, P, n, &s_fail);
+    __syncthreads();
+    t1 = clock64();
+    if (!s_fail) back_substitute24(L, y, s_x24, n);
+  }
   __syncthreads();
   const long long t2 = clock64();
   for (int k = tid; k < n; k += kSolveThreads) x[k] = s_fail ? 0.0 : y[k];
@@ -2389,6 +2418,7 @@ struct cmos_ba {
   // to its device array by one kernel (it was ~25 pageable copies of ~15 us each: a third of a LocalBundleAdjustment call)
   uint8_t *h_stage = nullptr, *d_stage = nullptr;
   size_t cap_stage = 0;
+  size_t pose_stage[5] = {0, 0, 0, 0, 0};      // offsets of the pose-optimisation call's packed layout
   // topology of the last problem (keyframe flags + observation index arrays): an identical one skips the structure build
   std::vector<uint8_t> topo_flags;
   std::vector<int> topo_obs_cam, topo_obs_pt, topo_perm;
@@ -2541,6 +2571,8 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
     if (d.Kv > 0) {
       if (h->schur_chunked) {
         k_schur_chunks<<<(d.n_chunks + kSchurWarps - 1) / kSchurWarps, 32 * kSchurWarps, 0, st>>>(d);
+        // (summing the chunks inside k_solve_small instead — one launch less — was measured: one CTA walks 8 k entries x ~5
+        // dependent global loads, +13 us per iteration; the 190-CTA kernel takes 7)
         k_schur_combine<<<(d.n_blocks * 48 + 255) / 256, 256, 0, st>>>(d);
         h->launches += 2;
       } else {
@@ -2749,13 +2781,35 @@ int cmos_ba_pose_optimization(cmos_ba_t h, int32_t n_frames, double* pose7, cons
     CMOS_REQUIRE(n_frames <= h->p.max_pose_batch && stride <= h->p.max_pose_corr,
                  "batch %d x %d exceeds the handle's pose capacity %d x %d", n_frames, stride, h->p.max_pose_batch,
                  h->p.max_pose_corr);
-    CMOS_CUDA_OK(cudaMemcpyAsync(h->dp_pose, pose7, 7 * B * sizeof(double), cudaMemcpyHostToDevice, st));
-    CMOS_CUDA_OK(cudaMemcpyAsync(h->dp_n, n_corr, B * sizeof(int), cudaMemcpyHostToDevice, st));
-    CMOS_CUDA_OK(cudaMemcpyAsync(h->dp_xw, xw, 3 * BC * sizeof(double), cudaMemcpyHostToDevice, st));
-    CMOS_CUDA_OK(cudaMemcpyAsync(h->dp_uv, uv, 2 * BC * sizeof(float), cudaMemcpyHostToDevice, st));
-    CMOS_CUDA_OK(cudaMemcpyAsync(h->dp_w, inv_sigma2, BC * sizeof(float), cudaMemcpyHostToDevice, st));
-    a.pose7 = h->dp_pose; a.n_corr = h->dp_n; a.xw = h->dp_xw; a.uv = h->dp_uv; a.inv_sigma2 = h->dp_w;
-    a.is_outlier = h->dp_out; a.n_inliers = h->dp_inl; a.summaries = h->dp_sum; a.trace = h->dp_trace;
+    // One page-locked buffer, laid out [xw | uv | w | n | pose | summaries | inliers | outlier flags]: ONE upload of
+    // xw..pose, the kernel works in place, ONE download of pose..flags (it was five pageable copies in and four out:
+    // 0.13 ms around a 0.06 ms solve, per tracked frame).
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t o_xw = 0, o_uv = o_xw + al(3 * BC * sizeof(double)), o_w = o_uv + al(2 * BC * sizeof(float)),
+                 o_n = o_w + al(BC * sizeof(float)), o_pose = o_n + al(B * sizeof(int)), o_sum = o_pose + al(7 * B * sizeof(double)),
+                 o_inl = o_sum + al(B * sizeof(cmos_ba_summary)), o_out = o_inl + al(B * sizeof(int)), total = o_out + al(BC);
+    CMOS_CUDA_OK(cudaStreamSynchronize(st));
+    if (st != h->stream) CMOS_CUDA_OK(cudaStreamSynchronize(h->stream));     // the buffer is shared with set_problem / get_results
+    if (total > h->cap_stage) {
+      if (h->h_stage) cudaFreeHost(h->h_stage);
+      if (h->d_stage) cudaFree(h->d_stage);
+      h->h_stage = h->d_stage = nullptr; h->cap_stage = 0;
+      const size_t want = total + total / 4 + 4096;
+      CMOS_CUDA_OK(cudaMallocHost((void**)&h->h_stage, want));
+      CMOS_CUDA_OK(cudaMalloc((void**)&h->d_stage, want));
+      h->cap_stage = want;
+    }
+    std::memcpy(h->h_stage + o_xw, xw, 3 * BC * sizeof(double));
+    std::memcpy(h->h_stage + o_uv, uv, 2 * BC * sizeof(float));
+    std::memcpy(h->h_stage + o_w, inv_sigma2, BC * sizeof(float));
+    std::memcpy(h->h_stage + o_n, n_corr, B * sizeof(int));
+    std::memcpy(h->h_stage + o_pose, pose7, 7 * B * sizeof(double));
+    CMOS_CUDA_OK(cudaMemcpyAsync(h->d_stage, h->h_stage, o_sum, cudaMemcpyHostToDevice, st));
+    uint8_t* ds = h->d_stage;
+    a.pose7 = (double*)(ds + o_pose); a.n_corr = (const int*)(ds + o_n); a.xw = (const double*)(ds + o_xw);
+    a.uv = (const float*)(ds + o_uv); a.inv_sigma2 = (const float*)(ds + o_w);
+    a.is_outlier = ds + o_out; a.n_inliers = (int*)(ds + o_inl); a.summaries = (cmos_ba_summary*)(ds + o_sum); a.trace = h->dp_trace;
+    h->pose_stage[0] = o_pose; h->pose_stage[1] = o_sum; h->pose_stage[2] = o_inl; h->pose_stage[3] = o_out; h->pose_stage[4] = total;
   }
   h->timer.begin(st);
   k_pose_opt<<<n_frames, kPoseThreads, 0, st>>>(a);
@@ -2763,12 +2817,13 @@ int cmos_ba_pose_optimization(cmos_ba_t h, int32_t n_frames, double* pose7, cons
   CMOS_CUDA_OK(cudaGetLastError());
   h->launches = 1;
   if (!on_device) {
-    CMOS_CUDA_OK(cudaMemcpyAsync(pose7, h->dp_pose, 7 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CMOS_CUDA_OK(cudaMemcpyAsync(is_outlier, h->dp_out, BC, cudaMemcpyDeviceToHost, st));
-    CMOS_CUDA_OK(cudaMemcpyAsync(n_inliers, h->dp_inl, B * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (summaries)
-      CMOS_CUDA_OK(cudaMemcpyAsync(summaries, h->dp_sum, B * sizeof(cmos_ba_summary), cudaMemcpyDeviceToHost, st));
+    const size_t* o = h->pose_stage;
+    CMOS_CUDA_OK(cudaMemcpyAsync(h->h_stage + o[0], h->d_stage + o[0], o[4] - o[0], cudaMemcpyDeviceToHost, st));
     CMOS_CUDA_OK(cudaStreamSynchronize(st));
+    std::memcpy(pose7, h->h_stage + o[0], 7 * B * sizeof(double));
+    if (summaries) std::memcpy(summaries, h->h_stage + o[1], B * sizeof(cmos_ba_summary));
+    std::memcpy(n_inliers, h->h_stage + o[2], B * sizeof(int));
+    std::memcpy(is_outlier, h->h_stage + o[3], BC);
   }
   return CMOS_OK;
 }
@@ -2864,7 +2919,7 @@ struct Stager {
 
 extern "C" {
 
-int cmos_debug_solve_spd(const double* A, const double* b, int32_t n, double* x, int32_t* failed, int64_t* cycles2) {
+int cmos_debug_solve_spd(const double* A, const double* b, int32_t n, int32_t variant, double* x, int32_t* failed, int64_t* cycles2) {
   CMOS_REQUIRE(A && b && x && failed && n >= 6 && n % 6 == 0 && n <= kSmallMaxN, "bad argument (n a multiple of 6, <= %d)", kSmallMaxN);
   double *dA = nullptr, *db = nullptr, *dx = nullptr; int* df = nullptr; long long* dc = nullptr;
   CMOS_CUDA_OK(cudaMalloc(&dA, (size_t)n * n * 8)); CMOS_CUDA_OK(cudaMalloc(&db, n * 8)); CMOS_CUDA_OK(cudaMalloc(&dx, n * 8));
@@ -2874,7 +2929,7 @@ int cmos_debug_solve_spd(const double* A, const double* b, int32_t n, double* x,
   const size_t smem = ((size_t)(n + 1) * (n + 2) / 2 + chol_scratch_doubles(n)) * sizeof(double);
   CMOS_CUDA_OK(cudaFuncSetAttribute(k_debug_solve_spd, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
   for (int rep = 0; rep < 2; rep++)       // the second run reports warm instruction-cache cycles
-    k_debug_solve_spd<<<1, kSolveThreads, smem>>>(dA, db, n, dx, df, dc);
+    k_debug_solve_spd<<<1, kSolveThreads, smem>>>(dA, db, n, dx, df, dc, variant);
   CMOS_CUDA_OK(cudaDeviceSynchronize());
   long long hc[2];
   CMOS_CUDA_OK(cudaMemcpy(x, dx, n * 8, cudaMemcpyDeviceToHost));

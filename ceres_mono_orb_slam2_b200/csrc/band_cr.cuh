@@ -468,11 +468,10 @@ __global__ void __launch_bounds__(kSolveThreads) k_crb_solve(BaDev d, CrArgs a) 
     L[e] = v - ((s0 + s1) + (s2 + s3));
   }
   __syncthreads();
-  factor_and_invert24(L, P, nb, &s_fail);
+  factor_and_solve(L, P, nb, &s_fail, s_x24);
   __syncthreads();
   if (s_fail) { if (tid == 0) st.solve_failed = 1; return; }
-  double* y = L + ne;
-  back_substitute24(L, y, s_x24, nb);
+  const double* y = L + ne;
   double* xb = crb_xb(a);
   for (int k = tid; k < nb; k += kSolveThreads) xb[k] = y[k];
 }

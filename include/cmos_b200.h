@@ -587,9 +587,11 @@ int cmos_ba_debug_stop_at(cmos_ba_t h, int32_t pass, int32_t iteration);
 int cmos_ba_debug_pose_trace(cmos_ba_t h, int32_t frame, double* trace, int32_t rows);
 /* Test tap of the small dense reduced-camera-system solver (what Ceres' DENSE_SCHUR / SPARSE_SCHUR hand to LAPACK / CHOLMOD,
  * src/CeresOptimizer.cc:178-187, 516-519): solves A x = b for a symmetric positive definite A (n x n row-major, n a multiple
- * of 6, <= 228) with exactly the device routines the BA kernels use.  failed = 1 if a pivot was not positive.  cycles2
+ * of 6, <= 228) with exactly the device routines the BA kernels use: variant 0 = factorisation into the 24-block format +
+ * 24-row back substitution (GlobalBA's nested-dissection nodes), variant 1 = the whole solve as LocalBA's reduced camera
+ * system takes it.  failed = 1 if a pivot was not positive.  cycles2
  * (optional, 2 entries): SM cycles of the factorisation and of the back substitution. */
-int cmos_debug_solve_spd(const double* A, const double* b, int32_t n, double* x, int32_t* failed, int64_t* cycles2);
+int cmos_debug_solve_spd(const double* A, const double* b, int32_t n, int32_t variant, double* x, int32_t* failed, int64_t* cycles2);
 /* How the last cmos_ba_optimize_essential_graph call solved its normal equations (what Ceres' SPARSE_NORMAL_CHOLESKY does
  * with CHOLMOD, src/CeresOptimizer.cc:897-901): info6 = {1 if nested dissection over a band + border structure was used
  * (0: blocked Cholesky inside the row envelope), keyframes per node, unknowns per node, nodes, border keyframes, border

@@ -27,11 +27,11 @@ def _spd(n, seed, banded=False):
     return (A * d[:, None]) * d[None, :]
 
 
-def _solve(A, b):
+def _solve(A, b, variant=0):
     n = A.shape[0]
     x = np.zeros(n); failed = C.c_int32(-1); cyc = (C.c_int64 * 2)()
     A = np.ascontiguousarray(A, np.float64); b = np.ascontiguousarray(b, np.float64)
-    _lib.check(_lib.lib().cmos_debug_solve_spd(_lib.ptr(A), _lib.ptr(b), n, _lib.ptr(x), C.byref(failed), cyc))
+    _lib.check(_lib.lib().cmos_debug_solve_spd(_lib.ptr(A), _lib.ptr(b), n, variant, _lib.ptr(x), C.byref(failed), cyc))
     return x, failed.value, (cyc[0], cyc[1])
 
 
@@ -40,12 +40,13 @@ def test_solve_equals_lapack(n):
     for seed, banded in ((n, False), (1000 + n, True)):
         A = _spd(n, seed, banded)
         b = np.random.default_rng(7 * n + seed).standard_normal(n)
-        x, failed, cyc = _solve(A, b)
         ref = np.linalg.solve(A, b)
-        assert failed == 0
-        err = np.abs(x - ref).max() / np.abs(ref).max()
-        assert err < TOL, (n, banded, err)
-        assert cyc[0] > 0
+        for variant in (0, 1):
+            x, failed, cyc = _solve(A, b, variant)
+            assert failed == 0
+            err = np.abs(x - ref).max() / np.abs(ref).max()
+            assert err < TOL, (n, banded, variant, err)
+            assert cyc[0] > 0
 
 
 def test_identity_and_diagonal():
@@ -60,8 +61,8 @@ def test_identity_and_diagonal():
 def test_indefinite_matrix_is_reported(n):
     A = _spd(n, 5)
     A[n // 2, n // 2] = -1.0                      # a negative pivot appears at that column
-    _, failed, _ = _solve(A, np.ones(n))
-    assert failed == 1
+    for variant in (0, 1):
+        assert _solve(A, np.ones(n), variant)[1] == 1
     A = _spd(n, 6)
     A[n - 1, n - 1] = np.nan
     _, failed, _ = _solve(A, np.ones(n))
