@@ -24,10 +24,18 @@ timeout 900 ncu --set full --clock-control none -k regex:k_ -s 45 -c 36 -o $O/fu
   python bench.py --steps 2 --warmup 3 --no-ba --no-cpu > $O/ncu_full_orb.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ -s 30 -c 12 -o $O/full_ba_local \
   python tools/ba_profile.py local > $O/ncu_full_ba_local.log 2>&1
+# nested-dissection kernels of GlobalBA (first LM iteration of the second solve: warm) and of the essential graph
+timeout 600 ncu --set full --clock-control none -k regex:k_cr_ -s 46 -c 23 -o $O/full_ba_cr \
+  python tools/ba_profile.py global 2 > $O/ncu_full_ba_cr.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file $O/launches_eg.csv \
+  python tools/ba_profile.py essential 1000 > $O/ncu_eg.log 2>&1
+python tools/ncu_summary.py $O/full_ba_cr.ncu-rep $O/ncu_full_ba_cr.json > /dev/null 2>&1
+python tools/summarize_launches.py $O/launches_eg.csv > $O/launches_eg_summary.txt 2>&1
 python -c 'import bench; print(bench.orb_source_hash())' > $O/src_sha256.txt
 # summarise on the box: gpurun copies back at most 64 MiB, the reports themselves stay behind when they are large
 python tools/ncu_summary.py $O/full_orb.ncu-rep $O/ncu_full_orb.json > /dev/null 2>&1
 python tools/ncu_summary.py $O/full_ba_local.ncu-rep $O/ncu_full_ba_local.json > /dev/null 2>&1
 for f in launches_orb launches_ba_local launches_ba_global; do python tools/summarize_launches.py $O/$f.csv > $O/${f}_summary.txt 2>&1; done
-find $O -name '*.ncu-rep' -size +12M -delete
+find $O -name '*.ncu-rep' -size +10M -delete
+rm -f $O/launches_eg.csv
 ls -la $O
