@@ -26,8 +26,9 @@ with open(os.path.join(ROOT, "profiles", "r2_sass_instruction_table.md"), "w") a
     o.write("# SASS instruction census of the shipped library (round 2)\n\n`cuobjdump -sass ceres_mono_orb_slam2_b200/libcmos_b200.so` "
             "(sm_100a), sha256 prefix `%s`, %d kernels.\n\n" % (sha, len(funcs) - 1))
     o.write("| mnemonic | sites in the library | meaning |\n|---|---|---|\n")
-    o.write("| `DMMA` | %d | fp64 tensor-core MMA (`mma.sync.m8n8k4.f64`): nested-dissection solver tile products, rank-6 trailing "
-            "update of `packed_cholesky` |\n" % tot["DMMA"])
+    o.write("| `DMMA` | %d | fp64 tensor-core MMA (`mma.sync.m8n8k4.f64`): register-resident tile Cholesky (`packed_cholesky_reg`: panel "
+            "products, trailing updates), nested-dissection spikes / Schur / border products, rank-6 update of the "
+            "shared-memory `packed_cholesky` |\n" % tot["DMMA"])
     o.write("| `UBLKCP` | %d | TMA bulk copy without tensor map (`cp.async.bulk.shared::cluster.global`): `k_blur` tile rows, "
             "`k_band_backsub` column ring |\n" % tot["UBLKCP"])
     o.write("| `UTMALDG` | %d | TMA tensor-map load: not used — faults with *illegal instruction* on this pool's B200s "
