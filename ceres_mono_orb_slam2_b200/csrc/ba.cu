@@ -2589,7 +2589,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
         // factorisations, all nodes of a level in parallel
         const CrArgs ca{h->cr_n, h->cr_Wb, h->cr_N, h->band_W, h->cr_levels, h->d_band_blk, d.S};
         const int nt = ca.n / 24, tile_ctas = (nt * nt + kCrGemmWarps - 1) / kCrGemmWarps;
-        k_cr_assemble<<<ca.N, 256, 0, st>>>(d, ca);
+        k_cr_assemble<<<dim3(ca.N, kCrAsmSplit), 256, 0, st>>>(d, ca);
         h->launches++;
         for (int l = 1; l <= ca.levels; l++) {
           const int cnt = ((ca.N >> (l - 1)) + 1) / 2;
@@ -3669,10 +3669,14 @@ int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Sc
         const int cnt = ((ca.N >> (l - 1)) + 1) / 2;
         k_cr_factor<<<cnt, kSolveThreads, cr_factor_smem(ca.n), st>>>(dv, ca, l);
         h->launches++;
-        if (l < ca.levels) { k_cr_spike<<<dim3(nt / kw, 2, cnt), 32 * kw, cr_spike_smem(ca.n), st>>>(dv, ca, l, 0); h->launches++; }
-        if (ntb) { k_cr_spike<<<dim3((ntb + kw - 1) / kw, 1, cnt), 32 * kw, cr_spike_smem(ca.n), st>>>(dv, ca, l, 2); h->launches++; }
-        if (l < ca.levels) { k_cr_schur<<<dim3(tile_ctas, 4, cnt), 32 * kCrGemmWarps, 0, st>>>(dv, ca, l); h->launches++; }
-        if (ntb) { k_crb_schur<<<dim3(tile_ctas_b, 4, cnt), 32 * kCrGemmWarps, 0, st>>>(dv, ca, l); h->launches++; }
+        // neighbour and border spikes in one launch, neighbour and border products in one launch; the last level has no neighbours
+        const int sx = std::max(nt / kw, (ntb + kw - 1) / kw);
+        if (l < ca.levels) k_cr_spike<<<dim3(ntb ? sx : nt / kw, ntb ? 3 : 2, cnt), 32 * kw, cr_spike_smem(ca.n), st>>>(dv, ca, l, 0);
+        else if (ntb) k_cr_spike<<<dim3((ntb + kw - 1) / kw, 1, cnt), 32 * kw, cr_spike_smem(ca.n), st>>>(dv, ca, l, 2);
+        if (l < ca.levels && ntb) k_cr_schur_all<<<dim3(std::max(tile_ctas, tile_ctas_b), 8, cnt), 32 * kCrGemmWarps, 0, st>>>(dv, ca, l);
+        else if (l < ca.levels) k_cr_schur<<<dim3(tile_ctas, 4, cnt), 32 * kCrGemmWarps, 0, st>>>(dv, ca, l);
+        else if (ntb) k_crb_schur<<<dim3(tile_ctas_b, 4, cnt), 32 * kCrGemmWarps, 0, st>>>(dv, ca, l);
+        h->launches += (l < ca.levels || ntb) ? 2 : 0;
       }
       if (ntb) { k_crb_solve<<<1, kSolveThreads, crb_solve_smem(ca.nbp), st>>>(dv, ca); h->launches++; }
       for (int l = ca.levels; l >= 1; l--) {

@@ -85,20 +85,27 @@ inline size_t cr_factor_smem(int n) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Assembly: one CTA per node zero-fills its arrays and scatters the Sblk blocks of its block columns.
+// Assembly: kCrAsmSplit CTAs per node, each zero-fills a quarter of the node's block rows in D0 / Ep and scatters the Sblk
+// blocks that land there (one CTA per node spent 53 us writing 230 KB of zeros with 256 threads: latency of one SM).
+constexpr int kCrAsmSplit = 4;          // Wb is a multiple of 4
 __global__ void __launch_bounds__(256) k_cr_assemble(BaDev d, CrArgs a) {
   const LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
-  const int node = blockIdx.x + 1, tid = threadIdx.x, n = a.n, n2 = n * n;
+  const int node = blockIdx.x + 1, part = blockIdx.y, tid = threadIdx.x, n = a.n;
   double* D0 = cr_arr(a, CR_D0, node);
   double* Ep = cr_arr(a, CR_EP, node);
+  const int bl0 = part * (a.Wb / kCrAsmSplit), bl1 = bl0 + a.Wb / kCrAsmSplit;     // block rows of this CTA
   // (AccL / AccR / bL / bR need no clearing: their first contribution, at level 1, is a plain store — cr_has_acc)
   const double2 z2 = make_double2(0.0, 0.0);
-  for (int e = tid; e < n2 / 2; e += 256) { ((double2*)D0)[e] = z2; ((double2*)Ep)[e] = z2; }
+  {
+    double2* d2 = (double2*)(D0 + (size_t)6 * bl0 * n);
+    double2* e2 = (double2*)(Ep + (size_t)6 * bl0 * n);
+    for (int e = tid; e < 6 * (bl1 - bl0) * n / 2; e += 256) { d2[e] = z2; e2[e] = z2; }
+  }
   __syncthreads();
   const int b0 = (node - 1) * a.Wb, NB = a.W + 1;
-  for (int e = tid; e < a.Wb * NB * 36; e += 256) {
-    const int bl = e / (NB * 36), rem = e - bl * NB * 36, off = rem / 36, rc = rem - 36 * off, r = rc / 6, c = rc - 6 * r;
+  for (int e = tid; e < (bl1 - bl0) * NB * 36; e += 256) {
+    const int bl = bl0 + e / (NB * 36), rem = e % (NB * 36), off = rem / 36, rc = rem - 36 * off, r = rc / 6, c = rc - 6 * r;
     const int b = b0 + bl, aa = b - off;
     if (b >= d.Kv) {                                   // padding block: identity
       if (off == 0 && r == c) D0[(size_t)(6 * bl + r) * n + 6 * bl + r] = 1.0;
@@ -337,10 +344,10 @@ __global__ void __launch_bounds__(192) k_cr_spike(BaDev d, CrArgs a, int level, 
 // Schur products of an eliminated node: grid (tile groups, product, node).
 //   product 0: AccR[l] += V_l' V_l (lower tiles)   1: AccL[r] += V_r' V_r (lower tiles)   2: Clr[i] = V_l' V_r
 //   product 3: bR[l] += V_l' y_i, bL[r] += V_r' y_i
-__global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur(BaDev d, CrArgs a, int level) {
+__device__ __forceinline__ void cr_schur_body(const BaDev& d, const CrArgs& a, const int level, const int prod) {
   const LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
-  const int node = cr_node_at(level, blockIdx.z), prod = blockIdx.y, n = a.n, nt = n / 24, h = 1 << (level - 1);
+  const int node = cr_node_at(level, blockIdx.z), n = a.n, nt = n / 24, h = 1 << (level - 1);
   const int l = node - h, r = node + h;
   const bool has_l = l >= 1, has_r = r <= a.N;
   const double* __restrict__ Vl = cr_arr(a, CR_VL, node);
@@ -384,10 +391,10 @@ __global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur(BaDev d, CrArgs 
 
 // Border products of an eliminated node: grid (tile groups, product, node).
 //   product 0: FaccR[l] += V_l' V_b   1: FaccL[r] += V_r' V_b   2: Cpart[i] = V_b' V_b (lower tiles)   3: gpart[i] = V_b' y_i
-__global__ void __launch_bounds__(32 * kCrGemmWarps) k_crb_schur(BaDev d, CrArgs a, int level) {
+__device__ __forceinline__ void crb_schur_body(const BaDev& d, const CrArgs& a, const int level, const int prod) {
   const LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
-  const int node = cr_node_at(level, blockIdx.z), prod = blockIdx.y, n = a.n, nbp = a.nbp, h = 1 << (level - 1);
+  const int node = cr_node_at(level, blockIdx.z), n = a.n, nbp = a.nbp, h = 1 << (level - 1);
   const int l = node - h, r = node + h;
   const bool has_l = l >= 1, has_r = r <= a.N;
   const double* __restrict__ Vb = crb_arr(a, CRB_VB, node);
@@ -424,6 +431,14 @@ __global__ void __launch_bounds__(32 * kCrGemmWarps) k_crb_schur(BaDev d, CrArgs
       if (prod == 2 || level == 1) *o = make_double2(t.c[mi][ni][0], t.c[mi][ni][1]);
       else { const double2 old = *o; *o = make_double2(old.x + t.c[mi][ni][0], old.y + t.c[mi][ni][1]); }
     }
+}
+
+__global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur(BaDev d, CrArgs a, int level) { cr_schur_body(d, a, level, blockIdx.y); }
+__global__ void __launch_bounds__(32 * kCrGemmWarps) k_crb_schur(BaDev d, CrArgs a, int level) { crb_schur_body(d, a, level, blockIdx.y); }
+// both in one launch (bordered systems, every level but the last): grid (tile groups, 8 products, node)
+__global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur_all(BaDev d, CrArgs a, int level) {
+  if (blockIdx.y < 4) cr_schur_body(d, a, level, blockIdx.y);
+  else crb_schur_body(d, a, level, blockIdx.y - 4);
 }
 
 // The border system after every node is eliminated: (C0 - sum_i Cpart[i]) x_C = gB - sum_i gpart[i], sums in node order;

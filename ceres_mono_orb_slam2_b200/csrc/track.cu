@@ -25,7 +25,41 @@ struct Lane {
   cmos_keypoint* d_last_kps = nullptr;
   int *d_last_counts = nullptr, *d_match = nullptr, *d_nm = nullptr;
   uint8_t *d_flags = nullptr, *d_last_desc = nullptr;
+  // compact last-frame input (cmos_track_submit_points): packed records, per-frame offsets, record -> last-frame index
+  cmos_last_point* d_points = nullptr;
+  int *d_point_start = nullptr, *d_pidx = nullptr;
 };
+
+static_assert(sizeof(cmos_last_point) == 64, "cmos_last_point is a 64-byte record");
+// One record per usable last-frame map point -> the per-keypoint arrays the search kernels read (frame f of the chunk,
+// record j): octave / angle of the keypoint, flags, world position, descriptor; pidx keeps the keypoint's own index.
+__global__ void __launch_bounds__(256) k_unpack_last(const cmos_last_point* __restrict__ pts, const int* __restrict__ start, int base,
+                                                     int stride, cmos_keypoint* __restrict__ kps, int* __restrict__ counts,
+                                                     uint8_t* __restrict__ flags, double* __restrict__ xw, uint8_t* __restrict__ desc,
+                                                     int* __restrict__ pidx) {
+  const int f = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+  const int s0 = start[f] - base, n = min(start[f + 1] - start[f], stride);
+  if (j == 0) counts[f] = n;
+  if (j >= n) return;
+  const cmos_last_point& r = pts[s0 + j];
+  const size_t o = (size_t)f * stride + j;
+  cmos_keypoint kp;
+  kp.x = 0.f; kp.y = 0.f; kp.size = 0.f; kp.angle = r.angle; kp.response = 0.f; kp.octave = r.octave; kp.class_id = -1;
+  kps[o] = kp;
+  flags[o] = r.flags;
+  xw[3 * o] = r.xw[0]; xw[3 * o + 1] = r.xw[1]; xw[3 * o + 2] = r.xw[2];
+  const uint4* d4 = (const uint4*)r.descriptor;
+  ((uint4*)(desc + 32 * o))[0] = d4[0]; ((uint4*)(desc + 32 * o))[1] = d4[1];
+  pidx[o] = r.index;
+}
+// match holds record numbers: back to last-frame keypoint indices
+__global__ void __launch_bounds__(256) k_remap_match(int* __restrict__ match, const int* __restrict__ pidx, int stride, int n_total) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= n_total) return;
+  const int m = match[t];
+  if (m >= 0) match[t] = pidx[(size_t)(t / stride) * stride + m];
+}
+
 
 constexpr int kTrackSlots = 4;        // batches that may be in flight between cmos_track_submit and cmos_track_wait
 struct Slot {
@@ -60,7 +94,8 @@ int cmos_track_destroy(cmos_track_t h) {
   for (Lane& L : h->lanes) {
     if (L.orb) cmos_orb_destroy(L.orb);
     if (L.match) cmos_match_destroy(L.match);
-    void* bufs[] = {L.d_T, L.d_xw, L.d_last_kps, L.d_last_counts, L.d_match, L.d_nm, L.d_flags, L.d_last_desc};
+    void* bufs[] = {L.d_T, L.d_xw, L.d_last_kps, L.d_last_counts, L.d_match, L.d_nm, L.d_flags, L.d_last_desc, L.d_points, L.d_point_start,
+                    L.d_pidx};
     for (void* b : bufs)
       if (b) cudaFree(b);
     if (L.st) cudaStreamDestroy(L.st);
@@ -95,6 +130,9 @@ int cmos_track_create(const cmos_track_params* params, const cmos_camera* cam, c
     L.d_nm = dev_alloc<int>(params->chunk_frames, &err);
     L.d_flags = dev_alloc<uint8_t>(n, &err);
     L.d_last_desc = dev_alloc<uint8_t>(n * 32, &err);
+    L.d_points = dev_alloc<cmos_last_point>(n, &err);
+    L.d_point_start = dev_alloc<int>(params->chunk_frames + 1, &err);
+    L.d_pidx = dev_alloc<int>(n, &err);
     if (err != cudaSuccess) { set_error("device allocation failed: %s", cudaGetErrorString(err)); rc = CMOS_ERR_CUDA; break; }
   }
   for (Slot& sl : h->slots) {
@@ -113,16 +151,28 @@ int cmos_track_keypoint_capacity(cmos_track_t h, int32_t* cap) {
   return CMOS_OK;
 }
 
-int cmos_track_submit(cmos_track_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
-                      int32_t height, int32_t n_frames, const double* Tcw, const cmos_keypoint* last_keypoints,
-                      const int32_t* last_counts, const uint8_t* last_flags, const double* last_xw,
-                      const uint8_t* last_descriptors, int32_t last_stride, float th, int32_t check_orientation,
-                      cmos_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int32_t capacity, int32_t* match,
-                      int32_t* nmatches, int64_t* ticket) {
-  CMOS_REQUIRE(h && images && Tcw && last_keypoints && last_counts && last_flags && last_xw && last_descriptors &&
-               keypoints && descriptors && counts && match && nmatches && ticket, "null argument");
+}  // extern "C"
+
+// points != nullptr: the last-frame inputs come as packed records (cmos_track_submit_points); otherwise as per-keypoint arrays
+static int submit_impl(cmos_track_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
+                       int32_t height, int32_t n_frames, const double* Tcw, const cmos_keypoint* last_keypoints,
+                       const int32_t* last_counts, const uint8_t* last_flags, const double* last_xw,
+                       const uint8_t* last_descriptors, int32_t last_stride, const cmos_last_point* points,
+                       const int32_t* point_start, float th, int32_t check_orientation,
+                       cmos_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int32_t capacity, int32_t* match,
+                       int32_t* nmatches, int64_t* ticket) {
+  CMOS_REQUIRE(h && images && Tcw && keypoints && descriptors && counts && match && nmatches && ticket, "null argument");
+  CMOS_REQUIRE(points ? point_start != nullptr
+                      : (last_keypoints && last_counts && last_flags && last_xw && last_descriptors), "null argument");
   CMOS_REQUIRE(n_frames >= 1, "n_frames must be positive");
   CMOS_REQUIRE(capacity >= h->kp_cap, "capacity %d < cmos_track_keypoint_capacity %d", capacity, h->kp_cap);
+  if (points) {
+    CMOS_REQUIRE(h->kp_cap <= 65536, "keypoint capacity %d does not fit the 16-bit record index", h->kp_cap);
+    last_stride = h->kp_cap;
+    for (int f = 0; f < n_frames; f++)
+      CMOS_REQUIRE(point_start[f + 1] >= point_start[f] && point_start[f + 1] - point_start[f] <= h->kp_cap,
+                   "frame %d: %d records outside 0..%d", f, point_start[f + 1] - point_start[f], h->kp_cap);
+  }
   CMOS_REQUIRE(last_stride >= 1 && last_stride <= h->kp_cap, "last_stride %d outside 1..%d", last_stride, h->kp_cap);
   CMOS_CUDA_OK(cudaSetDevice(h->p.orb.device));
   Slot* slot = nullptr;
@@ -150,11 +200,22 @@ int cmos_track_submit(cmos_track_t h, const uint8_t* images, int64_t frame_strid
     const int n = std::min(cf, n_frames - f0);
     const size_t nq = (size_t)n * last_stride, o = (size_t)f0 * last_stride;
     TRACK_CUDA(cudaMemcpyAsync(L.d_T, Tcw + (size_t)f0 * 16, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, L.st));
-    TRACK_CUDA(cudaMemcpyAsync(L.d_last_kps, last_keypoints + o, nq * sizeof(cmos_keypoint), cudaMemcpyHostToDevice, L.st));
-    TRACK_CUDA(cudaMemcpyAsync(L.d_last_counts, last_counts + f0, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, L.st));
-    TRACK_CUDA(cudaMemcpyAsync(L.d_flags, last_flags + o, nq, cudaMemcpyHostToDevice, L.st));
-    TRACK_CUDA(cudaMemcpyAsync(L.d_xw, last_xw + o * 3, nq * 3 * sizeof(double), cudaMemcpyHostToDevice, L.st));
-    TRACK_CUDA(cudaMemcpyAsync(L.d_last_desc, last_descriptors + o * 32, nq * 32, cudaMemcpyHostToDevice, L.st));
+    if (points) {
+      // packed records of this chunk's frames: ONE copy of exactly the bytes that matter, then unpacked on the device
+      const int base = point_start[f0], cnt = point_start[f0 + n] - base;
+      TRACK_CUDA(cudaMemcpyAsync(L.d_point_start, point_start + f0, (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, L.st));
+      if (cnt > 0)
+        TRACK_CUDA(cudaMemcpyAsync(L.d_points, points + base, (size_t)cnt * sizeof(cmos_last_point), cudaMemcpyHostToDevice, L.st));
+      k_unpack_last<<<dim3((h->kp_cap + 255) / 256, n), 256, 0, L.st>>>(L.d_points, L.d_point_start, base, last_stride, L.d_last_kps,
+                                                                       L.d_last_counts, L.d_flags, L.d_xw, L.d_last_desc, L.d_pidx);
+      launches++;
+    } else {
+      TRACK_CUDA(cudaMemcpyAsync(L.d_last_kps, last_keypoints + o, nq * sizeof(cmos_keypoint), cudaMemcpyHostToDevice, L.st));
+      TRACK_CUDA(cudaMemcpyAsync(L.d_last_counts, last_counts + f0, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, L.st));
+      TRACK_CUDA(cudaMemcpyAsync(L.d_flags, last_flags + o, nq, cudaMemcpyHostToDevice, L.st));
+      TRACK_CUDA(cudaMemcpyAsync(L.d_xw, last_xw + o * 3, nq * 3 * sizeof(double), cudaMemcpyHostToDevice, L.st));
+      TRACK_CUDA(cudaMemcpyAsync(L.d_last_desc, last_descriptors + o * 32, nq * 32, cudaMemcpyHostToDevice, L.st));
+    }
     if ((rc = cmos_orb_extract_async(L.orb, images + (size_t)f0 * frame_stride, frame_stride, pitch, width, height, n,
                                      keypoints + (size_t)f0 * capacity, descriptors + (size_t)f0 * capacity * 32,
                                      counts + f0, capacity, L.st))) break;
@@ -164,6 +225,11 @@ int cmos_track_submit(cmos_track_t h, const uint8_t* images, int64_t frame_strid
     if ((rc = cmos_match_search_by_projection_frame(L.match, L.d_T, L.d_last_kps, L.d_last_counts, L.d_flags, L.d_xw,
                                                     L.d_last_desc, last_stride, th, check_orientation, nullptr, L.d_match,
                                                     L.d_nm, 1, L.st))) break;
+    if (points) {
+      const int tot = n * h->kp_cap;
+      k_remap_match<<<(tot + 255) / 256, 256, 0, L.st>>>(L.d_match, L.d_pidx, h->kp_cap, tot);
+      launches++;
+    }
     const size_t row = (size_t)h->kp_cap * sizeof(int);
     if (capacity == h->kp_cap) {
       TRACK_CUDA(cudaMemcpyAsync(match + (size_t)f0 * capacity, L.d_match, row * n, cudaMemcpyDeviceToHost, L.st));
@@ -193,6 +259,30 @@ int cmos_track_submit(cmos_track_t h, const uint8_t* images, int64_t frame_strid
   slot->busy = true; slot->ticket = h->next_ticket++; slot->match = match; slot->n_frames = n_frames; slot->capacity = capacity;
   *ticket = slot->ticket;
   return CMOS_OK;
+}
+
+extern "C" {
+
+int cmos_track_submit(cmos_track_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
+                      int32_t height, int32_t n_frames, const double* Tcw, const cmos_keypoint* last_keypoints,
+                      const int32_t* last_counts, const uint8_t* last_flags, const double* last_xw,
+                      const uint8_t* last_descriptors, int32_t last_stride, float th, int32_t check_orientation,
+                      cmos_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int32_t capacity, int32_t* match,
+                      int32_t* nmatches, int64_t* ticket) {
+  CMOS_REQUIRE(last_keypoints && last_counts && last_flags && last_xw && last_descriptors, "null argument");
+  return submit_impl(h, images, frame_stride, pitch, width, height, n_frames, Tcw, last_keypoints, last_counts, last_flags, last_xw,
+                     last_descriptors, last_stride, nullptr, nullptr, th, check_orientation, keypoints, descriptors, counts, capacity,
+                     match, nmatches, ticket);
+}
+
+int cmos_track_submit_points(cmos_track_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
+                             int32_t height, int32_t n_frames, const double* Tcw, const cmos_last_point* points,
+                             const int32_t* point_start, float th, int32_t check_orientation, cmos_keypoint* keypoints,
+                             uint8_t* descriptors, int32_t* counts, int32_t capacity, int32_t* match, int32_t* nmatches,
+                             int64_t* ticket) {
+  CMOS_REQUIRE(points && point_start, "null argument");
+  return submit_impl(h, images, frame_stride, pitch, width, height, n_frames, Tcw, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                     points, point_start, th, check_orientation, keypoints, descriptors, counts, capacity, match, nmatches, ticket);
 }
 
 int cmos_track_wait(cmos_track_t h, int64_t ticket) {

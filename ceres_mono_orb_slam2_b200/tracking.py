@@ -13,6 +13,26 @@ from ._lib import KP_DTYPE, OrbParams, check, ptr
 from .orb_matcher import Camera
 
 
+LAST_POINT_DTYPE = np.dtype([("descriptor", "u1", (32,)), ("xw", "<f8", (3,)), ("angle", "<f4"), ("index", "<u2"), ("octave", "i1"),
+                             ("flags", "u1")])
+assert LAST_POINT_DTYPE.itemsize == 64      # == sizeof(cmos_last_point)
+
+
+def pack_last_points(last_keypoints, last_counts, last_flags, last_xw, last_descriptors):
+    """Per-keypoint last-frame arrays [B,S]... -> (records, point_start): one cmos_last_point per keypoint with flag bit 0 set,
+    frame after frame, in increasing keypoint index (what a caller would build straight from LastFrame.map_points_)."""
+    B = len(last_counts)
+    recs, start = [], [0]
+    for f in range(B):
+        n = int(last_counts[f])
+        idx = np.nonzero(last_flags[f, :n] & 1)[0]
+        r = np.zeros(len(idx), LAST_POINT_DTYPE)
+        r["descriptor"] = last_descriptors[f, idx]; r["xw"] = last_xw[f, idx]; r["angle"] = last_keypoints["angle"][f, idx]
+        r["index"] = idx; r["octave"] = last_keypoints["octave"][f, idx]; r["flags"] = last_flags[f, idx]
+        recs.append(r); start.append(start[-1] + len(idx))
+    return np.concatenate(recs) if recs else np.zeros(0, LAST_POINT_DTYPE), np.array(start, np.int32)
+
+
 class TrackParams(C.Structure):
     _fields_ = [("orb", OrbParams), ("lanes", C.c_int32), ("chunk_frames", C.c_int32)]
 
@@ -73,6 +93,18 @@ class TrackingFrontEnd:
                                         ptr(last_counts), ptr(last_flags), ptr(last_xw), ptr(last_descriptors), S,
                                         C.c_float(th), int(self.check_ori), ptr(kps), ptr(desc), ptr(counts), cap,
                                         ptr(match), ptr(nm), C.byref(t)))
+        return t.value
+
+    def submit_points(self, images, Tcw, points, point_start, th: float, out):
+        """submit() with the last-frame inputs as packed 64-byte records (cmos_track_submit_points; pack_last_points builds them):
+        the upload carries only the keypoints that have a usable map point.  Same results as submit()."""
+        B, H, W = images.shape
+        kps, desc, counts, match, nm = out
+        cap = match.shape[1]
+        t = C.c_int64(-1)
+        check(self._L.cmos_track_submit_points(self._h, ptr(images), C.c_int64(H * W), W, W, H, B, ptr(Tcw), ptr(points),
+                                               ptr(point_start), C.c_float(th), int(self.check_ori), ptr(kps), ptr(desc),
+                                               ptr(counts), cap, ptr(match), ptr(nm), C.byref(t)))
         return t.value
 
     def wait(self, ticket: int):

@@ -435,6 +435,27 @@ int cmos_track_submit(cmos_track_t h, const uint8_t* images, int64_t frame_strid
                       int32_t* nmatches, int64_t* ticket);
 int cmos_track_wait(cmos_track_t h, int64_t ticket);
 
+/* The same call with the last-frame inputs in COMPACT form: one 64-byte record per last-frame keypoint that carries a usable
+ * map point — exactly what the loop of ORBmatcher.cc:1187-1195 visits (`pMP && !LastFrame.is_outliers_[i]`) — instead of
+ * 85 bytes for every keypoint slot (cmos_keypoint 28 + flag 1 + position 24 + descriptor 32).  The end-to-end call is bound
+ * by the host->device copy, so the bytes matter.  Records of frame f are points[point_start[f] .. point_start[f + 1]), in
+ * increasing keypoint index (the reference's visiting order: it decides who wins a contested keypoint); `match` reports
+ * the records' `index`, i.e. the same last-frame keypoint indices cmos_track_submit returns.  Results are identical to
+ * cmos_track_submit on the arrays the records were taken from. */
+typedef struct cmos_last_point {
+  uint8_t descriptor[32];  /* MapPoint::GetDescriptor() */
+  double xw[3];            /* MapPoint::GetWorldPos() */
+  float angle;             /* LastFrame.undistort_keypoints_[index].angle */
+  uint16_t index;          /* keypoint index in the last frame */
+  int8_t octave;           /* LastFrame.undistort_keypoints_[index].octave */
+  uint8_t flags;           /* bit0 set (usable), bit1: the point has Observations() > 0 */
+} cmos_last_point;         /* 64 bytes */
+int cmos_track_submit_points(cmos_track_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
+                             int32_t height, int32_t n_frames, const double* Tcw, const cmos_last_point* points,
+                             const int32_t* point_start, float th, int32_t check_orientation, cmos_keypoint* keypoints,
+                             uint8_t* descriptors, int32_t* counts, int32_t capacity, int32_t* match, int32_t* nmatches,
+                             int64_t* ticket);
+
 /* Kernels launched by the last cmos_track_frames / cmos_track_submit call. */
 int cmos_track_last_launch_count(cmos_track_t h, int32_t* n);
 

@@ -334,6 +334,23 @@ def test_tracking_front_end_equals_unfused_calls(lanes, chunk):
             assert np.array_equal(k2[j, :n], kps[f, :n]) and np.array_equal(m2[j, :n], match[f, :n])
     with pytest.raises(CmosError):
         fe.wait(tickets[0])            # already waited for
+    # compact last-frame inputs (cmos_track_submit_points): one record per usable map point, same results; a frame without
+    # any record and records given in the middle of a batch are part of the case
+    from ceres_mono_orb_slam2_b200.tracking import pack_last_points
+    fl2 = flags.copy(); fl2[B // 2] = 0                       # one frame whose last frame carries no map point at all
+    match2, nm2 = m.SearchByProjectionFrame(T, lk, lcounts, fl2, xw, mdesc, cap, 15.0)
+    pts, pstart = pack_last_points(lk, lcounts, fl2, xw, mdesc)
+    assert pstart[B // 2 + 1] == pstart[B // 2] and len(pts) == int((fl2 & 1).sum())
+    for _ in range(2):
+        o = (np.zeros((B, cap), KP_DTYPE), np.zeros((B, cap, 32), np.uint8), np.zeros(B, np.int32),
+             np.full((B, cap), -1, np.int32), np.zeros(B, np.int32))
+        fe.wait(fe.submit_points(frames, T, pts, pstart, 15.0, out=o))
+        k2, d2, c2, m2, n2 = o
+        assert np.array_equal(c2, counts) and np.array_equal(n2, nm2)
+        for f in range(B):
+            n = int(counts[f])
+            assert np.array_equal(k2[f, :n], kps[f, :n]) and np.array_equal(m2[f, :n], match2[f, :n])
+    assert nm2[B // 2] == 0 and nm2.sum() > 100 * (B - 1)
 
 
 def test_undistort_keypoints_and_distorted_bounds():

@@ -43,6 +43,10 @@ P = synth.make_pose_problem(150, seed=8)
 opt.PoseOptimization(P["pose"][None], P["Xw"][None], P["uv"][None], P["inv_sigma2"][None], K4)
 G2 = synth.make_ba_problem_fast(64, 64 * 40, 5, seed=3, window=4)     # banded: the nested-dissection solver
 opt.BundleAdjustment(G2["poses"], G2["fixed"], G2["points"], G2["obs_cam"], G2["obs_pt"], G2["uv"], G2["inv_sigma2"], K4, n_iterations=2)
+E = synth.make_essential_graph_problem(40, seed=12, n_group=3, covis=(2, 3), n_points=10)    # band + border nested dissection
+r = opt.OptimizeEssentialGraph(E["Scw"], E["kf_flags"], E["Snc"], E["edge_j"], E["edge_i"], E["edge_kind"], E["Xw"], E["ref_kf"],
+                               max_iterations=2)
+assert opt.essential_graph_plan()["nested_dissection"] == 1
 print("SANITIZER_WORKLOAD_DONE", int(counts.sum()), int(nm[0]))
 ''' % ROOT
 
