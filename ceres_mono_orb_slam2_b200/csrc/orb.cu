@@ -891,26 +891,36 @@ __global__ void __launch_bounds__(kDescThreads) k_describe(
   }
   if (slot == 0 && lane == 0) counts[f] = total;
   if (level < 0) return;
+  // (the level's geometry is read into registers ONCE: `g.lv[level].pitch` is a dynamically indexed constant-bank load, and
+  // the compiler re-issued it — plus the 64-bit address arithmetic behind it — under every predicate of the unrolled loops
+  // below: the source-level counters of round 2 showed ~45 % of this kernel's instructions in the 31-row centroid loop)
   const LevelGeom& L = g.lv[level];
+  const int pitch = L.pitch;
   const uint32_t v = stage[(long long)f * g.kp_cap + L.kp_off + idx];
   const int x = (int)(v & 0xfff) + kMinBorder, y = (int)((v >> 12) & 0xfff) + kMinBorder;   // level coords
   const long long plane = (long long)f * g.frame_bytes + L.plane_off;
-  const uint8_t* c = pyr + plane + (long long)(y + kBorder) * L.pitch + kXOff + x;
+  const uint8_t* c = pyr + plane + (long long)(y + kBorder) * pitch + kXOff + x;
 
-  // intensity centroid over the 31-px disc: lane = column u+15
+  // intensity centroid over the 31-px disc: lane = column u+15.  A pointer walks down the column; the column sum is
+  // multiplied by u once (m10 = u * sum_v I), m01 takes the row number as an immediate.
+  // Column u of the disc spans rows -vlim..vlim (umax is non-increasing): rows +r and -r share ONE comparison, the loads
+  // are unconditional (the 19-pixel border keeps all 31 rows inside the plane) and masked by a select — 31 predicated
+  // loads made the compiler pack 31 long-lived predicates into a bit register and spill.
   int m10 = 0, m01 = 0;
   const int u = lane - 15;
   if (lane < 31) {
-    const int au = u < 0 ? -u : u;
+    const int vlim = g.vlim[u < 0 ? -u : u];
+    const uint8_t* p0 = c + u;
+    int colsum = *p0;
 #pragma unroll
-    for (int vv = -15; vv <= 15; vv++) {
-      const int av = vv < 0 ? -vv : vv;
-      if (au <= g.umax[av]) {
-        int I = c[vv * L.pitch + u];
-        m10 += u * I;
-        m01 += vv * I;
-      }
+    for (int r = 1; r <= 15; r++) {
+      int ip = p0[(long long)r * pitch], im = p0[-(long long)r * pitch];
+      const bool in = r <= vlim;
+      ip = in ? ip : 0; im = in ? im : 0;
+      colsum += ip + im;
+      m01 += r * (ip - im);
     }
+    m10 = u * colsum;
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
@@ -949,12 +959,16 @@ __global__ void __launch_bounds__(kDescThreads) k_describe(
     }
   }
 #else
-  const uint8_t* bc = blur + plane + (long long)(y + kBorder) * L.pitch + kXOff + x;
+  const uint8_t* bc = blur + plane + (long long)(y + kBorder) * pitch + kXOff + x;
+  // the lane's 16 pattern points arrive as eight aligned words (4 signed bytes each) instead of 32 byte loads
+  const uint32_t* pw = (const uint32_t*)pat;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
-    float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1], x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
-    int t0 = bc[__float2int_rn(x0 * b + y0 * a) * L.pitch + __float2int_rn(x0 * a - y0 * b)];
-    int t1 = bc[__float2int_rn(x1 * b + y1 * a) * L.pitch + __float2int_rn(x1 * a - y1 * b)];
+    const uint32_t w = __ldg(pw + k);
+    const float x0 = (float)(int8_t)(w & 0xff), y0 = (float)(int8_t)((w >> 8) & 0xff);
+    const float x1 = (float)(int8_t)((w >> 16) & 0xff), y1 = (float)(int8_t)(w >> 24);
+    const int t0 = bc[__float2int_rn(x0 * b + y0 * a) * pitch + __float2int_rn(x0 * a - y0 * b)];
+    const int t1 = bc[__float2int_rn(x1 * b + y1 * a) * pitch + __float2int_rn(x1 * a - y1 * b)];
     byte |= (t0 < t1) << k;
   }
 #endif
@@ -1056,6 +1070,11 @@ bool build_geometry(const cmos_orb* h, int w, int ht, GeomBuild* out) {
   g.ini_th = h->p.ini_th_fast;
   g.min_th = h->p.min_th_fast;
   for (int i = 0; i < 16; i++) g.umax[i] = h->umax[i];
+  for (int au = 0; au < 16; au++) {       // the disc u <= umax[|v|] read by columns: umax is non-increasing in |v|
+    int n = 0;                            // (ORBextractor.cc:455-468), so a column is the contiguous range of rows |v| <= vlim
+    while (n < 16 && au <= h->umax[n]) n++;
+    g.vlim[au] = n - 1;
+  }
   long long plane = 0, cand = 0;
   int kp = 0, maxn = 8;
   out->xoff.assign(nl, 0);

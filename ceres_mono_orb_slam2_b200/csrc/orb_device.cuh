@@ -37,6 +37,7 @@ struct OrbGeom {
   long long frame_bytes;   // pyramid bytes per frame
   long long cand_frame;    // candidate slots per frame
   int umax[16];
+  int vlim[16];            // vlim[|u|] = largest |v| with umax[|v|] >= |u|: column u of the centroid disc spans rows -vlim..vlim
   LevelGeom lv[kMaxLevels];
 };
 
