@@ -31,7 +31,8 @@ constexpr int kListCapPts = 8;
 // Frame::AssignFeaturesToGrid (Frame.cc:158-173) + PosInGrid (:309-320) as CSR, one CTA per frame.
 __global__ void __launch_bounds__(256) k_build_grid(cmos_camera cam, const cmos_keypoint* __restrict__ kps,
                                                     const int* __restrict__ counts, int stride, int max_kp,
-                                                    int* __restrict__ grid_start, int* __restrict__ grid_idx) {
+                                                    int* __restrict__ grid_start, int* __restrict__ grid_idx,
+                                                    float4* __restrict__ cells) {
   extern __shared__ int sm[];
   int* cnt = sm;                              // [kCells + 1]
   short* cell_of = (short*)(cnt + kCells + 1);   // [n]
@@ -89,12 +90,21 @@ __global__ void __launch_bounds__(256) k_build_grid(cmos_camera cam, const cmos_
       __syncwarp();
     }
   }
+  if (cells) {          // the keypoints in cell order, by every thread (octave < 128, i < 2^24: FrameDev::cells)
+    __syncthreads();
+    const int n_in = cnt[kCells];                   // keypoints inside the grid (the scan.s total; the cursors are cnt[0..kCells-1])
+    float4* cf = cells + (long long)f * max_kp;
+    for (int pos = tid; pos < n_in; pos += 256) {
+      const int i = gi[pos];
+      cf[pos] = make_float4(kp[i].x, kp[i].y, __int_as_float((kp[i].octave << 24) | i), 0.f);
+    }
+  }
 }
 
 int launch_build_grid(const cmos_camera& cam, const cmos_keypoint* kps, const int* counts, int stride, int max_kp,
-                      int* grid_start, int* grid_idx, int n_frames, cudaStream_t st) {
+                      int* grid_start, int* grid_idx, int n_frames, cudaStream_t st, float4* cells) {
   const size_t smem = (kCells + 1) * sizeof(int) + (size_t)stride * sizeof(short) + 16;
-  k_build_grid<<<n_frames, 256, smem, st>>>(cam, kps, counts, stride, max_kp, grid_start, grid_idx);
+  k_build_grid<<<n_frames, 256, smem, st>>>(cam, kps, counts, stride, max_kp, grid_start, grid_idx, cells);
   CMOS_CUDA_OK(cudaGetLastError());
   return CMOS_OK;
 }
@@ -114,6 +124,7 @@ struct SearchFrameArgs {
   uint8_t* claimed;                  // [B][stride] or null
   int* match;                        // [B][stride]
   int* nmatches;                     // [B]
+  const float4* cells;               // [B][max_kp] keypoints in cell order (FrameDev::cells), or null
 };
 
 struct QueryFrame { float u, v, radius; int oct; bool ok; };
@@ -165,7 +176,8 @@ __global__ void __launch_bounds__(kSfWarps * 32) k_sf_lists(
   if (q >= nq) return;
   const int n = min(counts[f], stride);
   FrameDev F{kps + (long long)f * stride, desc + (long long)f * stride * 32,
-             grid_start + (long long)f * (kCells + 1), grid_idx + (long long)f * max_kp, n};
+             grid_start + (long long)f * (kCells + 1), grid_idx + (long long)f * max_kp, n,
+             a.cells ? a.cells + (long long)f * max_kp : nullptr};
   const cmos_keypoint* last = a.last_kps + (long long)f * a.last_stride;
   const uint8_t flag = a.last_flags[(long long)f * a.last_stride + q];
   const size_t slot = (size_t)f * a.last_stride + q;
@@ -261,7 +273,8 @@ __global__ void __launch_bounds__(kReplayThreads) k_sf_replay(cmos_camera cam, c
   __shared__ int s_nmatch, s_nev, s_hist[CMOS_HISTO_LENGTH], s_keep[3], s_changed, s_nover;
 
   FrameDev F{kps + (long long)f * stride, desc + (long long)f * stride * 32,
-             grid_start + (long long)f * (kCells + 1), grid_idx + (long long)f * max_kp, n};
+             grid_start + (long long)f * (kCells + 1), grid_idx + (long long)f * max_kp, n,
+             a.cells ? a.cells + (long long)f * max_kp : nullptr};
   const cmos_keypoint* last = a.last_kps + (long long)f * a.last_stride;
   const double* lxw = a.last_xw + (long long)f * a.last_stride * 3;
   const uint8_t* ldesc = a.last_desc + (long long)f * a.last_stride * 32;
@@ -736,6 +749,7 @@ struct cmos_match {
   int launches = 0;
   // own device buffers
   int *d_grid_start = nullptr, *d_grid_idx = nullptr;
+  float4* d_cells = nullptr;          // keypoints in cell order (FrameDev::cells)
   uint32_t* g_lists = nullptr;     // HBM candidate lists of k_search_points (allocated on first use by a large local map)
   uint16_t* g_cnt = nullptr;
   uint32_t *d_lists = nullptr, *d_best = nullptr;   // SearchByProjection(frame,last) phase-1 results
@@ -814,6 +828,7 @@ int cmos_match_create(const cmos_match_params* params, cmos_match_t* out) {
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) err = cudaErrorUnknown;
   h->d_grid_start = dev_alloc<int>(B * (kCells + 1), &err);
   h->d_grid_idx = dev_alloc<int>(B * K, &err);
+  h->d_cells = dev_alloc<float4>(B * K, &err);
   h->d_lists = dev_alloc<uint32_t>(B * K * kListCap, &err);
   h->d_best = dev_alloc<uint32_t>(B * K, &err);
   h->d_cnt = dev_alloc<uint16_t>(B * K, &err);
@@ -857,7 +872,7 @@ int cmos_match_create(const cmos_match_params* params, cmos_match_t* out) {
 int cmos_match_destroy(cmos_match_t h) {
   if (!h) return CMOS_OK;
   cudaSetDevice(h->p.device);
-  void* bufs[] = {h->d_grid_start, h->d_grid_idx, h->d_lists, h->d_best, h->d_cnt, h->s_kps, h->s_last_kps, h->s_desc, h->s_last_desc, h->s_last_flags,
+  void* bufs[] = {h->d_grid_start, h->d_grid_idx, h->d_cells, h->d_lists, h->d_best, h->d_cnt, h->s_kps, h->s_last_kps, h->s_desc, h->s_last_desc, h->s_last_flags,
                   h->s_claimed, h->s_counts, h->s_last_counts, h->s_match, h->s_nmatches, h->s_last_xw, h->s_T,
                   h->s_np, h->s_level, h->s_in_view, h->s_pdesc, h->s_has_obs, h->s_view_cos, h->s_proj, h->s_mind,
                   h->s_maxd, h->s_pxw, h->s_pnormal, h->s_pose, h->g_lists, h->g_cnt};
@@ -895,7 +910,7 @@ int cmos_match_set_frames(cmos_match_t h, const cmos_camera* cam, const cmos_key
   NvtxRange nvtx_grid("cmos.match.build_grid");
   h->timer[0].begin(st);
   k_build_grid<<<n_frames, 256, smem, st>>>(h->cam, h->kps, h->counts, stride, h->p.max_keypoints, h->d_grid_start,
-                                            h->d_grid_idx);
+                                            h->d_grid_idx, h->d_cells);
   h->timer[0].mark(st);
   CMOS_CUDA_OK(cudaGetLastError());
   h->launches = 1;
@@ -933,6 +948,7 @@ int cmos_match_search_by_projection_frame(cmos_match_t h, const double* Tcw, con
   const size_t nl = (size_t)B * last_stride, nc = (size_t)B * h->stride;
   SearchFrameArgs a{};
   a.last_stride = last_stride; a.th = th; a.check_ori = check_orientation;
+  { const char* e = std::getenv("CMOS_MATCH_NO_CELLS"); a.cells = (e && e[0] == '1') ? nullptr : h->d_cells; }     // (A/B knob)
   if (on_device) {
     a.Tcw = Tcw; a.last_kps = last_keypoints; a.last_counts = last_counts; a.last_flags = last_flags;
     a.last_xw = last_xw; a.last_desc = last_descriptors; a.claimed = claimed; a.match = match; a.nmatches = nmatches;
