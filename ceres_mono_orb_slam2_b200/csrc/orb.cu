@@ -334,6 +334,10 @@ __device__ __forceinline__ int fast_arc_max(const uint8_t* __restrict__ p, int t
 #ifndef CMOS_FAST_MINBLOCKS
 #define CMOS_FAST_MINBLOCKS 12     // resident 128-thread CTAs per SM asked of the compiler: 40 registers, 0.273 -> 0.262 ms per 64 frames (16: 32 registers with spills, 0.259)
 #endif
+// ((1 << 20) + d - 1) / d for d = 0..32: i / d == (i * kMagic20[d]) >> 20 for i < 2^13 (an integer division costs ~20
+// instructions per thread; k_fast needed two per CTA pass)
+__device__ __constant__ unsigned kMagic20[33] = {0u, 1048576u, 524288u, 349526u, 262144u, 209716u, 174763u, 149797u, 131072u, 116509u, 104858u, 95326u, 87382u, 80660u, 74899u, 69906u, 65536u, 61681u, 58255u, 55189u, 52429u, 49933u, 47663u, 45591u, 43691u, 41944u, 40330u, 38837u, 37450u, 36158u, 34953u, 33826u, 32768u};
+
 template <int kThreads, int kTW, int kTH, int kCap>
 #if CMOS_FAST_MINBLOCKS > 0
 __global__ void __launch_bounds__(kThreads, CMOS_FAST_MINBLOCKS * 128 / kThreads) k_fast(
@@ -354,19 +358,27 @@ __global__ void __launch_bounds__(kThreads) k_fast(
   const int level = ce.x & 0xff, ci = (ce.x >> 8) & 0xfff, cj = (ce.x >> 20) & 0xfff;
   const int x0 = ce.y & 0xffff, y0 = ce.y >> 16, cw = ce.z & 0xffff, ch = ce.z >> 16;
   const LevelGeom& L = g.lv[level];
+  const int pitch = L.pitch;
   const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const uint8_t* plane = pyr + (long long)f * g.frame_bytes + L.plane_off;
-  const long long org = (long long)(y0 + kBorder) * L.pitch + kXOff + x0;
+  const long long org = (long long)(y0 + kBorder) * pitch + kXOff + x0;
   const int shift = (int)(org & 3);
   const int words = (shift + cw + 3) >> 2;
-  const unsigned wmagic = ((1u << 20) + words - 1) / words;      // i / words == (i * wmagic) >> 20 for i < 2^13
-
-  for (int i = tid; i < ch * words; i += kThreads) {
-    int r = (int)(((unsigned)i * wmagic) >> 20), w = i - r * words;
-    uint32_t v = __ldg((const uint32_t*)(plane + org - shift + (long long)r * L.pitch) + w);
-    *(uint32_t*)(tile + r * kTW + 4 * w) = v;
+  const uint8_t* src = plane + org - shift;
+  if (kTW <= 64) {
+    // rows of at most 16 words: a half warp per row, two rows per warp and step — no index division at all
+    const int w = lane & 15;
+    for (int r = (tid >> 4); r < ch; r += kThreads / 16)
+      if (w < words) *(uint32_t*)(tile + r * kTW + 4 * w) = __ldg((const uint32_t*)(src + (long long)r * pitch) + w);
+  } else {
+    const unsigned wmagic = kMagic20[words];      // i / words == (i * wmagic) >> 20 for i < 2^13
+    for (int i = tid; i < ch * words; i += kThreads) {
+      int r = (int)(((unsigned)i * wmagic) >> 20), w = i - r * words;
+      uint32_t v = __ldg((const uint32_t*)(src + (long long)r * pitch) + w);
+      *(uint32_t*)(tile + r * kTW + 4 * w) = v;
+    }
   }
-  for (int i = tid; i < ch * (kTW / 4); i += kThreads) ((uint32_t*)score)[i] = 0;
+  for (int i = tid; i < ch * (kTW / 16); i += kThreads) ((uint4*)score)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) { s_n = 0; s_npx = 0; }
   __syncthreads();
 
@@ -380,7 +392,8 @@ __global__ void __launch_bounds__(kThreads) k_fast(
     {
       const int c0 = shift + 3, w_first = c0 >> 2, nw = ((c0 + dw - 1) >> 2) - w_first + 1;
       const int items = npx > 0 ? dh * nw : 0;
-      const unsigned nmagic = ((1u << 20) + nw - 1) / nw;
+      const unsigned nmagic = kMagic20[nw];
+      const unsigned full_words_end = dw > 3 ? (unsigned)(dw - 3) : 0u;     // words with 0 <= xb < this have four detection pixels
       const unsigned addc = (0x80u - (unsigned)((th + 1) >> 1)) * 0x01010101u;
       const uint32_t* t32 = (const uint32_t*)tile;
       for (int base = 0; base < items; base += kThreads) {
@@ -400,9 +413,11 @@ __global__ void __launch_bounds__(kThreads) k_fast(
           hit = (g0 | g8) & (g4 | g12) & 0x80808080u;
           xb = 4 * wc - c0;                       // detection-area x of byte 0 of this word
           // bytes outside [0, dw) are not detection pixels
+          if ((unsigned)xb >= full_words_end) {                 // only the first / last word of a row can stick out
 #pragma unroll
-          for (int j = 0; j < 4; j++)
-            if ((unsigned)(xb + j) >= (unsigned)dw) hit &= ~(0x80u << (8 * j));
+            for (int j = 0; j < 4; j++)
+              if ((unsigned)(xb + j) >= (unsigned)dw) hit &= ~(0x80u << (8 * j));
+          }
         }
         if (__any_sync(0xffffffffu, hit != 0)) {
           const unsigned b0 = __ballot_sync(0xffffffffu, hit & 0x80u), b1 = __ballot_sync(0xffffffffu, hit & 0x8000u);
