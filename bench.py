@@ -379,6 +379,17 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------
 # GPU arm
 
+def e2e_block(forms, d2h, call, extra):
+    """forms: name -> (value, ms_per_step, h2d bytes per step, call).  The fastest form is the headline; all are listed."""
+    best = max(forms, key=lambda k: forms[k][0])
+    blk = {"value": forms[best][0], "unit": UNIT, "form": best, "h2d_bytes_per_step": forms[best][2],
+           "d2h_bytes_per_step": d2h, "ms_per_step": forms[best][1], "call": call}
+    for k, (v, ms, h2d, c) in forms.items():
+        blk[k] = {"value": v, "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": h2d, "call": c}
+    blk.update(extra)
+    return blk
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -453,9 +464,13 @@ def run_b200(args):
 
     # pipelined form of the same public call: cmos_track_submit / cmos_track_wait with two batches in flight (a second set
     # of page-locked output buffers), so batch k + 1 uploads while batch k computes and batch k - 1 downloads
-    h_kps2 = pin((B, cap * 28), torch.uint8); h_desc2 = pin((B, cap, 32), torch.uint8); h_counts2 = pin((B,), torch.int32)
-    h_match2 = pin((B, cap), torch.int32); h_nm2 = pin((B,), torch.int32)
-    e2e_out2 = (h_kps2.numpy().view(KP_DTYPE).reshape(B, cap), h_desc2.numpy(), h_counts2.numpy(), h_match2.numpy(), h_nm2.numpy())
+    def out_set():
+        k_ = pin((B, cap * 28), torch.uint8); d_ = pin((B, cap, 32), torch.uint8); c_ = pin((B,), torch.int32)
+        m_ = pin((B, cap), torch.int32); n_ = pin((B,), torch.int32)
+        return (k_.numpy().view(KP_DTYPE).reshape(B, cap), d_.numpy(), c_.numpy(), m_.numpy(), n_.numpy()), (k_, d_, c_, m_, n_)
+    depth = max(2, min(int(args.inflight), 4))       # batches in flight (cmos_track_submit allows 4)
+    e2e_sets = [(e2e_out, None)] + [out_set() for _ in range(depth - 1)]
+    e2e_outs = [s_[0] for s_ in e2e_sets]
 
     # compact form of the last-frame inputs (cmos_track_submit_points): one 64-byte record per last-frame keypoint that carries
     # a usable map point instead of 85 bytes for every keypoint slot — the end-to-end call is bound by the host->device copy
@@ -465,18 +480,39 @@ def run_b200(args):
     h_pts = h_pts_u8.numpy()[: len(pts) * 64].view(LAST_POINT_DTYPE); h_pts[:] = pts
     h_pstart = pin((B + 1,), torch.int32); h_pstart.numpy()[:] = pstart
 
-    def run_pipelined(n_steps, compact=True):
-        outs = (e2e_out, e2e_out2)
-        pending = None
+    submit_host_s = [0.0]            # host time spent inside the submit calls of the last run_pipelined
+
+    # third form (cmos_track_submit_map): the map points' positions and descriptors live in a device-resident table that is
+    # written when the map changes (per keyframe: LocalMapping / BA), not per frame; a step uploads 12-byte association records
+    # (last-frame keypoint -> map-point slot).  The table is filled ONCE, outside the timed region, like the map it mirrors.
+    from ceres_mono_orb_slam2_b200.tracking import ASSOC_DTYPE
+    h_assoc_u8 = pin((max(len(pts), 1) * 12,), torch.uint8)
+    h_assoc = h_assoc_u8.numpy()[: len(pts) * 12].view(ASSOC_DTYPE)
+    h_assoc["slot"] = np.arange(len(pts), dtype=np.int32); h_assoc["angle"] = pts["angle"]; h_assoc["index"] = pts["index"]
+    h_assoc["octave"] = pts["octave"]; h_assoc["flags"] = pts["flags"]
+    front.map_reserve(max(len(pts), 1))
+    if len(pts):
+        front.map_update(pts["xw"], pts["descriptor"])
+
+    def run_pipelined(n_steps, compact=True, form=None):
+        form = form or ("points" if compact else "arrays")
+        from collections import deque
+        pending = deque()
+        submit_host_s[0] = 0.0
         for i in range(n_steps):
-            if compact:
-                t = front.submit_points(h_images.numpy(), h_T.numpy(), h_pts, h_pstart.numpy(), TH_PROJ, out=outs[i & 1])
+            th0 = time.perf_counter()
+            if form == "map":
+                t = front.submit_map(h_images.numpy(), h_T.numpy(), h_assoc, h_pstart.numpy(), TH_PROJ, out=e2e_outs[i % depth])
+            elif form == "points":
+                t = front.submit_points(h_images.numpy(), h_T.numpy(), h_pts, h_pstart.numpy(), TH_PROJ, out=e2e_outs[i % depth])
             else:
-                t = front.submit(*e2e_in, TH_PROJ, out=outs[i & 1])
-            if pending is not None:
-                front.wait(pending)
-            pending = t
-        front.wait(pending)
+                t = front.submit(*e2e_in, TH_PROJ, out=e2e_outs[i % depth])
+            submit_host_s[0] += time.perf_counter() - th0
+            pending.append(t)
+            if len(pending) >= depth:
+                front.wait(pending.popleft())
+        while pending:
+            front.wait(pending.popleft())
 
     def barrier():
         if world > 1:
@@ -513,55 +549,65 @@ def run_b200(args):
     # The per-frame tail of a step (quadtree, grid, greedy replay: one CTA per frame, latency-bound, ~15 % of the step) leaves
     # most SMs idle; with S sub-batches in flight the tail of one runs under the heavy kernels of another.  Same work per
     # step (all B frames, same kernels, same results); the single-stream pass above stays as the per-stage measurement.
-    S = args.split if (args.split > 1 and B % args.split == 0) else 1
+    S = args.split if (args.split >= 1 and B % args.split == 0) else 1
+    D = max(1, min(int(args.depth), 8))      # consecutive steps run on D independent buffer sets (own streams): step i on set i % D
     ms_split = None
     split_launches = 0
-    if S > 1:
+    if S * D > 1:
         Bs = B // S
-        subs = []
-        for si in range(S):
-            e_s = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, max_batch=Bs, device=local_rank)
-            assert e_s.capacity == cap
-            m_s = ORBmatcher(0.9, True, max_batch=Bs, max_keypoints=cap, max_points=1, device=local_rank)
-            st_s = torch.cuda.Stream(device=dev)
-            sl = slice(si * Bs, (si + 1) * Bs)
-            kp_s, desc_s, cnt_s, _, _ = e_s.device_results()
-            subs.append(dict(ext=e_s, m=m_s, st=st_s, img=d_images[sl], T=d_T[sl], lk=d_lk[sl], lc=d_lcounts[sl], fl=d_flags[sl],
-                             xw=d_xw[sl], md=d_mdesc[sl], match=d_match[sl], nm=d_nm[sl], kp=kp_s, desc=desc_s, cnt=cnt_s))
+        sets = []
+        for di in range(D):
+            dm = torch.empty((B, cap), dtype=torch.int32, device=dev); dn = torch.zeros((B,), dtype=torch.int32, device=dev)
+            subs = []
+            for si in range(S):
+                e_s = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, max_batch=Bs, device=local_rank)
+                assert e_s.capacity == cap
+                m_s = ORBmatcher(0.9, True, max_batch=Bs, max_keypoints=cap, max_points=1, device=local_rank)
+                st_s = torch.cuda.Stream(device=dev)
+                sl = slice(si * Bs, (si + 1) * Bs)
+                kp_s, desc_s, cnt_s, _, _ = e_s.device_results()
+                subs.append(dict(ext=e_s, m=m_s, st=st_s, img=d_images[sl], T=d_T[sl], lk=d_lk[sl], lc=d_lcounts[sl], fl=d_flags[sl],
+                                 xw=d_xw[sl], md=d_mdesc[sl], match=dm[sl], nm=dn[sl], kp=kp_s, desc=desc_s, cnt=cnt_s))
+            sets.append(dict(subs=subs, nm=dn))
+        all_subs = [u for s_ in sets for u in s_["subs"]]
+        it = [0]
 
         def step_split():
-            for u in subs:
+            for u in sets[it[0] % D]["subs"]:
                 q = u["st"].cuda_stream
                 u["ext"].extract_device(u["img"], H * W, W, W, H, Bs, stream=q)
                 u["m"].set_frames(cam, u["kp"], u["desc"], u["cnt"], Bs, cap, on_device=True, stream=q)
                 u["m"].SearchByProjectionFrame(u["T"], u["lk"], u["lc"], u["fl"], u["xw"], u["md"], cap, TH_PROJ, claimed=None,
                                                out=(u["match"], u["nm"]), on_device=True, stream=q)
+            it[0] += 1
 
-        d_nm.zero_()
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(max(args.warmup, 3, D)):
             step_split()
         barrier()
+        it[0] = 0
         s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
         s0.record(stream)
-        for u in subs:
+        for u in all_subs:
             u["st"].wait_event(s0)
         for _ in range(args.steps):
             step_split()
-        for u in subs:
+        for u in all_subs:
             ev = torch.cuda.Event()
             ev.record(u["st"])
             stream.wait_event(ev)
         s1.record(stream)
         barrier()
         ms_split = s0.elapsed_time(s1)
-        assert int(d_nm.sum().item()) == nm_device, "sub-batched pass and single-stream pass disagree on the matches"
-        n_sub = 0
-        for u in subs:
-            c_s = np.zeros(Bs, np.int32)
-            u["ext"].download(Bs, out=(None, None, c_s))
-            n_sub += int(c_s.sum())
-            split_launches += u["ext"].launch_count() + 1 + u["m"].launch_count()
-        assert n_sub == feats_per_step, "sub-batched extraction differs from the single-stream pass"
+        for s_ in sets:
+            assert int(s_["nm"].sum().item()) == nm_device, "overlapped pass and single-stream pass disagree on the matches"
+        for s_ in sets:
+            n_sub = 0
+            for u in s_["subs"]:
+                c_s = np.zeros(Bs, np.int32)
+                u["ext"].download(Bs, out=(None, None, c_s))
+                n_sub += int(c_s.sum())
+            assert n_sub == feats_per_step, "overlapped extraction differs from the single-stream pass"
+        split_launches = sum(u["ext"].launch_count() + 1 + u["m"].launch_count() for u in sets[0]["subs"])
 
     # ---- end to end through the host-buffer C ABI ----
     for _ in range(2):
@@ -573,38 +619,41 @@ def run_b200(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     assert int(h_nm.sum().item()) == nm_device, "host-buffer path and device path disagree on the matches"
-    run_pipelined(2, compact=False)
-    barrier()
-    t0 = time.perf_counter()
-    run_pipelined(args.steps, compact=False)
-    barrier()
-    e2e_full_s = time.perf_counter() - t0
-    assert int(h_nm.sum().item()) == nm_device and int(h_nm2.sum().item()) == nm_device
-    match_full = h_match.numpy().copy()
-    run_pipelined(2)
-    barrier()
-    t0 = time.perf_counter()
-    run_pipelined(args.steps)
-    barrier()
-    e2e_pipe_s = time.perf_counter() - t0
-    assert int(h_nm.sum().item()) == nm_device and int(h_nm2.sum().item()) == nm_device
-    assert np.array_equal(h_match.numpy(), match_full), "compact and per-keypoint last-frame inputs disagree"
+    def time_form(form):
+        run_pipelined(max(2, depth), form=form)
+        barrier()
+        t0 = time.perf_counter()
+        run_pipelined(args.steps, form=form)
+        barrier()
+        dt = time.perf_counter() - t0
+        assert all(int(o_[4].sum()) == nm_device for o_ in e2e_outs), form
+        return dt, h_match.numpy().copy(), submit_host_s[0] * 1e3 / args.steps
+
+    order = ["arrays", "points", "map"]
+    if os.environ.get("CMOS_BENCH_E2E_REVERSE"):      # diagnostic: does the position in the run matter?
+        order.reverse()
+    timed = {form: time_form(form) for form in order}
+    e2e_full_s, match_full, submit_host_ms = timed["arrays"]
+    e2e_pipe_s, e2e_map_s = timed["points"][0], timed["map"][0]
+    assert np.array_equal(timed["points"][1], match_full), "compact and per-keypoint last-frame inputs disagree"
+    assert np.array_equal(timed["map"][1], match_full), "map-table and per-keypoint last-frame inputs disagree"
     clocks = sampler.stop()
 
     ms_single = ms
     if ms_split is not None:
         ms = ms_split
-    t = torch.tensor([ms, e2e_s * 1e3, e2e_pipe_s * 1e3, ms_single, e2e_full_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, e2e_pipe_s * 1e3, ms_single, e2e_full_s * 1e3, e2e_map_s * 1e3], dtype=torch.float64, device=dev)
     tot = torch.tensor([feats_per_step], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_max, e2e_ms_max, e2e_pipe_ms_max, ms_single_max, e2e_full_ms_max = (float(t[i]) for i in range(5))
+    ms_max, e2e_ms_max, e2e_pipe_ms_max, ms_single_max, e2e_full_ms_max, e2e_map_ms_max = (float(t[i]) for i in range(6))
     feats_all = float(tot[0])
     value = feats_all * args.steps / (ms_max * 1e-3) / 1e6
     e2e_sync_value = feats_all * args.steps / (e2e_ms_max * 1e-3) / 1e6
     e2e_value = feats_all * args.steps / (e2e_pipe_ms_max * 1e-3) / 1e6
     e2e_arrays_value = feats_all * args.steps / (e2e_full_ms_max * 1e-3) / 1e6
+    e2e_map_value = feats_all * args.steps / (e2e_map_ms_max * 1e-3) / 1e6
 
     if rank == 0:
         peaks = {}
@@ -644,8 +693,9 @@ def run_b200(args):
                        "l2": "no explicit flush: one step touches ~%d MB (images + pyramid + blurred pyramid) > 126 MB L2"
                              % ((B * (H * W) + 2 * B * 1738559) // 1000000),
                        "parallelism": f"frames sharded, {world} rank(s), no collective on the data path",
-                       "sub_batches": (f"{S} sub-batches of {B // S} frames on {S} CUDA streams (the per-frame latency-bound "
-                                       f"kernels of one run under the heavy kernels of another)") if S > 1 else "none (one stream)"},
+                       "sub_batches": (f"each step = {S} sub-batch(es) of {B // S} frames on own CUDA streams, consecutive steps on {D} "
+                                       f"independent buffer set(s) ({S * D} streams in all): the per-frame latency-bound kernels of "
+                                       f"one run under the heavy kernels of another") if S * D > 1 else "none (one stream)"},
             "single_stream": {"value": feats_all * args.steps / (ms_single_max * 1e-3) / 1e6, "unit": UNIT,
                               "ms_per_step": single_step_ms,
                               "note": "the same K steps with the whole batch on ONE stream; roofline.stage_ms was measured in this pass"},
@@ -660,34 +710,33 @@ def run_b200(args):
                          "whole_step": {"algorithmic_bytes": alg["frame_total"] * B,
                                         "achieved": alg["frame_total"] * B / (step_ms * 1e-3) / 1e9,
                                         "frac": alg["frame_total"] * B / (step_ms * 1e-3) / 1e9 / peak}},
-            # Two forms of the same public call, both timed in this run, identical results (asserted above): the last-frame inputs
-            # as per-keypoint arrays (85 B per keypoint slot) or as packed records (64 B per usable map point).  Fewer bytes win
-            # where the host->device path is the limit (several GPUs behind one host), fewer launches win on one GPU; the
-            # headline is the faster one of THIS run and `form` says which, the other one is reported beside it.
-            "e2e": {"value": max(e2e_value, e2e_arrays_value), "unit": UNIT,
-                    "form": "packed_records" if e2e_value >= e2e_arrays_value else "per_keypoint_arrays",
-                    "h2d_bytes_per_step": (int(h_images.numel() + h_T.numel() * 8 + len(pts) * 64 + h_pstart.numel() * 4)
-                                           if e2e_value >= e2e_arrays_value else
-                                           int(h_images.numel() + h_flags.numel() + h_xw.numel() * 8 + h_mdesc.numel() +
-                                               h_T.numel() * 8 + h_lk_u8.numel() + h_lcounts.numel() * 4)),
-                    "d2h_bytes_per_step": int(h_kps_u8.numel() + h_desc.numel() + h_counts.numel() * 4 +
-                                              h_match.numel() * 4 + h_nm.numel() * 4),
-                    "ms_per_step": min(e2e_pipe_ms_max, e2e_full_ms_max) / args.steps,
-                    "call": f"cmos_track_submit[_points] / cmos_track_wait, two 64-frame batches in flight: {args.lanes} stream lanes x "
-                            f"chunks of {args.chunk} frames, pinned host buffers, every step uploads its images, poses and last-frame "
-                            f"inputs and downloads its keypoints / descriptors / matches",
-                    "packed_records": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_pipe_ms_max / args.steps,
-                                       "h2d_bytes_per_step": int(h_images.numel() + h_T.numel() * 8 + len(pts) * 64 + h_pstart.numel() * 4),
-                                       "call": "cmos_track_submit_points: one 64-byte record per last-frame keypoint with a usable map point"},
-                    "per_keypoint_arrays": {"value": e2e_arrays_value, "unit": UNIT, "ms_per_step": e2e_full_ms_max / args.steps,
-                                            "h2d_bytes_per_step": int(h_images.numel() + h_flags.numel() + h_xw.numel() * 8 +
-                                                                      h_mdesc.numel() + h_T.numel() * 8 + h_lk_u8.numel() +
-                                                                      h_lcounts.numel() * 4),
-                                            "call": "cmos_track_submit: per-keypoint arrays (85 bytes per keypoint slot)"},
-                    "synchronous": {"value": e2e_sync_value, "unit": UNIT, "ms_per_step": e2e_ms_max / args.steps,
-                                    "call": "cmos_track_frames (submit + wait per batch: pipeline fill and drain paid every call)"},
-                    "gpu_launches_per_step": front.launch_count()},
-            "gpu_launches": (split_launches if S > 1 else ext.launch_count() + 1 + matcher.launch_count()) * args.steps,
+            # Three forms of the same public call, all timed in this run, identical results (asserted above): the last-frame
+            # inputs as per-keypoint arrays (85 B per keypoint slot), as packed records (64 B per usable map point), or as
+            # 12-byte association records into a device-resident map-point table.  The headline is the fastest one of THIS run
+            # and `form` says which; the others are reported beside it.
+            "e2e": e2e_block(
+                {"per_keypoint_arrays": (e2e_arrays_value, e2e_full_ms_max / args.steps,
+                                         int(h_images.numel() + h_flags.numel() + h_xw.numel() * 8 + h_mdesc.numel() +
+                                             h_T.numel() * 8 + h_lk_u8.numel() + h_lcounts.numel() * 4),
+                                         "cmos_track_submit: per-keypoint arrays (85 bytes per keypoint slot)"),
+                 "packed_records": (e2e_value, e2e_pipe_ms_max / args.steps,
+                                    int(h_images.numel() + h_T.numel() * 8 + len(pts) * 64 + h_pstart.numel() * 4),
+                                    "cmos_track_submit_points: one 64-byte record per last-frame keypoint with a usable map point"),
+                 "map_associations": (e2e_map_value, e2e_map_ms_max / args.steps,
+                                      int(h_images.numel() + h_T.numel() * 8 + len(pts) * 12 + h_pstart.numel() * 4),
+                                      "cmos_track_submit_map: one 12-byte record (keypoint -> map-point slot) per usable last-frame "
+                                      "keypoint; positions and descriptors of the map points are read from the device-resident "
+                                      "table (cmos_track_map_update: written when the map changes, i.e. per keyframe — filled once "
+                                      f"before the timed region here, {len(pts) * 56} bytes)")},
+                d2h=int(h_kps_u8.numel() + h_desc.numel() + h_counts.numel() * 4 + h_match.numel() * 4 + h_nm.numel() * 4),
+                call=f"cmos_track_submit[_points|_map] / cmos_track_wait, {depth} 64-frame batches in flight: {args.lanes} stream lanes x "
+                     f"chunks of {args.chunk} frames, pinned host buffers, every step uploads its images, poses and last-frame "
+                     f"inputs and downloads its keypoints / descriptors / matches",
+                extra={"synchronous": {"value": e2e_sync_value, "unit": UNIT, "ms_per_step": e2e_ms_max / args.steps,
+                                       "call": "cmos_track_frames (submit + wait per batch: pipeline fill and drain paid every call)"},
+                       "host_submit_ms_per_step": submit_host_ms,
+                       "gpu_launches_per_step": front.launch_count()}),
+            "gpu_launches": (split_launches if S * D > 1 else ext.launch_count() + 1 + matcher.launch_count()) * args.steps,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
@@ -771,8 +820,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--lanes", type=int, default=8, help="stream lanes of the end-to-end front-end call")
-    ap.add_argument("--chunk", type=int, default=16, help="frames per pipelined chunk of the end-to-end call")
-    ap.add_argument("--split", type=int, default=4, help="sub-batches (own CUDA stream each) of the device-resident pass; 1 = off")
+    ap.add_argument("--inflight", type=int, default=4, help="batches in flight of the pipelined end-to-end call (2..4)")
+    ap.add_argument("--chunk", type=int, default=32, help="frames per pipelined chunk of the end-to-end call")
+    ap.add_argument("--split", type=int, default=1, help="sub-batches (own CUDA stream each) of the device-resident pass; 1 = off")
+    ap.add_argument("--depth", type=int, default=3, help="device-resident pass: consecutive steps on this many independent buffer sets")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ba", action="store_true", help="skip the bundle-adjustment section")

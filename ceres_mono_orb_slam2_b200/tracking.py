@@ -33,6 +33,25 @@ def pack_last_points(last_keypoints, last_counts, last_flags, last_xw, last_desc
     return np.concatenate(recs) if recs else np.zeros(0, LAST_POINT_DTYPE), np.array(start, np.int32)
 
 
+ASSOC_DTYPE = np.dtype([("slot", "<i4"), ("angle", "<f4"), ("index", "<u2"), ("octave", "i1"), ("flags", "u1")])
+assert ASSOC_DTYPE.itemsize == 12           # == sizeof(cmos_track_assoc)
+
+
+def pack_map_associations(last_keypoints, last_counts, last_flags, slots):
+    """Per-keypoint last-frame arrays [B,S] + the map-point slot of every keypoint (slots [B,S], read where flag bit 0 is set) ->
+    (records, assoc_start): one cmos_track_assoc per usable keypoint, frame after frame, in increasing keypoint index."""
+    B = len(last_counts)
+    recs, start = [], [0]
+    for f in range(B):
+        n = int(last_counts[f])
+        idx = np.nonzero(last_flags[f, :n] & 1)[0]
+        r = np.zeros(len(idx), ASSOC_DTYPE)
+        r["slot"] = slots[f, idx]; r["angle"] = last_keypoints["angle"][f, idx]; r["index"] = idx
+        r["octave"] = last_keypoints["octave"][f, idx]; r["flags"] = last_flags[f, idx]
+        recs.append(r); start.append(start[-1] + len(idx))
+    return np.concatenate(recs) if recs else np.zeros(0, ASSOC_DTYPE), np.array(start, np.int32)
+
+
 class TrackParams(C.Structure):
     _fields_ = [("orb", OrbParams), ("lanes", C.c_int32), ("chunk_frames", C.c_int32)]
 
@@ -105,6 +124,35 @@ class TrackingFrontEnd:
         check(self._L.cmos_track_submit_points(self._h, ptr(images), C.c_int64(H * W), W, W, H, B, ptr(Tcw), ptr(points),
                                                ptr(point_start), C.c_float(th), int(self.check_ori), ptr(kps), ptr(desc),
                                                ptr(counts), cap, ptr(match), ptr(nm), C.byref(t)))
+        return t.value
+
+    def map_reserve(self, n_slots: int):
+        """Size the device-resident map-point table (cmos_track_map_reserve); growing keeps the slots already written."""
+        check(self._L.cmos_track_map_reserve(self._h, int(n_slots)))
+
+    def map_update(self, xw, descriptors, slots=None, first_slot: int = 0):
+        """Write map points into the table (cmos_track_map_update): xw [n,3] float64, descriptors [n,32] uint8 into `slots` [n]
+        int32, or into first_slot .. first_slot + n - 1 when slots is None.  Waits for the batches in flight."""
+        xw = np.ascontiguousarray(xw, np.float64); descriptors = np.ascontiguousarray(descriptors, np.uint8)
+        n = len(xw)
+        assert xw.shape == (n, 3) and descriptors.shape == (n, 32)
+        sp = None
+        if slots is not None:
+            slots = np.ascontiguousarray(slots, np.int32)
+            assert slots.shape == (n,)
+            sp = ptr(slots)
+        check(self._L.cmos_track_map_update(self._h, n, sp, int(first_slot), ptr(xw), ptr(descriptors)))
+
+    def submit_map(self, images, Tcw, assoc, assoc_start, th: float, out):
+        """submit() with the last-frame inputs as 12-byte association records into the device-resident map-point table
+        (cmos_track_submit_map; pack_map_associations builds them).  Same results as submit()."""
+        B, H, W = images.shape
+        kps, desc, counts, match, nm = out
+        cap = match.shape[1]
+        t = C.c_int64(-1)
+        check(self._L.cmos_track_submit_map(self._h, ptr(images), C.c_int64(H * W), W, W, H, B, ptr(Tcw), ptr(assoc),
+                                            ptr(assoc_start), C.c_float(th), int(self.check_ori), ptr(kps), ptr(desc),
+                                            ptr(counts), cap, ptr(match), ptr(nm), C.byref(t)))
         return t.value
 
     def wait(self, ticket: int):

@@ -456,6 +456,35 @@ int cmos_track_submit_points(cmos_track_t h, const uint8_t* images, int64_t fram
                              uint8_t* descriptors, int32_t* counts, int32_t capacity, int32_t* match, int32_t* nmatches,
                              int64_t* ticket);
 
+/* Device-resident map points.  The reference's search reads pMP->GetWorldPos() / GetDescriptor() of every map point the last
+ * frame holds (src/ORBmatcher.cc:1183, :1211) out of the Map in host memory; a map point changes when LocalMapping / BA moves it
+ * (MapPoint::SetWorldPos, src/MapPoint.cc:112) or MapPoint::ComputeDistinctiveDescriptors picks another descriptor
+ * (src/MapPoint.cc:256), i.e. per keyframe, not per frame.
+ * The table mirrors those two fields on the device, one slot per map point (the caller's numbering, e.g. an index it keeps beside
+ * MapPoint::id_): cmos_track_map_reserve sizes it (growing keeps the contents), cmos_track_map_update writes n slots — the
+ * slots listed in `slots`, or first_slot .. first_slot + n - 1 when `slots` is NULL — from host arrays xw [n][3] and
+ * descriptors [n][32].  Both calls wait for the batches in flight and return when the table is updated.
+ * cmos_track_submit_map is cmos_track_submit_points with 12-byte association records instead of 64-byte ones: per frame the
+ * upload names which last-frame keypoint holds which slot (records of frame f: assoc[assoc_start[f] .. assoc_start[f+1]), in
+ * increasing keypoint index); position and descriptor come from the table.  Records whose slot lies outside the table are
+ * treated as keypoints without a map point.  Results are identical to cmos_track_submit on the arrays the records and the
+ * table were taken from. */
+typedef struct cmos_track_assoc {
+  int32_t slot;            /* map-point slot in the device table */
+  float angle;             /* LastFrame.undistort_keypoints_[index].angle */
+  uint16_t index;          /* keypoint index in the last frame */
+  int8_t octave;           /* LastFrame.undistort_keypoints_[index].octave */
+  uint8_t flags;           /* bit0 set (usable), bit1: the point has Observations() > 0 */
+} cmos_track_assoc;        /* 12 bytes */
+int cmos_track_map_reserve(cmos_track_t h, int32_t n_slots);
+int cmos_track_map_update(cmos_track_t h, int32_t n, const int32_t* slots, int32_t first_slot, const double* xw,
+                          const uint8_t* descriptors);
+int cmos_track_submit_map(cmos_track_t h, const uint8_t* images, int64_t frame_stride, int32_t pitch, int32_t width,
+                          int32_t height, int32_t n_frames, const double* Tcw, const cmos_track_assoc* assoc,
+                          const int32_t* assoc_start, float th, int32_t check_orientation, cmos_keypoint* keypoints,
+                          uint8_t* descriptors, int32_t* counts, int32_t capacity, int32_t* match, int32_t* nmatches,
+                          int64_t* ticket);
+
 /* Kernels launched by the last cmos_track_frames / cmos_track_submit call. */
 int cmos_track_last_launch_count(cmos_track_t h, int32_t* n);
 

@@ -351,6 +351,49 @@ def test_tracking_front_end_equals_unfused_calls(lanes, chunk):
             n = int(counts[f])
             assert np.array_equal(k2[f, :n], kps[f, :n]) and np.array_equal(m2[f, :n], match2[f, :n])
     assert nm2[B // 2] == 0 and nm2.sum() > 100 * (B - 1)
+    # device-resident map points (cmos_track_map_reserve / _update + cmos_track_submit_map): 12-byte association records, position
+    # and descriptor gathered from the table; slots are a permutation of the usable keypoints, the table is filled in two steps
+    # (a run of consecutive slots, then a slot list after growing it); one record points outside the table
+    from ceres_mono_orb_slam2_b200.tracking import pack_map_associations
+    rng = np.random.default_rng(77)
+    usable = np.argwhere(fl2 & 1)                               # (frame, keypoint) of every usable map point
+    n_mp = len(usable)
+    perm = rng.permutation(n_mp).astype(np.int32)
+    slots = np.full((B, cap), -1, np.int32); slots[usable[:, 0], usable[:, 1]] = perm
+    t_xw = np.zeros((n_mp, 3)); t_desc = np.zeros((n_mp, 32), np.uint8)
+    t_xw[perm] = xw[usable[:, 0], usable[:, 1]]; t_desc[perm] = mdesc[usable[:, 0], usable[:, 1]]
+    with pytest.raises(CmosError):
+        fe.submit_map(frames, T, np.zeros(1, np.uint8), np.zeros(B + 1, np.int32), 15.0, out=o)    # no table yet
+    half = n_mp // 2
+    fe.map_reserve(half)
+    fe.map_update(t_xw[:half], t_desc[:half])
+    with pytest.raises(CmosError):
+        fe.map_update(t_xw[:1], t_desc[:1], slots=np.array([half], np.int32))                     # outside the table
+    fe.map_reserve(n_mp)                                        # grows, keeps the first half
+    rest = rng.permutation(np.arange(half, n_mp)).astype(np.int32)
+    fe.map_update(t_xw[rest], t_desc[rest], slots=rest)
+    lost = usable[n_mp // 3]                                    # this keypoint's record gets a slot outside the table
+    slots[lost[0], lost[1]] = n_mp + 5
+    fl3 = fl2.copy(); fl3[lost[0], lost[1]] = 0
+    match3, nm3 = m.SearchByProjectionFrame(T, lk, lcounts, fl3, xw, mdesc, cap, 15.0)
+    assoc, astart = pack_map_associations(lk, lcounts, fl2, slots)
+    assert assoc.nbytes == 12 * n_mp and np.array_equal(astart, pstart)
+    for _ in range(2):
+        o = (np.zeros((B, cap), KP_DTYPE), np.zeros((B, cap, 32), np.uint8), np.zeros(B, np.int32),
+             np.full((B, cap), -1, np.int32), np.zeros(B, np.int32))
+        fe.wait(fe.submit_map(frames, T, assoc, astart, 15.0, out=o))
+        k2, d2, c2, m2, n2 = o
+        assert np.array_equal(c2, counts) and np.array_equal(n2, nm3)
+        for f in range(B):
+            n = int(counts[f])
+            assert np.array_equal(k2[f, :n], kps[f, :n]) and np.array_equal(m2[f, :n], match3[f, :n])
+    # a moved map point: the table entry changes, the records stay
+    mv = usable[n_mp // 2]
+    xw4 = xw.copy(); xw4[mv[0], mv[1]] += np.array([0.4, -0.3, 0.2])
+    fe.map_update(xw4[mv[0], mv[1]][None], mdesc[mv[0], mv[1]][None], slots=np.array([slots[mv[0], mv[1]]], np.int32))
+    match4, nm4 = m.SearchByProjectionFrame(T, lk, lcounts, fl3, xw4, mdesc, cap, 15.0)
+    fe.wait(fe.submit_map(frames, T, assoc, astart, 15.0, out=o))
+    assert np.array_equal(o[4], nm4) and all(np.array_equal(o[3][f, :int(counts[f])], match4[f, :int(counts[f])]) for f in range(B))
 
 
 def test_undistort_keypoints_and_distorted_bounds():
