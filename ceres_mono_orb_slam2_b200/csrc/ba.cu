@@ -113,7 +113,7 @@ __device__ bool chol6_solve(double A[6][6], double* b) {
   return true;
 }
 
-__global__ void __launch_bounds__(kPoseThreads) k_pose_opt(PoseArgs a) {
+__global__ void __launch_bounds__(kPoseThreads) k_pose_opt(PoseArgs a) { pdl_begin();
   __shared__ double s_pose[2][7];
   __shared__ double s_red[kPoseThreads / 32][28];
   __shared__ double s_acc[28];        // 21 H (packed upper) | 6 g | cost
@@ -306,7 +306,7 @@ __device__ __forceinline__ double huber_eval(double s, double a, double* w) {
   return 0.5 * s;
 }
 
-__global__ void __launch_bounds__(kPoseThreads) k_sim3_opt(Sim3Args a) {
+__global__ void __launch_bounds__(kPoseThreads) k_sim3_opt(Sim3Args a) { pdl_begin();
   __shared__ double s_x[2][7];
   __shared__ Sim3D s_S, s_Si;            // exp(x) and its inverse for the point being evaluated
   __shared__ double s_red[kPoseThreads / 32][36];
@@ -524,7 +524,7 @@ struct BaDev {
 
 // `pad` of LmState doubles as the "aborted" flag: LocalBundleAdjustment returns without writing anything back
 // when the stop flag is up at the start of a pass (CeresOptimizer.cc:509-512).
-__global__ void k_lm_init(BaDev d, int max_iterations) {
+__global__ void k_lm_init(BaDev d, int max_iterations) { pdl_begin();
   const int cur = d.st->cur, aborted = d.st->pad;
   lm_init(*d.st, max_iterations, cur & 1);
   d.st->pad = aborted;
@@ -540,7 +540,7 @@ __device__ __forceinline__ void dbg_raise_stop(const BaDev& d, const LmState& st
 __device__ void post_lin_body(const BaDev& d, LmState& st, int phase, double* scratch);
 __device__ void decide_body(const BaDev& d, LmState& st, int phase, double* scratch);
 
-__global__ void __launch_bounds__(kLinThreads) k_linearize(BaDev d) {
+__global__ void __launch_bounds__(kLinThreads) k_linearize(BaDev d) { pdl_begin();
   __shared__ double scratch[33];
   const LmState& st = *d.st;
   if (st.done || !st.need_lin) return;
@@ -626,7 +626,7 @@ __device__ void cam_finish(const BaDev& d, const LmState& st, int a) {
   d.part[d.o_cam_xn2 + a] = xn2;
 }
 
-__global__ void __launch_bounds__(kCamThreads) k_cam_blocks(BaDev d) {
+__global__ void __launch_bounds__(kCamThreads) k_cam_blocks(BaDev d) { pdl_begin();
   __shared__ double s_red[kCamThreads / 32][27];     // 108 doubles; reused as the 33-double scratch of the fused tail
   const LmState& st = *d.st;
   if (st.done || !st.need_lin) return;
@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_blocks(BaDev d) {
 }
 
 // Jacobi scale, gradient norm and parameter norm of one variable keyframe from its (global) H_cc, g_c
-__global__ void __launch_bounds__(128) k_cam_finish(BaDev d) {
+__global__ void __launch_bounds__(128) k_cam_finish(BaDev d) { pdl_begin();
   const LmState& st = *d.st;
   if (st.done || !st.need_lin) return;
   const int a = blockIdx.x * 128 + threadIdx.x;
@@ -734,7 +734,7 @@ __device__ void post_lin_body(const BaDev& d, LmState& st, int phase, double* sc
     }
   }
 }
-__global__ void __launch_bounds__(256) k_post_lin(BaDev d, int phase) {
+__global__ void __launch_bounds__(256) k_post_lin(BaDev d, int phase) { pdl_begin();
   __shared__ double scratch[33];
   LmState& st = *d.st;
   if (st.done) return;
@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(256) k_post_lin(BaDev d, int phase) {
   post_lin_body(d, st, phase, scratch);
 }
 
-__global__ void __launch_bounds__(kLinThreads) k_point_prep(BaDev d) {
+__global__ void __launch_bounds__(kLinThreads) k_point_prep(BaDev d) { pdl_begin();
   LmState& st = *d.st;
   if (st.done) return;
   const int j = blockIdx.x * kLinThreads + threadIdx.x;
@@ -838,7 +838,7 @@ __device__ __forceinline__ void schur_pair(const BaDev& d, const int e, const do
 // observation pairs, warp shuffles + a fixed-order cross-warp sum reduce the 6x6 (+ rhs); writes the
 // lower-triangle copy S[b][a].
 constexpr int kSchurThreads = 128;
-__global__ void __launch_bounds__(kSchurThreads) k_schur(BaDev d) {
+__global__ void __launch_bounds__(kSchurThreads) k_schur(BaDev d) { pdl_begin();
   __shared__ double s_part[kSchurThreads / 32][42];
   const LmState& st = *d.st;
   if (st.done) return;
@@ -901,7 +901,7 @@ constexpr int kSchurPart = 42;             // 36 block entries + 6 rhs entries p
 #ifndef CMOS_SCHUR_MINB
 #define CMOS_SCHUR_MINB 1   // resident CTAs per SM the register allocation must allow (A/B: tools/build_variant.sh)
 #endif
-__global__ void __launch_bounds__(32 * kSchurWarps, CMOS_SCHUR_MINB) k_schur_chunks(BaDev d) {
+__global__ void __launch_bounds__(32 * kSchurWarps, CMOS_SCHUR_MINB) k_schur_chunks(BaDev d) { pdl_begin();
   const LmState& st = *d.st;
   if (st.done) return;
   const int lane = threadIdx.x & 31, chunk = blockIdx.x * kSchurWarps + (threadIdx.x >> 5);
@@ -970,7 +970,7 @@ __device__ __forceinline__ double schur_combined(const BaDev& d, const LmState& 
   return (d.is_root ? d.scale_c[6 * (size_t)a + k] * d.gc[6 * (size_t)a + k] : 0.0) - sum;
 }
 
-__global__ void __launch_bounds__(256) k_schur_combine(BaDev d) {
+__global__ void __launch_bounds__(256) k_schur_combine(BaDev d) { pdl_begin();
   const LmState& st = *d.st;
   if (st.done) return;
   const int t = blockIdx.x * 256 + threadIdx.x;
@@ -1492,7 +1492,7 @@ __device__ __forceinline__ void factor_and_solve(double* __restrict__ L, double*
   if (!*s_fail) back_substitute24(L, L + n * (n + 1) / 2, s_x, n);
 }
 
-__global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
+__global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) { pdl_begin();
   extern __shared__ __align__(16) double smem_d[];
   LmState& st = *d.st;
   if (st.done) return;
@@ -1553,7 +1553,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_small(BaDev d) {
 // Test tap of the small dense solver (cmos_debug_solve_spd): A x = b through exactly the device code k_solve_small and
 // k_cr_factor run — factor_and_invert24 + back_substitute24 — on a caller-supplied SPD matrix.
 __global__ void __launch_bounds__(kSolveThreads) k_debug_solve_spd(const double* __restrict__ A, const double* __restrict__ b, int n,
-                                                                   double* __restrict__ x, int* fail, long long* cycles, int whole) {
+                                                                   double* __restrict__ x, int* fail, long long* cycles, int whole) { pdl_begin();
   extern __shared__ __align__(16) double smem_d[];
   const int tid = threadIdx.x;
   double* L = smem_d;
@@ -1585,7 +1585,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_debug_solve_spd(const double*
   if (tid == 0) { *fail = s_fail; cycles[0] = t1 - t0; cycles[1] = t2 - t1; }
 }
 
-__global__ void __launch_bounds__(kLinThreads) k_backsub(BaDev d) {
+__global__ void __launch_bounds__(kLinThreads) k_backsub(BaDev d) { pdl_begin();
   __shared__ double scratch[33];
   const LmState& st = *d.st;
   if (st.done) return;
@@ -1685,7 +1685,7 @@ __device__ void decide_body(const BaDev& d, LmState& st, int phase, double* scra
     }
   }
 }
-__global__ void __launch_bounds__(256) k_decide(BaDev d, int phase) {
+__global__ void __launch_bounds__(256) k_decide(BaDev d, int phase) { pdl_begin();
   __shared__ double scratch[33];
   LmState& st = *d.st;
   if (st.done) return;
@@ -1696,7 +1696,7 @@ __global__ void __launch_bounds__(256) k_decide(BaDev d, int phase) {
 // per-observation loss mode of the next pass (quirk Q2) and copies the pass summary out.
 __global__ void __launch_bounds__(256) k_outlier_scan(BaDev d, const uint8_t* __restrict__ cam_flags,
                                                       const int* __restrict__ perm, uint8_t* __restrict__ erase,
-                                                      int set_mode) {
+                                                      int set_mode) { pdl_begin();
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= d.N) return;
   const int cur = d.st->cur;
@@ -1713,7 +1713,7 @@ __global__ void __launch_bounds__(256) k_outlier_scan(BaDev d, const uint8_t* __
   if (set_mode) d.o_mode[p] = e ? 1 : 3;
 }
 
-__global__ void k_set_mode(BaDev d, int mode) {
+__global__ void k_set_mode(BaDev d, int mode) { pdl_begin();
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p < d.N) d.o_mode[p] = (uint8_t)mode;
 }
@@ -1721,7 +1721,7 @@ __global__ void k_set_mode(BaDev d, int mode) {
 // StopFlagCallback returns SOLVER_TERMINATE_SUCCESSFULLY (CeresOptimizer.h:340): ceres::Solve ends with USER_SUCCESS, a usable
 // solution, so the parameter blocks keep the iterate reached when the flag was seen — nothing is rolled back.  What discards
 // work is the reference's own `if (*stop_flag) return;` at the start of a LocalBundleAdjustment pass (`pad` above).
-__global__ void k_summary(BaDev d, cmos_ba_summary* out) {
+__global__ void k_summary(BaDev d, cmos_ba_summary* out) { pdl_begin();
   const LmState& st = *d.st;
   cmos_ba_summary s;
   s.iterations = st.iteration; s.successful_steps = st.successful; s.termination = st.termination;
@@ -1730,14 +1730,14 @@ __global__ void k_summary(BaDev d, cmos_ba_summary* out) {
 }
 
 // final parameters always end up in buffer 0 of the handle's "result" view
-__global__ void k_gather_result(BaDev d, const double* cams0, const double* pts0, double* cams_out, double* pts_out) {
+__global__ void k_gather_result(BaDev d, const double* cams0, const double* pts0, double* cams_out, double* pts_out) { pdl_begin();
   const int cur = d.st->cur, aborted = d.st->pad;
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i < 7 * d.K) cams_out[i] = aborted ? cams0[i] : d.cams[cur][i];
   if (i < 3 * d.M) pts_out[i] = aborted ? pts0[i] : d.pts[cur][i];
 }
 
-__global__ void __launch_bounds__(256) k_scatter_S(BaDev d) {
+__global__ void __launch_bounds__(256) k_scatter_S(BaDev d) { pdl_begin();
   if (d.st->done) return;
   const int e = blockIdx.x * 256 + threadIdx.x;
   if (e >= d.n_blocks * 36) return;
@@ -1756,7 +1756,7 @@ __global__ void __launch_bounds__(256) k_scatter_S(BaDev d) {
 // Right-looking on the UNSCALED columns — A[i][k] -= A[i][j] A[k][j] / A[j][j] needs one barrier per column and no
 // square root on the critical path; column j is scaled by rsqrt(A[j][j]) once, at the end.
 constexpr int kPotrfThreads = 1024;
-__global__ void __launch_bounds__(kPotrfThreads) k_potrf_diag(BaDev d, int k0, int kb, double* Linv) {
+__global__ void __launch_bounds__(kPotrfThreads) k_potrf_diag(BaDev d, int k0, int kb, double* Linv) { pdl_begin();
   extern __shared__ double dyn_smem[];
   double (*A)[kNB + 1] = (double (*)[kNB + 1])dyn_smem;
   double (*Li)[kNB + 1] = (double (*)[kNB + 1])(dyn_smem + kNB * (kNB + 1));
@@ -1850,7 +1850,7 @@ __global__ void __launch_bounds__(kPotrfThreads) k_potrf_diag(BaDev d, int k0, i
 // rows reach into or before the panel's columns — the row envelope of the reduced system, inside which all fill
 // of the factorisation stays.  For a windowed co-visibility graph that is a handful of tiles per panel.
 __global__ void __launch_bounds__(256) k_trsm_panel(BaDev d, int k0, int kb, const double* __restrict__ Linv,
-                                                    const int* __restrict__ tiles) {
+                                                    const int* __restrict__ tiles) { pdl_begin();
   extern __shared__ double dyn_smem[];
   double (*Li)[kNB + 1] = (double (*)[kNB + 1])dyn_smem;
   double (*Arow)[kNB + 1] = (double (*)[kNB + 1])(dyn_smem + kNB * (kNB + 1));
@@ -1880,7 +1880,7 @@ __global__ void __launch_bounds__(256) k_trsm_panel(BaDev d, int k0, int kb, con
 }
 
 // trailing update: A22 -= L21 L21' on 64x64 tiles of the lower triangle (and the rhs row), 256 threads, 4x4 per thread
-__global__ void __launch_bounds__(256) k_syrk_tile(BaDev d, int k0, int kb, const int* __restrict__ tiles) {
+__global__ void __launch_bounds__(256) k_syrk_tile(BaDev d, int k0, int kb, const int* __restrict__ tiles) { pdl_begin();
   extern __shared__ double dyn_smem[];
   double (*As)[64 + 1] = (double (*)[64 + 1])dyn_smem;                      // [k][i]
   double (*Bs)[64 + 1] = (double (*)[64 + 1])(dyn_smem + kNB * (64 + 1));   // [k][j]
@@ -1928,7 +1928,7 @@ __global__ void __launch_bounds__(256) k_syrk_tile(BaDev d, int k0, int kb, cons
 }
 
 // back substitution, panel by panel from the last: x_k = inv(L_kk)' y_k, then y_i -= L_ki' x_k for i < k0
-__global__ void __launch_bounds__(256) k_backsolve_panel(BaDev d, int k0, int kb, const double* __restrict__ Linv, int c_begin) {
+__global__ void __launch_bounds__(256) k_backsolve_panel(BaDev d, int k0, int kb, const double* __restrict__ Linv, int c_begin) { pdl_begin();
   __shared__ double xk[kNB];
   LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
@@ -1958,7 +1958,7 @@ inline bool use_back_all(int n) {      // CMOS_BA_PANEL_BACKSOLVE=1 forces the p
   const char* e = std::getenv("CMOS_BA_PANEL_BACKSOLVE");
   return n <= kBackAllMaxN && !(e && e[0] == '1');
 }
-__global__ void __launch_bounds__(1024) k_backsolve_all(BaDev d, const double* __restrict__ Linv, const int* __restrict__ first_col) {
+__global__ void __launch_bounds__(1024) k_backsolve_all(BaDev d, const double* __restrict__ Linv, const int* __restrict__ first_col) { pdl_begin();
   extern __shared__ double dyn_smem[];
   double* y = dyn_smem;                       // [n]
   double* xk = y + d.nc;                      // [kNB]
@@ -2068,7 +2068,7 @@ __device__ __forceinline__ bool band_diag(const double* Wm, int ld, int sj, cons
   return ok;
 }
 
-__global__ void __launch_bounds__(kBandThreads) k_solve_band(BaDev d, BandArgs ba) {
+__global__ void __launch_bounds__(kBandThreads) k_solve_band(BaDev d, BandArgs ba) { pdl_begin();
   extern __shared__ __align__(16) double smem_d[];
   LmState& st = *d.st;
   if (st.done) return;
@@ -2248,7 +2248,7 @@ __device__ __forceinline__ void ba_mbar_wait(uint64_t* bar, unsigned parity) {
 // round trip: the columns now arrive through a ring of kBackRing TMA bulk copies (one contiguous 6(W+1) x 6 panel each,
 // completion on an mbarrier), issued kBackRing steps before they are used.
 constexpr int kBackRing = 4;
-__global__ void __launch_bounds__(32) k_band_backsub(BaDev d, BandArgs ba) {
+__global__ void __launch_bounds__(32) k_band_backsub(BaDev d, BandArgs ba) { pdl_begin();
   __shared__ double s_x[6 * (kBandMaxW + 1)];
   __shared__ __align__(128) double s_ring[kBackRing][6 * (kBandMaxW + 1) * 6];
   __shared__ __align__(8) uint64_t s_bar[kBackRing];
@@ -2347,7 +2347,7 @@ __global__ void __launch_bounds__(32) k_band_backsub(BaDev d, BandArgs ba) {
 #include "band_cr.cuh"
 namespace cmos {
 
-__global__ void __launch_bounds__(256) k_cam_candidates(BaDev d) {
+__global__ void __launch_bounds__(256) k_cam_candidates(BaDev d) { pdl_begin();
   LmState& st = *d.st;
   if (st.done) return;
   const int cam = blockIdx.x * 256 + threadIdx.x;
@@ -2543,115 +2543,115 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
     return CMOS_OK;
   };
   auto linearize = [&]() -> int {
-    k_linearize<<<nlb, kLinThreads, 0, st>>>(d);
-    if (d.Kv > 0) k_cam_blocks<<<d.Kv, kCamThreads, 0, st>>>(d);
+    launch_chain(k_linearize, nlb, kLinThreads, 0, st, d);
+    if (d.Kv > 0) launch_chain(k_cam_blocks, d.Kv, kCamThreads, 0, st, d);
     h->launches += 2;
     if (!multi) {
-      if (d.Kv == 0) { k_post_lin<<<1, 256, 0, st>>>(d, 0); h->launches++; }   // otherwise the last CTA of k_cam_blocks ran it
+      if (d.Kv == 0) { launch_chain(k_post_lin, 1, 256, 0, st, d, 0); h->launches++; }   // otherwise the last CTA of k_cam_blocks ran it
       return CMOS_OK;
     }
     int rc;
-    k_post_lin<<<1, 256, 0, st>>>(d, 1);
+    launch_chain(k_post_lin, 1, 256, 0, st, d, 1);
     // ONE message: H_cc and g_c of every keyframe, then cost, |x|^2 and the per-rank gradient-max slots
     if ((rc = allreduce(h->d_HG, (size_t)27 * d.Kv + 2 + d.n_ranks, kNcclSum))) return rc;
-    if (d.Kv > 0) k_cam_finish<<<(d.Kv + 127) / 128, 128, 0, st>>>(d);
-    k_post_lin<<<1, 256, 0, st>>>(d, 2);
+    if (d.Kv > 0) launch_chain(k_cam_finish, (d.Kv + 127) / 128, 128, 0, st, d);
+    launch_chain(k_post_lin, 1, 256, 0, st, d, 2);
     h->launches += 3;
     return CMOS_OK;
   };
-  k_lm_init<<<1, 1, 0, st>>>(d, max_iterations);
+  launch_chain(k_lm_init, 1, 1, 0, st, d, max_iterations);
   h->launches++;
   NvtxRange nvtx_solve(pass == 0 ? "cmos.ba.solve.pass0" : "cmos.ba.solve.pass1");
   for (int it = 0; it < max_iterations; it++) {
     NvtxRange nvtx_it("cmos.ba.lm_iteration");
     int rc;
     if ((rc = linearize())) return rc;
-    k_point_prep<<<(d.M + kLinThreads - 1) / kLinThreads, kLinThreads, 0, st>>>(d);
+    launch_chain(k_point_prep, (d.M + kLinThreads - 1) / kLinThreads, kLinThreads, 0, st, d);
     h->launches++;
     if (d.Kv > 0) {
       if (h->schur_chunked) {
-        k_schur_chunks<<<(d.n_chunks + kSchurWarps - 1) / kSchurWarps, 32 * kSchurWarps, 0, st>>>(d);
+        launch_chain(k_schur_chunks, (d.n_chunks + kSchurWarps - 1) / kSchurWarps, 32 * kSchurWarps, 0, st, d);
         // (summing the chunks inside k_solve_small instead — one launch less — was measured: one CTA walks 8 k entries x ~5
         // dependent global loads, +13 us per iteration; the 190-CTA kernel takes 7)
-        k_schur_combine<<<(d.n_blocks * 48 + 255) / 256, 256, 0, st>>>(d);
+        launch_chain(k_schur_combine, (d.n_blocks * 48 + 255) / 256, 256, 0, st, d);
         h->launches += 2;
       } else {
-        k_schur<<<d.n_blocks, kSchurThreads, 0, st>>>(d);
+        launch_chain(k_schur, d.n_blocks, kSchurThreads, 0, st, d);
         h->launches++;
       }
       // the one exchange step of the sharded solve: partial reduced camera system + rhs summed over ranks
       if (multi && (rc = allreduce(d.Sblk, (size_t)d.n_blocks * 36 + d.nc, kNcclSum))) return rc;
       if (small) {
-        k_solve_small<<<1, kSolveThreads, small_smem, st>>>(d);
+        launch_chain(k_solve_small, 1, kSolveThreads, small_smem, st, d);
         h->launches++;
       } else if (h->band_W > 0 && h->cr_N > 0) {
         // nested-dissection (block cyclic reduction) Cholesky of the banded system: log2(N) levels of dense node
         // factorisations, all nodes of a level in parallel
         const CrArgs ca{h->cr_n, h->cr_Wb, h->cr_N, h->band_W, h->cr_levels, h->d_band_blk, d.S};
         const int nt = ca.n / 24, tile_ctas = (nt * nt + kCrGemmWarps - 1) / kCrGemmWarps;
-        k_cr_assemble<<<dim3(ca.N, kCrAsmSplit), 256, 0, st>>>(d, ca);
+        launch_chain(k_cr_assemble, dim3(ca.N, kCrAsmSplit), 256, 0, st, d, ca);
         h->launches++;
         for (int l = 1; l <= ca.levels; l++) {
           const int cnt = ((ca.N >> (l - 1)) + 1) / 2;
-          k_cr_factor<<<cnt, kSolveThreads, cr_factor_smem(ca.n), st>>>(d, ca, l);
+          launch_chain(k_cr_factor, cnt, kSolveThreads, cr_factor_smem(ca.n), st, d, ca, l);
           h->launches++;
           if (l < ca.levels) {
-            k_cr_spike<<<dim3(ca.n / kCrSlab / cr_spike_warps(ca.n), 2, cnt), 32 * cr_spike_warps(ca.n), cr_spike_smem(ca.n), st>>>(d, ca, l, 0);
-            k_cr_schur<<<dim3(tile_ctas, 4, cnt), 32 * kCrGemmWarps, 0, st>>>(d, ca, l);
+            launch_chain(k_cr_spike, dim3(ca.n / kCrSlab / cr_spike_warps(ca.n), 2, cnt), 32 * cr_spike_warps(ca.n), cr_spike_smem(ca.n), st, d, ca, l, 0);
+            launch_chain(k_cr_schur, dim3(tile_ctas, 4, cnt), 32 * kCrGemmWarps, 0, st, d, ca, l);
             h->launches += 2;
           }
         }
         for (int l = ca.levels; l >= 1; l--) {
           const int cnt = ((ca.N >> (l - 1)) + 1) / 2;
-          k_cr_back<<<cnt, 32 * kCrBackWarps, cr_back_smem(ca.n), st>>>(d, ca, l);
+          launch_chain(k_cr_back, cnt, 32 * kCrBackWarps, cr_back_smem(ca.n), st, d, ca, l);
           h->launches++;
         }
-        k_cam_candidates<<<(d.K + 255) / 256, 256, 0, st>>>(d);
+        launch_chain(k_cam_candidates, (d.K + 255) / 256, 256, 0, st, d);
         h->launches++;
       } else if (h->band_W > 0) {
         BandArgs ba{h->band_W, h->d_band_blk, d.S};
-        k_solve_band<<<1, kBandThreads, band_smem_bytes(h->band_W), st>>>(d, ba);
-        k_band_backsub<<<1, 32, 0, st>>>(d, ba);
+        launch_chain(k_solve_band, 1, kBandThreads, band_smem_bytes(h->band_W), st, d, ba);
+        launch_chain(k_band_backsub, 1, 32, 0, st, d, ba);
         h->launches += 2;
       } else {
         const int n = d.nc;
         CMOS_CUDA_OK(cudaMemsetAsync(d.S, 0, (size_t)n * n * sizeof(double), st));
-        k_scatter_S<<<(d.n_blocks * 36 + 255) / 256, 256, 0, st>>>(d);
+        launch_chain(k_scatter_S, (d.n_blocks * 36 + 255) / 256, 256, 0, st, d);
         h->launches++;
         for (int k0 = 0, p = 0; k0 < n; k0 += kNB, p++) {
           const int kb = std::min(kNB, n - k0);
-          k_potrf_diag<<<1, kPotrfThreads, kPanelSmem, st>>>(d, k0, kb, h->d_Linv);
+          launch_chain(k_potrf_diag, 1, kPotrfThreads, kPanelSmem, st, d, k0, kb, h->d_Linv);
           const int na = h->pan_start[p + 1] - h->pan_start[p];   // active tiles below this panel (rhs row included)
           if (na > 0) {
             const int* tiles = h->d_pan_tiles + h->pan_start[p];
-            k_trsm_panel<<<2 * na, 256, kPanelSmem, st>>>(d, k0, kb, h->d_Linv, tiles);
-            k_syrk_tile<<<na * (na + 1) / 2, 256, kPanelSmem, st>>>(d, k0, kb, tiles);
+            launch_chain(k_trsm_panel, 2 * na, 256, kPanelSmem, st, d, k0, kb, h->d_Linv, tiles);
+            launch_chain(k_syrk_tile, na * (na + 1) / 2, 256, kPanelSmem, st, d, k0, kb, tiles);
             h->launches += 2;
           }
           h->launches++;
         }
         if (use_back_all(n)) {
-          k_backsolve_all<<<1, 1024, back_all_smem(n), st>>>(d, h->d_Linv, h->d_pan_first);
+          launch_chain(k_backsolve_all, 1, 1024, back_all_smem(n), st, d, h->d_Linv, h->d_pan_first);
           h->launches++;
         } else
           for (int k0 = ((n - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {
             const int kb = std::min(kNB, n - k0);
             const int c0 = std::min(h->pan_first_col[k0 / kNB], k0);
-            k_backsolve_panel<<<std::max(1, (k0 - c0 + 255) / 256), 256, 0, st>>>(d, k0, kb, h->d_Linv, c0);
+            launch_chain(k_backsolve_panel, std::max(1, (k0 - c0 + 255) / 256), 256, 0, st, d, k0, kb, h->d_Linv, c0);
             h->launches++;
           }
-        k_cam_candidates<<<(d.K + 255) / 256, 256, 0, st>>>(d);
+        launch_chain(k_cam_candidates, (d.K + 255) / 256, 256, 0, st, d);
         h->launches++;
       }
     }
-    k_backsub<<<nlb, kLinThreads, 0, st>>>(d);
+    launch_chain(k_backsub, nlb, kLinThreads, 0, st, d);
     h->launches++;
     if (!multi) {
       // the last CTA of k_backsub decides
     } else {
-      k_decide<<<1, 256, 0, st>>>(d, 1);
+      launch_chain(k_decide, 1, 256, 0, st, d, 1);
       if ((rc = allreduce(d.red + 3, 4, kNcclSum))) return rc;                    // candidate cost, model change, |step|^2, failure
-      k_decide<<<1, 256, 0, st>>>(d, 2);
+      launch_chain(k_decide, 1, 256, 0, st, d, 2);
       h->launches += 2;
     }
   }
@@ -2659,7 +2659,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
     int rc;
     if ((rc = linearize())) return rc;
   }
-  k_summary<<<1, 1, 0, st>>>(d, h->d_summaries + pass);
+  launch_chain(k_summary, 1, 1, 0, st, d, h->d_summaries + pass);
   h->launches++;
   CMOS_CUDA_OK(cudaGetLastError());
   return CMOS_OK;
@@ -2812,7 +2812,7 @@ int cmos_ba_pose_optimization(cmos_ba_t h, int32_t n_frames, double* pose7, cons
     h->pose_stage[0] = o_pose; h->pose_stage[1] = o_sum; h->pose_stage[2] = o_inl; h->pose_stage[3] = o_out; h->pose_stage[4] = total;
   }
   h->timer.begin(st);
-  k_pose_opt<<<n_frames, kPoseThreads, 0, st>>>(a);
+  launch_chain(k_pose_opt, n_frames, kPoseThreads, 0, st, a);
   h->timer.mark(st);
   CMOS_CUDA_OK(cudaGetLastError());
   h->launches = 1;
@@ -2845,7 +2845,7 @@ struct StageTable { void* dst[kStageMax]; size_t off[kStageMax]; size_t bytes[kS
 // one launch deals the packed upload to its destination arrays (offsets are 16-byte aligned, sizes multiples of 4 except
 // the keyframe flags)
 // (to_stage != 0: the other direction — results gathered into the packed buffer for one download)
-__global__ void __launch_bounds__(256) k_stage_scatter(StageTable t, uint8_t* __restrict__ stage, int to_stage) {
+__global__ void __launch_bounds__(256) k_stage_scatter(StageTable t, uint8_t* __restrict__ stage, int to_stage) { pdl_begin();
   const size_t gt = (size_t)blockIdx.x * 256 + threadIdx.x, gs = (size_t)gridDim.x * 256;
   for (int e = 0; e < t.n; e++) {
     const uint8_t* s8 = to_stage ? (const uint8_t*)t.dst[e] : stage + t.off[e];
@@ -2888,7 +2888,7 @@ struct Stager {
     for (int e = 0; e < t.n; e++) std::memcpy(h->h_stage + t.off[e], srcs[e], t.bytes[e]);
     CMOS_CUDA_OK(cudaMemcpyAsync(h->d_stage, h->h_stage, used, cudaMemcpyHostToDevice, st));
     const int grid = (int)std::min<size_t>(296, (used / 4 + 255) / 256 + 1);
-    k_stage_scatter<<<grid, 256, 0, st>>>(t, h->d_stage, 0);
+    launch_chain(k_stage_scatter, grid, 256, 0, st, t, h->d_stage, 0);
     CMOS_CUDA_OK(cudaGetLastError());
     return CMOS_OK;
   }
@@ -2907,7 +2907,7 @@ struct Stager {
       h->cap_stage = want;
     }
     const int grid = (int)std::min<size_t>(296, (used / 4 + 255) / 256 + 1);
-    k_stage_scatter<<<grid, 256, 0, st>>>(t, h->d_stage, 1);
+    launch_chain(k_stage_scatter, grid, 256, 0, st, t, h->d_stage, 1);
     CMOS_CUDA_OK(cudaGetLastError());
     CMOS_CUDA_OK(cudaMemcpyAsync(h->h_stage, h->d_stage, used, cudaMemcpyDeviceToHost, st));
     CMOS_CUDA_OK(cudaStreamSynchronize(st));
@@ -3259,12 +3259,12 @@ int cmos_ba_run_local(cmos_ba_t h, int32_t iterations_pass0, int32_t iterations_
   BaDev& d = h->d;
   const int gN = (d.N + 255) / 256;
   h->timer.begin(st);
-  k_set_mode<<<gN, 256, 0, st>>>(d, 1);
+  launch_chain(k_set_mode, gN, 256, 0, st, d, 1);
   if ((rc = enqueue_solve(h, iterations_pass0, 0, st))) return rc;
-  k_outlier_scan<<<gN, 256, 0, st>>>(d, h->d_cam_flags, h->d_perm, h->d_erase, 1);
+  launch_chain(k_outlier_scan, gN, 256, 0, st, d, h->d_cam_flags, h->d_perm, h->d_erase, 1);
   if ((rc = enqueue_solve(h, iterations_pass1, 1, st))) return rc;
-  k_outlier_scan<<<gN, 256, 0, st>>>(d, h->d_cam_flags, h->d_perm, h->d_erase, 0);
-  k_gather_result<<<(std::max(7 * d.K, 3 * d.M) + 255) / 256, 256, 0, st>>>(d, h->d_cams0, h->d_pts0, h->d_cams_out, h->d_pts_out);
+  launch_chain(k_outlier_scan, gN, 256, 0, st, d, h->d_cam_flags, h->d_perm, h->d_erase, 0);
+  launch_chain(k_gather_result, (std::max(7 * d.K, 3 * d.M) + 255) / 256, 256, 0, st, d, h->d_cams0, h->d_pts0, h->d_cams_out, h->d_pts_out);
   h->timer.mark(st);
   h->launches += 4;
   CMOS_CUDA_OK(cudaGetLastError());
@@ -3283,9 +3283,9 @@ int cmos_ba_run_global(cmos_ba_t h, int32_t n_iterations, int32_t robust, const 
   h->ran = true;
   BaDev& d = h->d;
   h->timer.begin(st);
-  k_set_mode<<<(d.N + 255) / 256, 256, 0, st>>>(d, robust ? 1 : 2);
+  launch_chain(k_set_mode, (d.N + 255) / 256, 256, 0, st, d, robust ? 1 : 2);
   if ((rc = enqueue_solve(h, n_iterations, 0, st))) return rc;
-  k_gather_result<<<(std::max(7 * d.K, 3 * d.M) + 255) / 256, 256, 0, st>>>(d, h->d_cams0, h->d_pts0, h->d_cams_out, h->d_pts_out);
+  launch_chain(k_gather_result, (std::max(7 * d.K, 3 * d.M) + 255) / 256, 256, 0, st, d, h->d_cams0, h->d_pts0, h->d_cams_out, h->d_pts_out);
   h->timer.mark(st);
   h->launches += 2;
   CMOS_CUDA_OK(cudaGetLastError());
@@ -3448,7 +3448,7 @@ int cmos_ba_optimize_sim3(cmos_ba_t h, int32_t n, double* s12, double* R12, doub
   a.huber_a = std::sqrt((double)th2);
   a.max_iterations = max_iterations;
   a.is_bad = h->ds_bad; a.out = h->ds_out; a.summary = h->dp_sum; a.trace = h->dp_trace;
-  k_sim3_opt<<<1, kPoseThreads, 0, st>>>(a);
+  launch_chain(k_sim3_opt, 1, kPoseThreads, 0, st, a);
   CMOS_CUDA_OK(cudaGetLastError());
   h->launches = 1;
   double out[24];
@@ -3646,85 +3646,85 @@ int cmos_ba_optimize_essential_graph(cmos_ba_t h, int32_t n_kf, const double* Sc
   const int eff_iterations = Kv > 0 ? max_iterations : 0;
   h->launches = 0;
   const int gk = (n_kf + 127) / 128, ge = std::max(1, (n_edges + 63) / 64), gw = std::max(1, (Kv + 3) / 4);
-  k_eg_logs<<<gk, 128, 0, st>>>(d, eff_iterations);
-  k_eg_meas<<<std::max(1, (n_edges + 127) / 128), 128, 0, st>>>(d);
+  launch_chain(k_eg_logs, gk, 128, 0, st, d, eff_iterations);
+  launch_chain(k_eg_meas, std::max(1, (n_edges + 127) / 128), 128, 0, st, d);
   h->launches += 2;
   auto linearize = [&]() {
-    k_eg_linearize<<<ge, 64, 0, st>>>(d);
-    k_eg_assemble<<<gw, 128, 0, st>>>(d);
-    k_eg_post_lin<<<1, 256, 0, st>>>(d);
+    launch_chain(k_eg_linearize, ge, 64, 0, st, d);
+    launch_chain(k_eg_assemble, gw, 128, 0, st, d);
+    launch_chain(k_eg_post_lin, 1, 256, 0, st, d);
     h->launches += 3;
   };
   for (int it = 0; it < eff_iterations; it++) {
     linearize();
     if (plan.ok) {
       // nested dissection: log2(N) levels of node factorisations (all nodes of a level in parallel), the border last
-      k_eg_cr_clear<<<ca.N + 1, 256, 0, st>>>(d);
-      k_eg_build<<<gw, 128, 0, st>>>(d);
+      launch_chain(k_eg_cr_clear, ca.N + 1, 256, 0, st, d);
+      launch_chain(k_eg_build, gw, 128, 0, st, d);
       h->launches += 2;
       const int nt = ca.n / 24, ntb = ca.nbp / 24, kw = cr_spike_warps(ca.n);
       const int tile_ctas = (nt * nt + kCrGemmWarps - 1) / kCrGemmWarps;
       const int tile_ctas_b = (std::max(nt * ntb, ntb * ntb) + kCrGemmWarps - 1) / kCrGemmWarps;
       for (int l = 1; l <= ca.levels; l++) {
         const int cnt = ((ca.N >> (l - 1)) + 1) / 2;
-        k_cr_factor<<<cnt, kSolveThreads, cr_factor_smem(ca.n), st>>>(dv, ca, l);
+        launch_chain(k_cr_factor, cnt, kSolveThreads, cr_factor_smem(ca.n), st, dv, ca, l);
         h->launches++;
         // neighbour and border spikes in one launch, neighbour and border products in one launch; the last level has no neighbours
         const int sx = std::max(nt / kw, (ntb + kw - 1) / kw);
-        if (l < ca.levels) k_cr_spike<<<dim3(ntb ? sx : nt / kw, ntb ? 3 : 2, cnt), 32 * kw, cr_spike_smem(ca.n), st>>>(dv, ca, l, 0);
-        else if (ntb) k_cr_spike<<<dim3((ntb + kw - 1) / kw, 1, cnt), 32 * kw, cr_spike_smem(ca.n), st>>>(dv, ca, l, 2);
-        if (l < ca.levels && ntb) k_cr_schur_all<<<dim3(std::max(tile_ctas, tile_ctas_b), 8, cnt), 32 * kCrGemmWarps, 0, st>>>(dv, ca, l);
-        else if (l < ca.levels) k_cr_schur<<<dim3(tile_ctas, 4, cnt), 32 * kCrGemmWarps, 0, st>>>(dv, ca, l);
-        else if (ntb) k_crb_schur<<<dim3(tile_ctas_b, 4, cnt), 32 * kCrGemmWarps, 0, st>>>(dv, ca, l);
+        if (l < ca.levels) launch_chain(k_cr_spike, dim3(ntb ? sx : nt / kw, ntb ? 3 : 2, cnt), 32 * kw, cr_spike_smem(ca.n), st, dv, ca, l, 0);
+        else if (ntb) launch_chain(k_cr_spike, dim3((ntb + kw - 1) / kw, 1, cnt), 32 * kw, cr_spike_smem(ca.n), st, dv, ca, l, 2);
+        if (l < ca.levels && ntb) launch_chain(k_cr_schur_all, dim3(std::max(tile_ctas, tile_ctas_b), 8, cnt), 32 * kCrGemmWarps, 0, st, dv, ca, l);
+        else if (l < ca.levels) launch_chain(k_cr_schur, dim3(tile_ctas, 4, cnt), 32 * kCrGemmWarps, 0, st, dv, ca, l);
+        else if (ntb) launch_chain(k_crb_schur, dim3(tile_ctas_b, 4, cnt), 32 * kCrGemmWarps, 0, st, dv, ca, l);
         h->launches += (l < ca.levels || ntb) ? 2 : 0;
       }
-      if (ntb) { k_crb_solve<<<1, kSolveThreads, crb_solve_smem(ca.nbp), st>>>(dv, ca); h->launches++; }
+      if (ntb) { launch_chain(k_crb_solve, 1, kSolveThreads, crb_solve_smem(ca.nbp), st, dv, ca); h->launches++; }
       for (int l = ca.levels; l >= 1; l--) {
         const int cnt = ((ca.N >> (l - 1)) + 1) / 2;
-        k_cr_back<<<cnt, 32 * kCrBackWarps, cr_back_smem(ca.n), st>>>(dv, ca, l);
+        launch_chain(k_cr_back, cnt, 32 * kCrBackWarps, cr_back_smem(ca.n), st, dv, ca, l);
         h->launches++;
       }
-      k_eg_cr_scatter<<<(n + 255) / 256, 256, 0, st>>>(d);
+      launch_chain(k_eg_cr_scatter, (n + 255) / 256, 256, 0, st, d);
       h->launches++;
     } else {
     CMOS_CUDA_OK(cudaMemsetAsync(g.S, 0, (size_t)n * n * sizeof(double), st));
-    k_eg_build<<<gw, 128, 0, st>>>(d);
+    launch_chain(k_eg_build, gw, 128, 0, st, d);
     h->launches++;
     for (int k0 = 0, p = 0; k0 < n; k0 += kNB, p++) {
       const int kb = std::min(kNB, n - k0);
-      k_potrf_diag<<<1, kPotrfThreads, kPanelSmem, st>>>(dv, k0, kb, g.Linv);
+      launch_chain(k_potrf_diag, 1, kPotrfThreads, kPanelSmem, st, dv, k0, kb, g.Linv);
       const int na = pan_start[p + 1] - pan_start[p];
       if (na > 0) {
         const int* tl = g.tiles + pan_start[p];
-        k_trsm_panel<<<2 * na, 256, kPanelSmem, st>>>(dv, k0, kb, g.Linv, tl);
-        k_syrk_tile<<<na * (na + 1) / 2, 256, kPanelSmem, st>>>(dv, k0, kb, tl);
+        launch_chain(k_trsm_panel, 2 * na, 256, kPanelSmem, st, dv, k0, kb, g.Linv, tl);
+        launch_chain(k_syrk_tile, na * (na + 1) / 2, 256, kPanelSmem, st, dv, k0, kb, tl);
         h->launches += 2;
       }
       h->launches++;
     }
     if (use_back_all(n)) {
-      k_backsolve_all<<<1, 1024, back_all_smem(n), st>>>(dv, g.Linv, g.first_col);
+      launch_chain(k_backsolve_all, 1, 1024, back_all_smem(n), st, dv, g.Linv, g.first_col);
       h->launches++;
     } else
       for (int k0 = ((n - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {
         const int kb = std::min(kNB, n - k0);
         const int c0 = std::min(pan_first_col[k0 / kNB], k0);
-        k_backsolve_panel<<<std::max(1, (k0 - c0 + 255) / 256), 256, 0, st>>>(dv, k0, kb, g.Linv, c0);
+        launch_chain(k_backsolve_panel, std::max(1, (k0 - c0 + 255) / 256), 256, 0, st, dv, k0, kb, g.Linv, c0);
         h->launches++;
       }
     }
-    k_eg_step<<<gk, 128, 0, st>>>(d);
-    k_eg_eval<<<ge, 64, 0, st>>>(d);
-    k_eg_decide<<<1, 256, 0, st>>>(d, g.done_host);
+    launch_chain(k_eg_step, gk, 128, 0, st, d);
+    launch_chain(k_eg_eval, ge, 64, 0, st, d);
+    launch_chain(k_eg_decide, 1, 256, 0, st, d, g.done_host);
     h->launches += 3;
     CMOS_CUDA_OK(cudaStreamSynchronize(st));         // one word: has the device-side state machine terminated?
     if (*g.done_host) break;
   }
   if (eff_iterations == 0) linearize();              // Ceres still evaluates iteration 0
-  k_eg_summary<<<1, 1, 0, st>>>(d, h->dp_sum);
-  k_eg_finish<<<gk, 128, 0, st>>>(d, g.lie_out, g.Tiw, g.Swc);
+  launch_chain(k_eg_summary, 1, 1, 0, st, d, h->dp_sum);
+  launch_chain(k_eg_finish, gk, 128, 0, st, d, g.lie_out, g.Tiw, g.Swc);
   h->launches += 2;
-  if (n_points > 0) { k_eg_points<<<(n_points + 255) / 256, 256, 0, st>>>(d, n_points, g.Xw, g.ref, g.Swc, g.Xo); h->launches++; }
+  if (n_points > 0) { launch_chain(k_eg_points, (n_points + 255) / 256, 256, 0, st, d, n_points, g.Xw, g.ref, g.Swc, g.Xo); h->launches++; }
   CMOS_CUDA_OK(cudaGetLastError());
   if (lie_out) CMOS_CUDA_OK(cudaMemcpyAsync(lie_out, g.lie_out, (size_t)n_kf * 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (Tiw_out) CMOS_CUDA_OK(cudaMemcpyAsync(Tiw_out, g.Tiw, (size_t)n_kf * 16 * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -5,7 +5,37 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <utility>
+
 namespace cmos {
+
+// ---- programmatic dependent launch ------------------------------------------------------------------------------------------
+// A solve is a chain of small, dependent kernels on one stream (LocalBundleAdjustment: 98 launches of 3-30 us).  Every kernel
+// of these files starts with pdl_begin(): it lets the NEXT kernel of the stream be scheduled at once (its CTAs become resident
+// and park in griddepcontrol.wait) and then waits until the PREVIOUS kernel has completed and its writes are visible — so a
+// kernel starts computing the moment its predecessor retires instead of paying the launch latency after it.  launch_chain
+// launches with the attribute that enables this; kernels launched without it see the two instructions as no-ops.
+// CMOS_BA_NO_PDL=1 launches the ordinary way (A/B).
+__device__ __forceinline__ void pdl_begin() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+inline bool pdl_enabled() {
+  static const bool on = getenv("CMOS_BA_NO_PDL") == nullptr;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);     // errors surface through cudaGetLastError like <<< >>>
+}
 
 constexpr double kHuberA = 2.447651936039926;    // sqrt(5.991), CeresOptimizer.cc:81,296,421
 constexpr double kHuberB = kHuberA * kHuberA;

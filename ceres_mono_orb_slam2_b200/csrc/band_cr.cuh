@@ -88,7 +88,7 @@ inline size_t cr_factor_smem(int n) {
 // Assembly: kCrAsmSplit CTAs per node, each zero-fills a quarter of the node's block rows in D0 / Ep and scatters the Sblk
 // blocks that land there (one CTA per node spent 53 us writing 230 KB of zeros with 256 threads: latency of one SM).
 constexpr int kCrAsmSplit = 4;          // Wb is a multiple of 4
-__global__ void __launch_bounds__(256) k_cr_assemble(BaDev d, CrArgs a) {
+__global__ void __launch_bounds__(256) k_cr_assemble(BaDev d, CrArgs a) { pdl_begin();
   const LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
   const int node = blockIdx.x + 1, part = blockIdx.y, tid = threadIdx.x, n = a.n;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) k_cr_assemble(BaDev d, CrArgs a) {
 // ---------------------------------------------------------------------------------------------------------------------
 // Factor one node per CTA: gather D and b, packed Cholesky in shared memory (the rhs rides as row n and leaves as y), the
 // packed factor and y to HBM.
-__global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, int level) {
+__global__ void __launch_bounds__(kSolveThreads) k_cr_factor(BaDev d, CrArgs a, int level) { pdl_begin();
   extern __shared__ __align__(16) double smem_d[];
   LmState& st = *d.st;
   if (st.done || st.solve_failed) return;                // (k_point_prep raises solve_failed for a singular point block)
@@ -267,7 +267,7 @@ inline size_t cr_spike_smem(int n) {
   return ((size_t)n * (n + 1) / 2 + (size_t)n * (kCrSlab * cr_spike_warps(n) + 4)) * sizeof(double);
 }
 // side 2 (launched on its own, side0 = 2): V_b = L^-1 (F_i - FaccL - FaccR), nbp columns.
-__global__ void __launch_bounds__(192) k_cr_spike(BaDev d, CrArgs a, int level, int side0) {
+__global__ void __launch_bounds__(192) k_cr_spike(BaDev d, CrArgs a, int level, int side0) { pdl_begin();
   extern __shared__ __align__(16) double smem_d[];
   const LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
@@ -433,10 +433,10 @@ __device__ __forceinline__ void crb_schur_body(const BaDev& d, const CrArgs& a, 
     }
 }
 
-__global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur(BaDev d, CrArgs a, int level) { cr_schur_body(d, a, level, blockIdx.y); }
-__global__ void __launch_bounds__(32 * kCrGemmWarps) k_crb_schur(BaDev d, CrArgs a, int level) { crb_schur_body(d, a, level, blockIdx.y); }
+__global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur(BaDev d, CrArgs a, int level) { pdl_begin(); cr_schur_body(d, a, level, blockIdx.y); }
+__global__ void __launch_bounds__(32 * kCrGemmWarps) k_crb_schur(BaDev d, CrArgs a, int level) { pdl_begin(); crb_schur_body(d, a, level, blockIdx.y); }
 // both in one launch (bordered systems, every level but the last): grid (tile groups, 8 products, node)
-__global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur_all(BaDev d, CrArgs a, int level) {
+__global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur_all(BaDev d, CrArgs a, int level) { pdl_begin();
   if (blockIdx.y < 4) cr_schur_body(d, a, level, blockIdx.y);
   else crb_schur_body(d, a, level, blockIdx.y - 4);
 }
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(32 * kCrGemmWarps) k_cr_schur_all(BaDev d, CrA
 // The border system after every node is eliminated: (C0 - sum_i Cpart[i]) x_C = gB - sum_i gpart[i], sums in node order;
 // one CTA, the same small dense solver as LocalBundleAdjustment's reduced camera system.
 inline size_t crb_solve_smem(int nbp) { return ((size_t)(nbp + 1) * (nbp + 2) / 2 + chol_scratch_doubles(nbp)) * sizeof(double); }
-__global__ void __launch_bounds__(kSolveThreads) k_crb_solve(BaDev d, CrArgs a) {
+__global__ void __launch_bounds__(kSolveThreads) k_crb_solve(BaDev d, CrArgs a) { pdl_begin();
   extern __shared__ __align__(16) double smem_d[];
   LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_crb_solve(BaDev d, CrArgs a) 
 // factor in shared memory, from the last 24-row block up (right-looking: x_p = inv(L_pp)' z_p, then z_q -= L_pq' x_p, q < p).
 constexpr int kCrBackWarps = 16;
 inline size_t cr_back_smem(int n) { return ((size_t)n * (n + 1) / 2 + 2) * sizeof(double); }
-__global__ void __launch_bounds__(32 * kCrBackWarps) k_cr_back(BaDev d, CrArgs a, int level) {
+__global__ void __launch_bounds__(32 * kCrBackWarps) k_cr_back(BaDev d, CrArgs a, int level) { pdl_begin();
   extern __shared__ __align__(16) double smem_d[];
   __shared__ double s_z[kCrMaxN], s_xl[kCrMaxN], s_xr[kCrMaxN], s_x[kCrMaxN];
   const LmState& st = *d.st;

@@ -81,7 +81,7 @@ __device__ __forceinline__ double* eg_rhs_entry(const EgDev& d, int a, int r) {
 
 // Zero the node blocks the assembly accumulates into and put ones on the diagonal of the padding rows (a node holds Wb
 // keyframes = 7 Wb unknowns, padded to a multiple of 24; the border likewise).  One CTA per node + one for the border.
-__global__ void __launch_bounds__(256) k_eg_cr_clear(EgDev d) {
+__global__ void __launch_bounds__(256) k_eg_cr_clear(EgDev d) { pdl_begin();
   const LmState& st = *d.st;
   if (st.done) return;
   const CrArgs& ca = d.ca;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) k_eg_cr_clear(EgDev d) {
 }
 
 // solution by node / border -> yc in variable-keyframe order
-__global__ void __launch_bounds__(256) k_eg_cr_scatter(EgDev d) {
+__global__ void __launch_bounds__(256) k_eg_cr_scatter(EgDev d) { pdl_begin();
   const LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
   const int q = blockIdx.x * 256 + threadIdx.x;
@@ -128,7 +128,7 @@ __device__ __forceinline__ void sim3_from_srt(const double* v13, Sim3D& S) {
   for (int i = 0; i < 3; i++) S.t[i] = v13[10 + i];
 }
 
-__global__ void __launch_bounds__(128) k_eg_logs(EgDev d, int max_iterations) {
+__global__ void __launch_bounds__(128) k_eg_logs(EgDev d, int max_iterations) { pdl_begin();
   const int k = blockIdx.x * 128 + threadIdx.x;
   if (k == 0) lm_init(*d.st, max_iterations, 0);
   if (k >= d.n_kf) return;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(128) k_eg_logs(EgDev d, int max_iterations) {
   for (int a = 0; a < 7; a++) { d.x0[7 * (size_t)k + a] = v[a]; d.x[0][7 * (size_t)k + a] = v[a]; d.x[1][7 * (size_t)k + a] = v[a]; }
 }
 
-__global__ void __launch_bounds__(128) k_eg_meas(EgDev d) {
+__global__ void __launch_bounds__(128) k_eg_meas(EgDev d) { pdl_begin();
   const int e = blockIdx.x * 128 + threadIdx.x;
   if (e >= d.E) return;
   const int j = d.edge_j[e], i = d.edge_i[e];
@@ -162,7 +162,7 @@ __device__ inline void eg_residual(const Sim3D& M, const double* xj, const doubl
   if (Sj_out) *Sj_out = Sj;
 }
 
-__global__ void __launch_bounds__(64) k_eg_linearize(EgDev d) {
+__global__ void __launch_bounds__(64) k_eg_linearize(EgDev d) { pdl_begin();
   const LmState& st = *d.st;
   if (st.done || !st.need_lin) return;
   const int e = blockIdx.x * 64 + threadIdx.x;
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(64) k_eg_linearize(EgDev d) {
   }
 }
 
-__global__ void __launch_bounds__(128) k_eg_assemble(EgDev d) {
+__global__ void __launch_bounds__(128) k_eg_assemble(EgDev d) { pdl_begin();
   const LmState& st = *d.st;
   if (st.done || !st.need_lin) return;
   const int a = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(128) k_eg_assemble(EgDev d) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_eg_post_lin(EgDev d) {
+__global__ void __launch_bounds__(256) k_eg_post_lin(EgDev d) { pdl_begin();
   __shared__ double scratch[33];
   LmState& st = *d.st;
   if (st.done || !st.need_lin) return;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) k_eg_post_lin(EgDev d) {
   if (tid == 0) lm_after_linearize(st, c, m, sqrt(xn), d.trace);
 }
 
-__global__ void __launch_bounds__(128) k_eg_build(EgDev d) {
+__global__ void __launch_bounds__(128) k_eg_build(EgDev d) { pdl_begin();
   LmState& st = *d.st;
   if (st.done) return;
   const int a = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(128) k_eg_build(EgDev d) {
   }
 }
 
-__global__ void __launch_bounds__(128) k_eg_step(EgDev d) {
+__global__ void __launch_bounds__(128) k_eg_step(EgDev d) { pdl_begin();
   LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
   const int k = blockIdx.x * 128 + threadIdx.x;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(128) k_eg_step(EgDev d) {
   d.p_sn2[a] = sn2;
 }
 
-__global__ void __launch_bounds__(64) k_eg_eval(EgDev d) {
+__global__ void __launch_bounds__(64) k_eg_eval(EgDev d) { pdl_begin();
   const LmState& st = *d.st;
   if (st.done || st.solve_failed) return;
   const int e = blockIdx.x * 64 + threadIdx.x;
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(64) k_eg_eval(EgDev d) {
   d.p_cand[e] = 0.5 * c;
 }
 
-__global__ void __launch_bounds__(256) k_eg_decide(EgDev d, int* done_host) {
+__global__ void __launch_bounds__(256) k_eg_decide(EgDev d, int* done_host) { pdl_begin();
   __shared__ double scratch[33];
   LmState& st = *d.st;
   if (st.done) { if (threadIdx.x == 0) *done_host = 1; return; }
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(256) k_eg_decide(EgDev d, int* done_host) {
 // rejected step: the candidate buffer must hold x again for the constant-keyframe invariant — not needed: only variable
 // keyframes are rewritten by k_eg_step, and every variable keyframe is rewritten before the candidate is read.
 
-__global__ void k_eg_summary(EgDev d, cmos_ba_summary* out) {
+__global__ void k_eg_summary(EgDev d, cmos_ba_summary* out) { pdl_begin();
   const LmState& st = *d.st;
   cmos_ba_summary s;
   s.iterations = st.iteration; s.successful_steps = st.successful; s.termination = st.termination;
@@ -373,7 +373,7 @@ __global__ void k_eg_summary(EgDev d, cmos_ba_summary* out) {
 }
 
 // lie_out [n_kf][7], Tiw_out [n_kf][16], Swc [n_kf] (corrected_Swcs)
-__global__ void __launch_bounds__(128) k_eg_finish(EgDev d, double* lie_out, double* Tiw_out, Sim3D* Swc) {
+__global__ void __launch_bounds__(128) k_eg_finish(EgDev d, double* lie_out, double* Tiw_out, Sim3D* Swc) { pdl_begin();
   const int k = blockIdx.x * 128 + threadIdx.x;
   if (k >= d.n_kf) return;
   const double* x = d.x[d.st->cur] + 7 * (size_t)k;
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(128) k_eg_finish(EgDev d, double* lie_out, dou
 }
 
 __global__ void __launch_bounds__(256) k_eg_points(EgDev d, int n_points, const double* __restrict__ Xw, const int* __restrict__ ref_kf,
-                                                   const Sim3D* __restrict__ Swc, double* __restrict__ Xo) {
+                                                   const Sim3D* __restrict__ Swc, double* __restrict__ Xo) { pdl_begin();
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= n_points) return;
   const int rk = ref_kf[p];
