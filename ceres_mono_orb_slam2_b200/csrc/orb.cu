@@ -165,9 +165,15 @@ __global__ void __launch_bounds__(256) k_resize(OrbGeom g, int level, const shor
 //   * the reflect-101 borders of all levels are filled afterwards by ONE launch of k_borders (the resize itself clamps source
 //     coordinates, ORBextractor.cc:1120 / OpenCV's xofs clamp, and never reads a border).
 // Bit-exact with cv::resize INTER_LINEAR (tests compare every plane byte with the oracle and with the reference build).
-constexpr int kRzTW = 128, kRzTH = 16, kRzMaxSrcRows = 24;
+// Tile height: the column set-up (table loads, funnel-shift amounts: ~110 instructions per thread) is paid once per tile, so a
+// 128 x 16 tile (two output rows per thread) spent more on it than on the pixels: 50 thread-instructions per output pixel.
+// 128 x 64 tiles (eight output rows per thread, 80 source rows = 20 KB of shared memory) amortise it four times better.
+constexpr int kRzTW = 128;
+__host__ __device__ constexpr int rz_max_src_rows(int th) { return th == 64 ? 80 : th == 32 ? 42 : 24; }
+template <int kRzTH>
 __global__ void __launch_bounds__(256) k_resize2(OrbGeom g, int level, const short4* __restrict__ xtab,
                                                  const short4* __restrict__ ytab, uint8_t* __restrict__ pyr) {
+  constexpr int kRzMaxSrcRows = rz_max_src_rows(kRzTH);
   __shared__ __align__(8) uint16_t s_h[kRzMaxSrcRows][kRzTW];
   const LevelGeom& L = g.lv[level];
   const LevelGeom& S = g.lv[level - 1];
@@ -1075,6 +1081,7 @@ struct cmos_orb {
   bool fast_small_cells = false;   // every cell of the current geometry fits the 48 x 48 tile (CMOS_FAST_LARGE_TILE=1 disables)
   int resize_rows = 2;      // CMOS_RESIZE_ROWS=1|2|4 output rows per thread of k_resize (tuning knob)
   bool resize_v2 = true;    // k_resize2 + k_borders (CMOS_RESIZE_V1=1 selects round 1's k_resize, A/B runs)
+  int resize_th = 64;       // output rows per k_resize2 tile (CMOS_RESIZE_TH=16|32|64)
   bool has_result = false;
   StageTimer timer;
 };
@@ -1253,8 +1260,11 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
   if (h->resize_v2) {
     for (int l = 1; l < g.nlevels; l++) {
       const LevelGeom& L = g.lv[l];
-      dim3 grid((L.w + kRzTW - 1) / kRzTW, (L.h + kRzTH - 1) / kRzTH, n_frames);
-      k_resize2<<<grid, 256, 0, st>>>(g, l, h->d_tab + h->xtab_off[l], h->d_tab + h->ytab_off[l], h->d_pyr);
+      const int th = h->resize_th;
+      dim3 grid((L.w + kRzTW - 1) / kRzTW, (L.h + th - 1) / th, n_frames);
+      if (th == 64) k_resize2<64><<<grid, 256, 0, st>>>(g, l, h->d_tab + h->xtab_off[l], h->d_tab + h->ytab_off[l], h->d_pyr);
+      else if (th == 32) k_resize2<32><<<grid, 256, 0, st>>>(g, l, h->d_tab + h->xtab_off[l], h->d_tab + h->ytab_off[l], h->d_pyr);
+      else k_resize2<16><<<grid, 256, 0, st>>>(g, l, h->d_tab + h->xtab_off[l], h->d_tab + h->ytab_off[l], h->d_pyr);
       launches++;
     }
     if (g.nlevels > 1) {
@@ -1340,6 +1350,10 @@ int cmos_orb_create(const cmos_orb_params* params, cmos_orb_t* out) {
   h->device = params->device;
   if (const char* e = std::getenv("CMOS_FAST_THREADS")) h->fast_threads = std::atoi(e) == 256 ? 256 : 128;
   if (const char* e = std::getenv("CMOS_RESIZE_V1")) h->resize_v2 = !(e[0] == '1');
+  if (const char* e = std::getenv("CMOS_RESIZE_TH")) { int t = std::atoi(e); h->resize_th = t == 16 ? 16 : t == 32 ? 32 : 64; }
+  // a tile of th output rows reads (th - 1) * scale + 3 source rows at most; the shared-memory tile holds rz_max_src_rows(th)
+  while (h->resize_th > 16 && (h->resize_th - 1) * (double)params->scale_factor + 3 > rz_max_src_rows(h->resize_th)) h->resize_th /= 2;
+  if ((h->resize_th - 1) * (double)params->scale_factor + 3 > rz_max_src_rows(h->resize_th)) h->resize_v2 = false;
   if (const char* e = std::getenv("CMOS_RESIZE_ROWS")) { int r = std::atoi(e); h->resize_rows = r == 2 ? 2 : r == 4 ? 4 : 1; }
   // tables of the constructor, ORBextractor.cc:410-470 (scaleFactor member is double, ORBextractor.h:95)
   const int nl = params->nlevels;
