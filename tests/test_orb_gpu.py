@@ -110,6 +110,19 @@ def test_other_parameters_and_resize_of_handle():
         assert np.array_equal(kps, okps) and np.array_equal(desc, odesc), (w, h)
 
 
+@pytest.mark.parametrize("scale,nlevels", [(1.25, 6), (1.5, 5), (2.0, 4)])
+def test_scale_factors_pick_a_resize_tile_that_holds_the_source_rows(scale, nlevels):
+    """k_resize2's shared-memory tile holds a fixed number of source rows: 64 output rows fit up to scale 1.22, 32 up to 1.25,
+    16 up to 1.4, beyond that the handle falls back to the per-row kernel.  Every level byte and the result stay exact."""
+    w, h = 752, 480
+    img = synth.make_image(w, h, 31)
+    ext = ORBextractor(1200, scale, nlevels, 20, 7, max_width=w, max_height=h, max_batch=1)
+    oracle = po.OrbOracle(1200, scale, nlevels, 20, 7)
+    kps, desc = ext(img)
+    okps, odesc = _compare_frame(ext, oracle, img, 0, f"scale{scale}")
+    assert np.array_equal(kps, okps) and np.array_equal(desc, odesc)
+
+
 def test_empty_image_and_errors():
     ext = ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=1)
     kps, desc = ext(np.zeros((0, 0), np.uint8))
