@@ -626,7 +626,8 @@ __device__ void cam_finish(const BaDev& d, const LmState& st, int a) {
   d.part[d.o_cam_xn2 + a] = xn2;
 }
 
-__global__ void __launch_bounds__(kCamThreads) k_cam_blocks(BaDev d) { pdl_begin();
+// n_cam_ctas: CTAs of the launch that run this body (the ticket of the fused tail counts them)
+__device__ __forceinline__ void cam_blocks_body(const BaDev& d, int n_cam_ctas) {
   __shared__ double s_red[kCamThreads / 32][27];     // 108 doubles; reused as the 33-double scratch of the fused tail
   const LmState& st = *d.st;
   if (st.done || !st.need_lin) return;
@@ -662,7 +663,10 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_blocks(BaDev d) { pdl_begin
   __syncthreads();
   if (d.multi) return;
   if (tid == 0) cam_finish(d, st, a);
-  if (last_cta_arrives(d.ticket, gridDim.x)) post_lin_body(d, *d.st, 0, &s_red[0][0]);
+  if (last_cta_arrives(d.ticket, n_cam_ctas)) post_lin_body(d, *d.st, 0, &s_red[0][0]);
+}
+__global__ void __launch_bounds__(kCamThreads) k_cam_blocks(BaDev d) { pdl_begin();
+  cam_blocks_body(d, gridDim.x);
 }
 
 // Jacobi scale, gradient norm and parameter norm of one variable keyframe from its (global) H_cc, g_c
@@ -749,10 +753,9 @@ __global__ void __launch_bounds__(256) k_post_lin(BaDev d, int phase) { pdl_begi
   post_lin_body(d, st, phase, scratch);
 }
 
-__global__ void __launch_bounds__(kLinThreads) k_point_prep(BaDev d) { pdl_begin();
+__device__ __forceinline__ void point_prep_body(const BaDev& d, int j) {
   LmState& st = *d.st;
   if (st.done) return;
-  const int j = blockIdx.x * kLinThreads + threadIdx.x;
   if (j >= d.M) return;
   const double* H = d.Hpp + 6 * (size_t)j;
   const double s0 = d.scale_p[3 * (size_t)j], s1 = d.scale_p[3 * (size_t)j + 1], s2 = d.scale_p[3 * (size_t)j + 2];
@@ -776,6 +779,17 @@ __global__ void __launch_bounds__(kLinThreads) k_point_prep(BaDev d) { pdl_begin
   d.tp[3 * (size_t)j] = inv[0] * g0 + inv[1] * g1 + inv[2] * g2;
   d.tp[3 * (size_t)j + 1] = inv[1] * g0 + inv[3] * g1 + inv[4] * g2;
   d.tp[3 * (size_t)j + 2] = inv[2] * g0 + inv[4] * g1 + inv[5] * g2;
+}
+__global__ void __launch_bounds__(kLinThreads) k_point_prep(BaDev d) { pdl_begin();
+  point_prep_body(d, blockIdx.x * kLinThreads + threadIdx.x);
+}
+// Both consumers of a linearisation in ONE launch (single-GPU solves): CTAs [0, Kv) sum the camera blocks (the last of them runs
+// the reduce-and-decide tail), the CTAs behind them invert the damped point blocks.  The two parts read what k_linearize wrote
+// and the trust-region radius, which the tail does not touch; a point CTA that still sees done == 0 while the tail raises it
+// computes blocks nobody reads.  One launch less per LM iteration, and the 5 us of point work run beside the 13 us of camera work.
+__global__ void __launch_bounds__(kCamThreads) k_cam_blocks_prep(BaDev d) { pdl_begin();
+  if ((int)blockIdx.x < d.Kv) cam_blocks_body(d, d.Kv);
+  else point_prep_body(d, ((int)blockIdx.x - d.Kv) * kCamThreads + (int)threadIdx.x);
 }
 
 __device__ __forceinline__ void load_jc_scaled(const BaDev& d, int p, const double* sc, double* Jc) {
@@ -2542,9 +2556,11 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
     if (rc != 0) { set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString(rc)); return CMOS_ERR_CUDA; }
     return CMOS_OK;
   };
-  auto linearize = [&]() -> int {
+  const bool fuse_prep = !multi && d.Kv > 0 && getenv("CMOS_BA_NO_FUSED_PREP") == nullptr;
+  auto linearize = [&](bool with_prep) -> int {
     launch_chain(k_linearize, nlb, kLinThreads, 0, st, d);
-    if (d.Kv > 0) launch_chain(k_cam_blocks, d.Kv, kCamThreads, 0, st, d);
+    if (with_prep && fuse_prep) launch_chain(k_cam_blocks_prep, d.Kv + (d.M + kCamThreads - 1) / kCamThreads, kCamThreads, 0, st, d);
+    else if (d.Kv > 0) launch_chain(k_cam_blocks, d.Kv, kCamThreads, 0, st, d);
     h->launches += 2;
     if (!multi) {
       if (d.Kv == 0) { launch_chain(k_post_lin, 1, 256, 0, st, d, 0); h->launches++; }   // otherwise the last CTA of k_cam_blocks ran it
@@ -2565,9 +2581,11 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
   for (int it = 0; it < max_iterations; it++) {
     NvtxRange nvtx_it("cmos.ba.lm_iteration");
     int rc;
-    if ((rc = linearize())) return rc;
-    launch_chain(k_point_prep, (d.M + kLinThreads - 1) / kLinThreads, kLinThreads, 0, st, d);
-    h->launches++;
+    if ((rc = linearize(true))) return rc;
+    if (!fuse_prep) {
+      launch_chain(k_point_prep, (d.M + kLinThreads - 1) / kLinThreads, kLinThreads, 0, st, d);
+      h->launches++;
+    }
     if (d.Kv > 0) {
       if (h->schur_chunked) {
         launch_chain(k_schur_chunks, (d.n_chunks + kSchurWarps - 1) / kSchurWarps, 32 * kSchurWarps, 0, st, d);
@@ -2657,7 +2675,7 @@ int enqueue_solve(cmos_ba* h, int max_iterations, int pass, cudaStream_t st) {
   }
   if (max_iterations == 0) {   // Ceres still evaluates iteration 0
     int rc;
-    if ((rc = linearize())) return rc;
+    if ((rc = linearize(false))) return rc;
   }
   launch_chain(k_summary, 1, 1, 0, st, d, h->d_summaries + pass);
   h->launches++;

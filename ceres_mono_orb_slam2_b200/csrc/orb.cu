@@ -99,19 +99,26 @@ __global__ void __launch_bounds__(256) k_resize(OrbGeom g, int level, const shor
   const uint8_t* src = frame + S.plane_off + (long long)kBorder * S.pitch + kXOff;
   uint8_t* dst = frame + L.plane_off + c4 * 4;
   const int bx0 = c4 * 4 - kXOff;
-  if (bx0 >= 0 && bx0 + 3 < L.w) {
+  // fast path: interior word whose four source pairs start within bytes 0..7 of three aligned words (always the case up to
+  // scale 4/3; a wider group — scale 1.5, 2.0 — takes the generic path below)
+  bool fast = bx0 >= 0 && bx0 + 3 < L.w;
+  unsigned coef[4] = {0u, 0u, 0u, 0u}, sh[4] = {0u, 0u, 0u, 0u};
+  bool hi[4] = {false, false, false, false};
+  int wb = 0;
+  if (fast) {
     const int4 ta = __ldg((const int4*)(xtab + bx0)), tb = __ldg((const int4*)(xtab + bx0) + 1);
-    const unsigned coef[4] = {(unsigned)ta.x, (unsigned)ta.z, (unsigned)tb.x, (unsigned)tb.z};
+    coef[0] = (unsigned)ta.x; coef[1] = (unsigned)ta.z; coef[2] = (unsigned)tb.x; coef[3] = (unsigned)tb.z;
     const int sx[4] = {ta.y & 0xffff, ta.w & 0xffff, tb.y & 0xffff, tb.w & 0xffff};
-    const int wb = sx[0] >> 2;
-    bool hi[4];
-    unsigned sh[4];
+    wb = sx[0] >> 2;
+    if (sx[3] - 4 * wb > 7) fast = false;
 #pragma unroll
     for (int b = 0; b < 4; b++) {
-      const int o = sx[b] - 4 * wb;           // 0..8
+      const int o = sx[b] - 4 * wb;           // 0..7
       hi[b] = o >= 4;
       sh[b] = 8u * (unsigned)(o & 3);
     }
+  }
+  if (fast) {
 #pragma unroll
     for (int rr = 0; rr < kResizeRows; rr++) {
       const int row = row_first + rr;
@@ -1081,7 +1088,9 @@ struct cmos_orb {
   bool fast_small_cells = false;   // every cell of the current geometry fits the 48 x 48 tile (CMOS_FAST_LARGE_TILE=1 disables)
   int resize_rows = 2;      // CMOS_RESIZE_ROWS=1|2|4 output rows per thread of k_resize (tuning knob)
   bool resize_v2 = true;    // k_resize2 + k_borders (CMOS_RESIZE_V1=1 selects round 1's k_resize, A/B runs)
-  int resize_th = 64;       // output rows per k_resize2 tile (CMOS_RESIZE_TH=16|32|64)
+  int resize_th = 64;       // output rows per k_resize2 tile (CMOS_RESIZE_TH=16|32|64): the largest one wanted
+  int geo_resize_th = 0;    // ... and the largest one whose shared-memory tile holds the source rows of the current image size
+                            // (0: none, or a column group leaves the word window: round 1's k_resize with its generic path)
   bool has_result = false;
   StageTimer timer;
 };
@@ -1097,6 +1106,9 @@ struct GeomBuild {
   std::vector<short4> tab;
   std::vector<int> xoff, yoff;
   int oct_maxn = 0;
+  // what the resize kernels' fast paths assume, checked on the tables of THIS image size:
+  bool window_ok = true;              // every aligned group of four output columns reads source bytes 0..8 of its first word
+  int max_src_rows[3] = {0, 0, 0};    // source rows a k_resize2 tile of 16 / 32 / 64 output rows reads at most
 };
 
 bool build_geometry(const cmos_orb* h, int w, int ht, GeomBuild* out) {
@@ -1187,12 +1199,27 @@ bool build_geometry(const cmos_orb* h, int w, int ht, GeomBuild* out) {
         if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
         out->tab.push_back(make_short4((short)cv_round_f((1.f - fx) * 2048.f), (short)cv_round_f(fx * 2048.f), (short)sx, 0));
       }
+      // the word-window fast path (three aligned words, funnel shifts by 8 * (offset & 3) out of word pair 0 or 1) holds
+      // offsets 0..7 of the first tap: a group of four columns whose last tap starts further right needs the generic path
+      for (int x0 = 0; x0 < L.w; x0 += 4) {
+        const int s0 = out->tab[out->xoff[l] + x0].z, s3 = out->tab[out->xoff[l] + std::min(x0 + 3, L.w - 1)].z;
+        if (s3 - 4 * (s0 >> 2) > 7) out->window_ok = false;
+      }
       out->yoff[l] = (int)out->tab.size();
       for (int dy = 0; dy < L.h; dy++) {
         float fy = (float)((dy + 0.5) * scale_y - 0.5);
         int sy = (int)std::floor(fy);
         fy -= sy;
         out->tab.push_back(make_short4((short)sy, (short)cv_round_f((1.f - fy) * 2048.f), (short)cv_round_f(fy * 2048.f), 0));
+      }
+      for (int k = 0; k < 3; k++) {
+        const int th = 16 << k;
+        for (int r0 = 0; r0 < L.h; r0 += th) {
+          const int r1 = std::min(r0 + th, L.h) - 1;
+          const int y_lo = std::min(std::max((int)out->tab[out->yoff[l] + r0].x, 0), S.h - 1);
+          const int y_hi = std::min(std::max((int)out->tab[out->yoff[l] + r1].x + 1, 0), S.h - 1);
+          out->max_src_rows[k] = std::max(out->max_src_rows[k], y_hi - y_lo + 1);
+        }
       }
     }
   }
@@ -1236,6 +1263,10 @@ int ensure_geometry(cmos_orb* h, int w, int ht) {
   h->n_tiles = (int)gb.tiles.size();
   h->xtab_off = gb.xoff;
   h->ytab_off = gb.yoff;
+  h->geo_resize_th = 0;
+  if (gb.window_ok)
+    for (int k = 2; k >= 0; k--)
+      if ((16 << k) <= h->resize_th && gb.max_src_rows[k] <= rz_max_src_rows(16 << k)) { h->geo_resize_th = 16 << k; break; }
   h->oct_maxn = gb.oct_maxn;
   h->cur_w = w;
   h->cur_h = ht;
@@ -1257,10 +1288,10 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
     k_level0<<<grid, blk, 0, st>>>(g, d_images, frame_stride, pitch, h->d_pyr);
     launches++;
   }
-  if (h->resize_v2) {
+  if (h->resize_v2 && h->geo_resize_th > 0) {
     for (int l = 1; l < g.nlevels; l++) {
       const LevelGeom& L = g.lv[l];
-      const int th = h->resize_th;
+      const int th = h->geo_resize_th;
       dim3 grid((L.w + kRzTW - 1) / kRzTW, (L.h + th - 1) / th, n_frames);
       if (th == 64) k_resize2<64><<<grid, 256, 0, st>>>(g, l, h->d_tab + h->xtab_off[l], h->d_tab + h->ytab_off[l], h->d_pyr);
       else if (th == 32) k_resize2<32><<<grid, 256, 0, st>>>(g, l, h->d_tab + h->xtab_off[l], h->d_tab + h->ytab_off[l], h->d_pyr);
@@ -1351,9 +1382,6 @@ int cmos_orb_create(const cmos_orb_params* params, cmos_orb_t* out) {
   if (const char* e = std::getenv("CMOS_FAST_THREADS")) h->fast_threads = std::atoi(e) == 256 ? 256 : 128;
   if (const char* e = std::getenv("CMOS_RESIZE_V1")) h->resize_v2 = !(e[0] == '1');
   if (const char* e = std::getenv("CMOS_RESIZE_TH")) { int t = std::atoi(e); h->resize_th = t == 16 ? 16 : t == 32 ? 32 : 64; }
-  // a tile of th output rows reads (th - 1) * scale + 3 source rows at most; the shared-memory tile holds rz_max_src_rows(th)
-  while (h->resize_th > 16 && (h->resize_th - 1) * (double)params->scale_factor + 3 > rz_max_src_rows(h->resize_th)) h->resize_th /= 2;
-  if ((h->resize_th - 1) * (double)params->scale_factor + 3 > rz_max_src_rows(h->resize_th)) h->resize_v2 = false;
   if (const char* e = std::getenv("CMOS_RESIZE_ROWS")) { int r = std::atoi(e); h->resize_rows = r == 2 ? 2 : r == 4 ? 4 : 1; }
   // tables of the constructor, ORBextractor.cc:410-470 (scaleFactor member is double, ORBextractor.h:95)
   const int nl = params->nlevels;
