@@ -1084,7 +1084,9 @@ struct cmos_orb {
   std::vector<int> xtab_off, ytab_off;
   size_t images_cap = 0;
   int last_frames = 0, launches = 0;
-  int fast_threads = 128;   // CMOS_FAST_THREADS=256 selects the wider CTA (tuning knob)
+  int fast_threads = 128;   // CMOS_FAST_THREADS=256 / 64 select other CTA widths (tuning knob).  64 threads (two warps share a cell's
+                            // fixed cost instead of four): k_fast alone 0.252 -> 0.236 ms, but the overlapped step gets slower
+                            // (155.8 -> 153.8 Mfeat/s, end to end 148.5 -> 141.1): 23 resident CTAs per SM crowd out the other streams' kernels
   bool fast_small_cells = false;   // every cell of the current geometry fits the 48 x 48 tile (CMOS_FAST_LARGE_TILE=1 disables)
   int resize_rows = 2;      // CMOS_RESIZE_ROWS=1|2|4 output rows per thread of k_resize (tuning knob)
   bool resize_v2 = true;    // k_resize2 + k_borders (CMOS_RESIZE_V1=1 selects round 1's k_resize, A/B runs)
@@ -1321,7 +1323,8 @@ int enqueue_extract(cmos_orb* h, const uint8_t* d_images, long long frame_stride
 #define CMOS_FAST_LAUNCH(T, TW, TH, CAP) \
   k_fast<T, TW, TH, CAP><<<fg, T, 0, st>>>(g, h->d_cells, h->d_pyr, h->d_cand, h->d_cand_count, h->d_overflow, h->d_dbg, h->dbg_cell)
     const bool small = h->fast_small_cells && h->dbg_cell < 0;      // the debug dump has the large tile's layout
-    if (h->fast_threads == 128) { if (small) CMOS_FAST_LAUNCH(128, kSmallTileW, kSmallTileH, kSmallListCap); else CMOS_FAST_LAUNCH(128, kTileW, kTileH, kCellListCap); }
+    if (h->fast_threads == 64 && small) CMOS_FAST_LAUNCH(64, kSmallTileW, kSmallTileH, kSmallListCap);
+    else if (h->fast_threads <= 128) { if (small) CMOS_FAST_LAUNCH(128, kSmallTileW, kSmallTileH, kSmallListCap); else CMOS_FAST_LAUNCH(128, kTileW, kTileH, kCellListCap); }
     else { if (small) CMOS_FAST_LAUNCH(256, kSmallTileW, kSmallTileH, kSmallListCap); else CMOS_FAST_LAUNCH(256, kTileW, kTileH, kCellListCap); }
 #undef CMOS_FAST_LAUNCH
     launches++;
@@ -1379,7 +1382,7 @@ int cmos_orb_create(const cmos_orb_params* params, cmos_orb_t* out) {
   cmos_orb* h = new cmos_orb();
   h->p = *params;
   h->device = params->device;
-  if (const char* e = std::getenv("CMOS_FAST_THREADS")) h->fast_threads = std::atoi(e) == 256 ? 256 : 128;
+  if (const char* e = std::getenv("CMOS_FAST_THREADS")) h->fast_threads = std::atoi(e) == 256 ? 256 : std::atoi(e) == 64 ? 64 : 128;
   if (const char* e = std::getenv("CMOS_RESIZE_V1")) h->resize_v2 = !(e[0] == '1');
   if (const char* e = std::getenv("CMOS_RESIZE_TH")) { int t = std::atoi(e); h->resize_th = t == 16 ? 16 : t == 32 ? 32 : 64; }
   if (const char* e = std::getenv("CMOS_RESIZE_ROWS")) { int r = std::atoi(e); h->resize_rows = r == 2 ? 2 : r == 4 ? 4 : 1; }
