@@ -390,6 +390,29 @@ def e2e_block(forms, d2h, call, extra):
     return blk
 
 
+def pin_to_gpu_numa(nvml_index: int):
+    """Several ranks behind one host: keep this rank's threads — and with them the page-locked buffers it allocates (first
+    touch) — on the CPUs NVML lists as local to its GPU, so uploads do not cross the socket interconnect.  Returns a note for
+    the JSON line; does nothing when NVML or the affinity call is unavailable or the mask would be empty."""
+    if os.environ.get("CMOS_BENCH_NO_AFFINITY"):
+        return "off (CMOS_BENCH_NO_AFFINITY)"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(nvml_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(ncpu, 1024) + 63) // 64)
+        local = {64 * wi + b for wi, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        want = local & allowed
+        if not want or want == allowed:
+            return f"unchanged ({len(allowed)} cpus allowed, {len(local)} local to the GPU)"
+        os.sched_setaffinity(0, want)
+        return f"{len(want)} of {len(allowed)} allowed cpus (NVML: local to GPU {nvml_index})"
+    except Exception as e:      # noqa: BLE001
+        return f"unchanged ({type(e).__name__})"
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -401,6 +424,9 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")
+    nvml_index = int(vis[local_rank]) if local_rank < len(vis) and vis[local_rank].strip().isdigit() else local_rank
+    affinity_note = pin_to_gpu_numa(nvml_index) if world > 1 else "not applied (one rank)"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -519,8 +545,6 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")
-    nvml_index = int(vis[local_rank]) if local_rank < len(vis) and vis[local_rank].strip().isdigit() else local_rank
     sampler = ClockSampler(nvml_index)
     sampler.start()
 
@@ -693,6 +717,7 @@ def run_b200(args):
                        "l2": "no explicit flush: one step touches ~%d MB (images + pyramid + blurred pyramid) > 126 MB L2"
                              % ((B * (H * W) + 2 * B * 1738559) // 1000000),
                        "parallelism": f"frames sharded, {world} rank(s), no collective on the data path",
+                       "cpu_affinity_rank0": affinity_note,
                        "sub_batches": (f"each step = {S} sub-batch(es) of {B // S} frames on own CUDA streams, consecutive steps on {D} "
                                        f"independent buffer set(s) ({S * D} streams in all): the per-frame latency-bound kernels of "
                                        f"one run under the heavy kernels of another") if S * D > 1 else "none (one stream)"},

@@ -15,7 +15,7 @@ for f in funcs[1:]:
     name = f.split("\n", 1)[0].strip()
     dem = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip().split("(")[0]
     dem = dem.replace("void ", "").replace("cmos::", "")
-    c = {k: len(re.findall(r"\b" + k + r"\b", f)) for k in ("DMMA", "UBLKCP", "UTMALDG", "DFMA", "IDP")}
+    c = {k: len(re.findall(r"\b" + k + r"\b", f)) for k in ("DMMA", "UBLKCP", "UTMALDG", "DFMA", "IDP", "PREEXIT", "ACQBULK")}
     c["UTC"] = len(re.findall(r"UTC\w*MMA", f)); c["LDTM"] = len(re.findall(r"\bLDTM\b|\bSTTM\b", f))
     for k, v in c.items():
         tot[k] += v
@@ -35,6 +35,8 @@ with open(os.path.join(ROOT, "profiles", "r2_sass_instruction_table.md"), "w") a
             "(`r1_tma_tensor_map_illegal_instruction_sanitizer.log`) |\n" % tot["UTMALDG"])
     o.write("| `UTC*MMA` / `LDTM` / `STTM` | %d / %d | tcgen05 MMA / TMEM: not used — the only GEMM-shaped work is fp64 (1e-4 parity "
             "bar), which tcgen05 does not do |\n" % (tot["UTC"], tot["LDTM"]))
+    o.write("| `PREEXIT` / `ACQBULK` | %d / %d | programmatic dependent launch (`griddepcontrol.launch_dependents` / `.wait`): first two "
+            "instructions of every bundle-adjustment / pose-graph kernel (`pdl_begin`, `ba_device.cuh`) |\n" % (tot["PREEXIT"], tot["ACQBULK"]))
     o.write("| `DFMA` | %d | scalar fp64 FMA |\n| `IDP` | %d | integer dot product (`DP2A`/`DP4A`: pyramid, blur) |\n\n" % (tot["DFMA"], tot["IDP"]))
     o.write("Kernels with tensor-core or TMA instructions:\n\n| kernel | DMMA | UBLKCP |\n|---|---|---|\n")
     for dem, c in sorted(rows, key=lambda r: -r[1]["DMMA"]):
