@@ -3,9 +3,12 @@
 // What the reference does per frame on the Tracking thread (GrabImageMonocular -> Frame::Frame, src/Frame.cc:98-156:
 // ExtractORB :116 -> ORBextractor::operator() :175-177, AssignFeaturesToGrid :155; then TrackWithMotionModel ->
 // ORBmatcher::SearchByProjection(current_frame_, last_frame_, th), src/Tracking.cc:632, src/ORBmatcher.cc:1161-1271) is one call here for a
-// batch of frames with HOST buffers.  The batch is cut into chunks; chunk c runs on lane c % lanes (one stream,
-// one extractor handle, one matcher handle per lane), so the host->device copy of chunk c+1, the kernels of chunk c
-// and the device->host copy of chunk c-1 overlap.  Only public entry points of the same C ABI are used.
+// batch of frames with HOST buffers.  The batch is cut into chunks that are dealt round-robin — across batches — to the lanes
+// (one compute stream + one upload stream, one extractor handle, one matcher handle per lane), so the host->device copies of
+// one chunk, the kernels of another and the device->host copy of a third overlap; cmos_track_submit / cmos_track_wait keep up
+// to four batches in flight, which is what keeps the copy engine busy between batches.  The last-frame inputs come in three
+// forms with identical results: per-keypoint arrays, packed 64-byte records, or 12-byte association records into a
+// device-resident map-point table (cmos_track_map_reserve / _update).  Only public entry points of the same C ABI are used.
 #include <cuda_runtime.h>
 
 #include <algorithm>
