@@ -34,6 +34,26 @@ flags[0, :n0] = fl; X[0, :n0] = xw; D[0, :n0] = md
 m = ORBmatcher(0.9, True, max_batch=1, max_keypoints=cap)
 m.set_frames(cam, kps[1:2], desc[1:2], counts[1:2], 1, cap)
 match, nm = m.SearchByProjectionFrame(np.eye(4).reshape(1, 16), kps[0:1], counts[0:1], flags, X, D, cap, 15.0)
+# the stream-pipelined front end, all three forms of the last-frame inputs (two lanes, one frame per chunk, two batches in flight)
+from ceres_mono_orb_slam2_b200 import KP_DTYPE, TrackingFrontEnd
+from ceres_mono_orb_slam2_b200.tracking import pack_last_points, pack_map_associations
+fe = TrackingFrontEnd(cam, 300, 1.2, 8, 20, 7, max_width=W, max_height=H, lanes=2, chunk_frames=1)
+T2 = np.tile(np.eye(4).reshape(1, 16), (2, 1))
+lk2 = np.stack([kps[0], kps[0]]); lc2 = np.array([n0, n0], np.int32)
+fl2_ = np.concatenate([flags, flags]); X2 = np.concatenate([X, X]); D2 = np.concatenate([D, D])
+mk = lambda: (np.zeros((2, cap), KP_DTYPE), np.zeros((2, cap, 32), np.uint8), np.zeros(2, np.int32), np.full((2, cap), -1, np.int32), np.zeros(2, np.int32))
+oa, ob, oc = mk(), mk(), mk()
+ta = fe.submit(frames, T2, lk2, lc2, fl2_, X2, D2, 15.0, out=oa)
+pts, pstart = pack_last_points(lk2, lc2, fl2_, X2, D2)
+tb = fe.submit_points(frames, T2, pts, pstart, 15.0, out=ob)
+fe.wait(ta); fe.wait(tb)
+slots = np.full((2, cap), -1, np.int32); us = np.argwhere(fl2_ & 1); slots[us[:, 0], us[:, 1]] = np.arange(len(us), dtype=np.int32)
+fe.map_reserve(len(us)); fe.map_update(X2[us[:, 0], us[:, 1]][: len(us) // 2], D2[us[:, 0], us[:, 1]][: len(us) // 2])
+rest = np.arange(len(us) // 2, len(us), dtype=np.int32)
+fe.map_update(X2[us[rest, 0], us[rest, 1]], D2[us[rest, 0], us[rest, 1]], slots=rest)
+assoc, astart = pack_map_associations(lk2, lc2, fl2_, slots)
+fe.wait(fe.submit_map(frames, T2, assoc, astart, 15.0, out=oc))
+assert np.array_equal(oa[3], ob[3]) and np.array_equal(oa[3], oc[3]) and int(oa[4][1]) == int(nm[0])
 K4 = np.array(synth.KITTI_K, np.float32)
 G = synth.make_ba_problem(6, 120, 4, seed=11, n_fixed_extra=2)
 fl2 = G["fixed"].copy(); fl2[6:] |= 2
