@@ -123,6 +123,29 @@ def test_scale_factors_pick_a_resize_tile_that_holds_the_source_rows(scale, nlev
     assert np.array_equal(kps, okps) and np.array_equal(desc, odesc)
 
 
+@pytest.mark.parametrize("w,h,nfeat,scale,nlevels,ini,mn", [
+    (160, 120, 200, 1.2, 4, 20, 7),        # tiny image
+    (641, 479, 1000, 1.2, 8, 20, 7),       # odd sizes: every level has partial words / partial cells
+    (1920, 1080, 3000, 1.2, 8, 20, 7),     # large cells (the general FAST tile), 3 x the KITTI pixel count
+    (640, 480, 5000, 1.2, 8, 12, 5),       # more features asked for than most levels can give
+    (640, 480, 50, 1.2, 8, 20, 7),         # quotas of one to a dozen keypoints per level
+    (640, 480, 1000, 1.2, 1, 20, 7),       # a single level: no resize at all
+    (752, 480, 1000, 1.1, 8, 20, 7),       # fine pyramid
+    (640, 480, 1000, 1.2, 8, 7, 7),        # iniThFAST == minThFAST: the fallback pass repeats the first one
+    (320, 240, 1000, 1.2, 12, 20, 7),      # twelve levels, the last one 43 x 32
+])
+def test_parameter_sweep_bit_exact(w, h, nfeat, scale, nlevels, ini, mn):
+    """Unusual but legal parameter sets (the reference reads all of them from the settings file, ORBextractor.cc:410-470): every
+    pyramid byte, FAST candidate, blurred byte, keypoint and descriptor bit equals the oracle."""
+    img = synth.make_image(w, h, 77 + w + nlevels)
+    ext = ORBextractor(nfeat, scale, nlevels, ini, mn, max_width=w, max_height=h, max_batch=1)
+    oracle = po.OrbOracle(nfeat, scale, nlevels, ini, mn)
+    assert np.array_equal(ext.features_per_level, oracle.quota)
+    kps, desc = ext(img)
+    okps, odesc = _compare_frame(ext, oracle, img, 0, f"sweep{w}x{h}_{nfeat}_{scale}_{nlevels}_{ini}_{mn}")
+    assert len(kps) == len(okps) and np.array_equal(kps, okps) and np.array_equal(desc, odesc)
+
+
 def test_empty_image_and_errors():
     ext = ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=1)
     kps, desc = ext(np.zeros((0, 0), np.uint8))
