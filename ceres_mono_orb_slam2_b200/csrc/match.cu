@@ -173,6 +173,25 @@ __global__ void __launch_bounds__(kSfWarps * 32) k_sf_lists(
   const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = blockIdx.x * kSfWarps + warp;
   const int nq = min(a.last_counts[f], a.last_stride);
+  // The projection and the cell window of a query are scalar work (fp64 pose product, a division, four floor / ceil): done by
+  // its warp they cost a full warp instruction each, ~190 per query.  Thread t of the CTA does them for query t of the CTA's
+  // eight instead — one warp's worth of issue slots for all eight — and hands {u, v, radius, window} over in shared memory.
+  __shared__ float4 s_uvr[kSfWarps];     // u, v, radius, (min_cx | max_cx << 8 | min_cy << 16 | max_cy << 24) or -1: no window
+  if (threadIdx.x < kSfWarps) {
+    const int qq = blockIdx.x * kSfWarps + threadIdx.x;
+    float4 o = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    if (qq < nq && (a.last_flags[(long long)f * a.last_stride + qq] & 1)) {
+      const int oct = a.last_kps[(long long)f * a.last_stride + qq].octave;
+      const QueryFrame Q = project_last(cam, a.Tcw + (long long)f * 16, a.last_xw + ((long long)f * a.last_stride + qq) * 3, oct);
+      if (Q.ok) {
+        const float radius = a.th * cam.scale_factors[oct];
+        const Window w = make_window(cam, Q.u, Q.v, radius);
+        if (w.ok) o = make_float4(Q.u, Q.v, radius, __int_as_float(w.min_cx | (w.max_cx << 8) | (w.min_cy << 16) | (w.max_cy << 24)));
+      }
+    }
+    s_uvr[threadIdx.x] = o;
+  }
+  __syncthreads();
   if (q >= nq) return;
   const int n = min(counts[f], stride);
   FrameDev F{kps + (long long)f * stride, desc + (long long)f * stride * 32,
@@ -186,10 +205,12 @@ __global__ void __launch_bounds__(kSfWarps * 32) k_sf_lists(
   int tidx = 0, total = 0;
   if (flag & 1) {
     const int oct = last[q].octave;
-    QueryFrame Q = project_last(cam, a.Tcw + (long long)f * 16, a.last_xw + ((long long)f * a.last_stride + q) * 3, oct);
-    if (Q.ok) {
-      const float radius = a.th * cam.scale_factors[oct];
-      const Window w = make_window(cam, Q.u, Q.v, radius);
+    const float4 uvr = s_uvr[warp];
+    const int wbits = __float_as_int(uvr.w);
+    {
+      struct { float u, v; } Q{uvr.x, uvr.y};
+      const float radius = uvr.z;
+      const Window w{wbits & 0xff, (wbits >> 8) & 0xff, (wbits >> 16) & 0xff, (wbits >> 24) & 0xff, wbits >= 0};
       if (w.ok) {
         uint32_t dq[8];
         const uint32_t* dsrc = (const uint32_t*)(a.last_desc + ((long long)f * a.last_stride + q) * 32);
