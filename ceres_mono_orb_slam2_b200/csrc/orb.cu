@@ -970,6 +970,9 @@ __global__ void __launch_bounds__(kDescThreads) k_describe(
     m10 += __shfl_xor_sync(0xffffffffu, m10, o);
     m01 += __shfl_xor_sync(0xffffffffu, m01, o);
   }
+  // (measured and dropped: handing the moments over in shared memory so that ONE thread per keypoint computes angle, cosine and
+  // sine for the CTA's eight keypoints — the scheme that took a quarter off k_sf_lists — costs two CTA barriers here and made
+  // this kernel slower, 0.149 -> 0.159 ms: its warps wait on L2 gathers, and the barriers tie eight of them together)
   const float angle = dev_fast_atan2((float)m01, (float)m10);
 
   // steered BRIEF: lane = descriptor byte
