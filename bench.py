@@ -706,6 +706,25 @@ def run_b200(args):
             single["pyramid"] = "k_pyramid"
         big = max((k for k in stage_avg if k in single), key=lambda k: stage_avg[k])
         big_ach = alg[big] * B / (stage_avg[big] * 1e-3) / 1e9 if stage_avg[big] > 0 else 0.0
+        # The path is instruction-issue bound (DRAM <= 18 % everywhere): beside the HBM roofline the contract asks for, report the
+        # step against the issue peak — warp instructions of one step (ncu smsp__inst_executed.sum, stored with the traffic
+        # capture and valid under the same source hash) / (SMs x 4 schedulers x SM clock).
+        issue = None
+        try:
+            wi = (traffic_all or {}).get("_warp_instructions")
+            if wi:
+                props = torch.cuda.get_device_properties(dev)
+                clk_mhz = float(clocks.get("sm_mhz") or 0.0) if isinstance(clocks, dict) else 0.0
+                if clk_mhz > 0:
+                    peak_wi = props.multi_processor_count * 4 * clk_mhz * 1e6          # warp instructions per second
+                    tot_wi = float(sum(wi.values()))
+                    issue = {"warp_instructions_per_step": tot_wi, "per_stage": wi,
+                             "peak_warp_instructions_per_s": peak_wi, "sm_count": props.multi_processor_count,
+                             "achieved_per_s": tot_wi / (step_ms * 1e-3), "frac": tot_wi / (step_ms * 1e-3) / peak_wi,
+                             "single_stream_frac": tot_wi / (single_step_ms * 1e-3) / peak_wi,
+                             "source": "profiles/traffic.json _warp_instructions (same capture and source hash as `traffic`)"}
+        except Exception as ex:      # noqa: BLE001 — an auxiliary figure must never cost the bench line
+            issue = {"unavailable": type(ex).__name__}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -730,6 +749,7 @@ def run_b200(args):
                                                    "algorithmic_bytes_per_launch": alg[big] * B, "achieved": big_ach,
                                                    "frac": big_ach / peak,
                                                    "traffic": traffic_all.get(big) if traffic_all else None},
+                         "issue_bound": issue,
                          "algorithmic_bytes_per_launch": alg[dom] * B, "kernel_ms": dom_ms,
                          "stage_ms": stage_avg, "stage_share": {k: v / single_step_ms for k, v in stage_avg.items()},
                          "whole_step": {"algorithmic_bytes": alg["frame_total"] * B,
