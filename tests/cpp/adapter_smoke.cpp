@@ -7,6 +7,7 @@
 #include "../../include/orb_slam2/CeresOptimizer.h"
 #include "../../include/orb_slam2/ORBextractor.h"
 #include "../../include/orb_slam2/ORBmatcher.h"
+#include "../../include/orb_slam2/TrackingFrontEnd.h"
 
 using namespace ORB_SLAM2;
 
@@ -157,6 +158,62 @@ int main() {
       // (the scale column of the reference's Jacobian is analytically zero, quirk Q7: if a step is accepted at this ~1e-9
       // cost the scale moves by rounding noise, so the check is a band, not an equality)
       if (inl < n - 2 || bad > 2 || std::fabs(S12.s - 1.0) > 0.05 || std::fabs(S12.t[0] - 1.0) > 0.05) return 9;
+    }
+    {
+      // The batched front end: two copies of the frame as one batch, last frame = the frame itself.  The three forms of the
+      // last-frame inputs (arrays, packed records, association records into the device-resident map-point table) must agree
+      // with each other and with the per-frame matcher call above.
+      TrackingFrontEnd fe(F.camera, 1000, 1.2f, 8, 20, 7, W, H, /*lanes=*/2, /*chunk_frames=*/1);
+      const int B = 2, cap = fe.capacity(), N = (int)kps.size();
+      std::vector<uint8_t> imgs((size_t)B * W * H);
+      std::vector<double> T((size_t)B * 16, 0.0);
+      std::vector<KeyPoint> lk((size_t)B * cap);
+      std::vector<int32_t> lc(B, N), start(1, 0);
+      std::vector<uint8_t> lf((size_t)B * cap, 0), ld((size_t)B * cap * 32, 0);
+      std::vector<double> lx((size_t)B * cap * 3, 0.0);
+      std::vector<cmos_last_point> pts;
+      std::vector<cmos_track_assoc> as;
+      for (int f = 0; f < B; f++) {
+        std::copy(img.begin(), img.end(), imgs.begin() + (size_t)f * W * H);
+        for (int i = 0; i < 4; i++) T[(size_t)f * 16 + 5 * i] = 1.0;
+        std::copy(kps.begin(), kps.end(), lk.begin() + (size_t)f * cap);
+        std::copy(flags.begin(), flags.end(), lf.begin() + (size_t)f * cap);
+        std::copy(X.begin(), X.end(), lx.begin() + (size_t)f * cap * 3);
+        std::copy(desc.data.begin(), desc.data.begin() + (size_t)N * 32, ld.begin() + (size_t)f * cap * 32);
+        for (int i = 0; i < N; i++) {
+          cmos_last_point r;
+          std::copy(desc.data.begin() + (size_t)i * 32, desc.data.begin() + (size_t)(i + 1) * 32, r.descriptor);
+          for (int k = 0; k < 3; k++) r.xw[k] = X[3 * (size_t)i + k];
+          r.angle = kps[i].angle; r.index = (uint16_t)i; r.octave = (int8_t)kps[i].octave; r.flags = flags[i];
+          pts.push_back(r);
+          const cmos_track_assoc a = {(int32_t)i, kps[i].angle, (uint16_t)i, (int8_t)kps[i].octave, flags[i]};   // slot = keypoint index
+          as.push_back(a);
+        }
+        start.push_back((int32_t)pts.size());
+      }
+      struct Out {
+        std::vector<KeyPoint> k; std::vector<uint8_t> d; std::vector<int32_t> c, m, n;
+        Out(int B, int cap) : k((size_t)B * cap), d((size_t)B * cap * 32), c(B), m((size_t)B * cap, -1), n(B) {}
+      };
+      Out o0(B, cap), o1(B, cap), o2(B, cap);
+      auto batch = [&](Out& o) {
+        TrackingFrontEnd::Batch b;
+        b.images = imgs.data(); b.frame_stride = (int64_t)W * H; b.pitch = W; b.width = W; b.height = H; b.n_frames = B;
+        b.Tcw = T.data(); b.keypoints = o.k.data(); b.descriptors = o.d.data(); b.counts = o.c.data(); b.capacity = cap;
+        b.match = o.m.data(); b.nmatches = o.n.data();
+        return b;
+      };
+      const int64_t t0 = fe.Submit(batch(o0), lk.data(), lc.data(), lf.data(), lx.data(), ld.data(), cap, 15.f);
+      const int64_t t1 = fe.SubmitPoints(batch(o1), pts.data(), start.data(), 15.f);      // two batches in flight
+      fe.Wait(t0); fe.Wait(t1);
+      fe.ReserveMapPoints(N);
+      fe.UpdateMapPointRange(0, N, X.data(), desc.data.data());
+      fe.Wait(fe.SubmitMap(batch(o2), as.data(), start.data(), 15.f));
+      std::printf("TrackingFrontEnd: %d + %d matches (arrays), %d + %d (records), %d + %d (map-point table)\n", o0.n[0], o0.n[1],
+                  o1.n[0], o1.n[1], o2.n[0], o2.n[1]);
+      for (int f = 0; f < B; f++)
+        if (o0.c[f] != N || o0.n[f] != nm || o1.n[f] != nm || o2.n[f] != nm) return 11;
+      if (o0.m != o1.m || o0.m != o2.m) return 12;
     }
     CeresOptimizer::release();
     std::printf("ADAPTERS_OK\n");
