@@ -400,14 +400,21 @@ int cmos_track_map_reserve(cmos_track_t h, int32_t n_slots) {
   if (n_slots <= h->map_slots) return CMOS_OK;
   int rc = map_quiesce(h);
   if (rc) return rc;
+  // on the first lane's stream (idle after the quiesce) and waited for there: a cudaMemset on the legacy stream is asynchronous
+  // and NOT ordered with the lanes' non-blocking streams, which read and update the table
+  cudaStream_t st = h->lanes[0].st;
   cudaError_t err = cudaSuccess;
   double* xw = dev_alloc<double>((size_t)n_slots * 3, &err);
   uint8_t* desc = dev_alloc<uint8_t>((size_t)n_slots * 32, &err);
-  if (err == cudaSuccess) err = cudaMemset(xw, 0, (size_t)n_slots * 3 * sizeof(double));
-  if (err == cudaSuccess) err = cudaMemset(desc, 0, (size_t)n_slots * 32);
+  if (err == cudaSuccess) err = cudaMemsetAsync(xw, 0, (size_t)n_slots * 3 * sizeof(double), st);
+  if (err == cudaSuccess) err = cudaMemsetAsync(desc, 0, (size_t)n_slots * 32, st);
   if (err == cudaSuccess && h->map_slots > 0) {     // growing keeps the slots already written
-    err = cudaMemcpy(xw, h->d_map_xw, (size_t)h->map_slots * 3 * sizeof(double), cudaMemcpyDeviceToDevice);
-    if (err == cudaSuccess) err = cudaMemcpy(desc, h->d_map_desc, (size_t)h->map_slots * 32, cudaMemcpyDeviceToDevice);
+    err = cudaMemcpyAsync(xw, h->d_map_xw, (size_t)h->map_slots * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(desc, h->d_map_desc, (size_t)h->map_slots * 32, cudaMemcpyDeviceToDevice, st);
+  }
+  {
+    const cudaError_t e2 = cudaStreamSynchronize(st);
+    if (err == cudaSuccess) err = e2;
   }
   if (err != cudaSuccess) {
     if (xw) cudaFree(xw);
@@ -436,22 +443,29 @@ int cmos_track_map_update(cmos_track_t h, int32_t n, const int32_t* slots, int32
   }
   int rc = map_quiesce(h);
   if (rc) return rc;
+  // everything below runs on the first lane's stream (idle after the quiesce) and is waited for there: no device-wide
+  // synchronisation and no legacy-stream copy, so an optimiser thread working on its own stream is not stalled by a map update
+  cudaStream_t st = h->lanes[0].st;
   if (!slots) {     // a run of consecutive slots: two plain copies
-    CMOS_CUDA_OK(cudaMemcpy(h->d_map_xw + 3 * (size_t)first_slot, xw, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
-    CMOS_CUDA_OK(cudaMemcpy(h->d_map_desc + 32 * (size_t)first_slot, descriptors, (size_t)n * 32, cudaMemcpyHostToDevice));
+    CMOS_CUDA_OK(cudaMemcpyAsync(h->d_map_xw + 3 * (size_t)first_slot, xw, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CMOS_CUDA_OK(cudaMemcpyAsync(h->d_map_desc + 32 * (size_t)first_slot, descriptors, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    CMOS_CUDA_OK(cudaStreamSynchronize(st));
     return CMOS_OK;
   }
   cudaError_t err = cudaSuccess;
   int* d_slots = dev_alloc<int>((size_t)n, &err);
   double* d_xw = dev_alloc<double>((size_t)n * 3, &err);
   uint8_t* d_desc = dev_alloc<uint8_t>((size_t)n * 32, &err);
-  if (err == cudaSuccess) err = cudaMemcpy(d_slots, slots, (size_t)n * sizeof(int), cudaMemcpyHostToDevice);
-  if (err == cudaSuccess) err = cudaMemcpy(d_xw, xw, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice);
-  if (err == cudaSuccess) err = cudaMemcpy(d_desc, descriptors, (size_t)n * 32, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(d_slots, slots, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(d_xw, xw, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(d_desc, descriptors, (size_t)n * 32, cudaMemcpyHostToDevice, st);
   if (err == cudaSuccess) {
-    k_map_scatter<<<(n + 255) / 256, 256>>>(d_slots, d_xw, d_desc, n, h->map_slots, h->d_map_xw, h->d_map_desc);
+    k_map_scatter<<<(n + 255) / 256, 256, 0, st>>>(d_slots, d_xw, d_desc, n, h->map_slots, h->d_map_xw, h->d_map_desc);
     err = cudaGetLastError();
-    if (err == cudaSuccess) err = cudaDeviceSynchronize();
+  }
+  {
+    const cudaError_t e2 = cudaStreamSynchronize(st);      // also before the frees below when something failed
+    if (err == cudaSuccess) err = e2;
   }
   if (d_slots) cudaFree(d_slots);
   if (d_xw) cudaFree(d_xw);
