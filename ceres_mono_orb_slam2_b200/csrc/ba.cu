@@ -2746,6 +2746,8 @@ int cmos_ba_create(const cmos_ba_params* params, cmos_ba_t* out) {
   cudaFuncSetAttribute(k_syrk_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
   cudaFuncSetAttribute(k_backsolve_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)back_all_smem(kBackAllMaxN));
   CMOS_CUDA_OK(cudaMemset(h->d_red, 0, 16 * sizeof(double)));      // incl. the arrival tickets
+  // cudaMemset runs asynchronously on the legacy stream, which is NOT ordered with the handle's non-blocking stream
+  CMOS_CUDA_OK(cudaDeviceSynchronize());
   CMOS_CUDA_OK(cudaGetLastError());
   *out = h;
   return CMOS_OK;

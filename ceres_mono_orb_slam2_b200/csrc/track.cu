@@ -205,6 +205,9 @@ int cmos_track_create(const cmos_track_params* params, const cmos_camera* cam, c
       if (!rc && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = CMOS_ERR_CUDA;
   }
   if (rc) { cmos_track_destroy(h); return rc; }
+  // the lanes' extractor handles clear their buffers with cudaMemset at creation: asynchronous on the legacy stream, which is
+  // not ordered with the lanes' non-blocking streams — wait once here
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("cudaDeviceSynchronize failed"); cmos_track_destroy(h); return CMOS_ERR_CUDA; }
   *out = h;
   return CMOS_OK;
 }
